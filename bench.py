@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""Headline benchmark: full-rank evaluation throughput of the NAIS region/distance scorer (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision tc_split|tc_fast|fp32]
+    torchrun --nproc-per-node N ... bench.py --gpus N ...        (one rank per GPU, NCCL)
+
+One *step* = one fused full-rank pass (scoring + top-k) of a batch of `--users-per-step` users against the whole
+synthetic catalogue of the workload:
+
+    C2 (default)  Gowalla-shaped: 30,000 users x 40,000 POIs, history 128, D = hid = 64, top-20   [BASELINE configs[1]]
+    C4            Yelp-scale:     100,000 users x 1,000,000 POIs, history 128, D = hid = 64, top-20
+
+Successive steps take successive user batches (wrapping around).  With N > 1 GPUs the catalogue is range-sharded
+across ranks, every rank scores the same user batch against its shard, the per-shard top-k lists are all-gathered
+over NCCL and merged on device (north_star); total work per step is fixed -> "scaling": "strong".
+
+value   users/s with inputs resident in HBM (pair-scores/s = users/s x POIs is reported alongside)
+e2e     the same metric through the drop-in API (`model.predict_topk` on host CSR arrays): pinned host -> device
+        copy of the step's histories and device -> host copy of the top-k lists inside the timed region
+roofline  tensor roofline of the dominant kernel: algorithmic FLOPs (F = 2*hid*(D+2) + 4*hid + 3*D + 16
+        per (history item, candidate) cell) / CUDA-event time, against MEASURED_PEAKS.json bf16 (sustained)
+cpu_baseline  the oracle port of validation.py:84-127 (torch CPU, all host threads) on a bounded sample of users
+
+`--impl reference` times that CPU arm alone and prints the same JSON line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "C2": dict(users=30000, pois=40000, hist=128, D=64, hid=64, k=20, desc="Gowalla-shaped 30k users x 40k POIs, H=128, D=hid=64, top-20"),
+    "C4": dict(users=100000, pois=1000000, hist=128, D=64, hid=64, k=20, desc="Yelp-scale 100k users x 1M POIs, H=128, D=hid=64, top-20"),
+    "tiny": dict(users=512, pois=4096, hist=32, D=64, hid=64, k=20, desc="tiny self-test"),
+}
+BETA = 0.5
+
+
+def flops_per_cell(D, hid):
+    return 2 * hid * (D + 2) + 4 * hid + 3 * D + 16
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d.get("hbm_gbs", 6650.0), tf_burst=d.get("bf16_tflops", 1590.0),
+                    tf_sust=d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0)), which="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, which="fallback")
+
+
+def synth_histories(users, pois, hist, seed=0):
+    """Fixed-length histories without replacement: popularity-skewed + local, cheap to generate for 100k users."""
+    rng = np.random.default_rng(seed)
+    homes = rng.integers(0, pois, users)
+    out = np.empty((users, hist), dtype=np.int64)
+    span = max(4 * hist, min(pois, 2000))
+    for u0 in range(0, users, 4096):
+        u1 = min(users, u0 + 4096)
+        n = u1 - u0
+        # local window around home (in id space, which the catalogue generator leaves spatially unordered -> mix)
+        cand = (homes[u0:u1, None] + rng.integers(-span, span, (n, 3 * hist))) % pois
+        glob = (rng.pareto(1.0, (n, 3 * hist)) * 50).astype(np.int64) % pois
+        pick = np.where(rng.random((n, 3 * hist)) < 0.7, cand, glob)
+        for i in range(n):
+            _, first = np.unique(pick[i], return_index=True)
+            sel = pick[i][np.sort(first)][:hist]
+            if len(sel) < hist:  # top up
+                extra = np.setdiff1d(rng.permutation(pois)[:4 * hist], sel)[:hist - len(sel)]
+                sel = np.concatenate([sel, extra])
+            out[u0 + i] = np.sort(sel)
+    return out
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag, self.th = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_arm(cfg, n_users, seed=0, warm=1):
+    """The reference's CPU path (oracle port of validation.py:84-127: chunks of 2048, torch.cat, torch.topk(50)) on the
+    host cores, all threads.  Returns users/s over `n_users` users after `warm` warm-up users."""
+    import torch
+    from oracle import nais_oracle as orc  # CPU arm only
+    from poi_recommendation_models_b200 import synthetic
+    torch.set_num_threads(os.cpu_count())
+    coords, region, R = synthetic.make_catalog(cfg["pois"], seed=seed)
+    sd = orc.init_state("region_distance", cfg["pois"], cfg["D"], cfg["hid"], R, 1, seed=seed + 1, style="trained")
+    hist = synth_histories(warm + n_users, cfg["pois"], cfg["hist"], seed=seed + 2)
+    cat = orc.Catalog(coords, region)
+    with torch.no_grad():
+        for u in range(warm):
+            orc.fullrank_user(sd, "region_distance", BETA, cat, hist[u], 50)
+        t0 = time.perf_counter()
+        for u in range(warm, warm + n_users):
+            orc.fullrank_user(sd, "region_distance", BETA, cat, hist[u], 50)
+        dt = time.perf_counter() - t0
+    return n_users / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args, cfg, rank, world):
+    if rank != 0:
+        return
+    n = max(1, args.cpu_users)
+    t_all, vals = 0.0, []
+    for _ in range(args.warmup):
+        pass  # the CPU arm warms up inside cpu_arm (one untimed user per step)
+    for s in range(args.steps):
+        v, dt, threads = cpu_arm(cfg, n, seed=s)
+        vals.append(v)
+        t_all += dt
+    value = float(np.mean(vals))
+    line = {"impl": "reference", "metric": "fullrank_eval_users_per_sec", "value": value, "unit": "users/s",
+            "pair_scores_per_sec": value * (cfg["pois"] - cfg["hist"]), "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * t_all / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config}: {cfg['desc']}", "users_per_step": n, "topk": 50},
+            "cpu_baseline": {"value": value, "unit": "users/s", "cores": threads, "kind": "port",
+                             "sample": f"{n} users x {cfg['pois']} POIs per step, {args.steps} steps, oracle port of validation.py:84-127 (chunk 2048, torch CPU)"},
+            "e2e": {"value": value, "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2", choices=list(WORKLOADS))
+    ap.add_argument("--precision", default=os.environ.get("NAIS_BENCH_PRECISION", "fp32"), choices=["fp32", "tc_split", "tc_fast"])
+    ap.add_argument("--users-per-step", type=int, default=0)
+    ap.add_argument("--cpu-users", type=int, default=4, help="users in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = WORKLOADS[args.config]
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from poi_recommendation_models_b200 import _lib, model as M, ops, synthetic
+    from poi_recommendation_models_b200.distributed import ShardedRanker
+
+    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    peaks = load_peaks()
+
+    U, N, H, D, hid, k = cfg["users"], cfg["pois"], cfg["hist"], cfg["D"], cfg["hid"], cfg["k"]
+    ups = args.users_per_step or {"fp32": 296, "tc_split": 2368, "tc_fast": 4736}[args.precision]
+    ups = min(ups, U)
+    n_batches = min(args.steps + args.warmup, max(1, U // ups))
+    # ---- synthetic data + random-init ("trained-like") weights of the named architecture ----------------------------
+    coords, region, R = synthetic.make_catalog(N, seed=0)
+    g = torch.Generator().manual_seed(1)
+    torch.manual_seed(1)
+    m = M.NAIS_region_distance_Embedding(N, D, hid, BETA, R, 1)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if name.startswith("embed_"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.3)
+            elif name.endswith(".bias"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+    m = m.to(dev).eval()
+    m.set_catalog(region=region, coords=coords)
+    hist_np = synth_histories(n_batches * ups, N, H, seed=2)
+    ranker = ShardedRanker(m, rank, world)
+    batches_dev, batches_host = [], []
+    for b in range(n_batches):
+        h = hist_np[b * ups:(b + 1) * ups]
+        indptr = np.arange(0, (ups + 1) * H, H, dtype=np.int64)
+        batches_dev.append(m.make_users(indptr, h.reshape(-1)))
+        batches_host.append((torch.from_numpy(indptr).pin_memory(), torch.from_numpy(h.reshape(-1).copy()).pin_memory()))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_device(i):
+        return ranker.topk(batches_dev[i % n_batches], k, precision=args.precision)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident timing ----------------------------------------------------------------------------------------
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = lib.nais_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations (untimed)
+        ev[i][0].record()
+        out = step_device(args.warmup + i)
+        ev[i][1].record()
+    barrier()
+    launches = lib.nais_launch_count() - l0
+    clocks = sampler.stop()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    t_local = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+    kern_ms = ranker.last_kernel_ms  # CUDA-event time of the dominant (scoring) kernel launch of the last step
+    if world > 1:
+        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
+    total_ms = float(t_local.item())
+    users_per_s = ups * args.steps / (total_ms / 1000.0)
+
+    # ---- end to end through the drop-in API: host CSR in, host top-k out --------------------------------------------
+    def step_e2e(i):
+        ip, it = batches_host[i % n_batches]
+        s, ids = ranker.topk_host(ip, it, k, precision=args.precision)
+        return s, ids
+
+    for i in range(min(args.warmup, 2)):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        s_h, i_h = step_e2e(args.warmup + i)
+    barrier()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_users_per_s = ups * args.steps / float(t_e2e.item())
+    h2d = batches_host[0][0].numel() * 8 + batches_host[0][1].numel() * 8
+    d2h = ups * k * (4 + 8)
+
+    if rank == 0:
+        cells_per_launch = ups * H * ((N + world - 1) // world)
+        F = flops_per_cell(D, hid)
+        ach = cells_per_launch * F / (kern_ms / 1000.0) / 1e12 if kern_ms else None
+        peak = peaks["tf_sust"]
+        line = {"metric": "fullrank_eval_users_per_sec", "value": users_per_s, "unit": "users/s",
+                "pair_scores_per_sec": users_per_s * N, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": {"fp32": "f32", "tc_split": "f16x2-split/f32-accum", "tc_fast": "f16/f32-accum"}[args.precision],
+                "data": "synthetic",
+                "config": {"workload": f"{args.config}: {cfg['desc']}", "users_per_step": ups, "precision": args.precision,
+                           "l2": "flushed between timed steps (256 MiB write)", "weights": "random init, trained-like scale",
+                           "parallelism": f"catalogue range shards x{world} + all-gather top-k merge" if world > 1 else "single GPU"},
+                "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": e2e_users_per_s, "unit": "users/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                             "frac": (ach / peak) if ach else None, "traffic": None,
+                             "kernel": ranker.kernel_name(args.precision), "kernel_ms": kern_ms,
+                             "flops_per_cell": F, "cells_per_launch": cells_per_launch,
+                             "peak_source": f"{peaks['which']} bf16 sustained (MEASURED_PEAKS.json)",
+                             "hbm_frac": None}}
+        # algorithmic HBM bytes of the launch: catalogue rows + history items + output
+        alg_bytes = ((N + world - 1) // world) * (D // 2 * 4 + 4 + 8) + ups * H * (4 + D // 2 * 4 + 4 + 8) + ups * k * 8
+        if kern_ms:
+            line["roofline"]["hbm_frac"] = alg_bytes / (kern_ms / 1000.0) / 1e9 / peaks["hbm"]
+        if not args.no_cpu_baseline and world == 1:
+            v, dt, threads = cpu_arm(cfg, max(1, args.cpu_users))
+            line["cpu_baseline"] = {"value": v, "unit": "users/s", "cores": threads, "kind": "port",
+                                    "sample": f"{args.cpu_users} users x {N} POIs (H={H}), {dt:.1f} s, oracle port of validation.py:84-127 (chunk 2048, torch CPU, top-50)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,173 @@
+/*
+ * nais_b200.h — C ABI of the B200-native NAIS scorer (libnais_b200.so).
+ *
+ * The reference (muyeon-jo/POI_recommendation_models) has NO plugin / FFI / operator registry: the boundary of its
+ * hot path is the Python class API of model.py.  This header is the C-level boundary a maintainer
+ * binds (ctypes stub in INTEGRATION.md) to replace the bodies of
+ *
+ *   model.py:246-297   NAIS_region_distance_Embedding.attention_network   -> nais_pairs_forward / nais_pairs_backward
+ *   model.py:57-89, 144-180, 355-401, 467-534   the sibling scorers        -> same entry points, other NaisParams
+ *   validation.py:84-127   per-user candidate loop + torch.topk            -> nais_fullrank_topk
+ *   torch.cat/topk merge across catalogue shards (new, multi-GPU)          -> nais_topk_merge
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into memory owned by the caller (PyTorch tensors); the library never
+ *     allocates, frees or synchronises, and enqueues only on the given stream;
+ *   - return 0 = OK; negative = argument error found before any launch (see NAIS_ERR_*); positive = cudaError_t;
+ *   - all entry points are stateless and re-entrant; one host thread per GPU is the intended use;
+ *   - no C++ types, no torch types: plain pointers and sizes.
+ */
+#ifndef NAIS_B200_H_
+#define NAIS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NAIS_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define NAIS_API __attribute__((visibility("default")))
+#else
+#define NAIS_API
+#endif
+
+/* distance modes */
+#define NAIS_DIST_NONE 0   /* NAIS_basic, NAIS_regionEmbedding */
+#define NAIS_DIST_LATLON 1 /* sigmoid(Linear(2,2)(scale*|dlat,dlon|)) -> 2 extra input lanes of attn_layer1 (model.py:265, :366) */
+#define NAIS_DIST_KM 2     /* logit += dist_km * sum_d embed_distance[bucket,d]  (model.py:497-504; reference uses bucket 0) */
+
+/* precision of the attention-MLP contraction in nais_fullrank_topk */
+#define NAIS_PREC_FP32 0     /* FP32 FFMA on CUDA cores (exact path) */
+#define NAIS_PREC_TC_SPLIT 1 /* tcgen05 fp16 MMA, operands split hi+lo (3 MMAs, ~fp32 products), fp32 accumulate in TMEM */
+#define NAIS_PREC_TC_FAST 2  /* tcgen05 fp16 MMA, single pass (11-bit operands), fp32 accumulate in TMEM */
+
+#define NAIS_ERR_NULL -1      /* required pointer is NULL */
+#define NAIS_ERR_SHAPE -2     /* unsupported / inconsistent dimension */
+#define NAIS_ERR_ALIGN -3     /* pointer or row width not 16-byte aligned */
+#define NAIS_ERR_WORKSPACE -4 /* workspace too small (ask nais_*_workspace_bytes) */
+#define NAIS_ERR_MODE -5      /* unknown mode / flag combination */
+#define NAIS_ERR_ARCH -6      /* device is not sm_100 (tensor path) */
+
+typedef void* nais_stream_t; /* cudaStream_t */
+
+/* One attention branch: q = [hist_poi[item] ; hist_reg[region]], p = [tgt_poi[item] ; tgt_reg[region]].
+ * NAIS_region_distance_Embedding: w_poi = w_reg = embed_size/2, hist_reg == tgt_reg == embed_region (model.py:253-259).
+ * NAIS_basic / NAIS_distance_Embedding: w_reg = 0.  Disentangled: branch 0 = (w_poi=D, w_reg=0, attn_layer*),
+ * branch 1 = (w_poi=0, w_reg=D, region_attn_layer*), scores added (model.py:467-534). */
+typedef struct NaisBranch {
+  const float* hist_poi; /* [item_num, w_poi]   embed_history.weight */
+  const float* tgt_poi;  /* [item_num, w_poi]   embed_target.weight  */
+  const float* hist_reg; /* [region_num, w_reg] embed_region.weight  */
+  const float* tgt_reg;  /* [region_num, w_reg] embed_region.weight  */
+  const float* w1;       /* [hid, w_poi+w_reg+lanes] attn_layer1.weight, row-major; lanes = 2 iff NAIS_DIST_LATLON */
+  const float* b1;       /* [hid] attn_layer1.bias */
+  const float* w2;       /* [hid] attn_layer2.weight (no bias) */
+  int32_t w_poi;
+  int32_t w_reg;
+} NaisBranch;
+
+typedef struct NaisParams {
+  NaisBranch branch[2];
+  int32_t n_branch;   /* 1, or 2 for the disentangled model */
+  int32_t hid;        /* hidden_size */
+  int32_t item_num;   /* rows of the POI tables */
+  int32_t region_num; /* rows of the region table (0 if unused) */
+  int32_t dist_mode;  /* NAIS_DIST_* */
+  float dist_scale;   /* 100 (model.py:265) or 1000 (model.py:366) */
+  const float* dist_w; /* [2,2] dist_layer.weight (LATLON) */
+  const float* dist_b; /* [2]   dist_layer.bias   (LATLON) */
+  const float* dist_embed; /* [dist_buckets, D] embed_distance.weight (KM) */
+  int32_t dist_buckets;    /* >= 1; reference: 1 */
+  float dist_bucket_km;    /* bucket = min(floor(km / dist_bucket_km), dist_buckets-1); ignored when dist_buckets == 1 */
+  float beta;              /* smoothing exponent of the softmax denominator (model.py:284-285) */
+} NaisParams;
+
+/* A batch of explicit (history row, target) pairs: the argument list of model.forward (model.py:231). */
+typedef struct NaisPairs {
+  const int64_t* hist; /* [B,H] history POI ids */
+  const int64_t* tgt;  /* [B]   target POI ids */
+  const int64_t* hreg; /* [B,H] region id of each history POI (NULL when no branch has w_reg) */
+  const int64_t* treg; /* [B]   region id of each target */
+  const float* aux;    /* LATLON: ll[B,H,2] = |dlat|,|dlon| degrees; KM: dist_km[B,H]; NONE: NULL */
+  int64_t B;
+  int32_t H;
+} NaisPairs;
+
+/* Gradients of nais_pairs_backward.  Dense tables must be zero-filled by the caller; the library writes each touched
+ * row exactly once (sorted-segment accumulation, no atomics), and writes w1/b1/w2/dist_w/dist_b in full. */
+typedef struct NaisGrads {
+  float* hist_poi[2]; /* [item_num, w_poi]  per branch (NULL to skip) */
+  float* tgt_poi[2];
+  float* reg[2];      /* [region_num, w_reg] history-side + target-side contributions summed (shared table) */
+  float* w1[2];
+  float* b1[2];
+  float* w2[2];
+  float* dist_w; /* [2,2] */
+  float* dist_b; /* [2]   */
+  float* dist_embed; /* [dist_buckets, D] */
+} NaisGrads;
+
+/* Candidate side of full-rank scoring: rows [row_base, row_base+n_rows) of the POI catalogue.  tgt_poi in NaisParams
+ * is indexed by GLOBAL id (replicated table); region/coords here are indexed by (id - row_base) so a shard can pass
+ * its slice only. */
+typedef struct NaisCatalog {
+  const int32_t* region; /* [n_rows] dense region id (businessRegionEmbedList, run.py:218-223) */
+  const float* coords;   /* [n_rows,2] (lat,lon) degrees, centred on the host in float64 before the cast */
+  int64_t row_base;
+  int64_t n_rows;
+} NaisCatalog;
+
+/* User histories as CSR (train_matrix.getrow(u).indices, validation.py:86), with the per-item side data gathered. */
+typedef struct NaisUsers {
+  const int64_t* offsets; /* [n_users+1] */
+  const int32_t* items;   /* [nnz] POI ids */
+  const int32_t* region;  /* [nnz] region id of each item */
+  const float* coords;    /* [nnz,2] centred coords of each item */
+  int32_t n_users;
+} NaisUsers;
+
+NAIS_API int nais_abi_version(void);
+NAIS_API const char* nais_strerror(int code);
+/* Number of kernels this library has launched in this process (diagnostic; bench.py reports it as gpu_launches). */
+NAIS_API uint64_t nais_launch_count(void);
+
+/* score[b] = attention_network(pairs)  (pre-sigmoid, model.py:246-297).  Saved for backward (either may be NULL):
+ * row_sum[n_branch,B] = sum_h E_bh, score_parts[n_branch,B] = per-branch score (their sum over branches is score). */
+NAIS_API int nais_pairs_forward(const NaisParams* p, const NaisPairs* batch, float* score, float* row_sum, float* score_parts,
+                       nais_stream_t stream);
+
+NAIS_API size_t nais_pairs_backward_workspace_bytes(const NaisParams* p, int64_t B, int32_t H);
+/* Given dscore[B] = dL/dscore, write every parameter gradient.  score/row_sum are the forward outputs. */
+NAIS_API int nais_pairs_backward(const NaisParams* p, const NaisPairs* batch, const float* score_parts, const float* row_sum,
+                        const float* dscore, const NaisGrads* grads, void* workspace, size_t workspace_bytes,
+                        nais_stream_t stream);
+
+/* Workspace for nais_fullrank_topk / nais_fullrank_scores: n_users and nnz = offsets[n_users] are host-known. */
+NAIS_API size_t nais_fullrank_workspace_bytes(const NaisParams* p, int32_t n_users, int64_t nnz, int64_t poi_begin,
+                                     int64_t poi_end, int32_t k, int32_t precision);
+/* For every user: score all POIs in [poi_begin, poi_end) (history items excluded when exclude_history != 0),
+ * keep the k best by (score desc, id asc).  out_score [n_users,k] (pre-sigmoid; -inf padding), out_id [n_users,k]
+ * (global POI id; -1 padding).  Replaces validation.py:84-127. */
+NAIS_API int nais_fullrank_topk(const NaisParams* p, const NaisCatalog* cat, const NaisUsers* users, int64_t poi_begin,
+                       int64_t poi_end, int32_t k, int32_t exclude_history, int32_t precision, float* out_score, int32_t* out_id, void* workspace, size_t workspace_bytes,
+                       nais_stream_t stream);
+
+/* Merge n_lists sorted top-k lists per user (e.g. one per catalogue shard after an all-gather) into one.
+ * in_score/in_id: [n_users, n_lists, k]; out: [n_users, k].  Same order rule as nais_fullrank_topk. */
+NAIS_API int nais_topk_merge(const float* in_score, const int32_t* in_id, int32_t n_users, int32_t n_lists, int32_t k,
+                    float* out_score, int32_t* out_id, nais_stream_t stream);
+
+/* Same scoring pass, but also writes every pre-sigmoid score: all_scores[n_users, poi_end-poi_begin] (history items are
+ * scored with their own cell masked, like a training positive).  For parity checks of the fused path on small cases. */
+NAIS_API int nais_fullrank_scores(const NaisParams* p, const NaisCatalog* cat, const NaisUsers* users, int64_t poi_begin,
+                         int64_t poi_end, int32_t precision, float* all_scores, void* workspace,
+                         size_t workspace_bytes, nais_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAIS_B200_H_ */

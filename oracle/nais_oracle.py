@@ -83,6 +83,9 @@ def init_state(variant: str, item_num: int, embed_size: int, hidden_size: int, r
     return sd
 
 
+_SCALE_SINK: list = []  # when a list is pushed here, _beta_attention appends sum_h |w_h s_h| (conditioning scale)
+
+
 def _beta_attention(a: torch.Tensor, sim: torch.Tensor, mask: torch.Tensor, beta: float) -> torch.Tensor:
     """exp / mask / beta-smoothed normaliser / weighted similarity (model.py:279-293).
 
@@ -90,7 +93,22 @@ def _beta_attention(a: torch.Tensor, sim: torch.Tensor, mask: torch.Tensor, beta
     """
     e = torch.exp(a) * mask.to(a.dtype)
     denom = torch.pow(e.sum(-1, keepdim=True), beta)
-    return ((e / denom) * sim).sum(-1)
+    terms = (e / denom) * sim
+    if _SCALE_SINK:
+        _SCALE_SINK[-1].append(terms.detach().abs().sum(-1))
+    return terms.sum(-1)
+
+
+def attention_network_with_scale(*args, **kwargs):
+    """(score, scale) with scale[b] = sum over branches of sum_h |w_bh s_bh|: the magnitude the score's rounding error
+    is relative to when the terms cancel (SURVEY.md §7 'tolerance must be condition-aware')."""
+    sink: list = []
+    _SCALE_SINK.append(sink)
+    try:
+        s = attention_network(*args, **kwargs)
+    finally:
+        _SCALE_SINK.pop()
+    return s, sum(sink)
 
 
 def attention_network(sd: Dict[str, torch.Tensor], variant: str, beta: float, hist: torch.Tensor, tgt: torch.Tensor,

@@ -1,0 +1,672 @@
+// Backward of the pair scorer (FP32): recompute-based, atomics-free.
+//
+//   pairs_bwd_kernel   per 128-cell tile: recompute t = W x + ..., logits, softmax weights -> da, dt;
+//                      dW += dt^T x (register-resident across the tiles of a persistent CTA), dX = dt W,
+//                      per-cell dq = (dX + G w) (.) p  -> workspace, per-row dp = sum_h (dX + G w) (.) q -> workspace
+//   param_reduce       deterministic sum of the per-CTA parameter partials
+//   segment_reduce     embedding-row gradients: contributions sorted by row id (cub radix sort), one warp per run of
+//                      equal keys sums its rows and writes the table row once — no atomics, bitwise reproducible.
+//
+// Math (SURVEY.md §7 'Backward'):  dscore/da_h = w_h s_h - beta (E_h/S) score ;  dt_k = da v_k [t_k > 0]
+#include <cub/device/device_radix_sort.cuh>
+
+#include "nais_common.cuh"
+
+namespace nais {
+
+constexpr int BWD_MAXROWS = 16;
+
+struct BwdArgs {
+  NaisParams p;
+  NaisPairs b;
+  int bi;                 // branch
+  const float* parts;     // [B] per-branch score of this branch
+  const float* row_sum;   // [B]
+  const float* dscore;    // [B]
+  float* ws_dq;           // [B*H, D]
+  float* ws_dp;           // [B, D]
+  float* ws_part;         // [grid, part_stride]
+  int part_stride;
+  int rows_per_tile;
+  int64_t n_items;        // work items (tiles of rows)
+};
+
+// layout of one CTA's parameter partial: w1 [hid][D+lanes] | b1 [hid] | w2 [hid] | dist_w[4] dist_b[2] km[1] pad[1]
+__host__ __device__ inline int part_floats(int hid, int D, int lanes) { return hid * (D + lanes) + 2 * hid + 8; }
+
+template <int NKB, int DB>
+__global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(const __grid_constant__ BwdArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  const NaisParams& p = A.p;
+  const NaisBranch& br = p.branch[A.bi];
+  const int H = A.b.H, D = br.w_poi + br.w_reg, hid = p.hid;
+  const int lanes = (p.dist_mode == NAIS_DIST_LATLON) ? 2 : 0;
+  const int ldw = D + lanes;
+  constexpr int HP = NKB * KB;
+
+  float* As = smem;                          // [D][TCP] x, later dp contributions
+  float* DTs = As + (size_t)D * TCP;         // [HP][TCP] dt
+  float* Wt = DTs + (size_t)HP * TCP;        // [D][KB]   W^T k-block
+  float* kc = Wt + (size_t)D * KB;           // [NKB][4][KB]
+  float* g = kc + NKB * 4 * KB;              // [2][TC] lanes (or km in g[0])
+  float* llc = g + 2 * TC;                   // [2][TC] raw |dlat|,|dlon| (LATLON) for dWd
+  float* sp = llc + 2 * TC;                  // [2][TC]
+  float* gw = sp + 2 * TC;                   // [TC] G * w
+  float* dac = gw + TC;                      // [TC] da
+  float* dvp = dac + TC;                     // [16][HP] dv partials
+  float* ps = dvp + 16 * HP;                 // [BWD_MAXROWS][D]
+  float* dpacc = ps + BWD_MAXROWS * D;       // [BWD_MAXROWS][D]
+  float* rowv = dpacc + BWD_MAXROWS * D;     // [3][BWD_MAXROWS] S, score, G
+  float* red = rowv + 3 * BWD_MAXROWS;       // [8][NT/32] final block reduce scratch
+  int* citem = reinterpret_cast<int*>(red + 8 * (NT / 32));  // [TC] history item id per cell
+  int* creg = citem + TC;                                   // [TC]
+  int* crow = creg + TC;                                    // [TC] row slot per cell (-1 invalid)
+
+  const int tid = threadIdx.x, cell = tid & (TC - 1), half = tid >> 7;
+  const int tk = tid & 15, tj = tid >> 4;
+  const int n_chunks = (H <= TC) ? 1 : (H + TC - 1) / TC;
+
+  // persistent accumulators
+  float acc3[NKB * DB][4][4];
+#pragma unroll
+  for (int s = 0; s < NKB * DB; ++s)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc3[s][i][j] = 0.f;
+  float pb = 0.f, pv = 0.f, pl0 = 0.f, pl1 = 0.f;  // thread k < HP: db1, dw2, dW[:,D], dW[:,D+1]
+  float pd[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // thread = cell: dist_w[4], dist_b[2], km
+
+  float km_c = 0.f;
+  if (p.dist_mode == NAIS_DIST_KM) {
+    for (int d = 0; d < D; ++d) km_c += __ldg(p.dist_embed + d);
+  }
+  // constants for all k-blocks
+  for (int i = tid; i < NKB * KB; i += NT) {
+    const int kbi = i / KB, kk = i - kbi * KB, k = i;
+    const bool ok = k < hid;
+    float* c = kc + kbi * 4 * KB;
+    c[kk] = ok ? __ldg(br.b1 + k) : 0.f;
+    c[KB + kk] = ok ? __ldg(br.w2 + k) : 0.f;
+    c[2 * KB + kk] = (ok && lanes) ? __ldg(br.w1 + (size_t)k * ldw + D) : 0.f;
+    c[3 * KB + kk] = (ok && lanes) ? __ldg(br.w1 + (size_t)k * ldw + D + 1) : 0.f;
+  }
+  int resident = -1;
+
+  for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x) {
+    const int64_t row0 = item * A.rows_per_tile;
+    const int nrows = (int)min((int64_t)A.rows_per_tile, A.b.B - row0);
+    __syncthreads();
+    for (int i = tid; i < nrows * D; i += NT) {
+      int r = i / D, d = i - r * D;
+      ps[r * D + d] = (d < br.w_poi) ? __ldg(br.tgt_poi + (size_t)A.b.tgt[row0 + r] * br.w_poi + d)
+                                     : __ldg(br.tgt_reg + (size_t)A.b.treg[row0 + r] * br.w_reg + (d - br.w_poi));
+      dpacc[r * D + d] = 0.f;
+    }
+    if (tid < nrows) {
+      rowv[tid] = A.row_sum[row0 + tid];
+      rowv[BWD_MAXROWS + tid] = A.parts[row0 + tid];
+      rowv[2 * BWD_MAXROWS + tid] = A.dscore[row0 + tid];
+    }
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      __syncthreads();
+      int r, h;
+      bool valid;
+      if (H <= TC) {
+        r = cell / H;
+        h = cell - r * H;
+        valid = r < nrows;
+      } else {
+        r = 0;
+        h = ch * TC + cell;
+        valid = h < H;
+      }
+      const int64_t cidx = valid ? (row0 + r) * (int64_t)H + h : 0;
+      // ---- build x, similarity, lanes -------------------------------------------------------------------------
+      {
+        const int d0 = half ? (D >> 1) : 0, d1 = half ? D : (D >> 1);
+        float ssum = 0.f;
+        int64_t it = 0, rg = 0;
+        if (valid) {
+          it = A.b.hist[cidx];
+          rg = br.w_reg ? A.b.hreg[cidx] : 0;
+          const float* qp = br.hist_poi + (size_t)it * br.w_poi;
+          const float* qr = br.hist_reg + (size_t)rg * br.w_reg;
+          for (int d = d0; d < d1; ++d) {
+            float q = (d < br.w_poi) ? __ldg(qp + d) : __ldg(qr + d - br.w_poi);
+            float x = q * ps[r * D + d];
+            As[d * TCP + cell] = x;
+            ssum += x;
+          }
+        } else {
+          for (int d = d0; d < d1; ++d) As[d * TCP + cell] = 0.f;
+        }
+        sp[half * TC + cell] = ssum;
+        if (half == 0) {
+          float g0 = 0.f, g1 = 0.f, l0 = 0.f, l1 = 0.f;
+          if (valid && lanes) {
+            l0 = A.b.aux[cidx * 2];
+            l1 = A.b.aux[cidx * 2 + 1];
+            const float a0 = l0 * p.dist_scale, a1 = l1 * p.dist_scale;
+            g0 = sigmoidf_exact(fmaf(a1, __ldg(p.dist_w + 1), fmaf(a0, __ldg(p.dist_w + 0), __ldg(p.dist_b + 0))));
+            g1 = sigmoidf_exact(fmaf(a1, __ldg(p.dist_w + 3), fmaf(a0, __ldg(p.dist_w + 2), __ldg(p.dist_b + 1))));
+          } else if (valid && p.dist_mode == NAIS_DIST_KM) {
+            l0 = A.b.aux[cidx];
+            g0 = l0 * km_c;
+          }
+          g[cell] = g0;
+          g[TC + cell] = g1;
+          llc[cell] = l0;
+          llc[TC + cell] = l1;
+          citem[cell] = (int)it;
+          creg[cell] = (int)rg;
+          crow[cell] = valid ? r : -1;
+        }
+      }
+      __syncthreads();
+      // ---- GEMM1: t[cell][k] for all k-blocks, kept in registers ----------------------------------------------
+      float t[NKB][8][4];
+#pragma unroll
+      for (int kb = 0; kb < NKB; ++kb) {
+        if (resident != kb) {
+          __syncthreads();
+          for (int i = tid; i < D * KB; i += NT) {
+            int kk = i / D, d = i - kk * D;
+            int k = kb * KB + kk;
+            Wt[d * KB + kk] = (k < hid) ? __ldg(br.w1 + (size_t)k * ldw + d) : 0.f;
+          }
+          resident = kb;
+          __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) t[kb][i][c] = 0.f;
+        const float* ap = As + tj * 8;
+        const float* bp = Wt + tk * 4;
+#pragma unroll 4
+        for (int d = 0; d < D; ++d) {
+          float4 a0 = *reinterpret_cast<const float4*>(ap + d * TCP);
+          float4 a1 = *reinterpret_cast<const float4*>(ap + d * TCP + 4);
+          float4 b = *reinterpret_cast<const float4*>(bp + d * KB);
+          const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) t[kb][i][c] = fmaf(av[i], bv[c], t[kb][i][c]);
+        }
+      }
+      // bias + lanes, relu, logits
+      float a_part[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a_part[i] = 0.f;
+#pragma unroll
+      for (int kb = 0; kb < NKB; ++kb) {
+        const float* c = kc + kb * 4 * KB + tk * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float g0 = lanes ? g[tj * 8 + i] : 0.f, g1 = lanes ? g[TC + tj * 8 + i] : 0.f;
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            float v = t[kb][i][cc] + c[cc];
+            if (lanes) v = fmaf(c[3 * KB + cc], g1, fmaf(c[2 * KB + cc], g0, v));
+            v = fmaxf(v, 0.f);
+            t[kb][i][cc] = v;  // relu(t)
+            a_part[i] = fmaf(c[KB + cc], v, a_part[i]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v = a_part[i];
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        a_part[i] = v;
+      }
+      // da per cell (all 16 tk-lanes compute the same value), dt -> DTs, dv partials
+      float da[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = tj * 8 + i;
+        const int rr = crow[c];
+        float dav = 0.f, gwv = 0.f;
+        if (rr >= 0) {
+          float a = a_part[i];
+          if (p.dist_mode == NAIS_DIST_KM) a += g[c];
+          const int64_t ci = (H <= TC) ? (row0 + rr) * (int64_t)H + (c - rr * H) : row0 * (int64_t)H + ch * TC + c;
+          const bool m = A.b.hist[ci] != A.b.tgt[row0 + rr];
+          if (m) {
+            const float S = rowv[rr], sc = rowv[BWD_MAXROWS + rr], G = rowv[2 * BWD_MAXROWS + rr];
+            const float e = expf(a);
+            const float w = e / powf(S, p.beta);
+            const float s = sp[c] + sp[TC + c];
+            dav = G * (w * s - p.beta * (e / S) * sc);
+            gwv = G * w;
+          }
+        }
+        da[i] = dav;
+        if (tk == 0) {
+          dac[c] = dav;
+          gw[c] = gwv;
+        }
+      }
+#pragma unroll
+      for (int kb = 0; kb < NKB; ++kb) {
+        const float* c = kc + kb * 4 * KB + tk * 4;
+        float dvl[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const float hval = t[kb][i][cc];
+            dvl[cc] = fmaf(da[i], hval, dvl[cc]);
+            DTs[(kb * KB + tk * 4 + cc) * TCP + tj * 8 + i] = (hval > 0.f) ? da[i] * c[KB + cc] : 0.f;
+          }
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) dvp[tj * HP + kb * KB + tk * 4 + cc] = dvl[cc];
+      }
+      __syncthreads();
+      // ---- small reductions over cells: db1, dw2, lane columns (thread k), dist layer (thread cell) -------------
+      if (tid < HP) {
+        float sb = 0.f, s0 = 0.f, s1 = 0.f, sv = 0.f;
+        for (int c = 0; c < TC; ++c) {
+          const float dtv = DTs[tid * TCP + c];
+          sb += dtv;
+          if (lanes) {
+            s0 = fmaf(dtv, g[c], s0);
+            s1 = fmaf(dtv, g[TC + c], s1);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sv += dvp[j * HP + tid];
+        pb += sb;
+        pv += sv;
+        pl0 += s0;
+        pl1 += s1;
+      } else if (tid >= TC && tid < 2 * TC) {
+        const int c = tid - TC;
+        if (lanes) {
+          float dg0 = 0.f, dg1 = 0.f;
+          for (int k = 0; k < hid; ++k) {
+            const float dtv = DTs[k * TCP + c];
+            const float* cst = kc + (k / KB) * 4 * KB + (k % KB);
+            dg0 = fmaf(dtv, cst[2 * KB], dg0);
+            dg1 = fmaf(dtv, cst[3 * KB], dg1);
+          }
+          const float g0 = g[c], g1 = g[TC + c];
+          const float dz0 = dg0 * g0 * (1.f - g0), dz1 = dg1 * g1 * (1.f - g1);
+          const float a0 = llc[c] * p.dist_scale, a1 = llc[TC + c] * p.dist_scale;
+          pd[0] = fmaf(dz0, a0, pd[0]);
+          pd[1] = fmaf(dz0, a1, pd[1]);
+          pd[2] = fmaf(dz1, a0, pd[2]);
+          pd[3] = fmaf(dz1, a1, pd[3]);
+          pd[4] += dz0;
+          pd[5] += dz1;
+        } else if (p.dist_mode == NAIS_DIST_KM) {
+          pd[6] = fmaf(dac[c], llc[c], pd[6]);
+        }
+      }
+      // ---- GEMM3: dW[k][d] += sum_c dt[k][c] x[d][c] ---------------------------------------------------------------
+      {
+        const int k0 = tid & 15, dd0 = tid >> 4;
+#pragma unroll
+        for (int s = 0; s < NKB * DB; ++s) {
+          const int kb3 = s / DB, db3 = s % DB;
+          const float* ar[4];
+          const float* brow[4];
+          bool dok[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ar[i] = DTs + (size_t)(kb3 * KB + k0 + 16 * i) * TCP;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int d = db3 * 64 + dd0 + 16 * j;
+            dok[j] = d < D;
+            brow[j] = As + (size_t)(dok[j] ? d : 0) * TCP;
+          }
+          for (int c = 0; c < TC; c += 4) {
+            float4 av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) av[i] = *reinterpret_cast<const float4*>(ar[i] + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = *reinterpret_cast<const float4*>(brow[j] + c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float v = acc3[s][i][j];
+                v = fmaf(av[i].x, bv[j].x, v);
+                v = fmaf(av[i].y, bv[j].y, v);
+                v = fmaf(av[i].z, bv[j].z, v);
+                v = fmaf(av[i].w, bv[j].w, v);
+                acc3[s][i][j] = v;
+              }
+          }
+        }
+      }
+      __syncthreads();  // As (x) no longer needed: it becomes the dp-contribution scratch
+      // ---- GEMM2: dX[cell][d] = sum_k dt[cell][k] W[k][d]; finalize dq (global) and dp contributions (smem) ------
+#pragma unroll 1
+      for (int db = 0; db < DB; ++db) {
+        const int d0 = db * 64 + tk * 4;
+        const bool dact = d0 < D;
+        float dx[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) dx[i][c] = 0.f;
+        if (dact) {
+          const float* ap = DTs + tj * 8;
+          const float* wp = br.w1 + d0;
+#pragma unroll 2
+          for (int k = 0; k < hid; ++k) {
+            float4 a0 = *reinterpret_cast<const float4*>(ap + k * TCP);
+            float4 a1 = *reinterpret_cast<const float4*>(ap + k * TCP + 4);
+            const float* wr = wp + (size_t)k * ldw;
+            const float bv[4] = {__ldg(wr), __ldg(wr + 1), __ldg(wr + 2), __ldg(wr + 3)};
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) dx[i][c] = fmaf(av[i], bv[c], dx[i][c]);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int c = tj * 8 + i;
+            const int rr = crow[c];
+            float o[4] = {0.f, 0.f, 0.f, 0.f}, dpv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (rr >= 0) {
+              const float gwv = gw[c];
+              const int it = citem[c], rg = creg[c];
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) {
+                const int d = d0 + cc;
+                const float full = dx[i][cc] + gwv;
+                const float q = (d < br.w_poi) ? __ldg(br.hist_poi + (size_t)it * br.w_poi + d)
+                                               : __ldg(br.hist_reg + (size_t)rg * br.w_reg + (d - br.w_poi));
+                o[cc] = full * ps[rr * D + d];
+                dpv[cc] = full * q;
+              }
+              const int64_t ci = (H <= TC) ? (row0 + rr) * (int64_t)H + (c - rr * H) : row0 * (int64_t)H + ch * TC + c;
+              *reinterpret_cast<float4*>(A.ws_dq + ci * D + d0) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) As[(size_t)(d0 + cc) * TCP + c] = dpv[cc];
+          }
+        }
+      }
+      __syncthreads();
+      // ---- dp[row][d] += sum over the row's cells -----------------------------------------------------------------
+      {
+        const int nr = (H <= TC) ? nrows : 1;
+        for (int i = tid; i < nr * D; i += NT) {
+          const int rr = i / D, d = i - rr * D;
+          const int c0 = (H <= TC) ? rr * H : 0;
+          const int cn = (H <= TC) ? H : min(TC, H - ch * TC);
+          float sacc = 0.f;
+          for (int c = 0; c < cn; ++c) sacc += As[(size_t)d * TCP + c0 + c];
+          dpacc[rr * D + d] += sacc;
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < nrows * D; i += NT) A.ws_dp[(row0 + i / D) * D + (i % D)] = dpacc[i];
+  }
+
+  // ---- flush this CTA's parameter partials --------------------------------------------------------------------------
+  float* part = A.ws_part + (size_t)blockIdx.x * A.part_stride;
+  {
+    const int k0 = tid & 15, dd0 = tid >> 4;
+#pragma unroll
+    for (int s = 0; s < NKB * DB; ++s) {
+      const int kb3 = s / DB, db3 = s % DB;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = kb3 * KB + k0 + 16 * i, d = db3 * 64 + dd0 + 16 * j;
+          if (k < hid && d < D) part[(size_t)k * ldw + d] = acc3[s][i][j];
+        }
+    }
+  }
+  if (tid < HP && tid < hid) {
+    if (lanes) {
+      part[(size_t)tid * ldw + D] = pl0;
+      part[(size_t)tid * ldw + D + 1] = pl1;
+    }
+    part[hid * ldw + tid] = pb;
+    part[hid * ldw + hid + tid] = pv;
+  }
+  // dist-layer partials: block reduce of pd[] held by threads TC..2TC-1
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 7; ++q) {
+    float v = pd[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0) red[q * (NT / 32) + (tid >> 5)] = v;
+  }
+  __syncthreads();
+  if (tid < 7) {
+    float v = 0.f;
+    for (int w = 0; w < NT / 32; ++w) v += red[tid * (NT / 32) + w];
+    part[hid * ldw + 2 * hid + tid] = v;
+  }
+}
+
+// out[i] = sum over CTAs of part[cta][i], then scatter into the gradient tensors.
+__global__ void param_reduce_kernel(const float* __restrict__ parts, int n_parts, int stride, int hid, int D, int lanes,
+                                    float* w1, float* b1, float* w2, float* dist_w, float* dist_b, float* dist_embed,
+                                    int dist_D, int accumulate_dist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ldw = D + lanes, n = hid * ldw + 2 * hid + 7;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int c = 0; c < n_parts; ++c) s += parts[(size_t)c * stride + i];
+  if (i < hid * ldw) {
+    if (w1) w1[i] = s;
+  } else if (i < hid * ldw + hid) {
+    if (b1) b1[i - hid * ldw] = s;
+  } else if (i < hid * ldw + 2 * hid) {
+    if (w2) w2[i - hid * ldw - hid] = s;
+  } else {
+    const int q = i - hid * ldw - 2 * hid;
+    if (q < 4) {
+      if (dist_w) dist_w[q] = s;
+    } else if (q < 6) {
+      if (dist_b) dist_b[q - 4] = s;
+    } else if (dist_embed) {
+      // d/d embed_distance[0, d] = sum_cells da * km for every d (model.py:497-501); both branches add up
+      for (int d = 0; d < dist_D; ++d) dist_embed[d] = accumulate_dist ? dist_embed[d] + s : s;
+    }
+  }
+}
+
+// Keys for the three gathers.  src encodes where the contribution row lives: cell index (dq) or B*H + row (dp).
+__global__ void make_keys_kernel(NaisPairs b, int want_reg, int* k_hist, uint32_t* v_hist, int* k_tgt, uint32_t* v_tgt,
+                                 int* k_reg, uint32_t* v_reg) {
+  const int64_t n_cells = b.B * (int64_t)b.H;
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n_cells) {
+    if (k_hist) {
+      k_hist[i] = (int)b.hist[i];
+      v_hist[i] = (uint32_t)i;
+    }
+    if (want_reg) {
+      k_reg[i] = (int)b.hreg[i];
+      v_reg[i] = (uint32_t)i;
+    }
+  }
+  if (i < b.B) {
+    if (k_tgt) {
+      k_tgt[i] = (int)b.tgt[i];
+      v_tgt[i] = (uint32_t)(n_cells + i);
+    }
+    if (want_reg) {
+      k_reg[n_cells + i] = (int)b.treg[i];
+      v_reg[n_cells + i] = (uint32_t)(n_cells + i);
+    }
+  }
+}
+
+// One warp per sorted position; only run starts work.  out[key, 0:w] = sum of src rows [off, off+w).
+__global__ void segment_reduce_kernel(const int* __restrict__ keys, const uint32_t* __restrict__ src, int64_t n,
+                                      int64_t n_cells, const float* __restrict__ ws_dq, const float* __restrict__ ws_dp,
+                                      int D, int off, int w, float* __restrict__ out) {
+  const int64_t pos = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (pos >= n) return;
+  const int key = keys[pos];
+  if (pos > 0 && keys[pos - 1] == key) return;
+  for (int d0 = 0; d0 < w; d0 += 32) {
+    const int d = d0 + lane;
+    float acc = 0.f;
+    for (int64_t i = pos; i < n && keys[i] == key; ++i) {
+      const uint32_t s = src[i];
+      const float* row = (s < n_cells) ? ws_dq + (size_t)s * D : ws_dp + (size_t)(s - n_cells) * D;
+      if (d < w) acc += row[off + d];
+    }
+    if (d < w) out[(size_t)key * w + d] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct BwdLayout {
+  size_t dq, dp, part, keys[6], cub, total;
+  int grid, stride;
+  size_t cub_bytes;
+};
+
+static int bwd_grid() { return 148 * 2; }
+
+static BwdLayout bwd_layout(const NaisParams& p, int64_t B, int H) {
+  BwdLayout L;
+  int D = 0;
+  for (int i = 0; i < p.n_branch; ++i) D = D > p.branch[i].w_poi + p.branch[i].w_reg ? D : p.branch[i].w_poi + p.branch[i].w_reg;
+  const int lanes = p.dist_mode == NAIS_DIST_LATLON ? 2 : 0;
+  const int64_t n_cells = B * H, n_max = n_cells + B;
+  size_t o = 0;
+  L.dq = o;
+  o += align_up((size_t)n_cells * D * 4);
+  L.dp = o;
+  o += align_up((size_t)B * D * 4);
+  L.grid = bwd_grid();
+  L.stride = part_floats(p.hid, D, lanes);
+  L.part = o;
+  o += align_up((size_t)L.grid * L.stride * 4);
+  for (int i = 0; i < 6; ++i) {  // keys_in, vals_in, keys_out, vals_out (x1), sized for the largest list; reused
+    L.keys[i] = o;
+    o += align_up((size_t)n_max * 4);
+  }
+  size_t cb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cb, (const int*)nullptr, (int*)nullptr, (const uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, (int)(n_max > 0x7fffffff ? 0x7fffffff : n_max));
+  L.cub_bytes = cb;
+  L.cub = o;
+  o += align_up(cb);
+  L.total = o;
+  return L;
+}
+
+size_t pairs_bwd_workspace_bytes(const NaisParams& p, int64_t B, int H) { return bwd_layout(p, B, H).total; }
+
+template <int NKB, int DB>
+static int launch_bwd_tile(const BwdArgs& A, int D, int grid, cudaStream_t stream) {
+  constexpr int HP = NKB * KB;
+  const size_t fl = (size_t)D * TCP + (size_t)HP * TCP + (size_t)D * KB + NKB * 4 * KB + 8 * TC + 16 * HP +
+                    2 * (size_t)BWD_MAXROWS * D + 3 * BWD_MAXROWS + 8 * (NT / 32);
+  const size_t smem = fl * 4 + 3 * TC * 4;
+  cudaError_t e = cudaFuncSetAttribute(pairs_bwd_kernel<NKB, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  pairs_bwd_kernel<NKB, DB><<<grid, NT, smem, stream>>>(A);
+  NAIS_COUNT_LAUNCH(1);
+  return (int)cudaGetLastError();
+}
+
+int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score_parts, const float* row_sum,
+                     const float* dscore, const NaisGrads& g, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (b.B * (int64_t)b.H + b.B >= 0x7fffffffLL) return NAIS_ERR_SHAPE;
+  const BwdLayout L = bwd_layout(p, b.B, b.H);
+  if (ws_bytes < L.total) return NAIS_ERR_WORKSPACE;
+  char* base = reinterpret_cast<char*>(ws);
+  const int lanes = p.dist_mode == NAIS_DIST_LATLON ? 2 : 0;
+  const int64_t n_cells = b.B * (int64_t)b.H;
+  int* kin = reinterpret_cast<int*>(base + L.keys[0]);
+  uint32_t* vin = reinterpret_cast<uint32_t*>(base + L.keys[1]);
+  int* kout = reinterpret_cast<int*>(base + L.keys[2]);
+  uint32_t* vout = reinterpret_cast<uint32_t*>(base + L.keys[3]);
+  int* kin2 = reinterpret_cast<int*>(base + L.keys[4]);
+  uint32_t* vin2 = reinterpret_cast<uint32_t*>(base + L.keys[5]);
+
+  for (int bi = 0; bi < p.n_branch; ++bi) {
+    const NaisBranch& br = p.branch[bi];
+    const int D = br.w_poi + br.w_reg;
+    if (D > 128 || p.hid > 128) return NAIS_ERR_SHAPE;  // backward tiles: D, hid <= 128 in this version
+    BwdArgs A;
+    A.p = p;
+    A.b = b;
+    A.bi = bi;
+    A.parts = score_parts + (size_t)bi * b.B;
+    A.row_sum = row_sum + (size_t)bi * b.B;
+    A.dscore = dscore;
+    A.ws_dq = reinterpret_cast<float*>(base + L.dq);
+    A.ws_dp = reinterpret_cast<float*>(base + L.dp);
+    A.ws_part = reinterpret_cast<float*>(base + L.part);
+    A.part_stride = L.stride;
+    int rpt = (b.H <= TC) ? TC / b.H : 1;
+    if (rpt > BWD_MAXROWS) rpt = BWD_MAXROWS;
+    A.rows_per_tile = rpt;
+    A.n_items = (b.B + rpt - 1) / rpt;
+    int grid = (int)(A.n_items < L.grid ? A.n_items : L.grid);
+    int rc;
+    const int nkb = p.hid <= 64 ? 1 : 2, db = D <= 64 ? 1 : 2;
+    if (nkb == 1 && db == 1) rc = launch_bwd_tile<1, 1>(A, D, grid, stream);
+    else if (nkb == 1) rc = launch_bwd_tile<1, 2>(A, D, grid, stream);
+    else if (db == 1) rc = launch_bwd_tile<2, 1>(A, D, grid, stream);
+    else rc = launch_bwd_tile<2, 2>(A, D, grid, stream);
+    if (rc) return rc;
+    {
+      const int n = p.hid * (D + lanes) + 2 * p.hid + 7;
+      param_reduce_kernel<<<(n + 255) / 256, 256, 0, stream>>>(A.ws_part, grid, L.stride, p.hid, D, lanes, g.w1[bi], g.b1[bi],
+                                                              g.w2[bi], bi == 0 ? g.dist_w : nullptr,
+                                                              bi == 0 ? g.dist_b : nullptr,
+                                                              p.dist_mode == NAIS_DIST_KM ? g.dist_embed : nullptr, D, bi > 0);
+  NAIS_COUNT_LAUNCH(1);
+    }
+    // embedding rows
+    const bool want_hist = br.w_poi > 0 && g.hist_poi[bi];
+    const bool want_tgt = br.w_poi > 0 && g.tgt_poi[bi];
+    const bool want_reg = br.w_reg > 0 && g.reg[bi];
+    const int64_t n_thr = n_cells > b.B ? n_cells : b.B;
+    make_keys_kernel<<<(unsigned)((n_thr + 255) / 256), 256, 0, stream>>>(b, 0, want_hist ? kin : nullptr, vin,
+                                                                         want_tgt ? kin2 : nullptr, vin2,
+                                                                         nullptr, nullptr);
+  NAIS_COUNT_LAUNCH(1);
+    size_t cb = L.cub_bytes;
+    auto seg = [&](int* ki, uint32_t* vi, int64_t n, int off, int w, float* out, int bits) {
+      cub::DeviceRadixSort::SortPairs(base + L.cub, cb, ki, kout, vi, vout, (int)n, 0, bits, stream);
+      const int64_t threads = n * 32;
+      segment_reduce_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(kout, vout, n, n_cells, A.ws_dq, A.ws_dp, D,
+                                                                                  off, w, out);
+  NAIS_COUNT_LAUNCH(1);
+    };
+    auto bits_for = [](int n) { int bts = 1; while ((1ll << bts) < n && bts < 31) ++bts; return bts; };
+    if (want_hist) seg(kin, vin, n_cells, 0, br.w_poi, g.hist_poi[bi], bits_for(p.item_num));
+    if (want_tgt) seg(kin2, vin2, b.B, 0, br.w_poi, g.tgt_poi[bi], bits_for(p.item_num));
+    if (want_reg) {
+      make_keys_kernel<<<(unsigned)((n_thr + 255) / 256), 256, 0, stream>>>(b, 1, nullptr, nullptr, nullptr, nullptr, kin, vin);
+  NAIS_COUNT_LAUNCH(1);
+      seg(kin, vin, n_cells + b.B, br.w_poi, br.w_reg, g.reg[bi], bits_for(p.region_num));
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  return 0;
+}
+
+}  // namespace nais

@@ -1,0 +1,188 @@
+// extern "C" entry points of libnais_b200.so: argument validation + dispatch.  See include/nais_b200.h.
+#include <cstdio>
+
+#include "nais_common.cuh"
+
+namespace nais {
+// nais_fp32.cu
+int launch_pairs_fwd(const NaisParams& p, const NaisPairs& b, float* score, float* row_sum, float* parts, cudaStream_t stream);
+int launch_fullrank_fp32(const NaisParams& p, const NaisCatalog& cat, const NaisUsers& users, int64_t poi_begin,
+                         int64_t poi_end, int k, int exclude, float* out_score, int32_t* out_id, float* all_scores,
+                         void* ws, size_t ws_bytes, cudaStream_t stream);
+int launch_topk_merge(const unsigned long long* in_keys, const float* in_score, const int32_t* in_id, int n_users,
+                      int n_lists, int k, float* out_score, int32_t* out_id, cudaStream_t stream);
+int choose_splits(int n_users, int64_t range);
+// nais_bwd.cu
+size_t pairs_bwd_workspace_bytes(const NaisParams& p, int64_t B, int H);
+int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score_parts, const float* row_sum,
+                     const float* dscore, const NaisGrads& g, void* ws, size_t ws_bytes, cudaStream_t stream);
+// nais_tc.cu
+size_t fullrank_tc_workspace_bytes(const NaisParams& p, int n_users, int64_t nnz, int64_t poi_begin, int64_t poi_end, int k,
+                                   int precision);
+int launch_fullrank_tc(const NaisParams& p, const NaisCatalog& cat, const NaisUsers& users, int64_t poi_begin,
+                       int64_t poi_end, int k, int exclude, int precision, float* out_score, int32_t* out_id,
+                       float* all_scores, void* ws, size_t ws_bytes, cudaStream_t stream);
+bool tc_supported(const NaisParams& p);
+}  // namespace nais
+
+namespace nais { unsigned long long g_launches = 0; }
+using namespace nais;
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int check_params(const NaisParams* p) {
+  if (!p) return NAIS_ERR_NULL;
+  if (p->n_branch < 1 || p->n_branch > 2) return NAIS_ERR_SHAPE;
+  if (p->hid < 1 || p->hid > 1024 || p->item_num < 1) return NAIS_ERR_SHAPE;
+  if (p->dist_mode < NAIS_DIST_NONE || p->dist_mode > NAIS_DIST_KM) return NAIS_ERR_MODE;
+  for (int i = 0; i < p->n_branch; ++i) {
+    const NaisBranch& b = p->branch[i];
+    const int D = b.w_poi + b.w_reg;
+    if (b.w_poi < 0 || b.w_reg < 0 || D < 4 || D > MAXD || (D & 3)) return NAIS_ERR_SHAPE;
+    if (b.w_poi && (!b.hist_poi || !b.tgt_poi)) return NAIS_ERR_NULL;
+    if (b.w_reg && (!b.hist_reg || !b.tgt_reg || p->region_num < 1)) return NAIS_ERR_NULL;
+    if (!b.w1 || !b.b1 || !b.w2) return NAIS_ERR_NULL;
+  }
+  if (p->dist_mode == NAIS_DIST_LATLON && (!p->dist_w || !p->dist_b)) return NAIS_ERR_NULL;
+  if (p->dist_mode == NAIS_DIST_KM && (!p->dist_embed || p->dist_buckets < 1)) return NAIS_ERR_NULL;
+  if (p->dist_mode == NAIS_DIST_KM && p->dist_buckets > 1 && !(p->dist_bucket_km > 0.f)) return NAIS_ERR_MODE;
+  return 0;
+}
+
+static int check_pairs(const NaisParams* p, const NaisPairs* b) {
+  if (!b) return NAIS_ERR_NULL;
+  if (b->B < 0 || b->H < 1) return NAIS_ERR_SHAPE;
+  if (b->B == 0) return 0;
+  if (!b->hist || !b->tgt) return NAIS_ERR_NULL;
+  bool need_reg = false;
+  for (int i = 0; i < p->n_branch; ++i) need_reg |= p->branch[i].w_reg > 0;
+  if (need_reg && (!b->hreg || !b->treg)) return NAIS_ERR_NULL;
+  if (p->dist_mode != NAIS_DIST_NONE && !b->aux) return NAIS_ERR_NULL;
+  return 0;
+}
+
+extern "C" {
+
+int nais_abi_version(void) { return NAIS_ABI_VERSION; }
+uint64_t nais_launch_count(void) { return __atomic_load_n(&nais::g_launches, __ATOMIC_RELAXED); }
+
+const char* nais_strerror(int code) {
+  switch (code) {
+    case 0: return "ok";
+    case NAIS_ERR_NULL: return "nais: required pointer is NULL";
+    case NAIS_ERR_SHAPE: return "nais: unsupported or inconsistent dimension";
+    case NAIS_ERR_ALIGN: return "nais: pointer or row width not 16-byte aligned";
+    case NAIS_ERR_WORKSPACE: return "nais: workspace too small";
+    case NAIS_ERR_MODE: return "nais: unknown mode or unsupported flag combination";
+    case NAIS_ERR_ARCH: return "nais: tensor path needs an sm_100 device";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+  return "nais: unknown error";
+}
+
+int nais_pairs_forward(const NaisParams* p, const NaisPairs* batch, float* score, float* row_sum, float* score_parts,
+                       nais_stream_t stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  rc = check_pairs(p, batch);
+  if (rc) return rc;
+  if (batch->B && !score) return NAIS_ERR_NULL;
+  return launch_pairs_fwd(*p, *batch, score, row_sum, score_parts, static_cast<cudaStream_t>(stream));
+}
+
+size_t nais_pairs_backward_workspace_bytes(const NaisParams* p, int64_t B, int32_t H) {
+  if (check_params(p) || B < 0 || H < 1) return 0;
+  return pairs_bwd_workspace_bytes(*p, B, H);
+}
+
+int nais_pairs_backward(const NaisParams* p, const NaisPairs* batch, const float* score_parts, const float* row_sum,
+                        const float* dscore, const NaisGrads* grads, void* workspace, size_t workspace_bytes,
+                        nais_stream_t stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  rc = check_pairs(p, batch);
+  if (rc) return rc;
+  if (!grads) return NAIS_ERR_NULL;
+  if (batch->B == 0) return 0;
+  if (!score_parts || !row_sum || !dscore || !workspace) return NAIS_ERR_NULL;
+  if (!aligned16(workspace)) return NAIS_ERR_ALIGN;
+  if (workspace_bytes < pairs_bwd_workspace_bytes(*p, batch->B, batch->H)) return NAIS_ERR_WORKSPACE;
+  return launch_pairs_bwd(*p, *batch, score_parts, row_sum, dscore, *grads, workspace, workspace_bytes,
+                          static_cast<cudaStream_t>(stream));
+}
+
+static int check_fullrank(const NaisParams* p, const NaisCatalog* cat, const NaisUsers* users, int64_t poi_begin,
+                          int64_t poi_end, int precision) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  if (!cat || !users) return NAIS_ERR_NULL;
+  if (users->n_users < 0 || poi_begin < 0 || poi_end < poi_begin || poi_end > p->item_num) return NAIS_ERR_SHAPE;
+  if (poi_begin < cat->row_base || poi_end > cat->row_base + cat->n_rows) return NAIS_ERR_SHAPE;
+  if (users->n_users && (!users->offsets || !users->items)) return NAIS_ERR_NULL;
+  bool need_reg = false;
+  for (int i = 0; i < p->n_branch; ++i) need_reg |= p->branch[i].w_reg > 0;
+  const bool work = users->n_users > 0 && poi_end > poi_begin;
+  if (work && need_reg && (!cat->region || !users->region)) return NAIS_ERR_NULL;
+  if (work && p->dist_mode == NAIS_DIST_LATLON && (!cat->coords || !users->coords)) return NAIS_ERR_NULL;
+  if (p->dist_mode == NAIS_DIST_KM) return NAIS_ERR_MODE;  // fused haversine: next tier
+  if (precision < NAIS_PREC_FP32 || precision > NAIS_PREC_TC_FAST) return NAIS_ERR_MODE;
+  if (precision != NAIS_PREC_FP32 && !tc_supported(*p)) return NAIS_ERR_SHAPE;
+  return 0;
+}
+
+size_t nais_fullrank_workspace_bytes(const NaisParams* p, int32_t n_users, int64_t nnz, int64_t poi_begin,
+                                     int64_t poi_end, int32_t k, int32_t precision) {
+  if (check_params(p) || n_users < 0 || poi_end < poi_begin || k < 1) return 0;
+  if (precision != NAIS_PREC_FP32) return fullrank_tc_workspace_bytes(*p, n_users, nnz, poi_begin, poi_end, k, precision);
+  const int s = choose_splits(n_users, poi_end - poi_begin);
+  return 1024 + (size_t)n_users * 8 + (s > 1 ? (size_t)n_users * s * k * sizeof(unsigned long long) : 0);
+}
+
+int nais_fullrank_topk(const NaisParams* p, const NaisCatalog* cat, const NaisUsers* users, int64_t poi_begin,
+                       int64_t poi_end, int32_t k, int32_t exclude_history, int32_t precision, float* out_score,
+                       int32_t* out_id, void* workspace, size_t workspace_bytes, nais_stream_t stream) {
+  int rc = check_fullrank(p, cat, users, poi_begin, poi_end, precision);
+  if (rc) return rc;
+  if (k < 1 || k > KCAP) return NAIS_ERR_SHAPE;
+  if (users->n_users && (!out_score || !out_id || !workspace)) return NAIS_ERR_NULL;
+  if (!aligned16(workspace)) return NAIS_ERR_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (precision == NAIS_PREC_FP32)
+    return launch_fullrank_fp32(*p, *cat, *users, poi_begin, poi_end, k, exclude_history, out_score, out_id, nullptr,
+                                workspace, workspace_bytes, st);
+  return launch_fullrank_tc(*p, *cat, *users, poi_begin, poi_end, k, exclude_history, precision, out_score, out_id,
+                            nullptr, workspace, workspace_bytes, st);
+}
+
+int nais_fullrank_scores(const NaisParams* p, const NaisCatalog* cat, const NaisUsers* users, int64_t poi_begin,
+                         int64_t poi_end, int32_t precision, float* all_scores, void* workspace,
+                         size_t workspace_bytes, nais_stream_t stream) {
+  int rc = check_fullrank(p, cat, users, poi_begin, poi_end, precision);
+  if (rc) return rc;
+  if (users->n_users && (!all_scores || !workspace)) return NAIS_ERR_NULL;
+  if (!aligned16(workspace)) return NAIS_ERR_ALIGN;
+  // top-1 lists are produced into the head of the workspace and ignored
+  const size_t head = ((size_t)users->n_users * (sizeof(float) + sizeof(int32_t)) + 255) & ~size_t(255);
+  if (workspace_bytes < head) return NAIS_ERR_WORKSPACE;
+  float* sc = reinterpret_cast<float*>(workspace);
+  int32_t* id = reinterpret_cast<int32_t*>(sc + users->n_users);
+  char* rest = reinterpret_cast<char*>(workspace) + head;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (precision == NAIS_PREC_FP32)
+    return launch_fullrank_fp32(*p, *cat, *users, poi_begin, poi_end, 1, 0, sc, id, all_scores, rest,
+                                workspace_bytes - head, st);
+  return launch_fullrank_tc(*p, *cat, *users, poi_begin, poi_end, 1, 0, precision, sc, id, all_scores, rest,
+                            workspace_bytes - head, st);
+}
+
+int nais_topk_merge(const float* in_score, const int32_t* in_id, int32_t n_users, int32_t n_lists, int32_t k,
+                    float* out_score, int32_t* out_id, nais_stream_t stream) {
+  if (n_users < 0 || n_lists < 1 || k < 1) return NAIS_ERR_SHAPE;
+  if (n_users == 0) return 0;
+  if (!in_score || !in_id || !out_score || !out_id) return NAIS_ERR_NULL;
+  return launch_topk_merge(nullptr, in_score, in_id, n_users, n_lists, k, out_score, out_id,
+                           static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// Shared device helpers for the NAIS kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nais_b200.h"
+
+namespace nais {
+
+// launch counter (diagnostic): every kernel launch of the library goes through NAIS_COUNT_LAUNCH
+extern unsigned long long g_launches;
+#define NAIS_COUNT_LAUNCH(n) (__atomic_fetch_add(&::nais::g_launches, (unsigned long long)(n), __ATOMIC_RELAXED))
+
+constexpr int TC = 128;   // cells (history item x candidate pairs) per tile of the FP32 tile-GEMM
+constexpr int TCP = 132;  // padded cell stride of cell-major smem rows (16B-aligned, breaks bank regularity)
+constexpr int KB = 64;    // hidden units per k-block
+constexpr int NT = 256;   // threads per CTA of the FP32 kernels
+constexpr int HC = 32;    // history rows staged in smem per chunk
+constexpr int KCAP = 128; // max k of the fused top-k
+constexpr int MAXD = 256; // max embed_size
+
+// Order-preserving float -> uint32 (larger float => larger uint).  NaN is mapped to -inf by the callers.
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+// Ranking key: score descending, then POI id ascending.  0 = "no candidate".
+__device__ __forceinline__ unsigned long long make_key(float score, int id) {
+  if (score != score) score = -INFINITY;
+  return ((unsigned long long)f2ord(score) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)id);
+}
+__device__ __forceinline__ void split_key(unsigned long long key, float& score, int& id) {
+  if (key == 0ull) {
+    score = -INFINITY;
+    id = -1;
+  } else {
+    score = ord2f((uint32_t)(key >> 32));
+    id = (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+  }
+}
+
+// Descending bitonic sort of n (power of two) keys in shared memory by all threads of the CTA.
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long* buf, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          unsigned long long a = buf[i], b = buf[ixj];
+          bool desc_half = ((i & k) == 0);
+          if (desc_half ? (a < b) : (a > b)) {
+            buf[i] = b;
+            buf[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ float sigmoidf_exact(float z) { return 1.0f / (1.0f + expf(-z)); }
+
+// Great-circle km from centred coordinates, haversine form (well conditioned in fp32 for short distances; equals the
+// reference's law-of-cosines value powerLaw.py:7-21 mathematically, incl. its 1e-6 short-circuit).
+__device__ __forceinline__ float dist_km_f(float lat1, float lon1, float lat2, float lon2, float coslat1, float coslat2) {
+  float dlat = lat1 - lat2, dlon = lon1 - lon2;
+  if (fabsf(dlat) < 1e-6f && fabsf(dlon) < 1e-6f) return 0.f;
+  const float d2r = 0.017453292519943295f;
+  float sa = sinf(0.5f * dlat * d2r), sb = sinf(0.5f * dlon * d2r);
+  float h = sa * sa + coslat1 * coslat2 * sb * sb;
+  return 2.f * 6371.f * asinf(fminf(1.f, sqrtf(h)));
+}
+
+}  // namespace nais

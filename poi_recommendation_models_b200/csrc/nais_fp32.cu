@@ -1,0 +1,578 @@
+// FP32 (CUDA-core FFMA) NAIS kernels: the numerically exact path.
+//
+//   tile_logits      shared tile-GEMM: for 128 cells, a_c = sum_k v_k relu(sum_d W[k,d] x_c[d] + b_k + wd.g_c)
+//   pairs_fwd        explicit (history row, target) pairs      (model.py:246-297 and siblings)
+//   fullrank_fp32    user x catalogue-range scoring + fused block top-k (validation.py:84-127)
+//   topk_merge       merge of per-split / per-shard top-k lists
+//
+// The B x H x (D+2) pair tensor of the reference (model.py:266-269) only ever exists as one 128-cell tile in
+// shared memory.
+#include "nais_common.cuh"
+
+namespace nais {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Shared-memory carve-up common to the tile kernels
+// ---------------------------------------------------------------------------------------------------------------------
+struct TileSmem {
+  float* As;  // [D][TCP]  x = q (.) p per cell, d-major
+  float* Wt;  // [D][KB]   attn_layer1.weight^T, current k-block (x part only)
+  float* kc;  // [4][KB]   b1, w2, w1[:,D], w1[:,D+1] of the current k-block
+  float* g;   // [2][TC]   distance lanes per cell (LATLON) / logit bias in g[0] (KM)
+  float* sp;  // [2][TC]   similarity partial sums of the two d-halves
+  float* a;   // [TC]      logits out
+};
+__host__ __device__ inline size_t tile_smem_floats(int D) { return (size_t)D * TCP + (size_t)D * KB + 4 * KB + 5 * TC; }
+__device__ inline float* carve_tile(float* base, int D, TileSmem& s) {
+  s.As = base;
+  base += (size_t)D * TCP;
+  s.Wt = base;
+  base += (size_t)D * KB;
+  s.kc = base;
+  base += 4 * KB;
+  s.g = base;
+  base += 2 * TC;
+  s.sp = base;
+  base += 2 * TC;
+  s.a = base;
+  base += TC;
+  return base;
+}
+
+// Load k-block kb of branch br: Wt[d][kk] = w1[kb*KB+kk][d], constants; zero padding beyond hid.
+__device__ inline void load_wblock(const NaisBranch& br, int hid, int D, int lanes, int kb, const TileSmem& s) {
+  const int ldw = D + lanes;
+  for (int i = threadIdx.x; i < D * KB; i += blockDim.x) {
+    int kk = i / D, d = i - kk * D;
+    int k = kb * KB + kk;
+    s.Wt[d * KB + kk] = (k < hid) ? __ldg(br.w1 + (size_t)k * ldw + d) : 0.f;
+  }
+  for (int kk = threadIdx.x; kk < KB; kk += blockDim.x) {
+    int k = kb * KB + kk;
+    bool ok = k < hid;
+    s.kc[kk] = ok ? __ldg(br.b1 + k) : 0.f;
+    s.kc[KB + kk] = ok ? __ldg(br.w2 + k) : 0.f;
+    s.kc[2 * KB + kk] = (ok && lanes) ? __ldg(br.w1 + (size_t)k * ldw + D) : 0.f;
+    s.kc[3 * KB + kk] = (ok && lanes) ? __ldg(br.w1 + (size_t)k * ldw + D + 1) : 0.f;
+  }
+}
+
+// One k-block of the tile GEMM + MLP epilogue.  Thread (tj = tid/16, tk = tid%16) owns cells tj*8..+7 and hidden
+// units tk*4..+3 of the block; a_part[i] accumulates sum_k v_k relu(t_k) over this thread's hidden units.
+__device__ __forceinline__ void tile_kblock(const TileSmem& s, int D, bool lanes, float (&a_part)[8]) {
+  const int tk = threadIdx.x & 15, tj = threadIdx.x >> 4;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+  const float* ap = s.As + tj * 8;
+  const float* bp = s.Wt + tk * 4;
+#pragma unroll 4
+  for (int d = 0; d < D; ++d) {
+    float4 a0 = *reinterpret_cast<const float4*>(ap + d * TCP);
+    float4 a1 = *reinterpret_cast<const float4*>(ap + d * TCP + 4);
+    float4 b = *reinterpret_cast<const float4*>(bp + d * KB);
+    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(av[i], bv[c], acc[i][c]);
+  }
+  const float4 bb = *reinterpret_cast<const float4*>(s.kc + tk * 4);
+  const float4 vv = *reinterpret_cast<const float4*>(s.kc + KB + tk * 4);
+  const float4 w0 = *reinterpret_cast<const float4*>(s.kc + 2 * KB + tk * 4);
+  const float4 w1 = *reinterpret_cast<const float4*>(s.kc + 3 * KB + tk * 4);
+  const float bbv[4] = {bb.x, bb.y, bb.z, bb.w}, vvv[4] = {vv.x, vv.y, vv.z, vv.w};
+  const float w0v[4] = {w0.x, w0.y, w0.z, w0.w}, w1v[4] = {w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float g0 = 0.f, g1 = 0.f;
+    if (lanes) {
+      g0 = s.g[tj * 8 + i];
+      g1 = s.g[TC + tj * 8 + i];
+    }
+    float r = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float t = acc[i][c] + bbv[c];
+      if (lanes) t = fmaf(w1v[c], g1, fmaf(w0v[c], g0, t));
+      r = fmaf(vvv[c], fmaxf(t, 0.f), r);
+    }
+    a_part[i] += r;
+  }
+}
+
+// Whole MLP for the tile currently in s.As / s.g: writes s.a[cell].  `resident_kb` says which (branch,kb) block is
+// already in s.Wt (updated).  All threads must call; ends with a __syncthreads().
+__device__ inline void tile_logits(const NaisBranch& br, int br_idx, int hid, int D, int lanes, const TileSmem& s,
+                                   int& resident) {
+  const int n_kb = (hid + KB - 1) / KB;
+  float a_part[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a_part[i] = 0.f;
+  for (int kb = 0; kb < n_kb; ++kb) {
+    const int want = br_idx * 1024 + kb;
+    if (resident != want) {
+      __syncthreads();  // previous users of Wt are done
+      load_wblock(br, hid, D, lanes, kb, s);
+      resident = want;
+      __syncthreads();
+    }
+    tile_kblock(s, D, lanes != 0, a_part);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float v = a_part[i];
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    a_part[i] = v;
+  }
+  if ((threadIdx.x & 15) == 0) {
+    const int tj = threadIdx.x >> 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s.a[tj * 8 + i] = a_part[i];
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void dist_lanes(const NaisParams& p, float dlat, float dlon, float& g0, float& g1) {
+  const float l0 = dlat * p.dist_scale, l1 = dlon * p.dist_scale;
+  const float z0 = fmaf(l1, __ldg(p.dist_w + 1), fmaf(l0, __ldg(p.dist_w + 0), __ldg(p.dist_b + 0)));
+  const float z1 = fmaf(l1, __ldg(p.dist_w + 3), fmaf(l0, __ldg(p.dist_w + 2), __ldg(p.dist_b + 1)));
+  g0 = sigmoidf_exact(z0);
+  g1 = sigmoidf_exact(z1);
+}
+
+__device__ __forceinline__ float km_coef(const NaisParams& p, int D, float km) {
+  // sum_d embed_distance[bucket, d]   (model.py:497-501; the reference only has bucket 0)
+  int b = 0;
+  if (p.dist_buckets > 1) b = min((int)floorf(km / p.dist_bucket_km), p.dist_buckets - 1);
+  float c = 0.f;
+  for (int d = 0; d < D; ++d) c += __ldg(p.dist_embed + (size_t)b * D + d);
+  return c;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Explicit pairs: forward
+// ---------------------------------------------------------------------------------------------------------------------
+struct PairsFwdArgs {
+  NaisParams p;
+  NaisPairs b;
+  float* score;    // [B]
+  float* row_sum;  // [n_branch,B] or NULL
+  float* parts;    // [n_branch,B] per-branch score or NULL
+  int rows_per_tile;
+};
+
+constexpr int MAXROWS = 16;  // rows (targets) sharing one 128-cell tile when H is small
+
+__global__ void __launch_bounds__(NT, 2) pairs_fwd_kernel(const __grid_constant__ PairsFwdArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  const NaisParams& p = A.p;
+  const int H = A.b.H;
+  const int lanes = (p.dist_mode == NAIS_DIST_LATLON) ? 2 : 0;
+  int Dmax = 0;
+  for (int i = 0; i < p.n_branch; ++i) Dmax = max(Dmax, p.branch[i].w_poi + p.branch[i].w_reg);
+  TileSmem s;
+  float* rest = carve_tile(smem, Dmax, s);
+  float* ps = rest;                        // [MAXROWS][Dmax] target vectors of the rows in this tile
+  float* red_e = ps + MAXROWS * Dmax;      // [TC] masked exp per cell
+  float* red_es = red_e + TC;              // [TC] masked exp * similarity
+  float* row_e = red_es + TC;              // [MAXROWS] running sum E
+  float* row_es = row_e + MAXROWS;         // [MAXROWS] running sum E*s
+  __shared__ float km_c;
+
+  const int64_t row0 = (int64_t)blockIdx.x * A.rows_per_tile;
+  const int nrows = (int)min((int64_t)A.rows_per_tile, A.b.B - row0);
+  const int n_chunks = (H <= TC) ? 1 : (H + TC - 1) / TC;
+  const int tid = threadIdx.x, cell = tid & (TC - 1), half = tid >> 7;
+  int resident = -1;
+  float my_total = 0.f;  // thread r (< nrows) accumulates the final score of row r over branches
+
+  for (int bi = 0; bi < p.n_branch; ++bi) {
+    const NaisBranch& br = p.branch[bi];
+    const int D = br.w_poi + br.w_reg;
+    if (p.dist_mode == NAIS_DIST_KM && p.dist_buckets == 1) {
+      if (tid == 0) km_c = km_coef(p, D, 0.f);
+    }
+    __syncthreads();
+    // target vectors
+    for (int i = tid; i < nrows * D; i += NT) {
+      int r = i / D, d = i - r * D;
+      int64_t t = A.b.tgt[row0 + r];
+      ps[r * Dmax + d] = (d < br.w_poi) ? __ldg(br.tgt_poi + (size_t)t * br.w_poi + d)
+                                        : __ldg(br.tgt_reg + (size_t)A.b.treg[row0 + r] * br.w_reg + (d - br.w_poi));
+    }
+    if (tid < MAXROWS) {
+      row_e[tid] = 0.f;
+      row_es[tid] = 0.f;
+    }
+    __syncthreads();
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      // cell -> (row, h)
+      int r, h;
+      bool valid;
+      if (H <= TC) {
+        r = cell / H;
+        h = cell - r * H;
+        valid = r < nrows;
+      } else {
+        r = 0;
+        h = ch * TC + cell;
+        valid = h < H;
+      }
+      const int64_t cidx = valid ? (row0 + r) * (int64_t)H + h : 0;
+      // build x = q (.) p for this thread's d-half, similarity partial, distance lanes
+      {
+        const int d0 = half ? (D >> 1) : 0, d1 = half ? D : (D >> 1);
+        float ssum = 0.f;
+        if (valid) {
+          const int64_t item = A.b.hist[cidx];
+          const int64_t reg = br.w_reg ? A.b.hreg[cidx] : 0;
+          const float* qp = br.hist_poi + (size_t)item * br.w_poi;
+          const float* qr = br.hist_reg + (size_t)reg * br.w_reg;
+          for (int d = d0; d < d1; ++d) {
+            float q = (d < br.w_poi) ? __ldg(qp + d) : __ldg(qr + d - br.w_poi);
+            float x = q * ps[r * Dmax + d];
+            s.As[d * TCP + cell] = x;
+            ssum += x;
+          }
+        } else {
+          for (int d = d0; d < d1; ++d) s.As[d * TCP + cell] = 0.f;
+        }
+        s.sp[half * TC + cell] = ssum;
+        if (half == 0) {
+          float g0 = 0.f, g1 = 0.f;
+          if (valid && p.dist_mode == NAIS_DIST_LATLON) {
+            dist_lanes(p, A.b.aux[cidx * 2], A.b.aux[cidx * 2 + 1], g0, g1);
+          } else if (valid && p.dist_mode == NAIS_DIST_KM) {
+            float km = A.b.aux[cidx];
+            g0 = km * (p.dist_buckets == 1 ? km_c : km_coef(p, D, km));
+          }
+          s.g[cell] = g0;
+          s.g[TC + cell] = g1;
+        }
+      }
+      __syncthreads();
+      tile_logits(br, bi, p.hid, D, lanes, s, resident);
+      if (tid < TC) {
+        float e = 0.f, es = 0.f;
+        if (valid) {
+          float a = s.a[cell];
+          if (p.dist_mode == NAIS_DIST_KM) a += s.g[cell];
+          const bool m = A.b.hist[cidx] != A.b.tgt[row0 + r];
+          e = m ? expf(a) : 0.f;
+          es = e * (s.sp[cell] + s.sp[TC + cell]);
+          if (!m) es = 0.f;  // exp overflow * 0 must stay 0, like the reference's exp_A * mask then * history
+        }
+        red_e[cell] = e;
+        red_es[cell] = es;
+      }
+      __syncthreads();
+      // row reductions: warp w handles rows w, w+8, ...
+      {
+        const int w = tid >> 5, lane = tid & 31;
+        for (int rr = w; rr < ((H <= TC) ? nrows : 1); rr += NT / 32) {
+          const int c0 = (H <= TC) ? rr * H : 0;
+          const int cn = (H <= TC) ? H : min(TC, H - ch * TC);
+          float e = 0.f, es = 0.f;
+          for (int c = lane; c < cn; c += 32) {
+            e += red_e[c0 + c];
+            es += red_es[c0 + c];
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            e += __shfl_xor_sync(0xffffffffu, e, o);
+            es += __shfl_xor_sync(0xffffffffu, es, o);
+          }
+          if (lane == 0) {
+            row_e[rr] += e;
+            row_es[rr] += es;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (tid < nrows) {
+      const float S = row_e[tid];
+      const float sc = row_es[tid] / powf(S, p.beta);
+      my_total += sc;
+      if (A.row_sum) A.row_sum[(size_t)bi * A.b.B + row0 + tid] = S;
+      if (A.parts) A.parts[(size_t)bi * A.b.B + row0 + tid] = sc;
+    }
+    __syncthreads();
+  }
+  if (tid < nrows) A.score[row0 + tid] = my_total;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Full-rank scoring + fused block top-k (FP32)
+// ---------------------------------------------------------------------------------------------------------------------
+struct FullrankArgs {
+  NaisParams p;
+  NaisCatalog cat;
+  NaisUsers users;
+  int64_t poi_begin, poi_end;
+  int k;
+  int exclude;
+  int n_splits;
+  unsigned long long* part_keys;  // [n_users, n_splits, k] (n_splits > 1)
+  float* out_score;               // [n_users, k]           (n_splits == 1)
+  int32_t* out_id;
+  float* all_scores;  // optional [n_users, poi_end - poi_begin]
+};
+
+__global__ void __launch_bounds__(NT, 2) fullrank_fp32_kernel(const __grid_constant__ FullrankArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  const NaisParams& p = A.p;
+  const int lanes = (p.dist_mode == NAIS_DIST_LATLON) ? 2 : 0;
+  int Dmax = 0;
+  for (int i = 0; i < p.n_branch; ++i) Dmax = max(Dmax, p.branch[i].w_poi + p.branch[i].w_reg);
+  TileSmem s;
+  float* rest = carve_tile(smem, Dmax, s);
+  float* Ps = rest;                                 // [Dmax][TCP] candidate vectors, d-major
+  float* Qs = Ps + (size_t)Dmax * TCP;              // [HC][Dmax]  history vectors of the current chunk
+  int* hid_s = reinterpret_cast<int*>(Qs + HC * Dmax);  // [HC] history item ids
+  float* hco = reinterpret_cast<float*>(hid_s + HC);    // [HC][2] history coords
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(hco + 2 * HC);  // [2*KCAP]
+
+  const int u = blockIdx.x, split = blockIdx.y;
+  const int64_t h_begin = A.users.offsets[u];
+  const int H = (int)(A.users.offsets[u + 1] - h_begin);
+  const int64_t range = A.poi_end - A.poi_begin;
+  const int n_tiles = (int)((range + TC - 1) / TC);
+  const int tid = threadIdx.x, cell = tid & (TC - 1), half = tid >> 7;
+  int resident = -1;
+
+  for (int i = tid; i < 2 * KCAP; i += NT) keys[i] = 0ull;
+  __syncthreads();
+
+  for (int tile = split; tile < n_tiles; tile += A.n_splits) {
+    const int64_t j = A.poi_begin + (int64_t)tile * TC + cell;  // global POI id of this thread's cell
+    const bool jvalid = j < A.poi_end;
+    const int64_t jl = j - A.cat.row_base;
+    float cla = 0.f, clo = 0.f;
+    if (jvalid && lanes) {
+      cla = __ldg(A.cat.coords + jl * 2);
+      clo = __ldg(A.cat.coords + jl * 2 + 1);
+    }
+    float score = 0.f;
+    bool excluded = false;
+    for (int bi = 0; bi < p.n_branch; ++bi) {
+      const NaisBranch& br = p.branch[bi];
+      const int D = br.w_poi + br.w_reg;
+      // candidate tile, d-major
+      __syncthreads();
+      {
+        const int d0 = half ? (D >> 1) : 0, d1 = half ? D : (D >> 1);
+        if (jvalid) {
+          const float* pp = br.tgt_poi + (size_t)j * br.w_poi;
+          const float* pr = br.w_reg ? br.tgt_reg + (size_t)__ldg(A.cat.region + jl) * br.w_reg : nullptr;
+          for (int d = d0; d < d1; ++d)
+            Ps[d * TCP + cell] = (d < br.w_poi) ? __ldg(pp + d) : __ldg(pr + d - br.w_poi);
+        } else {
+          for (int d = d0; d < d1; ++d) Ps[d * TCP + cell] = 0.f;
+        }
+      }
+      float sumE = 0.f, sumES = 0.f;
+      for (int h0 = 0; h0 < H; h0 += HC) {
+        const int hn = min(HC, H - h0);
+        __syncthreads();
+        for (int i = tid; i < hn * D; i += NT) {
+          int hh = i / D, d = i - hh * D;
+          const int64_t e = h_begin + h0 + hh;
+          Qs[hh * Dmax + d] = (d < br.w_poi)
+                                  ? __ldg(br.hist_poi + (size_t)__ldg(A.users.items + e) * br.w_poi + d)
+                                  : __ldg(br.hist_reg + (size_t)__ldg(A.users.region + e) * br.w_reg + (d - br.w_poi));
+        }
+        if (tid < hn) {
+          const int64_t e = h_begin + h0 + tid;
+          hid_s[tid] = __ldg(A.users.items + e);
+          if (lanes) {
+            hco[2 * tid] = __ldg(A.users.coords + 2 * e);
+            hco[2 * tid + 1] = __ldg(A.users.coords + 2 * e + 1);
+          }
+        }
+        __syncthreads();
+        for (int hh = 0; hh < hn; ++hh) {
+          {
+            const int d0 = half ? (D >> 1) : 0, d1 = half ? D : (D >> 1);
+            const float* q = Qs + hh * Dmax;
+            float ssum = 0.f;
+            for (int d = d0; d < d1; ++d) {
+              float x = Ps[d * TCP + cell] * q[d];
+              s.As[d * TCP + cell] = x;
+              ssum += x;
+            }
+            s.sp[half * TC + cell] = ssum;
+            if (half == 0 && lanes) {
+              float g0, g1;
+              dist_lanes(p, fabsf(cla - hco[2 * hh]), fabsf(clo - hco[2 * hh + 1]), g0, g1);
+              s.g[cell] = g0;
+              s.g[TC + cell] = g1;
+            }
+          }
+          __syncthreads();
+          tile_logits(br, bi, p.hid, D, lanes, s, resident);
+          if (tid < TC) {
+            const bool m = (int64_t)hid_s[hh] != j;
+            if (m) {
+              const float e = expf(s.a[cell]);
+              sumE += e;
+              sumES = fmaf(e, s.sp[cell] + s.sp[TC + cell], sumES);
+            } else {
+              excluded = true;
+            }
+          }
+          // next iteration's As writes are ordered after this read of s.a/s.sp by the barrier inside tile_logits
+          // of the NEXT call only for Wt; As/sp/g are rewritten immediately -> barrier here.
+          __syncthreads();
+        }
+      }
+      if (tid < TC) score += sumES / powf(sumE, p.beta);
+    }
+    if (tid < TC) {
+      if (A.all_scores && jvalid) A.all_scores[(size_t)u * range + (j - A.poi_begin)] = score;
+      const bool keep = jvalid && !(A.exclude && excluded);
+      keys[KCAP + cell] = keep ? make_key(score, (int)j) : 0ull;
+    }
+    __syncthreads();
+    bitonic_sort_desc(keys, 2 * KCAP);
+  }
+  // emit
+  if (A.n_splits == 1) {
+    for (int i = tid; i < A.k; i += NT) {
+      float sc;
+      int id;
+      split_key(keys[i], sc, id);
+      A.out_score[(size_t)u * A.k + i] = sc;
+      A.out_id[(size_t)u * A.k + i] = id;
+    }
+  } else {
+    for (int i = tid; i < A.k; i += NT) A.part_keys[((size_t)u * A.n_splits + split) * A.k + i] = keys[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Top-k merge: n_lists lists of k per user -> k
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void topk_merge_kernel(const unsigned long long* in_keys, const float* in_score, const int32_t* in_id,
+                                  int n_lists, int k, int n_pow2, float* out_score, int32_t* out_id) {
+  extern __shared__ __align__(16) unsigned long long mkeys[];
+  const int u = blockIdx.x, n = n_lists * k;
+  for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+    unsigned long long key = 0ull;
+    if (i < n) {
+      if (in_keys) {
+        key = in_keys[(size_t)u * n + i];
+      } else {
+        const int id = in_id[(size_t)u * n + i];
+        if (id >= 0) key = make_key(in_score[(size_t)u * n + i], id);
+      }
+    }
+    mkeys[i] = key;
+  }
+  __syncthreads();
+  bitonic_sort_desc(mkeys, n_pow2);
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    float sc;
+    int id;
+    split_key(mkeys[i], sc, id);
+    out_score[(size_t)u * k + i] = sc;
+    out_id[(size_t)u * k + i] = id;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Host launchers (called from nais_capi.cu)
+// ---------------------------------------------------------------------------------------------------------------------
+static int max_D(const NaisParams& p) {
+  int D = 0;
+  for (int i = 0; i < p.n_branch; ++i) D = D > p.branch[i].w_poi + p.branch[i].w_reg ? D : p.branch[i].w_poi + p.branch[i].w_reg;
+  return D;
+}
+
+int launch_pairs_fwd(const NaisParams& p, const NaisPairs& b, float* score, float* row_sum, float* parts,
+                     cudaStream_t stream) {
+  if (b.B == 0) return 0;
+  PairsFwdArgs A;
+  A.p = p;
+  A.b = b;
+  A.score = score;
+  A.row_sum = row_sum;
+  A.parts = parts;
+  int rpt = (b.H <= TC) ? TC / b.H : 1;
+  if (rpt > MAXROWS) rpt = MAXROWS;
+  A.rows_per_tile = rpt;
+  const int D = max_D(p);
+  const size_t smem = (tile_smem_floats(D) + (size_t)MAXROWS * D + 2 * TC + 2 * MAXROWS) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(pairs_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int64_t grid = (b.B + rpt - 1) / rpt;
+  pairs_fwd_kernel<<<(unsigned)grid, NT, smem, stream>>>(A);
+  NAIS_COUNT_LAUNCH(1);
+  return (int)cudaGetLastError();
+}
+
+size_t fullrank_fp32_smem(const NaisParams& p) {
+  const int D = max_D(p);
+  return (tile_smem_floats(D) + (size_t)D * TCP + (size_t)HC * D + 3 * HC) * sizeof(float) + 2 * KCAP * sizeof(unsigned long long) + 16;
+}
+
+int choose_splits(int n_users, int64_t range) {
+  const int n_tiles = (int)((range + TC - 1) / TC);
+  int s = (148 * 2 * 4 + n_users - 1) / (n_users > 0 ? n_users : 1);
+  if (s > 32) s = 32;
+  if (s > n_tiles) s = n_tiles;
+  if (s < 1) s = 1;
+  return s;
+}
+
+int launch_topk_merge(const unsigned long long* in_keys, const float* in_score, const int32_t* in_id, int n_users,
+                      int n_lists, int k, float* out_score, int32_t* out_id, cudaStream_t stream) {
+  if (n_users == 0) return 0;
+  int n = n_lists * k, n2 = 1;
+  while (n2 < n) n2 <<= 1;
+  if (n2 > 4096) return NAIS_ERR_SHAPE;
+  const int threads = n2 >= 512 ? 512 : (n2 < 64 ? 64 : n2);
+  topk_merge_kernel<<<n_users, threads, n2 * sizeof(unsigned long long), stream>>>(in_keys, in_score, in_id, n_lists, k, n2,
+                                                                                  out_score, out_id);
+  NAIS_COUNT_LAUNCH(1);
+  return (int)cudaGetLastError();
+}
+
+int launch_fullrank_fp32(const NaisParams& p, const NaisCatalog& cat, const NaisUsers& users, int64_t poi_begin,
+                         int64_t poi_end, int k, int exclude, float* out_score, int32_t* out_id, float* all_scores,
+                         void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (users.n_users == 0 || poi_end <= poi_begin) return 0;
+  FullrankArgs A;
+  A.p = p;
+  A.cat = cat;
+  A.users = users;
+  A.poi_begin = poi_begin;
+  A.poi_end = poi_end;
+  A.k = k;
+  A.exclude = exclude;
+  A.n_splits = choose_splits(users.n_users, poi_end - poi_begin);
+  A.out_score = out_score;
+  A.out_id = out_id;
+  A.all_scores = all_scores;
+  A.part_keys = reinterpret_cast<unsigned long long*>(ws);
+  if (A.n_splits > 1 && ws_bytes < (size_t)users.n_users * A.n_splits * k * sizeof(unsigned long long)) return NAIS_ERR_WORKSPACE;
+  const size_t smem = fullrank_fp32_smem(p);
+  cudaError_t e = cudaFuncSetAttribute(fullrank_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid(users.n_users, A.n_splits);
+  fullrank_fp32_kernel<<<grid, NT, smem, stream>>>(A);
+  NAIS_COUNT_LAUNCH(1);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  if (A.n_splits > 1) return launch_topk_merge(A.part_keys, nullptr, nullptr, users.n_users, A.n_splits, k, out_score, out_id, stream);
+  return 0;
+}
+
+}  // namespace nais

@@ -1,0 +1,238 @@
+"""Drop-in mirror of the reference's NAIS classes (`/root/reference/model.py`), backed by libnais_b200.so.
+
+Same class names, constructor arguments, `forward` / `attention_network` / `get_mask` / `loss_function` signatures,
+attributes (`embed_size, item_num, beta, hidden_size, loss_func`) and `state_dict` keys as
+
+    NAIS_basic                                   model.py:8-97
+    NAIS_regionEmbedding                         model.py:99-187
+    NAIS_region_distance_Embedding               model.py:189-304     <- the parity target (run.py:222)
+    NAIS_distance_Embedding                      model.py:306-408
+    NAIS_region_distance_disentangled_Embedding  model.py:410-541
+
+so `torch.optim.Adagrad(model.parameters())`, `model.train()/eval()`, `torch.save(model)`, and loading a reference
+checkpoint's `state_dict` all work unchanged.  The submodules are created and initialised in the reference's order, so
+the same `torch.manual_seed` gives the same initial weights.  What differs is what runs: `attention_network` is one
+fused CUDA kernel (plus hand-written backward kernels) instead of ~25 ATen ops, and there is an additional
+`predict_topk` entry that replaces the whole per-user loop of `validation.py:84-127`.
+
+There is no CPU path: calling a model whose parameters or inputs are not on a CUDA device raises.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+class _NAISBase(nn.Module):
+    variant = ""
+    _dropout_on_l1 = False  # NAIS_basic / NAIS_regionEmbedding apply nn.Dropout() to the L1 output (model.py:71,162)
+
+    # -- shared construction helpers -------------------------------------------------------------------------------
+    def _common(self, item_num, embed_size, hidden_size, beta):
+        self.DEVICE = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.embed_size = embed_size
+        self.item_num = item_num
+        self.beta = beta
+        self.hidden_size = hidden_size
+        self._catalog: Optional[ops.DeviceCatalog] = None
+
+    def _acts(self):
+        self.relu = nn.ReLU()
+        self.sigmoid = nn.Sigmoid()
+        self.loss_func = nn.BCELoss()
+
+    def _init_weight_(self):
+        # embeddings N(0, 0.01); Linear biases zero; Linear weights keep torch's default (model.py:219-229)
+        for name in ("embed_history", "embed_target", "embed_region", "embed_distance"):
+            if hasattr(self, name):
+                nn.init.normal_(getattr(self, name).weight, std=0.01)
+        for m in self.modules():
+            if isinstance(m, nn.Linear) and m.bias is not None:
+                m.bias.data.zero_()
+
+    # -- the scorer -------------------------------------------------------------------------------------------------
+    def _params(self) -> Dict[str, torch.Tensor]:
+        named = dict(self.named_parameters())
+        return {n: named[n] for n in ops.VARIANT_PARAMS[self.variant]}
+
+    def _score(self, hist, tgt, hreg=None, treg=None, aux=None) -> torch.Tensor:
+        if self._dropout_on_l1 and self.training and self.drop.p > 0:
+            raise NotImplementedError(
+                f"{type(self).__name__}: train-mode dropout on the attention hidden layer (model.py:71,162) is not "
+                "fused yet; call .eval() or set .drop.p = 0 (the region+distance models have no dropout)")
+        P = self._params()
+        return ops.pairs_score(self.variant, float(self.beta), tuple(P.values()), hist, tgt, hreg, treg, aux)
+
+    def get_mask(self, user_history, target_item):
+        return user_history != target_item.reshape([len(target_item), 1])
+
+    def loss_function(self, prediction, label):
+        return self.loss_func(prediction, label)
+
+    # -- full-rank ranking (new, additive) -----------------------------------------------------------------------------
+    def set_catalog(self, region: Optional[Sequence[int]] = None, coords: Optional[np.ndarray] = None,
+                    row_base: int = 0) -> None:
+        """Register the per-POI side data once (replaces the `businessRegionEmbedList` and `latlon_mat` arguments of
+        validation.py:62): dense region ids [N] and (lat, lon) [N,2].  Coordinates are centred on the bounding-box
+        midpoint in float64 before the float32 cast, so in-kernel |dlat|,|dlon| match the reference's float64
+        differences to ~1e-8 degrees (run.py:47-54, SURVEY.md §7 'Coordinates')."""
+        dev = next(self.parameters()).device
+        reg = None if region is None else torch.as_tensor(np.asarray(region), dtype=torch.int32, device=dev)
+        crd, center = None, (0.0, 0.0)
+        if coords is not None:
+            c = np.asarray(coords, dtype=np.float64)
+            center = (float((c[:, 0].min() + c[:, 0].max()) / 2), float((c[:, 1].min() + c[:, 1].max()) / 2))
+            crd = torch.as_tensor((c - np.array(center)).astype(np.float32), device=dev)
+        n = len(reg) if reg is not None else (len(crd) if crd is not None else self.item_num - row_base)
+        self._catalog = ops.DeviceCatalog(reg, crd, row_base, n, center)
+
+    def make_users(self, indptr, indices) -> ops.DeviceUsers:
+        """CSR histories (train_matrix.indptr / .indices, validation.py:86) -> device arrays with region ids and
+        centred coordinates of every history item gathered."""
+        if self._catalog is None:
+            raise RuntimeError("call set_catalog(region, coords) first")
+        cat = self._catalog
+        dev = next(self.parameters()).device
+        off = torch.as_tensor(np.asarray(indptr), dtype=torch.int64, device=dev)
+        it = torch.as_tensor(np.asarray(indices), dtype=torch.int64, device=dev)
+        if cat.row_base != 0 and (cat.region is not None or cat.coords is not None):
+            raise RuntimeError("history gathering needs the full catalogue on this device (row_base == 0)")
+        reg = cat.region[it] if cat.region is not None else None
+        crd = cat.coords[it].contiguous() if cat.coords is not None else None
+        return ops.DeviceUsers(off, it.to(torch.int32), reg, crd, len(indptr) - 1, int(len(indices)))
+
+    @torch.no_grad()
+    def predict_topk(self, users, k: int, exclude_history: bool = True, poi_begin: int = 0,
+                     poi_end: Optional[int] = None, precision: str = "fp32") -> Tuple[torch.Tensor, torch.Tensor]:
+        """Top-k POIs of [poi_begin, poi_end) for every user: (sigmoid score [U,k] as `forward` would return,
+        ids [U,k] int64, -1 padded).  `users` is a DeviceUsers or an (indptr, indices) pair.  One call replaces the
+        user loop of validation.py:84-127 (candidates = all - history, chunked forward, cat, topk)."""
+        if not isinstance(users, ops.DeviceUsers):
+            users = self.make_users(*users)
+        s, i = ops.fullrank_topk(self.variant, float(self.beta), self._params(), self._catalog, users, k, poi_begin,
+                                 poi_end, exclude_history, precision)
+        return torch.sigmoid(s), i.to(torch.int64)
+
+
+class NAIS_basic(_NAISBase):
+    variant = "basic"
+    _dropout_on_l1 = True
+
+    def __init__(self, item_num, embed_size, hidden_size, beta):
+        super().__init__()
+        self._common(item_num, embed_size, hidden_size, beta)
+        self.embed_history = nn.Embedding(item_num, embed_size)
+        self.embed_target = nn.Embedding(item_num, embed_size)
+        self._acts()
+        self.drop = nn.Dropout()
+        self.attn_layer1 = nn.Linear(embed_size, hidden_size)
+        self.attn_layer2 = nn.Linear(hidden_size, 1, bias=False)
+        self._init_weight_()
+
+    def forward(self, history, target):
+        return self.sigmoid(self.attention_network(history, target))
+
+    def attention_network(self, user_history, target_item):
+        return self._score(user_history, target_item)
+
+
+class NAIS_regionEmbedding(_NAISBase):
+    variant = "region"
+    _dropout_on_l1 = True
+
+    def __init__(self, item_num, embed_size, hidden_size, beta, region_embed_size):
+        super().__init__()
+        self._common(item_num, embed_size, hidden_size, beta)
+        self.embed_history = nn.Embedding(item_num, int(embed_size / 2))
+        self.embed_target = nn.Embedding(item_num, int(embed_size / 2))
+        self.embed_region = nn.Embedding(region_embed_size, int(embed_size / 2))
+        self._acts()
+        self.attn_layer1 = nn.Linear(embed_size, hidden_size)
+        self.attn_layer2 = nn.Linear(hidden_size, 1, bias=False)
+        self.drop = nn.Dropout()
+        self._init_weight_()
+
+    def forward(self, history, target, history_region, target_region):
+        return self.sigmoid(self.attention_network(history, target, history_region, target_region))
+
+    def attention_network(self, user_history, target_item, history_region, target_region):
+        return self._score(user_history, target_item, history_region, target_region)
+
+
+class NAIS_region_distance_Embedding(_NAISBase):
+    variant = "region_distance"
+
+    def __init__(self, item_num, embed_size, hidden_size, beta, region_embed_size, dist_embed_size):
+        super().__init__()
+        self._common(item_num, embed_size, hidden_size, beta)
+        self.embed_history = nn.Embedding(item_num, int(embed_size / 2))
+        self.embed_target = nn.Embedding(item_num, int(embed_size / 2))
+        self.embed_region = nn.Embedding(region_embed_size, int(embed_size / 2))
+        self.embed_distance = nn.Embedding(dist_embed_size, embed_size)  # allocated, never read (model.py:204)
+        self._acts()
+        self.tanh = nn.Tanh()
+        self.attn_layer1 = nn.Linear(embed_size + 2, hidden_size)
+        self.attn_layer2 = nn.Linear(hidden_size, 1, bias=False)
+        self.dist_layer = nn.Linear(2, 2)
+        self._init_weight_()
+
+    def forward(self, history, target, history_region, target_region, target_lat_long):
+        return self.sigmoid(self.attention_network(history, target, history_region, target_region, target_lat_long))
+
+    def attention_network(self, user_history, target_item, history_region, target_region, target_lat_long_tensor):
+        return self._score(user_history, target_item, history_region, target_region, target_lat_long_tensor)
+
+
+class NAIS_distance_Embedding(_NAISBase):
+    variant = "distance"
+
+    def __init__(self, item_num, embed_size, hidden_size, beta, region_embed_size, dist_embed_size):
+        super().__init__()
+        self._common(item_num, embed_size, hidden_size, beta)
+        self.embed_history = nn.Embedding(item_num, embed_size)
+        self.embed_target = nn.Embedding(item_num, embed_size)
+        self._acts()
+        self.attn_layer1 = nn.Linear(embed_size + 2, hidden_size)
+        self.attn_layer2 = nn.Linear(hidden_size, 1, bias=False)
+        self.dist_layer = nn.Linear(2, 2)
+        self._init_weight_()
+
+    def forward(self, history, target, history_region, target_region, target_distance):
+        # region arguments are accepted and ignored, as in the reference (model.py:340-353)
+        return self.sigmoid(self.attention_network(history, target, target_distance))
+
+    def attention_network(self, user_history, target_item, target_lat_long_tensor):
+        return self._score(user_history, target_item, None, None, target_lat_long_tensor)
+
+
+class NAIS_region_distance_disentangled_Embedding(_NAISBase):
+    variant = "disentangled"
+
+    def __init__(self, item_num, embed_size, hidden_size, beta, region_embed_size, dist_embed_size):
+        super().__init__()
+        self._common(item_num, embed_size, hidden_size, beta)
+        self.embed_history = nn.Embedding(item_num, embed_size)
+        self.embed_target = nn.Embedding(item_num, embed_size)
+        self.embed_region = nn.Embedding(region_embed_size, embed_size)
+        self.embed_distance = nn.Embedding(dist_embed_size, embed_size)
+        self._acts()
+        self.attn_layer1 = nn.Linear(embed_size, hidden_size)
+        self.attn_layer2 = nn.Linear(hidden_size, 1, bias=False)
+        self.region_attn_layer1 = nn.Linear(embed_size, hidden_size)
+        self.region_attn_layer2 = nn.Linear(hidden_size, 1, bias=False)
+        self._init_weight_()
+
+    def forward(self, history, target, history_region, target_region, target_distance):
+        return self.sigmoid(self.attention_network(history, target, history_region, target_region, target_distance))
+
+    def attention_network(self, user_history, target_item, history_region, target_region, target_distance):
+        return self._score(user_history, target_item, history_region, target_region, target_distance)
+
+
+CLASSES = {c.variant: c for c in (NAIS_basic, NAIS_regionEmbedding, NAIS_region_distance_Embedding,
+                                  NAIS_distance_Embedding, NAIS_region_distance_disentangled_Embedding)}

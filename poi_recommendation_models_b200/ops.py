@@ -1,0 +1,276 @@
+"""Tensor-level wrappers over the C ABI (include/nais_b200.h).
+
+PyTorch is plumbing here: it owns device memory, the current stream and autograd bookkeeping; every number is computed
+by the CUDA kernels in libnais_b200.so.  All ops raise if the tensors are not on a CUDA device — there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (DIST_KM, DIST_LATLON, DIST_NONE, PRECISIONS, NaisBranch, NaisCatalog, NaisGrads, NaisPairs,
+                   NaisParams, NaisUsers)
+
+# parameter names per variant, in the reference's state_dict naming (SURVEY.md §5 checkpoint row)
+VARIANT_PARAMS: Dict[str, Tuple[str, ...]] = {
+    "basic": ("embed_history.weight", "embed_target.weight", "attn_layer1.weight", "attn_layer1.bias", "attn_layer2.weight"),
+    "region": ("embed_history.weight", "embed_target.weight", "embed_region.weight", "attn_layer1.weight",
+               "attn_layer1.bias", "attn_layer2.weight"),
+    # embed_distance.weight exists in this class but is never read by its forward (model.py:204,270-276)
+    "region_distance": ("embed_history.weight", "embed_target.weight", "embed_region.weight",
+                        "attn_layer1.weight", "attn_layer1.bias", "attn_layer2.weight", "dist_layer.weight",
+                        "dist_layer.bias"),
+    "distance": ("embed_history.weight", "embed_target.weight", "attn_layer1.weight", "attn_layer1.bias",
+                 "attn_layer2.weight", "dist_layer.weight", "dist_layer.bias"),
+    "disentangled": ("embed_history.weight", "embed_target.weight", "embed_region.weight", "embed_distance.weight",
+                     "attn_layer1.weight", "attn_layer1.bias", "attn_layer2.weight", "region_attn_layer1.weight",
+                     "region_attn_layer1.bias", "region_attn_layer2.weight"),
+}
+VARIANT_DIST = {"basic": (DIST_NONE, 0.0), "region": (DIST_NONE, 0.0), "region_distance": (DIST_LATLON, 100.0),
+                "distance": (DIST_LATLON, 1000.0), "disentangled": (DIST_KM, 0.0)}
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("NAIS ops run only on a CUDA device (no CPU fallback); got a tensor on " + str(t.device))
+        dev = dev or t.device
+        if t.device != dev:
+            raise RuntimeError("NAIS ops: tensors on different devices")
+    return dev
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise RuntimeError("NAIS ops compute in float32; got " + str(t.dtype))
+    return t.contiguous()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def build_params(variant: str, P: Dict[str, torch.Tensor], beta: float, keep: List[torch.Tensor]) -> NaisParams:
+    """NaisParams for a reference-shaped parameter dict.  Contiguous copies are appended to `keep` to stay alive."""
+    def g(name):
+        t = _f32(P[name].detach())
+        keep.append(t)
+        return t
+
+    p = NaisParams()
+    mode, scale = VARIANT_DIST[variant]
+    eh, et = g("embed_history.weight"), g("embed_target.weight")
+    w1, b1, w2 = g("attn_layer1.weight"), g("attn_layer1.bias"), g("attn_layer2.weight")
+    p.item_num = eh.shape[0]
+    p.hid = w1.shape[0]
+    p.dist_mode, p.dist_scale, p.beta = mode, scale, float(beta)
+    p.dist_buckets, p.dist_bucket_km, p.region_num, p.n_branch = 1, 1.0, 0, 1
+    b0 = p.branch[0]
+    b0.hist_poi, b0.tgt_poi, b0.w_poi, b0.w_reg = eh.data_ptr(), et.data_ptr(), eh.shape[1], 0
+    b0.w1, b0.b1, b0.w2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr()
+    if variant in ("region", "region_distance"):
+        er = g("embed_region.weight")
+        b0.hist_reg = b0.tgt_reg = er.data_ptr()
+        b0.w_reg, p.region_num = er.shape[1], er.shape[0]
+    if mode == DIST_LATLON:
+        p.dist_w, p.dist_b = g("dist_layer.weight").data_ptr(), g("dist_layer.bias").data_ptr()
+    if variant == "disentangled":
+        er, ed = g("embed_region.weight"), g("embed_distance.weight")
+        rw1, rb1, rw2 = g("region_attn_layer1.weight"), g("region_attn_layer1.bias"), g("region_attn_layer2.weight")
+        p.n_branch, p.region_num = 2, er.shape[0]
+        b1_ = p.branch[1]
+        b1_.hist_reg = b1_.tgt_reg = er.data_ptr()
+        b1_.w_poi, b1_.w_reg = 0, er.shape[1]
+        b1_.w1, b1_.b1, b1_.w2 = rw1.data_ptr(), rb1.data_ptr(), rw2.data_ptr()
+        p.dist_embed, p.dist_buckets = ed.data_ptr(), 1  # the reference only ever reads bucket 0 (model.py:497-498)
+    w_in = b0.w_poi + b0.w_reg + (2 if mode == DIST_LATLON else 0)
+    if w1.shape[1] != w_in or b1.numel() != p.hid or w2.numel() != p.hid:
+        raise RuntimeError(f"attn_layer shapes do not match the variant: w1 {tuple(w1.shape)}, expected [*, {w_in}]")
+    return p
+
+
+def _pairs_struct(hist, tgt, hreg, treg, aux, keep) -> NaisPairs:
+    def i64(t):
+        if t is None:
+            return None
+        t = t.to(torch.int64).contiguous()
+        keep.append(t)
+        return t
+    hist, tgt, hreg, treg = i64(hist), i64(tgt), i64(hreg), i64(treg)
+    if hist.dim() != 2 or tgt.dim() != 1 or hist.shape[0] != tgt.shape[0]:
+        raise RuntimeError(f"expected history [B,H] and target [B]; got {tuple(hist.shape)} and {tuple(tgt.shape)}")
+    if aux is not None:
+        aux = _f32(aux)
+        keep.append(aux)
+    b = NaisPairs()
+    b.hist, b.tgt, b.hreg, b.treg, b.aux = _ptr(hist), _ptr(tgt), _ptr(hreg), _ptr(treg), _ptr(aux)
+    b.B, b.H = hist.shape[0], hist.shape[1]
+    return b
+
+
+class _PairsFunction(torch.autograd.Function):
+    """score = attention_network(pairs).  forward -> nais_pairs_forward, backward -> nais_pairs_backward."""
+
+    @staticmethod
+    def forward(ctx, variant, beta, hist, tgt, hreg, treg, aux, *params):
+        names = VARIANT_PARAMS[variant]
+        P = dict(zip(names, params))
+        dev = _need_cuda(hist, tgt, hreg, treg, aux, *params)
+        lib = _lib.load()
+        keep: List[torch.Tensor] = []
+        with torch.cuda.device(dev):
+            p = build_params(variant, P, beta, keep)
+            b = _pairs_struct(hist, tgt, hreg, treg, aux, keep)
+            B = b.B
+            score = torch.empty(B, device=dev, dtype=torch.float32)
+            row_sum = torch.empty(p.n_branch, B, device=dev, dtype=torch.float32)
+            parts = torch.empty(p.n_branch, B, device=dev, dtype=torch.float32)
+            _lib.check(lib.nais_pairs_forward(C.byref(p), C.byref(b), score.data_ptr(), row_sum.data_ptr(),
+                                              parts.data_ptr(), _stream()), "nais_pairs_forward")
+        ctx.variant, ctx.beta = variant, beta
+        ctx.save_for_backward(hist, tgt, hreg if hreg is not None else torch.empty(0), treg if treg is not None else torch.empty(0),
+                              aux if aux is not None else torch.empty(0), row_sum, parts, *params)
+        ctx.has = (hreg is not None, treg is not None, aux is not None)
+        return score
+
+    @staticmethod
+    def backward(ctx, dscore):
+        hist, tgt, hreg, treg, aux, row_sum, parts, *params = ctx.saved_tensors
+        hreg = hreg if ctx.has[0] else None
+        treg = treg if ctx.has[1] else None
+        aux = aux if ctx.has[2] else None
+        variant = ctx.variant
+        names = VARIANT_PARAMS[variant]
+        P = dict(zip(names, params))
+        dev = dscore.device
+        lib = _lib.load()
+        keep: List[torch.Tensor] = []
+        with torch.cuda.device(dev):
+            p = build_params(variant, P, ctx.beta, keep)
+            b = _pairs_struct(hist, tgt, hreg, treg, aux, keep)
+            G = {n: torch.zeros_like(t, dtype=torch.float32, memory_format=torch.contiguous_format) for n, t in P.items()}
+            g = NaisGrads()
+            g.hist_poi[0], g.tgt_poi[0] = G["embed_history.weight"].data_ptr(), G["embed_target.weight"].data_ptr()
+            g.w1[0], g.b1[0], g.w2[0] = (G["attn_layer1.weight"].data_ptr(), G["attn_layer1.bias"].data_ptr(),
+                                         G["attn_layer2.weight"].data_ptr())
+            if variant in ("region", "region_distance"):
+                g.reg[0] = G["embed_region.weight"].data_ptr()
+            if "dist_layer.weight" in G:
+                g.dist_w, g.dist_b = G["dist_layer.weight"].data_ptr(), G["dist_layer.bias"].data_ptr()
+            if variant == "disentangled":
+                g.reg[1] = G["embed_region.weight"].data_ptr()
+                g.w1[1], g.b1[1], g.w2[1] = (G["region_attn_layer1.weight"].data_ptr(),
+                                             G["region_attn_layer1.bias"].data_ptr(),
+                                             G["region_attn_layer2.weight"].data_ptr())
+                g.dist_embed = G["embed_distance.weight"].data_ptr()
+            ws_bytes = lib.nais_pairs_backward_workspace_bytes(C.byref(p), b.B, b.H)
+            ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
+            ds = _f32(dscore)
+            _lib.check(lib.nais_pairs_backward(C.byref(p), C.byref(b), parts.data_ptr(), row_sum.data_ptr(), ds.data_ptr(),
+                                               C.byref(g), ws.data_ptr(), ws_bytes, _stream()), "nais_pairs_backward")
+        grads = tuple(G[n].to(P[n].dtype) if ctx.needs_input_grad[7 + i] else None for i, n in enumerate(names))
+        return (None, None, None, None, None, None, None) + grads
+
+
+def pairs_score(variant: str, beta: float, params: Sequence[torch.Tensor], hist, tgt, hreg=None, treg=None, aux=None):
+    """Pre-sigmoid scores [B] of explicit pairs (differentiable w.r.t. `params`, ordered as VARIANT_PARAMS[variant])."""
+    return _PairsFunction.apply(variant, beta, hist, tgt, hreg, treg, aux, *params)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Full-rank scoring + top-k
+# ----------------------------------------------------------------------------------------------------------------------
+@dataclass
+class DeviceCatalog:
+    """Candidate-side arrays resident on the device (replaces businessRegionEmbedList + latlon_mat arguments of
+    validation.py:62).  coords are centred in float64 on the host before the float32 cast."""
+    region: Optional[torch.Tensor]  # [n_rows] int32
+    coords: Optional[torch.Tensor]  # [n_rows,2] float32, centred
+    row_base: int
+    n_rows: int
+    center: Tuple[float, float]
+
+
+@dataclass
+class DeviceUsers:
+    offsets: torch.Tensor  # [U+1] int64 (device)
+    items: torch.Tensor  # [nnz] int32
+    region: Optional[torch.Tensor]  # [nnz] int32
+    coords: Optional[torch.Tensor]  # [nnz,2] float32 centred
+    n_users: int
+    nnz: int
+
+
+def _structs(cat: DeviceCatalog, users: DeviceUsers):
+    c = NaisCatalog()
+    c.region, c.coords, c.row_base, c.n_rows = _ptr(cat.region), _ptr(cat.coords), cat.row_base, cat.n_rows
+    u = NaisUsers()
+    u.offsets, u.items, u.region, u.coords, u.n_users = (_ptr(users.offsets), _ptr(users.items), _ptr(users.region),
+                                                         _ptr(users.coords), users.n_users)
+    return c, u
+
+
+def fullrank_topk(variant: str, beta: float, P: Dict[str, torch.Tensor], cat: DeviceCatalog, users: DeviceUsers, k: int,
+                  poi_begin: int = 0, poi_end: Optional[int] = None, exclude_history: bool = True,
+                  precision: str = "fp32") -> Tuple[torch.Tensor, torch.Tensor]:
+    """(score[U,k] pre-sigmoid descending, id[U,k] int32 global POI ids; -inf / -1 padding)."""
+    dev = _need_cuda(users.offsets, users.items, *P.values())
+    lib = _lib.load()
+    keep: List[torch.Tensor] = []
+    with torch.cuda.device(dev):
+        p = build_params(variant, P, beta, keep)
+        poi_end = p.item_num if poi_end is None else poi_end
+        c, u = _structs(cat, users)
+        prec = PRECISIONS[precision]
+        out_s = torch.empty(users.n_users, k, device=dev, dtype=torch.float32)
+        out_i = torch.empty(users.n_users, k, device=dev, dtype=torch.int32)
+        ws_bytes = lib.nais_fullrank_workspace_bytes(C.byref(p), users.n_users, users.nnz, poi_begin, poi_end, k, prec)
+        ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
+        _lib.check(lib.nais_fullrank_topk(C.byref(p), C.byref(c), C.byref(u), poi_begin, poi_end, k, int(exclude_history),
+                                          prec, out_s.data_ptr(), out_i.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
+                   "nais_fullrank_topk")
+    return out_s, out_i
+
+
+def fullrank_scores(variant: str, beta: float, P: Dict[str, torch.Tensor], cat: DeviceCatalog, users: DeviceUsers,
+                    poi_begin: int = 0, poi_end: Optional[int] = None, precision: str = "fp32") -> torch.Tensor:
+    """All pre-sigmoid scores [U, poi_end-poi_begin] through the fused path (small cases / parity checks)."""
+    dev = _need_cuda(users.offsets, users.items, *P.values())
+    lib = _lib.load()
+    keep: List[torch.Tensor] = []
+    with torch.cuda.device(dev):
+        p = build_params(variant, P, beta, keep)
+        poi_end = p.item_num if poi_end is None else poi_end
+        c, u = _structs(cat, users)
+        prec = PRECISIONS[precision]
+        out = torch.empty(users.n_users, poi_end - poi_begin, device=dev, dtype=torch.float32)
+        ws_bytes = lib.nais_fullrank_workspace_bytes(C.byref(p), users.n_users, users.nnz, poi_begin, poi_end, 1, prec)
+        ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
+        _lib.check(lib.nais_fullrank_scores(C.byref(p), C.byref(c), C.byref(u), poi_begin, poi_end, prec, out.data_ptr(),
+                                            ws.data_ptr(), ws_bytes, _stream()), "nais_fullrank_scores")
+    return out
+
+
+def topk_merge(scores: torch.Tensor, ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge [U, L, k] lists (one per catalogue shard) into [U, k] by (score desc, id asc)."""
+    dev = _need_cuda(scores, ids)
+    U, L, k = scores.shape
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        s, i = _f32(scores), ids.to(torch.int32).contiguous()
+        out_s = torch.empty(U, k, device=dev, dtype=torch.float32)
+        out_i = torch.empty(U, k, device=dev, dtype=torch.int32)
+        _lib.check(lib.nais_topk_merge(s.data_ptr(), i.data_ptr(), U, L, k, out_s.data_ptr(), out_i.data_ptr(), _stream()),
+                   "nais_topk_merge")
+    return out_s, out_i

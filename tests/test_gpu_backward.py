@@ -1,0 +1,111 @@
+"""GPU parity of the hand-written backward (through autograd.Function -> nais_pairs_backward) against the
+reference's autograd gradients (golden, float64) and against oracle autograd on fresh shapes; plus whole train steps."""
+import numpy as np
+import pytest
+import torch
+
+import nais_testutil as util
+from oracle import nais_oracle as orc
+from poi_recommendation_models_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+VARIANTS = list(orc.VARIANTS)
+GTOL = 2e-4  # per tensor: max|got-ref| <= GTOL * max|ref|  (fp32 kernels vs float64 truth)
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _check_grads(m, ref_grads, tol=GTOL):
+    worst = {}
+    for name, p in m.named_parameters():
+        ref = np.asarray(ref_grads[name], dtype=np.float64)
+        got = np.zeros_like(ref) if p.grad is None else p.grad.detach().cpu().double().numpy()
+        scale = np.abs(ref).max()
+        err = np.abs(got - ref).max()
+        worst[name] = (err, scale)
+        assert err <= tol * scale + 1e-12, (name, err, scale)
+    return worst
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_gradients_match_reference_golden(variant):
+    z = util.load_golden(f"scorer_{variant}.npz")
+    sd = util.golden_sd(z, "trained_sd.")
+    m = util.make_model(variant, sd, float(z["beta"]))  # eval(): dropout of basic/region off, like the golden grads
+    t = {k: _dev(z[f"trained_{k}"]) for k in ("hist", "tgt", "hreg", "treg", "aux")}
+    pred = util.call(m, variant, t["hist"], t["tgt"], t["hreg"], t["treg"], t["aux"], pre_sigmoid=False)
+    loss = m.loss_func(pred, _dev(z["grad_label"]).float())
+    loss.backward()
+    assert abs(loss.item() - float(z["grad_loss"])) < 1e-5 * abs(float(z["grad_loss"]))
+    _check_grads(m, {k[5:]: z[k] for k in z.files if k.startswith("grad.")})
+
+
+@pytest.mark.parametrize("H,B,D,hid", [(1, 9, 32, 32), (7, 40, 64, 64), (100, 33, 64, 64), (128, 20, 64, 64), (200, 5, 64, 64),
+                                       (16, 50, 128, 64), (16, 50, 64, 128), (24, 31, 128, 128), (5, 300, 32, 100)])
+def test_gradients_shapes_vs_oracle_autograd(H, B, D, hid):
+    rng = np.random.default_rng(H * 1000 + B)
+    N, beta = 400, 0.5
+    coords, region, R = synthetic.make_catalog(N, seed=2)
+    sd = orc.init_state("region_distance", N, D, hid, R, 1, seed=4, style="trained")
+    hist = np.stack([rng.choice(N, H, replace=False) for _ in range(B)]).astype(np.int64)
+    tgt = rng.integers(0, N, B).astype(np.int64)
+    if H > 1:
+        tgt[::3] = hist[::3, H // 2]  # training positives: live mask
+    aux = orc.latlon_abs_diff(coords, tgt, hist)
+    dscore = rng.normal(size=B)
+    m = util.make_model("region_distance", sd, beta)
+    s = m.attention_network(_dev(hist), _dev(tgt), _dev(region[hist]), _dev(region[tgt]), _dev(aux))
+    (s * _dev(dscore).float()).sum().backward()
+    _, ref = orc.grads(sd, "region_distance", beta, torch.from_numpy(hist), torch.from_numpy(tgt), torch.from_numpy(region[hist]),
+                       torch.from_numpy(region[tgt]), torch.from_numpy(aux), torch.from_numpy(dscore))
+    ref = {k: v.numpy() for k, v in ref.items()}
+    ref.setdefault("embed_distance.weight", np.zeros((1, D)))
+    _check_grads(m, ref)
+
+
+def test_backward_is_deterministic():
+    rng = np.random.default_rng(0)
+    N, D, hid, B, H = 300, 64, 64, 64, 20
+    coords, region, R = synthetic.make_catalog(N, seed=2)
+    sd = orc.init_state("region_distance", N, D, hid, R, 1, seed=4, style="trained")
+    hist = np.stack([rng.choice(N, H, replace=False) for _ in range(B)]).astype(np.int64)
+    tgt = rng.integers(0, N, B).astype(np.int64)
+    aux = orc.latlon_abs_diff(coords, tgt, hist)
+    outs = []
+    for _ in range(2):
+        m = util.make_model("region_distance", sd, 0.5)
+        m.attention_network(_dev(hist), _dev(tgt), _dev(region[hist]), _dev(region[tgt]), _dev(aux)).sum().backward()
+        outs.append({n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None})
+    for n in outs[0]:
+        assert torch.equal(outs[0][n], outs[1][n]), n  # no atomics: bitwise reproducible
+
+
+def test_train_steps_match_reference_flow():
+    """Three user-steps of run.py:235-254 (BCE + dense Adagrad) on the drop-in module vs the oracle's restatement."""
+    import random
+    from poi_recommendation_models_b200 import batches as PB
+    N, D, hid, beta = 300, 64, 64, 0.5
+    data = synthetic.make_checkins(3, N, seed=9, hist_len=None, max_hist=20, min_hist=5, median_hist=10)
+    sd = orc.init_state("region_distance", N, D, hid, data.region_num, 1, seed=2, style="trained")
+    m = util.make_model("region_distance", sd, beta).train()
+    opt = torch.optim.Adagrad(m.parameters(), lr=0.01, weight_decay=0.0)
+    csr = data.train_csr()
+    ref_sd, ref_sum = {k: v.double() for k, v in sd.items()}, None
+    for u in range(3):
+        random.seed(50 + u)
+        hist, tgt, label, hreg, treg = PB.get_NAIS_batch_region(csr, N, u, 4, data.region)
+        ll = PB.lat_lon_pairs(data.coords, tgt.cpu().numpy(), hist.cpu().numpy())
+        opt.zero_grad()
+        pred = m(hist, tgt, hreg, treg, ll)
+        loss = m.loss_func(pred, label)
+        loss.backward()
+        opt.step()
+        rl, ref_sd, ref_sum = orc.train_step_bce(ref_sd, "region_distance", beta, hist.cpu(), tgt.cpu(), hreg.cpu(), treg.cpu(),
+                                                 ll.cpu(), label.cpu(), 0.01, ref_sum, dtype=torch.float64)
+        assert abs(loss.item() - rl) < 1e-5 * abs(rl)
+    for k, v in m.state_dict().items():
+        ref = ref_sd[k].numpy()
+        # Adagrad's first steps move every touched weight by ~lr regardless of gradient size; compare updates
+        np.testing.assert_allclose(v.cpu().double().numpy(), ref, rtol=0, atol=2e-5, err_msg=k)
