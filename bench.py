@@ -173,7 +173,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=list(WORKLOADS))
-    ap.add_argument("--precision", default=os.environ.get("NAIS_BENCH_PRECISION", "fp32"), choices=["fp32", "tc_split", "tc_fast"])
+    ap.add_argument("--precision", default=os.environ.get("NAIS_BENCH_PRECISION", "tc_split"), choices=["fp32", "tc_split", "tc_fast"])
     ap.add_argument("--users-per-step", type=int, default=0)
     ap.add_argument("--cpu-users", type=int, default=4, help="users in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

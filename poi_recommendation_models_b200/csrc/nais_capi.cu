@@ -61,6 +61,14 @@ static int check_pairs(const NaisParams* p, const NaisPairs* b) {
   return 0;
 }
 
+__global__ void fill_empty_topk_kernel(float* s, int32_t* id, size_t n) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) {
+    s[i] = -INFINITY;
+    id[i] = -1;
+  }
+}
+
 extern "C" {
 
 int nais_abi_version(void) { return NAIS_ABI_VERSION; }
@@ -148,6 +156,12 @@ int nais_fullrank_topk(const NaisParams* p, const NaisCatalog* cat, const NaisUs
   if (users->n_users && (!out_score || !out_id || !workspace)) return NAIS_ERR_NULL;
   if (!aligned16(workspace)) return NAIS_ERR_ALIGN;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (users->n_users && poi_end == poi_begin) {  // empty shard: every list is padding
+    const size_t n = (size_t)users->n_users * k;
+    fill_empty_topk_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out_score, out_id, n);
+    NAIS_COUNT_LAUNCH(1);
+    return (int)cudaGetLastError();
+  }
   if (precision == NAIS_PREC_FP32)
     return launch_fullrank_fp32(*p, *cat, *users, poi_begin, poi_end, k, exclude_history, out_score, out_id, nullptr,
                                 workspace, workspace_bytes, st);

@@ -545,6 +545,60 @@ int launch_topk_merge(const unsigned long long* in_keys, const float* in_score, 
   return (int)cudaGetLastError();
 }
 
+
+// Keys -> keys (or final score/id) merge of blocks of `lpb` lists; grid (blocks, users).
+__global__ void topk_merge_keys_kernel(const unsigned long long* __restrict__ in, int n_lists, int k, int lpb, int n2,
+                                       unsigned long long* out_keys, float* out_score, int32_t* out_id) {
+  extern __shared__ __align__(16) unsigned long long mk[];
+  const int u = blockIdx.y, b = blockIdx.x;
+  const int l0 = b * lpb, l1 = min(n_lists, l0 + lpb);
+  const int n = (l1 - l0) * k;
+  const unsigned long long* src = in + ((size_t)u * n_lists + l0) * k;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) mk[i] = i < n ? src[i] : 0ull;
+  __syncthreads();
+  bitonic_sort_desc(mk, n2);
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    if (out_keys) {
+      out_keys[((size_t)u * gridDim.x + b) * k + i] = mk[i];
+    } else {
+      float sc;
+      int id;
+      split_key(mk[i], sc, id);
+      out_score[(size_t)u * k + i] = sc;
+      out_id[(size_t)u * k + i] = id;
+    }
+  }
+}
+
+// Hierarchical merge of [n_users][n_lists][k] keys (ping-pong between `keys` and `scratch`).
+int launch_topk_merge_keys_multi(unsigned long long* keys, unsigned long long* scratch, int n_users, int n_lists, int k,
+                                 float* out_score, int32_t* out_id, cudaStream_t stream) {
+  if (n_users == 0) return 0;
+  cudaError_t e = cudaFuncSetAttribute(topk_merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8);
+  if (e != cudaSuccess) return (int)e;
+  unsigned long long *src = keys, *dst = scratch;
+  while (true) {
+    int lpb = 8192 / k;
+    if (lpb > 64) lpb = 64;
+    if (lpb > n_lists) lpb = n_lists;
+    const int blocks = (n_lists + lpb - 1) / lpb;
+    int n2 = 1;
+    while (n2 < lpb * k) n2 <<= 1;
+    const bool last = blocks == 1;
+    dim3 grid(blocks, n_users);
+    const int threads = n2 >= 1024 ? 512 : (n2 < 64 ? 64 : n2 / 2);
+    topk_merge_keys_kernel<<<grid, threads, (size_t)n2 * 8, stream>>>(src, n_lists, k, lpb, n2, last ? nullptr : dst, out_score, out_id);
+    NAIS_COUNT_LAUNCH(1);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    if (last) return 0;
+    n_lists = blocks;
+    unsigned long long* t = src;
+    src = dst;
+    dst = t;
+  }
+}
+
 int launch_fullrank_fp32(const NaisParams& p, const NaisCatalog& cat, const NaisUsers& users, int64_t poi_begin,
                          int64_t poi_end, int k, int exclude, float* out_score, int32_t* out_id, float* all_scores,
                          void* ws, size_t ws_bytes, cudaStream_t stream) {

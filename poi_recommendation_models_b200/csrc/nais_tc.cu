@@ -1,8 +1,760 @@
-// placeholder until the tcgen05 path lands
+// Tensor-core (tcgen05 / TMEM) full-rank scorer for sm_100a.
+//
+// Per user u and candidate j the attention logits need t[k] = sum_d W[k,d] q_h[d] p_j[d] for every history item h and
+// hidden unit k: a GEMM  T[j, (h,k)] = P[j,:] . B_u[(h,k),:]^T  with  B_u[(h,k), d] = c_k W[k,d] q_h[d]  built ONCE per
+// user (pack kernel) and reused against the whole catalogue.  M = 128 candidates (one TMEM lane = one candidate = one
+// epilogue thread), N = 2 history items x (hid + 2) rows, K = D + 16:
+//
+//   * the two distance lanes and the bias are folded into an extra K-step: A_ext[j, 2*hs+c] = g_c(h_hs, j) (written by
+//     the epilogue warps, 3 steps ahead), A_ext[j,4] = 1;  B_ext[(hs,k), 2*hs+c] = c_k W[k,D+c], B_ext[.,4] = c_k b_k;
+//   * ReLU + second layer in ONE FADD per accumulator element: with c_k = |v_k|/2 and t'_k = c_k t_k,
+//         sum_k v_k relu(t_k) = sum_k sgn_k t'_k + sum_k sgn_k |t'_k| = L + sum_{k in pos}|t'_k| - sum_{k in neg}|t'_k|
+//     L is linear, so it is one more row of B ("L row"); hidden units are permuted positive-v first;
+//   * the similarity s_hj = <q_h, p_j> is another row of B ("S row");
+//   * fp32-grade products from fp16 tensor cores: every operand is split x = hi + lo (two fp16 planes, power-of-two
+//     pre-scaling), D += A_hi B_hi + A_hi B_lo + A_lo B_hi  (NAIS_PREC_TC_SPLIT).  NAIS_PREC_TC_FAST keeps the three
+//     passes only for the S/L rows (an N=16 MMA at a column offset) and runs the main rows single-pass.
+//
+// Warp roles (320 threads, 1 CTA/SM, persistent over work items = (user, 3 candidate tiles)):
+//   warps 0-7  epilogue: lane quarter = warp%4, history slot = warp/4; produce A_ext, TMEM -> registers, beta-softmax state
+//   warp 8     MMA issuer (one elected lane) + TMEM allocation
+//   warp 9     bulk-copy producer (one elected lane): A tiles per item, B chunks through a ring of stages
+#include <cuda_fp16.h>
+
 #include "nais_common.cuh"
+#include "umma.cuh"
+
 namespace nais {
-bool tc_supported(const NaisParams&) { return false; }
-size_t fullrank_tc_workspace_bytes(const NaisParams&, int, int64_t, int64_t, int64_t, int, int) { return 0; }
-int launch_fullrank_tc(const NaisParams&, const NaisCatalog&, const NaisUsers&, int64_t, int64_t, int, int, int, float*,
-                       int32_t*, float*, void*, size_t, cudaStream_t) { return NAIS_ERR_MODE; }
+
+using namespace umma;
+
+namespace tc {
+
+constexpr int TM = 128;
+constexpr int NBUF = 3;          // TMEM accumulator buffers == A_ext buffers == look-ahead of the g producer
+constexpr int ACC_STRIDE = 160;  // TMEM columns per accumulator buffer
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = (EPI_WARPS + 2) * 32;
+constexpr int MAX_STAGES = 3;
+constexpr int SORTN = 512;
+
+struct Geo {
+  int D, hid, lanes, split;
+  int kx;        // D / 8 x k-chunks
+  int nrow;      // rows of a B chunk (2*(hid+2) padded to 16)
+  int tpc;       // candidate tiles per item
+  int stages;    // B ring depth
+  int a_plane, a_tile;          // bytes
+  int b_hi, b_lo, b_chunk;      // bytes
+  int smem_bytes;
+};
+
+__host__ __device__ inline int pad16(int x) { return (x + 15) / 16 * 16; }
+
+__host__ inline bool make_geo(const NaisParams& p, int precision, Geo& g) {
+  if (p.n_branch != 1) return false;
+  const NaisBranch& br = p.branch[0];
+  g.D = br.w_poi + br.w_reg;
+  g.hid = p.hid;
+  g.lanes = p.dist_mode == NAIS_DIST_LATLON ? 2 : 0;
+  g.split = precision == NAIS_PREC_TC_SPLIT;
+  if (p.dist_mode == NAIS_DIST_KM) return false;
+  if (g.D % 16 || g.D < 16 || g.D > 64 || g.hid % 16 || g.hid < 16 || g.hid > 64) return false;
+  g.kx = g.D / 8;
+  g.nrow = pad16(2 * g.hid + 4);
+  if (g.nrow < 2 * g.hid + 16) g.nrow = 2 * g.hid + 16;
+  if (g.nrow > ACC_STRIDE) return false;
+  g.a_plane = g.kx * TM * 16;
+  g.a_tile = 2 * g.a_plane;
+  g.b_hi = (g.kx + 1) * g.nrow * 16;
+  g.b_lo = g.split ? g.b_hi : (g.kx + 1) * 16 * 16;
+  g.b_chunk = g.b_hi + g.b_lo;
+  g.tpc = 3;
+  g.stages = g.split ? 2 : 3;
+  // smem: A tiles | B stages | A_ext (hi,lo) x NBUF | zero | keys | comb | barriers
+  g.smem_bytes = g.tpc * g.a_tile + g.stages * g.b_chunk + NBUF * 2 * TM * 16 + 4096 + SORTN * 8 + 3 * g.tpc * TM * 4 + 256 + 128;
+  return g.smem_bytes <= 227 * 1024;
+}
+
+// device-side scalars written by tc_scales_kernel
+struct Scales {
+  float sA, sS, sB, sAe, sBe, inv_sigma, inv_s;
+  int npos;
+  float omega0, omega1, omegab, pad;
+};
+// workspace header: [0,64) maxes (uint bits) | [64, 128) Scales | [128, 128+4*hid) perm | ck[hid] | u[D]
+constexpr int HDR_BYTES = 4096;
+
+__global__ void absmax_kernel(const float* __restrict__ x, size_t n, unsigned* out) {
+  float m = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));  // non-negative floats order like their bit patterns
+}
+
+__device__ __forceinline__ float pow2floor(float x) { return exp2f(floorf(log2f(x))); }
+
+// One CTA: permutation (positive v first), c_k, u_d, omegas, power-of-two scales.
+__global__ void scales_kernel(NaisParams p, unsigned char* hdr) {
+  const NaisBranch& br = p.branch[0];
+  const int D = br.w_poi + br.w_reg, hid = p.hid;
+  const int lanes = p.dist_mode == NAIS_DIST_LATLON ? 2 : 0, ldw = D + lanes;
+  const unsigned* mx = reinterpret_cast<const unsigned*>(hdr);
+  Scales* sc = reinterpret_cast<Scales*>(hdr + 64);
+  int* perm = reinterpret_cast<int*>(hdr + 128);
+  float* ck = reinterpret_cast<float*>(hdr + 128 + 4 * 64);
+  float* u = reinterpret_cast<float*>(hdr + 128 + 8 * 64);
+  __shared__ float red[8];
+  __shared__ int s_npos;
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int k = 0; k < hid; ++k)
+      if (br.w2[k] >= 0.f) perm[n++] = k;
+    s_npos = n;
+    for (int k = 0; k < hid; ++k)
+      if (!(br.w2[k] >= 0.f)) perm[n++] = k;
+    for (int i = 0; i < 8; ++i) red[i] = 0.f;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < hid; k += blockDim.x) ck[k] = 0.5f * fabsf(br.w2[k]);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float a = 0.f;
+    for (int k = 0; k < hid; ++k) a += 0.5f * br.w2[k] * br.w1[(size_t)k * ldw + d];
+    u[d] = a;
+  }
+  __syncthreads();
+  // maxima of the MLP-derived operand factors
+  float mcw = 0.f, mbe = 0.f;
+  for (int i = threadIdx.x; i < hid * D; i += blockDim.x) {
+    int k = i / D, d = i - k * D;
+    mcw = fmaxf(mcw, fabsf(ck[k] * br.w1[(size_t)k * ldw + d]));
+  }
+  for (int d = threadIdx.x; d < D; d += blockDim.x) mcw = fmaxf(mcw, fabsf(u[d]));
+  for (int k = threadIdx.x; k < hid; k += blockDim.x) {
+    mbe = fmaxf(mbe, fabsf(ck[k] * br.b1[k]));
+    if (lanes) {
+      mbe = fmaxf(mbe, fabsf(ck[k] * br.w1[(size_t)k * ldw + D]));
+      mbe = fmaxf(mbe, fabsf(ck[k] * br.w1[(size_t)k * ldw + D + 1]));
+    }
+  }
+  atomicMax(reinterpret_cast<unsigned*>(&red[0]), __float_as_uint(mcw));
+  atomicMax(reinterpret_cast<unsigned*>(&red[1]), __float_as_uint(mbe));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float o0 = 0.f, o1 = 0.f, ob = 0.f;
+    for (int k = 0; k < hid; ++k) {
+      const float hv = 0.5f * br.w2[k];
+      ob += hv * br.b1[k];
+      if (lanes) {
+        o0 += hv * br.w1[(size_t)k * ldw + D];
+        o1 += hv * br.w1[(size_t)k * ldw + D + 1];
+      }
+    }
+    const float tiny = 1e-30f;
+    const float maxP = fmaxf(fmaxf(__uint_as_float(mx[0]), __uint_as_float(mx[1])), tiny);
+    const float maxQ = fmaxf(fmaxf(__uint_as_float(mx[2]), __uint_as_float(mx[3])), tiny);
+    const float maxB = fmaxf(maxQ * red[0], tiny);
+    const float maxBe = fmaxf(fmaxf(red[1], fmaxf(fabsf(o0), fmaxf(fabsf(o1), fabsf(ob)))), tiny);
+    float sA = pow2floor(512.f / maxP), sS = pow2floor(512.f / maxQ), sB = pow2floor(512.f / maxB);
+    const float sAe = 256.f;
+    // ext products must carry the same scale sigma = sA*sB = sAe*sBe and stay inside fp16
+    float sBe = sA * sB / sAe;
+    while (maxBe * sBe > 16384.f) {
+      sB *= 0.5f;
+      sBe *= 0.5f;
+    }
+    sc->sA = sA;
+    sc->sS = sS;
+    sc->sB = sB;
+    sc->sAe = sAe;
+    sc->sBe = sBe;
+    sc->inv_sigma = 1.f / (sA * sB);
+    sc->inv_s = 1.f / (sA * sS);
+    sc->npos = s_npos;
+    sc->omega0 = o0;
+    sc->omega1 = o1;
+    sc->omegab = ob;
+  }
+}
+
+// Candidate tiles: image [tile][plane hi|lo][k-chunk][row][8 x fp16] of p_j * sA.  One thread = (row, k-chunk).
+__global__ void pack_candidates_kernel(NaisParams p, NaisCatalog cat, int64_t poi_begin, int64_t poi_end, Geo g,
+                                       const unsigned char* hdr, unsigned char* Pimg) {
+  const NaisBranch& br = p.branch[0];
+  const Scales* sc = reinterpret_cast<const Scales*>(hdr + 64);
+  const float sA = sc->sA;
+  const int tile = blockIdx.x;
+  for (int i = threadIdx.x; i < TM * g.kx; i += blockDim.x) {
+    const int c = i / TM, r = i - c * TM;
+    const int64_t j = poi_begin + (int64_t)tile * TM + r;
+    __half hi[8], lo[8];
+    if (j < poi_end) {
+      const int64_t jl = j - cat.row_base;
+      for (int e = 0; e < 8; ++e) {
+        const int d = c * 8 + e;
+        const float v = (d < br.w_poi) ? __ldg(br.tgt_poi + (size_t)j * br.w_poi + d)
+                                       : __ldg(br.tgt_reg + (size_t)__ldg(cat.region + jl) * br.w_reg + (d - br.w_poi));
+        split_f16(v * sA, hi[e], lo[e]);
+      }
+    } else {
+      for (int e = 0; e < 8; ++e) hi[e] = lo[e] = __float2half(0.f);
+    }
+    unsigned char* base = Pimg + (size_t)tile * g.a_tile + ((size_t)c * TM + r) * 16;
+    *reinterpret_cast<uint4*>(base) = *reinterpret_cast<uint4*>(hi);
+    *reinterpret_cast<uint4*>(base + g.a_plane) = *reinterpret_cast<uint4*>(lo);
+  }
+}
+
+__device__ __forceinline__ int64_t chunk_base(const int64_t* offsets, int u) { return (offsets[u] + u) >> 1; }
+
+// User operand: grid (chunk slot, user).  One thread = (row n, k-chunk c) -> 8 fp16 (hi) + 8 fp16 (lo).
+__global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g, const unsigned char* hdr, unsigned char* Bimg,
+                                  int max_chunks) {
+  const NaisBranch& br = p.branch[0];
+  const Scales* sc = reinterpret_cast<const Scales*>(hdr + 64);
+  const int* perm = reinterpret_cast<const int*>(hdr + 128);
+  const float* ck = reinterpret_cast<const float*>(hdr + 128 + 4 * 64);
+  const float* uu = reinterpret_cast<const float*>(hdr + 128 + 8 * 64);
+  const int u = blockIdx.y;
+  const int64_t hb = users.offsets[u];
+  const int H = (int)(users.offsets[u + 1] - hb);
+  const int nchunks = (H + 1) >> 1;
+  const int D = g.D, hid = g.hid, ldw = D + g.lanes;
+  __shared__ float q[2][64];
+  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) {
+      const int hs = i / D, d = i - hs * D, h = 2 * chunk + hs;
+      float v = 0.f;
+      if (h < H) {
+        const int64_t e = hb + h;
+        v = (d < br.w_poi) ? __ldg(br.hist_poi + (size_t)__ldg(users.items + e) * br.w_poi + d)
+                           : __ldg(br.hist_reg + (size_t)__ldg(users.region + e) * br.w_reg + (d - br.w_poi));
+      }
+      q[hs][d] = v;
+    }
+    __syncthreads();
+    unsigned char* cb = Bimg + (size_t)(chunk_base(users.offsets, u) - chunk_base(users.offsets, 0) + chunk) * g.b_chunk;
+    for (int i = threadIdx.x; i < g.nrow * (g.kx + 1); i += blockDim.x) {
+      const int c = i / g.nrow, n = i - c * g.nrow;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      int hs = -1, kind = -1, k = 0;  // kind 0 main, 1 S, 2 L
+      if (n < 2 * hid) {
+        hs = n / hid;
+        kind = 0;
+        k = perm[n - hs * hid];
+      } else if (n < 2 * hid + 4) {
+        hs = (n - 2 * hid) >> 1;
+        kind = 1 + ((n - 2 * hid) & 1);
+      }
+      if (kind >= 0 && 2 * chunk + hs < H) {
+        if (c < g.kx) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int d = c * 8 + e;
+            const float qd = q[hs][d];
+            if (kind == 0) v[e] = ck[k] * __ldg(br.w1 + (size_t)k * ldw + d) * qd * sc->sB;
+            else if (kind == 1) v[e] = qd * sc->sS;
+            else v[e] = uu[d] * qd * sc->sB;
+          }
+        } else {  // ext chunk: [2*hs + lane] distance lanes, [4] bias
+          if (kind == 0) {
+            if (g.lanes) {
+              v[2 * hs] = ck[k] * __ldg(br.w1 + (size_t)k * ldw + D) * sc->sBe;
+              v[2 * hs + 1] = ck[k] * __ldg(br.w1 + (size_t)k * ldw + D + 1) * sc->sBe;
+            }
+            v[4] = ck[k] * __ldg(br.b1 + k) * sc->sBe;
+          } else if (kind == 2) {
+            v[2 * hs] = sc->omega0 * sc->sBe;
+            v[2 * hs + 1] = sc->omega1 * sc->sBe;
+            v[4] = sc->omegab * sc->sBe;
+          }
+        }
+      }
+      __half hi[8], lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) split_f16(v[e], hi[e], lo[e]);
+      *reinterpret_cast<uint4*>(cb + ((size_t)c * g.nrow + n) * 16) = *reinterpret_cast<uint4*>(hi);
+      if (g.split) {
+        *reinterpret_cast<uint4*>(cb + g.b_hi + ((size_t)c * g.nrow + n) * 16) = *reinterpret_cast<uint4*>(lo);
+      } else if (n >= 2 * hid && n < 2 * hid + 16) {
+        *reinterpret_cast<uint4*>(cb + g.b_hi + ((size_t)c * 16 + (n - 2 * hid)) * 16) = *reinterpret_cast<uint4*>(lo);
+      }
+    }
+  }
+  (void)max_chunks;
+}
+
+struct MainArgs {
+  NaisParams p;
+  NaisCatalog cat;
+  NaisUsers users;
+  Geo g;
+  int64_t poi_begin, poi_end;
+  int k, exclude, groups;
+  int64_t n_items;
+  const unsigned char* hdr;
+  const unsigned char* Pimg;
+  const unsigned char* Bimg;
+  unsigned long long* part_keys;  // [n_users, groups, k]
+  float* all_scores;              // optional [n_users, range]
+};
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_constant__ MainArgs A) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const Geo& g = A.g;
+  unsigned char* sA = smem;
+  unsigned char* sB = sA + g.tpc * g.a_tile;
+  unsigned char* sE = sB + g.stages * g.b_chunk;          // A_ext: [NBUF][hi 2KB | lo 2KB]
+  unsigned char* sZ = sE + NBUF * 2 * TM * 16;            // 4 KB of zeros (aliased second k-chunk of the ext step)
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(sZ + 4096);  // [SORTN]
+  float* comb = reinterpret_cast<float*>(keys + SORTN);                          // [3][tpc][TM] partials of hslot 1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(comb + 3 * g.tpc * TM);
+  uint64_t* a_full = bars + 0;
+  uint64_t* a_empty = bars + 1;
+  uint64_t* b_full = bars + 2;                 // [MAX_STAGES]
+  uint64_t* b_empty = bars + 2 + MAX_STAGES;   // [MAX_STAGES]
+  uint64_t* e_full = bars + 2 + 2 * MAX_STAGES;          // [NBUF] A_ext written
+  uint64_t* acc_full = e_full + NBUF;                    // [NBUF] MMA done
+  uint64_t* acc_empty = acc_full + NBUF;                 // [NBUF] accumulator drained
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(acc_empty + NBUF);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const Scales sc = *reinterpret_cast<const Scales*>(A.hdr + 64);
+
+  // ---- one-time setup ---------------------------------------------------------------------------------------------
+  for (int i = tid; i < 4096 / 4; i += THREADS) reinterpret_cast<uint32_t*>(sZ)[i] = 0u;
+  // A_ext constant part: column 4 = 1.0 * sAe (hi plane), everything else 0
+  for (int i = tid; i < NBUF * 2 * TM * 4; i += THREADS) reinterpret_cast<uint32_t*>(sE)[i] = 0u;
+  __syncthreads();
+  for (int i = tid; i < NBUF * TM; i += THREADS) {
+    const int b = i / TM, r = i - b * TM;
+    reinterpret_cast<__half*>(sE + (size_t)b * 2 * TM * 16 + r * 16)[4] = __float2half(sc.sAe);
+  }
+  if (tid == 0) {
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    for (int i = 0; i < MAX_STAGES; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < NBUF; ++i) {
+      mbar_init(&e_full[i], EPI_WARPS);
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == EPI_WARPS) tmem_alloc(tslot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+
+  const int tpc = g.tpc;
+  const int64_t cb0 = chunk_base(A.users.offsets, 0);
+
+  if (warp == EPI_WARPS + 1) {
+    // =================================================== bulk-copy producer ========================================
+    if (lane == 0) {
+      uint32_t it = 0, bstep = 0;
+      for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x, ++it) {
+        const int u = (int)(item / A.groups), grp = (int)(item % A.groups);
+        const int H = (int)(A.users.offsets[u + 1] - A.users.offsets[u]);
+        const int nchunks = (H + 1) >> 1;
+        mbar_wait(a_empty, (it & 1) ^ 1);
+        mbar_expect_tx(a_full, (uint32_t)(tpc * g.a_tile));
+        for (int t = 0; t < tpc; ++t)
+          bulk_g2s(sA + (size_t)t * g.a_tile, A.Pimg + ((size_t)grp * tpc + t) * g.a_tile, (uint32_t)g.a_tile, a_full);
+        const unsigned char* src = A.Bimg + (size_t)(chunk_base(A.users.offsets, u) - cb0) * g.b_chunk;
+        for (int c = 0; c < nchunks; ++c, ++bstep) {
+          const int st = bstep % g.stages;
+          mbar_wait(&b_empty[st], ((bstep / g.stages) & 1) ^ 1);
+          mbar_expect_tx(&b_full[st], (uint32_t)g.b_chunk);
+          bulk_g2s(sB + (size_t)st * g.b_chunk, src + (size_t)c * g.b_chunk, (uint32_t)g.b_chunk, &b_full[st]);
+        }
+      }
+    }
+  } else if (warp == EPI_WARPS) {
+    // =================================================== MMA issuer ================================================
+    if (lane == 0) {
+      const uint32_t idN = idesc_f16(TM, g.nrow), id16 = idesc_f16(TM, 16);
+      const uint32_t zaddr = smem_u32(sZ);
+      uint32_t it = 0, bstep = 0, n = 0;
+      for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x, ++it) {
+        const int u = (int)(item / A.groups);
+        const int H = (int)(A.users.offsets[u + 1] - A.users.offsets[u]);
+        const int nchunks = (H + 1) >> 1;
+        mbar_wait(a_full, it & 1);
+        for (int c = 0; c < nchunks; ++c, ++bstep) {
+          const int st = bstep % g.stages;
+          mbar_wait(&b_full[st], (bstep / g.stages) & 1);
+          const uint32_t bhi = smem_u32(sB + (size_t)st * g.b_chunk), blo = bhi + g.b_hi;
+          for (int t = 0; t < tpc; ++t, ++n) {
+            const int buf = n % NBUF;
+            const uint32_t ph = (n / NBUF) & 1;
+            mbar_wait(&e_full[buf], ph);
+            mbar_wait(&acc_empty[buf], ph ^ 1);
+            tc_fence_after();
+            const uint32_t d_t = tmem + buf * ACC_STRIDE;
+            const uint32_t ahi = smem_u32(sA + (size_t)t * g.a_tile), alo = ahi + g.a_plane;
+            const uint32_t ehi = smem_u32(sE + (size_t)buf * 2 * TM * 16), elo = ehi + TM * 16;
+            const uint32_t a_lbo = TM * 16, b_lbo = g.nrow * 16;
+            uint32_t acc = 0;
+            // pass 1: A_hi x B_hi over all rows
+            for (int s = 0; s < g.kx / 2; ++s, acc = 1)
+              mma_f16(d_t, smem_desc(ahi + s * 2 * a_lbo, a_lbo, 128), smem_desc(bhi + s * 2 * b_lbo, b_lbo, 128), idN, acc);
+            {
+              const uint32_t be = bhi + g.kx * b_lbo;
+              mma_f16(d_t, smem_desc(ehi, zaddr - ehi, 128), smem_desc(be, zaddr - be, 128), idN, 1);
+            }
+            if (g.split) {
+              // pass 2: A_hi x B_lo ; pass 3: A_lo x B_hi
+              for (int s = 0; s < g.kx / 2; ++s)
+                mma_f16(d_t, smem_desc(ahi + s * 2 * a_lbo, a_lbo, 128), smem_desc(blo + s * 2 * b_lbo, b_lbo, 128), idN, 1);
+              {
+                const uint32_t be = blo + g.kx * b_lbo;
+                mma_f16(d_t, smem_desc(ehi, zaddr - ehi, 128), smem_desc(be, zaddr - be, 128), idN, 1);
+              }
+              for (int s = 0; s < g.kx / 2; ++s)
+                mma_f16(d_t, smem_desc(alo + s * 2 * a_lbo, a_lbo, 128), smem_desc(bhi + s * 2 * b_lbo, b_lbo, 128), idN, 1);
+              {
+                const uint32_t be = bhi + g.kx * b_lbo;
+                mma_f16(d_t, smem_desc(elo, zaddr - elo, 128), smem_desc(be, zaddr - be, 128), idN, 1);
+              }
+            } else {
+              // S/L rows only (N = 16 at column 2*hid): A_hi x B_lo(aux rows) ; A_lo x B_hi(aux rows)
+              const uint32_t d_aux = d_t + 2 * g.hid;
+              const uint32_t l_lbo = 16 * 16;
+              for (int s = 0; s < g.kx / 2; ++s)
+                mma_f16(d_aux, smem_desc(ahi + s * 2 * a_lbo, a_lbo, 128), smem_desc(blo + s * 2 * l_lbo, l_lbo, 128), id16, 1);
+              {
+                const uint32_t be = blo + g.kx * l_lbo;
+                mma_f16(d_aux, smem_desc(ehi, zaddr - ehi, 128), smem_desc(be, zaddr - be, 128), id16, 1);
+              }
+              const uint32_t bha = bhi + 2 * g.hid * 16;
+              for (int s = 0; s < g.kx / 2; ++s)
+                mma_f16(d_aux, smem_desc(alo + s * 2 * a_lbo, a_lbo, 128), smem_desc(bha + s * 2 * b_lbo, b_lbo, 128), id16, 1);
+              {
+                const uint32_t be = bha + g.kx * b_lbo;
+                mma_f16(d_aux, smem_desc(elo, zaddr - elo, 128), smem_desc(be, zaddr - be, 128), id16, 1);
+              }
+            }
+            mma_commit(&acc_full[buf]);
+          }
+          mma_commit(&b_empty[st]);
+        }
+        mma_commit(a_empty);
+      }
+    }
+  } else {
+    // =================================================== epilogue warps ============================================
+    const int qd = warp & 3, hs = warp >> 2;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    const float w00 = g.lanes ? __ldg(A.p.dist_w + 0) : 0.f, w01 = g.lanes ? __ldg(A.p.dist_w + 1) : 0.f;
+    const float w10 = g.lanes ? __ldg(A.p.dist_w + 2) : 0.f, w11 = g.lanes ? __ldg(A.p.dist_w + 3) : 0.f;
+    const float bd0 = g.lanes ? __ldg(A.p.dist_b + 0) : 0.f, bd1 = g.lanes ? __ldg(A.p.dist_b + 1) : 0.f;
+    const float dscale = A.p.dist_scale, beta = A.p.beta;
+    const int npos = sc.npos, hid = g.hid;
+    uint32_t n = 0;  // global step counter (same sequence as the MMA warp)
+
+    for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x) {
+      const int u = (int)(item / A.groups), grp = (int)(item % A.groups);
+      const int64_t hb = A.users.offsets[u];
+      const int H = (int)(A.users.offsets[u + 1] - hb);
+      const int nchunks = (H + 1) >> 1;
+      const int nsteps = nchunks * tpc;
+      // candidates of this thread's row in the item's tiles
+      float clat[3], clon[3], sumE[3], sumES[3];
+      int64_t jid[3];
+      bool excl[3];
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        jid[t] = A.poi_begin + ((int64_t)grp * tpc + t) * TM + r;
+        const bool v = t < tpc && jid[t] < A.poi_end;
+        clat[t] = (v && g.lanes) ? __ldg(A.cat.coords + 2 * (jid[t] - A.cat.row_base)) : 0.f;
+        clon[t] = (v && g.lanes) ? __ldg(A.cat.coords + 2 * (jid[t] - A.cat.row_base) + 1) : 0.f;
+        sumE[t] = 0.f;
+        sumES[t] = 0.f;
+        excl[t] = false;
+      }
+      // writes g lanes of local step `ls` (chunk = ls / tpc, tile = ls % tpc) into A_ext buffer (n0 + ls) % NBUF
+      auto produce = [&](int ls, uint32_t nglob) {
+        const int c = ls / tpc, t = ls - c * tpc, h = 2 * c + hs;
+        float g0 = 0.f, g1 = 0.f;
+        if (g.lanes && h < H) {
+          const float hla = __ldg(A.users.coords + 2 * (hb + h)), hlo = __ldg(A.users.coords + 2 * (hb + h) + 1);
+          const float ct_la = t == 0 ? clat[0] : (t == 1 ? clat[1] : clat[2]);
+          const float ct_lo = t == 0 ? clon[0] : (t == 1 ? clon[1] : clon[2]);
+          const float l0 = fabsf(ct_la - hla) * dscale, l1 = fabsf(ct_lo - hlo) * dscale;
+          const float z0 = fmaf(l1, w01, fmaf(l0, w00, bd0)), z1 = fmaf(l1, w11, fmaf(l0, w10, bd1));
+          g0 = __fdividef(1.f, 1.f + __expf(-z0)) * sc.sAe;
+          g1 = __fdividef(1.f, 1.f + __expf(-z1)) * sc.sAe;
+        }
+        __half h0, l0h, h1, l1h;
+        split_f16(g0, h0, l0h);
+        split_f16(g1, h1, l1h);
+        unsigned char* eb = sE + (size_t)(nglob % NBUF) * 2 * TM * 16 + r * 16 + hs * 4;
+        *reinterpret_cast<__half2*>(eb) = __halves2half2(h0, h1);
+        *reinterpret_cast<__half2*>(eb + TM * 16) = __halves2half2(l0h, l1h);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&e_full[nglob % NBUF]);
+      };
+      const uint32_t n0 = n;
+      for (int ls = 0; ls < NBUF && ls < nsteps; ++ls) produce(ls, n0 + ls);
+
+      for (int ls = 0; ls < nsteps; ++ls, ++n) {
+        const int c = ls / tpc, t = ls - c * tpc, h = 2 * c + hs;
+        const int buf = n % NBUF;
+        const int hist_id = (h < H) ? __ldg(A.users.items + hb + h) : -1;
+        mbar_wait(&acc_full[buf], (n / NBUF) & 1);
+        tc_fence_after();
+        // MMA(n) is complete: its A_ext buffer is free again -> produce step ls + NBUF into it
+        if (ls + NBUF < nsteps) produce(ls + NBUF, n + NBUF);
+        // ---- drain this thread's 1 x (hid + 2) slice of the accumulator ---------------------------------------------
+        const uint32_t t_main = tmem + lane_addr + buf * ACC_STRIDE + hs * hid;
+        const uint32_t t_aux = tmem + lane_addr + buf * ACC_STRIDE + 2 * hid + 2 * hs;
+        float accp = 0.f, accn = 0.f;
+        uint32_t aux[2];
+        tmem_ld2(t_aux, aux);
+        for (int c0 = 0; c0 < hid; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_main + c0, v);
+          tmem_wait_ld();
+          if (c0 + 16 <= npos) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) accp += fabsf(__uint_as_float(v[i]));
+          } else if (c0 >= npos) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) accn += fabsf(__uint_as_float(v[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float av = fabsf(__uint_as_float(v[i]));
+              if (c0 + i < npos) accp += av;
+              else accn += av;
+            }
+          }
+        }
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        const float S = __uint_as_float(aux[0]) * sc.inv_s;
+        const float a = (__uint_as_float(aux[1]) + (accp - accn)) * sc.inv_sigma;
+        if (h < H) {
+          const int64_t j = t == 0 ? jid[0] : (t == 1 ? jid[1] : jid[2]);
+          if ((int64_t)hist_id != j) {
+            const float e = __expf(a);
+            if (t == 0) { sumE[0] += e; sumES[0] = fmaf(e, S, sumES[0]); }
+            else if (t == 1) { sumE[1] += e; sumES[1] = fmaf(e, S, sumES[1]); }
+            else { sumE[2] += e; sumES[2] = fmaf(e, S, sumES[2]); }
+          } else {
+            if (t == 0) excl[0] = true;
+            else if (t == 1) excl[1] = true;
+            else excl[2] = true;
+          }
+        }
+      }
+      // ---- item epilogue: combine the two history slots, score, block top-k ------------------------------------------
+      epi_bar();  // previous item's readers of keys/comb are done
+      if (hs == 1) {
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+          if (t < tpc) {
+            comb[(0 * tpc + t) * TM + r] = sumE[t];
+            comb[(1 * tpc + t) * TM + r] = sumES[t];
+            comb[(2 * tpc + t) * TM + r] = excl[t] ? 1.f : 0.f;
+          }
+      }
+      epi_bar();
+      if (hs == 0) {
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+          if (t < tpc) {
+            const float E = sumE[t] + comb[(0 * tpc + t) * TM + r];
+            const float ES = sumES[t] + comb[(1 * tpc + t) * TM + r];
+            const bool ex = excl[t] || comb[(2 * tpc + t) * TM + r] != 0.f;
+            const float score = ES / powf(E, beta);
+            const bool valid = jid[t] < A.poi_end;
+            if (A.all_scores && valid) A.all_scores[(size_t)u * (A.poi_end - A.poi_begin) + (jid[t] - A.poi_begin)] = score;
+            keys[t * TM + r] = (valid && !(A.exclude && ex)) ? make_key(score, (int)jid[t]) : 0ull;
+          }
+        for (int i = tpc * TM + r; i < SORTN; i += TM) keys[i] = 0ull;
+      }
+      epi_bar();
+      // bitonic sort (descending) of SORTN keys by the 256 epilogue threads
+      for (int kk = 2; kk <= SORTN; kk <<= 1) {
+        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+          for (int i = tid; i < SORTN; i += EPI_WARPS * 32) {
+            const int ixj = i ^ jj;
+            if (ixj > i) {
+              const unsigned long long x = keys[i], y = keys[ixj];
+              const bool desc = (i & kk) == 0;
+              if (desc ? (x < y) : (x > y)) {
+                keys[i] = y;
+                keys[ixj] = x;
+              }
+            }
+          }
+          epi_bar();
+        }
+      }
+      for (int i = tid; i < A.k; i += EPI_WARPS * 32) A.part_keys[((size_t)u * A.groups + grp) * A.k + i] = keys[i];
+    }
+  }
+  // ---- teardown ---------------------------------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == EPI_WARPS) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+int launch_topk_merge(const unsigned long long* in_keys, const float* in_score, const int32_t* in_id, int n_users,
+                      int n_lists, int k, float* out_score, int32_t* out_id, cudaStream_t stream);
+int launch_topk_merge_keys_multi(unsigned long long* keys, unsigned long long* scratch, int n_users, int n_lists, int k,
+                                 float* out_score, int32_t* out_id, cudaStream_t stream);
+
+static inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
+
+struct TcLayout {
+  size_t hdr, pimg, bimg, keys, scratch, total;
+  int groups, n_tiles_pad;
+  int64_t max_chunks;
+};
+
+static bool tc_layout(const NaisParams& p, int n_users, int64_t nnz, int64_t poi_begin, int64_t poi_end, int k, int precision,
+                      tc::Geo& g, TcLayout& L) {
+  if (!tc::make_geo(p, precision, g)) return false;
+  const int64_t range = poi_end - poi_begin;
+  const int64_t tiles = (range + tc::TM - 1) / tc::TM;
+  L.groups = (int)((tiles + g.tpc - 1) / g.tpc);
+  if (L.groups < 1) L.groups = 1;
+  L.n_tiles_pad = L.groups * g.tpc;
+  L.max_chunks = (nnz + n_users) / 2 + 2;
+  size_t o = 0;
+  L.hdr = o;
+  o += tc::HDR_BYTES;
+  L.pimg = o;
+  o += al256((size_t)L.n_tiles_pad * g.a_tile);
+  L.bimg = o;
+  o += al256((size_t)L.max_chunks * g.b_chunk);
+  L.keys = o;
+  o += al256((size_t)n_users * L.groups * k * 8);
+  L.scratch = o;
+  o += al256((size_t)n_users * ((L.groups + 63) / 64) * k * 8);
+  L.total = o;
+  return true;
+}
+
+bool tc_supported(const NaisParams& p) {
+  tc::Geo g;
+  return tc::make_geo(p, NAIS_PREC_TC_SPLIT, g);
+}
+
+size_t fullrank_tc_workspace_bytes(const NaisParams& p, int n_users, int64_t nnz, int64_t poi_begin, int64_t poi_end, int k,
+                                   int precision) {
+  tc::Geo g;
+  TcLayout L;
+  if (!tc_layout(p, n_users, nnz, poi_begin, poi_end, k, precision, g, L)) return 0;
+  return L.total + 1024 + (size_t)n_users * 8;
+}
+
+int launch_fullrank_tc(const NaisParams& p, const NaisCatalog& cat, const NaisUsers& users, int64_t poi_begin,
+                       int64_t poi_end, int k, int exclude, int precision, float* out_score, int32_t* out_id,
+                       float* all_scores, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (users.n_users == 0 || poi_end <= poi_begin) return 0;
+  int dev = 0, major = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) return NAIS_ERR_ARCH;
+  // nnz is not known to the library (offsets live on the device): the caller sized the workspace with it; recover the
+  // chunk capacity from the workspace size instead.
+  tc::Geo g;
+  if (!tc::make_geo(p, precision, g)) return NAIS_ERR_SHAPE;
+  const int64_t range = poi_end - poi_begin;
+  const int64_t tiles = (range + tc::TM - 1) / tc::TM;
+  const int groups = (int)((tiles + g.tpc - 1) / g.tpc);
+  const int n_tiles_pad = groups * g.tpc;
+  unsigned char* base = reinterpret_cast<unsigned char*>(ws);
+  size_t o = 0;
+  unsigned char* hdr = base + o;
+  o += tc::HDR_BYTES;
+  unsigned char* pimg = base + o;
+  o += al256((size_t)n_tiles_pad * g.a_tile);
+  const size_t keys_bytes = al256((size_t)users.n_users * groups * k * 8);
+  const size_t scratch_bytes = al256((size_t)users.n_users * ((groups + 63) / 64) * k * 8);
+  if (ws_bytes < o + keys_bytes + scratch_bytes + g.b_chunk) return NAIS_ERR_WORKSPACE;
+  const size_t bimg_bytes = (ws_bytes - o - keys_bytes - scratch_bytes) / 256 * 256;
+  unsigned char* bimg = base + o;
+  o += bimg_bytes;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(base + o);
+  o += keys_bytes;
+  unsigned long long* scratch = reinterpret_cast<unsigned long long*>(base + o);
+  const int64_t max_chunks = (int64_t)(bimg_bytes / g.b_chunk);
+
+  const NaisBranch& br = p.branch[0];
+  cudaError_t e = cudaMemsetAsync(hdr, 0, tc::HDR_BYTES, stream);
+  if (e != cudaSuccess) return (int)e;
+  unsigned* mx = reinterpret_cast<unsigned*>(hdr);
+  auto amax = [&](const float* x, size_t n, unsigned* out) {
+    if (!x || n == 0) return;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 592) blocks = 592;
+    tc::absmax_kernel<<<blocks, 256, 0, stream>>>(x, n, out);
+    NAIS_COUNT_LAUNCH(1);
+  };
+  amax(br.tgt_poi, (size_t)p.item_num * br.w_poi, mx + 0);
+  amax(br.tgt_reg, (size_t)p.region_num * br.w_reg, mx + 1);
+  amax(br.hist_poi, (size_t)p.item_num * br.w_poi, mx + 2);
+  amax(br.hist_reg, (size_t)p.region_num * br.w_reg, mx + 3);
+  tc::scales_kernel<<<1, 256, 0, stream>>>(p, hdr);
+  NAIS_COUNT_LAUNCH(1);
+  tc::pack_candidates_kernel<<<n_tiles_pad, 256, 0, stream>>>(p, cat, poi_begin, poi_end, g, hdr, pimg);
+  NAIS_COUNT_LAUNCH(1);
+  {
+    dim3 grid(64, users.n_users);
+    tc::pack_users_kernel<<<grid, 256, 0, stream>>>(p, users, g, hdr, bimg, (int)max_chunks);
+    NAIS_COUNT_LAUNCH(1);
+  }
+  tc::MainArgs A;
+  A.p = p;
+  A.cat = cat;
+  A.users = users;
+  A.g = g;
+  A.poi_begin = poi_begin;
+  A.poi_end = poi_end;
+  A.k = k;
+  A.exclude = exclude;
+  A.groups = groups;
+  A.n_items = (int64_t)users.n_users * groups;
+  A.hdr = hdr;
+  A.Pimg = pimg;
+  A.Bimg = bimg;
+  A.part_keys = keys;
+  A.all_scores = all_scores;
+  e = cudaFuncSetAttribute(tc::fullrank_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes);
+  if (e != cudaSuccess) return (int)e;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)(A.n_items < sms ? A.n_items : sms);
+  tc::fullrank_tc_kernel<<<grid, tc::THREADS, g.smem_bytes, stream>>>(A);
+  NAIS_COUNT_LAUNCH(1);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  return launch_topk_merge_keys_multi(keys, scratch, users.n_users, groups, k, out_score, out_id, stream);
+}
+
 }  // namespace nais

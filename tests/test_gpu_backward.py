@@ -53,6 +53,8 @@ def test_gradients_shapes_vs_oracle_autograd(H, B, D, hid):
     tgt = rng.integers(0, N, B).astype(np.int64)
     if H > 1:
         tgt[::3] = hist[::3, H // 2]  # training positives: live mask
+    else:
+        tgt = np.where(tgt == hist[:, 0], (tgt + 1) % N, tgt)  # an all-masked row is NaN in the reference too
     aux = orc.latlon_abs_diff(coords, tgt, hist)
     dscore = rng.normal(size=B)
     m = util.make_model("region_distance", sd, beta)
