@@ -15,10 +15,11 @@
 //     pre-scaling), D += A_hi B_hi + A_hi B_lo + A_lo B_hi  (NAIS_PREC_TC_SPLIT).  NAIS_PREC_TC_FAST keeps the three
 //     passes only for the S/L rows (an N=16 MMA at a column offset) and runs the main rows single-pass.
 //
-// Warp roles (320 threads, 1 CTA/SM, persistent over work items = (user, 3 candidate tiles)):
-//   warps 0-7  epilogue: lane quarter = warp%4, history slot = warp/4; produce A_ext, TMEM -> registers, beta-softmax state
-//   warp 8     MMA issuer (one elected lane) + TMEM allocation
-//   warp 9     bulk-copy producer (one elected lane): A tiles per item, B chunks through a ring of stages
+// Warp roles (576 threads, 1 CTA/SM, persistent over work items = (user, 3 candidate tiles)):
+//   warps 0-15 epilogue, two groups of 8 alternating steps: lane quarter = warp%4, history slot = (warp/4)%2;
+//              produce A_ext, TMEM -> registers, beta-softmax state
+//   warp 16    MMA issuer (one elected lane) + TMEM allocation
+//   warp 17    bulk-copy producer (one elected lane): A tiles per item, B chunks through a ring of stages
 #include <cuda_fp16.h>
 
 #include "nais_common.cuh"
@@ -33,10 +34,14 @@ namespace tc {
 constexpr int TM = 128;
 constexpr int NBUF = 3;          // TMEM accumulator buffers == A_ext buffers == look-ahead of the g producer
 constexpr int ACC_STRIDE = 160;  // TMEM columns per accumulator buffer
-constexpr int EPI_WARPS = 8;
+constexpr int TPC = 3;           // candidate tiles per work item
+constexpr int EPI_WARPS = 16;    // two groups of 8 alternate steps
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int ARRIVE_WARPS = 8;  // warps that arrive per step on e_full / acc_empty (one group)
 constexpr int THREADS = (EPI_WARPS + 2) * 32;
 constexpr int MAX_STAGES = 3;
 constexpr int SORTN = 512;
+constexpr int HMETA = 512;      // history items whose id/coords are staged in smem per item (longer ones: __ldg)
 
 struct Geo {
   int D, hid, lanes, split;
@@ -69,10 +74,10 @@ __host__ inline bool make_geo(const NaisParams& p, int precision, Geo& g) {
   g.b_hi = (g.kx + 1) * g.nrow * 16;
   g.b_lo = g.split ? g.b_hi : (g.kx + 1) * 16 * 16;
   g.b_chunk = g.b_hi + g.b_lo;
-  g.tpc = 3;
+  g.tpc = TPC;
   g.stages = g.split ? 2 : 3;
   // smem: A tiles | B stages | A_ext (hi,lo) x NBUF | zero | keys | comb | barriers
-  g.smem_bytes = g.tpc * g.a_tile + g.stages * g.b_chunk + NBUF * 2 * TM * 16 + 4096 + SORTN * 8 + 3 * g.tpc * TM * 4 + 256 + 128;
+  g.smem_bytes = g.tpc * g.a_tile + g.stages * g.b_chunk + NBUF * 2 * TM * 16 + 4096 + SORTN * 8 + 9 * g.tpc * TM * 4 + 3 * HMETA * 4 + 256 + 128;
   return g.smem_bytes <= 227 * 1024;
 }
 
@@ -303,7 +308,7 @@ struct MainArgs {
   float* all_scores;              // optional [n_users, range]
 };
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_constant__ MainArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -314,14 +319,18 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
   unsigned char* sZ = sE + NBUF * 2 * TM * 16;            // 4 KB of zeros (aliased second k-chunk of the ext step)
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(sZ + 4096);  // [SORTN]
   float* comb = reinterpret_cast<float*>(keys + SORTN);                          // [3][tpc][TM] partials of hslot 1
-  uint64_t* bars = reinterpret_cast<uint64_t*>(comb + 3 * g.tpc * TM);
+  int* hm_id = reinterpret_cast<int*>(comb + 9 * g.tpc * TM);                    // [HMETA]
+  float* hm_la = reinterpret_cast<float*>(hm_id + HMETA);
+  float* hm_lo = hm_la + HMETA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(hm_lo + HMETA);
   uint64_t* a_full = bars + 0;
   uint64_t* a_empty = bars + 1;
   uint64_t* b_full = bars + 2;                 // [MAX_STAGES]
   uint64_t* b_empty = bars + 2 + MAX_STAGES;   // [MAX_STAGES]
   uint64_t* e_full = bars + 2 + 2 * MAX_STAGES;          // [NBUF] A_ext written
-  uint64_t* acc_full = e_full + NBUF;                    // [NBUF] MMA done
-  uint64_t* acc_empty = acc_full + NBUF;                 // [NBUF] accumulator drained
+  uint64_t* acc_full = e_full + NBUF;                    // [2][NBUF] MMA done, one set per epilogue group: a parity
+                                                          // wait is only valid if the waiter observes EVERY phase in order
+  uint64_t* acc_empty = acc_full + 2 * NBUF;             // [NBUF] accumulator drained
   uint32_t* tslot = reinterpret_cast<uint32_t*>(acc_empty + NBUF);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -344,9 +353,10 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       mbar_init(&b_empty[i], 1);
     }
     for (int i = 0; i < NBUF; ++i) {
-      mbar_init(&e_full[i], EPI_WARPS);
+      mbar_init(&e_full[i], ARRIVE_WARPS);
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], EPI_WARPS);
+      mbar_init(&acc_full[NBUF + i], 1);
+      mbar_init(&acc_empty[i], ARRIVE_WARPS);
     }
     fence_barrier_init();
   }
@@ -362,100 +372,135 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
 
   if (warp == EPI_WARPS + 1) {
     // =================================================== bulk-copy producer ========================================
-    if (lane == 0) {
+    // (warp-uniform control flow, one elected lane issues; see the MMA warp)
+    {
       uint32_t it = 0, bstep = 0;
       for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x, ++it) {
         const int u = (int)(item / A.groups), grp = (int)(item % A.groups);
-        const int H = (int)(A.users.offsets[u + 1] - A.users.offsets[u]);
+        const int H = __shfl_sync(0xffffffffu, (int)(A.users.offsets[u + 1] - A.users.offsets[u]), 0);
+        const int64_t cbu = __shfl_sync(0xffffffffu, chunk_base(A.users.offsets, u) - cb0, 0);
         const int nchunks = (H + 1) >> 1;
         mbar_wait(a_empty, (it & 1) ^ 1);
-        mbar_expect_tx(a_full, (uint32_t)(tpc * g.a_tile));
-        for (int t = 0; t < tpc; ++t)
-          bulk_g2s(sA + (size_t)t * g.a_tile, A.Pimg + ((size_t)grp * tpc + t) * g.a_tile, (uint32_t)g.a_tile, a_full);
-        const unsigned char* src = A.Bimg + (size_t)(chunk_base(A.users.offsets, u) - cb0) * g.b_chunk;
+        if (elect_one()) {
+          mbar_expect_tx(a_full, (uint32_t)(tpc * g.a_tile));
+          for (int t = 0; t < tpc; ++t)
+            bulk_g2s(sA + (size_t)t * g.a_tile, A.Pimg + ((size_t)grp * tpc + t) * g.a_tile, (uint32_t)g.a_tile, a_full);
+        }
+        __syncwarp();
+        const unsigned char* src = A.Bimg + (size_t)cbu * g.b_chunk;
         for (int c = 0; c < nchunks; ++c, ++bstep) {
           const int st = bstep % g.stages;
           mbar_wait(&b_empty[st], ((bstep / g.stages) & 1) ^ 1);
-          mbar_expect_tx(&b_full[st], (uint32_t)g.b_chunk);
-          bulk_g2s(sB + (size_t)st * g.b_chunk, src + (size_t)c * g.b_chunk, (uint32_t)g.b_chunk, &b_full[st]);
+          if (elect_one()) {
+            mbar_expect_tx(&b_full[st], (uint32_t)g.b_chunk);
+            bulk_g2s(sB + (size_t)st * g.b_chunk, src + (size_t)c * g.b_chunk, (uint32_t)g.b_chunk, &b_full[st]);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == EPI_WARPS) {
     // =================================================== MMA issuer ================================================
-    if (lane == 0) {
+    // One thread issues 3*(D/16+1) MMAs per step, so the issue path must be a handful of integer ops per MMA: every
+    // shared-memory descriptor is (constant high word, low word = base + index*delta), and a K-step only adds a
+    // constant to the 14-bit start-address field of the low word.
+    // The whole warp runs the (warp-uniform) control flow so descriptors live in uniform registers; only the MMA and
+    // commit instructions are predicated on one elected lane (a `if (lane == 0)` region would make ptxas wrap every
+    // UTCHMMA in an R2UR waterfall loop, ~130 clk per MMA).
+    {
       const uint32_t idN = idesc_f16(TM, g.nrow), id16 = idesc_f16(TM, 16);
       const uint32_t zaddr = smem_u32(sZ);
-      uint32_t it = 0, bstep = 0, n = 0;
+      const uint32_t a_lbo = TM * 16, b_lbo = g.nrow * 16, l_lbo = 16 * 16;
+      const uint32_t a_step = (2 * a_lbo) >> 4, b_step = (2 * b_lbo) >> 4, l_step = (2 * l_lbo) >> 4;
+      const uint32_t hi_word = (uint32_t)(smem_desc(0, 0, 128) >> 32);  // SBO = 128 B, version 1, no swizzle
+      auto lo_of = [](uint32_t addr, uint32_t lbo) { return ((addr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); };
+      auto mk = [&](uint32_t lo) { return ((uint64_t)hi_word << 32) | lo; };
+      const uint32_t sa0 = smem_u32(sA), sb0 = smem_u32(sB), se0 = smem_u32(sE);
+      // low words for index 0 and the per-index deltas (all linear in the tile / buffer / stage index)
+      const uint32_t A_hi0 = lo_of(sa0, a_lbo), A_lo0 = lo_of(sa0 + g.a_plane, a_lbo), A_d = (uint32_t)g.a_tile >> 4;
+      const uint32_t E_hi0 = lo_of(se0, zaddr - se0), E_lo0 = lo_of(se0 + TM * 16, zaddr - se0 - TM * 16);
+      const uint32_t E_d = ((2 * TM * 16) >> 4) - (((2 * TM * 16) >> 4) << 16);
+      const uint32_t bc = (uint32_t)g.b_chunk >> 4;
+      const uint32_t B_d = bc, Bz_d = bc - (bc << 16);  // plain / zero-aliased-LBO descriptors
+      const uint32_t bex = sb0 + g.kx * b_lbo, blo0 = sb0 + g.b_hi;
+      const uint32_t B_hi0 = lo_of(sb0, b_lbo), Be_hi0 = lo_of(bex, zaddr - bex);
+      uint32_t B_lo0 = 0, Be_lo0 = 0, Ba_hi0 = 0, Bae_hi0 = 0, Ba_lo0 = 0, Bae_lo0 = 0;
+      if (g.split) {
+        B_lo0 = lo_of(blo0, b_lbo);
+        Be_lo0 = lo_of(blo0 + g.kx * b_lbo, zaddr - (blo0 + g.kx * b_lbo));
+      } else {
+        const uint32_t bha = sb0 + 2 * g.hid * 16;
+        Ba_hi0 = lo_of(bha, b_lbo);                                               // S/L rows of the hi plane
+        Bae_hi0 = lo_of(bha + g.kx * b_lbo, zaddr - (bha + g.kx * b_lbo));
+        Ba_lo0 = lo_of(blo0, l_lbo);                                              // S/L rows, lo image (16 rows)
+        Bae_lo0 = lo_of(blo0 + g.kx * l_lbo, zaddr - (blo0 + g.kx * l_lbo));
+      }
+      const int ksteps = g.kx / 2;
+      const bool split = g.split != 0;
+      uint32_t it = 0, bstep = 0, n = 0, st = 0, stph = 0, buf = 0, ph = 0;
       for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x, ++it) {
         const int u = (int)(item / A.groups);
-        const int H = (int)(A.users.offsets[u + 1] - A.users.offsets[u]);
+        const int H = __shfl_sync(0xffffffffu, (int)(A.users.offsets[u + 1] - A.users.offsets[u]), 0);
         const int nchunks = (H + 1) >> 1;
         mbar_wait(a_full, it & 1);
         for (int c = 0; c < nchunks; ++c, ++bstep) {
-          const int st = bstep % g.stages;
-          mbar_wait(&b_full[st], (bstep / g.stages) & 1);
-          const uint32_t bhi = smem_u32(sB + (size_t)st * g.b_chunk), blo = bhi + g.b_hi;
-          for (int t = 0; t < tpc; ++t, ++n) {
-            const int buf = n % NBUF;
-            const uint32_t ph = (n / NBUF) & 1;
+          mbar_wait(&b_full[st], stph);
+          const uint32_t bh = B_hi0 + st * B_d, beh = Be_hi0 + st * Bz_d;
+          const uint32_t bl = B_lo0 + st * B_d, bel = Be_lo0 + st * Bz_d;
+          const uint32_t bah = Ba_hi0 + st * B_d, baeh = Bae_hi0 + st * Bz_d;
+          const uint32_t bal = Ba_lo0 + st * B_d, bael = Bae_lo0 + st * Bz_d;
+#pragma unroll
+          for (int t = 0; t < TPC; ++t, ++n) {
+            const uint32_t ah = A_hi0 + t * A_d, al = A_lo0 + t * A_d;
+            const uint32_t eh = E_hi0 + buf * E_d, el = E_lo0 + buf * E_d;
+            const uint32_t d_t = tmem + buf * ACC_STRIDE;
             mbar_wait(&e_full[buf], ph);
             mbar_wait(&acc_empty[buf], ph ^ 1);
             tc_fence_after();
-            const uint32_t d_t = tmem + buf * ACC_STRIDE;
-            const uint32_t ahi = smem_u32(sA + (size_t)t * g.a_tile), alo = ahi + g.a_plane;
-            const uint32_t ehi = smem_u32(sE + (size_t)buf * 2 * TM * 16), elo = ehi + TM * 16;
-            const uint32_t a_lbo = TM * 16, b_lbo = g.nrow * 16;
-            uint32_t acc = 0;
+            if (elect_one()) {
             // pass 1: A_hi x B_hi over all rows
-            for (int s = 0; s < g.kx / 2; ++s, acc = 1)
-              mma_f16(d_t, smem_desc(ahi + s * 2 * a_lbo, a_lbo, 128), smem_desc(bhi + s * 2 * b_lbo, b_lbo, 128), idN, acc);
-            {
-              const uint32_t be = bhi + g.kx * b_lbo;
-              mma_f16(d_t, smem_desc(ehi, zaddr - ehi, 128), smem_desc(be, zaddr - be, 128), idN, 1);
-            }
-            if (g.split) {
+            for (int s = 0; s < ksteps; ++s) mma_f16(d_t, mk(ah + s * a_step), mk(bh + s * b_step), idN, s > 0);
+            mma_f16(d_t, mk(eh), mk(beh), idN, 1);
+            if (split) {
               // pass 2: A_hi x B_lo ; pass 3: A_lo x B_hi
-              for (int s = 0; s < g.kx / 2; ++s)
-                mma_f16(d_t, smem_desc(ahi + s * 2 * a_lbo, a_lbo, 128), smem_desc(blo + s * 2 * b_lbo, b_lbo, 128), idN, 1);
-              {
-                const uint32_t be = blo + g.kx * b_lbo;
-                mma_f16(d_t, smem_desc(ehi, zaddr - ehi, 128), smem_desc(be, zaddr - be, 128), idN, 1);
-              }
-              for (int s = 0; s < g.kx / 2; ++s)
-                mma_f16(d_t, smem_desc(alo + s * 2 * a_lbo, a_lbo, 128), smem_desc(bhi + s * 2 * b_lbo, b_lbo, 128), idN, 1);
-              {
-                const uint32_t be = bhi + g.kx * b_lbo;
-                mma_f16(d_t, smem_desc(elo, zaddr - elo, 128), smem_desc(be, zaddr - be, 128), idN, 1);
-              }
+              for (int s = 0; s < ksteps; ++s) mma_f16(d_t, mk(ah + s * a_step), mk(bl + s * b_step), idN, 1);
+              mma_f16(d_t, mk(eh), mk(bel), idN, 1);
+              for (int s = 0; s < ksteps; ++s) mma_f16(d_t, mk(al + s * a_step), mk(bh + s * b_step), idN, 1);
+              mma_f16(d_t, mk(el), mk(beh), idN, 1);
             } else {
               // S/L rows only (N = 16 at column 2*hid): A_hi x B_lo(aux rows) ; A_lo x B_hi(aux rows)
               const uint32_t d_aux = d_t + 2 * g.hid;
-              const uint32_t l_lbo = 16 * 16;
-              for (int s = 0; s < g.kx / 2; ++s)
-                mma_f16(d_aux, smem_desc(ahi + s * 2 * a_lbo, a_lbo, 128), smem_desc(blo + s * 2 * l_lbo, l_lbo, 128), id16, 1);
-              {
-                const uint32_t be = blo + g.kx * l_lbo;
-                mma_f16(d_aux, smem_desc(ehi, zaddr - ehi, 128), smem_desc(be, zaddr - be, 128), id16, 1);
-              }
-              const uint32_t bha = bhi + 2 * g.hid * 16;
-              for (int s = 0; s < g.kx / 2; ++s)
-                mma_f16(d_aux, smem_desc(alo + s * 2 * a_lbo, a_lbo, 128), smem_desc(bha + s * 2 * b_lbo, b_lbo, 128), id16, 1);
-              {
-                const uint32_t be = bha + g.kx * b_lbo;
-                mma_f16(d_aux, smem_desc(elo, zaddr - elo, 128), smem_desc(be, zaddr - be, 128), id16, 1);
-              }
+              for (int s = 0; s < ksteps; ++s) mma_f16(d_aux, mk(ah + s * a_step), mk(bal + s * l_step), id16, 1);
+              mma_f16(d_aux, mk(eh), mk(bael), id16, 1);
+              for (int s = 0; s < ksteps; ++s) mma_f16(d_aux, mk(al + s * a_step), mk(bah + s * b_step), id16, 1);
+              mma_f16(d_aux, mk(el), mk(baeh), id16, 1);
             }
-            mma_commit(&acc_full[buf]);
+            mma_commit(&acc_full[(c & 1) * NBUF + buf]);
+            }
+            __syncwarp();
+            if (++buf == NBUF) {
+              buf = 0;
+              ph ^= 1;
+            }
           }
-          mma_commit(&b_empty[st]);
+          if (elect_one()) mma_commit(&b_empty[st]);
+          __syncwarp();
+          if (++st == (uint32_t)g.stages) {
+            st = 0;
+            stph ^= 1;
+          }
         }
-        mma_commit(a_empty);
+        if (elect_one()) mma_commit(a_empty);
+        __syncwarp();
       }
     }
   } else {
     // =================================================== epilogue warps ============================================
-    const int qd = warp & 3, hs = warp >> 2;
+    // Two groups of 8 warps alternate history chunks (group = parity of the chunk index), so one group's TMEM-load /
+    // exp latencies hide behind the other's FADD stream.  Within a group: lane quarter = warp % 4 (the TMEM
+    // lanes a warp may touch), history slot = (warp / 4) % 2.
+    const int egrp = warp >> 3;
+    const int qd = warp & 3, hs = (warp >> 2) & 1;
     const int r = qd * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
     const float w00 = g.lanes ? __ldg(A.p.dist_w + 0) : 0.f, w01 = g.lanes ? __ldg(A.p.dist_w + 1) : 0.f;
@@ -463,91 +508,135 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
     const float bd0 = g.lanes ? __ldg(A.p.dist_b + 0) : 0.f, bd1 = g.lanes ? __ldg(A.p.dist_b + 1) : 0.f;
     const float dscale = A.p.dist_scale, beta = A.p.beta;
     const int npos = sc.npos, hid = g.hid;
-    uint32_t n = 0;  // global step counter (same sequence as the MMA warp)
+    uint32_t n0 = 0;  // global index of the current item's first step (same sequence as the MMA warp)
+    uint32_t phbits = 0;  // phase parity of this group's acc_full barrier, one bit per buffer
 
     for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x) {
       const int u = (int)(item / A.groups), grp = (int)(item % A.groups);
       const int64_t hb = A.users.offsets[u];
       const int H = (int)(A.users.offsets[u + 1] - hb);
       const int nchunks = (H + 1) >> 1;
-      const int nsteps = nchunks * tpc;
+      const int nsteps = nchunks * TPC;
+      // stage this user's history ids / coords (previous item's readers are past their last epi_bar)
+      epi_bar();
+      for (int i = tid; i < H && i < HMETA; i += EPI_THREADS) {
+        hm_id[i] = __ldg(A.users.items + hb + i);
+        hm_la[i] = g.lanes ? __ldg(A.users.coords + 2 * (hb + i)) : 0.f;
+        hm_lo[i] = g.lanes ? __ldg(A.users.coords + 2 * (hb + i) + 1) : 0.f;
+      }
       // candidates of this thread's row in the item's tiles
-      float clat[3], clon[3], sumE[3], sumES[3];
-      int64_t jid[3];
-      bool excl[3];
+      float clat[TPC], clon[TPC], sumE[TPC], sumES[TPC];
+      int64_t jid[TPC];
+      bool excl[TPC];
 #pragma unroll
-      for (int t = 0; t < 3; ++t) {
-        jid[t] = A.poi_begin + ((int64_t)grp * tpc + t) * TM + r;
-        const bool v = t < tpc && jid[t] < A.poi_end;
+      for (int t = 0; t < TPC; ++t) {
+        jid[t] = A.poi_begin + ((int64_t)grp * TPC + t) * TM + r;
+        const bool v = jid[t] < A.poi_end;
         clat[t] = (v && g.lanes) ? __ldg(A.cat.coords + 2 * (jid[t] - A.cat.row_base)) : 0.f;
         clon[t] = (v && g.lanes) ? __ldg(A.cat.coords + 2 * (jid[t] - A.cat.row_base) + 1) : 0.f;
         sumE[t] = 0.f;
         sumES[t] = 0.f;
         excl[t] = false;
       }
-      // writes g lanes of local step `ls` (chunk = ls / tpc, tile = ls % tpc) into A_ext buffer (n0 + ls) % NBUF
-      auto produce = [&](int ls, uint32_t nglob) {
-        const int c = ls / tpc, t = ls - c * tpc, h = 2 * c + hs;
+      epi_bar();
+      // writes the g lanes of local step m into A_ext buffer (n0 + m) % NBUF
+      auto produce = [&](int m) {
+        const int pc = m / TPC, pt = m - pc * TPC;
+        const uint32_t pbuf = (n0 + (uint32_t)m) % NBUF;
+        const int h = 2 * pc + hs;
         float g0 = 0.f, g1 = 0.f;
         if (g.lanes && h < H) {
-          const float hla = __ldg(A.users.coords + 2 * (hb + h)), hlo = __ldg(A.users.coords + 2 * (hb + h) + 1);
-          const float ct_la = t == 0 ? clat[0] : (t == 1 ? clat[1] : clat[2]);
-          const float ct_lo = t == 0 ? clon[0] : (t == 1 ? clon[1] : clon[2]);
+          float hla, hlo;
+          if (h < HMETA) {
+            hla = hm_la[h];
+            hlo = hm_lo[h];
+          } else {
+            hla = __ldg(A.users.coords + 2 * (hb + h));
+            hlo = __ldg(A.users.coords + 2 * (hb + h) + 1);
+          }
+          const float ct_la = pt == 0 ? clat[0] : (pt == 1 ? clat[1] : clat[2]);
+          const float ct_lo = pt == 0 ? clon[0] : (pt == 1 ? clon[1] : clon[2]);
           const float l0 = fabsf(ct_la - hla) * dscale, l1 = fabsf(ct_lo - hlo) * dscale;
           const float z0 = fmaf(l1, w01, fmaf(l0, w00, bd0)), z1 = fmaf(l1, w11, fmaf(l0, w10, bd1));
-          g0 = __fdividef(1.f, 1.f + __expf(-z0)) * sc.sAe;
-          g1 = __fdividef(1.f, 1.f + __expf(-z1)) * sc.sAe;
+          g0 = __fdividef(sc.sAe, 1.f + __expf(-z0));
+          g1 = __fdividef(sc.sAe, 1.f + __expf(-z1));
         }
-        __half h0, l0h, h1, l1h;
-        split_f16(g0, h0, l0h);
-        split_f16(g1, h1, l1h);
-        unsigned char* eb = sE + (size_t)(nglob % NBUF) * 2 * TM * 16 + r * 16 + hs * 4;
-        *reinterpret_cast<__half2*>(eb) = __halves2half2(h0, h1);
-        *reinterpret_cast<__half2*>(eb + TM * 16) = __halves2half2(l0h, l1h);
+        const __half2 hi2 = __floats2half2_rn(g0, g1);
+        const float2 hif = __half22float2(hi2);
+        const __half2 lo2 = __floats2half2_rn(g0 - hif.x, g1 - hif.y);
+        unsigned char* eb = sE + (size_t)pbuf * 2 * TM * 16 + r * 16 + hs * 4;
+        *reinterpret_cast<__half2*>(eb) = hi2;
+        *reinterpret_cast<__half2*>(eb + TM * 16) = lo2;
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&e_full[nglob % NBUF]);
+        if (lane == 0) mbar_arrive(&e_full[pbuf]);
       };
-      const uint32_t n0 = n;
-      for (int ls = 0; ls < NBUF && ls < nsteps; ++ls) produce(ls, n0 + ls);
+      // Group g owns the history chunks of parity g (a fixed set of h per partial sum, whatever tile / shard / item
+      // order a candidate is scored in: results are bit-identical between a sharded and an unsharded catalogue).
+      // prologue: the first NBUF steps (= chunk 0) are produced by its owner, group 0
+      if (egrp == 0)
+        for (int m = 0; m < NBUF && m < nsteps; ++m) produce(m);
 
-      for (int ls = 0; ls < nsteps; ++ls, ++n) {
-        const int c = ls / tpc, t = ls - c * tpc, h = 2 * c + hs;
-        const int buf = n % NBUF;
-        const int hist_id = (h < H) ? __ldg(A.users.items + hb + h) : -1;
-        mbar_wait(&acc_full[buf], (n / NBUF) & 1);
+      for (int ls = egrp * TPC; ls < nsteps; ls = (ls % TPC == TPC - 1) ? ls + TPC + 1 : ls + 1) {
+        const uint32_t n = n0 + (uint32_t)ls;
+        const uint32_t buf = n % NBUF;
+        const int c = ls / TPC, t = ls - c * TPC;
+        const int h = 2 * c + hs;
+        int hist_id = -1;
+        if (h < H) hist_id = h < HMETA ? hm_id[h] : __ldg(A.users.items + hb + h);
+        mbar_wait(&acc_full[egrp * NBUF + buf], (phbits >> buf) & 1u);
+        phbits ^= 1u << buf;
         tc_fence_after();
-        // MMA(n) is complete: its A_ext buffer is free again -> produce step ls + NBUF into it
-        if (ls + NBUF < nsteps) produce(ls + NBUF, n + NBUF);
-        // ---- drain this thread's 1 x (hid + 2) slice of the accumulator ---------------------------------------------
+        // MMA(n) is complete, so its A_ext buffer is free: refill it for step ls + NBUF (keeps the MMA queue fed)
+        if (ls + NBUF < nsteps) produce(ls + NBUF);
+        // ---- TMEM -> registers, 32 columns at a time.  Loads and their wait are kept back to back: the destination
+        // registers are written asynchronously, so no other code may sit between a tcgen05.ld and its wait::ld (the
+        // other epilogue group hides the latency instead).
         const uint32_t t_main = tmem + lane_addr + buf * ACC_STRIDE + hs * hid;
-        const uint32_t t_aux = tmem + lane_addr + buf * ACC_STRIDE + 2 * hid + 2 * hs;
+        uint32_t aux[2], v[32];
         float accp = 0.f, accn = 0.f;
-        uint32_t aux[2];
-        tmem_ld2(t_aux, aux);
-        for (int c0 = 0; c0 < hid; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(t_main + c0, v);
-          tmem_wait_ld();
-          if (c0 + 16 <= npos) {
+        tmem_ld2(tmem + lane_addr + buf * ACC_STRIDE + 2 * hid + 2 * hs, aux);
+        if (hid >= 32) tmem_ld32(t_main, v);
+        else tmem_ld16(t_main, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        tmem_wait_ld();
+        auto absum = [&](int c0, int cnt) {  // columns [c0, c0+cnt) of this thread's slice are in v[0..cnt)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) accp += fabsf(__uint_as_float(v[i]));
-          } else if (c0 >= npos) {
+          for (int g16 = 0; g16 < 32; g16 += 16) {
+            if (g16 < cnt) {
+              const int cc = c0 + g16;
+              if (cc + 16 <= npos || cc >= npos) {
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) accn += fabsf(__uint_as_float(v[i]));
-          } else {
+                for (int i = 0; i < 16; i += 4) {
+                  s0 += fabsf(__uint_as_float(v[g16 + i]));
+                  s1 += fabsf(__uint_as_float(v[g16 + i + 1]));
+                  s2 += fabsf(__uint_as_float(v[g16 + i + 2]));
+                  s3 += fabsf(__uint_as_float(v[g16 + i + 3]));
+                }
+                const float ssum = (s0 + s1) + (s2 + s3);
+                if (cc >= npos) accn += ssum;
+                else accp += ssum;
+              } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float av = fabsf(__uint_as_float(v[i]));
-              if (c0 + i < npos) accp += av;
-              else accn += av;
+                for (int i = 0; i < 16; ++i) {
+                  const float av = fabsf(__uint_as_float(v[g16 + i]));
+                  if (cc + i < npos) accp += av;
+                  else accn += av;
+                }
+              }
             }
           }
+        };
+        absum(0, hid >= 32 ? 32 : 16);
+        if (hid > 32) {
+          if (hid >= 64) tmem_ld32(t_main + 32, v);
+          else tmem_ld16(t_main + 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+          tmem_wait_ld();
         }
-        tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        if (hid > 32) absum(32, hid >= 64 ? 32 : 16);
         const float S = __uint_as_float(aux[0]) * sc.inv_s;
         const float a = (__uint_as_float(aux[1]) + (accp - accn)) * sc.inv_sigma;
         if (h < H) {
@@ -564,37 +653,41 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
           }
         }
       }
-      // ---- item epilogue: combine the two history slots, score, block top-k ------------------------------------------
-      epi_bar();  // previous item's readers of keys/comb are done
-      if (hs == 1) {
+      n0 += (uint32_t)nsteps;
+      // ---- item epilogue: combine the 4 partial states (2 groups x 2 history slots), score, block top-k --------------
+      const int part = egrp * 2 + hs;  // partial 0 is the combiner
+      if (part != 0) {
 #pragma unroll
-        for (int t = 0; t < 3; ++t)
-          if (t < tpc) {
-            comb[(0 * tpc + t) * TM + r] = sumE[t];
-            comb[(1 * tpc + t) * TM + r] = sumES[t];
-            comb[(2 * tpc + t) * TM + r] = excl[t] ? 1.f : 0.f;
-          }
+        for (int t2 = 0; t2 < TPC; ++t2) {
+          comb[((part - 1) * 3 + 0) * TPC * TM + t2 * TM + r] = sumE[t2];
+          comb[((part - 1) * 3 + 1) * TPC * TM + t2 * TM + r] = sumES[t2];
+          comb[((part - 1) * 3 + 2) * TPC * TM + t2 * TM + r] = excl[t2] ? 1.f : 0.f;
+        }
       }
       epi_bar();
-      if (hs == 0) {
+      if (part == 0) {
 #pragma unroll
-        for (int t = 0; t < 3; ++t)
-          if (t < tpc) {
-            const float E = sumE[t] + comb[(0 * tpc + t) * TM + r];
-            const float ES = sumES[t] + comb[(1 * tpc + t) * TM + r];
-            const bool ex = excl[t] || comb[(2 * tpc + t) * TM + r] != 0.f;
-            const float score = ES / powf(E, beta);
-            const bool valid = jid[t] < A.poi_end;
-            if (A.all_scores && valid) A.all_scores[(size_t)u * (A.poi_end - A.poi_begin) + (jid[t] - A.poi_begin)] = score;
-            keys[t * TM + r] = (valid && !(A.exclude && ex)) ? make_key(score, (int)jid[t]) : 0ull;
+        for (int t2 = 0; t2 < TPC; ++t2) {
+          float E = sumE[t2], ES = sumES[t2];
+          bool ex = excl[t2];
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            E += comb[(q * 3 + 0) * TPC * TM + t2 * TM + r];
+            ES += comb[(q * 3 + 1) * TPC * TM + t2 * TM + r];
+            ex = ex || comb[(q * 3 + 2) * TPC * TM + t2 * TM + r] != 0.f;
           }
-        for (int i = tpc * TM + r; i < SORTN; i += TM) keys[i] = 0ull;
+          const float score = ES / powf(E, beta);
+          const bool valid = jid[t2] < A.poi_end;
+          if (A.all_scores && valid) A.all_scores[(size_t)u * (A.poi_end - A.poi_begin) + (jid[t2] - A.poi_begin)] = score;
+          keys[t2 * TM + r] = (valid && !(A.exclude && ex)) ? make_key(score, (int)jid[t2]) : 0ull;
+        }
+        for (int i = TPC * TM + r; i < SORTN; i += TM) keys[i] = 0ull;
       }
       epi_bar();
-      // bitonic sort (descending) of SORTN keys by the 256 epilogue threads
+      // bitonic sort (descending) of SORTN keys, one key pair per epilogue thread
       for (int kk = 2; kk <= SORTN; kk <<= 1) {
         for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-          for (int i = tid; i < SORTN; i += EPI_WARPS * 32) {
+          for (int i = tid; i < SORTN; i += EPI_THREADS) {
             const int ixj = i ^ jj;
             if (ixj > i) {
               const unsigned long long x = keys[i], y = keys[ixj];
@@ -608,7 +701,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
           epi_bar();
         }
       }
-      for (int i = tid; i < A.k; i += EPI_WARPS * 32) A.part_keys[((size_t)u * A.groups + grp) * A.k + i] = keys[i];
+      for (int i = tid; i < A.k; i += EPI_THREADS) A.part_keys[((size_t)u * A.groups + grp) * A.k + i] = keys[i];
     }
   }
   // ---- teardown ---------------------------------------------------------------------------------------------------------
