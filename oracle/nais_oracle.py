@@ -259,8 +259,12 @@ def fullrank(sd, variant, beta, cat: Catalog, indptr: np.ndarray, indices: np.nd
 # Metrics (eval_metrics.py:36-69)
 # ----------------------------------------------------------------------------------------------------------------------
 def precision_at_k(actual, predicted, k: int) -> float:
-    """mean over ALL users of |pos ∩ rec[:k]| / k (eval_metrics.py:36-44)."""
-    return sum(len(set(a) & set(p[:k])) / float(k) for a, p in zip(actual, predicted)) / len(predicted)
+    """mean over ALL users of |pos ∩ rec[:k]| / k (eval_metrics.py:36-44).  Accumulated sequentially like the
+    reference's `+=` loop: Python >= 3.12's built-in sum() is compensated and differs in the last bit."""
+    tot = 0.0
+    for a, p in zip(actual, predicted):
+        tot += len(set(a) & set(p[:k])) / float(k)
+    return tot / len(predicted)
 
 
 def recall_at_k(actual, predicted, k: int) -> float:

@@ -33,8 +33,9 @@ def gather_lists(score: torch.Tensor, ids: torch.Tensor, world: int) -> Tuple[to
     U, k = score.shape
     gs = torch.empty(world, U, k, dtype=score.dtype, device=score.device)
     gi = torch.empty(world, U, k, dtype=ids.dtype, device=ids.device)
-    dist.all_gather_into_tensor(gs, score.contiguous())
-    dist.all_gather_into_tensor(gi, ids.contiguous())
+    # list form: supported by both nccl and gloo (all_gather_into_tensor is nccl-only)
+    dist.all_gather(list(gs.unbind(0)), score.contiguous())
+    dist.all_gather(list(gi.unbind(0)), ids.contiguous())
     return gs.permute(1, 0, 2).contiguous(), gi.permute(1, 0, 2).contiguous()
 
 

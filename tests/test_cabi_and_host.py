@@ -1,0 +1,139 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every symbol the header declares; host-side drop-ins
+(batches, eval_metrics, synthetic data, shard ranges) against the reference / oracle.  No compute calls need a GPU."""
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nais_oracle as orc
+from oracle import ref_shim
+from poi_recommendation_models_b200 import _lib, batches as PB, eval_metrics as PM, model as M, synthetic
+from poi_recommendation_models_b200.distributed import shard_range
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    import __graft_entry__
+    __graft_entry__.build()
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "nais_b200.h")).read()
+    declared = set(re.findall(r"NAIS_API\s+[\w\s\*]+?\b(nais_\w+)\s*\(", hdr))
+    assert declared and declared == set(_lib.SYMBOLS), (declared ^ set(_lib.SYMBOLS))
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.nais_abi_version() == 1
+    assert b"workspace" in lib.nais_strerror(-4)
+    assert lib.nais_launch_count() >= 0
+
+
+def test_argument_errors_are_reported_before_any_launch():
+    import ctypes as C
+    lib = _lib.load()
+    p = _lib.NaisParams()
+    b = _lib.NaisPairs()
+    assert lib.nais_pairs_forward(C.byref(p), C.byref(b), None, None, None, None) == -2  # n_branch = 0 -> shape error
+    p.n_branch, p.hid, p.item_num = 1, 64, 10
+    p.branch[0].w_poi = 64
+    assert lib.nais_pairs_forward(C.byref(p), C.byref(b), None, None, None, None) == -1  # NULL tables
+    assert lib.nais_fullrank_workspace_bytes(C.byref(p), 4, 100, 0, 10, 5, 0) == 0  # invalid params -> 0
+
+
+def test_ops_refuse_cpu_tensors():
+    m = M.NAIS_basic(20, 16, 16, 0.5).eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(2, 3, dtype=torch.long), torch.zeros(2, dtype=torch.long))
+
+
+def test_state_dict_keys_and_init_match_reference_classes():
+    if not ref_shim.reference_available():
+        pytest.skip("/root/reference not present")
+    ref = ref_shim.load_reference("model")
+    cases = [("NAIS_basic", (50, 16, 8, 0.5)), ("NAIS_regionEmbedding", (50, 16, 8, 0.5, 7)),
+             ("NAIS_region_distance_Embedding", (50, 16, 8, 0.5, 7, 1)), ("NAIS_distance_Embedding", (50, 16, 8, 0.5, 7, 1)),
+             ("NAIS_region_distance_disentangled_Embedding", (50, 16, 8, 0.5, 7, 1))]
+    for name, args in cases:
+        torch.manual_seed(0)
+        a = getattr(ref, name)(*args)
+        torch.manual_seed(0)
+        b = getattr(M, name)(*args)
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa.keys()) == list(sb.keys()), name
+        for k in sa:
+            assert torch.equal(sa[k], sb[k]), (name, k)  # same seed -> same initial weights
+        b.load_state_dict(sa)  # reference checkpoints load
+        for attr in ("embed_size", "item_num", "beta", "hidden_size"):
+            assert getattr(a, attr) == getattr(b, attr)
+
+
+def test_batches_match_reference_golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "batches.npz"))
+    import scipy.sparse as sp
+    csr = sp.csr_matrix((np.ones(len(z["indices"])), z["indices"], z["indptr"]), shape=(4, int(z["N"])))
+    for u in range(4):
+        random.seed(123 + u)
+        hist, tgt, label, hreg, treg = PB.get_NAIS_batch_region(csr, int(z["N"]), u, int(z["num_ng"]), z["region"])
+        for name, got in (("hist", hist), ("tgt", tgt), ("label", label), ("hreg", hreg), ("treg", treg)):
+            assert np.array_equal(got.cpu().numpy(), z[f"u{u}.{name}"]), (u, name)
+        h2, t2, _, _, _ = PB.get_NAIS_batch_test_region(csr, u, z["region"])
+        assert np.array_equal(t2.cpu().numpy(), z[f"u{u}.test_tgt"])
+        assert np.array_equal(h2[0].cpu().numpy(), z[f"u{u}.test_hist0"])
+
+
+def test_lat_lon_pairs_equals_latlon_mat_lookup():
+    rng = np.random.default_rng(0)
+    coords = np.stack([40.5 + rng.random(30), -74 + rng.random(30)], 1)
+    mat = np.zeros((30, 30, 2))
+    for i in range(30):  # run.py:47-54
+        for j in range(30):
+            mat[i][j][0] = abs(coords[i][0] - coords[j][0])
+            mat[i][j][1] = abs(coords[i][1] - coords[j][1])
+    tgt = rng.integers(0, 30, 7)
+    hist = np.stack([rng.choice(30, 5, replace=False) for _ in range(7)])
+    ref = torch.tensor(mat[np.repeat(tgt.reshape(-1, 1), 5, 1), hist], dtype=torch.float32)  # run.py:239-247
+    assert torch.equal(PB.lat_lon_pairs(coords, tgt, hist, device="cpu"), ref)
+
+
+def test_metrics_bit_identical_to_reference():
+    rng = np.random.default_rng(3)
+    U = 200
+    actual = [rng.choice(500, rng.integers(0, 6), replace=False).tolist() for _ in range(U)]
+    pred = [rng.choice(500, 50, replace=False).tolist() for _ in range(U)]
+    for k in (5, 10, 15, 20, 25, 30):
+        assert PM.precision_at_k(actual, pred, k) == orc.precision_at_k(actual, pred, k)
+        assert PM.recall_at_k(actual, pred, k) == orc.recall_at_k(actual, pred, k)
+        assert PM.hitrate_at_k(actual, pred, k) == orc.hitrate_at_k(actual, pred, k)
+        assert PM.ndcg_at_k(actual, pred, k) == orc.ndcg_at_k(actual, pred, k)
+    if ref_shim.reference_available():
+        ref = ref_shim.load_reference("eval_metrics")
+        for k in (5, 10, 30):
+            assert PM.precision_at_k(actual, pred, k) == ref.precision_at_k(actual, pred, k)
+            assert PM.recall_at_k(actual, pred, k) == ref.recall_at_k(actual, pred, k)
+            assert PM.hitrate_at_k(actual, pred, k) == ref.hitrate_at_k(actual, pred, k)
+
+
+def test_synthetic_checkins_are_consistent():
+    d = synthetic.make_checkins(20, 800, seed=1)
+    assert d.indptr[-1] == len(d.indices) and d.region.max() + 1 == d.region_num
+    for u in range(20):
+        h = d.history(u)
+        assert len(set(h.tolist())) == len(h) and (np.diff(h) > 0).all()
+        assert not set(h.tolist()) & set(d.val_positive[u]) and not set(h.tolist()) & set(d.test_positive[u])
+        assert len(d.val_positive[u]) >= 1
+    d2 = synthetic.make_checkins(20, 800, seed=1)
+    assert np.array_equal(d.indices, d2.indices) and np.array_equal(d.coords, d2.coords)  # seed-exact
+    fixed = synthetic.make_checkins(5, 400, hist_len=32, seed=2)
+    assert (np.diff(fixed.indptr) == 32).all()
+
+
+@pytest.mark.parametrize("n,world", [(40000, 1), (40000, 8), (1000, 3), (100, 8), (5, 4), (1000000, 8)])
+def test_shard_ranges_partition_the_catalogue(n, world):
+    ranges = [shard_range(n, r, world) for r in range(world)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == n
+    for (a0, a1), (b0, b1) in zip(ranges, ranges[1:]):
+        assert a1 == b0 and a0 <= a1
+    for lo, hi in ranges[:-1]:
+        assert lo % 128 == 0 or lo == n
