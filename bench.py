@@ -166,6 +166,74 @@ def run_reference(args, cfg, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_train(args, dev, lib, peaks, rank, world):
+    """BASELINE config C3: BPR-style training forward + backward on (user, pos, neg) triples — 4,096 triples = 8,192
+    (history row, target) pairs, history 128, D = hid = 64; every row has its own history, positives are in the history
+    (live mask), negatives are not.  Step = pair forward, -log sigmoid(s+ - s-), hand-written backward of every
+    parameter (attention MLP + embedding-row segment reduce).  Data parallel over triples with N > 1 (+ all-reduce)."""
+    import torch
+    import torch.distributed as dist
+    from poi_recommendation_models_b200 import model as M, synthetic
+    from poi_recommendation_models_b200.distributed import allreduce_gradients
+    N, H, D, hid, T = 40000, 128, 64, 64, 4096
+    coords, region, R = synthetic.make_catalog(N, seed=0)
+    torch.manual_seed(1)
+    m = M.NAIS_region_distance_Embedding(N, D, hid, BETA, R, 1)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if name.startswith("embed_"):
+                p.normal_(0, 0.3)
+    m = m.to(dev).train()
+    hist_np = synth_histories(T, N, H, seed=3 + rank)
+    rng = np.random.default_rng(4 + rank)
+    pos = hist_np[np.arange(T), rng.integers(0, H, T)]
+    neg = rng.integers(0, N, T)
+    clash = (hist_np == neg[:, None]).any(1)
+    neg[clash] = (neg[clash] + 1) % N
+    hist = torch.from_numpy(np.concatenate([hist_np, hist_np])).to(dev)
+    tgt = torch.from_numpy(np.concatenate([pos, neg])).to(dev)
+    reg = torch.from_numpy(region).to(dev)
+    c = torch.from_numpy(coords).to(dev)
+    ll = (c[tgt][:, None, :] - c[hist]).abs().float().contiguous()
+    hreg, treg = reg[hist], reg[tgt]
+
+    def step():
+        m.zero_grad(set_to_none=True)
+        s = m.attention_network(hist, tgt, hreg, treg, ll)
+        loss = -torch.nn.functional.logsigmoid(s[:T] - s[T:]).mean()
+        loss.backward()
+        allreduce_gradients(m, world)
+        return loss
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = lib.nais_launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        loss = step()
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank == 0:
+        cells = 2 * T * H
+        F = flops_per_cell(D, hid)
+        tf = cells * 4 * F * args.steps / (ms / 1000.0) / 1e12  # fwd F + bwd ~3F (SURVEY.md §8d)
+        print(json.dumps({"metric": "bpr_train_triples_per_sec", "value": T * world * args.steps / (ms / 1000.0), "unit": "triples/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                          "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "C3: 4096 (user,pos,neg) triples, H=128, D=hid=64, fwd+bwd (FP32 kernels)"},
+                          "gpu_launches": int(lib.nais_launch_count() - l0), "loss": float(loss),
+                          "roofline": {"bound": "fp32-ffma", "achieved": tf, "unit": "TFLOP/s",
+                                       "note": "algorithmic 4F per cell; CUDA-core path (tensor-core backward is next-round work)"}}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -175,6 +243,7 @@ def main():
     ap.add_argument("--config", default="C2", choices=list(WORKLOADS))
     ap.add_argument("--precision", default=os.environ.get("NAIS_BENCH_PRECISION", "tc_split"), choices=["fp32", "tc_split", "tc_fast"])
     ap.add_argument("--users-per-step", type=int, default=0)
+    ap.add_argument("--mode", default="eval", choices=["eval", "train"], help="eval = headline full-rank metric; train = C3 BPR fwd+bwd (triples/s)")
     ap.add_argument("--cpu-users", type=int, default=4, help="users in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -200,9 +269,12 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     peaks = load_peaks()
+    if args.mode == "train":
+        run_train(args, dev, lib, peaks, rank, world)
+        return
 
     U, N, H, D, hid, k = cfg["users"], cfg["pois"], cfg["hist"], cfg["D"], cfg["hid"], cfg["k"]
-    ups = args.users_per_step or {"fp32": 296, "tc_split": 2368, "tc_fast": 4736}[args.precision]
+    ups = args.users_per_step or max(148, int({"fp32": 296, "tc_split": 2368, "tc_fast": 4736}[args.precision] * min(1.0, 40000 / N)))
     ups = min(ups, U)
     n_batches = min(args.steps + args.warmup, max(1, U // ups))
     # ---- synthetic data + random-init ("trained-like") weights of the named architecture ----------------------------
@@ -303,6 +375,21 @@ def main():
                              "flops_per_cell": F, "cells_per_launch": cells_per_launch,
                              "peak_source": f"{peaks['which']} bf16 sustained (MEASURED_PEAKS.json)",
                              "hbm_frac": None}}
+        if args.precision != "fp32":
+            # FLOPs the tensor pipe actually executes per step of 256 cells (128 candidates x 2 history items):
+            # SPLIT 3 passes x (D/16 + 1 ext) MMAs of 128 x nrow x 16; FAST 1 such pass + 2 passes of N = 16 (S/L rows)
+            nrow = max((2 * hid + 4 + 15) // 16 * 16, 2 * hid + 16)
+            ks = D // 16 + 1
+            per_step = (3 * ks * 2 * 128 * nrow * 16) if args.precision == "tc_split" else (ks * 2 * 128 * nrow * 16 + 2 * ks * 2 * 128 * 16 * 16)
+            issued = cells_per_launch / 256 * per_step / (kern_ms / 1000.0) / 1e12
+            line["roofline"].update({"issued_tflops": issued, "issued_frac": issued / peak,
+                                     "issued_note": "tensor FLOPs executed incl. fp16 hi/lo split passes, ext K-step and S/L rows"})
+        tr = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+        if os.path.isfile(tr) and args.precision == "tc_split":
+            with open(tr) as f:
+                t = json.load(f)
+            line["roofline"]["traffic"] = t["dram_bytes_per_user"] * ups + t.get("dram_bytes_const", 0)
+            line["roofline"]["traffic_source"] = t["source"]
         # algorithmic HBM bytes of the launch: catalogue rows + history items + output
         alg_bytes = ((N + world - 1) // world) * (D // 2 * 4 + 4 + 8) + ups * H * (4 + D // 2 * 4 + 4 + 8) + ups * k * 8
         if kern_ms:

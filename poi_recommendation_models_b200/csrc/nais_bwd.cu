@@ -512,32 +512,96 @@ __global__ void make_keys_kernel(NaisPairs b, int want_reg, int* k_hist, uint32_
   }
 }
 
-// One warp per sorted position; only run starts work.  out[key, 0:w] = sum of src rows [off, off+w).
-__global__ void segment_reduce_kernel(const int* __restrict__ keys, const uint32_t* __restrict__ src, int64_t n,
-                                      int64_t n_cells, const float* __restrict__ ws_dq, const float* __restrict__ ws_dp,
-                                      int D, int off, int w, float* __restrict__ out) {
-  const int64_t pos = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+// Embedding-row gradients: out[key, 0:w] = sum of the contribution rows of every sorted entry with that key.
+// Two deterministic passes, no atomics:
+//   pass 1  one warp per chunk of SEG_CHUNK consecutive sorted entries accumulates runs of equal keys in order;
+//           a run that lies strictly inside its chunk is complete and is written to the table row directly, the
+//           (at most two) runs that touch a chunk boundary go to partial slots [2*chunk] (first run) / [2*chunk+1]
+//           (last run) together with a flag saying whether the run STARTS in this chunk;
+//   pass 2  one warp per starting partial adds the following chunks' continuing first-run partials, in chunk order.
+constexpr int SEG_CHUNK = 64;
+
+__device__ __forceinline__ const float* seg_row(uint32_t s, int64_t n_cells, const float* ws_dq, const float* ws_dp, int D) {
+  return (s < n_cells) ? ws_dq + (size_t)s * D : ws_dp + (size_t)(s - n_cells) * D;
+}
+
+__global__ void segment_reduce_pass1_kernel(const int* __restrict__ keys, const uint32_t* __restrict__ src, int64_t n,
+                                            int64_t n_cells, const float* __restrict__ ws_dq,
+                                            const float* __restrict__ ws_dp, int D, int off, int w, float* __restrict__ out,
+                                            int* __restrict__ part_key, int* __restrict__ part_start,
+                                            float* __restrict__ part_rows) {
+  const int64_t chunk = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (pos >= n) return;
-  const int key = keys[pos];
-  if (pos > 0 && keys[pos - 1] == key) return;
-  for (int d0 = 0; d0 < w; d0 += 32) {
-    const int d = d0 + lane;
-    float acc = 0.f;
-    for (int64_t i = pos; i < n && keys[i] == key; ++i) {
-      const uint32_t s = src[i];
-      const float* row = (s < n_cells) ? ws_dq + (size_t)s * D : ws_dp + (size_t)(s - n_cells) * D;
-      if (d < w) acc += row[off + d];
+  const int64_t start = chunk * SEG_CHUNK;
+  if (start >= n) return;
+  const int64_t end = min(n, start + SEG_CHUNK);
+  if (lane < 2) part_key[2 * chunk + lane] = -1;
+  __syncwarp();
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int cur = keys[start];
+  bool first = true;
+  auto flush = [&](bool last) {
+    const bool left = first && start > 0 && keys[start - 1] == cur;
+    const bool right = last && end < n && keys[end] == cur;
+    if (!left && !right) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (lane + 32 * i < w) out[(size_t)cur * w + lane + 32 * i] = acc[i];
+    } else {
+      const int64_t slot = 2 * chunk + (first ? 0 : 1);
+      if (lane == 0) {
+        part_key[slot] = cur;
+        part_start[slot] = left ? 0 : 1;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (lane + 32 * i < w) part_rows[(size_t)slot * w + lane + 32 * i] = acc[i];
     }
-    if (d < w) out[(size_t)key * w + d] = acc;
+  };
+  for (int64_t i = start; i < end; ++i) {
+    const int k = keys[i];
+    if (k != cur) {
+      flush(false);
+      first = false;
+      cur = k;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = 0.f;
+    }
+    const float* row = seg_row(src[i], n_cells, ws_dq, ws_dp, D) + off;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (lane + 32 * j < w) acc[j] += row[lane + 32 * j];
   }
+  flush(true);
+}
+
+__global__ void segment_reduce_pass2_kernel(const int* __restrict__ part_key, const int* __restrict__ part_start,
+                                            const float* __restrict__ part_rows, int64_t n_chunks, int w,
+                                            float* __restrict__ out) {
+  const int64_t slot = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (slot >= 2 * n_chunks) return;
+  const int key = part_key[slot];
+  if (key < 0 || !part_start[slot]) return;
+  float acc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i] = (lane + 32 * i < w) ? part_rows[(size_t)slot * w + lane + 32 * i] : 0.f;
+  for (int64_t c = (slot >> 1) + 1; c < n_chunks && part_key[2 * c] == key && !part_start[2 * c]; ++c) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (lane + 32 * i < w) acc[i] += part_rows[(size_t)(2 * c) * w + lane + 32 * i];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (lane + 32 * i < w) out[(size_t)key * w + lane + 32 * i] = acc[i];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct BwdLayout {
-  size_t dq, dp, part, keys[6], cub, total;
+  size_t dq, dp, part, keys[6], cub, pkey, pstart, prows, total;
+  int64_t n_chunks;
   int grid, stride;
   size_t cub_bytes;
 };
@@ -569,6 +633,13 @@ static BwdLayout bwd_layout(const NaisParams& p, int64_t B, int H) {
   L.cub_bytes = cb;
   L.cub = o;
   o += align_up(cb);
+  L.n_chunks = (n_max + SEG_CHUNK - 1) / SEG_CHUNK;
+  L.pkey = o;
+  o += align_up((size_t)2 * L.n_chunks * 4);
+  L.pstart = o;
+  o += align_up((size_t)2 * L.n_chunks * 4);
+  L.prows = o;
+  o += align_up((size_t)2 * L.n_chunks * D * 4);
   L.total = o;
   return L;
 }
@@ -650,10 +721,15 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
     size_t cb = L.cub_bytes;
     auto seg = [&](int* ki, uint32_t* vi, int64_t n, int off, int w, float* out, int bits) {
       cub::DeviceRadixSort::SortPairs(base + L.cub, cb, ki, kout, vi, vout, (int)n, 0, bits, stream);
-      const int64_t threads = n * 32;
-      segment_reduce_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(kout, vout, n, n_cells, A.ws_dq, A.ws_dp, D,
-                                                                                  off, w, out);
-  NAIS_COUNT_LAUNCH(1);
+      const int64_t nch = (n + SEG_CHUNK - 1) / SEG_CHUNK;
+      int* pk = reinterpret_cast<int*>(base + L.pkey);
+      int* pst = reinterpret_cast<int*>(base + L.pstart);
+      float* pr = reinterpret_cast<float*>(base + L.prows);
+      segment_reduce_pass1_kernel<<<(unsigned)((nch * 32 + 255) / 256), 256, 0, stream>>>(kout, vout, n, n_cells, A.ws_dq, A.ws_dp,
+                                                                                        D, off, w, out, pk, pst, pr);
+      NAIS_COUNT_LAUNCH(1);
+      segment_reduce_pass2_kernel<<<(unsigned)((2 * nch * 32 + 255) / 256), 256, 0, stream>>>(pk, pst, pr, nch, w, out);
+      NAIS_COUNT_LAUNCH(1);
     };
     auto bits_for = [](int n) { int bts = 1; while ((1ll << bts) < n && bts < 31) ++bts; return bts; };
     if (want_hist) seg(kin, vin, n_cells, 0, br.w_poi, g.hist_poi[bi], bits_for(p.item_num));
