@@ -84,6 +84,12 @@ typedef struct NaisParams {
   int32_t dist_buckets;    /* >= 1; reference: 1 */
   float dist_bucket_km;    /* bucket = min(floor(km / dist_bucket_km), dist_buckets-1); ignored when dist_buckets == 1 */
   float beta;              /* smoothing exponent of the softmax denominator (model.py:284-285) */
+  /* Train-mode dropout on the attention hidden layer, relu(drop(W x + b)) (NAIS_basic / NAIS_regionEmbedding,
+   * model.py:71,162).  0 disables.  Element (pair b, history h, hidden k) is kept iff
+   * hi32(splitmix64(dropout_seed + ((b*H + h)*hid + k))) >= dropout_p * 2^32, kept values are scaled by 1/(1-p);
+   * forward and backward of one step must be given the same seed.  Pair API only. */
+  float dropout_p;
+  uint64_t dropout_seed;
 } NaisParams;
 
 /* A batch of explicit (history row, target) pairs: the argument list of model.forward (model.py:231). */

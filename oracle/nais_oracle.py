@@ -113,11 +113,14 @@ def attention_network_with_scale(*args, **kwargs):
 
 def attention_network(sd: Dict[str, torch.Tensor], variant: str, beta: float, hist: torch.Tensor, tgt: torch.Tensor,
                       hreg: Optional[torch.Tensor] = None, treg: Optional[torch.Tensor] = None,
-                      aux: Optional[torch.Tensor] = None, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+                      aux: Optional[torch.Tensor] = None, dtype: torch.dtype = torch.float32,
+                      l1_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Pre-sigmoid score[B] of (history row, target) pairs.
 
     region_distance: model.py:246-297; basic: :57-89; region: :144-180; distance: :355-401; disentangled: :467-534.
     `aux` is ll[B,H,2] = (|dlat|,|dlon|) degrees for the lat/lon variants, dist_km[B,H] for the disentangled one.
+    `l1_scale` [B,H,hid] multiplies the first layer's output before the ReLU: with keep_mask/(1-p) it restates the
+    train-mode `relu(drop(attn_layer1(x)))` of NAIS_basic / NAIS_regionEmbedding (model.py:71,162) for a GIVEN mask.
     """
     v = VARIANTS[variant]
     P = {k: t.to(dtype) for k, t in sd.items()}
@@ -141,7 +144,10 @@ def attention_network(sd: Dict[str, torch.Tensor], variant: str, beta: float, hi
     if v["dist"] == "latlon":
         g = torch.sigmoid((aux.to(dtype) * v["scale"]) @ P["dist_layer.weight"].T + P["dist_layer.bias"])  # :265 / :366
         x = torch.cat((x, g), -1)
-    a = torch.relu(x @ P["attn_layer1.weight"].T + P["attn_layer1.bias"]) @ P["attn_layer2.weight"][0]
+    t1 = x @ P["attn_layer1.weight"].T + P["attn_layer1.bias"]
+    if l1_scale is not None:
+        t1 = t1 * l1_scale.to(dtype)
+    a = torch.relu(t1) @ P["attn_layer2.weight"][0]
     return _beta_attention(a, sim, mask, beta)
 
 

@@ -23,7 +23,8 @@ class NaisParams(C.Structure):
     _fields_ = [("branch", NaisBranch * 2), ("n_branch", C.c_int32), ("hid", C.c_int32), ("item_num", C.c_int32),
                 ("region_num", C.c_int32), ("dist_mode", C.c_int32), ("dist_scale", C.c_float), ("dist_w", C.c_void_p),
                 ("dist_b", C.c_void_p), ("dist_embed", C.c_void_p), ("dist_buckets", C.c_int32),
-                ("dist_bucket_km", C.c_float), ("beta", C.c_float)]
+                ("dist_bucket_km", C.c_float), ("beta", C.c_float), ("dropout_p", C.c_float),
+                ("dropout_seed", C.c_uint64)]
 
 
 class NaisPairs(C.Structure):

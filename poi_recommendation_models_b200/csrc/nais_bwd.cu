@@ -61,6 +61,9 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
   int* citem = reinterpret_cast<int*>(red + 8 * (NT / 32));  // [TC] history item id per cell
   int* creg = citem + TC;                                   // [TC]
   int* crow = creg + TC;                                    // [TC] row slot per cell (-1 invalid)
+  long long* cgl = reinterpret_cast<long long*>(crow + TC);  // [TC] global cell index (dropout mask)
+  const uint32_t dthresh = p.dropout_p > 0.f ? dropout_threshold(p.dropout_p) : 0u;
+  const float dinv = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
 
   const int tid = threadIdx.x, cell = tid & (TC - 1), half = tid >> 7;
   const int tk = tid & 15, tj = tid >> 4;
@@ -161,6 +164,7 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
           citem[cell] = (int)it;
           creg[cell] = (int)rg;
           crow[cell] = valid ? r : -1;
+          cgl[cell] = cidx;
         }
       }
       __syncthreads();
@@ -211,6 +215,10 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
           for (int cc = 0; cc < 4; ++cc) {
             float v = t[kb][i][cc] + c[cc];
             if (lanes) v = fmaf(c[3 * KB + cc], g1, fmaf(c[2 * KB + cc], g0, v));
+            if (dthresh) {
+              const uint64_t idx = (uint64_t)cgl[tj * 8 + i] * (uint64_t)hid + (uint64_t)(kb * KB + tk * 4 + cc);
+              v = dropout_bits(p.dropout_seed, idx) >= dthresh ? v * dinv : 0.f;
+            }
             v = fmaxf(v, 0.f);
             t[kb][i][cc] = v;  // relu(t)
             a_part[i] = fmaf(c[KB + cc], v, a_part[i]);
@@ -263,7 +271,7 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
           for (int cc = 0; cc < 4; ++cc) {
             const float hval = t[kb][i][cc];
             dvl[cc] = fmaf(da[i], hval, dvl[cc]);
-            DTs[(kb * KB + tk * 4 + cc) * TCP + tj * 8 + i] = (hval > 0.f) ? da[i] * c[KB + cc] : 0.f;
+            DTs[(kb * KB + tk * 4 + cc) * TCP + tj * 8 + i] = (hval > 0.f) ? da[i] * c[KB + cc] * dinv : 0.f;
           }
         }
 #pragma unroll
@@ -651,7 +659,7 @@ static int launch_bwd_tile(const BwdArgs& A, int D, int grid, cudaStream_t strea
   constexpr int HP = NKB * KB;
   const size_t fl = (size_t)D * TCP + (size_t)HP * TCP + (size_t)D * KB + NKB * 4 * KB + 8 * TC + 16 * HP +
                     2 * (size_t)BWD_MAXROWS * D + 3 * BWD_MAXROWS + 8 * (NT / 32);
-  const size_t smem = fl * 4 + 3 * TC * 4;
+  const size_t smem = fl * 4 + 3 * TC * 4 + TC * 8 + 8;
   cudaError_t e = cudaFuncSetAttribute(pairs_bwd_kernel<NKB, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   pairs_bwd_kernel<NKB, DB><<<grid, NT, smem, stream>>>(A);

@@ -62,6 +62,19 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* buf, int n
   }
 }
 
+// Dropout keep-mask (see NaisParams::dropout_p): counter-based, so forward and backward regenerate the same mask.
+__host__ __device__ __forceinline__ uint32_t dropout_bits(uint64_t seed, uint64_t idx) {
+  uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (uint32_t)(z >> 32);
+}
+__host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
+  const double t = (double)p * 4294967296.0;
+  return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+}
+
 __device__ __forceinline__ float sigmoidf_exact(float z) { return 1.0f / (1.0f + expf(-z)); }
 
 // Great-circle km from centred coordinates, haversine form (well conditioned in fp32 for short distances; equals the

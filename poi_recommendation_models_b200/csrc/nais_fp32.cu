@@ -21,8 +21,9 @@ struct TileSmem {
   float* g;   // [2][TC]   distance lanes per cell (LATLON) / logit bias in g[0] (KM)
   float* sp;  // [2][TC]   similarity partial sums of the two d-halves
   float* a;   // [TC]      logits out
+  long long* cg;  // [TC]  global cell index (pair*H + h) of each cell, for the dropout mask (pair kernels)
 };
-__host__ __device__ inline size_t tile_smem_floats(int D) { return (size_t)D * TCP + (size_t)D * KB + 4 * KB + 5 * TC; }
+__host__ __device__ inline size_t tile_smem_floats(int D) { return (size_t)D * TCP + (size_t)D * KB + 4 * KB + 5 * TC + 2 * TC; }
 __device__ inline float* carve_tile(float* base, int D, TileSmem& s) {
   s.As = base;
   base += (size_t)D * TCP;
@@ -36,6 +37,8 @@ __device__ inline float* carve_tile(float* base, int D, TileSmem& s) {
   base += 2 * TC;
   s.a = base;
   base += TC;
+  s.cg = reinterpret_cast<long long*>(base);  // 8-byte aligned: every preceding block is an even number of floats
+  base += 2 * TC;
   return base;
 }
 
@@ -57,9 +60,16 @@ __device__ inline void load_wblock(const NaisBranch& br, int hid, int D, int lan
   }
 }
 
+struct DropCtx {
+  uint32_t thresh;  // 0 = dropout off
+  float inv_keep;
+  uint64_t seed;
+  int hid;
+};
+
 // One k-block of the tile GEMM + MLP epilogue.  Thread (tj = tid/16, tk = tid%16) owns cells tj*8..+7 and hidden
 // units tk*4..+3 of the block; a_part[i] accumulates sum_k v_k relu(t_k) over this thread's hidden units.
-__device__ __forceinline__ void tile_kblock(const TileSmem& s, int D, bool lanes, float (&a_part)[8]) {
+__device__ __forceinline__ void tile_kblock(const TileSmem& s, int D, bool lanes, float (&a_part)[8], const DropCtx& dc, int kb) {
   const int tk = threadIdx.x & 15, tj = threadIdx.x >> 4;
   float acc[8][4];
 #pragma unroll
@@ -98,6 +108,10 @@ __device__ __forceinline__ void tile_kblock(const TileSmem& s, int D, bool lanes
     for (int c = 0; c < 4; ++c) {
       float t = acc[i][c] + bbv[c];
       if (lanes) t = fmaf(w1v[c], g1, fmaf(w0v[c], g0, t));
+      if (dc.thresh) {  // relu(drop(W x + b)), model.py:71,162
+        const uint64_t idx = (uint64_t)s.cg[tj * 8 + i] * (uint64_t)dc.hid + (uint64_t)(kb * KB + tk * 4 + c);
+        t = dropout_bits(dc.seed, idx) >= dc.thresh ? t * dc.inv_keep : 0.f;
+      }
       r = fmaf(vvv[c], fmaxf(t, 0.f), r);
     }
     a_part[i] += r;
@@ -107,7 +121,7 @@ __device__ __forceinline__ void tile_kblock(const TileSmem& s, int D, bool lanes
 // Whole MLP for the tile currently in s.As / s.g: writes s.a[cell].  `resident_kb` says which (branch,kb) block is
 // already in s.Wt (updated).  All threads must call; ends with a __syncthreads().
 __device__ inline void tile_logits(const NaisBranch& br, int br_idx, int hid, int D, int lanes, const TileSmem& s,
-                                   int& resident) {
+                                   int& resident, const DropCtx& dc) {
   const int n_kb = (hid + KB - 1) / KB;
   float a_part[8];
 #pragma unroll
@@ -120,7 +134,7 @@ __device__ inline void tile_logits(const NaisBranch& br, int br_idx, int hid, in
       resident = want;
       __syncthreads();
     }
-    tile_kblock(s, D, lanes != 0, a_part);
+    tile_kblock(s, D, lanes != 0, a_part, dc, kb);
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -191,6 +205,11 @@ __global__ void __launch_bounds__(NT, 2) pairs_fwd_kernel(const __grid_constant_
   const int n_chunks = (H <= TC) ? 1 : (H + TC - 1) / TC;
   const int tid = threadIdx.x, cell = tid & (TC - 1), half = tid >> 7;
   int resident = -1;
+  DropCtx dc{0u, 1.f, p.dropout_seed, p.hid};
+  if (p.dropout_p > 0.f) {
+    dc.thresh = dropout_threshold(p.dropout_p);
+    dc.inv_keep = 1.f / (1.f - p.dropout_p);
+  }
   float my_total = 0.f;  // thread r (< nrows) accumulates the final score of row r over branches
 
   for (int bi = 0; bi < p.n_branch; ++bi) {
@@ -246,6 +265,7 @@ __global__ void __launch_bounds__(NT, 2) pairs_fwd_kernel(const __grid_constant_
         }
         s.sp[half * TC + cell] = ssum;
         if (half == 0) {
+          s.cg[cell] = cidx;
           float g0 = 0.f, g1 = 0.f;
           if (valid && p.dist_mode == NAIS_DIST_LATLON) {
             dist_lanes(p, A.b.aux[cidx * 2], A.b.aux[cidx * 2 + 1], g0, g1);
@@ -258,7 +278,7 @@ __global__ void __launch_bounds__(NT, 2) pairs_fwd_kernel(const __grid_constant_
         }
       }
       __syncthreads();
-      tile_logits(br, bi, p.hid, D, lanes, s, resident);
+      tile_logits(br, bi, p.hid, D, lanes, s, resident, dc);
       if (tid < TC) {
         float e = 0.f, es = 0.f;
         if (valid) {
@@ -417,7 +437,7 @@ __global__ void __launch_bounds__(NT, 2) fullrank_fp32_kernel(const __grid_const
             }
           }
           __syncthreads();
-          tile_logits(br, bi, p.hid, D, lanes, s, resident);
+          tile_logits(br, bi, p.hid, D, lanes, s, resident, DropCtx{0u, 1.f, 0ull, 0});
           if (tid < TC) {
             const bool m = (int64_t)hid_s[hh] != j;
             if (m) {

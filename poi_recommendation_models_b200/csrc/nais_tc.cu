@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       // low words for index 0 and the per-index deltas (all linear in the tile / buffer / stage index)
       const uint32_t A_hi0 = lo_of(sa0, a_lbo), A_lo0 = lo_of(sa0 + g.a_plane, a_lbo), A_d = (uint32_t)g.a_tile >> 4;
       const uint32_t E_hi0 = lo_of(se0, zaddr - se0), E_lo0 = lo_of(se0 + TM * 16, zaddr - se0 - TM * 16);
-      const uint32_t E_d = ((2 * TM * 16) >> 4) - (((2 * TM * 16) >> 4) << 16);
+      const uint32_t E_d = (uint32_t)((2 * TM * 16) >> 4) - ((uint32_t)((2 * TM * 16) >> 4) << 16);  // wraps: LBO shrinks as the start grows
       const uint32_t bc = (uint32_t)g.b_chunk >> 4;
       const uint32_t B_d = bc, Bz_d = bc - (bc << 16);  // plain / zero-aliased-LBO descriptors
       const uint32_t bex = sb0 + g.kx * b_lbo, blo0 = sb0 + g.b_hi;

@@ -61,12 +61,14 @@ class _NAISBase(nn.Module):
         return {n: named[n] for n in ops.VARIANT_PARAMS[self.variant]}
 
     def _score(self, hist, tgt, hreg=None, treg=None, aux=None) -> torch.Tensor:
+        drop_p, seed = 0.0, 0
         if self._dropout_on_l1 and self.training and self.drop.p > 0:
-            raise NotImplementedError(
-                f"{type(self).__name__}: train-mode dropout on the attention hidden layer (model.py:71,162) is not "
-                "fused yet; call .eval() or set .drop.p = 0 (the region+distance models have no dropout)")
+            # relu(drop(attn_layer1(x))) in train mode (model.py:71,162): fused, counter-based mask; the seed comes from
+            # torch's CPU generator so torch.manual_seed makes a run reproducible (not the reference's mask stream)
+            drop_p, seed = float(self.drop.p), int(torch.randint(0, 2 ** 62, (1,)).item())
+            self.last_dropout_seed = seed
         P = self._params()
-        return ops.pairs_score(self.variant, float(self.beta), tuple(P.values()), hist, tgt, hreg, treg, aux)
+        return ops.pairs_score(self.variant, float(self.beta), tuple(P.values()), hist, tgt, hreg, treg, aux, drop_p, seed)
 
     def get_mask(self, user_history, target_item):
         return user_history != target_item.reshape([len(target_item), 1])

@@ -61,7 +61,8 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def build_params(variant: str, P: Dict[str, torch.Tensor], beta: float, keep: List[torch.Tensor]) -> NaisParams:
+def build_params(variant: str, P: Dict[str, torch.Tensor], beta: float, keep: List[torch.Tensor],
+                 dropout_p: float = 0.0, dropout_seed: int = 0) -> NaisParams:
     """NaisParams for a reference-shaped parameter dict.  Contiguous copies are appended to `keep` to stay alive."""
     def g(name):
         t = _f32(P[name].detach())
@@ -76,6 +77,7 @@ def build_params(variant: str, P: Dict[str, torch.Tensor], beta: float, keep: Li
     p.hid = w1.shape[0]
     p.dist_mode, p.dist_scale, p.beta = mode, scale, float(beta)
     p.dist_buckets, p.dist_bucket_km, p.region_num, p.n_branch = 1, 1.0, 0, 1
+    p.dropout_p, p.dropout_seed = float(dropout_p), int(dropout_seed)
     b0 = p.branch[0]
     b0.hist_poi, b0.tgt_poi, b0.w_poi, b0.w_reg = eh.data_ptr(), et.data_ptr(), eh.shape[1], 0
     b0.w1, b0.b1, b0.w2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr()
@@ -123,14 +125,14 @@ class _PairsFunction(torch.autograd.Function):
     """score = attention_network(pairs).  forward -> nais_pairs_forward, backward -> nais_pairs_backward."""
 
     @staticmethod
-    def forward(ctx, variant, beta, hist, tgt, hreg, treg, aux, *params):
+    def forward(ctx, variant, beta, drop, hist, tgt, hreg, treg, aux, *params):
         names = VARIANT_PARAMS[variant]
         P = dict(zip(names, params))
         dev = _need_cuda(hist, tgt, hreg, treg, aux, *params)
         lib = _lib.load()
         keep: List[torch.Tensor] = []
         with torch.cuda.device(dev):
-            p = build_params(variant, P, beta, keep)
+            p = build_params(variant, P, beta, keep, *drop)
             b = _pairs_struct(hist, tgt, hreg, treg, aux, keep)
             B = b.B
             score = torch.empty(B, device=dev, dtype=torch.float32)
@@ -138,7 +140,7 @@ class _PairsFunction(torch.autograd.Function):
             parts = torch.empty(p.n_branch, B, device=dev, dtype=torch.float32)
             _lib.check(lib.nais_pairs_forward(C.byref(p), C.byref(b), score.data_ptr(), row_sum.data_ptr(),
                                               parts.data_ptr(), _stream()), "nais_pairs_forward")
-        ctx.variant, ctx.beta = variant, beta
+        ctx.variant, ctx.beta, ctx.drop = variant, beta, drop
         ctx.save_for_backward(hist, tgt, hreg if hreg is not None else torch.empty(0), treg if treg is not None else torch.empty(0),
                               aux if aux is not None else torch.empty(0), row_sum, parts, *params)
         ctx.has = (hreg is not None, treg is not None, aux is not None)
@@ -157,7 +159,7 @@ class _PairsFunction(torch.autograd.Function):
         lib = _lib.load()
         keep: List[torch.Tensor] = []
         with torch.cuda.device(dev):
-            p = build_params(variant, P, ctx.beta, keep)
+            p = build_params(variant, P, ctx.beta, keep, *ctx.drop)
             b = _pairs_struct(hist, tgt, hreg, treg, aux, keep)
             G = {n: torch.zeros_like(t, dtype=torch.float32, memory_format=torch.contiguous_format) for n, t in P.items()}
             g = NaisGrads()
@@ -179,13 +181,29 @@ class _PairsFunction(torch.autograd.Function):
             ds = _f32(dscore)
             _lib.check(lib.nais_pairs_backward(C.byref(p), C.byref(b), parts.data_ptr(), row_sum.data_ptr(), ds.data_ptr(),
                                                C.byref(g), ws.data_ptr(), ws_bytes, _stream()), "nais_pairs_backward")
-        grads = tuple(G[n].to(P[n].dtype) if ctx.needs_input_grad[7 + i] else None for i, n in enumerate(names))
-        return (None, None, None, None, None, None, None) + grads
+        grads = tuple(G[n].to(P[n].dtype) if ctx.needs_input_grad[8 + i] else None for i, n in enumerate(names))
+        return (None, None, None, None, None, None, None, None) + grads
 
 
-def pairs_score(variant: str, beta: float, params: Sequence[torch.Tensor], hist, tgt, hreg=None, treg=None, aux=None):
-    """Pre-sigmoid scores [B] of explicit pairs (differentiable w.r.t. `params`, ordered as VARIANT_PARAMS[variant])."""
-    return _PairsFunction.apply(variant, beta, hist, tgt, hreg, treg, aux, *params)
+def pairs_score(variant: str, beta: float, params: Sequence[torch.Tensor], hist, tgt, hreg=None, treg=None, aux=None,
+                dropout_p: float = 0.0, dropout_seed: int = 0):
+    """Pre-sigmoid scores [B] of explicit pairs (differentiable w.r.t. `params`, ordered as VARIANT_PARAMS[variant]).
+    `dropout_p > 0` applies the train-mode dropout of NAIS_basic / NAIS_regionEmbedding (model.py:71,162) with the
+    counter-based mask of NaisParams::dropout_seed; backward regenerates the same mask."""
+    return _PairsFunction.apply(variant, beta, (float(dropout_p), int(dropout_seed)), hist, tgt, hreg, treg, aux, *params)
+
+
+def dropout_keep_mask(seed: int, B: int, H: int, hid: int, p: float):
+    """The keep-mask the kernels use, on the host (numpy bool [B,H,hid]) — for tests / reproducing a step."""
+    import numpy as np
+    idx = np.arange(B * H * hid, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + idx * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    t = min(int(float(np.float32(p)) * 4294967296.0), 0xFFFFFFFF)
+    return ((z >> np.uint64(32)) >= np.uint64(t)).reshape(B, H, hid)
 
 
 # ----------------------------------------------------------------------------------------------------------------------

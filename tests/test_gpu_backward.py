@@ -111,3 +111,38 @@ def test_train_steps_match_reference_flow():
         ref = ref_sd[k].numpy()
         # Adagrad's first steps move every touched weight by ~lr regardless of gradient size; compare updates
         np.testing.assert_allclose(v.cpu().double().numpy(), ref, rtol=0, atol=2e-5, err_msg=k)
+
+
+@pytest.mark.parametrize("variant", ["basic", "region"])
+def test_train_mode_dropout_forward_and_gradients(variant):
+    """relu(drop(attn_layer1(x))) of NAIS_basic / NAIS_regionEmbedding in train mode (model.py:71,162): the fused
+    counter-based mask is replayed on the host and handed to the oracle, so values and gradients must agree."""
+    from poi_recommendation_models_b200 import ops
+    rng = np.random.default_rng(5)
+    N, D, hid, beta, B, H = 300, 32, 48, 0.5, 23, 11
+    coords, region, R = synthetic.make_catalog(N, seed=2)
+    sd = orc.init_state(variant, N, D, hid, R, 1, seed=4, style="trained")
+    hist = np.stack([rng.choice(N, H, replace=False) for _ in range(B)]).astype(np.int64)
+    tgt = rng.integers(0, N, B).astype(np.int64)
+    tgt[::4] = hist[::4, 3]
+    m = util.make_model(variant, sd, beta).train()
+    assert m.drop.p == 0.5
+    args = (_dev(hist), _dev(tgt)) if variant == "basic" else (_dev(hist), _dev(tgt), _dev(region[hist]), _dev(region[tgt]))
+    torch.manual_seed(123)
+    s = m.attention_network(*args)
+    dscore = rng.normal(size=B)
+    (s * _dev(dscore).float()).sum().backward()
+    keep = ops.dropout_keep_mask(m.last_dropout_seed, B, H, hid, 0.5)
+    assert 0.4 < keep.mean() < 0.6
+    scale = torch.from_numpy(keep.astype(np.float64) * 2.0)
+    P = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    ref = orc.attention_network(P, variant, beta, torch.from_numpy(hist), torch.from_numpy(tgt), torch.from_numpy(region[hist]),
+                                torch.from_numpy(region[tgt]), None, dtype=torch.float64, l1_scale=scale)
+    (ref * torch.from_numpy(dscore)).sum().backward()
+    np.testing.assert_allclose(s.detach().cpu().double().numpy(), ref.detach().numpy(), rtol=1e-4, atol=1e-6)
+    _check_grads(m, {k: (v.grad if v.grad is not None else torch.zeros_like(v)).numpy() for k, v in P.items()})
+    # a second forward draws a new mask; eval() is deterministic
+    s2 = m.attention_network(*args)
+    assert not torch.equal(s.detach(), s2.detach())
+    m.eval()
+    assert torch.equal(m.attention_network(*args), m.attention_network(*args))
