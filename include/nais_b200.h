@@ -125,6 +125,8 @@ typedef struct NaisCatalog {
   const float* coords;   /* [n_rows,2] (lat,lon) degrees, centred on the host in float64 before the cast */
   int64_t row_base;
   int64_t n_rows;
+  float center_lat; /* the (lat, lon) that was subtracted from every coordinate (catalogue AND user items);      */
+  float center_lon; /* NAIS_DIST_KM needs cos(latitude) = cos(center_lat + centred lat) for the haversine distance */
 } NaisCatalog;
 
 /* User histories as CSR (train_matrix.getrow(u).indices, validation.py:86), with the per-item side data gathered. */

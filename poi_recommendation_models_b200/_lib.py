@@ -39,7 +39,8 @@ class NaisGrads(C.Structure):
 
 
 class NaisCatalog(C.Structure):
-    _fields_ = [("region", C.c_void_p), ("coords", C.c_void_p), ("row_base", C.c_int64), ("n_rows", C.c_int64)]
+    _fields_ = [("region", C.c_void_p), ("coords", C.c_void_p), ("row_base", C.c_int64), ("n_rows", C.c_int64),
+                ("center_lat", C.c_float), ("center_lon", C.c_float)]
 
 
 class NaisUsers(C.Structure):

@@ -132,8 +132,8 @@ static int check_fullrank(const NaisParams* p, const NaisCatalog* cat, const Nai
   for (int i = 0; i < p->n_branch; ++i) need_reg |= p->branch[i].w_reg > 0;
   const bool work = users->n_users > 0 && poi_end > poi_begin;
   if (work && need_reg && (!cat->region || !users->region)) return NAIS_ERR_NULL;
-  if (work && p->dist_mode == NAIS_DIST_LATLON && (!cat->coords || !users->coords)) return NAIS_ERR_NULL;
-  if (p->dist_mode == NAIS_DIST_KM) return NAIS_ERR_MODE;  // fused haversine: next tier
+  if (work && p->dist_mode != NAIS_DIST_NONE && (!cat->coords || !users->coords)) return NAIS_ERR_NULL;
+  if (p->dist_mode == NAIS_DIST_KM && precision != NAIS_PREC_FP32) return NAIS_ERR_MODE;  // fused haversine: FP32 path only
   if (precision < NAIS_PREC_FP32 || precision > NAIS_PREC_TC_FAST) return NAIS_ERR_MODE;
   if (precision != NAIS_PREC_FP32 && !tc_supported(*p)) return NAIS_ERR_SHAPE;
   return 0;

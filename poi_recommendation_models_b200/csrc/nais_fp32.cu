@@ -350,6 +350,16 @@ __global__ void __launch_bounds__(NT, 2) fullrank_fp32_kernel(const __grid_const
   extern __shared__ __align__(16) float smem[];
   const NaisParams& p = A.p;
   const int lanes = (p.dist_mode == NAIS_DIST_LATLON) ? 2 : 0;
+  const bool km_mode = p.dist_mode == NAIS_DIST_KM, geo = lanes || km_mode;
+  __shared__ float km_coef_s[64];  // sum_d embed_distance[bucket, d] (model.py:497-501)
+  if (km_mode) {
+    for (int b = threadIdx.x; b < min(p.dist_buckets, 64); b += blockDim.x) {
+      float c = 0.f;
+      const int Dk = p.branch[0].w_poi + p.branch[0].w_reg;
+      for (int d = 0; d < Dk; ++d) c += __ldg(p.dist_embed + (size_t)b * Dk + d);
+      km_coef_s[b] = c;
+    }
+  }
   int Dmax = 0;
   for (int i = 0; i < p.n_branch; ++i) Dmax = max(Dmax, p.branch[i].w_poi + p.branch[i].w_reg);
   TileSmem s;
@@ -375,10 +385,11 @@ __global__ void __launch_bounds__(NT, 2) fullrank_fp32_kernel(const __grid_const
     const int64_t j = A.poi_begin + (int64_t)tile * TC + cell;  // global POI id of this thread's cell
     const bool jvalid = j < A.poi_end;
     const int64_t jl = j - A.cat.row_base;
-    float cla = 0.f, clo = 0.f;
-    if (jvalid && lanes) {
+    float cla = 0.f, clo = 0.f, ccos = 1.f;
+    if (jvalid && geo) {
       cla = __ldg(A.cat.coords + jl * 2);
       clo = __ldg(A.cat.coords + jl * 2 + 1);
+      if (km_mode) ccos = cosf((A.cat.center_lat + cla) * 0.017453292519943295f);
     }
     float score = 0.f;
     bool excluded = false;
@@ -412,7 +423,7 @@ __global__ void __launch_bounds__(NT, 2) fullrank_fp32_kernel(const __grid_const
         if (tid < hn) {
           const int64_t e = h_begin + h0 + tid;
           hid_s[tid] = __ldg(A.users.items + e);
-          if (lanes) {
+          if (geo) {
             hco[2 * tid] = __ldg(A.users.coords + 2 * e);
             hco[2 * tid + 1] = __ldg(A.users.coords + 2 * e + 1);
           }
@@ -441,7 +452,15 @@ __global__ void __launch_bounds__(NT, 2) fullrank_fp32_kernel(const __grid_const
           if (tid < TC) {
             const bool m = (int64_t)hid_s[hh] != j;
             if (m) {
-              const float e = expf(s.a[cell]);
+              float a = s.a[cell];
+              if (km_mode) {  // logit += dist_km * sum_d embed_distance[bucket] (haversine from centred coordinates)
+                const float hla = hco[2 * hh], hlo = hco[2 * hh + 1];
+                const float km = dist_km_f(cla, clo, hla, hlo, ccos, cosf((A.cat.center_lat + hla) * 0.017453292519943295f));
+                int bkt = 0;
+                if (p.dist_buckets > 1) bkt = min(min((int)floorf(km / p.dist_bucket_km), p.dist_buckets - 1), 63);
+                a = fmaf(km, km_coef_s[bkt], a);
+              }
+              const float e = expf(a);
               sumE += e;
               sumES = fmaf(e, s.sp[cell] + s.sp[TC + cell], sumES);
             } else {

@@ -233,6 +233,7 @@ class DeviceUsers:
 def _structs(cat: DeviceCatalog, users: DeviceUsers):
     c = NaisCatalog()
     c.region, c.coords, c.row_base, c.n_rows = _ptr(cat.region), _ptr(cat.coords), cat.row_base, cat.n_rows
+    c.center_lat, c.center_lon = float(cat.center[0]), float(cat.center[1])
     u = NaisUsers()
     u.offsets, u.items, u.region, u.coords, u.n_users = (_ptr(users.offsets), _ptr(users.items), _ptr(users.region),
                                                          _ptr(users.coords), users.n_users)

@@ -65,6 +65,9 @@ def oracle_user_scores(sd, variant, beta, coords, region, history, cand, dtype=t
     aux = None
     if orc.VARIANTS[variant]["dist"] == "latlon":
         aux = torch.from_numpy(orc.latlon_abs_diff(coords, cand, history[None, :].repeat(B, 0)))
+    elif orc.VARIANTS[variant]["dist"] == "km":
+        aux = torch.from_numpy(orc.dist_km(coords[cand][:, None, 0], coords[cand][:, None, 1], coords[history][None, :, 0],
+                                           coords[history][None, :, 1]))  # float64 km, powerLaw.dist
     s, scale = orc.attention_network_with_scale(sd, variant, beta, hist, torch.from_numpy(cand), hreg, treg, aux, dtype=dtype)
     return s.numpy(), scale.numpy()
 

@@ -114,6 +114,24 @@ def test_fullrank_scores_match_oracle(variant, precision):
         assert util.cond_err(got[u], ref, scale) < PREC_TOL[precision], (u, util.cond_err(got[u], ref, scale))
 
 
+def test_fullrank_disentangled_fused_haversine():
+    """Two-branch disentangled model through the fused FP32 full-rank path: dist_km (powerLaw.dist, law of cosines in
+    float64) is formed in-kernel as a haversine of centred fp32 coordinates."""
+    U, N, beta = 4, 600, 0.5
+    data, sd, m = _fullrank_case("disentangled", U, N, seed=31, D=32, hid=32, hist_len=None, max_hist=30, min_hist=2, median_hist=10)
+    sd["embed_distance.weight"] = sd["embed_distance.weight"] * 3  # make the distance bias matter (|coef*km| ~ 1)
+    m.load_state_dict(sd)
+    users = m.make_users(data.indptr, data.indices)
+    got = ops.fullrank_scores("disentangled", beta, m._params(), m._catalog, users).cpu().numpy()
+    for u in range(U):
+        ref, scale = util.oracle_user_scores(sd, "disentangled", beta, data.coords, data.region, data.history(u), np.arange(N))
+        assert util.cond_err(got[u], ref, scale) < util.TOL, (u, util.cond_err(got[u], ref, scale))
+    s, ids = m.predict_topk(users, 10)
+    assert ids.shape == (U, 10) and (ids >= 0).all()
+    with pytest.raises(RuntimeError):
+        m.predict_topk(users, 10, precision="tc_split")
+
+
 @pytest.mark.parametrize("precision", ["fp32", "tc_split"])
 def test_fullrank_topk_matches_reference_validation_golden(precision):
     z = util.load_golden("validation_rd.npz")
