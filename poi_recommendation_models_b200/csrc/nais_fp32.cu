@@ -549,6 +549,7 @@ int launch_pairs_fwd(const NaisParams& p, const NaisPairs& b, float* score, floa
   A.rows_per_tile = rpt;
   const int D = max_D(p);
   const size_t smem = (tile_smem_floats(D) + (size_t)MAXROWS * D + 2 * TC + 2 * MAXROWS) * sizeof(float);
+  if (smem > 227 * 1024) return NAIS_ERR_SHAPE;
   cudaError_t e = cudaFuncSetAttribute(pairs_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int64_t grid = (b.B + rpt - 1) / rpt;
@@ -657,6 +658,7 @@ int launch_fullrank_fp32(const NaisParams& p, const NaisCatalog& cat, const Nais
   A.part_keys = reinterpret_cast<unsigned long long*>(ws);
   if (A.n_splits > 1 && ws_bytes < (size_t)users.n_users * A.n_splits * k * sizeof(unsigned long long)) return NAIS_ERR_WORKSPACE;
   const size_t smem = fullrank_fp32_smem(p);
+  if (smem > 227 * 1024) return NAIS_ERR_SHAPE;  // embed_size > 128: the candidate + pair tiles no longer fit in shared memory
   cudaError_t e = cudaFuncSetAttribute(fullrank_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   dim3 grid(users.n_users, A.n_splits);
