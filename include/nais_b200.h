@@ -9,6 +9,7 @@
  *   model.py:57-89, 144-180, 355-401, 467-534   the sibling scorers        -> same entry points, other NaisParams
  *   validation.py:84-127   per-user candidate loop + torch.topk            -> nais_fullrank_topk
  *   torch.cat/topk merge across catalogue shards (new, multi-GPU)          -> nais_topk_merge
+ *   eval_metrics.py:36-69  set-overlap counts behind precision/recall/hit@k  -> nais_hits_at_k
  *
  * Conventions
  *   - every pointer is a DEVICE pointer into memory owned by the caller (PyTorch tensors); the library never
@@ -168,6 +169,14 @@ NAIS_API int nais_fullrank_topk(const NaisParams* p, const NaisCatalog* cat, con
  * in_score/in_id: [n_users, n_lists, k]; out: [n_users, k].  Same order rule as nais_fullrank_topk. */
 NAIS_API int nais_topk_merge(const float* in_score, const int32_t* in_id, int32_t n_users, int32_t n_lists, int32_t k,
                     float* out_score, int32_t* out_id, nais_stream_t stream);
+
+/* Per-user hit counts behind eval_metrics.precision_at_k / recall_at_k / hitrate_at_k (eval_metrics.py:36-69):
+ * hits[u, i] = |positives(u) ∩ rec[u, :k_list[i]]| for the recommended lists rec [n_users, k_rec] (ids, -1 padding) and the
+ * positives CSR (pos_offsets [n_users+1], pos_items).  Integer work only: the float means are formed by the caller in the
+ * reference's order, so the metrics stay bit-identical.  k_list is a DEVICE array of n_k ints. */
+NAIS_API int nais_hits_at_k(const int32_t* rec, int32_t n_users, int32_t k_rec, const int64_t* pos_offsets,
+                            const int32_t* pos_items, const int32_t* k_list, int32_t n_k, int32_t* hits,
+                            nais_stream_t stream);
 
 /* Same scoring pass, but also writes every pre-sigmoid score: all_scores[n_users, poi_end-poi_begin] (history items are
  * scored with their own cell masked, like a training positive).  For parity checks of the fused path on small cases. */

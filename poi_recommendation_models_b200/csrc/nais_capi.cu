@@ -69,6 +69,32 @@ __global__ void fill_empty_topk_kernel(float* s, int32_t* id, size_t n) {
   }
 }
 
+// hits[u,i] = | set(pos(u)) & set(rec[u,:k_i]) | : one warp per user; duplicates in either list count once, like the
+// reference's Python set intersection (eval_metrics.py:40-42).
+__global__ void hits_at_k_kernel(const int32_t* __restrict__ rec, int n_users, int k_rec, const int64_t* __restrict__ po,
+                                 const int32_t* __restrict__ pi, const int32_t* __restrict__ k_list, int n_k, int32_t* hits) {
+  const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (u >= n_users) return;
+  const int64_t p0 = po[u], p1 = po[u + 1];
+  for (int ki = 0; ki < n_k; ++ki) {
+    const int k = min(k_list[ki], k_rec);
+    int cnt = 0;
+    for (int r = lane; r < k; r += 32) {
+      const int id = rec[(size_t)u * k_rec + r];
+      if (id < 0) continue;
+      bool dup = false;  // first occurrence within the prefix only
+      for (int q = 0; q < r && !dup; ++q) dup = rec[(size_t)u * k_rec + q] == id;
+      if (dup) continue;
+      bool hit = false;
+      for (int64_t q = p0; q < p1 && !hit; ++q) hit = pi[q] == id;
+      cnt += hit ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) hits[(size_t)u * n_k + ki] = cnt;
+  }
+}
+
 extern "C" {
 
 int nais_abi_version(void) { return NAIS_ABI_VERSION; }
@@ -188,6 +214,18 @@ int nais_fullrank_scores(const NaisParams* p, const NaisCatalog* cat, const Nais
                                 workspace_bytes - head, st);
   return launch_fullrank_tc(*p, *cat, *users, poi_begin, poi_end, 1, 0, precision, sc, id, all_scores, rest,
                             workspace_bytes - head, st);
+}
+
+int nais_hits_at_k(const int32_t* rec, int32_t n_users, int32_t k_rec, const int64_t* pos_offsets, const int32_t* pos_items,
+                   const int32_t* k_list, int32_t n_k, int32_t* hits, nais_stream_t stream) {
+  if (n_users < 0 || k_rec < 1 || n_k < 1) return NAIS_ERR_SHAPE;
+  if (n_users == 0) return 0;
+  if (!rec || !pos_offsets || !k_list || !hits) return NAIS_ERR_NULL;
+  const int64_t threads = (int64_t)n_users * 32;
+  hits_at_k_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(rec, n_users, k_rec, pos_offsets,
+                                                                                                  pos_items, k_list, n_k, hits);
+  NAIS_COUNT_LAUNCH(1);
+  return (int)cudaGetLastError();
 }
 
 int nais_topk_merge(const float* in_score, const int32_t* in_id, int32_t n_users, int32_t n_lists, int32_t k,

@@ -66,3 +66,27 @@ def evaluate_mp(positive_list, recommended_list, k_list):
     recall = [recall_at_k(positive_list, recommended_list, k) for k in k_list]
     hit = [hitrate_at_k(positive_list, recommended_list, k) for k in k_list]
     return precision, recall, hit
+
+
+def evaluate_device(positive_list, rec_ids, k_list):
+    """(precision, recall, hit) lists like `evaluate_mp`, from a DEVICE tensor of recommended ids [U, k] (as
+    `model.predict_topk` returns): the set overlaps are counted on the GPU (`nais_hits_at_k`), only U x len(k_list)
+    integers come back, and the means are accumulated here exactly like eval_metrics.py:36-69 — same floats."""
+    from . import ops
+    hits = ops.hits_at_k(rec_ids, positive_list, k_list).cpu().tolist()
+    sizes = [len(set(int(x) for x in p)) for p in positive_list]
+    precision, recall, hit = [], [], []
+    for i, k in enumerate(k_list):
+        sp, sr, sh, n = 0.0, 0.0, 0.0, 0
+        for u, m in enumerate(sizes):
+            h = hits[u][i]
+            sp += h / float(k)
+            if m != 0:
+                sr += h / float(m)
+                if h > 0:
+                    sh += 1
+                n += 1
+        precision.append(sp / len(sizes))
+        recall.append(sr / n)
+        hit.append(sh / n)
+    return precision, recall, hit

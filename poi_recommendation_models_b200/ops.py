@@ -293,3 +293,25 @@ def topk_merge(scores: torch.Tensor, ids: torch.Tensor) -> Tuple[torch.Tensor, t
         _lib.check(lib.nais_topk_merge(s.data_ptr(), i.data_ptr(), U, L, k, out_s.data_ptr(), out_i.data_ptr(), _stream()),
                    "nais_topk_merge")
     return out_s, out_i
+
+
+def hits_at_k(rec_ids: torch.Tensor, positives: Sequence[Sequence[int]], k_list: Sequence[int]) -> torch.Tensor:
+    """hits[U, len(k_list)] = |set(positives[u]) & set(rec_ids[u, :k])| on the device (nais_hits_at_k) — the integer core
+    of eval_metrics.precision_at_k / recall_at_k / hitrate_at_k (eval_metrics.py:36-69)."""
+    import numpy as np
+    dev = _need_cuda(rec_ids)
+    U, k_rec = rec_ids.shape
+    lens = np.fromiter((len(p) for p in positives), dtype=np.int64, count=U)
+    off = np.zeros(U + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    flat = np.fromiter((int(x) for p in positives for x in p), dtype=np.int32, count=int(off[-1]))
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        rec = rec_ids.to(torch.int32).contiguous()
+        po = torch.from_numpy(off).to(dev)
+        pi = torch.from_numpy(flat).to(dev) if len(flat) else torch.zeros(1, dtype=torch.int32, device=dev)
+        kl = torch.tensor(list(k_list), dtype=torch.int32, device=dev)
+        hits = torch.empty(U, len(k_list), dtype=torch.int32, device=dev)
+        _lib.check(lib.nais_hits_at_k(rec.data_ptr(), U, k_rec, po.data_ptr(), pi.data_ptr(), kl.data_ptr(), len(k_list),
+                                      hits.data_ptr(), _stream()), "nais_hits_at_k")
+    return hits

@@ -196,3 +196,21 @@ def test_fullrank_empty_inputs():
     users = m.make_users(data.indptr, data.indices)
     s, i = ops.fullrank_topk("region_distance", 0.5, m._params(), m._catalog, users, 5, 10, 10)
     assert (i.cpu() == -1).all()
+
+
+def test_device_metrics_bit_identical_to_reference_functions():
+    from poi_recommendation_models_b200 import eval_metrics as PM
+    rng = np.random.default_rng(4)
+    U, k_list = 300, [5, 10, 15, 20, 25, 30]
+    actual = [rng.choice(600, rng.integers(0, 7), replace=False).tolist() for _ in range(U)]
+    actual[3] = actual[3] + actual[3][:1]  # duplicate positive: a Python set counts it once
+    rec = np.stack([rng.choice(600, 50, replace=False) for _ in range(U)]).astype(np.int64)
+    rec[5, 40:] = -1  # padded list
+    got = PM.evaluate_device(actual, torch.from_numpy(rec).cuda(), k_list)
+    rec_l = [[i for i in r if i >= 0] for r in rec.tolist()]
+    ref = (
+        [orc.precision_at_k(actual, rec_l, k) for k in k_list],
+        [orc.recall_at_k(actual, rec_l, k) for k in k_list],
+        [orc.hitrate_at_k(actual, rec_l, k) for k in k_list],
+    )
+    assert got[0] == ref[0] and got[1] == ref[1] and got[2] == ref[2]
