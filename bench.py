@@ -84,42 +84,46 @@ def synth_histories(users, pois, hist, seed=0):
 
 
 class ClockSampler:
+    """`nvidia-smi -lms 100` streamed for the duration of the timed region (the recipe's clocks line)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.rows, self.stop_flag, self.th = index, [], False, None
-
-    def _run(self):
-        while not self.stop_flag:
-            try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([x.strip() for x in o.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        self.index, self.proc = index, None
 
     def start(self):
-        self.th = threading.Thread(target=self._run, daemon=True)
-        self.th.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.3)  # first sample is in flight before the timed region starts
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self.stop_flag = True
-        if self.th:
-            self.th.join(timeout=6)
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = []
+        if self.proc is not None:
+            try:
+                time.sleep(0.15)
+                self.proc.terminate()
+                out, _ = self.proc.communicate(timeout=5)
+                rows = [[x.strip() for x in ln.split(",")] for ln in out.splitlines() if ln.strip()]
+            except Exception:
+                pass
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
+                pw.append(float(r[2]))
             except Exception:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        # "under load" = samples drawing more than half of the maximum power seen
+        load = [c for c, p_ in zip(sm, pw) if pw and p_ >= 0.5 * max(pw)] or sm
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(load),
+                "power_w_max": max(pw) if pw else None}
 
 
 def cpu_arm(cfg, n_users, seed=0, warm=1):
