@@ -1,0 +1,149 @@
+"""Property-style GPU parity cases the reference never tested: beta in {0, 0.5, 1}, duplicate history
+items, H = 1, exact score ties in the top-k, saturated sigmoid, large logits, and shard/merge invariance at random cuts."""
+import numpy as np
+import pytest
+import torch
+
+import nais_testutil as util
+from oracle import nais_oracle as orc
+from poi_recommendation_models_b200 import ops, synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _case(N=500, D=64, hid=64, seed=0, style="trained", variant="region_distance"):
+    coords, region, R = synthetic.make_catalog(N, seed=seed)
+    sd = orc.init_state(variant, N, D, hid, R, 1, seed=seed + 1, style=style)
+    return coords, region, R, sd
+
+
+@pytest.mark.parametrize("beta", [0.0, 0.5, 1.0, 0.25])
+def test_beta_values_pairs_and_fullrank(beta):
+    N = 500
+    coords, region, R, sd = _case(N)
+    rng = np.random.default_rng(int(beta * 100))
+    B, H = 33, 21
+    hist = np.stack([rng.choice(N, H, replace=False) for _ in range(B)]).astype(np.int64)
+    tgt = rng.integers(0, N, B).astype(np.int64)
+    tgt[::3] = hist[::3, 0]
+    aux = orc.latlon_abs_diff(coords, tgt, hist)
+    m = util.make_model("region_distance", sd, beta)
+    with torch.no_grad():
+        s = m.attention_network(_dev(hist), _dev(tgt), _dev(region[hist]), _dev(region[tgt]), _dev(aux)).cpu().numpy()
+    ref, scale = orc.attention_network_with_scale(sd, "region_distance", beta, torch.from_numpy(hist), torch.from_numpy(tgt),
+                                                  torch.from_numpy(region[hist]), torch.from_numpy(region[tgt]),
+                                                  torch.from_numpy(aux), dtype=torch.float64)
+    assert util.cond_err(s, ref.numpy(), scale.numpy()) < util.TOL
+    m.set_catalog(region=region, coords=coords)
+    users = m.make_users(np.array([0, H]), hist[0])
+    for prec in ("fp32", "tc_split"):
+        got = ops.fullrank_scores("region_distance", beta, m._params(), m._catalog, users, precision=prec).cpu().numpy()[0]
+        r2, sc2 = util.oracle_user_scores(sd, "region_distance", beta, coords, region, hist[0], np.arange(N))
+        assert util.cond_err(got, r2, sc2) < util.TOL, prec
+
+
+def test_duplicate_history_items_and_h1():
+    """The reference never pads or de-duplicates: a POI listed twice counts twice; with H = 1 the softmax has one term."""
+    N = 300
+    coords, region, R, sd = _case(N, seed=3)
+    m = util.make_model("region_distance", sd, 0.5)
+    hist = np.array([[5, 9, 5, 7, 9, 5]], dtype=np.int64).repeat(4, 0)
+    tgt = np.array([1, 5, 9, 200], dtype=np.int64)  # 5 and 9 are masked at every occurrence
+    aux = orc.latlon_abs_diff(coords, tgt, hist)
+    with torch.no_grad():
+        s = m.attention_network(_dev(hist), _dev(tgt), _dev(region[hist]), _dev(region[tgt]), _dev(aux)).cpu().numpy()
+    ref, scale = orc.attention_network_with_scale(sd, "region_distance", 0.5, torch.from_numpy(hist), torch.from_numpy(tgt),
+                                                  torch.from_numpy(region[hist]), torch.from_numpy(region[tgt]),
+                                                  torch.from_numpy(aux), dtype=torch.float64)
+    assert util.cond_err(s, ref.numpy(), scale.numpy()) < util.TOL
+    m.set_catalog(region=region, coords=coords)
+    for prec in ("fp32", "tc_split", "tc_fast"):
+        users = m.make_users(np.array([0, 6, 7]), np.array([5, 9, 5, 7, 9, 5, 42]))  # user 1 has H = 1
+        got = ops.fullrank_scores("region_distance", 0.5, m._params(), m._catalog, users, precision=prec).cpu().numpy()
+        for u, h in enumerate(([5, 9, 5, 7, 9, 5], [42])):
+            r2, sc2 = util.oracle_user_scores(sd, "region_distance", 0.5, coords, region, np.array(h), np.arange(N))
+            ok = ~np.isnan(r2)  # H = 1 and target == that item: NaN in the reference too
+            assert util.cond_err(got[u][ok], r2[ok], sc2[ok]) < (5e-4 if prec == "tc_fast" else util.TOL), (prec, u)
+            assert np.isnan(got[u][~ok]).all()
+        s_k, i_k = ops.fullrank_topk("region_distance", 0.5, m._params(), m._catalog, users, 10, precision=prec)
+        assert not set(i_k[0].tolist()) & {5, 7, 9} and 42 not in i_k[1].tolist()
+
+
+def test_exact_ties_are_broken_by_poi_id():
+    """Identical candidate rows (same target embedding, region, coordinates) score identically; the top-k must list them
+    in ascending id order on every path and across shard merges."""
+    N = 400
+    coords, region, R, sd = _case(N, seed=5)
+    hist = np.array([10, 20, 30, 40, 50, 60, 70])
+    m0 = util.make_model("region_distance", sd, 0.5)
+    m0.set_catalog(region=region, coords=coords)
+    sc0 = ops.fullrank_scores("region_distance", 0.5, m0._params(), m0._catalog, m0.make_users(np.array([0, len(hist)]), hist)).cpu().numpy()[0]
+    sc0[hist] = -np.inf
+    base = int(np.argmax(sc0))  # the user's best candidate ...
+    clones = np.array([base] + [c for c in (230, 3, 399, 120) if c != base])
+    for c in clones[1:]:  # ... cloned into four other ids
+        sd["embed_target.weight"][c] = sd["embed_target.weight"][base]
+        region[c] = region[base]
+        coords[c] = coords[base]
+    m = util.make_model("region_distance", sd, 0.5)
+    m.set_catalog(region=region, coords=coords)
+    users = m.make_users(np.array([0, len(hist)]), hist)
+    for prec in ("fp32", "tc_split", "tc_fast"):
+        sc = ops.fullrank_scores("region_distance", 0.5, m._params(), m._catalog, users, precision=prec).cpu().numpy()[0]
+        assert len(set(sc[clones].tolist())) == 1, prec  # bitwise equal scores
+        s_k, i_k = ops.fullrank_topk("region_distance", 0.5, m._params(), m._catalog, users, 8, precision=prec)
+        ids = i_k[0].cpu().numpy()
+        assert ids[:len(clones)].tolist() == np.sort(clones).tolist(), (prec, ids)
+        cuts = [0, 100, 250, N]
+        parts = [ops.fullrank_topk("region_distance", 0.5, m._params(), m._catalog, users, 8, cuts[i], cuts[i + 1], precision=prec) for i in range(3)]
+        ms, mi = ops.topk_merge(torch.stack([p[0] for p in parts], 1), torch.stack([p[1] for p in parts], 1))
+        assert torch.equal(mi, i_k) and torch.equal(ms, s_k)
+
+
+def test_saturated_sigmoid_and_large_logits():
+    """forward() = sigmoid(score) saturates to exactly 1.0 / 0.0 in fp32 like the reference; ranking uses the raw score, a
+    valid refinement of ranking the saturated values."""
+    N = 300
+    coords, region, R, sd = _case(N, seed=7)
+    for k in ("embed_history.weight", "embed_target.weight", "embed_region.weight"):
+        sd[k] = sd[k] * 4.0  # |score| up to hundreds, logits of tens
+    rng = np.random.default_rng(1)
+    B, H = 64, 9
+    hist = np.stack([rng.choice(N, H, replace=False) for _ in range(B)]).astype(np.int64)
+    tgt = rng.integers(0, N, B).astype(np.int64)
+    aux = orc.latlon_abs_diff(coords, tgt, hist)
+    m = util.make_model("region_distance", sd, 0.5)
+    with torch.no_grad():
+        f = m(_dev(hist), _dev(tgt), _dev(region[hist]), _dev(region[tgt]), _dev(aux)).cpu().numpy()
+        s = m.attention_network(_dev(hist), _dev(tgt), _dev(region[hist]), _dev(region[tgt]), _dev(aux)).cpu().numpy()
+    ref32 = orc.forward(sd, "region_distance", 0.5, torch.from_numpy(hist), torch.from_numpy(tgt), torch.from_numpy(region[hist]),
+                        torch.from_numpy(region[tgt]), torch.from_numpy(aux)).numpy()
+    ref, scale = orc.attention_network_with_scale(sd, "region_distance", 0.5, torch.from_numpy(hist), torch.from_numpy(tgt),
+                                                  torch.from_numpy(region[hist]), torch.from_numpy(region[tgt]),
+                                                  torch.from_numpy(aux), dtype=torch.float64)
+    assert np.abs(ref.numpy()).max() > 20
+    assert util.cond_err(s, ref.numpy(), scale.numpy()) < util.TOL
+    np.testing.assert_allclose(f, ref32, rtol=util.TOL, atol=1e-30)
+    assert ((f == 1.0) == (ref32 == 1.0)).all()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_shard_cuts_are_bit_identical(seed):
+    rng = np.random.default_rng(seed)
+    U, N, k = 7, 2000, 20
+    data = synthetic.make_checkins(U, N, seed=seed + 40, hist_len=None, max_hist=70, min_hist=1, median_hist=20)
+    sd = orc.init_state("region_distance", N, 64, 64, data.region_num, 1, seed=seed, style="trained")
+    m = util.make_model("region_distance", sd, 0.5)
+    m.set_catalog(region=data.region, coords=data.coords)
+    users = m.make_users(data.indptr, data.indices)
+    for prec in ("fp32", "tc_split"):
+        full = ops.fullrank_topk("region_distance", 0.5, m._params(), m._catalog, users, k, precision=prec)
+        cuts = [0] + sorted(rng.choice(np.arange(1, N), 4, replace=False).tolist()) + [N]
+        parts = [ops.fullrank_topk("region_distance", 0.5, m._params(), m._catalog, users, k, cuts[i], cuts[i + 1], precision=prec)
+                 for i in range(len(cuts) - 1)]
+        ms, mi = ops.topk_merge(torch.stack([p[0] for p in parts], 1), torch.stack([p[1] for p in parts], 1))
+        assert torch.equal(mi, full[1]) and torch.equal(ms, full[0]), (prec, cuts)
