@@ -69,6 +69,25 @@ def main():
     torch.cuda.synchronize()
     t_train = time.perf_counter() - t0
 
+    # ---- the same epoch with batches built on the device (f1): same distribution, device RNG -----------------------------
+    model2 = M.NAIS_region_distance_Embedding(args.pois, D, hid, beta, data.region_num, 1).to(dev)
+    model2.load_state_dict(sd0)
+    opt2 = torch.optim.Adagrad(model2.parameters(), lr=lr, weight_decay=0.0)
+    bt = PB.DeviceBatcher(csr, data.region, data.coords, device=dev, seed=0)
+    model2.train()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    loss2 = torch.zeros((), device=dev)
+    for u in order:
+        hist, tgt, label, hreg, treg, ll = bt.batch(u, num_ng)
+        opt2.zero_grad()
+        l2 = model2.loss_func(model2(hist, tgt, hreg, treg, ll), label)
+        l2.backward()
+        opt2.step()
+        loss2 += l2.detach()
+    torch.cuda.synchronize()
+    t_train_dev = time.perf_counter() - t0
+
     # ---- oracle replay of the first steps (float64, same RNG stream) ---------------------------------------------------
     random.setstate(rng_state)
     ref_sd, ref_sum = {k: v.double() for k, v in sd0.items()}, None
@@ -117,6 +136,8 @@ def main():
     report = {
         "config": f"C1: {args.users} users x {args.pois} POIs, D=hid=64, H<=100, 1 epoch BCE/Adagrad + full-rank eval",
         "train": {"gpu_s": t_train, "gpu_users_per_s": args.users / t_train, "epoch_loss_sum": loss_sum,
+                  "device_batcher_gpu_s": t_train_dev, "device_batcher_users_per_s": args.users / t_train_dev,
+                  "device_batcher_epoch_loss_sum": float(loss2),
                   "oracle_users_per_s": args.ref_train_users / t_ref_train, "oracle_users": args.ref_train_users,
                   "max_abs_param_diff_after_oracle_steps": train_diff},
         "eval": {"gpu_s": t_eval, "gpu_users_per_s": args.users / t_eval, "precision": args.precision,

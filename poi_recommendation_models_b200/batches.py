@@ -76,3 +76,47 @@ def lat_lon_pairs(place_coords, target_pois, history_pois, device=None):
         h = np.broadcast_to(h, (len(t), len(h)))
     ll = np.abs(c[t][:, None, :] - c[h]).astype(np.float32)
     return torch.from_numpy(ll).to(device or _device())
+
+
+class DeviceBatcher:
+    """Training batches built ON THE DEVICE: same batch layout as `get_NAIS_batch_region`
+    (batches.py:67-108: shuffled positives, targets interleaved [p, n..n], labels [1, 0..0], history repeated per target)
+    and the same sampling *distribution* — `len(pos)*num_ng` negatives uniform without replacement over the non-visited
+    POIs — but drawn with a device RNG (`torch.randperm`), not the reference's Python `random` stream, and without any
+    O(N) Python list work or host->device copies per user.  Also returns the |dlat|,|dlon| tensor of run.py:239-247.
+
+    PyTorch ops only (index plumbing); the scorer kernels are untouched."""
+
+    def __init__(self, train_matrix, businessRegionEmbedList, place_coords, device=None, seed=0):
+        dev = torch.device(device or _device())
+        csr = train_matrix.tocsr()
+        csr.sort_indices()
+        self.num_poi = csr.shape[1]
+        self.indptr = np.asarray(csr.indptr, dtype=np.int64)
+        self.indices = torch.from_numpy(np.asarray(csr.indices, dtype=np.int64)).to(dev)
+        self.region = torch.from_numpy(np.asarray(businessRegionEmbedList, dtype=np.int64)).to(dev)
+        self.coords = torch.from_numpy(np.asarray(place_coords, dtype=np.float64)).to(dev)
+        self.gen = torch.Generator(device=dev)
+        self.gen.manual_seed(seed)
+        self.dev = dev
+        self._visited = torch.zeros(self.num_poi, dtype=torch.bool, device=dev)
+
+    def batch(self, uid: int, negative_num: int):
+        """-> (user_history [B,H], train_data [B], train_label [B], user_history_region [B,H], train_data_region [B],
+        target_lat_long [B,H,2])  with B = H * (negative_num + 1)."""
+        a, b = int(self.indptr[uid]), int(self.indptr[uid + 1])
+        pos = self.indices[a:b]
+        H = b - a
+        pos = pos[torch.randperm(H, device=self.dev, generator=self.gen)]
+        m = H * negative_num
+        # uniform without replacement over the non-visited POIs: a random permutation with the visited ones removed
+        perm = torch.randperm(self.num_poi, device=self.dev, generator=self.gen)[: m + H]
+        self._visited[pos] = True
+        neg = perm[~self._visited[perm]][:m]
+        self._visited[pos] = False
+        tgt = torch.cat((pos.view(-1, 1), neg.view(-1, negative_num)), dim=1).reshape(-1)
+        label = torch.zeros(H, negative_num + 1, device=self.dev)
+        label[:, 0] = 1.0
+        hist = pos.unsqueeze(0).expand(tgt.numel(), H).contiguous()
+        ll = (self.coords[tgt].unsqueeze(1) - self.coords[pos].unsqueeze(0)).abs().to(torch.float32).contiguous()
+        return hist, tgt, label.reshape(-1), self.region[hist], self.region[tgt], ll

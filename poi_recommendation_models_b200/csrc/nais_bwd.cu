@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
         if (resident != kb) {
           __syncthreads();
           for (int i = tid; i < D * KB; i += NT) {
-            int kk = i / D, d = i - kk * D;
+            const int d = i / KB, kk = i - d * KB;  // consecutive threads -> consecutive smem words (no bank conflicts)
             int k = kb * KB + kk;
             Wt[d * KB + kk] = (k < hid) ? __ldg(br.w1 + (size_t)k * ldw + d) : 0.f;
           }

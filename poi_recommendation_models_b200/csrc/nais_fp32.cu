@@ -46,7 +46,7 @@ __device__ inline float* carve_tile(float* base, int D, TileSmem& s) {
 __device__ inline void load_wblock(const NaisBranch& br, int hid, int D, int lanes, int kb, const TileSmem& s) {
   const int ldw = D + lanes;
   for (int i = threadIdx.x; i < D * KB; i += blockDim.x) {
-    int kk = i / D, d = i - kk * D;
+    const int d = i / KB, kk = i - d * KB;  // consecutive threads -> consecutive smem words (no bank conflicts)
     int k = kb * KB + kk;
     s.Wt[d * KB + kk] = (k < hid) ? __ldg(br.w1 + (size_t)k * ldw + d) : 0.f;
   }

@@ -146,3 +146,31 @@ def test_train_mode_dropout_forward_and_gradients(variant):
     assert not torch.equal(s.detach(), s2.detach())
     m.eval()
     assert torch.equal(m.attention_network(*args), m.attention_network(*args))
+
+
+def test_device_batcher_layout_and_distribution():
+    from poi_recommendation_models_b200 import batches as PB
+    N = 500
+    data = synthetic.make_checkins(5, N, seed=11, hist_len=None, max_hist=30, min_hist=5, median_hist=12)
+    bt = PB.DeviceBatcher(data.train_csr(), data.region, data.coords, device="cuda", seed=1)
+    counts = np.zeros(N)
+    for rep in range(40):
+        for u in range(5):
+            hist, tgt, label, hreg, treg, ll = bt.batch(u, 4)
+            H = len(data.history(u))
+            assert hist.shape == (5 * H, H) and tgt.shape == (5 * H,) and ll.shape == (5 * H, H, 2)
+            t = tgt.view(H, 5).cpu().numpy()
+            assert sorted(t[:, 0].tolist()) == data.history(u).tolist()  # positives: a permutation of the history
+            assert (hist[0].cpu().numpy() == t[:, 0]).all() and torch.equal(hist[0], hist[-1])
+            negs = t[:, 1:].reshape(-1)
+            assert len(set(negs.tolist())) == len(negs) and not set(negs.tolist()) & set(data.history(u).tolist())
+            assert torch.equal(label.view(H, 5)[:, 0], torch.ones(H, device="cuda")) and label.sum().item() == H
+            assert torch.equal(hreg, bt.region[hist]) and torch.equal(treg, bt.region[tgt])
+            ref_ll = orc.latlon_abs_diff(data.coords, tgt.cpu().numpy(), hist.cpu().numpy())
+            assert np.array_equal(ll.cpu().numpy(), ref_ll)  # same float32 values as run.py:239-247
+            if u == 0:
+                counts[negs] += 1
+    nonvis = np.setdiff1d(np.arange(N), data.history(0))
+    expected = 40 * 4 * len(data.history(0)) / len(nonvis)
+    assert counts[data.history(0)].sum() == 0 and abs(counts[nonvis].mean() - expected) < 1e-9
+    assert counts[nonvis].std() < 3 * np.sqrt(expected)  # roughly uniform over the non-visited POIs
