@@ -342,4 +342,4 @@ def train_step_bce(sd, variant, beta, hist, tgt, hreg, treg, aux, label, lr=0.01
         gk = t.grad if t.grad is not None else torch.zeros_like(t)
         new_sum[k] = state_sum[k].to(dtype) + gk * gk
         new_sd[k] = (t.detach() - lr * gk / (new_sum[k].sqrt() + 1e-10))
-    return float(loss), new_sd, new_sum
+    return float(loss.detach()), new_sd, new_sum

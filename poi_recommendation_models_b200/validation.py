@@ -16,7 +16,7 @@ import torch
 from . import eval_metrics
 
 
-def _recommend(model, args, train_matrix, num_users, precision="fp32", user_batch=8192):
+def _recommend(model, args, train_matrix, num_users, precision="fp32", user_batch=2048):
     csr = train_matrix.tocsr()
     csr.sort_indices()
     k = int(args.topk)

@@ -147,3 +147,20 @@ def test_random_shard_cuts_are_bit_identical(seed):
                  for i in range(len(cuts) - 1)]
         ms, mi = ops.topk_merge(torch.stack([p[0] for p in parts], 1), torch.stack([p[1] for p in parts], 1))
         assert torch.equal(mi, full[1]) and torch.equal(ms, full[0]), (prec, cuts)
+
+
+@pytest.mark.parametrize("H", [513, 700])
+def test_long_history_beyond_the_smem_staging_window(H):
+    """History longer than the 512 items the tensor kernel stages in shared memory (the rest is read with __ldg), odd
+    length (last chunk half empty)."""
+    N = 1200
+    coords, region, R, sd = _case(N, seed=9)
+    rng = np.random.default_rng(H)
+    hist = np.sort(rng.choice(N, H, replace=False))
+    m = util.make_model("region_distance", sd, 0.5)
+    m.set_catalog(region=region, coords=coords)
+    users = m.make_users(np.array([0, H]), hist)
+    ref, scale = util.oracle_user_scores(sd, "region_distance", 0.5, coords, region, hist, np.arange(N))
+    for prec in ("fp32", "tc_split"):
+        got = ops.fullrank_scores("region_distance", 0.5, m._params(), m._catalog, users, precision=prec).cpu().numpy()[0]
+        assert util.cond_err(got, ref, scale) < util.TOL, prec
