@@ -200,8 +200,6 @@ __global__ void __launch_bounds__(NT, 2) pairs_fwd_kernel(const __grid_constant_
   float* row_es = row_e + MAXROWS;         // [MAXROWS] running sum E*s
   __shared__ float km_c;
 
-  const int64_t row0 = (int64_t)blockIdx.x * A.rows_per_tile;
-  const int nrows = (int)min((int64_t)A.rows_per_tile, A.b.B - row0);
   const int n_chunks = (H <= TC) ? 1 : (H + TC - 1) / TC;
   const int tid = threadIdx.x, cell = tid & (TC - 1), half = tid >> 7;
   int resident = -1;
@@ -210,6 +208,11 @@ __global__ void __launch_bounds__(NT, 2) pairs_fwd_kernel(const __grid_constant_
     dc.thresh = dropout_threshold(p.dropout_p);
     dc.inv_keep = 1.f / (1.f - p.dropout_p);
   }
+  // persistent over work items (groups of rows): the W^T block stays resident in shared memory across items
+  const int64_t n_items = (A.b.B + A.rows_per_tile - 1) / A.rows_per_tile;
+  for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+  const int64_t row0 = item * A.rows_per_tile;
+  const int nrows = (int)min((int64_t)A.rows_per_tile, A.b.B - row0);
   float my_total = 0.f;  // thread r (< nrows) accumulates the final score of row r over branches
 
   for (int bi = 0; bi < p.n_branch; ++bi) {
@@ -327,6 +330,8 @@ __global__ void __launch_bounds__(NT, 2) pairs_fwd_kernel(const __grid_constant_
     __syncthreads();
   }
   if (tid < nrows) A.score[row0 + tid] = my_total;
+  __syncthreads();
+  }  // items
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -552,7 +557,8 @@ int launch_pairs_fwd(const NaisParams& p, const NaisPairs& b, float* score, floa
   if (smem > 227 * 1024) return NAIS_ERR_SHAPE;
   cudaError_t e = cudaFuncSetAttribute(pairs_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  const int64_t grid = (b.B + rpt - 1) / rpt;
+  int64_t grid = (b.B + rpt - 1) / rpt;
+  if (grid > 148 * 4) grid = 148 * 4;
   pairs_fwd_kernel<<<(unsigned)grid, NT, smem, stream>>>(A);
   NAIS_COUNT_LAUNCH(1);
   return (int)cudaGetLastError();
