@@ -46,7 +46,10 @@ constexpr int HMETA = 512;      // history items whose id/coords are staged in s
 struct Geo {
   int D, hid, lanes, split;
   int kx;        // D / 8 x k-chunks
-  int nrow;      // rows of a B chunk (2*(hid+2) padded to 16)
+  int hch;       // history items per chunk / MMA step: 2 (hid <= 64) or 1 (hid 96, 128: a cell's hidden columns are split
+                 // between the two warps of a lane quarter and their partial sums exchanged through shared memory)
+  int aux0;      // first S/L row = hch * hid
+  int nrow;      // rows of a B chunk (hch*hid + 2*hch S/L rows, padded; at least aux0 + 16 for the N = 16 aux MMA)
   int tpc;       // candidate tiles per item
   int stages;    // B ring depth
   int a_plane, a_tile;          // bytes
@@ -64,10 +67,13 @@ __host__ inline bool make_geo(const NaisParams& p, int precision, Geo& g) {
   g.lanes = p.dist_mode == NAIS_DIST_LATLON ? 2 : 0;
   g.split = precision == NAIS_PREC_TC_SPLIT;
   if (p.dist_mode == NAIS_DIST_KM) return false;
-  if (g.D % 16 || g.D < 16 || g.D > 64 || g.hid % 16 || g.hid < 16 || g.hid > 64) return false;
+  if (g.D % 16 || g.D < 16 || g.D > 64 || g.hid % 16 || g.hid < 16 || g.hid > 128) return false;
+  g.hch = g.hid <= 64 ? 2 : 1;
+  if (g.hch == 1 && g.hid % 32) return false;
   g.kx = g.D / 8;
-  g.nrow = pad16(2 * g.hid + 4);
-  if (g.nrow < 2 * g.hid + 16) g.nrow = 2 * g.hid + 16;
+  g.aux0 = g.hch * g.hid;
+  g.nrow = pad16(g.aux0 + 2 * g.hch);
+  if (g.nrow < g.aux0 + 16) g.nrow = g.aux0 + 16;
   if (g.nrow > ACC_STRIDE) return false;
   g.a_plane = g.kx * TM * 16;
   g.a_tile = 2 * g.a_plane;
@@ -77,7 +83,7 @@ __host__ inline bool make_geo(const NaisParams& p, int precision, Geo& g) {
   g.tpc = TPC;
   g.stages = g.split ? 2 : 3;
   // smem: A tiles | B stages | A_ext (hi,lo) x NBUF | zero | keys | comb | barriers
-  g.smem_bytes = g.tpc * g.a_tile + g.stages * g.b_chunk + NBUF * 2 * TM * 16 + 4096 + SORTN * 8 + 9 * g.tpc * TM * 4 + 3 * HMETA * 4 + 256 + 128;
+  g.smem_bytes = g.tpc * g.a_tile + g.stages * g.b_chunk + NBUF * 2 * TM * 16 + 4096 + SORTN * 8 + 9 * g.tpc * TM * 4 + 3 * HMETA * 4 + 4 * TM * 4 + 256 + 128;
   return g.smem_bytes <= 227 * 1024;
 }
 
@@ -87,8 +93,9 @@ struct Scales {
   int npos;
   float omega0, omega1, omegab, pad;
 };
-// workspace header: [0,64) maxes (uint bits) | [64, 128) Scales | [128, 128+4*hid) perm | ck[hid] | u[D]
+// workspace header: [0,64) maxes (uint bits) | [64,128) Scales | perm[128] int | ck[128] float | u[128] float
 constexpr int HDR_BYTES = 4096;
+constexpr int HDR_PERM = 128, HDR_CK = HDR_PERM + 128 * 4, HDR_U = HDR_CK + 128 * 4;
 
 __global__ void absmax_kernel(const float* __restrict__ x, size_t n, unsigned* out) {
   float m = 0.f;
@@ -107,9 +114,9 @@ __global__ void scales_kernel(NaisParams p, unsigned char* hdr) {
   const int lanes = p.dist_mode == NAIS_DIST_LATLON ? 2 : 0, ldw = D + lanes;
   const unsigned* mx = reinterpret_cast<const unsigned*>(hdr);
   Scales* sc = reinterpret_cast<Scales*>(hdr + 64);
-  int* perm = reinterpret_cast<int*>(hdr + 128);
-  float* ck = reinterpret_cast<float*>(hdr + 128 + 4 * 64);
-  float* u = reinterpret_cast<float*>(hdr + 128 + 8 * 64);
+  int* perm = reinterpret_cast<int*>(hdr + HDR_PERM);
+  float* ck = reinterpret_cast<float*>(hdr + HDR_CK);
+  float* u = reinterpret_cast<float*>(hdr + HDR_U);
   __shared__ float red[8];
   __shared__ int s_npos;
   if (threadIdx.x == 0) {
@@ -211,26 +218,30 @@ __global__ void pack_candidates_kernel(NaisParams p, NaisCatalog cat, int64_t po
   }
 }
 
-__device__ __forceinline__ int64_t chunk_base(const int64_t* offsets, int u) { return (offsets[u] + u) >> 1; }
+// first chunk slot of user u: users get ceil(H/hch) consecutive slots (hch = 2: (offsets[u] + u) / 2 never overlaps)
+__device__ __forceinline__ int64_t chunk_base(const int64_t* offsets, int u, int hch) {
+  return hch == 2 ? (offsets[u] + u) >> 1 : offsets[u];
+}
 
 // User operand: grid (chunk slot, user).  One thread = (row n, k-chunk c) -> 8 fp16 (hi) + 8 fp16 (lo).
 __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g, const unsigned char* hdr, unsigned char* Bimg,
                                   int max_chunks) {
   const NaisBranch& br = p.branch[0];
   const Scales* sc = reinterpret_cast<const Scales*>(hdr + 64);
-  const int* perm = reinterpret_cast<const int*>(hdr + 128);
-  const float* ck = reinterpret_cast<const float*>(hdr + 128 + 4 * 64);
-  const float* uu = reinterpret_cast<const float*>(hdr + 128 + 8 * 64);
+  const int* perm = reinterpret_cast<const int*>(hdr + HDR_PERM);
+  const float* ck = reinterpret_cast<const float*>(hdr + HDR_CK);
+  const float* uu = reinterpret_cast<const float*>(hdr + HDR_U);
   const int u = blockIdx.y;
   const int64_t hb = users.offsets[u];
   const int H = (int)(users.offsets[u + 1] - hb);
-  const int nchunks = (H + 1) >> 1;
+  const int hch = g.hch, aux0 = g.aux0;
+  const int nchunks = (H + hch - 1) / hch;
   const int D = g.D, hid = g.hid, ldw = D + g.lanes;
   __shared__ float q[2][64];
   for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) {
-      const int hs = i / D, d = i - hs * D, h = 2 * chunk + hs;
+    for (int i = threadIdx.x; i < hch * D; i += blockDim.x) {
+      const int hs = i / D, d = i - hs * D, h = hch * chunk + hs;
       float v = 0.f;
       if (h < H) {
         const int64_t e = hb + h;
@@ -240,22 +251,22 @@ __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g, const un
       q[hs][d] = v;
     }
     __syncthreads();
-    unsigned char* cb = Bimg + (size_t)(chunk_base(users.offsets, u) - chunk_base(users.offsets, 0) + chunk) * g.b_chunk;
+    unsigned char* cb = Bimg + (size_t)(chunk_base(users.offsets, u, hch) - chunk_base(users.offsets, 0, hch) + chunk) * g.b_chunk;
     for (int i = threadIdx.x; i < g.nrow * (g.kx + 1); i += blockDim.x) {
       const int c = i / g.nrow, n = i - c * g.nrow;
       float v[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = 0.f;
       int hs = -1, kind = -1, k = 0;  // kind 0 main, 1 S, 2 L
-      if (n < 2 * hid) {
+      if (n < aux0) {
         hs = n / hid;
         kind = 0;
         k = perm[n - hs * hid];
-      } else if (n < 2 * hid + 4) {
-        hs = (n - 2 * hid) >> 1;
-        kind = 1 + ((n - 2 * hid) & 1);
+      } else if (n < aux0 + 2 * hch) {
+        hs = (n - aux0) >> 1;
+        kind = 1 + ((n - aux0) & 1);
       }
-      if (kind >= 0 && 2 * chunk + hs < H) {
+      if (kind >= 0 && hch * chunk + hs < H) {
         if (c < g.kx) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -285,8 +296,8 @@ __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g, const un
       *reinterpret_cast<uint4*>(cb + ((size_t)c * g.nrow + n) * 16) = *reinterpret_cast<uint4*>(hi);
       if (g.split) {
         *reinterpret_cast<uint4*>(cb + g.b_hi + ((size_t)c * g.nrow + n) * 16) = *reinterpret_cast<uint4*>(lo);
-      } else if (n >= 2 * hid && n < 2 * hid + 16) {
-        *reinterpret_cast<uint4*>(cb + g.b_hi + ((size_t)c * 16 + (n - 2 * hid)) * 16) = *reinterpret_cast<uint4*>(lo);
+      } else if (n >= aux0 && n < aux0 + 16) {
+        *reinterpret_cast<uint4*>(cb + g.b_hi + ((size_t)c * 16 + (n - aux0)) * 16) = *reinterpret_cast<uint4*>(lo);
       }
     }
   }
@@ -322,7 +333,8 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
   int* hm_id = reinterpret_cast<int*>(comb + 9 * g.tpc * TM);                    // [HMETA]
   float* hm_la = reinterpret_cast<float*>(hm_id + HMETA);
   float* hm_lo = hm_la + HMETA;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(hm_lo + HMETA);
+  float* xch = hm_lo + HMETA;                                                   // [2][2][TM] partner-warp exchange (hch = 1)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 4 * TM);
   uint64_t* a_full = bars + 0;
   uint64_t* a_empty = bars + 1;
   uint64_t* b_full = bars + 2;                 // [MAX_STAGES]
@@ -368,7 +380,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
   const uint32_t tmem = *tslot;
 
   const int tpc = g.tpc;
-  const int64_t cb0 = chunk_base(A.users.offsets, 0);
+  const int64_t cb0 = chunk_base(A.users.offsets, 0, g.hch);
 
   if (warp == EPI_WARPS + 1) {
     // =================================================== bulk-copy producer ========================================
@@ -378,8 +390,8 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x, ++it) {
         const int u = (int)(item / A.groups), grp = (int)(item % A.groups);
         const int H = __shfl_sync(0xffffffffu, (int)(A.users.offsets[u + 1] - A.users.offsets[u]), 0);
-        const int64_t cbu = __shfl_sync(0xffffffffu, chunk_base(A.users.offsets, u) - cb0, 0);
-        const int nchunks = (H + 1) >> 1;
+        const int64_t cbu = __shfl_sync(0xffffffffu, chunk_base(A.users.offsets, u, g.hch) - cb0, 0);
+        const int nchunks = (H + g.hch - 1) / g.hch;
         mbar_wait(a_empty, (it & 1) ^ 1);
         if (elect_one()) {
           mbar_expect_tx(a_full, (uint32_t)(tpc * g.a_tile));
@@ -429,7 +441,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
         B_lo0 = lo_of(blo0, b_lbo);
         Be_lo0 = lo_of(blo0 + g.kx * b_lbo, zaddr - (blo0 + g.kx * b_lbo));
       } else {
-        const uint32_t bha = sb0 + 2 * g.hid * 16;
+        const uint32_t bha = sb0 + g.aux0 * 16;
         Ba_hi0 = lo_of(bha, b_lbo);                                               // S/L rows of the hi plane
         Bae_hi0 = lo_of(bha + g.kx * b_lbo, zaddr - (bha + g.kx * b_lbo));
         Ba_lo0 = lo_of(blo0, l_lbo);                                              // S/L rows, lo image (16 rows)
@@ -441,7 +453,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x, ++it) {
         const int u = (int)(item / A.groups);
         const int H = __shfl_sync(0xffffffffu, (int)(A.users.offsets[u + 1] - A.users.offsets[u]), 0);
-        const int nchunks = (H + 1) >> 1;
+        const int nchunks = (H + g.hch - 1) / g.hch;
         mbar_wait(a_full, it & 1);
         for (int c = 0; c < nchunks; ++c, ++bstep) {
           mbar_wait(&b_full[st], stph);
@@ -469,7 +481,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
               mma_f16(d_t, mk(el), mk(beh), idN, 1);
             } else {
               // S/L rows only (N = 16 at column 2*hid): A_hi x B_lo(aux rows) ; A_lo x B_hi(aux rows)
-              const uint32_t d_aux = d_t + 2 * g.hid;
+              const uint32_t d_aux = d_t + g.aux0;
               for (int s = 0; s < ksteps; ++s) mma_f16(d_aux, mk(ah + s * a_step), mk(bal + s * l_step), id16, 1);
               mma_f16(d_aux, mk(eh), mk(bael), id16, 1);
               for (int s = 0; s < ksteps; ++s) mma_f16(d_aux, mk(al + s * a_step), mk(bah + s * b_step), id16, 1);
@@ -507,7 +519,10 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
     const float w10 = g.lanes ? __ldg(A.p.dist_w + 2) : 0.f, w11 = g.lanes ? __ldg(A.p.dist_w + 3) : 0.f;
     const float bd0 = g.lanes ? __ldg(A.p.dist_b + 0) : 0.f, bd1 = g.lanes ? __ldg(A.p.dist_b + 1) : 0.f;
     const float dscale = A.p.dist_scale, beta = A.p.beta;
-    const int npos = sc.npos, hid = g.hid;
+    const int npos = sc.npos, hid = g.hid, hch = g.hch;
+    const int ncols = hch == 2 ? hid : hid / 2;   // accumulator columns this thread sums per step
+    const int col0 = hs * ncols;                  // hch = 2: slot hs's hidden units; hch = 1: this warp's half of them
+    const int kidx0 = hch == 2 ? 0 : col0;        // hidden-unit index of column col0 (sign classification)
     uint32_t n0 = 0;  // global index of the current item's first step (same sequence as the MMA warp)
     uint32_t phbits = 0;  // phase parity of this group's acc_full barrier, one bit per buffer
 
@@ -515,7 +530,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       const int u = (int)(item / A.groups), grp = (int)(item % A.groups);
       const int64_t hb = A.users.offsets[u];
       const int H = (int)(A.users.offsets[u + 1] - hb);
-      const int nchunks = (H + 1) >> 1;
+      const int nchunks = (H + hch - 1) / hch;
       const int nsteps = nchunks * TPC;
       // stage this user's history ids / coords (previous item's readers are past their last epi_bar)
       epi_bar();
@@ -543,9 +558,9 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       auto produce = [&](int m) {
         const int pc = m / TPC, pt = m - pc * TPC;
         const uint32_t pbuf = (n0 + (uint32_t)m) % NBUF;
-        const int h = 2 * pc + hs;
+        const int h = hch == 2 ? 2 * pc + hs : pc;
         float g0 = 0.f, g1 = 0.f;
-        if (g.lanes && h < H) {
+        if (g.lanes && h < H && (hch == 2 || hs == 0)) {
           float hla, hlo;
           if (h < HMETA) {
             hla = hm_la[h];
@@ -564,9 +579,11 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
         const __half2 hi2 = __floats2half2_rn(g0, g1);
         const float2 hif = __half22float2(hi2);
         const __half2 lo2 = __floats2half2_rn(g0 - hif.x, g1 - hif.y);
-        unsigned char* eb = sE + (size_t)pbuf * 2 * TM * 16 + r * 16 + hs * 4;
-        *reinterpret_cast<__half2*>(eb) = hi2;
-        *reinterpret_cast<__half2*>(eb + TM * 16) = lo2;
+        if (hch == 2 || hs == 0) {
+          unsigned char* eb = sE + (size_t)pbuf * 2 * TM * 16 + r * 16 + hs * 4;
+          *reinterpret_cast<__half2*>(eb) = hi2;
+          *reinterpret_cast<__half2*>(eb + TM * 16) = lo2;
+        }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&e_full[pbuf]);
@@ -581,7 +598,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
         const uint32_t n = n0 + (uint32_t)ls;
         const uint32_t buf = n % NBUF;
         const int c = ls / TPC, t = ls - c * TPC;
-        const int h = 2 * c + hs;
+        const int h = hch == 2 ? 2 * c + hs : c;
         int hist_id = -1;
         if (h < H) hist_id = h < HMETA ? hm_id[h] : __ldg(A.users.items + hb + h);
         mbar_wait(&acc_full[egrp * NBUF + buf], (phbits >> buf) & 1u);
@@ -592,18 +609,18 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
         // ---- TMEM -> registers, 32 columns at a time.  Loads and their wait are kept back to back: the destination
         // registers are written asynchronously, so no other code may sit between a tcgen05.ld and its wait::ld (the
         // other epilogue group hides the latency instead).
-        const uint32_t t_main = tmem + lane_addr + buf * ACC_STRIDE + hs * hid;
+        const uint32_t t_main = tmem + lane_addr + buf * ACC_STRIDE + col0;
         uint32_t aux[2], v[32];
         float accp = 0.f, accn = 0.f;
-        tmem_ld2(tmem + lane_addr + buf * ACC_STRIDE + 2 * hid + 2 * hs, aux);
-        if (hid >= 32) tmem_ld32(t_main, v);
+        tmem_ld2(tmem + lane_addr + buf * ACC_STRIDE + g.aux0 + (hch == 2 ? 2 * hs : 0), aux);
+        if (ncols >= 32) tmem_ld32(t_main, v);
         else tmem_ld16(t_main, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
         tmem_wait_ld();
         auto absum = [&](int c0, int cnt) {  // columns [c0, c0+cnt) of this thread's slice are in v[0..cnt)
 #pragma unroll
           for (int g16 = 0; g16 < 32; g16 += 16) {
             if (g16 < cnt) {
-              const int cc = c0 + g16;
+              const int cc = kidx0 + c0 + g16;
               if (cc + 16 <= npos || cc >= npos) {
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
@@ -627,19 +644,27 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
             }
           }
         };
-        absum(0, hid >= 32 ? 32 : 16);
-        if (hid > 32) {
-          if (hid >= 64) tmem_ld32(t_main + 32, v);
+        absum(0, ncols >= 32 ? 32 : 16);
+        if (ncols > 32) {
+          if (ncols >= 64) tmem_ld32(t_main + 32, v);
           else tmem_ld16(t_main + 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
           tmem_wait_ld();
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
-        if (hid > 32) absum(32, hid >= 64 ? 32 : 16);
+        if (ncols > 32) absum(32, ncols >= 64 ? 32 : 16);
+        float asum = accp - accn;
+        if (hch == 1) {
+          // the other half of this cell's hidden units was summed by the partner warp (same lane quarter)
+          float* slot = xch + ((ls & 1) * 2 + egrp) * TM + r;
+          if (hs == 1) *slot = asum;
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + egrp * 4 + qd) : "memory");
+          if (hs == 0) asum += *slot;
+        }
         const float S = __uint_as_float(aux[0]) * sc.inv_s;
-        const float a = (__uint_as_float(aux[1]) + (accp - accn)) * sc.inv_sigma;
-        if (h < H) {
+        const float a = (__uint_as_float(aux[1]) + asum) * sc.inv_sigma;
+        if (h < H && (hch == 2 || hs == 0)) {
           const int64_t j = t == 0 ? jid[0] : (t == 1 ? jid[1] : jid[2]);
           if ((int64_t)hist_id != j) {
             const float e = __expf(a);
@@ -736,7 +761,7 @@ static bool tc_layout(const NaisParams& p, int n_users, int64_t nnz, int64_t poi
   L.groups = (int)((tiles + g.tpc - 1) / g.tpc);
   if (L.groups < 1) L.groups = 1;
   L.n_tiles_pad = L.groups * g.tpc;
-  L.max_chunks = (nnz + n_users) / 2 + 2;
+  L.max_chunks = (g.hch == 2 ? (nnz + n_users) / 2 : nnz) + 2;
   size_t o = 0;
   L.hdr = o;
   o += tc::HDR_BYTES;

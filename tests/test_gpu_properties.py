@@ -164,3 +164,26 @@ def test_long_history_beyond_the_smem_staging_window(H):
     for prec in ("fp32", "tc_split"):
         got = ops.fullrank_scores("region_distance", 0.5, m._params(), m._catalog, users, precision=prec).cpu().numpy()[0]
         assert util.cond_err(got, ref, scale) < util.TOL, prec
+
+
+@pytest.mark.parametrize("D,hid", [(64, 128), (64, 96), (32, 128), (48, 32), (16, 16), (32, 64)])
+@pytest.mark.parametrize("precision", ["tc_split", "tc_fast"])
+def test_tensor_path_shapes(D, hid, precision):
+    """Every (D, hid) tiling of the tensor-core path: two history items per MMA step for hid <= 64, one for hid 96/128
+    (a cell's hidden columns are split between two warps and exchanged through shared memory)."""
+    U, N = 4, 900
+    data = synthetic.make_checkins(U, N, seed=D + hid, hist_len=None, max_hist=50, min_hist=1, median_hist=15)
+    sd = orc.init_state("region_distance", N, D, hid, data.region_num, 1, seed=3, style="trained")
+    m = util.make_model("region_distance", sd, 0.5)
+    m.set_catalog(region=data.region, coords=data.coords)
+    users = m.make_users(data.indptr, data.indices)
+    got = ops.fullrank_scores("region_distance", 0.5, m._params(), m._catalog, users, precision=precision).cpu().numpy()
+    tol = util.TOL if precision == "tc_split" else 5e-4
+    for u in range(U):
+        ref, scale = util.oracle_user_scores(sd, "region_distance", 0.5, data.coords, data.region, data.history(u), np.arange(N))
+        assert util.cond_err(got[u], ref, scale) < tol, (u, util.cond_err(got[u], ref, scale))
+    full = ops.fullrank_topk("region_distance", 0.5, m._params(), m._catalog, users, 20, precision=precision)
+    parts = [ops.fullrank_topk("region_distance", 0.5, m._params(), m._catalog, users, 20, lo, hi, precision=precision)
+             for lo, hi in ((0, 300), (300, 333), (333, N))]
+    ms, mi = ops.topk_merge(torch.stack([p[0] for p in parts], 1), torch.stack([p[1] for p in parts], 1))
+    assert torch.equal(mi, full[1]) and torch.equal(ms, full[0])
