@@ -50,10 +50,14 @@ struct Geo {
                  // between the two warps of a lane quarter and their partial sums exchanged through shared memory)
   int aux0;      // first S/L row = hch * hid
   int nrow;      // rows of a B chunk (hch*hid + 2*hch S/L rows, padded; at least aux0 + 16 for the N = 16 aux MMA)
-  int tpc;       // candidate tiles per item
+  int tpc;       // candidate tiles per item (3, or 2 when the A tiles of D > 64 would not fit)
   int stages;    // B ring depth
+  int kp;        // K-parts per B chunk: 1 (D <= 64: a stage = the whole chunk) or D/32 (a stage = 4 x k-chunks of both
+                 // planes; the last part also carries the ext k-chunk)
+  int kc_part;   // x k-chunks per part
+  int part_bytes, part_last_bytes, stage_bytes;
   int a_plane, a_tile;          // bytes
-  int b_hi, b_lo, b_chunk;      // bytes
+  int b_hi, b_lo, b_chunk;      // bytes (whole chunk, all parts)
   int smem_bytes;
 };
 
@@ -67,7 +71,7 @@ __host__ inline bool make_geo(const NaisParams& p, int precision, Geo& g) {
   g.lanes = p.dist_mode == NAIS_DIST_LATLON ? 2 : 0;
   g.split = precision == NAIS_PREC_TC_SPLIT;
   if (p.dist_mode == NAIS_DIST_KM) return false;
-  if (g.D % 16 || g.D < 16 || g.D > 64 || g.hid % 16 || g.hid < 16 || g.hid > 128) return false;
+  if (g.D % 16 || g.D < 16 || g.D > 128 || (g.D > 64 && g.D % 32) || g.hid % 16 || g.hid < 16 || g.hid > 128) return false;
   g.hch = g.hid <= 64 ? 2 : 1;
   if (g.hch == 1 && g.hid % 32) return false;
   g.kx = g.D / 8;
@@ -80,11 +84,26 @@ __host__ inline bool make_geo(const NaisParams& p, int precision, Geo& g) {
   g.b_hi = (g.kx + 1) * g.nrow * 16;
   g.b_lo = g.split ? g.b_hi : (g.kx + 1) * 16 * 16;
   g.b_chunk = g.b_hi + g.b_lo;
-  g.tpc = TPC;
-  g.stages = g.split ? 2 : 3;
-  // smem: A tiles | B stages | A_ext (hi,lo) x NBUF | zero | keys | comb | barriers
-  g.smem_bytes = g.tpc * g.a_tile + g.stages * g.b_chunk + NBUF * 2 * TM * 16 + 4096 + SORTN * 8 + 9 * g.tpc * TM * 4 + 3 * HMETA * 4 + 4 * TM * 4 + 256 + 128;
-  return g.smem_bytes <= 227 * 1024;
+  if (g.D <= 64) {
+    g.kp = 1;
+    g.kc_part = g.kx;
+    g.part_bytes = g.part_last_bytes = g.stage_bytes = g.b_chunk;
+    g.stages = g.split ? 2 : 3;
+  } else {
+    g.kp = g.D / 32;
+    g.kc_part = 4;
+    const int lo4 = g.split ? 4 * g.nrow * 16 : 4 * 16 * 16, lo5 = g.split ? 5 * g.nrow * 16 : 5 * 16 * 16;
+    g.part_bytes = 4 * g.nrow * 16 + lo4;
+    g.part_last_bytes = g.stage_bytes = 5 * g.nrow * 16 + lo5;
+    g.stages = 3;
+  }
+  // smem: A tiles | B stages | A_ext (hi,lo) x NBUF | zero  (item-end `comb` partials alias A_ext+zero) | keys | hist meta |
+  //       partner exchange | barriers
+  for (g.tpc = TPC; g.tpc >= 2; --g.tpc) {
+    g.smem_bytes = g.tpc * g.a_tile + g.stages * g.stage_bytes + NBUF * 2 * TM * 16 + 4096 + SORTN * 8 + 3 * HMETA * 4 + 4 * TM * 4 + 256 + 128;
+    if (g.smem_bytes <= 227 * 1024) return true;
+  }
+  return false;
 }
 
 // device-side scalars written by tc_scales_kernel
@@ -237,7 +256,7 @@ __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g, const un
   const int hch = g.hch, aux0 = g.aux0;
   const int nchunks = (H + hch - 1) / hch;
   const int D = g.D, hid = g.hid, ldw = D + g.lanes;
-  __shared__ float q[2][64];
+  __shared__ float q[2][128];
   for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
     __syncthreads();
     for (int i = threadIdx.x; i < hch * D; i += blockDim.x) {
@@ -293,11 +312,17 @@ __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g, const un
       __half hi[8], lo[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) split_f16(v[e], hi[e], lo[e]);
-      *reinterpret_cast<uint4*>(cb + ((size_t)c * g.nrow + n) * 16) = *reinterpret_cast<uint4*>(hi);
+      // image = [part][hi plane | lo section][k-chunk in part][row][16 B]; one part = one bulk copy = one smem stage
+      const int part = g.kp == 1 ? 0 : min(c / g.kc_part, g.kp - 1);
+      const int cp = c - part * g.kc_part;                          // k-chunk inside the part
+      const int nkc = g.kc_part + (part == g.kp - 1 ? 1 : 0);      // the last part also holds the ext k-chunk
+      unsigned char* pb = cb + (size_t)part * g.part_bytes;
+      *reinterpret_cast<uint4*>(pb + ((size_t)cp * g.nrow + n) * 16) = *reinterpret_cast<uint4*>(hi);
+      unsigned char* lb = pb + (size_t)nkc * g.nrow * 16;
       if (g.split) {
-        *reinterpret_cast<uint4*>(cb + g.b_hi + ((size_t)c * g.nrow + n) * 16) = *reinterpret_cast<uint4*>(lo);
+        *reinterpret_cast<uint4*>(lb + ((size_t)cp * g.nrow + n) * 16) = *reinterpret_cast<uint4*>(lo);
       } else if (n >= aux0 && n < aux0 + 16) {
-        *reinterpret_cast<uint4*>(cb + g.b_hi + ((size_t)c * 16 + (n - aux0)) * 16) = *reinterpret_cast<uint4*>(lo);
+        *reinterpret_cast<uint4*>(lb + ((size_t)cp * 16 + (n - aux0)) * 16) = *reinterpret_cast<uint4*>(lo);
       }
     }
   }
@@ -326,11 +351,12 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
   const Geo& g = A.g;
   unsigned char* sA = smem;
   unsigned char* sB = sA + g.tpc * g.a_tile;
-  unsigned char* sE = sB + g.stages * g.b_chunk;          // A_ext: [NBUF][hi 2KB | lo 2KB]
+  unsigned char* sE = sB + g.stages * g.stage_bytes;          // A_ext: [NBUF][hi 2KB | lo 2KB]
   unsigned char* sZ = sE + NBUF * 2 * TM * 16;            // 4 KB of zeros (aliased second k-chunk of the ext step)
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(sZ + 4096);  // [SORTN]
-  float* comb = reinterpret_cast<float*>(keys + SORTN);                          // [3][tpc][TM] partials of hslot 1
-  int* hm_id = reinterpret_cast<int*>(comb + 9 * g.tpc * TM);                    // [HMETA]
+  float* comb = reinterpret_cast<float*>(sE);   // [3 partial sets][3 arrays][TPC][TM] = 13.5 KB: ALIASES A_ext + zero (16 KB),
+                                                // only touched between the item-end barriers, then re-initialised
+  int* hm_id = reinterpret_cast<int*>(keys + SORTN);                             // [HMETA]
   float* hm_la = reinterpret_cast<float*>(hm_id + HMETA);
   float* hm_lo = hm_la + HMETA;
   float* xch = hm_lo + HMETA;                                                   // [2][2][TM] partner-warp exchange (hch = 1)
@@ -349,14 +375,13 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
   const Scales sc = *reinterpret_cast<const Scales*>(A.hdr + 64);
 
   // ---- one-time setup ---------------------------------------------------------------------------------------------
-  for (int i = tid; i < 4096 / 4; i += THREADS) reinterpret_cast<uint32_t*>(sZ)[i] = 0u;
-  // A_ext constant part: column 4 = 1.0 * sAe (hi plane), everything else 0
-  for (int i = tid; i < NBUF * 2 * TM * 4; i += THREADS) reinterpret_cast<uint32_t*>(sE)[i] = 0u;
-  __syncthreads();
-  for (int i = tid; i < NBUF * TM; i += THREADS) {
-    const int b = i / TM, r = i - b * TM;
-    reinterpret_cast<__half*>(sE + (size_t)b * 2 * TM * 16 + r * 16)[4] = __float2half(sc.sAe);
-  }
+  // A_ext (3 x hi|lo planes) and the zero region: everything 0 except column 4 of each hi plane = 1.0 * sAe (bias lane)
+  auto init_ext_word = [&](int i) {  // i = 32-bit word index inside [sE, sZ + 4096)
+    const int byte = i * 4, in_buf = byte % (2 * TM * 16);
+    const bool bias = byte < NBUF * 2 * TM * 16 && in_buf < TM * 16 && (in_buf & 15) == 8;  // halves 4,5 of a hi-plane row
+    reinterpret_cast<uint32_t*>(sE)[i] = bias ? (uint32_t)__half_as_ushort(__float2half(sc.sAe)) : 0u;
+  };
+  for (int i = tid; i < (NBUF * 2 * TM * 16 + 4096) / 4; i += THREADS) init_ext_word(i);
   if (tid == 0) {
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
@@ -400,14 +425,17 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
         }
         __syncwarp();
         const unsigned char* src = A.Bimg + (size_t)cbu * g.b_chunk;
-        for (int c = 0; c < nchunks; ++c, ++bstep) {
-          const int st = bstep % g.stages;
-          mbar_wait(&b_empty[st], ((bstep / g.stages) & 1) ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(&b_full[st], (uint32_t)g.b_chunk);
-            bulk_g2s(sB + (size_t)st * g.b_chunk, src + (size_t)c * g.b_chunk, (uint32_t)g.b_chunk, &b_full[st]);
+        for (int c = 0; c < nchunks; ++c) {
+          for (int pp = 0; pp < g.kp; ++pp, ++bstep) {
+            const int st = bstep % g.stages;
+            const uint32_t bytes = (uint32_t)(pp == g.kp - 1 ? g.part_last_bytes : g.part_bytes);
+            mbar_wait(&b_empty[st], ((bstep / g.stages) & 1) ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(&b_full[st], bytes);
+              bulk_g2s(sB + (size_t)st * g.stage_bytes, src + (size_t)c * g.b_chunk + (size_t)pp * g.part_bytes, bytes, &b_full[st]);
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
     }
@@ -419,6 +447,8 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
     // The whole warp runs the (warp-uniform) control flow so descriptors live in uniform registers; only the MMA and
     // commit instructions are predicated on one elected lane (a `if (lane == 0)` region would make ptxas wrap every
     // UTCHMMA in an R2UR waterfall loop, ~130 clk per MMA).
+    // A B chunk arrives in g.kp K-parts (one smem stage each); the tpc accumulators of a chunk stay open across the
+    // parts, the ext K-step and the commit come with the last part.
     {
       const uint32_t idN = idesc_f16(TM, g.nrow), id16 = idesc_f16(TM, 16);
       const uint32_t zaddr = smem_u32(sZ);
@@ -432,74 +462,74 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       const uint32_t A_hi0 = lo_of(sa0, a_lbo), A_lo0 = lo_of(sa0 + g.a_plane, a_lbo), A_d = (uint32_t)g.a_tile >> 4;
       const uint32_t E_hi0 = lo_of(se0, zaddr - se0), E_lo0 = lo_of(se0 + TM * 16, zaddr - se0 - TM * 16);
       const uint32_t E_d = (uint32_t)((2 * TM * 16) >> 4) - ((uint32_t)((2 * TM * 16) >> 4) << 16);  // wraps: LBO shrinks as the start grows
-      const uint32_t bc = (uint32_t)g.b_chunk >> 4;
-      const uint32_t B_d = bc, Bz_d = bc - (bc << 16);  // plain / zero-aliased-LBO descriptors
-      const uint32_t bex = sb0 + g.kx * b_lbo, blo0 = sb0 + g.b_hi;
-      const uint32_t B_hi0 = lo_of(sb0, b_lbo), Be_hi0 = lo_of(bex, zaddr - bex);
-      uint32_t B_lo0 = 0, Be_lo0 = 0, Ba_hi0 = 0, Bae_hi0 = 0, Ba_lo0 = 0, Bae_lo0 = 0;
-      if (g.split) {
-        B_lo0 = lo_of(blo0, b_lbo);
-        Be_lo0 = lo_of(blo0 + g.kx * b_lbo, zaddr - (blo0 + g.kx * b_lbo));
-      } else {
-        const uint32_t bha = sb0 + g.aux0 * 16;
-        Ba_hi0 = lo_of(bha, b_lbo);                                               // S/L rows of the hi plane
-        Bae_hi0 = lo_of(bha + g.kx * b_lbo, zaddr - (bha + g.kx * b_lbo));
-        Ba_lo0 = lo_of(blo0, l_lbo);                                              // S/L rows, lo image (16 rows)
-        Bae_lo0 = lo_of(blo0 + g.kx * l_lbo, zaddr - (blo0 + g.kx * l_lbo));
-      }
-      const int ksteps = g.kx / 2;
+      const uint32_t sbytes = (uint32_t)g.stage_bytes >> 4;
+      const uint32_t B_d = sbytes, Bz_d = sbytes - (sbytes << 16);  // plain / zero-aliased-LBO descriptors, per stage
+      const int kcp = g.kc_part, ks_part = kcp / 2;
       const bool split = g.split != 0;
-      uint32_t it = 0, bstep = 0, n = 0, st = 0, stph = 0, buf = 0, ph = 0;
+      // stage-0 low words.  Inside a stage: hi plane (nkc x k-chunks) then the lo section; nkc = kcp (+1 in the last part)
+      const uint32_t B_hi0 = lo_of(sb0, b_lbo);
+      const uint32_t lo_off_mid = (uint32_t)kcp * b_lbo, lo_off_last = (uint32_t)(kcp + 1) * b_lbo;  // byte offset of the lo section
+      const uint32_t bex = sb0 + kcp * b_lbo;                                                       // ext k-chunk, hi plane (last part)
+      const uint32_t Be_hi0 = lo_of(bex, zaddr - bex);
+      const uint32_t belx = sb0 + lo_off_last + kcp * b_lbo;                                        // ext k-chunk, lo plane (split)
+      const uint32_t Be_lo0 = lo_of(belx, zaddr - belx);
+      const uint32_t bha = sb0 + g.aux0 * 16;                                                       // S/L rows inside the hi plane
+      const uint32_t Ba_hi0 = lo_of(bha, b_lbo), Bae_hi0 = lo_of(bha + kcp * b_lbo, zaddr - (bha + kcp * b_lbo));
+      const uint32_t baelx = sb0 + lo_off_last + kcp * l_lbo;                                       // ext k-chunk of the 16-row lo image
+      const uint32_t Bae_lo0 = lo_of(baelx, zaddr - baelx);
+      uint32_t it = 0, n = 0, st = 0, stph = 0;
       for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x, ++it) {
         const int u = (int)(item / A.groups);
         const int H = __shfl_sync(0xffffffffu, (int)(A.users.offsets[u + 1] - A.users.offsets[u]), 0);
         const int nchunks = (H + g.hch - 1) / g.hch;
         mbar_wait(a_full, it & 1);
-        for (int c = 0; c < nchunks; ++c, ++bstep) {
-          mbar_wait(&b_full[st], stph);
-          const uint32_t bh = B_hi0 + st * B_d, beh = Be_hi0 + st * Bz_d;
-          const uint32_t bl = B_lo0 + st * B_d, bel = Be_lo0 + st * Bz_d;
-          const uint32_t bah = Ba_hi0 + st * B_d, baeh = Bae_hi0 + st * Bz_d;
-          const uint32_t bal = Ba_lo0 + st * B_d, bael = Bae_lo0 + st * Bz_d;
-#pragma unroll
-          for (int t = 0; t < TPC; ++t, ++n) {
-            const uint32_t ah = A_hi0 + t * A_d, al = A_lo0 + t * A_d;
-            const uint32_t eh = E_hi0 + buf * E_d, el = E_lo0 + buf * E_d;
-            const uint32_t d_t = tmem + buf * ACC_STRIDE;
-            mbar_wait(&e_full[buf], ph);
-            mbar_wait(&acc_empty[buf], ph ^ 1);
-            tc_fence_after();
-            if (elect_one()) {
-            // pass 1: A_hi x B_hi over all rows
-            for (int s = 0; s < ksteps; ++s) mma_f16(d_t, mk(ah + s * a_step), mk(bh + s * b_step), idN, s > 0);
-            mma_f16(d_t, mk(eh), mk(beh), idN, 1);
-            if (split) {
-              // pass 2: A_hi x B_lo ; pass 3: A_lo x B_hi
-              for (int s = 0; s < ksteps; ++s) mma_f16(d_t, mk(ah + s * a_step), mk(bl + s * b_step), idN, 1);
-              mma_f16(d_t, mk(eh), mk(bel), idN, 1);
-              for (int s = 0; s < ksteps; ++s) mma_f16(d_t, mk(al + s * a_step), mk(bh + s * b_step), idN, 1);
-              mma_f16(d_t, mk(el), mk(beh), idN, 1);
-            } else {
-              // S/L rows only (N = 16 at column 2*hid): A_hi x B_lo(aux rows) ; A_lo x B_hi(aux rows)
-              const uint32_t d_aux = d_t + g.aux0;
-              for (int s = 0; s < ksteps; ++s) mma_f16(d_aux, mk(ah + s * a_step), mk(bal + s * l_step), id16, 1);
-              mma_f16(d_aux, mk(eh), mk(bael), id16, 1);
-              for (int s = 0; s < ksteps; ++s) mma_f16(d_aux, mk(al + s * a_step), mk(bah + s * b_step), id16, 1);
-              mma_f16(d_aux, mk(el), mk(baeh), id16, 1);
+        for (int c = 0; c < nchunks; ++c, n += (uint32_t)tpc) {
+          for (int pp = 0; pp < g.kp; ++pp) {
+            const bool lastp = pp == g.kp - 1;
+            mbar_wait(&b_full[st], stph);
+            const uint32_t lo_off = lastp ? lo_off_last : lo_off_mid;
+            const uint32_t bh = B_hi0 + st * B_d;                               // hi plane, x k-chunks of this part
+            const uint32_t bl = lo_of(sb0 + lo_off, b_lbo) + st * B_d;          // lo plane (split)
+            const uint32_t bal = lo_of(sb0 + lo_off, l_lbo) + st * B_d;         // 16-row lo image of the S/L rows (fast)
+            const uint32_t bah = Ba_hi0 + st * B_d;
+            const uint32_t beh = Be_hi0 + st * Bz_d, bel = Be_lo0 + st * Bz_d;
+            const uint32_t baeh = Bae_hi0 + st * Bz_d, bael = Bae_lo0 + st * Bz_d;
+            const uint32_t ka = (uint32_t)(pp * ks_part) * a_step;              // this part's first K-step inside the A tile
+            for (int t = 0; t < tpc; ++t) {
+              const uint32_t nn = n + (uint32_t)t, buf = nn % NBUF, ph = (nn / NBUF) & 1u;
+              const uint32_t ah = A_hi0 + t * A_d + ka, al = A_lo0 + t * A_d + ka;
+              const uint32_t eh = E_hi0 + buf * E_d, el = E_lo0 + buf * E_d;
+              const uint32_t d_t = tmem + buf * ACC_STRIDE, d_aux = d_t + g.aux0;
+              if (pp == 0) mbar_wait(&acc_empty[buf], ph ^ 1);
+              if (lastp) mbar_wait(&e_full[buf], ph);
+              tc_fence_after();
+              if (elect_one()) {
+                // pass 1: A_hi x B_hi over all rows
+                for (int s2 = 0; s2 < ks_part; ++s2) mma_f16(d_t, mk(ah + s2 * a_step), mk(bh + s2 * b_step), idN, (pp | s2) != 0);
+                if (lastp) mma_f16(d_t, mk(eh), mk(beh), idN, 1);
+                if (split) {
+                  // pass 2: A_hi x B_lo ; pass 3: A_lo x B_hi
+                  for (int s2 = 0; s2 < ks_part; ++s2) mma_f16(d_t, mk(ah + s2 * a_step), mk(bl + s2 * b_step), idN, 1);
+                  if (lastp) mma_f16(d_t, mk(eh), mk(bel), idN, 1);
+                  for (int s2 = 0; s2 < ks_part; ++s2) mma_f16(d_t, mk(al + s2 * a_step), mk(bh + s2 * b_step), idN, 1);
+                  if (lastp) mma_f16(d_t, mk(el), mk(beh), idN, 1);
+                } else {
+                  // S/L rows only (N = 16 at column aux0): A_hi x B_lo(aux rows) ; A_lo x B_hi(aux rows)
+                  for (int s2 = 0; s2 < ks_part; ++s2) mma_f16(d_aux, mk(ah + s2 * a_step), mk(bal + s2 * l_step), id16, 1);
+                  if (lastp) mma_f16(d_aux, mk(eh), mk(bael), id16, 1);
+                  for (int s2 = 0; s2 < ks_part; ++s2) mma_f16(d_aux, mk(al + s2 * a_step), mk(bah + s2 * b_step), id16, 1);
+                  if (lastp) mma_f16(d_aux, mk(el), mk(baeh), id16, 1);
+                }
+                if (lastp) mma_commit(&acc_full[(c & 1) * NBUF + buf]);
+              }
+              __syncwarp();
             }
-            mma_commit(&acc_full[(c & 1) * NBUF + buf]);
-            }
+            if (elect_one()) mma_commit(&b_empty[st]);
             __syncwarp();
-            if (++buf == NBUF) {
-              buf = 0;
-              ph ^= 1;
+            if (++st == (uint32_t)g.stages) {
+              st = 0;
+              stph ^= 1;
             }
-          }
-          if (elect_one()) mma_commit(&b_empty[st]);
-          __syncwarp();
-          if (++st == (uint32_t)g.stages) {
-            st = 0;
-            stph ^= 1;
           }
         }
         if (elect_one()) mma_commit(a_empty);
@@ -531,7 +561,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       const int64_t hb = A.users.offsets[u];
       const int H = (int)(A.users.offsets[u + 1] - hb);
       const int nchunks = (H + hch - 1) / hch;
-      const int nsteps = nchunks * TPC;
+      const int nsteps = nchunks * tpc;
       // stage this user's history ids / coords (previous item's readers are past their last epi_bar)
       epi_bar();
       for (int i = tid; i < H && i < HMETA; i += EPI_THREADS) {
@@ -545,7 +575,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       bool excl[TPC];
 #pragma unroll
       for (int t = 0; t < TPC; ++t) {
-        jid[t] = A.poi_begin + ((int64_t)grp * TPC + t) * TM + r;
+        jid[t] = t < tpc ? A.poi_begin + ((int64_t)grp * tpc + t) * TM + r : A.poi_end;
         const bool v = jid[t] < A.poi_end;
         clat[t] = (v && g.lanes) ? __ldg(A.cat.coords + 2 * (jid[t] - A.cat.row_base)) : 0.f;
         clon[t] = (v && g.lanes) ? __ldg(A.cat.coords + 2 * (jid[t] - A.cat.row_base) + 1) : 0.f;
@@ -556,7 +586,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       epi_bar();
       // writes the g lanes of local step m into A_ext buffer (n0 + m) % NBUF
       auto produce = [&](int m) {
-        const int pc = m / TPC, pt = m - pc * TPC;
+        const int pc = m / tpc, pt = m - pc * tpc;
         const uint32_t pbuf = (n0 + (uint32_t)m) % NBUF;
         const int h = hch == 2 ? 2 * pc + hs : pc;
         float g0 = 0.f, g1 = 0.f;
@@ -594,10 +624,10 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       if (egrp == 0)
         for (int m = 0; m < NBUF && m < nsteps; ++m) produce(m);
 
-      for (int ls = egrp * TPC; ls < nsteps; ls = (ls % TPC == TPC - 1) ? ls + TPC + 1 : ls + 1) {
+      for (int ls = egrp * tpc; ls < nsteps; ls = (ls % tpc == tpc - 1) ? ls + tpc + 1 : ls + 1) {
         const uint32_t n = n0 + (uint32_t)ls;
         const uint32_t buf = n % NBUF;
-        const int c = ls / TPC, t = ls - c * TPC;
+        const int c = ls / tpc, t = ls - c * tpc;
         const int h = hch == 2 ? 2 * c + hs : c;
         int hist_id = -1;
         if (h < H) hist_id = h < HMETA ? hm_id[h] : __ldg(A.users.items + hb + h);
@@ -681,6 +711,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       n0 += (uint32_t)nsteps;
       // ---- item epilogue: combine the 4 partial states (2 groups x 2 history slots), score, block top-k --------------
       const int part = egrp * 2 + hs;  // partial 0 is the combiner
+      epi_bar();  // every group is past its last step: all MMAs are complete, so A_ext + zero are idle and may hold `comb`
       if (part != 0) {
 #pragma unroll
         for (int t2 = 0; t2 < TPC; ++t2) {
@@ -709,6 +740,9 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
         for (int i = TPC * TM + r; i < SORTN; i += TM) keys[i] = 0ull;
       }
       epi_bar();
+      // `comb` is consumed: restore A_ext / zero for the next item's MMAs (generic writes -> async proxy fence)
+      for (int i = tid; i < (NBUF * 2 * TM * 16 + 4096) / 4; i += EPI_THREADS) init_ext_word(i);
+      fence_proxy_async();
       // bitonic sort (descending) of SORTN keys, one key pair per epilogue thread
       for (int kk = 2; kk <= SORTN; kk <<= 1) {
         for (int jj = kk >> 1; jj > 0; jj >>= 1) {

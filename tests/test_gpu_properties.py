@@ -166,7 +166,8 @@ def test_long_history_beyond_the_smem_staging_window(H):
         assert util.cond_err(got, ref, scale) < util.TOL, prec
 
 
-@pytest.mark.parametrize("D,hid", [(64, 128), (64, 96), (32, 128), (48, 32), (16, 16), (32, 64)])
+@pytest.mark.parametrize("D,hid", [(64, 128), (64, 96), (32, 128), (48, 32), (16, 16), (32, 64), (128, 128), (128, 64), (96, 96),
+                                   (128, 32), (96, 16)])
 @pytest.mark.parametrize("precision", ["tc_split", "tc_fast"])
 def test_tensor_path_shapes(D, hid, precision):
     """Every (D, hid) tiling of the tensor-core path: two history items per MMA step for hid <= 64, one for hid 96/128
