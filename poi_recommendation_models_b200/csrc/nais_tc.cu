@@ -99,11 +99,10 @@ __host__ inline bool make_geo(const NaisParams& p, int precision, Geo& g) {
   }
   // smem: A tiles | B stages | A_ext (hi,lo) x NBUF | zero  (item-end `comb` partials alias A_ext+zero) | keys | hist meta |
   //       partner exchange | barriers
-  for (g.tpc = TPC; g.tpc >= 2; --g.tpc) {
-    g.smem_bytes = g.tpc * g.a_tile + g.stages * g.stage_bytes + NBUF * 2 * TM * 16 + 4096 + SORTN * 8 + 3 * HMETA * 4 + 4 * TM * 4 + 256 + 128;
-    if (g.smem_bytes <= 227 * 1024) return true;
-  }
-  return false;
+  g.tpc = g.kp == 1 ? TPC : 2;  // compile-time constant per kernel instantiation (kSinglePart)
+  g.smem_bytes = g.tpc * g.a_tile + g.stages * g.stage_bytes + NBUF * 2 * TM * 16 + 4096 + SORTN * 8 + 3 * HMETA * 4 + 4 * TM * 4 + 256 + 128 +
+                 (g.kp == 1 ? 9 * TPC * TM * 4 : 0);  // D <= 64 has room for a private `comb`; D > 64 aliases it on A_ext + zero
+  return g.smem_bytes <= 227 * 1024;
 }
 
 // device-side scalars written by tc_scales_kernel
@@ -346,6 +345,8 @@ struct MainArgs {
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
+// kSinglePart: D <= 64, a B stage holds a whole chunk (kp == 1).  kHch: history items per MMA step (2: hid <= 64, 1: hid 96/128).
+template <bool kSinglePart, int kHch>
 __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_constant__ MainArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   const Geo& g = A.g;
@@ -354,9 +355,10 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
   unsigned char* sE = sB + g.stages * g.stage_bytes;          // A_ext: [NBUF][hi 2KB | lo 2KB]
   unsigned char* sZ = sE + NBUF * 2 * TM * 16;            // 4 KB of zeros (aliased second k-chunk of the ext step)
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(sZ + 4096);  // [SORTN]
-  float* comb = reinterpret_cast<float*>(sE);   // [3 partial sets][3 arrays][TPC][TM] = 13.5 KB: ALIASES A_ext + zero (16 KB),
-                                                // only touched between the item-end barriers, then re-initialised
-  int* hm_id = reinterpret_cast<int*>(keys + SORTN);                             // [HMETA]
+  // item-end partial sums [3 partial sets][3 arrays][TPC][TM] = 13.5 KB.  D <= 64: private region.  D > 64 (smem is full):
+  // ALIASES A_ext + zero (16 KB), only touched between the item-end barriers, then re-initialised.
+  float* comb = kSinglePart ? reinterpret_cast<float*>(keys + SORTN) : reinterpret_cast<float*>(sE);
+  int* hm_id = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(keys + SORTN) + (kSinglePart ? 9 * TPC * TM * 4 : 0));  // [HMETA]
   float* hm_la = reinterpret_cast<float*>(hm_id + HMETA);
   float* hm_lo = hm_la + HMETA;
   float* xch = hm_lo + HMETA;                                                   // [2][2][TM] partner-warp exchange (hch = 1)
@@ -404,8 +406,8 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem = *tslot;
 
-  const int tpc = g.tpc;
-  const int64_t cb0 = chunk_base(A.users.offsets, 0, g.hch);
+  constexpr int tpc = kSinglePart ? TPC : 2;  // == g.tpc
+  const int64_t cb0 = chunk_base(A.users.offsets, 0, kHch);
 
   if (warp == EPI_WARPS + 1) {
     // =================================================== bulk-copy producer ========================================
@@ -415,8 +417,8 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x, ++it) {
         const int u = (int)(item / A.groups), grp = (int)(item % A.groups);
         const int H = __shfl_sync(0xffffffffu, (int)(A.users.offsets[u + 1] - A.users.offsets[u]), 0);
-        const int64_t cbu = __shfl_sync(0xffffffffu, chunk_base(A.users.offsets, u, g.hch) - cb0, 0);
-        const int nchunks = (H + g.hch - 1) / g.hch;
+        const int64_t cbu = __shfl_sync(0xffffffffu, chunk_base(A.users.offsets, u, kHch) - cb0, 0);
+        const int nchunks = (H + kHch - 1) / kHch;
         mbar_wait(a_empty, (it & 1) ^ 1);
         if (elect_one()) {
           mbar_expect_tx(a_full, (uint32_t)(tpc * g.a_tile));
@@ -426,9 +428,10 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
         __syncwarp();
         const unsigned char* src = A.Bimg + (size_t)cbu * g.b_chunk;
         for (int c = 0; c < nchunks; ++c) {
-          for (int pp = 0; pp < g.kp; ++pp, ++bstep) {
+          const int kp_t = kSinglePart ? 1 : g.kp;
+          for (int pp = 0; pp < kp_t; ++pp, ++bstep) {
             const int st = bstep % g.stages;
-            const uint32_t bytes = (uint32_t)(pp == g.kp - 1 ? g.part_last_bytes : g.part_bytes);
+            const uint32_t bytes = (uint32_t)(pp == kp_t - 1 ? g.part_last_bytes : g.part_bytes);
             mbar_wait(&b_empty[st], ((bstep / g.stages) & 1) ^ 1);
             if (elect_one()) {
               mbar_expect_tx(&b_full[st], bytes);
@@ -481,11 +484,12 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x, ++it) {
         const int u = (int)(item / A.groups);
         const int H = __shfl_sync(0xffffffffu, (int)(A.users.offsets[u + 1] - A.users.offsets[u]), 0);
-        const int nchunks = (H + g.hch - 1) / g.hch;
+        const int nchunks = (H + kHch - 1) / kHch;
         mbar_wait(a_full, it & 1);
         for (int c = 0; c < nchunks; ++c, n += (uint32_t)tpc) {
-          for (int pp = 0; pp < g.kp; ++pp) {
-            const bool lastp = pp == g.kp - 1;
+          const int kp_m = kSinglePart ? 1 : g.kp;
+          for (int pp = 0; pp < kp_m; ++pp) {
+            const bool lastp = kSinglePart ? true : pp == kp_m - 1;
             mbar_wait(&b_full[st], stph);
             const uint32_t lo_off = lastp ? lo_off_last : lo_off_mid;
             const uint32_t bh = B_hi0 + st * B_d;                               // hi plane, x k-chunks of this part
@@ -495,7 +499,9 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
             const uint32_t beh = Be_hi0 + st * Bz_d, bel = Be_lo0 + st * Bz_d;
             const uint32_t baeh = Bae_hi0 + st * Bz_d, bael = Bae_lo0 + st * Bz_d;
             const uint32_t ka = (uint32_t)(pp * ks_part) * a_step;              // this part's first K-step inside the A tile
-            for (int t = 0; t < tpc; ++t) {
+#pragma unroll
+            for (int t = 0; t < TPC; ++t) {
+              if (t >= tpc) break;
               const uint32_t nn = n + (uint32_t)t, buf = nn % NBUF, ph = (nn / NBUF) & 1u;
               const uint32_t ah = A_hi0 + t * A_d + ka, al = A_lo0 + t * A_d + ka;
               const uint32_t eh = E_hi0 + buf * E_d, el = E_lo0 + buf * E_d;
@@ -549,10 +555,12 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
     const float w10 = g.lanes ? __ldg(A.p.dist_w + 2) : 0.f, w11 = g.lanes ? __ldg(A.p.dist_w + 3) : 0.f;
     const float bd0 = g.lanes ? __ldg(A.p.dist_b + 0) : 0.f, bd1 = g.lanes ? __ldg(A.p.dist_b + 1) : 0.f;
     const float dscale = A.p.dist_scale, beta = A.p.beta;
-    const int npos = sc.npos, hid = g.hid, hch = g.hch;
+    const int npos = sc.npos, hid = g.hid;
+    constexpr int hch = kHch;
     const int ncols = hch == 2 ? hid : hid / 2;   // accumulator columns this thread sums per step
     const int col0 = hs * ncols;                  // hch = 2: slot hs's hidden units; hch = 1: this warp's half of them
     const int kidx0 = hch == 2 ? 0 : col0;        // hidden-unit index of column col0 (sign classification)
+    auto div_tpc = [&](int x) { return x / tpc; };  // tpc is a compile-time constant: mul-shift, not a runtime division
     uint32_t n0 = 0;  // global index of the current item's first step (same sequence as the MMA warp)
     uint32_t phbits = 0;  // phase parity of this group's acc_full barrier, one bit per buffer
 
@@ -586,7 +594,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       epi_bar();
       // writes the g lanes of local step m into A_ext buffer (n0 + m) % NBUF
       auto produce = [&](int m) {
-        const int pc = m / tpc, pt = m - pc * tpc;
+        const int pc = div_tpc(m), pt = m - pc * tpc;
         const uint32_t pbuf = (n0 + (uint32_t)m) % NBUF;
         const int h = hch == 2 ? 2 * pc + hs : pc;
         float g0 = 0.f, g1 = 0.f;
@@ -624,10 +632,11 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       if (egrp == 0)
         for (int m = 0; m < NBUF && m < nsteps; ++m) produce(m);
 
-      for (int ls = egrp * tpc; ls < nsteps; ls = (ls % tpc == tpc - 1) ? ls + tpc + 1 : ls + 1) {
+      // steps of this group's chunks: (c, t) for c = egrp, egrp + 2, ... and t = 0 .. tpc-1
+      for (int c = egrp, t = 0; c < nchunks; (t + 1 == tpc) ? (t = 0, c += 2) : ++t) {
+        const int ls = c * tpc + t;
         const uint32_t n = n0 + (uint32_t)ls;
         const uint32_t buf = n % NBUF;
-        const int c = ls / tpc, t = ls - c * tpc;
         const int h = hch == 2 ? 2 * c + hs : c;
         int hist_id = -1;
         if (h < H) hist_id = h < HMETA ? hm_id[h] : __ldg(A.users.items + hb + h);
@@ -711,7 +720,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       n0 += (uint32_t)nsteps;
       // ---- item epilogue: combine the 4 partial states (2 groups x 2 history slots), score, block top-k --------------
       const int part = egrp * 2 + hs;  // partial 0 is the combiner
-      epi_bar();  // every group is past its last step: all MMAs are complete, so A_ext + zero are idle and may hold `comb`
+      if (!kSinglePart) epi_bar();  // every group is past its last step: all MMAs are complete, A_ext + zero may hold `comb`
       if (part != 0) {
 #pragma unroll
         for (int t2 = 0; t2 < TPC; ++t2) {
@@ -741,8 +750,10 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       }
       epi_bar();
       // `comb` is consumed: restore A_ext / zero for the next item's MMAs (generic writes -> async proxy fence)
-      for (int i = tid; i < (NBUF * 2 * TM * 16 + 4096) / 4; i += EPI_THREADS) init_ext_word(i);
-      fence_proxy_async();
+      if (!kSinglePart) {
+        for (int i = tid; i < (NBUF * 2 * TM * 16 + 4096) / 4; i += EPI_THREADS) init_ext_word(i);
+        fence_proxy_async();
+      }
       // bitonic sort (descending) of SORTN keys, one key pair per epilogue thread
       for (int kk = 2; kk <= SORTN; kk <<= 1) {
         for (int jj = kk >> 1; jj > 0; jj >>= 1) {
@@ -897,12 +908,14 @@ int launch_fullrank_tc(const NaisParams& p, const NaisCatalog& cat, const NaisUs
   A.Bimg = bimg;
   A.part_keys = keys;
   A.all_scores = all_scores;
-  e = cudaFuncSetAttribute(tc::fullrank_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes);
+  void (*kern)(const tc::MainArgs) = g.kp == 1 ? (g.hch == 2 ? tc::fullrank_tc_kernel<true, 2> : tc::fullrank_tc_kernel<true, 1>)
+                                               : (g.hch == 2 ? tc::fullrank_tc_kernel<false, 2> : tc::fullrank_tc_kernel<false, 1>);
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes);
   if (e != cudaSuccess) return (int)e;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = (int)(A.n_items < sms ? A.n_items : sms);
-  tc::fullrank_tc_kernel<<<grid, tc::THREADS, g.smem_bytes, stream>>>(A);
+  kern<<<grid, tc::THREADS, g.smem_bytes, stream>>>(A);
   NAIS_COUNT_LAUNCH(1);
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
