@@ -349,6 +349,8 @@ struct FullrankArgs {
   float* out_score;               // [n_users, k]           (n_splits == 1)
   int32_t* out_id;
   float* all_scores;  // optional [n_users, poi_end - poi_begin]
+  int stage_p;        // 1: candidate vectors staged in smem (embed_size <= 128); 0: re-read from the tables (L1/L2) per history item
+  int hc;             // history rows staged per chunk (HC, smaller when shared memory is tight)
 };
 
 __global__ void __launch_bounds__(NT, 2) fullrank_fp32_kernel(const __grid_constant__ FullrankArgs A) {
@@ -369,11 +371,12 @@ __global__ void __launch_bounds__(NT, 2) fullrank_fp32_kernel(const __grid_const
   for (int i = 0; i < p.n_branch; ++i) Dmax = max(Dmax, p.branch[i].w_poi + p.branch[i].w_reg);
   TileSmem s;
   float* rest = carve_tile(smem, Dmax, s);
-  float* Ps = rest;                                 // [Dmax][TCP] candidate vectors, d-major
-  float* Qs = Ps + (size_t)Dmax * TCP;              // [HC][Dmax]  history vectors of the current chunk
-  int* hid_s = reinterpret_cast<int*>(Qs + HC * Dmax);  // [HC] history item ids
-  float* hco = reinterpret_cast<float*>(hid_s + HC);    // [HC][2] history coords
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(hco + 2 * HC);  // [2*KCAP]
+  const int HCr = A.hc;
+  float* Ps = rest;                                 // [Dmax][TCP] candidate vectors, d-major (only if A.stage_p)
+  float* Qs = Ps + (A.stage_p ? (size_t)Dmax * TCP : 0);  // [HCr][Dmax]  history vectors of the current chunk
+  int* hid_s = reinterpret_cast<int*>(Qs + HCr * Dmax);  // [HCr] history item ids
+  float* hco = reinterpret_cast<float*>(hid_s + HCr);    // [HCr][2] history coords
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(hco + 2 * HCr);  // [2*KCAP]
 
   const int u = blockIdx.x, split = blockIdx.y;
   const int64_t h_begin = A.users.offsets[u];
@@ -403,11 +406,11 @@ __global__ void __launch_bounds__(NT, 2) fullrank_fp32_kernel(const __grid_const
       const int D = br.w_poi + br.w_reg;
       // candidate tile, d-major
       __syncthreads();
-      {
+      const float* pp = jvalid ? br.tgt_poi + (size_t)j * br.w_poi : nullptr;
+      const float* pr = (jvalid && br.w_reg) ? br.tgt_reg + (size_t)__ldg(A.cat.region + jl) * br.w_reg : nullptr;
+      if (A.stage_p) {
         const int d0 = half ? (D >> 1) : 0, d1 = half ? D : (D >> 1);
         if (jvalid) {
-          const float* pp = br.tgt_poi + (size_t)j * br.w_poi;
-          const float* pr = br.w_reg ? br.tgt_reg + (size_t)__ldg(A.cat.region + jl) * br.w_reg : nullptr;
           for (int d = d0; d < d1; ++d)
             Ps[d * TCP + cell] = (d < br.w_poi) ? __ldg(pp + d) : __ldg(pr + d - br.w_poi);
         } else {
@@ -415,8 +418,8 @@ __global__ void __launch_bounds__(NT, 2) fullrank_fp32_kernel(const __grid_const
         }
       }
       float sumE = 0.f, sumES = 0.f;
-      for (int h0 = 0; h0 < H; h0 += HC) {
-        const int hn = min(HC, H - h0);
+      for (int h0 = 0; h0 < H; h0 += HCr) {
+        const int hn = min(HCr, H - h0);
         __syncthreads();
         for (int i = tid; i < hn * D; i += NT) {
           int hh = i / D, d = i - hh * D;
@@ -439,10 +442,19 @@ __global__ void __launch_bounds__(NT, 2) fullrank_fp32_kernel(const __grid_const
             const int d0 = half ? (D >> 1) : 0, d1 = half ? D : (D >> 1);
             const float* q = Qs + hh * Dmax;
             float ssum = 0.f;
-            for (int d = d0; d < d1; ++d) {
-              float x = Ps[d * TCP + cell] * q[d];
-              s.As[d * TCP + cell] = x;
-              ssum += x;
+            if (A.stage_p) {
+              for (int d = d0; d < d1; ++d) {
+                float x = Ps[d * TCP + cell] * q[d];
+                s.As[d * TCP + cell] = x;
+                ssum += x;
+              }
+            } else {  // embed_size > 128: no room for the candidate tile, re-read the table rows (L1/L2 resident)
+              for (int d = d0; d < d1; ++d) {
+                const float pv = !jvalid ? 0.f : ((d < br.w_poi) ? __ldg(pp + d) : __ldg(pr + d - br.w_poi));
+                float x = pv * q[d];
+                s.As[d * TCP + cell] = x;
+                ssum += x;
+              }
             }
             s.sp[half * TC + cell] = ssum;
             if (half == 0 && lanes) {
@@ -564,9 +576,12 @@ int launch_pairs_fwd(const NaisParams& p, const NaisPairs& b, float* score, floa
   return (int)cudaGetLastError();
 }
 
-size_t fullrank_fp32_smem(const NaisParams& p) {
+size_t fullrank_fp32_smem(const NaisParams& p, int& stage_p, int& hc) {
   const int D = max_D(p);
-  return (tile_smem_floats(D) + (size_t)D * TCP + (size_t)HC * D + 3 * HC) * sizeof(float) + 2 * KCAP * sizeof(unsigned long long) + 16;
+  stage_p = D <= 128;
+  hc = D <= 128 ? HC : 8;
+  return (tile_smem_floats(D) + (stage_p ? (size_t)D * TCP : 0) + (size_t)hc * D + 3 * hc) * sizeof(float) +
+         2 * KCAP * sizeof(unsigned long long) + 16;
 }
 
 int choose_splits(int n_users, int64_t range) {
@@ -663,8 +678,8 @@ int launch_fullrank_fp32(const NaisParams& p, const NaisCatalog& cat, const Nais
   A.all_scores = all_scores;
   A.part_keys = reinterpret_cast<unsigned long long*>(ws);
   if (A.n_splits > 1 && ws_bytes < (size_t)users.n_users * A.n_splits * k * sizeof(unsigned long long)) return NAIS_ERR_WORKSPACE;
-  const size_t smem = fullrank_fp32_smem(p);
-  if (smem > 227 * 1024) return NAIS_ERR_SHAPE;  // embed_size > 128: the candidate + pair tiles no longer fit in shared memory
+  const size_t smem = fullrank_fp32_smem(p, A.stage_p, A.hc);
+  if (smem > 227 * 1024) return NAIS_ERR_SHAPE;
   cudaError_t e = cudaFuncSetAttribute(fullrank_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   dim3 grid(users.n_users, A.n_splits);

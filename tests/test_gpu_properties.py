@@ -188,3 +188,18 @@ def test_tensor_path_shapes(D, hid, precision):
              for lo, hi in ((0, 300), (300, 333), (333, N))]
     ms, mi = ops.topk_merge(torch.stack([p[0] for p in parts], 1), torch.stack([p[1] for p in parts], 1))
     assert torch.equal(mi, full[1]) and torch.equal(ms, full[0])
+
+
+@pytest.mark.parametrize("D,hid", [(256, 64), (256, 256), (128, 128), (192, 96)])
+def test_fp32_fullrank_large_dims(D, hid):
+    """embed_size up to 256 through the fused FP32 full-rank kernel (above 128 the candidate tile is not staged in smem)."""
+    U, N = 3, 500
+    data = synthetic.make_checkins(U, N, seed=D, hist_len=None, max_hist=40, min_hist=1, median_hist=12)
+    sd = orc.init_state("region_distance", N, D, hid, data.region_num, 1, seed=3, style="trained")
+    m = util.make_model("region_distance", sd, 0.5)
+    m.set_catalog(region=data.region, coords=data.coords)
+    users = m.make_users(data.indptr, data.indices)
+    got = ops.fullrank_scores("region_distance", 0.5, m._params(), m._catalog, users, precision="fp32").cpu().numpy()
+    for u in range(U):
+        ref, scale = util.oracle_user_scores(sd, "region_distance", 0.5, data.coords, data.region, data.history(u), np.arange(N))
+        assert util.cond_err(got[u], ref, scale) < util.TOL, (u, util.cond_err(got[u], ref, scale))
