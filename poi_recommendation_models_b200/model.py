@@ -106,7 +106,8 @@ class _NAISBase(nn.Module):
             raise RuntimeError("history gathering needs the full catalogue on this device (row_base == 0)")
         reg = cat.region[it] if cat.region is not None else None
         crd = cat.coords[it].contiguous() if cat.coords is not None else None
-        return ops.DeviceUsers(off, it.to(torch.int32), reg, crd, len(indptr) - 1, int(len(indices)))
+        return ops.DeviceUsers(off, it.to(torch.int32), reg, crd, len(indptr) - 1, int(len(indices)),
+                               np.asarray(indptr, dtype=np.int64))
 
     @torch.no_grad()
     def predict_topk(self, users, k: int, exclude_history: bool = True, poi_begin: int = 0,

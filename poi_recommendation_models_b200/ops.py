@@ -228,6 +228,14 @@ class DeviceUsers:
     coords: Optional[torch.Tensor]  # [nnz,2] float32 centred
     n_users: int
     nnz: int
+    host_offsets: Optional[object] = None  # numpy copy of `offsets` (lets predict_topk split huge batches by workspace size)
+
+    def slice(self, u0: int, u1: int) -> "DeviceUsers":
+        """Users [u0, u1) as a new DeviceUsers (offsets rebased); needs `host_offsets`."""
+        ho = self.host_offsets
+        a, b = int(ho[u0]), int(ho[u1])
+        return DeviceUsers((self.offsets[u0:u1 + 1] - a).contiguous(), self.items[a:b], None if self.region is None else self.region[a:b],
+                           None if self.coords is None else self.coords[a:b], u1 - u0, b - a, ho[u0:u1 + 1] - a)
 
 
 def _structs(cat: DeviceCatalog, users: DeviceUsers):
@@ -240,6 +248,9 @@ def _structs(cat: DeviceCatalog, users: DeviceUsers):
     return c, u
 
 
+WORKSPACE_LIMIT_BYTES = 8 << 30  # user batches whose workspace would exceed this are scored in slices
+
+
 def fullrank_topk(variant: str, beta: float, P: Dict[str, torch.Tensor], cat: DeviceCatalog, users: DeviceUsers, k: int,
                   poi_begin: int = 0, poi_end: Optional[int] = None, exclude_history: bool = True,
                   precision: str = "fp32") -> Tuple[torch.Tensor, torch.Tensor]:
@@ -250,11 +261,17 @@ def fullrank_topk(variant: str, beta: float, P: Dict[str, torch.Tensor], cat: De
     with torch.cuda.device(dev):
         p = build_params(variant, P, beta, keep)
         poi_end = p.item_num if poi_end is None else poi_end
-        c, u = _structs(cat, users)
         prec = PRECISIONS[precision]
+        ws_bytes = lib.nais_fullrank_workspace_bytes(C.byref(p), users.n_users, users.nnz, poi_begin, poi_end, k, prec)
+        if ws_bytes > WORKSPACE_LIMIT_BYTES and users.host_offsets is not None and users.n_users > 1:
+            n_slices = min(users.n_users, -(-ws_bytes // WORKSPACE_LIMIT_BYTES))
+            step = -(-users.n_users // n_slices)
+            parts = [fullrank_topk(variant, beta, P, cat, users.slice(u0, min(users.n_users, u0 + step)), k, poi_begin, poi_end,
+                                   exclude_history, precision) for u0 in range(0, users.n_users, step)]
+            return torch.cat([a for a, _ in parts]), torch.cat([b for _, b in parts])
+        c, u = _structs(cat, users)
         out_s = torch.empty(users.n_users, k, device=dev, dtype=torch.float32)
         out_i = torch.empty(users.n_users, k, device=dev, dtype=torch.int32)
-        ws_bytes = lib.nais_fullrank_workspace_bytes(C.byref(p), users.n_users, users.nnz, poi_begin, poi_end, k, prec)
         ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
         _lib.check(lib.nais_fullrank_topk(C.byref(p), C.byref(c), C.byref(u), poi_begin, poi_end, k, int(exclude_history),
                                           prec, out_s.data_ptr(), out_i.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),

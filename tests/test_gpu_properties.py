@@ -203,3 +203,17 @@ def test_fp32_fullrank_large_dims(D, hid):
     for u in range(U):
         ref, scale = util.oracle_user_scores(sd, "region_distance", 0.5, data.coords, data.region, data.history(u), np.arange(N))
         assert util.cond_err(got[u], ref, scale) < util.TOL, (u, util.cond_err(got[u], ref, scale))
+
+
+def test_predict_topk_slices_huge_batches(monkeypatch):
+    """Batches whose workspace would exceed ops.WORKSPACE_LIMIT_BYTES are scored in user slices with identical results."""
+    U, N = 40, 800
+    data = synthetic.make_checkins(U, N, seed=77, hist_len=None, max_hist=40, min_hist=1, median_hist=12)
+    sd = orc.init_state("region_distance", N, 64, 64, data.region_num, 1, seed=3, style="trained")
+    m = util.make_model("region_distance", sd, 0.5)
+    m.set_catalog(region=data.region, coords=data.coords)
+    users = m.make_users(data.indptr, data.indices)
+    full = ops.fullrank_topk("region_distance", 0.5, m._params(), m._catalog, users, 10, precision="tc_split")
+    monkeypatch.setattr(ops, "WORKSPACE_LIMIT_BYTES", 8 << 20)
+    sliced = ops.fullrank_topk("region_distance", 0.5, m._params(), m._catalog, users, 10, precision="tc_split")
+    assert torch.equal(full[0], sliced[0]) and torch.equal(full[1], sliced[1])
