@@ -243,7 +243,7 @@ __device__ __forceinline__ int64_t chunk_base(const int64_t* offsets, int u, int
 
 // User operand: grid (chunk slot, user).  One thread = (row n, k-chunk c) -> 8 fp16 (hi) + 8 fp16 (lo).
 __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g, const unsigned char* hdr, unsigned char* Bimg,
-                                  int max_chunks) {
+                                  int64_t max_chunks) {
   const NaisBranch& br = p.branch[0];
   const Scales* sc = reinterpret_cast<const Scales*>(hdr + 64);
   const int* perm = reinterpret_cast<const int*>(hdr + HDR_PERM);
@@ -269,7 +269,9 @@ __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g, const un
       q[hs][d] = v;
     }
     __syncthreads();
-    unsigned char* cb = Bimg + (size_t)(chunk_base(users.offsets, u, hch) - chunk_base(users.offsets, 0, hch) + chunk) * g.b_chunk;
+    const int64_t slot = chunk_base(users.offsets, u, hch) - chunk_base(users.offsets, 0, hch) + chunk;
+    if (slot >= max_chunks) continue;  // workspace sized with a wrong nnz: never write out of bounds (the main kernel clamps too)
+    unsigned char* cb = Bimg + (size_t)slot * g.b_chunk;
     for (int i = threadIdx.x; i < g.nrow * (g.kx + 1); i += blockDim.x) {
       const int c = i / g.nrow, n = i - c * g.nrow;
       float v[8];
@@ -325,7 +327,14 @@ __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g, const un
       }
     }
   }
-  (void)max_chunks;
+}
+
+// chunks of user u that exist in the operand image (== ceil(H / hch) when the workspace was sized correctly)
+__device__ __forceinline__ int user_chunks(const int64_t* offsets, int u, int hch, int64_t cb0, int64_t max_chunks) {
+  const int H = (int)(offsets[u + 1] - offsets[u]);
+  const int64_t room = max_chunks - (chunk_base(offsets, u, hch) - cb0);
+  const int n = (H + hch - 1) / hch;
+  return (int)(room < n ? (room < 0 ? 0 : room) : n);
 }
 
 struct MainArgs {
@@ -341,6 +350,7 @@ struct MainArgs {
   const unsigned char* Bimg;
   unsigned long long* part_keys;  // [n_users, groups, k]
   float* all_scores;              // optional [n_users, range]
+  int64_t max_chunks;             // chunk slots the operand image holds (users beyond it are truncated, never read out of bounds)
 };
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
@@ -416,9 +426,8 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       uint32_t it = 0, bstep = 0;
       for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x, ++it) {
         const int u = (int)(item / A.groups), grp = (int)(item % A.groups);
-        const int H = __shfl_sync(0xffffffffu, (int)(A.users.offsets[u + 1] - A.users.offsets[u]), 0);
         const int64_t cbu = __shfl_sync(0xffffffffu, chunk_base(A.users.offsets, u, kHch) - cb0, 0);
-        const int nchunks = (H + kHch - 1) / kHch;
+        const int nchunks = __shfl_sync(0xffffffffu, user_chunks(A.users.offsets, u, kHch, cb0, A.max_chunks), 0);
         mbar_wait(a_empty, (it & 1) ^ 1);
         if (elect_one()) {
           mbar_expect_tx(a_full, (uint32_t)(tpc * g.a_tile));
@@ -483,8 +492,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       uint32_t it = 0, n = 0, st = 0, stph = 0;
       for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x, ++it) {
         const int u = (int)(item / A.groups);
-        const int H = __shfl_sync(0xffffffffu, (int)(A.users.offsets[u + 1] - A.users.offsets[u]), 0);
-        const int nchunks = (H + kHch - 1) / kHch;
+        const int nchunks = __shfl_sync(0xffffffffu, user_chunks(A.users.offsets, u, kHch, cb0, A.max_chunks), 0);
         mbar_wait(a_full, it & 1);
         for (int c = 0; c < nchunks; ++c, n += (uint32_t)tpc) {
           const int kp_m = kSinglePart ? 1 : g.kp;
@@ -568,7 +576,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       const int u = (int)(item / A.groups), grp = (int)(item % A.groups);
       const int64_t hb = A.users.offsets[u];
       const int H = (int)(A.users.offsets[u + 1] - hb);
-      const int nchunks = (H + hch - 1) / hch;
+      const int nchunks = user_chunks(A.users.offsets, u, hch, cb0, A.max_chunks);
       const int nsteps = nchunks * tpc;
       // stage this user's history ids / coords (previous item's readers are past their last epi_bar)
       epi_bar();
@@ -889,7 +897,7 @@ int launch_fullrank_tc(const NaisParams& p, const NaisCatalog& cat, const NaisUs
   NAIS_COUNT_LAUNCH(1);
   {
     dim3 grid(64, users.n_users);
-    tc::pack_users_kernel<<<grid, 256, 0, stream>>>(p, users, g, hdr, bimg, (int)max_chunks);
+    tc::pack_users_kernel<<<grid, 256, 0, stream>>>(p, users, g, hdr, bimg, max_chunks);
     NAIS_COUNT_LAUNCH(1);
   }
   tc::MainArgs A;
@@ -908,6 +916,7 @@ int launch_fullrank_tc(const NaisParams& p, const NaisCatalog& cat, const NaisUs
   A.Bimg = bimg;
   A.part_keys = keys;
   A.all_scores = all_scores;
+  A.max_chunks = max_chunks;
   void (*kern)(const tc::MainArgs) = g.kp == 1 ? (g.hch == 2 ? tc::fullrank_tc_kernel<true, 2> : tc::fullrank_tc_kernel<true, 1>)
                                                : (g.hch == 2 ? tc::fullrank_tc_kernel<false, 2> : tc::fullrank_tc_kernel<false, 1>);
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes);
