@@ -559,10 +559,12 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
     const int qd = warp & 3, hs = (warp >> 2) & 1;
     const int r = qd * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-    const float w00 = g.lanes ? __ldg(A.p.dist_w + 0) : 0.f, w01 = g.lanes ? __ldg(A.p.dist_w + 1) : 0.f;
-    const float w10 = g.lanes ? __ldg(A.p.dist_w + 2) : 0.f, w11 = g.lanes ? __ldg(A.p.dist_w + 3) : 0.f;
-    const float bd0 = g.lanes ? __ldg(A.p.dist_b + 0) : 0.f, bd1 = g.lanes ? __ldg(A.p.dist_b + 1) : 0.f;
-    const float dscale = A.p.dist_scale, beta = A.p.beta;
+    // sigmoid(z) = 1 / (1 + 2^(-log2e * z)): -log2e and the input scale (100 / 1000) are folded into the 2x2 layer
+    const float nl2e = -1.4426950408889634f, dsc = A.p.dist_scale * nl2e;
+    const float w00 = g.lanes ? __ldg(A.p.dist_w + 0) * dsc : 0.f, w01 = g.lanes ? __ldg(A.p.dist_w + 1) * dsc : 0.f;
+    const float w10 = g.lanes ? __ldg(A.p.dist_w + 2) * dsc : 0.f, w11 = g.lanes ? __ldg(A.p.dist_w + 3) * dsc : 0.f;
+    const float bd0 = g.lanes ? __ldg(A.p.dist_b + 0) * nl2e : 0.f, bd1 = g.lanes ? __ldg(A.p.dist_b + 1) * nl2e : 0.f;
+    const float beta = A.p.beta;
     const int npos = sc.npos, hid = g.hid;
     constexpr int hch = kHch;
     const int ncols = hch == 2 ? hid : hid / 2;   // accumulator columns this thread sums per step
@@ -617,10 +619,10 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
           }
           const float ct_la = pt == 0 ? clat[0] : (pt == 1 ? clat[1] : clat[2]);
           const float ct_lo = pt == 0 ? clon[0] : (pt == 1 ? clon[1] : clon[2]);
-          const float l0 = fabsf(ct_la - hla) * dscale, l1 = fabsf(ct_lo - hlo) * dscale;
+          const float l0 = fabsf(ct_la - hla), l1 = fabsf(ct_lo - hlo);
           const float z0 = fmaf(l1, w01, fmaf(l0, w00, bd0)), z1 = fmaf(l1, w11, fmaf(l0, w10, bd1));
-          g0 = __fdividef(sc.sAe, 1.f + __expf(-z0));
-          g1 = __fdividef(sc.sAe, 1.f + __expf(-z1));
+          g0 = __fdividef(sc.sAe, 1.f + exp2f(z0));
+          g1 = __fdividef(sc.sAe, 1.f + exp2f(z1));
         }
         const __half2 hi2 = __floats2half2_rn(g0, g1);
         const float2 hif = __half22float2(hi2);
