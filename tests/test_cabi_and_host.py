@@ -137,3 +137,18 @@ def test_shard_ranges_partition_the_catalogue(n, world):
         assert a1 == b0 and a0 <= a1
     for lo, hi in ranges[:-1]:
         assert lo % 128 == 0 or lo == n
+
+
+def test_whole_module_pickle_roundtrip(tmp_path):
+    """run.py:266-268 checkpoints with torch.save(model): the drop-in modules must survive a whole-module pickle."""
+    for name, args in (("NAIS_region_distance_Embedding", (40, 16, 16, 0.5, 5, 1)), ("NAIS_basic", (40, 16, 16, 0.5)),
+                       ("NAIS_region_distance_disentangled_Embedding", (40, 16, 16, 0.5, 5, 1))):
+        m = getattr(M, name)(*args)
+        m.set_catalog(region=np.arange(40) % 5, coords=np.stack([40.5 + np.arange(40) * 1e-3, -74 + np.arange(40) * 1e-3], 1))
+        path = tmp_path / (name + ".pt")
+        torch.save(m, path)
+        m2 = torch.load(path, weights_only=False)
+        assert type(m2).__name__ == name and m2.beta == m.beta and m2.item_num == m.item_num
+        for (k1, v1), (k2, v2) in zip(m.state_dict().items(), m2.state_dict().items()):
+            assert k1 == k2 and torch.equal(v1, v2)
+        assert m2._catalog.n_rows == 40 and torch.equal(m2._catalog.region, m._catalog.region)
