@@ -245,7 +245,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=list(WORKLOADS))
-    ap.add_argument("--precision", default=os.environ.get("NAIS_BENCH_PRECISION", "tc_split"), choices=["fp32", "tc_split", "tc_fast"])
+    ap.add_argument("--precision", default=os.environ.get("NAIS_BENCH_PRECISION", "tc_split"), choices=["fp32", "tc_split", "tc_mix", "tc_fast"])
     ap.add_argument("--users-per-step", type=int, default=0)
     ap.add_argument("--mode", default="eval", choices=["eval", "train"], help="eval = headline full-rank metric; train = C3 BPR fwd+bwd (triples/s)")
     ap.add_argument("--cpu-users", type=int, default=4, help="users in the bounded CPU-baseline sample")
@@ -278,7 +278,7 @@ def main():
         return
 
     U, N, H, D, hid, k = cfg["users"], cfg["pois"], cfg["hist"], cfg["D"], cfg["hid"], cfg["k"]
-    ups = args.users_per_step or max(148, int({"fp32": 296, "tc_split": 2368, "tc_fast": 4736}[args.precision] * min(1.0, 40000 / N)))
+    ups = args.users_per_step or max(148, int({"fp32": 296, "tc_split": 2368, "tc_mix": 2368, "tc_fast": 4736}[args.precision] * min(1.0, 40000 / N)))
     ups = min(ups, U)
     n_batches = min(args.steps + args.warmup, max(1, U // ups))
     # ---- synthetic data + random-init ("trained-like") weights of the named architecture ----------------------------
@@ -366,7 +366,8 @@ def main():
         line = {"metric": "fullrank_eval_users_per_sec", "value": users_per_s, "unit": "users/s",
                 "pair_scores_per_sec": users_per_s * N, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": {"fp32": "f32", "tc_split": "f16x2-split/f32-accum", "tc_fast": "f16/f32-accum"}[args.precision],
+                "dtype": {"fp32": "f32", "tc_split": "f16x2-split/f32-accum", "tc_mix": "f16+e5m2-corrections/f32-accum",
+                          "tc_fast": "f16/f32-accum"}[args.precision],
                 "data": "synthetic",
                 "config": {"workload": f"{args.config}: {cfg['desc']}", "users_per_step": ups, "precision": args.precision,
                            "l2": "flushed between timed steps (256 MiB write)", "weights": "random init, trained-like scale",
@@ -384,10 +385,14 @@ def main():
             # SPLIT 3 passes x (D/16 + 1 ext) MMAs of 128 x nrow x 16; FAST 1 such pass + 2 passes of N = 16 (S/L rows)
             nrow = max((2 * hid + 4 + 15) // 16 * 16, 2 * hid + 16)
             ks = D // 16 + 1
-            per_step = (3 * ks * 2 * 128 * nrow * 16) if args.precision == "tc_split" else (ks * 2 * 128 * nrow * 16 + 2 * ks * 2 * 128 * 16 * 16)
+            # MIX: 1 fp16 pass (incl. ONE ext MMA) + 2 e5m2 passes of D/32 K=32 MMAs, each occupying the pipe like an fp16
+            # K=16 MMA (measured: tests/umma_probe_f8.cu) -> counted as fp16-equivalent pipe FLOPs
+            per_step = {"tc_split": 3 * ks * 2 * 128 * nrow * 16,
+                        "tc_mix": (ks + 2 * (D // 32)) * 2 * 128 * nrow * 16,
+                        "tc_fast": ks * 2 * 128 * nrow * 16 + 2 * ks * 2 * 128 * 16 * 16}[args.precision]
             issued = cells_per_launch / 256 * per_step / (kern_ms / 1000.0) / 1e12
             line["roofline"].update({"issued_tflops": issued, "issued_frac": issued / peak,
-                                     "issued_note": "tensor FLOPs executed incl. fp16 hi/lo split passes, ext K-step and S/L rows"})
+                                     "issued_note": "tensor-pipe FLOPs executed (fp16-equivalent issue slots) incl. split/correction passes, ext K-step and S/L rows"})
         tr = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
         if os.path.isfile(tr) and args.precision == "tc_split":
             with open(tr) as f:

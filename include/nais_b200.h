@@ -45,6 +45,7 @@ extern "C" {
 #define NAIS_PREC_FP32 0     /* FP32 FFMA on CUDA cores (exact path) */
 #define NAIS_PREC_TC_SPLIT 1 /* tcgen05 fp16 MMA, operands split hi+lo (3 MMAs, ~fp32 products), fp32 accumulate in TMEM */
 #define NAIS_PREC_TC_FAST 2  /* tcgen05 fp16 MMA, single pass (11-bit operands), fp32 accumulate in TMEM */
+#define NAIS_PREC_TC_MIX 3   /* tcgen05 fp16 MMA for hi*hi + two e5m2 (kind::f8f6f4) MMAs for the hi*lo, lo*hi corrections */
 
 #define NAIS_ERR_NULL -1      /* required pointer is NULL */
 #define NAIS_ERR_SHAPE -2     /* unsupported / inconsistent dimension */

@@ -22,7 +22,7 @@ size_t fullrank_tc_workspace_bytes(const NaisParams& p, int n_users, int64_t nnz
 int launch_fullrank_tc(const NaisParams& p, const NaisCatalog& cat, const NaisUsers& users, int64_t poi_begin,
                        int64_t poi_end, int k, int exclude, int precision, float* out_score, int32_t* out_id,
                        float* all_scores, void* ws, size_t ws_bytes, cudaStream_t stream);
-bool tc_supported(const NaisParams& p);
+bool tc_supported(const NaisParams& p, int precision);
 }  // namespace nais
 
 namespace nais { unsigned long long g_launches = 0; }
@@ -160,8 +160,8 @@ static int check_fullrank(const NaisParams* p, const NaisCatalog* cat, const Nai
   if (work && need_reg && (!cat->region || !users->region)) return NAIS_ERR_NULL;
   if (work && p->dist_mode != NAIS_DIST_NONE && (!cat->coords || !users->coords)) return NAIS_ERR_NULL;
   if (p->dist_mode == NAIS_DIST_KM && precision != NAIS_PREC_FP32) return NAIS_ERR_MODE;  // fused haversine: FP32 path only
-  if (precision < NAIS_PREC_FP32 || precision > NAIS_PREC_TC_FAST) return NAIS_ERR_MODE;
-  if (precision != NAIS_PREC_FP32 && !tc_supported(*p)) return NAIS_ERR_SHAPE;
+  if (precision < NAIS_PREC_FP32 || precision > NAIS_PREC_TC_MIX) return NAIS_ERR_MODE;
+  if (precision != NAIS_PREC_FP32 && !tc_supported(*p, precision)) return NAIS_ERR_SHAPE;
   return 0;
 }
 

@@ -14,6 +14,12 @@
 //   * fp32-grade products from fp16 tensor cores: every operand is split x = hi + lo (two fp16 planes, power-of-two
 //     pre-scaling), D += A_hi B_hi + A_hi B_lo + A_lo B_hi  (NAIS_PREC_TC_SPLIT).  NAIS_PREC_TC_FAST keeps the three
 //     passes only for the S/L rows (an N=16 MMA at a column offset) and runs the main rows single-pass.
+//     NAIS_PREC_TC_MIX keeps A_hi B_hi in fp16 and issues the two correction products as e5m2 MMAs
+//     (kind::f8f6f4, K = 32 per instruction, same issue time as an fp16 K = 16 MMA): D += A_hi B_hi + e5m2(A_hi) e5m2(B_lo)
+//     + e5m2(A_lo) e5m2(B_hi).  e5m2 has fp16's exponent range, so the byte planes need no extra scaling; the corrections
+//     are ~2^-12 of the product, so their 3-bit significands leave ~3e-5 per term (1e-5 conditioned, tests/ and
+//     examples/precision_emulation.py).  The ext K-step carries its own hi/lo split inside its 16 K slots (one MMA).
+//     9 MMA issue slots per step instead of 15.
 //
 // Warp roles (576 threads, 1 CTA/SM, persistent over work items = (user, 3 candidate tiles)):
 //   warps 0-15 epilogue, two groups of 8 alternating steps: lane quarter = warp%4, history slot = (warp/4)%2;
@@ -21,6 +27,7 @@
 //   warp 16    MMA issuer (one elected lane) + TMEM allocation
 //   warp 17    bulk-copy producer (one elected lane): A tiles per item, B chunks through a ring of stages
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 #include "nais_common.cuh"
 #include "umma.cuh"
@@ -45,6 +52,7 @@ constexpr int HMETA = 512;      // history items whose id/coords are staged in s
 
 struct Geo {
   int D, hid, lanes, split;
+  int mix;       // NAIS_PREC_TC_MIX: lo section of A tiles / B chunks = e5m2(hi) | e5m2(lo) byte planes, two ext k-chunks
   int kx;        // D / 8 x k-chunks
   int hch;       // history items per chunk / MMA step: 2 (hid <= 64) or 1 (hid 96, 128: a cell's hidden columns are split
                  // between the two warps of a lane quarter and their partial sums exchanged through shared memory)
@@ -70,7 +78,9 @@ __host__ inline bool make_geo(const NaisParams& p, int precision, Geo& g) {
   g.hid = p.hid;
   g.lanes = p.dist_mode == NAIS_DIST_LATLON ? 2 : 0;
   g.split = precision == NAIS_PREC_TC_SPLIT;
+  g.mix = precision == NAIS_PREC_TC_MIX;
   if (p.dist_mode == NAIS_DIST_KM) return false;
+  if (g.mix && g.D % 32) return false;  // an e5m2 MMA covers K = 32
   if (g.D % 16 || g.D < 16 || g.D > 128 || (g.D > 64 && g.D % 32) || g.hid % 16 || g.hid < 16 || g.hid > 128) return false;
   g.hch = g.hid <= 64 ? 2 : 1;
   if (g.hch == 1 && g.hid % 32) return false;
@@ -81,20 +91,23 @@ __host__ inline bool make_geo(const NaisParams& p, int precision, Geo& g) {
   if (g.nrow > ACC_STRIDE) return false;
   g.a_plane = g.kx * TM * 16;
   g.a_tile = 2 * g.a_plane;
-  g.b_hi = (g.kx + 1) * g.nrow * 16;
-  g.b_lo = g.split ? g.b_hi : (g.kx + 1) * 16 * 16;
+  // split: hi and lo planes of kx + 1 k-chunks.  mix: hi plane of kx + 2 k-chunks (two ext chunks), lo section = two byte
+  // planes of kx/2 k-chunks (16 e5m2 per 16 B).  Same totals.  fast: lo = a 16-row image of the S/L rows.
+  g.b_hi = (g.kx + 1 + g.mix) * g.nrow * 16;
+  g.b_lo = g.split ? g.b_hi : (g.mix ? g.kx * g.nrow * 16 : (g.kx + 1) * 16 * 16);
   g.b_chunk = g.b_hi + g.b_lo;
   if (g.D <= 64) {
     g.kp = 1;
     g.kc_part = g.kx;
     g.part_bytes = g.part_last_bytes = g.stage_bytes = g.b_chunk;
-    g.stages = g.split ? 2 : 3;
+    g.stages = (g.split || g.mix) ? 2 : 3;
   } else {
     g.kp = g.D / 32;
     g.kc_part = 4;
-    const int lo4 = g.split ? 4 * g.nrow * 16 : 4 * 16 * 16, lo5 = g.split ? 5 * g.nrow * 16 : 5 * 16 * 16;
+    const int lo4 = (g.split || g.mix) ? 4 * g.nrow * 16 : 4 * 16 * 16;
+    const int lo5 = g.split ? 5 * g.nrow * 16 : (g.mix ? lo4 : 5 * 16 * 16);
     g.part_bytes = 4 * g.nrow * 16 + lo4;
-    g.part_last_bytes = g.stage_bytes = 5 * g.nrow * 16 + lo5;
+    g.part_last_bytes = g.stage_bytes = (5 + g.mix) * g.nrow * 16 + lo5;
     g.stages = 3;
   }
   // smem: A tiles | B stages | A_ext (hi,lo) x NBUF | zero  (item-end `comb` partials alias A_ext+zero) | keys | hist meta |
@@ -208,6 +221,17 @@ __global__ void scales_kernel(NaisParams p, unsigned char* hdr) {
   }
 }
 
+// 8 fp16 -> 8 e5m2 bytes (round to nearest even; e5m2 shares fp16's exponent range, so no rescaling)
+__device__ __forceinline__ uint2 pack_e5m2(const __half* h) {
+  unsigned char b[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) b[e] = (unsigned char)__nv_cvt_halfraw_to_fp8(static_cast<__half_raw>(h[e]), __NV_SATFINITE, __NV_E5M2);
+  uint2 r;
+  r.x = b[0] | (b[1] << 8) | (b[2] << 16) | ((unsigned)b[3] << 24);
+  r.y = b[4] | (b[5] << 8) | (b[6] << 16) | ((unsigned)b[7] << 24);
+  return r;
+}
+
 // Candidate tiles: image [tile][plane hi|lo][k-chunk][row][8 x fp16] of p_j * sA.  One thread = (row, k-chunk).
 __global__ void pack_candidates_kernel(NaisParams p, NaisCatalog cat, int64_t poi_begin, int64_t poi_end, Geo g,
                                        const unsigned char* hdr, unsigned char* Pimg) {
@@ -232,7 +256,13 @@ __global__ void pack_candidates_kernel(NaisParams p, NaisCatalog cat, int64_t po
     }
     unsigned char* base = Pimg + (size_t)tile * g.a_tile + ((size_t)c * TM + r) * 16;
     *reinterpret_cast<uint4*>(base) = *reinterpret_cast<uint4*>(hi);
-    *reinterpret_cast<uint4*>(base + g.a_plane) = *reinterpret_cast<uint4*>(lo);
+    if (g.mix) {  // byte planes e5m2(hi) | e5m2(lo): 16 K elements per 16 B, this thread owns half a row of one k-chunk
+      unsigned char* b8 = Pimg + (size_t)tile * g.a_tile + g.a_plane + ((size_t)(c >> 1) * TM + r) * 16 + (c & 1) * 8;
+      *reinterpret_cast<uint2*>(b8) = pack_e5m2(hi);
+      *reinterpret_cast<uint2*>(b8 + g.a_plane / 2) = pack_e5m2(lo);
+    } else {
+      *reinterpret_cast<uint4*>(base + g.a_plane) = *reinterpret_cast<uint4*>(lo);
+    }
   }
 }
 
@@ -296,6 +326,7 @@ __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g, const un
             else if (kind == 1) v[e] = qd * sc->sS;
             else v[e] = uu[d] * qd * sc->sB;
           }
+        } else if (g.mix) {  // handled below (the ext values carry their own hi/lo split inside the two ext k-chunks)
         } else {  // ext chunk: [2*hs + lane] distance lanes, [4] bias
           if (kind == 0) {
             if (g.lanes) {
@@ -316,11 +347,51 @@ __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g, const un
       // image = [part][hi plane | lo section][k-chunk in part][row][16 B]; one part = one bulk copy = one smem stage
       const int part = g.kp == 1 ? 0 : min(c / g.kc_part, g.kp - 1);
       const int cp = c - part * g.kc_part;                          // k-chunk inside the part
-      const int nkc = g.kc_part + (part == g.kp - 1 ? 1 : 0);      // the last part also holds the ext k-chunk
+      const int nkc = g.kc_part + (part == g.kp - 1 ? 1 + g.mix : 0);  // the last part also holds the ext k-chunk(s)
       unsigned char* pb = cb + (size_t)part * g.part_bytes;
-      *reinterpret_cast<uint4*>(pb + ((size_t)cp * g.nrow + n) * 16) = *reinterpret_cast<uint4*>(hi);
       unsigned char* lb = pb + (size_t)nkc * g.nrow * 16;
-      if (g.split) {
+      if (g.mix && c == g.kx) {
+        // ext step of the MIX mode, ONE fp16 MMA over 16 K slots with the split inside (w = lane / bias weights * sBe):
+        //   chunk e0: [2hs+l] = hi(w_l)   [4] = hi(w_b)  [5] = lo(w_b)        A_ext: [2hs+l] = hi(g_l)  [4] = [5] = sAe
+        //   chunk e1: [2hs+l] = hi(w_l)   [4+2hs+l] = lo(w_l)                 A_ext: [2hs+l] = lo(g_l)  [4+2hs+l] = hi(g_l)
+        float w0 = 0.f, w1 = 0.f, wb = 0.f;
+        if (kind == 0 && hch * chunk + hs < H) {
+          if (g.lanes) {
+            w0 = ck[k] * __ldg(br.w1 + (size_t)k * ldw + D) * sc->sBe;
+            w1 = ck[k] * __ldg(br.w1 + (size_t)k * ldw + D + 1) * sc->sBe;
+          }
+          wb = ck[k] * __ldg(br.b1 + k) * sc->sBe;
+        } else if (kind == 2 && hch * chunk + hs < H) {
+          w0 = sc->omega0 * sc->sBe;
+          w1 = sc->omega1 * sc->sBe;
+          wb = sc->omegab * sc->sBe;
+        }
+        __half e0[8], e1[8], h0, l0, h1, l1, hb, lb2;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) e0[e] = e1[e] = __float2half(0.f);
+        split_f16(w0, h0, l0);
+        split_f16(w1, h1, l1);
+        split_f16(wb, hb, lb2);
+        if (hs >= 0) {
+          e0[2 * hs] = h0;
+          e0[2 * hs + 1] = h1;
+          e0[4] = hb;
+          e0[5] = lb2;
+          e1[2 * hs] = h0;
+          e1[2 * hs + 1] = h1;
+          e1[4 + 2 * hs] = l0;
+          e1[5 + 2 * hs] = l1;
+        }
+        *reinterpret_cast<uint4*>(pb + ((size_t)cp * g.nrow + n) * 16) = *reinterpret_cast<uint4*>(e0);
+        *reinterpret_cast<uint4*>(pb + ((size_t)(cp + 1) * g.nrow + n) * 16) = *reinterpret_cast<uint4*>(e1);
+        continue;
+      }
+      *reinterpret_cast<uint4*>(pb + ((size_t)cp * g.nrow + n) * 16) = *reinterpret_cast<uint4*>(hi);
+      if (g.mix) {
+        unsigned char* b8 = lb + ((size_t)(cp >> 1) * g.nrow + n) * 16 + (cp & 1) * 8;
+        *reinterpret_cast<uint2*>(b8) = pack_e5m2(hi);
+        *reinterpret_cast<uint2*>(b8 + (size_t)(g.kc_part / 2) * g.nrow * 16) = pack_e5m2(lo);
+      } else if (g.split) {
         *reinterpret_cast<uint4*>(lb + ((size_t)cp * g.nrow + n) * 16) = *reinterpret_cast<uint4*>(lo);
       } else if (n >= aux0 && n < aux0 + 16) {
         *reinterpret_cast<uint4*>(lb + ((size_t)cp * 16 + (n - aux0)) * 16) = *reinterpret_cast<uint4*>(lo);
@@ -391,7 +462,9 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
   auto init_ext_word = [&](int i) {  // i = 32-bit word index inside [sE, sZ + 4096)
     const int byte = i * 4, in_buf = byte % (2 * TM * 16);
     const bool bias = byte < NBUF * 2 * TM * 16 && in_buf < TM * 16 && (in_buf & 15) == 8;  // halves 4,5 of a hi-plane row
-    reinterpret_cast<uint32_t*>(sE)[i] = bias ? (uint32_t)__half_as_ushort(__float2half(sc.sAe)) : 0u;
+    const uint32_t one = (uint32_t)__half_as_ushort(__float2half(sc.sAe));
+    // split / fast: slot 4 = 1 (bias).  mix: the buffer is [k-chunk 0 | k-chunk 1] and slots 4, 5 of chunk 0 pair with hi / lo of the bias
+    reinterpret_cast<uint32_t*>(sE)[i] = bias ? (g.mix ? (one | (one << 16)) : one) : 0u;
   };
   for (int i = tid; i < (NBUF * 2 * TM * 16 + 4096) / 4; i += THREADS) init_ext_word(i);
   if (tid == 0) {
@@ -462,7 +535,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
     // A B chunk arrives in g.kp K-parts (one smem stage each); the tpc accumulators of a chunk stay open across the
     // parts, the ext K-step and the commit come with the last part.
     {
-      const uint32_t idN = idesc_f16(TM, g.nrow), id16 = idesc_f16(TM, 16);
+      const uint32_t idN = idesc_f16(TM, g.nrow), id16 = idesc_f16(TM, 16), idN8 = idesc_e5m2(TM, g.nrow);
       const uint32_t zaddr = smem_u32(sZ);
       const uint32_t a_lbo = TM * 16, b_lbo = g.nrow * 16, l_lbo = 16 * 16;
       const uint32_t a_step = (2 * a_lbo) >> 4, b_step = (2 * b_lbo) >> 4, l_step = (2 * l_lbo) >> 4;
@@ -477,10 +550,17 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       const uint32_t sbytes = (uint32_t)g.stage_bytes >> 4;
       const uint32_t B_d = sbytes, Bz_d = sbytes - (sbytes << 16);  // plain / zero-aliased-LBO descriptors, per stage
       const int kcp = g.kc_part, ks_part = kcp / 2;
-      const bool split = g.split != 0;
-      // stage-0 low words.  Inside a stage: hi plane (nkc x k-chunks) then the lo section; nkc = kcp (+1 in the last part)
+      const bool split = g.split != 0, mix = g.mix != 0;
+      // stage-0 low words.  Inside a stage: hi plane (nkc x k-chunks) then the lo section; nkc = kcp (+1 or, mix, +2 in the last part)
       const uint32_t B_hi0 = lo_of(sb0, b_lbo);
-      const uint32_t lo_off_mid = (uint32_t)kcp * b_lbo, lo_off_last = (uint32_t)(kcp + 1) * b_lbo;  // byte offset of the lo section
+      const uint32_t lo_off_mid = (uint32_t)kcp * b_lbo, lo_off_last = (uint32_t)(kcp + 1 + g.mix) * b_lbo;  // byte offset of the lo section
+      // mix: e5m2 planes.  A tile = [hi fp16 | e5m2(hi) | e5m2(lo)], a K = 32 step = two 16-byte k-chunks = a_step again;
+      // B lo section = [e5m2(hi) : kcp/2 k-chunks | e5m2(lo) : kcp/2 k-chunks].  The ext step is one fp16 MMA over two real
+      // k-chunks (A_ext buffer = [chunk 0 | chunk 1], B ext chunks kcp, kcp+1 of the hi plane): plain LBOs, no zero alias.
+      const int ks8 = kcp / 4;
+      const uint32_t A8_0 = lo_of(sa0 + g.a_plane, a_lbo), A8l_0 = lo_of(sa0 + g.a_plane + g.a_plane / 2, a_lbo);
+      const uint32_t Em_0 = lo_of(se0, TM * 16), Em_d = (uint32_t)((2 * TM * 16) >> 4);
+      const uint32_t Bem_0 = lo_of(sb0 + kcp * b_lbo, b_lbo);
       const uint32_t bex = sb0 + kcp * b_lbo;                                                       // ext k-chunk, hi plane (last part)
       const uint32_t Be_hi0 = lo_of(bex, zaddr - bex);
       const uint32_t belx = sb0 + lo_off_last + kcp * b_lbo;                                        // ext k-chunk, lo plane (split)
@@ -507,6 +587,9 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
             const uint32_t beh = Be_hi0 + st * Bz_d, bel = Be_lo0 + st * Bz_d;
             const uint32_t baeh = Bae_hi0 + st * Bz_d, bael = Bae_lo0 + st * Bz_d;
             const uint32_t ka = (uint32_t)(pp * ks_part) * a_step;              // this part's first K-step inside the A tile
+            const uint32_t ka8 = (uint32_t)(pp * ks8) * a_step;                 // same inside the e5m2 planes (K = 32 steps)
+            const uint32_t b8h = bl, b8l = bl + (uint32_t)((kcp / 2) * b_lbo >> 4);  // mix: e5m2(hi) plane, e5m2(lo) plane
+            const uint32_t bem = Bem_0 + st * B_d;
 #pragma unroll
             for (int t = 0; t < TPC; ++t) {
               if (t >= tpc) break;
@@ -520,14 +603,21 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
               if (elect_one()) {
                 // pass 1: A_hi x B_hi over all rows
                 for (int s2 = 0; s2 < ks_part; ++s2) mma_f16(d_t, mk(ah + s2 * a_step), mk(bh + s2 * b_step), idN, (pp | s2) != 0);
-                if (lastp) mma_f16(d_t, mk(eh), mk(beh), idN, 1);
-                if (split) {
+                if (mix) {
+                  // ext step with its inner hi/lo split, then the e5m2 corrections: e5m2(A_hi) x e5m2(B_lo) ; e5m2(A_lo) x e5m2(B_hi)
+                  if (lastp) mma_f16(d_t, mk(Em_0 + buf * Em_d), mk(bem), idN, 1);
+                  const uint32_t a8h = A8_0 + t * A_d + ka8, a8l = A8l_0 + t * A_d + ka8;
+                  for (int s8 = 0; s8 < ks8; ++s8) mma_f8(d_t, mk(a8h + s8 * a_step), mk(b8l + s8 * b_step), idN8, 1);
+                  for (int s8 = 0; s8 < ks8; ++s8) mma_f8(d_t, mk(a8l + s8 * a_step), mk(b8h + s8 * b_step), idN8, 1);
+                } else if (split) {
+                  if (lastp) mma_f16(d_t, mk(eh), mk(beh), idN, 1);
                   // pass 2: A_hi x B_lo ; pass 3: A_lo x B_hi
                   for (int s2 = 0; s2 < ks_part; ++s2) mma_f16(d_t, mk(ah + s2 * a_step), mk(bl + s2 * b_step), idN, 1);
                   if (lastp) mma_f16(d_t, mk(eh), mk(bel), idN, 1);
                   for (int s2 = 0; s2 < ks_part; ++s2) mma_f16(d_t, mk(al + s2 * a_step), mk(bh + s2 * b_step), idN, 1);
                   if (lastp) mma_f16(d_t, mk(el), mk(beh), idN, 1);
                 } else {
+                  if (lastp) mma_f16(d_t, mk(eh), mk(beh), idN, 1);
                   // S/L rows only (N = 16 at column aux0): A_hi x B_lo(aux rows) ; A_lo x B_hi(aux rows)
                   for (int s2 = 0; s2 < ks_part; ++s2) mma_f16(d_aux, mk(ah + s2 * a_step), mk(bal + s2 * l_step), id16, 1);
                   if (lastp) mma_f16(d_aux, mk(eh), mk(bael), id16, 1);
@@ -628,9 +718,12 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
         const float2 hif = __half22float2(hi2);
         const __half2 lo2 = __floats2half2_rn(g0 - hif.x, g1 - hif.y);
         if (hch == 2 || hs == 0) {
+          // split / fast: [hi plane | lo plane], slots 2hs, 2hs+1.  mix: [k-chunk 0 | k-chunk 1]: chunk 0 slots 2hs.. = hi,
+          // chunk 1 slots 2hs.. = lo and slots 4+2hs.. = hi again (pairs with the lo weights)
           unsigned char* eb = sE + (size_t)pbuf * 2 * TM * 16 + r * 16 + hs * 4;
           *reinterpret_cast<__half2*>(eb) = hi2;
           *reinterpret_cast<__half2*>(eb + TM * 16) = lo2;
+          if (g.mix) *reinterpret_cast<__half2*>(eb + TM * 16 + 8) = hi2;
         }
         fence_proxy_async();
         __syncwarp();
@@ -832,9 +925,9 @@ static bool tc_layout(const NaisParams& p, int n_users, int64_t nnz, int64_t poi
   return true;
 }
 
-bool tc_supported(const NaisParams& p) {
+bool tc_supported(const NaisParams& p, int precision) {
   tc::Geo g;
-  return tc::make_geo(p, NAIS_PREC_TC_SPLIT, g);
+  return tc::make_geo(p, precision, g);
 }
 
 size_t fullrank_tc_workspace_bytes(const NaisParams& p, int n_users, int64_t nnz, int64_t poi_begin, int64_t poi_end, int k,

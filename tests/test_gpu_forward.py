@@ -99,11 +99,11 @@ def _fullrank_case(variant, U, N, seed, D=64, hid=64, beta=0.5, **kw):
     return data, sd, m
 
 
-PREC_TOL = {"fp32": util.TOL, "tc_split": util.TOL, "tc_fast": 5e-4}  # tc_fast: single-pass fp16 logits (documented)
+PREC_TOL = {"fp32": util.TOL, "tc_split": util.TOL, "tc_mix": util.TOL, "tc_fast": 5e-4}  # tc_fast: single-pass fp16 logits (documented)
 
 
 @pytest.mark.parametrize("variant", ["region_distance", "region", "basic", "distance"])
-@pytest.mark.parametrize("precision", ["fp32", "tc_split", "tc_fast"])
+@pytest.mark.parametrize("precision", ["fp32", "tc_split", "tc_mix", "tc_fast"])
 def test_fullrank_scores_match_oracle(variant, precision):
     U, N, beta = 5, 700, 0.5
     data, sd, m = _fullrank_case(variant, U, N, seed=11, hist_len=None, max_hist=45, min_hist=2, median_hist=12)
@@ -132,7 +132,7 @@ def test_fullrank_disentangled_fused_haversine():
         m.predict_topk(users, 10, precision="tc_split")
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tc_split"])
+@pytest.mark.parametrize("precision", ["fp32", "tc_split", "tc_mix"])
 def test_fullrank_topk_matches_reference_validation_golden(precision):
     z = util.load_golden("validation_rd.npz")
     sd = util.golden_sd(z, "sd.")
@@ -161,7 +161,7 @@ def test_fullrank_topk_matches_reference_validation_golden(precision):
     assert np.array_equal(np.array(res, dtype=np.float64), z["metrics"])
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tc_split", "tc_fast"])
+@pytest.mark.parametrize("precision", ["fp32", "tc_split", "tc_mix", "tc_fast"])
 @pytest.mark.parametrize("U,N,k", [(3, 100, 50), (2, 130, 128), (300, 1000, 20), (1, 5000, 10)])
 def test_fullrank_topk_shapes_and_merge(U, N, k, precision):
     beta = 0.5
