@@ -427,8 +427,13 @@ struct MainArgs {
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 // kSinglePart: D <= 64, a B stage holds a whole chunk (kp == 1).  kHch: history items per MMA step (2: hid <= 64, 1: hid 96/128).
-template <bool kSinglePart, int kHch>
+// kFix: 0 = generic (every shape is a run-time value); 1 / 2 = the D = hid = 64 shape of the headline workload in SPLIT / MIX
+// precision with every tile constant known at compile time: a fully unrolled MMA issue sequence (descriptor = base +
+// immediate; the generic issuer spends ~15 instructions per MMA, which paces the kernel once a step is 9 MMAs) and the
+// specialised epilogue step loop (needs kSinglePart and kHch == 2).
+template <bool kSinglePart, int kHch, int kFix>
 __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_constant__ MainArgs A) {
+  constexpr bool kFastEpi = kFix != 0;
   extern __shared__ __align__(128) unsigned char smem[];
   const Geo& g = A.g;
   unsigned char* sA = smem;
@@ -467,6 +472,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
     reinterpret_cast<uint32_t*>(sE)[i] = bias ? (g.mix ? (one | (one << 16)) : one) : 0u;
   };
   for (int i = tid; i < (NBUF * 2 * TM * 16 + 4096) / 4; i += THREADS) init_ext_word(i);
+  if (kFastEpi && tid < 16) xch[tid] = ((sc.npos & ~15) + tid < sc.npos) ? 1.f : -1.f;
   if (tid == 0) {
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
@@ -534,6 +540,81 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
     // UTCHMMA in an R2UR waterfall loop, ~130 clk per MMA).
     // A B chunk arrives in g.kp K-parts (one smem stage each); the tpc accumulators of a chunk stay open across the
     // parts, the ext K-step and the commit come with the last part.
+    if constexpr (kFix != 0) {
+      // ---- static issuer: D = hid = 64, N = 144, K-steps 4 (fp16) + 1 (ext) [+ 2 + 2 e5m2], stages = 2, buffer == tile ----
+      constexpr bool kMix = kFix == 2;
+      constexpr uint32_t kNrow = 144, kALbo = TM * 16, kBLbo = kNrow * 16;
+      constexpr uint32_t kAStep = (2 * kALbo) >> 4, kBStep = (2 * kBLbo) >> 4;      // one K-step = two 16-byte k-chunks
+      constexpr uint32_t kAPlane = 8 * TM * 16, kATile = (2 * kAPlane) >> 4;        // (16-byte units)
+      constexpr uint32_t kStage = (2 * 9 * kNrow * 16) >> 4;
+      constexpr uint32_t kExtBuf = (2 * TM * 16) >> 4;
+      constexpr uint32_t idN = idesc_f16(TM, kNrow), idN8 = idesc_e5m2(TM, kNrow);
+      const uint32_t zaddr = smem_u32(sZ);
+      const uint32_t hi_word = (uint32_t)(smem_desc(0, 0, 128) >> 32);  // SBO = 128 B, version 1, no swizzle
+      auto lo_of = [](uint32_t addr, uint32_t lbo) { return ((addr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); };
+      auto mk = [&](uint32_t lo) { return ((uint64_t)hi_word << 32) | lo; };
+      const uint32_t sa0 = smem_u32(sA), sb0 = smem_u32(sB), se0 = smem_u32(sE);
+      const uint32_t A_hi = lo_of(sa0, kALbo);
+      const uint32_t A_lo = lo_of(sa0 + kAPlane, kALbo);                    // split: fp16 lo plane ; mix: e5m2(hi) plane
+      const uint32_t A_l8 = lo_of(sa0 + kAPlane + kAPlane / 2, kALbo);      // mix: e5m2(lo) plane
+      // split: ext step = k-chunk [hi | lo plane] + zero-aliased second chunk (LBO shrinks as the start grows)
+      const uint32_t E_hi = lo_of(se0, zaddr - se0), E_lo = lo_of(se0 + TM * 16, zaddr - se0 - TM * 16);
+      constexpr uint32_t kEz = kExtBuf - (kExtBuf << 16), kBz = kStage - (kStage << 16);
+      const uint32_t E_mx = lo_of(se0, TM * 16);                            // mix: [chunk 0 | chunk 1]
+      const uint32_t B_hi = lo_of(sb0, kBLbo);
+      const uint32_t Bx_hi = lo_of(sb0 + 8 * kBLbo, zaddr - (sb0 + 8 * kBLbo));     // split: ext chunk of the hi plane
+      const uint32_t Bx_lo = lo_of(sb0 + 17 * kBLbo, zaddr - (sb0 + 17 * kBLbo));   //        ... of the lo plane (9 + 8)
+      uint32_t it = 0, cc = 0, st = 0, stph = 0;
+      for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x, ++it) {
+        const int u = (int)(item / A.groups);
+        const int nchunks = __shfl_sync(0xffffffffu, user_chunks(A.users.offsets, u, kHch, cb0, A.max_chunks), 0);
+        mbar_wait(a_full, it & 1);
+        for (int c = 0; c < nchunks; ++c, ++cc) {
+          mbar_wait(&b_full[st], stph);
+          const uint32_t cph = cc & 1u;
+          const uint32_t bh = B_hi + st * kStage;
+          const uint32_t bxh = Bx_hi + st * kBz, bxl = Bx_lo + st * kBz;
+          uint64_t* const accf = &acc_full[(c & 1) * NBUF];
+#pragma unroll
+          for (int t = 0; t < TPC; ++t) {
+            const uint32_t d_t = tmem + t * ACC_STRIDE;
+            const uint32_t ah = A_hi + t * kATile, al = A_lo + t * kATile, al8 = A_l8 + t * kATile;
+            mbar_wait(&acc_empty[t], cph ^ 1u);
+            mbar_wait(&e_full[t], cph);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int s2 = 0; s2 < 4; ++s2) mma_f16(d_t, mk(ah + s2 * kAStep), mk(bh + s2 * kBStep), idN, s2 != 0);
+              if constexpr (kMix) {
+                mma_f16(d_t, mk(E_mx + t * kExtBuf), mk(bh + 4 * kBStep), idN, 1);               // ext: hi-plane chunks 8, 9
+                constexpr uint32_t b8h = (10 * kBLbo) >> 4, b8l = (14 * kBLbo) >> 4;              // e5m2(hi) / e5m2(lo) planes
+#pragma unroll
+                for (int s8 = 0; s8 < 2; ++s8) mma_f8(d_t, mk(al + s8 * kAStep), mk(bh + b8l + s8 * kBStep), idN8, 1);
+#pragma unroll
+                for (int s8 = 0; s8 < 2; ++s8) mma_f8(d_t, mk(al8 + s8 * kAStep), mk(bh + b8h + s8 * kBStep), idN8, 1);
+              } else {
+                constexpr uint32_t blo = (9 * kBLbo) >> 4;                                        // lo plane
+                mma_f16(d_t, mk(E_hi + t * kEz), mk(bxh), idN, 1);
+#pragma unroll
+                for (int s2 = 0; s2 < 4; ++s2) mma_f16(d_t, mk(ah + s2 * kAStep), mk(bh + blo + s2 * kBStep), idN, 1);
+                mma_f16(d_t, mk(E_hi + t * kEz), mk(bxl), idN, 1);
+#pragma unroll
+                for (int s2 = 0; s2 < 4; ++s2) mma_f16(d_t, mk(al + s2 * kAStep), mk(bh + s2 * kBStep), idN, 1);
+                mma_f16(d_t, mk(E_lo + t * kEz), mk(bxh), idN, 1);
+              }
+              mma_commit(&accf[t]);
+            }
+            __syncwarp();
+          }
+          if (elect_one()) mma_commit(&b_empty[st]);
+          __syncwarp();
+          st ^= 1u;
+          stph ^= (st == 0);
+        }
+        if (elect_one()) mma_commit(a_empty);
+        __syncwarp();
+      }
+    } else
     {
       const uint32_t idN = idesc_f16(TM, g.nrow), id16 = idesc_f16(TM, 16), idN8 = idesc_e5m2(TM, g.nrow);
       const uint32_t zaddr = smem_u32(sZ);
@@ -663,6 +744,12 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
     auto div_tpc = [&](int x) { return x / tpc; };  // tpc is a compile-time constant: mul-shift, not a runtime division
     uint32_t n0 = 0;  // global index of the current item's first step (same sequence as the MMA warp)
     uint32_t phbits = 0;  // phase parity of this group's acc_full barrier, one bit per buffer
+    // fast epilogue: one parity bit (every buffer completes once per own chunk), folded constants, sign split of the columns
+    uint32_t fph = 0;
+    const float c_a2 = sc.inv_sigma * 1.4426950408889634f, inv_sAe = 1.f / sc.sAe;
+    const float bd0s = bd0 - log2f(sc.sAe), bd1s = bd1 - log2f(sc.sAe);
+    const int nposb = npos >> 4, nposm = npos & 15;
+    const float* sgn_mixed = xch;  // [16] +-1 of the one 16-column block that holds both signs (xch is unused when hch == 2)
 
     for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x) {
       const int u = (int)(item / A.groups), grp = (int)(item % A.groups);
@@ -692,135 +779,257 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
         excl[t] = false;
       }
       epi_bar();
-      // writes the g lanes of local step m into A_ext buffer (n0 + m) % NBUF
-      auto produce = [&](int m) {
-        const int pc = div_tpc(m), pt = m - pc * tpc;
-        const uint32_t pbuf = (n0 + (uint32_t)m) % NBUF;
-        const int h = hch == 2 ? 2 * pc + hs : pc;
-        float g0 = 0.f, g1 = 0.f;
-        if (g.lanes && h < H && (hch == 2 || hs == 0)) {
-          float hla, hlo;
-          if (h < HMETA) {
-            hla = hm_la[h];
-            hlo = hm_lo[h];
-          } else {
-            hla = __ldg(A.users.coords + 2 * (hb + h));
-            hlo = __ldg(A.users.coords + 2 * (hb + h) + 1);
+      if constexpr (kFastEpi) {
+        // ---- specialised step loop: hid == 64, two history items per step, tpc == NBUF == 3 -----------------------------
+        // Every step index is then (chunk, t) with buffer == t, so the t loop unrolls with compile-time TMEM / A_ext
+        // addresses, the per-chunk history lookups leave the step body, and this group's acc_full parity is one bit that
+        // flips once per own chunk.  ~150 issue slots per warp-step instead of ~340 (the MIX mode is epilogue-issue bound).
+        const unsigned char* ebase = sE + r * 16 + hs * 4;
+        // A_ext of (chunk pc, tile t): 2 sigmoids -> hi/lo halves.  sAe / (1 + 2^z) = 1 / (1/sAe + 2^(z - log2 sAe))
+        auto produce_f = [&](int t, bool on, float hla, float hlo, float cla, float clo) {
+          float g0 = 0.f, g1 = 0.f;
+          if (on) {
+            const float l0 = fabsf(cla - hla), l1 = fabsf(clo - hlo);
+            const float z0 = fmaf(l1, w01, fmaf(l0, w00, bd0s)), z1 = fmaf(l1, w11, fmaf(l0, w10, bd1s));
+            g0 = rcp_approx(ex2_approx(z0) + inv_sAe);
+            g1 = rcp_approx(ex2_approx(z1) + inv_sAe);
           }
-          const float ct_la = pt == 0 ? clat[0] : (pt == 1 ? clat[1] : clat[2]);
-          const float ct_lo = pt == 0 ? clon[0] : (pt == 1 ? clon[1] : clon[2]);
-          const float l0 = fabsf(ct_la - hla), l1 = fabsf(ct_lo - hlo);
-          const float z0 = fmaf(l1, w01, fmaf(l0, w00, bd0)), z1 = fmaf(l1, w11, fmaf(l0, w10, bd1));
-          g0 = __fdividef(sc.sAe, 1.f + exp2f(z0));
-          g1 = __fdividef(sc.sAe, 1.f + exp2f(z1));
-        }
-        const __half2 hi2 = __floats2half2_rn(g0, g1);
-        const float2 hif = __half22float2(hi2);
-        const __half2 lo2 = __floats2half2_rn(g0 - hif.x, g1 - hif.y);
-        if (hch == 2 || hs == 0) {
-          // split / fast: [hi plane | lo plane], slots 2hs, 2hs+1.  mix: [k-chunk 0 | k-chunk 1]: chunk 0 slots 2hs.. = hi,
-          // chunk 1 slots 2hs.. = lo and slots 4+2hs.. = hi again (pairs with the lo weights)
-          unsigned char* eb = sE + (size_t)pbuf * 2 * TM * 16 + r * 16 + hs * 4;
+          const __half2 hi2 = __floats2half2_rn(g0, g1);
+          const float2 hif = __half22float2(hi2);
+          const __half2 lo2 = __floats2half2_rn(g0 - hif.x, g1 - hif.y);
+          unsigned char* eb = const_cast<unsigned char*>(ebase) + t * (2 * TM * 16);
           *reinterpret_cast<__half2*>(eb) = hi2;
           *reinterpret_cast<__half2*>(eb + TM * 16) = lo2;
           if (g.mix) *reinterpret_cast<__half2*>(eb + TM * 16 + 8) = hi2;
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&e_full[pbuf]);
-      };
-      // Group g owns the history chunks of parity g (a fixed set of h per partial sum, whatever tile / shard / item
-      // order a candidate is scored in: results are bit-identical between a sharded and an unsharded catalogue).
-      // prologue: the first NBUF steps (= chunk 0) are produced by its owner, group 0
-      if (egrp == 0)
-        for (int m = 0; m < NBUF && m < nsteps; ++m) produce(m);
-
-      // steps of this group's chunks: (c, t) for c = egrp, egrp + 2, ... and t = 0 .. tpc-1
-      for (int c = egrp, t = 0; c < nchunks; (t + 1 == tpc) ? (t = 0, c += 2) : ++t) {
-        const int ls = c * tpc + t;
-        const uint32_t n = n0 + (uint32_t)ls;
-        const uint32_t buf = n % NBUF;
-        const int h = hch == 2 ? 2 * c + hs : c;
-        int hist_id = -1;
-        if (h < H) hist_id = h < HMETA ? hm_id[h] : __ldg(A.users.items + hb + h);
-        mbar_wait(&acc_full[egrp * NBUF + buf], (phbits >> buf) & 1u);
-        phbits ^= 1u << buf;
-        tc_fence_after();
-        // MMA(n) is complete, so its A_ext buffer is free: refill it for step ls + NBUF (keeps the MMA queue fed)
-        if (ls + NBUF < nsteps) produce(ls + NBUF);
-        // ---- TMEM -> registers, 32 columns at a time.  Loads and their wait are kept back to back: the destination
-        // registers are written asynchronously, so no other code may sit between a tcgen05.ld and its wait::ld (the
-        // other epilogue group hides the latency instead).
-        const uint32_t t_main = tmem + lane_addr + buf * ACC_STRIDE + col0;
-        uint32_t aux[2], v[32];
-        float accp = 0.f, accn = 0.f;
-        tmem_ld2(tmem + lane_addr + buf * ACC_STRIDE + g.aux0 + (hch == 2 ? 2 * hs : 0), aux);
-        if (ncols >= 32) tmem_ld32(t_main, v);
-        else tmem_ld16(t_main, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-        tmem_wait_ld();
-        auto absum = [&](int c0, int cnt) {  // columns [c0, c0+cnt) of this thread's slice are in v[0..cnt)
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&e_full[t]);
+        };
+        auto hist_coords = [&](int h, float& la, float& lo) {
+          if (h < HMETA) {
+            la = hm_la[h];
+            lo = hm_lo[h];
+          } else {
+            la = __ldg(A.users.coords + 2 * (hb + h));
+            lo = __ldg(A.users.coords + 2 * (hb + h) + 1);
+          }
+        };
+        int jt[TPC];
 #pragma unroll
-          for (int g16 = 0; g16 < 32; g16 += 16) {
-            if (g16 < cnt) {
-              const int cc = kidx0 + c0 + g16;
-              if (cc + 16 <= npos || cc >= npos) {
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        for (int t = 0; t < TPC; ++t) jt[t] = jid[t] < A.poi_end ? (int)jid[t] : -2;
+        if (egrp == 0 && nchunks > 0) {  // prologue: chunk 0's A_ext
+          const bool on = g.lanes && hs < H;
+          float la = 0.f, lo = 0.f;
+          if (on) hist_coords(hs, la, lo);
+#pragma unroll
+          for (int t = 0; t < TPC; ++t) produce_f(t, on, la, lo, clat[t], clon[t]);
+        }
+        const uint32_t tb_main = tmem + lane_addr + (uint32_t)(hs * 64), tb_aux = tmem + lane_addr + 128u + (uint32_t)(2 * hs);
+        for (int c = egrp; c < nchunks; c += 2) {
+          const int h = 2 * c + hs;
+          const bool hvalid = h < H;
+          int hist_id = -1;
+          if (hvalid) hist_id = h < HMETA ? hm_id[h] : __ldg(A.users.items + hb + h);
+          const bool pn = c + 1 < nchunks;            // this group refills the A_ext buffers for the other group's next chunk
+          const bool pon = pn && g.lanes && (h + 2 < H);
+          float nla = 0.f, nlo = 0.f;
+          if (pon) hist_coords(h + 2, nla, nlo);
+#pragma unroll
+          for (int t = 0; t < TPC; ++t) {
+            mbar_wait(&acc_full[egrp * NBUF + t], fph);
+            tc_fence_after();
+            // The MMA issuer needs two things from this step before it may start step + 3: the accumulator drained
+            // (acc_empty) and the next A_ext (e_full).  Issue the first TMEM loads, build A_ext while they are in flight,
+            // and hand the accumulator back as soon as its last block is in registers.
+            uint32_t aux[2], va[16], vb[16];
+            float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+            auto blk = [&](const uint32_t(&v)[16], int b) {
+              if (b < nposb) {
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) {
-                  s0 += fabsf(__uint_as_float(v[g16 + i]));
-                  s1 += fabsf(__uint_as_float(v[g16 + i + 1]));
-                  s2 += fabsf(__uint_as_float(v[g16 + i + 2]));
-                  s3 += fabsf(__uint_as_float(v[g16 + i + 3]));
+                  p0 += fabsf(__uint_as_float(v[i]));
+                  p1 += fabsf(__uint_as_float(v[i + 1]));
+                  p2 += fabsf(__uint_as_float(v[i + 2]));
+                  p3 += fabsf(__uint_as_float(v[i + 3]));
                 }
-                const float ssum = (s0 + s1) + (s2 + s3);
-                if (cc >= npos) accn += ssum;
-                else accp += ssum;
-              } else {
+              } else if (b > nposb || nposm == 0) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const float av = fabsf(__uint_as_float(v[g16 + i]));
-                  if (cc + i < npos) accp += av;
-                  else accn += av;
+                for (int i = 0; i < 16; i += 4) {
+                  q0 += fabsf(__uint_as_float(v[i]));
+                  q1 += fabsf(__uint_as_float(v[i + 1]));
+                  q2 += fabsf(__uint_as_float(v[i + 2]));
+                  q3 += fabsf(__uint_as_float(v[i + 3]));
+                }
+              } else {  // the one block that holds both signs: signed FFMA with the +-1 vector kept in shared memory
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                  const float4 sg = *reinterpret_cast<const float4*>(sgn_mixed + i);
+                  p0 = fmaf(fabsf(__uint_as_float(v[i])), sg.x, p0);
+                  p1 = fmaf(fabsf(__uint_as_float(v[i + 1])), sg.y, p1);
+                  p2 = fmaf(fabsf(__uint_as_float(v[i + 2])), sg.z, p2);
+                  p3 = fmaf(fabsf(__uint_as_float(v[i + 3])), sg.w, p3);
+                }
+              }
+            };
+            tmem_ld2(tb_aux + t * ACC_STRIDE, aux);
+            tmem_ld16(tb_main + t * ACC_STRIDE, va);
+            tmem_ld16(tb_main + t * ACC_STRIDE + 16, vb);
+            if (pn) produce_f(t, pon, nla, nlo, clat[t], clon[t]);
+            tmem_wait_ld16(va);
+            tmem_wait_ld16(vb);
+            blk(va, 0);
+            tmem_ld16(tb_main + t * ACC_STRIDE + 32, va);
+            blk(vb, 1);
+            tmem_ld16(tb_main + t * ACC_STRIDE + 48, vb);
+            tmem_wait_ld16(va);
+            tmem_wait_ld16(vb);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[t]);
+            blk(va, 2);
+            blk(vb, 3);
+            const float asum = ((p0 + p1) + (p2 + p3)) - ((q0 + q1) + (q2 + q3));
+            const float S = __uint_as_float(aux[0]) * sc.inv_s;
+            const float a2 = (__uint_as_float(aux[1]) + asum) * c_a2;
+            const bool same = hist_id == jt[t];  // (hist_id is -1 when this slot is past the end of the history)
+            const float e = (hvalid && !same) ? ex2_approx(a2) : 0.f;
+            sumE[t] += e;
+            sumES[t] = fmaf(e, S, sumES[t]);
+            excl[t] = excl[t] || (hvalid && same);
+          }
+          fph ^= 1u;
+        }
+      } else {
+        // writes the g lanes of local step m into A_ext buffer (n0 + m) % NBUF
+        auto produce = [&](int m) {
+          const int pc = div_tpc(m), pt = m - pc * tpc;
+          const uint32_t pbuf = (n0 + (uint32_t)m) % NBUF;
+          const int h = hch == 2 ? 2 * pc + hs : pc;
+          float g0 = 0.f, g1 = 0.f;
+          if (g.lanes && h < H && (hch == 2 || hs == 0)) {
+            float hla, hlo;
+            if (h < HMETA) {
+              hla = hm_la[h];
+              hlo = hm_lo[h];
+            } else {
+              hla = __ldg(A.users.coords + 2 * (hb + h));
+              hlo = __ldg(A.users.coords + 2 * (hb + h) + 1);
+            }
+            const float ct_la = pt == 0 ? clat[0] : (pt == 1 ? clat[1] : clat[2]);
+            const float ct_lo = pt == 0 ? clon[0] : (pt == 1 ? clon[1] : clon[2]);
+            const float l0 = fabsf(ct_la - hla), l1 = fabsf(ct_lo - hlo);
+            const float z0 = fmaf(l1, w01, fmaf(l0, w00, bd0)), z1 = fmaf(l1, w11, fmaf(l0, w10, bd1));
+            g0 = __fdividef(sc.sAe, 1.f + exp2f(z0));
+            g1 = __fdividef(sc.sAe, 1.f + exp2f(z1));
+          }
+          const __half2 hi2 = __floats2half2_rn(g0, g1);
+          const float2 hif = __half22float2(hi2);
+          const __half2 lo2 = __floats2half2_rn(g0 - hif.x, g1 - hif.y);
+          if (hch == 2 || hs == 0) {
+            // split / fast: [hi plane | lo plane], slots 2hs, 2hs+1.  mix: [k-chunk 0 | k-chunk 1]: chunk 0 slots 2hs.. = hi,
+            // chunk 1 slots 2hs.. = lo and slots 4+2hs.. = hi again (pairs with the lo weights)
+            unsigned char* eb = sE + (size_t)pbuf * 2 * TM * 16 + r * 16 + hs * 4;
+            *reinterpret_cast<__half2*>(eb) = hi2;
+            *reinterpret_cast<__half2*>(eb + TM * 16) = lo2;
+            if (g.mix) *reinterpret_cast<__half2*>(eb + TM * 16 + 8) = hi2;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&e_full[pbuf]);
+        };
+        // Group g owns the history chunks of parity g (a fixed set of h per partial sum, whatever tile / shard / item
+        // order a candidate is scored in: results are bit-identical between a sharded and an unsharded catalogue).
+        // prologue: the first NBUF steps (= chunk 0) are produced by its owner, group 0
+        if (egrp == 0)
+          for (int m = 0; m < NBUF && m < nsteps; ++m) produce(m);
+
+        // steps of this group's chunks: (c, t) for c = egrp, egrp + 2, ... and t = 0 .. tpc-1
+        for (int c = egrp, t = 0; c < nchunks; (t + 1 == tpc) ? (t = 0, c += 2) : ++t) {
+          const int ls = c * tpc + t;
+          const uint32_t n = n0 + (uint32_t)ls;
+          const uint32_t buf = n % NBUF;
+          const int h = hch == 2 ? 2 * c + hs : c;
+          int hist_id = -1;
+          if (h < H) hist_id = h < HMETA ? hm_id[h] : __ldg(A.users.items + hb + h);
+          mbar_wait(&acc_full[egrp * NBUF + buf], (phbits >> buf) & 1u);
+          phbits ^= 1u << buf;
+          tc_fence_after();
+          // MMA(n) is complete, so its A_ext buffer is free: refill it for step ls + NBUF (keeps the MMA queue fed)
+          if (ls + NBUF < nsteps) produce(ls + NBUF);
+          // ---- TMEM -> registers, 32 columns at a time.  Loads and their wait are kept back to back: the destination
+          // registers are written asynchronously, so no other code may sit between a tcgen05.ld and its wait::ld (the
+          // other epilogue group hides the latency instead).
+          const uint32_t t_main = tmem + lane_addr + buf * ACC_STRIDE + col0;
+          uint32_t aux[2], v[32];
+          float accp = 0.f, accn = 0.f;
+          tmem_ld2(tmem + lane_addr + buf * ACC_STRIDE + g.aux0 + (hch == 2 ? 2 * hs : 0), aux);
+          if (ncols >= 32) tmem_ld32(t_main, v);
+          else tmem_ld16(t_main, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+          tmem_wait_ld();
+          auto absum = [&](int c0, int cnt) {  // columns [c0, c0+cnt) of this thread's slice are in v[0..cnt)
+  #pragma unroll
+            for (int g16 = 0; g16 < 32; g16 += 16) {
+              if (g16 < cnt) {
+                const int cc = kidx0 + c0 + g16;
+                if (cc + 16 <= npos || cc >= npos) {
+                  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  #pragma unroll
+                  for (int i = 0; i < 16; i += 4) {
+                    s0 += fabsf(__uint_as_float(v[g16 + i]));
+                    s1 += fabsf(__uint_as_float(v[g16 + i + 1]));
+                    s2 += fabsf(__uint_as_float(v[g16 + i + 2]));
+                    s3 += fabsf(__uint_as_float(v[g16 + i + 3]));
+                  }
+                  const float ssum = (s0 + s1) + (s2 + s3);
+                  if (cc >= npos) accn += ssum;
+                  else accp += ssum;
+                } else {
+  #pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    const float av = fabsf(__uint_as_float(v[g16 + i]));
+                    if (cc + i < npos) accp += av;
+                    else accn += av;
+                  }
                 }
               }
             }
+          };
+          absum(0, ncols >= 32 ? 32 : 16);
+          if (ncols > 32) {
+            if (ncols >= 64) tmem_ld32(t_main + 32, v);
+            else tmem_ld16(t_main + 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+            tmem_wait_ld();
           }
-        };
-        absum(0, ncols >= 32 ? 32 : 16);
-        if (ncols > 32) {
-          if (ncols >= 64) tmem_ld32(t_main + 32, v);
-          else tmem_ld16(t_main + 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-          tmem_wait_ld();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);
-        if (ncols > 32) absum(32, ncols >= 64 ? 32 : 16);
-        float asum = accp - accn;
-        if (hch == 1) {
-          // the other half of this cell's hidden units was summed by the partner warp (same lane quarter)
-          float* slot = xch + ((ls & 1) * 2 + egrp) * TM + r;
-          if (hs == 1) *slot = asum;
-          asm volatile("bar.sync %0, 64;" ::"r"(2 + egrp * 4 + qd) : "memory");
-          if (hs == 0) asum += *slot;
-        }
-        const float S = __uint_as_float(aux[0]) * sc.inv_s;
-        const float a = (__uint_as_float(aux[1]) + asum) * sc.inv_sigma;
-        if (h < H && (hch == 2 || hs == 0)) {
-          const int64_t j = t == 0 ? jid[0] : (t == 1 ? jid[1] : jid[2]);
-          if ((int64_t)hist_id != j) {
-            const float e = __expf(a);
-            if (t == 0) { sumE[0] += e; sumES[0] = fmaf(e, S, sumES[0]); }
-            else if (t == 1) { sumE[1] += e; sumES[1] = fmaf(e, S, sumES[1]); }
-            else { sumE[2] += e; sumES[2] = fmaf(e, S, sumES[2]); }
-          } else {
-            if (t == 0) excl[0] = true;
-            else if (t == 1) excl[1] = true;
-            else excl[2] = true;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          if (ncols > 32) absum(32, ncols >= 64 ? 32 : 16);
+          float asum = accp - accn;
+          if (hch == 1) {
+            // the other half of this cell's hidden units was summed by the partner warp (same lane quarter)
+            float* slot = xch + ((ls & 1) * 2 + egrp) * TM + r;
+            if (hs == 1) *slot = asum;
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + egrp * 4 + qd) : "memory");
+            if (hs == 0) asum += *slot;
+          }
+          const float S = __uint_as_float(aux[0]) * sc.inv_s;
+          const float a = (__uint_as_float(aux[1]) + asum) * sc.inv_sigma;
+          if (h < H && (hch == 2 || hs == 0)) {
+            const int64_t j = t == 0 ? jid[0] : (t == 1 ? jid[1] : jid[2]);
+            if ((int64_t)hist_id != j) {
+              const float e = __expf(a);
+              if (t == 0) { sumE[0] += e; sumES[0] = fmaf(e, S, sumES[0]); }
+              else if (t == 1) { sumE[1] += e; sumES[1] = fmaf(e, S, sumES[1]); }
+              else { sumE[2] += e; sumES[2] = fmaf(e, S, sumES[2]); }
+            } else {
+              if (t == 0) excl[0] = true;
+              else if (t == 1) excl[1] = true;
+              else excl[2] = true;
+            }
           }
         }
+        n0 += (uint32_t)nsteps;
       }
-      n0 += (uint32_t)nsteps;
       // ---- item epilogue: combine the 4 partial states (2 groups x 2 history slots), score, block top-k --------------
       const int part = egrp * 2 + hs;  // partial 0 is the combiner
       if (!kSinglePart) epi_bar();  // every group is past its last step: all MMAs are complete, A_ext + zero may hold `comb`
@@ -1012,8 +1221,15 @@ int launch_fullrank_tc(const NaisParams& p, const NaisCatalog& cat, const NaisUs
   A.part_keys = keys;
   A.all_scores = all_scores;
   A.max_chunks = max_chunks;
-  void (*kern)(const tc::MainArgs) = g.kp == 1 ? (g.hch == 2 ? tc::fullrank_tc_kernel<true, 2> : tc::fullrank_tc_kernel<true, 1>)
-                                               : (g.hch == 2 ? tc::fullrank_tc_kernel<false, 2> : tc::fullrank_tc_kernel<false, 1>);
+  // static D = hid = 64 instantiations (the reference's C1/C2 shape): 1 = SPLIT, 2 = MIX
+  const int fix = (g.D == 64 && g.hid == 64 && g.kp == 1 && g.hch == 2 && g.nrow == 144 && g.stages == 2 && !getenv("NAIS_TC_GENERIC"))
+                      ? (g.mix ? 2 : (g.split ? 1 : 0))
+                      : 0;
+  void (*kern)(const tc::MainArgs) =
+      g.kp == 1 ? (g.hch == 2 ? (fix == 2 ? tc::fullrank_tc_kernel<true, 2, 2>
+                                          : (fix == 1 ? tc::fullrank_tc_kernel<true, 2, 1> : tc::fullrank_tc_kernel<true, 2, 0>))
+                              : tc::fullrank_tc_kernel<true, 1, 0>)
+                : (g.hch == 2 ? tc::fullrank_tc_kernel<false, 2, 0> : tc::fullrank_tc_kernel<false, 1, 0>);
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes);
   if (e != cudaSuccess) return (int)e;
   int sms = 148;
