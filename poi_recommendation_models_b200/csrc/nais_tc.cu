@@ -427,6 +427,31 @@ struct MainArgs {
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 // kSinglePart: D <= 64, a B stage holds a whole chunk (kp == 1).  kHch: history items per MMA step (2: hid <= 64, 1: hid 96/128).
+// 32 keys, one per lane -> sorted descending across the lanes (bitonic network on shuffles)
+__device__ __forceinline__ unsigned long long warp_sort_desc(unsigned long long v, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, j);
+      const bool desc = k == 32 || (lane & k) == 0, lower = (lane & j) == 0;
+      v = (lower == desc) ? (v > o ? v : o) : (v < o ? v : o);
+    }
+  }
+  return v;
+}
+// two descending rows -> the best 32 of both, descending
+__device__ __forceinline__ unsigned long long warp_fold_top32(unsigned long long a, unsigned long long b, int lane) {
+  const unsigned long long br = __shfl_sync(0xffffffffu, b, 31 - lane);
+  unsigned long long v = a > br ? a : br;
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, j);
+    v = ((lane & j) == 0) ? (v > o ? v : o) : (v < o ? v : o);
+  }
+  return v;
+}
+
 // kFix: 0 = generic (every shape is a run-time value); 1 / 2 = the D = hid = 64 shape of the headline workload in SPLIT / MIX
 // precision with every tile constant known at compile time: a fully unrolled MMA issue sequence (descriptor = base +
 // immediate; the generic issuer spends ~15 instructions per MMA, which paces the kernel once a step is 9 MMAs) and the
@@ -1032,6 +1057,8 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       }
       // ---- item epilogue: combine the 4 partial states (2 groups x 2 history slots), score, block top-k --------------
       const int part = egrp * 2 + hs;  // partial 0 is the combiner
+      const bool small_k = A.k <= 32;
+      unsigned long long kreg[TPC];
       if (!kSinglePart) epi_bar();  // every group is past its last step: all MMAs are complete, A_ext + zero may hold `comb`
       if (part != 0) {
 #pragma unroll
@@ -1056,15 +1083,35 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
           const float score = ES / powf(E, beta);
           const bool valid = jid[t2] < A.poi_end;
           if (A.all_scores && valid) A.all_scores[(size_t)u * (A.poi_end - A.poi_begin) + (jid[t2] - A.poi_begin)] = score;
-          keys[t2 * TM + r] = (valid && !(A.exclude && ex)) ? make_key(score, (int)jid[t2]) : 0ull;
+          kreg[t2] = (valid && !(A.exclude && ex)) ? make_key(score, (int)jid[t2]) : 0ull;
+          if (!small_k) keys[t2 * TM + r] = kreg[t2];
         }
-        for (int i = TPC * TM + r; i < SORTN; i += TM) keys[i] = 0ull;
+        if (small_k) {
+          // k <= 32: the item's 384 keys live in the registers of warps 0-3.  Sort each 32-key row with warp shuffles,
+          // fold the rows keeping the best 32 (max of one sorted row against the other reversed is bitonic and holds the
+          // top 32 of both), park 4 x 32 candidates in shared memory; warp 0 folds those after the barrier.  Same total
+          // order as the 512-key sort below (keys are unique except the 0 = "no entry" filler), 2 barriers instead of 45.
+          unsigned long long a = warp_sort_desc(kreg[0], lane);
+          a = warp_fold_top32(a, warp_sort_desc(kreg[1], lane), lane);
+          a = warp_fold_top32(a, warp_sort_desc(kreg[2], lane), lane);
+          keys[r] = a;
+        } else {
+          for (int i = TPC * TM + r; i < SORTN; i += TM) keys[i] = 0ull;
+        }
       }
       epi_bar();
       // `comb` is consumed: restore A_ext / zero for the next item's MMAs (generic writes -> async proxy fence)
       if (!kSinglePart) {
         for (int i = tid; i < (NBUF * 2 * TM * 16 + 4096) / 4; i += EPI_THREADS) init_ext_word(i);
         fence_proxy_async();
+      }
+      if (small_k) {
+        if (warp == 0) {
+          unsigned long long a = warp_fold_top32(keys[lane], keys[32 + lane], lane);
+          a = warp_fold_top32(a, warp_fold_top32(keys[64 + lane], keys[96 + lane], lane), lane);
+          if (lane < A.k) A.part_keys[((size_t)u * A.groups + grp) * A.k + lane] = a;
+        }
+        continue;  // (the next item's first epi_bar orders these reads of `keys` before its writes)
       }
       // bitonic sort (descending) of SORTN keys, one key pair per epilogue thread
       for (int kk = 2; kk <= SORTN; kk <<= 1) {
