@@ -245,7 +245,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=list(WORKLOADS))
-    ap.add_argument("--precision", default=os.environ.get("NAIS_BENCH_PRECISION", "tc_split"), choices=["fp32", "tc_split", "tc_mix", "tc_fast"])
+    ap.add_argument("--precision", default=os.environ.get("NAIS_BENCH_PRECISION", "tc_auto"),
+                    choices=["fp32", "tc_auto", "tc_split", "tc_mix", "tc_fast"])
     ap.add_argument("--users-per-step", type=int, default=0)
     ap.add_argument("--mode", default="eval", choices=["eval", "train"], help="eval = headline full-rank metric; train = C3 BPR fwd+bwd (triples/s)")
     ap.add_argument("--cpu-users", type=int, default=4, help="users in the bounded CPU-baseline sample")
@@ -278,7 +279,7 @@ def main():
         return
 
     U, N, H, D, hid, k = cfg["users"], cfg["pois"], cfg["hist"], cfg["D"], cfg["hid"], cfg["k"]
-    ups = args.users_per_step or max(148, int({"fp32": 296, "tc_split": 2368, "tc_mix": 2368, "tc_fast": 4736}[args.precision] * min(1.0, 40000 / N)))
+    ups = args.users_per_step or max(148, int({"fp32": 296, "tc_auto": 2368, "tc_split": 2368, "tc_mix": 2368, "tc_fast": 4736}[args.precision] * min(1.0, 40000 / N)))
     ups = min(ups, U)
     n_batches = min(args.steps + args.warmup, max(1, U // ups))
     # ---- synthetic data + random-init ("trained-like") weights of the named architecture ----------------------------
@@ -358,6 +359,10 @@ def main():
     h2d = batches_host[0][0].numel() * 8 + batches_host[0][1].numel() * 8
     d2h = ups * k * (4 + 8)
 
+    eff, choice = args.precision, None
+    if args.precision == "tc_auto":  # the device-side gate picked MIX or SPLIT (no host sync inside the timed regions)
+        choice = ops.last_tc_choice()
+        eff = "tc_mix" if choice and choice["use_mix"] else "tc_split"
     if rank == 0:
         cells_per_launch = ups * H * ((N + world - 1) // world)
         F = flops_per_cell(D, hid)
@@ -367,9 +372,10 @@ def main():
                 "pair_scores_per_sec": users_per_s * N, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": {"fp32": "f32", "tc_split": "f16x2-split/f32-accum", "tc_mix": "f16+e5m2-corrections/f32-accum",
-                          "tc_fast": "f16/f32-accum"}[args.precision],
+                          "tc_fast": "f16/f32-accum"}[eff],
                 "data": "synthetic",
                 "config": {"workload": f"{args.config}: {cfg['desc']}", "users_per_step": ups, "precision": args.precision,
+                           "precision_effective": eff, "tc_auto_gate": choice,
                            "l2": "flushed between timed steps (256 MiB write)", "weights": "random init, trained-like scale",
                            "parallelism": f"catalogue range shards x{world} + all-gather top-k merge" if world > 1 else "single GPU"},
                 "clocks": clocks, "gpu_launches": int(launches),
@@ -389,16 +395,18 @@ def main():
             # K=16 MMA (measured: tests/umma_probe_f8.cu) -> counted as fp16-equivalent pipe FLOPs
             per_step = {"tc_split": 3 * ks * 2 * 128 * nrow * 16,
                         "tc_mix": (ks + 2 * (D // 32)) * 2 * 128 * nrow * 16,
-                        "tc_fast": ks * 2 * 128 * nrow * 16 + 2 * ks * 2 * 128 * 16 * 16}[args.precision]
+                        "tc_fast": ks * 2 * 128 * nrow * 16 + 2 * ks * 2 * 128 * 16 * 16}[eff]
             issued = cells_per_launch / 256 * per_step / (kern_ms / 1000.0) / 1e12
             line["roofline"].update({"issued_tflops": issued, "issued_frac": issued / peak,
                                      "issued_note": "tensor-pipe FLOPs executed (fp16-equivalent issue slots) incl. split/correction passes, ext K-step and S/L rows"})
         tr = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
-        if os.path.isfile(tr) and args.precision == "tc_split":
+        if os.path.isfile(tr) and eff in ("tc_split", "tc_mix"):
             with open(tr) as f:
                 t = json.load(f)
-            line["roofline"]["traffic"] = t["dram_bytes_per_user"] * ups + t.get("dram_bytes_const", 0)
-            line["roofline"]["traffic_source"] = t["source"]
+            t = t.get(eff, t if "dram_bytes_per_user" in t else None)  # one entry per precision mode
+            if t:
+                line["roofline"]["traffic"] = t["dram_bytes_per_user"] * ups + t.get("dram_bytes_const", 0)
+                line["roofline"]["traffic_source"] = t["source"]
         # algorithmic HBM bytes of the launch: catalogue rows + history items + output
         alg_bytes = ((N + world - 1) // world) * (D // 2 * 4 + 4 + 8) + ups * H * (4 + D // 2 * 4 + 4 + 8) + ups * k * 8
         if kern_ms:

@@ -46,6 +46,7 @@ extern "C" {
 #define NAIS_PREC_TC_SPLIT 1 /* tcgen05 fp16 MMA, operands split hi+lo (3 MMAs, ~fp32 products), fp32 accumulate in TMEM */
 #define NAIS_PREC_TC_FAST 2  /* tcgen05 fp16 MMA, single pass (11-bit operands), fp32 accumulate in TMEM */
 #define NAIS_PREC_TC_MIX 3   /* tcgen05 fp16 MMA for hi*hi + two e5m2 (kind::f8f6f4) MMAs for the hi*lo, lo*hi corrections */
+#define NAIS_PREC_TC_AUTO 4  /* MIX when a device-side bound on the logit scale keeps its error 4x under 1e-4, else SPLIT */
 
 #define NAIS_ERR_NULL -1      /* required pointer is NULL */
 #define NAIS_ERR_SHAPE -2     /* unsupported / inconsistent dimension */

@@ -8,8 +8,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libnais_b200.so")
 
 DIST_NONE, DIST_LATLON, DIST_KM = 0, 1, 2
-PREC_FP32, PREC_TC_SPLIT, PREC_TC_FAST, PREC_TC_MIX = 0, 1, 2, 3
-PRECISIONS = {"fp32": PREC_FP32, "tc_split": PREC_TC_SPLIT, "tc_fast": PREC_TC_FAST, "tc_mix": PREC_TC_MIX}
+PREC_FP32, PREC_TC_SPLIT, PREC_TC_FAST, PREC_TC_MIX, PREC_TC_AUTO = 0, 1, 2, 3, 4
+PRECISIONS = {"fp32": PREC_FP32, "tc_split": PREC_TC_SPLIT, "tc_fast": PREC_TC_FAST, "tc_mix": PREC_TC_MIX,
+              "tc_auto": PREC_TC_AUTO}
 
 c_float_p = C.c_void_p  # device pointers travel as integers
 

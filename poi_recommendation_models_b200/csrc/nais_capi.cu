@@ -160,7 +160,7 @@ static int check_fullrank(const NaisParams* p, const NaisCatalog* cat, const Nai
   if (work && need_reg && (!cat->region || !users->region)) return NAIS_ERR_NULL;
   if (work && p->dist_mode != NAIS_DIST_NONE && (!cat->coords || !users->coords)) return NAIS_ERR_NULL;
   if (p->dist_mode == NAIS_DIST_KM && precision != NAIS_PREC_FP32) return NAIS_ERR_MODE;  // fused haversine: FP32 path only
-  if (precision < NAIS_PREC_FP32 || precision > NAIS_PREC_TC_MIX) return NAIS_ERR_MODE;
+  if (precision < NAIS_PREC_FP32 || precision > NAIS_PREC_TC_AUTO) return NAIS_ERR_MODE;
   if (precision != NAIS_PREC_FP32 && !tc_supported(*p, precision)) return NAIS_ERR_SHAPE;
   return 0;
 }

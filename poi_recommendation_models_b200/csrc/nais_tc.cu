@@ -80,6 +80,10 @@ __host__ inline bool make_geo(const NaisParams& p, int precision, Geo& g) {
   g.split = precision == NAIS_PREC_TC_SPLIT;
   g.mix = precision == NAIS_PREC_TC_MIX;
   if (p.dist_mode == NAIS_DIST_KM) return false;
+  if (precision == NAIS_PREC_TC_AUTO) {  // MIX geometry where an e5m2 K-step exists, else SPLIT (same image sizes)
+    g.mix = g.D % 32 == 0;
+    g.split = !g.mix;
+  }
   if (g.mix && g.D % 32) return false;  // an e5m2 MMA covers K = 32
   if (g.D % 16 || g.D < 16 || g.D > 128 || (g.D > 64 && g.D % 32) || g.hid % 16 || g.hid < 16 || g.hid > 128) return false;
   g.hch = g.hid <= 64 ? 2 : 1;
@@ -122,8 +126,21 @@ __host__ inline bool make_geo(const NaisParams& p, int precision, Geo& g) {
 struct Scales {
   float sA, sS, sB, sAe, sBe, inv_sigma, inv_s;
   int npos;
-  float omega0, omega1, omegab, pad;
+  float omega0, omega1, omegab;
+  float rho;     // maxP * maxB * sqrt(hid * D): scale of the logit sum that the e5m2 corrections' ~3e-5 per-term error multiplies
+  int use_mix;   // NAIS_PREC_TC_AUTO: rho <= kMixRhoMax -> the MIX kernels run, else the SPLIT kernels (the others exit at once)
 };
+// Emulated (examples/precision_emulation.py) and measured (tests) conditioned error of MIX: ~1e-5 up to rho ~ 100, 2.3e-5 at
+// 250, 4.7e-5 at 490, 1.3e-4 at 1170 (embedding std 1.0 with 4x weights).  256 keeps 4x margin to the 1e-4 bar.
+constexpr float kMixRhoMax = 256.f;
+// ... and the similarity S_hj carries the same ~3e-5 per-term error into the score directly; it averages out over the
+// history but not for a handful of items (emulated worst case over 2000 candidates: H = 64: 1.7e-5, 16: 2.8e-5, 6: 7e-5,
+// 2: 1e-3), so under NAIS_PREC_TC_AUTO users with a shorter history than this take the SPLIT pass (they are cheap anyway).
+constexpr int kMixMinHist = 16;
+// NAIS_PREC_TC_AUTO runs a MIX pass (gate 1) and a SPLIT pass (gate 0) over the same user batch; each user belongs to one.
+__device__ __forceinline__ bool user_in_pass(int gate, int use_mix, int H) {
+  return gate < 0 || ((use_mix && H >= kMixMinHist) ? 1 : 0) == gate;
+}
 // workspace header: [0,64) maxes (uint bits) | [64,128) Scales | perm[128] int | ck[128] float | u[128] float
 constexpr int HDR_BYTES = 4096;
 constexpr int HDR_PERM = 128, HDR_CK = HDR_PERM + 128 * 4, HDR_U = HDR_CK + 128 * 4;
@@ -218,6 +235,8 @@ __global__ void scales_kernel(NaisParams p, unsigned char* hdr) {
     sc->omega0 = o0;
     sc->omega1 = o1;
     sc->omegab = ob;
+    sc->rho = maxP * maxB * sqrtf((float)(hid * D));
+    sc->use_mix = sc->rho <= kMixRhoMax ? 1 : 0;
   }
 }
 
@@ -234,9 +253,10 @@ __device__ __forceinline__ uint2 pack_e5m2(const __half* h) {
 
 // Candidate tiles: image [tile][plane hi|lo][k-chunk][row][8 x fp16] of p_j * sA.  One thread = (row, k-chunk).
 __global__ void pack_candidates_kernel(NaisParams p, NaisCatalog cat, int64_t poi_begin, int64_t poi_end, Geo g,
-                                       const unsigned char* hdr, unsigned char* Pimg) {
+                                       const unsigned char* hdr, unsigned char* Pimg, int gate) {
   const NaisBranch& br = p.branch[0];
   const Scales* sc = reinterpret_cast<const Scales*>(hdr + 64);
+  if (gate == 1 && !sc->use_mix) return;  // NAIS_PREC_TC_AUTO: no user takes the MIX pass
   const float sA = sc->sA;
   const int tile = blockIdx.x;
   for (int i = threadIdx.x; i < TM * g.kx; i += blockDim.x) {
@@ -273,7 +293,7 @@ __device__ __forceinline__ int64_t chunk_base(const int64_t* offsets, int u, int
 
 // User operand: grid (chunk slot, user).  One thread = (row n, k-chunk c) -> 8 fp16 (hi) + 8 fp16 (lo).
 __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g, const unsigned char* hdr, unsigned char* Bimg,
-                                  int64_t max_chunks) {
+                                  int64_t max_chunks, int gate) {
   const NaisBranch& br = p.branch[0];
   const Scales* sc = reinterpret_cast<const Scales*>(hdr + 64);
   const int* perm = reinterpret_cast<const int*>(hdr + HDR_PERM);
@@ -282,6 +302,7 @@ __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g, const un
   const int u = blockIdx.y;
   const int64_t hb = users.offsets[u];
   const int H = (int)(users.offsets[u + 1] - hb);
+  if (!user_in_pass(gate, sc->use_mix, H)) return;  // the other pass of NAIS_PREC_TC_AUTO packs (and scores) this user
   const int hch = g.hch, aux0 = g.aux0;
   const int nchunks = (H + hch - 1) / hch;
   const int D = g.D, hid = g.hid, ldw = D + g.lanes;
@@ -422,6 +443,7 @@ struct MainArgs {
   unsigned long long* part_keys;  // [n_users, groups, k]
   float* all_scores;              // optional [n_users, range]
   int64_t max_chunks;             // chunk slots the operand image holds (users beyond it are truncated, never read out of bounds)
+  int gate;                       // -1: always run; 0 / 1: run only if Scales::use_mix has this value (NAIS_PREC_TC_AUTO)
 };
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
@@ -486,6 +508,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const Scales sc = *reinterpret_cast<const Scales*>(A.hdr + 64);
+  if (A.gate == 1 && !sc.use_mix) return;  // NAIS_PREC_TC_AUTO, no user takes the MIX pass: whole grid, before any barrier
 
   // ---- one-time setup ---------------------------------------------------------------------------------------------
   // A_ext (3 x hi|lo planes) and the zero region: everything 0 except column 4 of each hi plane = 1.0 * sAe (bias lane)
@@ -527,9 +550,11 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
     // =================================================== bulk-copy producer ========================================
     // (warp-uniform control flow, one elected lane issues; see the MMA warp)
     {
-      uint32_t it = 0, bstep = 0;
-      for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x, ++it) {
+      uint32_t it_n = 0, bstep = 0;  // it_n counts the items this pass processes (all three roles skip the same ones)
+      for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x) {
         const int u = (int)(item / A.groups), grp = (int)(item % A.groups);
+        if (!user_in_pass(A.gate, sc.use_mix, (int)(A.users.offsets[u + 1] - A.users.offsets[u]))) continue;
+        const uint32_t it = it_n++;
         const int64_t cbu = __shfl_sync(0xffffffffu, chunk_base(A.users.offsets, u, kHch) - cb0, 0);
         const int nchunks = __shfl_sync(0xffffffffu, user_chunks(A.users.offsets, u, kHch, cb0, A.max_chunks), 0);
         mbar_wait(a_empty, (it & 1) ^ 1);
@@ -589,9 +614,11 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       const uint32_t B_hi = lo_of(sb0, kBLbo);
       const uint32_t Bx_hi = lo_of(sb0 + 8 * kBLbo, zaddr - (sb0 + 8 * kBLbo));     // split: ext chunk of the hi plane
       const uint32_t Bx_lo = lo_of(sb0 + 17 * kBLbo, zaddr - (sb0 + 17 * kBLbo));   //        ... of the lo plane (9 + 8)
-      uint32_t it = 0, cc = 0, st = 0, stph = 0;
-      for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x, ++it) {
+      uint32_t it_n = 0, cc = 0, st = 0, stph = 0;
+      for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x) {
         const int u = (int)(item / A.groups);
+        if (!user_in_pass(A.gate, sc.use_mix, (int)(A.users.offsets[u + 1] - A.users.offsets[u]))) continue;
+        const uint32_t it = it_n++;
         const int nchunks = __shfl_sync(0xffffffffu, user_chunks(A.users.offsets, u, kHch, cb0, A.max_chunks), 0);
         mbar_wait(a_full, it & 1);
         for (int c = 0; c < nchunks; ++c, ++cc) {
@@ -675,9 +702,11 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       const uint32_t Ba_hi0 = lo_of(bha, b_lbo), Bae_hi0 = lo_of(bha + kcp * b_lbo, zaddr - (bha + kcp * b_lbo));
       const uint32_t baelx = sb0 + lo_off_last + kcp * l_lbo;                                       // ext k-chunk of the 16-row lo image
       const uint32_t Bae_lo0 = lo_of(baelx, zaddr - baelx);
-      uint32_t it = 0, n = 0, st = 0, stph = 0;
-      for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x, ++it) {
+      uint32_t it_n = 0, n = 0, st = 0, stph = 0;
+      for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x) {
         const int u = (int)(item / A.groups);
+        if (!user_in_pass(A.gate, sc.use_mix, (int)(A.users.offsets[u + 1] - A.users.offsets[u]))) continue;
+        const uint32_t it = it_n++;
         const int nchunks = __shfl_sync(0xffffffffu, user_chunks(A.users.offsets, u, kHch, cb0, A.max_chunks), 0);
         mbar_wait(a_full, it & 1);
         for (int c = 0; c < nchunks; ++c, n += (uint32_t)tpc) {
@@ -780,6 +809,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       const int u = (int)(item / A.groups), grp = (int)(item % A.groups);
       const int64_t hb = A.users.offsets[u];
       const int H = (int)(A.users.offsets[u + 1] - hb);
+      if (!user_in_pass(A.gate, sc.use_mix, H)) continue;
       const int nchunks = user_chunks(A.users.offsets, u, hch, cb0, A.max_chunks);
       const int nsteps = nchunks * tpc;
       // stage this user's history ids / coords (previous item's readers are past their last epi_bar)
@@ -1244,48 +1274,67 @@ int launch_fullrank_tc(const NaisParams& p, const NaisCatalog& cat, const NaisUs
   amax(br.hist_reg, (size_t)p.region_num * br.w_reg, mx + 3);
   tc::scales_kernel<<<1, 256, 0, stream>>>(p, hdr);
   NAIS_COUNT_LAUNCH(1);
-  tc::pack_candidates_kernel<<<n_tiles_pad, 256, 0, stream>>>(p, cat, poi_begin, poi_end, g, hdr, pimg);
-  NAIS_COUNT_LAUNCH(1);
-  {
-    dim3 grid(64, users.n_users);
-    tc::pack_users_kernel<<<grid, 256, 0, stream>>>(p, users, g, hdr, bimg, max_chunks);
-    NAIS_COUNT_LAUNCH(1);
-  }
-  tc::MainArgs A;
-  A.p = p;
-  A.cat = cat;
-  A.users = users;
-  A.g = g;
-  A.poi_begin = poi_begin;
-  A.poi_end = poi_end;
-  A.k = k;
-  A.exclude = exclude;
-  A.groups = groups;
-  A.n_items = (int64_t)users.n_users * groups;
-  A.hdr = hdr;
-  A.Pimg = pimg;
-  A.Bimg = bimg;
-  A.part_keys = keys;
-  A.all_scores = all_scores;
-  A.max_chunks = max_chunks;
-  // static D = hid = 64 instantiations (the reference's C1/C2 shape): 1 = SPLIT, 2 = MIX
-  const int fix = (g.D == 64 && g.hid == 64 && g.kp == 1 && g.hch == 2 && g.nrow == 144 && g.stages == 2 && !getenv("NAIS_TC_GENERIC"))
-                      ? (g.mix ? 2 : (g.split ? 1 : 0))
-                      : 0;
-  void (*kern)(const tc::MainArgs) =
-      g.kp == 1 ? (g.hch == 2 ? (fix == 2 ? tc::fullrank_tc_kernel<true, 2, 2>
-                                          : (fix == 1 ? tc::fullrank_tc_kernel<true, 2, 1> : tc::fullrank_tc_kernel<true, 2, 0>))
-                              : tc::fullrank_tc_kernel<true, 1, 0>)
-                : (g.hch == 2 ? tc::fullrank_tc_kernel<false, 2, 0> : tc::fullrank_tc_kernel<false, 1, 0>);
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes);
-  if (e != cudaSuccess) return (int)e;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = (int)(A.n_items < sms ? A.n_items : sms);
-  kern<<<grid, tc::THREADS, g.smem_bytes, stream>>>(A);
-  NAIS_COUNT_LAUNCH(1);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return (int)e;
+  // one precision = one pass; NAIS_PREC_TC_AUTO = the MIX pass and the SPLIT pass back to back, each gated on the device-side
+  // flag (the library never synchronises, so the choice cannot come back to the host; the losing pass exits at once)
+  auto run = [&](const tc::Geo& gg, int gate) -> int {
+    tc::pack_candidates_kernel<<<n_tiles_pad, 256, 0, stream>>>(p, cat, poi_begin, poi_end, gg, hdr, pimg, gate);
+    NAIS_COUNT_LAUNCH(1);
+    {
+      dim3 grid(64, users.n_users);
+      tc::pack_users_kernel<<<grid, 256, 0, stream>>>(p, users, gg, hdr, bimg, max_chunks, gate);
+      NAIS_COUNT_LAUNCH(1);
+    }
+    tc::MainArgs A;
+    A.p = p;
+    A.cat = cat;
+    A.users = users;
+    A.g = gg;
+    A.poi_begin = poi_begin;
+    A.poi_end = poi_end;
+    A.k = k;
+    A.exclude = exclude;
+    A.groups = groups;
+    A.n_items = (int64_t)users.n_users * groups;
+    A.hdr = hdr;
+    A.Pimg = pimg;
+    A.Bimg = bimg;
+    A.part_keys = keys;
+    A.all_scores = all_scores;
+    A.max_chunks = max_chunks;
+    A.gate = gate;
+    // static D = hid = 64 instantiations (the reference's C1/C2 shape): 1 = SPLIT, 2 = MIX
+    const int fix = (gg.D == 64 && gg.hid == 64 && gg.kp == 1 && gg.hch == 2 && gg.nrow == 144 && gg.stages == 2 && !getenv("NAIS_TC_GENERIC"))
+                        ? (gg.mix ? 2 : (gg.split ? 1 : 0))
+                        : 0;
+    void (*kern)(const tc::MainArgs) =
+        gg.kp == 1 ? (gg.hch == 2 ? (fix == 2 ? tc::fullrank_tc_kernel<true, 2, 2>
+                                              : (fix == 1 ? tc::fullrank_tc_kernel<true, 2, 1> : tc::fullrank_tc_kernel<true, 2, 0>))
+                                  : tc::fullrank_tc_kernel<true, 1, 0>)
+                   : (gg.hch == 2 ? tc::fullrank_tc_kernel<false, 2, 0> : tc::fullrank_tc_kernel<false, 1, 0>);
+    cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gg.smem_bytes);
+    if (e2 != cudaSuccess) return (int)e2;
+    const int grid = (int)(A.n_items < sms ? A.n_items : sms);
+    kern<<<grid, tc::THREADS, gg.smem_bytes, stream>>>(A);
+    NAIS_COUNT_LAUNCH(1);
+    e2 = cudaGetLastError();
+    return e2 == cudaSuccess ? 0 : (int)e2;
+  };
+  if (precision == NAIS_PREC_TC_AUTO) {
+    tc::Geo gs;
+    if (!tc::make_geo(p, NAIS_PREC_TC_SPLIT, gs)) return NAIS_ERR_SHAPE;
+    if (g.mix) {  // make_geo(AUTO) gave the MIX geometry: same image sizes as SPLIT, so the two passes share the workspace
+      if (gs.a_tile != g.a_tile || gs.b_chunk != g.b_chunk) return NAIS_ERR_SHAPE;
+      int rc = run(g, 1);
+      if (rc) return rc;
+    }
+    int rc = run(gs, g.mix ? 0 : -1);  // users the MIX pass left out (short histories; everyone if the gate is closed)
+    if (rc) return rc;
+  } else {
+    int rc = run(g, -1);
+    if (rc) return rc;
+  }
   return launch_topk_merge_keys_multi(keys, scratch, users.n_users, groups, k, out_score, out_id, stream);
 }
 

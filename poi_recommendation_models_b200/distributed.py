@@ -67,7 +67,7 @@ class ShardedRanker:
         b.synchronize()
         return a.elapsed_time(b)
 
-    def topk(self, users, k: int, precision: str = "fp32"):
+    def topk(self, users, k: int, precision: str = "auto"):
         timed = torch.cuda.is_available() and users.offsets.is_cuda
         if timed:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -81,7 +81,7 @@ class ShardedRanker:
             s, i = self._merge(gs, gi)
         return s, i
 
-    def topk_host(self, indptr: torch.Tensor, items: torch.Tensor, k: int, precision: str = "fp32"):
+    def topk_host(self, indptr: torch.Tensor, items: torch.Tensor, k: int, precision: str = "auto"):
         """End-to-end call: pinned host CSR -> device, rank, top-k lists back on the host (sigmoid scores like
         `forward`, int64 ids)."""
         m = self.model

@@ -111,10 +111,12 @@ class _NAISBase(nn.Module):
 
     @torch.no_grad()
     def predict_topk(self, users, k: int, exclude_history: bool = True, poi_begin: int = 0,
-                     poi_end: Optional[int] = None, precision: str = "fp32") -> Tuple[torch.Tensor, torch.Tensor]:
+                     poi_end: Optional[int] = None, precision: str = "auto") -> Tuple[torch.Tensor, torch.Tensor]:
         """Top-k POIs of [poi_begin, poi_end) for every user: (sigmoid score [U,k] as `forward` would return,
         ids [U,k] int64, -1 padded).  `users` is a DeviceUsers or an (indptr, indices) pair.  One call replaces the
-        user loop of validation.py:84-127 (candidates = all - history, chunked forward, cat, topk)."""
+        user loop of validation.py:84-127 (candidates = all - history, chunked forward, cat, topk).  precision: "auto"
+        (tensor-core path with its device-side accuracy gate where the shape has one, else FP32), "fp32", "tc_auto",
+        "tc_split", "tc_mix", "tc_fast" (ops.resolve_precision, include/nais_b200.h NAIS_PREC_*)."""
         if not isinstance(users, ops.DeviceUsers):
             users = self.make_users(*users)
         s, i = ops.fullrank_topk(self.variant, float(self.beta), self._params(), self._catalog, users, k, poi_begin,

@@ -251,6 +251,14 @@ def _structs(cat: DeviceCatalog, users: DeviceUsers):
 WORKSPACE_LIMIT_BYTES = 8 << 30  # user batches whose workspace would exceed this are scored in slices
 
 
+def resolve_precision(lib, p, precision: str) -> str:
+    """"auto" = the tensor-core path with its device-side MIX/SPLIT gate ("tc_auto") wherever the model shape has one
+    (one attention branch, D and hid up to 128 in steps of 16/32, lat/lon or no distance mode), else the FP32 kernel."""
+    if precision != "auto":
+        return precision
+    return "tc_auto" if lib.nais_fullrank_workspace_bytes(C.byref(p), 1, 1, 0, min(128, p.item_num), 1, PRECISIONS["tc_auto"]) else "fp32"
+
+
 def fullrank_topk(variant: str, beta: float, P: Dict[str, torch.Tensor], cat: DeviceCatalog, users: DeviceUsers, k: int,
                   poi_begin: int = 0, poi_end: Optional[int] = None, exclude_history: bool = True,
                   precision: str = "fp32") -> Tuple[torch.Tensor, torch.Tensor]:
@@ -261,6 +269,7 @@ def fullrank_topk(variant: str, beta: float, P: Dict[str, torch.Tensor], cat: De
     with torch.cuda.device(dev):
         p = build_params(variant, P, beta, keep)
         poi_end = p.item_num if poi_end is None else poi_end
+        precision = resolve_precision(lib, p, precision)
         prec = PRECISIONS[precision]
         ws_bytes = lib.nais_fullrank_workspace_bytes(C.byref(p), users.n_users, users.nnz, poi_begin, poi_end, k, prec)
         if ws_bytes > WORKSPACE_LIMIT_BYTES and users.host_offsets is not None and users.n_users > 1:
@@ -276,7 +285,24 @@ def fullrank_topk(variant: str, beta: float, P: Dict[str, torch.Tensor], cat: De
         _lib.check(lib.nais_fullrank_topk(C.byref(p), C.byref(c), C.byref(u), poi_begin, poi_end, k, int(exclude_history),
                                           prec, out_s.data_ptr(), out_i.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
                    "nais_fullrank_topk")
+        if precision != "fp32" and ws_bytes >= 128:
+            _LAST_TC_HEADER[0] = ws[64:128]  # device-side scales / precision gate of this call (read lazily, see below)
     return out_s, out_i
+
+
+_LAST_TC_HEADER: List[Optional[torch.Tensor]] = [None]
+
+
+def last_tc_choice() -> Optional[Dict[str, float]]:
+    """What the last tensor-path call decided on the device: `rho` (bound on the logit scale) and `use_mix` (1 = the
+    fp16 + e5m2-correction kernels ran under precision="tc_auto" for every user with at least `min_hist_for_mix` history
+    items, 0 = the three-pass fp16 split for everyone).  Synchronises."""
+    h = _LAST_TC_HEADER[0]
+    if h is None:
+        return None
+    host = h.cpu()
+    return {"rho": float(host[44:48].view(torch.float32).item()), "use_mix": int(host[48:52].view(torch.int32).item()),
+            "min_hist_for_mix": 16}  # kMixRhoMax = 256 / kMixMinHist = 16 in csrc/nais_tc.cu
 
 
 def fullrank_scores(variant: str, beta: float, P: Dict[str, torch.Tensor], cat: DeviceCatalog, users: DeviceUsers,
@@ -289,6 +315,7 @@ def fullrank_scores(variant: str, beta: float, P: Dict[str, torch.Tensor], cat: 
         p = build_params(variant, P, beta, keep)
         poi_end = p.item_num if poi_end is None else poi_end
         c, u = _structs(cat, users)
+        precision = resolve_precision(lib, p, precision)
         prec = PRECISIONS[precision]
         out = torch.empty(users.n_users, poi_end - poi_begin, device=dev, dtype=torch.float32)
         ws_bytes = lib.nais_fullrank_workspace_bytes(C.byref(p), users.n_users, users.nnz, poi_begin, poi_end, 1, prec)

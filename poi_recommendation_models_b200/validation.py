@@ -16,7 +16,7 @@ import torch
 from . import eval_metrics
 
 
-def _recommend(model, args, train_matrix, num_users, precision="fp32", user_batch=2048):
+def _recommend(model, args, train_matrix, num_users, precision="auto", user_batch=2048):
     csr = train_matrix.tocsr()
     csr.sort_indices()
     k = int(args.topk)
@@ -36,7 +36,7 @@ def _finish(recommended_list, test_positive, val_positive, k_list):
     return precision_v, recall_v, hit_v, precision_t, recall_t, hit_t
 
 
-def NAIS_validation(model, args, num_users, test_positive, val_positive, train_matrix, k_list, precision="fp32"):
+def NAIS_validation(model, args, num_users, test_positive, val_positive, train_matrix, k_list, precision="auto"):
     """validation.py:7-31."""
     model.eval()
     if model._catalog is None:
@@ -45,7 +45,7 @@ def NAIS_validation(model, args, num_users, test_positive, val_positive, train_m
 
 
 def NAIS_region_validation(model, args, num_users, test_positive, val_positive, train_matrix, businessRegionEmbedList,
-                           k_list, precision="fp32"):
+                           k_list, precision="auto"):
     """validation.py:34-59."""
     model.eval()
     model.set_catalog(region=businessRegionEmbedList)
@@ -53,7 +53,7 @@ def NAIS_region_validation(model, args, num_users, test_positive, val_positive, 
 
 
 def NAIS_region_distance_validation(model, args, num_users, test_positive, val_positive, train_matrix,
-                                    businessRegionEmbedList, place_coords, k_list, precision="fp32",
+                                    businessRegionEmbedList, place_coords, k_list, precision="auto",
                                     return_recommended=False):
     """validation.py:62-131."""
     model.eval()

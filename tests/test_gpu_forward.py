@@ -99,7 +99,7 @@ def _fullrank_case(variant, U, N, seed, D=64, hid=64, beta=0.5, **kw):
     return data, sd, m
 
 
-PREC_TOL = {"fp32": util.TOL, "tc_split": util.TOL, "tc_mix": util.TOL, "tc_fast": 5e-4}  # tc_fast: single-pass fp16 logits (documented)
+PREC_TOL = {"fp32": util.TOL, "tc_split": util.TOL, "tc_mix": util.TOL, "tc_auto": util.TOL, "tc_fast": 5e-4}  # tc_fast: single-pass fp16 logits (documented)
 
 
 @pytest.mark.parametrize("variant", ["region_distance", "region", "basic", "distance"])
@@ -132,7 +132,7 @@ def test_fullrank_disentangled_fused_haversine():
         m.predict_topk(users, 10, precision="tc_split")
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tc_split", "tc_mix"])
+@pytest.mark.parametrize("precision", ["fp32", "tc_split", "tc_mix", "tc_auto"])
 def test_fullrank_topk_matches_reference_validation_golden(precision):
     z = util.load_golden("validation_rd.npz")
     sd = util.golden_sd(z, "sd.")

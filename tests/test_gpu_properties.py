@@ -61,7 +61,7 @@ def test_duplicate_history_items_and_h1():
                                                   torch.from_numpy(aux), dtype=torch.float64)
     assert util.cond_err(s, ref.numpy(), scale.numpy()) < util.TOL
     m.set_catalog(region=region, coords=coords)
-    for prec in ("fp32", "tc_split", "tc_mix", "tc_fast"):
+    for prec in ("fp32", "tc_split", "tc_auto", "tc_fast"):  # (tc_mix alone is specified for H >= 16: tc_auto routes these to SPLIT)
         users = m.make_users(np.array([0, 6, 7]), np.array([5, 9, 5, 7, 9, 5, 42]))  # user 1 has H = 1
         got = ops.fullrank_scores("region_distance", 0.5, m._params(), m._catalog, users, precision=prec).cpu().numpy()
         for u, h in enumerate(([5, 9, 5, 7, 9, 5], [42])):
@@ -219,3 +219,52 @@ def test_predict_topk_slices_huge_batches(monkeypatch):
     monkeypatch.setattr(ops, "WORKSPACE_LIMIT_BYTES", 8 << 20)
     sliced = ops.fullrank_topk("region_distance", 0.5, m._params(), m._catalog, users, 10, precision="tc_split")
     assert torch.equal(full[0], sliced[0]) and torch.equal(full[1], sliced[1])
+
+
+def test_tc_auto_gate_per_user_and_weight_scale():
+    """precision="tc_auto": a user takes the fp16 + e5m2-correction kernels (MIX) when the device-side bound
+    rho = max|p| * max|B| * sqrt(hid * D) is <= 256 AND the history has >= 16 items (MIX's per-term error averages out over
+    the history), else the three-pass fp16 split.  Each user's row is bit-identical to calling that mode directly, and
+    within tolerance of the float64 oracle; beyond the bound everything falls back to SPLIT."""
+    N = 600
+    lens = [3, 40, 15, 16, 2, 33]  # (H = 1 is covered by test_duplicate_history_items_and_h1; there |S| itself cancels over d)
+    U = len(lens)
+    rng = np.random.default_rng(5)
+    indptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    indices = np.concatenate([rng.choice(N, n, replace=False) for n in lens]).astype(np.int64)
+    coords, region, R = synthetic.make_catalog(N, seed=21)
+    sd = orc.init_state("region_distance", N, 64, 64, R, 1, seed=4, style="trained")
+
+    def run(sd_):
+        m = util.make_model("region_distance", sd_, 0.5)
+        m.set_catalog(region=region, coords=coords)
+        users = m.make_users(indptr, indices)
+        out = {p: ops.fullrank_scores("region_distance", 0.5, m._params(), m._catalog, users, precision=p).cpu().numpy()
+               for p in ("tc_split", "tc_mix")}
+        s_auto, i_auto = ops.fullrank_topk("region_distance", 0.5, m._params(), m._catalog, users, 10, precision="tc_auto")
+        choice = ops.last_tc_choice()
+        out["tc_auto"] = ops.fullrank_scores("region_distance", 0.5, m._params(), m._catalog, users, precision="tc_auto").cpu().numpy()
+        tk = {p: ops.fullrank_topk("region_distance", 0.5, m._params(), m._catalog, users, 10, precision=p) for p in ("tc_split", "tc_mix")}
+        err = 0.0
+        for u in range(U):
+            same = "tc_mix" if choice["use_mix"] and lens[u] >= choice["min_hist_for_mix"] else "tc_split"
+            assert np.array_equal(out["tc_auto"][u], out[same][u], equal_nan=True), (u, same)
+            assert torch.equal(i_auto[u], tk[same][1][u]) and torch.equal(s_auto[u], tk[same][0][u]), (u, same)
+            hist = indices[indptr[u]:indptr[u + 1]]
+            ref, scale = util.oracle_user_scores(sd_, "region_distance", 0.5, coords, region, hist, np.arange(N))
+            ok = ~np.isnan(ref)
+            err = max(err, util.cond_err(out["tc_auto"][u][ok], ref[ok], scale[ok]))
+        return choice, err
+
+    choice, err = run(sd)
+    assert choice["use_mix"] == 1 and choice["rho"] < 256 and choice["min_hist_for_mix"] == 16, choice
+    assert err < util.TOL, err
+    big = {k: v.clone() for k, v in sd.items()}
+    for k in big:
+        if k.startswith("embed_"):
+            big[k] = big[k] * (1.0 / 0.3)          # embedding std 1.0
+    big["attn_layer1.weight"] = big["attn_layer1.weight"] * 5
+    big["attn_layer2.weight"] = big["attn_layer2.weight"] * 5
+    choice, err = run(big)
+    assert choice["use_mix"] == 0 and choice["rho"] > 256, choice
+    assert err < util.TOL, err
