@@ -1,12 +1,23 @@
-"""CPU emulation (numpy float16 rounding, float32 accumulation) of the tensor path's arithmetic: single-pass fp16 (x1), single-pass
-main rows with split S/L rows (x1sl = NAIS_PREC_TC_FAST) and the three-pass hi/lo split (x3 = NAIS_PREC_TC_SPLIT), against the
-float64 oracle, at several weight scales.  This is the study behind the precision scheme in DESIGN.md section 3."""
+"""CPU emulation (numpy float16 / torch float8 rounding, float32 accumulation) of the tensor path's arithmetic against the
+float64 oracle, at several weight scales and history lengths.  This is the study behind the precision scheme in DESIGN.md
+section 3:
+  x3    = NAIS_PREC_TC_SPLIT  three fp16 passes hi*hi + hi*lo + lo*hi
+  mix55 = NAIS_PREC_TC_MIX    fp16 hi*hi + two e5m2 correction passes e5m2(hi)*e5m2(lo) + e5m2(lo)*e5m2(hi); the ext K-step
+                              (distance lanes, bias) keeps a full hi/lo split inside its 16 K slots
+and behind the NAIS_PREC_TC_AUTO gate: rho = max|p| * max|B| * sqrt(hid * D) <= 256 and history length >= 16.
+(`ref32` is the reference's own fp32-vs-fp64 gap on the same conditioned measure.)"""
 import numpy as np, torch, sys
-sys.path.insert(0,'.')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import nais_oracle as orc
 from poi_recommendation_models_b200 import synthetic
 def split16(x):
     hi = x.astype(np.float16); lo = (x - hi.astype(np.float32)).astype(np.float16); return hi, lo
+def r8(x, fmt, s=1.0):
+    t = torch.from_numpy(np.ascontiguousarray(x.astype(np.float32)*np.float32(s)))
+    dt = torch.float8_e5m2 if fmt=='e5m2' else torch.float8_e4m3fn
+    if fmt=='e4m3': t = t.clamp(-448,448)
+    return (t.to(dt).to(torch.float32).numpy()/np.float32(s)).astype(np.float32)
 def p2floor(x): return 2.0**np.floor(np.log2(x))
 def run(style, N=2000, D=64, hid=64, H=64, B=256, seed=0, emb_std=None, wscale=1.0):
     rng=np.random.default_rng(seed)
@@ -23,44 +34,60 @@ def run(style, N=2000, D=64, hid=64, H=64, B=256, seed=0, emb_std=None, wscale=1
     ref32 = orc.attention_network(sd,"region_distance",0.5,t(hist),t(tgt),t(region[hist]),t(region[tgt]),t(aux),dtype=torch.float32).numpy()
     ref=ref.numpy(); scale=scale.numpy()
     P={k:v.numpy().astype(np.float32) for k,v in sd.items()}
-    q = np.concatenate([P['embed_history.weight'][hist], P['embed_region.weight'][region[hist]]],-1)  # B,H,D
-    p = np.concatenate([P['embed_target.weight'][tgt], P['embed_region.weight'][region[tgt]]],-1)   # B,D
+    q = np.concatenate([P['embed_history.weight'][hist], P['embed_region.weight'][region[hist]]],-1)
+    p = np.concatenate([P['embed_target.weight'][tgt], P['embed_region.weight'][region[tgt]]],-1)
     W=P['attn_layer1.weight']; b=P['attn_layer1.bias']; v=P['attn_layer2.weight'][0]
     Wd=P['dist_layer.weight']; bd=P['dist_layer.bias']
-    z = (aux*np.float32(100.0))@Wd.T + bd; g = (1/(1+np.exp(-z))).astype(np.float32)  # B,H,2
+    z = (aux*np.float32(100.0))@Wd.T + bd; g = (1/(1+np.exp(-z))).astype(np.float32)
     c = 0.5*np.abs(v); sign=np.sign(v)
     maxP=np.abs(p).max(); maxQ=np.abs(q).max(); CW = c[:,None]*W[:,:D]; u=(sign[:,None]*CW).sum(0)
     maxB = maxQ*max(np.abs(CW).max(), np.abs(u).max())
     sA=p2floor(512/maxP); sS=p2floor(512/maxQ); sB=p2floor(512/maxB); sig=sA*sB; sAe=256.0; sBe=sig/sAe
-    ext_main = np.concatenate([c[:,None]*W[:,D:], (c*b)[:,None]],1)  # hid,3
+    ext_main = np.concatenate([c[:,None]*W[:,D:], (c*b)[:,None]],1)
     ext_L = (sign[:,None]*ext_main).sum(0)
     maxBe=max(np.abs(ext_main).max(), np.abs(ext_L).max())
     while maxBe*sBe > 2**14: sB/=2; sig=sA*sB; sBe=sig/sAe
     out={}
-    for mode in ('x1','x1sl','x3'):
-        # A: [B, D+3] per (b,h): p*sA, g*sAe, 1*sAe ; Bop: per (b,h): rows hid+2, cols D+3
+    f=lambda a:a.astype(np.float32)
+    for mode in ('x3','mix55'):
         A_x = (p*sA).astype(np.float32); A_e = np.concatenate([g*sAe, np.full(g.shape[:2]+(1,),sAe,np.float32)],-1)
-        Bx_main = (CW[None,None]*q[:,:,None,:]*sB).astype(np.float32)   # B,H,hid,D
-        Bx_L = (u[None,None]*q*sB).astype(np.float32)                    # B,H,D
+        Bx_main = (CW[None,None]*q[:,:,None,:]*sB).astype(np.float32)
+        Bx_L = (u[None,None]*q*sB).astype(np.float32)
         Bx_S = (q*sS).astype(np.float32)
         Be_main=(ext_main*sBe).astype(np.float32); Be_L=(ext_L*sBe).astype(np.float32)
-        def mm(Ah,Al,Bh,Bl,eq,aux=False):
-            f=lambda a:a.astype(np.float32)
+        def mm(Ah,Al,Bh,Bl,eq,aux=False,ext=False):
             r = np.einsum(eq,f(Ah),f(Bh))
-            if mode=='x3' or (mode=='x1sl' and aux): r = r + np.einsum(eq,f(Ah),f(Bl)) + np.einsum(eq,f(Al),f(Bh))
+            if mode=='x3' or ext or ((mode=='x1sl' or mode.endswith('sl')) and aux):
+                r = r + np.einsum(eq,f(Ah),f(Bl)) + np.einsum(eq,f(Al),f(Bh))
+            elif mode.startswith('mix'):
+                fh = 'e5m2' if mode[3]=='5' else 'e4m3'; fl = 'e5m2' if mode[4]=='5' else 'e4m3'
+                # hi factor scale: bring max 512 -> 256 for e4m3 ; lo factor: max ~0.25 -> scale 2^9 for e4m3
+                sh = 2.0**-9 if fh=='e4m3' else 1.0; sl = 512.0 if fl=='e4m3' else 1.0
+                r = r + np.einsum(eq,r8(f(Ah),fh,sh),r8(f(Bl),fl,sl)) + np.einsum(eq,r8(f(Al),fl,sl),r8(f(Bh),fh,sh))
             return r.astype(np.float32)
         Axh,Axl=split16(A_x); Aeh,Ael=split16(A_e)
         Bmh,Bml=split16(Bx_main); BLh,BLl=split16(Bx_L); BSh,BSl=split16(Bx_S); Bemh,Beml=split16(Be_main); BeLh,BeLl=split16(Be_L)
-        tmain = mm(Axh,Axl,Bmh,Bml,'bd,bhkd->bhk') + mm(Aeh,Ael,Bemh,Beml,'bhe,ke->bhk')
-        L = mm(Axh,Axl,BLh,BLl,'bd,bhd->bh',True) + mm(Aeh,Ael,BeLh,BeLl,'bhe,e->bh',True)
+        extsplit = mode.startswith('mix')
+        tmain = mm(Axh,Axl,Bmh,Bml,'bd,bhkd->bhk') + mm(Aeh,Ael,Bemh,Beml,'bhe,ke->bhk',ext=extsplit)
+        L = mm(Axh,Axl,BLh,BLl,'bd,bhd->bh',True) + mm(Aeh,Ael,BeLh,BeLl,'bhe,e->bh',True,ext=extsplit)
         S = mm(Axh,Axl,BSh,BSl,'bd,bhd->bh',True)
         acc = (np.abs(tmain)*sign[None,None]).sum(-1,dtype=np.float32)
         a = ((L+acc)*np.float32(1/sig)).astype(np.float32); s=(S*np.float32(1/(sA*sS))).astype(np.float32)
         e = np.exp(a)*(hist!=tgt[:,None]); 
         score = (e*s).sum(-1,dtype=np.float32)/np.sqrt(e.sum(-1,dtype=np.float32))
-        out[mode]=np.max(np.abs(score-ref)/np.maximum(np.abs(ref),scale))
-    out['ref32']=np.max(np.abs(ref32-ref)/np.maximum(np.abs(ref),scale))
-    a64 = None
+        out[mode]=float(np.max(np.abs(score-ref)/np.maximum(np.abs(ref),scale)))
+    out['rho']=float(maxP*maxB*np.sqrt(hid*D)); out['amax']=float(np.abs(a).max())
+    out['ref32']=float(np.max(np.abs(ref32-ref)/np.maximum(np.abs(ref),scale)))
     return out
-for style,es,ws in [('reference',None,1),('trained',None,1),('trained',1.0,1),('trained',0.3,4.0),('trained',1.0,4.0)]:
-    print(style,es,ws, run(style,emb_std=es,wscale=ws))
+
+
+if __name__ == "__main__":
+    print("# weight scale sweep (H = 64): MIX error against the gate variable rho")
+    for style, es, ws in [('reference', None, 1), ('trained', 0.3, 1), ('trained', 0.3, 4), ('trained', 0.3, 8), ('trained', 0.6, 4),
+                          ('trained', 1.0, 1), ('trained', 1.0, 2), ('trained', 1.0, 4)]:
+        o = run(style, emb_std=es, wscale=ws, B=128)
+        print(style, es, ws, {k: f"{v:.2e}" for k, v in o.items()})
+    print("# history length sweep (trained-like weights, worst case over 2000 candidates)")
+    for H in (1, 2, 6, 16, 64):
+        o = run('trained', H=H, B=2000)
+        print(H, {k: f"{v:.2e}" for k, v in o.items()})
