@@ -11,8 +11,10 @@ synthetic catalogue of the workload:
     C4            Yelp-scale:     100,000 users x 1,000,000 POIs, history 128, D = hid = 64, top-20
 
 Successive steps take successive user batches (wrapping around).  With N > 1 GPUs the catalogue is range-sharded
-across ranks, every rank scores the same user batch against its shard, the per-shard top-k lists are all-gathered
-over NCCL and merged on device (north_star); total work per step is fixed -> "scaling": "strong".
+across ranks as far as a shard keeps >= 32k POIs (C4: 8 shards, as north_star / SURVEY.md §8e prescribe) and the user
+batch is sliced across the remaining factor (C2's 40k POIs: user slices only; `distributed.grid_shape`); the per-rank
+top-k lists are all-gathered over NCCL and, with > 1 shard, merged on device; total work per step is fixed ->
+"scaling": "strong".
 
 value   users/s with inputs resident in HBM (pair-scores/s = users/s x POIs is reported alongside)
 e2e     the same metric through the drop-in API (`model.predict_topk` on host CSR arrays): pinned host -> device
@@ -364,7 +366,8 @@ def main():
         choice = ops.last_tc_choice()
         eff = "tc_mix" if choice and choice["use_mix"] else "tc_split"
     if rank == 0:
-        cells_per_launch = ups * H * ((N + world - 1) // world)
+        u0_, u1_, _ = ranker.user_range(ups)
+        cells_per_launch = (u1_ - u0_) * H * (ranker.hi - ranker.lo)  # rank 0's launch: its user slice x its catalogue range
         F = flops_per_cell(D, hid)
         ach = cells_per_launch * F / (kern_ms / 1000.0) / 1e12 if kern_ms else None
         peak = peaks["tf_sust"]
@@ -377,7 +380,7 @@ def main():
                 "config": {"workload": f"{args.config}: {cfg['desc']}", "users_per_step": ups, "precision": args.precision,
                            "precision_effective": eff, "tc_auto_gate": choice,
                            "l2": "flushed between timed steps (256 MiB write)", "weights": "random init, trained-like scale",
-                           "parallelism": f"catalogue range shards x{world} + all-gather top-k merge" if world > 1 else "single GPU"},
+                           "parallelism": ranker.parallelism if world > 1 else "single GPU"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_users_per_s, "unit": "users/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
@@ -408,7 +411,7 @@ def main():
                 line["roofline"]["traffic"] = t["dram_bytes_per_user"] * ups + t.get("dram_bytes_const", 0)
                 line["roofline"]["traffic_source"] = t["source"]
         # algorithmic HBM bytes of the launch: catalogue rows + history items + output
-        alg_bytes = ((N + world - 1) // world) * (D // 2 * 4 + 4 + 8) + ups * H * (4 + D // 2 * 4 + 4 + 8) + ups * k * 8
+        alg_bytes = (ranker.hi - ranker.lo) * (D // 2 * 4 + 4 + 8) + (u1_ - u0_) * H * (4 + D // 2 * 4 + 4 + 8) + (u1_ - u0_) * k * 8
         if kern_ms:
             line["roofline"]["hbm_frac"] = alg_bytes / (kern_ms / 1000.0) / 1e9 / peaks["hbm"]
         if not args.no_cpu_baseline and world == 1:

@@ -1,9 +1,9 @@
 """Multi-GPU plumbing for full-rank evaluation (one process per GPU, `torch.distributed`).
 
 The (user, candidate) pairs are independent — the beta-softmax normalises over the user's *history*, not over
-candidates — so the catalogue is split into `world` contiguous POI ranges; each rank scores every user
-of the batch against its own range with the fused kernel, keeps a local top-k, and ONE collective per user batch
-exchanges the lists: an all-gather of [U,k] (fp32 score, int32 global id) = U*k*8*world bytes per rank, followed by an
+candidates — so the catalogue is split into contiguous POI ranges (and, when the catalogue is too small
+for `world` useful shards, the user batch into slices: `grid_shape`); each rank scores its users against its own range
+with the fused kernel, keeps a local top-k, and ONE collective per user batch exchanges the lists: an all-gather of [U,k] (fp32 score, int32 global id) = U*k*8*world bytes per rank, followed by an
 on-device merge (`nais_topk_merge`, same order rule as the single-GPU top-k, so results are identical to one GPU).
 
 The reference has no distributed code at all; this module is new.
@@ -39,17 +39,33 @@ def gather_lists(score: torch.Tensor, ids: torch.Tensor, world: int) -> Tuple[to
     return gs.permute(1, 0, 2).contiguous(), gi.permute(1, 0, 2).contiguous()
 
 
+def grid_shape(n_items: int, world: int, min_shard_pois: int) -> Tuple[int, int]:
+    """(catalogue shards, user slices) with shards * slices == world: the catalogue is split as far as every shard keeps
+    at least `min_shard_pois` POIs, the remaining factor splits the users of a batch.  A rank packs the operand image of
+    every user it scores, whatever its catalogue range is, so thin shards pay that cost `world` times (C2's 40k POIs on 8
+    GPUs: 12 % of a step); a 1M-POI catalogue is sharded 8 ways as SURVEY.md §8e prescribes."""
+    gc = 1
+    for d in range(1, world + 1):
+        if world % d == 0 and (d == 1 or n_items // d >= min_shard_pois):
+            gc = d
+    return gc, world // gc
+
+
 class ShardedRanker:
-    """predict_topk over a range-sharded catalogue.  `local_topk` / `merge` are injectable so the host-side logic can
-    be exercised with the gloo backend on CPU (tests/test_distributed_cpu.py); the defaults are the CUDA ops."""
+    """predict_topk over a range-sharded catalogue (x user-sliced batches when the catalogue is small, `grid_shape`).
+    `local_topk` / `merge` / `slice_users` are injectable so the host-side logic can be exercised with the gloo backend on
+    CPU (tests/test_distributed_cpu.py); the defaults are the CUDA ops.  rank = user_slice * catalogue_shards + shard."""
 
     def __init__(self, model, rank: int = 0, world: int = 1, local_topk: Optional[Callable] = None,
-                 merge: Optional[Callable] = None):
+                 merge: Optional[Callable] = None, min_shard_pois: int = 32768, slice_users: Optional[Callable] = None):
         self.model, self.rank, self.world = model, rank, world
         self.n = model.item_num
-        self.lo, self.hi = shard_range(self.n, rank, world)
+        self.gc, self.gu = grid_shape(self.n, world, min_shard_pois)
+        self.rc, self.ru = rank % self.gc, rank // self.gc
+        self.lo, self.hi = shard_range(self.n, self.rc, self.gc)
         self._local = local_topk or self._cuda_local
         self._merge = merge or ops.topk_merge
+        self._slice = slice_users or (lambda users, u0, u1: users.slice(u0, u1))
         self.events = []
 
     def _cuda_local(self, users, k, lo, hi, precision):
@@ -60,6 +76,11 @@ class ShardedRanker:
         return {"fp32": "fullrank_fp32_kernel"}.get(precision, "fullrank_tc_kernel")
 
     @property
+    def parallelism(self) -> str:
+        return f"{self.gc} catalogue range shard(s) x {self.gu} user slice(s), all-gather of the top-k lists" + (
+            " + on-device merge" if self.gc > 1 else "")
+
+    @property
     def last_kernel_ms(self) -> Optional[float]:
         if not self.events:
             return None
@@ -67,8 +88,16 @@ class ShardedRanker:
         b.synchronize()
         return a.elapsed_time(b)
 
-    def topk(self, users, k: int, precision: str = "auto"):
-        timed = torch.cuda.is_available() and users.offsets.is_cuda
+    def user_range(self, n_users: int) -> Tuple[int, int, int]:
+        """(u0, u1, per): this rank scores users [u0, u1) of a batch; every slice is padded to `per` rows for the gather."""
+        per = (n_users + self.gu - 1) // self.gu
+        u0 = min(n_users, self.ru * per)
+        return u0, min(n_users, u0 + per), per
+
+    def _score_and_exchange(self, users, n_users: int, k: int, precision: str, timed: bool):
+        """`users` = this rank's slice.  Local fused scoring + top-k, then ONE all-gather of the lists and (catalogue
+        shards > 1) the on-device merge; every rank returns the lists of the whole batch [n_users, k]."""
+        u0, u1, per = self.user_range(n_users)
         if timed:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
@@ -76,23 +105,41 @@ class ShardedRanker:
         if timed:
             b.record()
             self.events = [(a, b)]
-        if self.world > 1:
-            gs, gi = gather_lists(s, i, self.world)
-            s, i = self._merge(gs, gi)
-        return s, i
+        if self.world == 1:
+            return s, i
+        if s.shape[0] < per:  # last slice: pad with "no entry" rows
+            s = torch.cat([s, s.new_full((per - s.shape[0], k), float("-inf"))])
+            i = torch.cat([i, i.new_full((per - i.shape[0], k), -1)])
+        gs, gi = gather_lists(s, i, self.world)                      # [per, world, k], rank-major along dim 1
+        gs = gs.view(per, self.gu, self.gc, k).permute(1, 0, 2, 3).reshape(self.gu * per, self.gc, k)[:n_users]
+        gi = gi.view(per, self.gu, self.gc, k).permute(1, 0, 2, 3).reshape(self.gu * per, self.gc, k)[:n_users]
+        if self.gc == 1:
+            return gs[:, 0].contiguous(), gi[:, 0].contiguous()
+        return self._merge(gs.contiguous(), gi.contiguous())
+
+    def topk(self, users, k: int, precision: str = "auto"):
+        """`users`: the whole batch (DeviceUsers), resident on every rank."""
+        timed = torch.cuda.is_available() and users.offsets.is_cuda
+        n_users = getattr(users, "n_users", None)
+        if self.gu > 1:
+            u0, u1, _ = self.user_range(n_users)
+            users = self._slice(users, u0, u1)
+        return self._score_and_exchange(users, n_users, k, precision, timed)
 
     def topk_host(self, indptr: torch.Tensor, items: torch.Tensor, k: int, precision: str = "auto"):
-        """End-to-end call: pinned host CSR -> device, rank, top-k lists back on the host (sigmoid scores like
-        `forward`, int64 ids)."""
+        """End-to-end call: pinned host CSR -> device (only this rank's user slice), rank, top-k lists of the whole batch
+        back on the host (sigmoid scores like `forward`, int64 ids)."""
         m = self.model
         dev = next(m.parameters()).device
-        ip = indptr.to(dev, non_blocking=True)
-        it = items.to(dev, non_blocking=True)
+        n_users = indptr.numel() - 1
+        u0, u1, _ = self.user_range(n_users)
+        a, b = int(indptr[u0]), int(indptr[u1])
+        ip = indptr[u0:u1 + 1].to(dev, non_blocking=True) - a
+        it = items[a:b].to(dev, non_blocking=True)
         cat = m._catalog
         users = ops.DeviceUsers(ip, it.to(torch.int32), cat.region[it] if cat.region is not None else None,
-                                cat.coords[it].contiguous() if cat.coords is not None else None,
-                                indptr.numel() - 1, items.numel())
-        s, i = self.topk(users, k, precision)
+                                cat.coords[it].contiguous() if cat.coords is not None else None, u1 - u0, b - a)
+        s, i = self._score_and_exchange(users, n_users, k, precision, True)
         s_h = torch.sigmoid(s).to("cpu", non_blocking=True)
         i_h = i.to(torch.int64).to("cpu", non_blocking=True)
         torch.cuda.current_stream().synchronize()

@@ -1,5 +1,5 @@
-"""World-size-2 gloo test (CPU) of the multi-GPU host logic: range sharding of the catalogue, all-gather layout of the
-per-shard top-k lists and the merge order rule — with the CUDA ops replaced by injected oracle-backed stand-ins (the
+"""World-size-2 / 4 gloo tests (CPU) of the multi-GPU host logic: range sharding of the catalogue, user slicing of the
+batch, all-gather layout of the per-rank top-k lists and the merge order rule — with the CUDA ops replaced by injected oracle-backed stand-ins (the
 product has no CPU path; only the plumbing in poi_recommendation_models_b200/distributed.py runs here)."""
 import os
 import socket
@@ -34,61 +34,94 @@ def _merge_ref(gs, gi):
     return torch.from_numpy(out_s), torch.from_numpy(out_i)
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, min_shard, want_grid):
     try:
-        _worker_body(rank, world, port, q)
+        _worker_body(rank, world, port, q, min_shard, want_grid)
     except Exception:  # surface the traceback in the parent
         import traceback
         q.put((rank, traceback.format_exc()))
 
 
-def _worker_body(rank, world, port, q):
+def _worker_body(rank, world, port, q, min_shard, want_grid):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from types import SimpleNamespace
-    from poi_recommendation_models_b200.distributed import ShardedRanker, allreduce_gradients
-    N, U, k = 1000, 6, 20
+    from poi_recommendation_models_b200.distributed import ShardedRanker, allreduce_gradients, shard_range
+    N, U, k = 1000, 7, 20  # 7 users: the last user slice is ragged and gets padded for the gather
     rng = np.random.default_rng(0)  # same scores on every rank
     scores = rng.normal(size=(U, N)).astype(np.float32)
     scores[:, ::7] = scores[:, 3:4]  # ties across shards: the id rule must break them identically
 
     def local_topk(users, kk, lo, hi, precision):
-        s = torch.from_numpy(scores[:, lo:hi])
+        rows = users.ids
         kk2 = min(kk, hi - lo)
-        out_s, out_i = torch.full((U, kk), -float("inf")), torch.full((U, kk), -1, dtype=torch.int32)
-        for u in range(U):
-            order = np.lexsort((np.arange(lo, hi), -s[u].numpy()))[:kk2]
-            out_s[u, :kk2], out_i[u, :kk2] = s[u][order], torch.from_numpy((order + lo).astype(np.int32))
+        out_s, out_i = torch.full((len(rows), kk), -float("inf")), torch.full((len(rows), kk), -1, dtype=torch.int32)
+        for j, u in enumerate(rows):
+            s = scores[u, lo:hi]
+            order = np.lexsort((np.arange(lo, hi), -s))[:kk2]
+            out_s[j, :kk2], out_i[j, :kk2] = torch.from_numpy(s[order]), torch.from_numpy((order + lo).astype(np.int32))
         return out_s, out_i
 
+    def slice_users(users, u0, u1):
+        return SimpleNamespace(offsets=users.offsets, n_users=u1 - u0, ids=users.ids[u0:u1])
+
     model = SimpleNamespace(item_num=N)
-    r = ShardedRanker(model, rank, world, local_topk=local_topk, merge=_merge_ref)
-    users = SimpleNamespace(offsets=torch.zeros(1))
+    r = ShardedRanker(model, rank, world, local_topk=local_topk, merge=_merge_ref, min_shard_pois=min_shard, slice_users=slice_users)
+    users = SimpleNamespace(offsets=torch.zeros(1), n_users=U, ids=np.arange(U))
     s, i = r.topk(users, k)
     ref_order = [np.lexsort((np.arange(N), -scores[u]))[:k] for u in range(U)]
-    ok = all(np.array_equal(i[u].numpy(), ref_order[u].astype(np.int32)) for u in range(U))
+    ok = s.shape == (U, k) and i.shape == (U, k)
+    ok = ok and all(np.array_equal(i[u].numpy(), ref_order[u].astype(np.int32)) for u in range(U))
     ok = ok and all(np.array_equal(s[u].numpy(), scores[u][ref_order[u]]) for u in range(U))
-    ok = ok and (r.lo, r.hi) == ((0, 512) if rank == 0 else (512, 1000))
+    ok = ok and (r.gc, r.gu) == want_grid and (r.lo, r.hi) == shard_range(N, rank % r.gc, r.gc)
+    if want_grid == (2, 1):
+        ok = ok and (r.lo, r.hi) == ((0, 512) if rank == 0 else (512, 1000))
     # data-parallel gradient averaging
     lin = torch.nn.Linear(4, 3)
     for p_ in lin.parameters():
         p_.grad = torch.full_like(p_, float(rank + 1))
     allreduce_gradients(lin, world)
-    ok = ok and all(torch.allclose(p_.grad, torch.full_like(p_, 1.5)) for p_ in lin.parameters())
+    mean = (world + 1) / 2.0
+    ok = ok and all(torch.allclose(p_.grad, torch.full_like(p_, mean)) for p_ in lin.parameters())
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
 
-def test_sharded_ranker_world2_gloo():
+def _run(world, min_shard, want_grid):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, min_shard, want_grid)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in range(2)]
+    res = [q.get(timeout=180) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
-    assert sorted(res) == [(0, True), (1, True)]
+    assert sorted(res) == [(r, True) for r in range(world)], res
+
+
+def test_sharded_ranker_world2_gloo():
+    """two catalogue range shards (the layout SURVEY.md §8e prescribes)"""
+    _run(2, 0, (2, 1))
+
+
+def test_user_sliced_ranker_world2_gloo():
+    """catalogue too small for two useful shards: the user batch is sliced instead (ragged last slice)"""
+    _run(2, 32768, (1, 2))
+
+
+def test_grid_ranker_world4_gloo():
+    """2 catalogue shards x 2 user slices"""
+    _run(4, 400, (2, 2))
+
+
+def test_grid_shape():
+    sys.path.insert(0, ROOT)
+    from poi_recommendation_models_b200.distributed import grid_shape
+    assert grid_shape(40000, 8, 32768) == (1, 8)       # C2: user slices only
+    assert grid_shape(1000000, 8, 32768) == (8, 1)     # C4: catalogue shards only
+    assert grid_shape(100000, 8, 32768) == (2, 4)
+    assert grid_shape(40000, 1, 32768) == (1, 1)
+    assert grid_shape(1000000, 6, 32768) == (6, 1)
