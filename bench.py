@@ -227,6 +227,50 @@ def run_train(args, dev, lib, peaks, rank, world):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    # the whole reference step (run.py:248-254: zero_grad, forward, BCELoss, backward, Adagrad.step) on 8192 pairs:
+    # dense torch.optim.Adagrad over the [N, D/2] tables vs the row-sparse Adagrad fused into the segment reduce (f2),
+    # at C3's catalogue (40k POIs: 5 MB tables) and at C4's (1M POIs: 128 MB tables, where the dense step is HBM traffic)
+    full = None
+    if world == 1:
+        full = {"note": "8192 pairs, BCE, lr 0.01: whole optimizer step; the fused variant touches only the rows in the batch"}
+        for n_big in (N, 1000000):
+            if n_big == N:
+                h2, t2, hr2, tr2, ll2, R2 = hist, tgt, hreg, treg, ll, R
+            else:
+                c2np, r2np, R2 = synthetic.make_catalog(n_big, seed=0)
+                hn = synth_histories(T, n_big, H, seed=5)
+                h2 = torch.from_numpy(np.concatenate([hn, hn])).to(dev)
+                t2 = torch.from_numpy(np.concatenate([hn[:, 0], (hn[:, 1] + 1) % n_big])).to(dev)
+                r2, c2 = torch.from_numpy(r2np).to(dev), torch.from_numpy(c2np).to(dev)
+                ll2 = (c2[t2][:, None, :] - c2[h2]).abs().float().contiguous()
+                hr2, tr2 = r2[h2], r2[t2]
+            label = torch.cat([torch.ones(T), torch.zeros(T)]).to(dev)
+            for kind in ("dense_adagrad", "fused_sparse_adagrad"):
+                torch.manual_seed(2)
+                m2 = M.NAIS_region_distance_Embedding(n_big, D, hid, BETA, R2, 1).to(dev).train()
+                opt = torch.optim.Adagrad(m2.parameters(), lr=0.01, weight_decay=0.0)
+
+                def full_step():
+                    if kind == "dense_adagrad":
+                        opt.zero_grad()
+                        ls_ = m2.loss_func(m2(h2, t2, hr2, tr2, ll2), label)
+                        ls_.backward()
+                        opt.step()
+                        return ls_.detach()
+                    return m2.fused_adagrad_step(opt, label, h2, t2, hr2, tr2, ll2)
+
+                for _ in range(args.warmup):
+                    full_step()
+                torch.cuda.synchronize()
+                a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a2.record()
+                for _ in range(args.steps):
+                    ls = full_step()
+                b2.record()
+                torch.cuda.synchronize()
+                full[f"{kind}_ms_N{n_big}"] = a2.elapsed_time(b2) / args.steps
+                full[f"{kind}_loss_N{n_big}"] = float(ls)
+                del m2, opt
     if rank == 0:
         cells = 2 * T * H
         F = flops_per_cell(D, hid)
@@ -235,7 +279,7 @@ def run_train(args, dev, lib, peaks, rank, world):
                           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                           "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
                           "config": {"workload": "C3: 4096 (user,pos,neg) triples, H=128, D=hid=64, fwd+bwd (FP32 kernels)"},
-                          "gpu_launches": int(lib.nais_launch_count() - l0), "loss": float(loss),
+                          "gpu_launches": int(lib.nais_launch_count() - l0), "loss": float(loss.detach()), "full_step": full,
                           "roofline": {"bound": "fp32-ffma", "achieved": tf, "unit": "TFLOP/s",
                                        "note": "algorithmic 4F per cell; CUDA-core path (tensor-core backward is next-round work)"}}), flush=True)
 

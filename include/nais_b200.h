@@ -157,6 +157,23 @@ NAIS_API int nais_pairs_backward(const NaisParams* p, const NaisPairs* batch, co
                         const float* dscore, const NaisGrads* grads, void* workspace, size_t workspace_bytes,
                         nais_stream_t stream);
 
+/* Row-sparse Adagrad fused into the embedding-gradient segment reduce.  Replaces, for the embedding tables, the dense
+ * `embedding_dense_backward` + `torch.optim.Adagrad.step()` of run.py:225,252-254 (weight_decay = 0, lr_decay = 0: a row
+ * whose gradient is zero does not move, so stepping only the touched rows IS the dense step).  For every table with a
+ * non-NULL `sum_*` pointer (the optimizer's `state['sum']`, same shape as the table) the summed row gradient g is applied
+ * in place instead of being written to NaisGrads:  sum += g*g ;  param -= lr * g / (sqrt(sum) + eps).  The parameter
+ * tables are the ones NaisParams points to (they ARE written).  One branch only. */
+typedef struct NaisAdagrad {
+  float lr, eps;
+  float* sum_hist_poi[2];
+  float* sum_tgt_poi[2];
+  float* sum_reg[2];
+} NaisAdagrad;
+/* Same as nais_pairs_backward (MLP / dist-layer gradients go to `grads`; table pointers in `grads` may be NULL). */
+NAIS_API int nais_pairs_backward_adagrad(const NaisParams* p, const NaisPairs* batch, const float* score_parts,
+                                const float* row_sum, const float* dscore, const NaisGrads* grads, const NaisAdagrad* opt,
+                                void* workspace, size_t workspace_bytes, nais_stream_t stream);
+
 /* Workspace for nais_fullrank_topk / nais_fullrank_scores: n_users and nnz = offsets[n_users] are host-known. */
 NAIS_API size_t nais_fullrank_workspace_bytes(const NaisParams* p, int32_t n_users, int64_t nnz, int64_t poi_begin,
                                      int64_t poi_end, int32_t k, int32_t precision);

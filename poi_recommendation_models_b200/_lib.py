@@ -39,6 +39,11 @@ class NaisGrads(C.Structure):
                 ("dist_b", C.c_void_p), ("dist_embed", C.c_void_p)]
 
 
+class NaisAdagrad(C.Structure):
+    _fields_ = [("lr", C.c_float), ("eps", C.c_float), ("sum_hist_poi", C.c_void_p * 2), ("sum_tgt_poi", C.c_void_p * 2),
+                ("sum_reg", C.c_void_p * 2)]
+
+
 class NaisCatalog(C.Structure):
     _fields_ = [("region", C.c_void_p), ("coords", C.c_void_p), ("row_base", C.c_int64), ("n_rows", C.c_int64),
                 ("center_lat", C.c_float), ("center_lon", C.c_float)]
@@ -59,6 +64,9 @@ SYMBOLS = {
     "nais_pairs_backward_workspace_bytes": (C.c_size_t, [C.POINTER(NaisParams), C.c_int64, C.c_int32]),
     "nais_pairs_backward": (C.c_int, [C.POINTER(NaisParams), C.POINTER(NaisPairs), C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.POINTER(NaisGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nais_pairs_backward_adagrad": (C.c_int, [C.POINTER(NaisParams), C.POINTER(NaisPairs), C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.POINTER(NaisGrads), C.POINTER(NaisAdagrad), C.c_void_p, C.c_size_t,
+                                              C.c_void_p]),
     "nais_fullrank_workspace_bytes": (C.c_size_t, [C.POINTER(NaisParams), C.c_int32, C.c_int64, C.c_int64, C.c_int64,
                                                    C.c_int32, C.c_int32]),
     "nais_fullrank_topk": (C.c_int, [C.POINTER(NaisParams), C.POINTER(NaisCatalog), C.POINTER(NaisUsers), C.c_int64,

@@ -529,13 +529,32 @@ __global__ void make_keys_kernel(NaisPairs b, int want_reg, int* k_hist, uint32_
 //   pass 2  one warp per starting partial adds the following chunks' continuing first-run partials, in chunk order.
 constexpr int SEG_CHUNK = 64;
 
+// Where a finished row gradient goes: into the dense gradient table (param == nullptr), or straight into a row-sparse
+// Adagrad step on the parameter row (run.py:225,254 with weight_decay = lr_decay = 0, where untouched rows do not move):
+//   sum += g*g ; param -= lr * g / (sqrt(sum) + eps)          (torch.optim.Adagrad's update, one row, written once)
+struct SegOut {
+  float* out;
+  float* param;
+  float* sum;
+  float lr, eps;
+};
+__device__ __forceinline__ void seg_store(const SegOut& o, size_t idx, float g) {
+  if (o.param) {
+    const float s2 = fmaf(g, g, o.sum[idx]);
+    o.sum[idx] = s2;
+    o.param[idx] -= o.lr * g / (sqrtf(s2) + o.eps);
+  } else {
+    o.out[idx] = g;
+  }
+}
+
 __device__ __forceinline__ const float* seg_row(uint32_t s, int64_t n_cells, const float* ws_dq, const float* ws_dp, int D) {
   return (s < n_cells) ? ws_dq + (size_t)s * D : ws_dp + (size_t)(s - n_cells) * D;
 }
 
 __global__ void segment_reduce_pass1_kernel(const int* __restrict__ keys, const uint32_t* __restrict__ src, int64_t n,
                                             int64_t n_cells, const float* __restrict__ ws_dq,
-                                            const float* __restrict__ ws_dp, int D, int off, int w, float* __restrict__ out,
+                                            const float* __restrict__ ws_dp, int D, int off, int w, SegOut out,
                                             int* __restrict__ part_key, int* __restrict__ part_start,
                                             float* __restrict__ part_rows) {
   const int64_t chunk = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -554,7 +573,7 @@ __global__ void segment_reduce_pass1_kernel(const int* __restrict__ keys, const 
     if (!left && !right) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        if (lane + 32 * i < w) out[(size_t)cur * w + lane + 32 * i] = acc[i];
+        if (lane + 32 * i < w) seg_store(out, (size_t)cur * w + lane + 32 * i, acc[i]);
     } else {
       const int64_t slot = 2 * chunk + (first ? 0 : 1);
       if (lane == 0) {
@@ -584,8 +603,7 @@ __global__ void segment_reduce_pass1_kernel(const int* __restrict__ keys, const 
 }
 
 __global__ void segment_reduce_pass2_kernel(const int* __restrict__ part_key, const int* __restrict__ part_start,
-                                            const float* __restrict__ part_rows, int64_t n_chunks, int w,
-                                            float* __restrict__ out) {
+                                            const float* __restrict__ part_rows, int64_t n_chunks, int w, SegOut out) {
   const int64_t slot = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (slot >= 2 * n_chunks) return;
@@ -601,7 +619,7 @@ __global__ void segment_reduce_pass2_kernel(const int* __restrict__ part_key, co
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i)
-    if (lane + 32 * i < w) out[(size_t)key * w + lane + 32 * i] = acc[i];
+    if (lane + 32 * i < w) seg_store(out, (size_t)key * w + lane + 32 * i, acc[i]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -668,8 +686,10 @@ static int launch_bwd_tile(const BwdArgs& A, int D, int grid, cudaStream_t strea
 }
 
 int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score_parts, const float* row_sum,
-                     const float* dscore, const NaisGrads& g, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                     const float* dscore, const NaisGrads& g, const NaisAdagrad* opt, void* ws, size_t ws_bytes,
+                     cudaStream_t stream) {
   if (b.B * (int64_t)b.H + b.B >= 0x7fffffffLL) return NAIS_ERR_SHAPE;
+  if (opt && p.n_branch != 1) return NAIS_ERR_MODE;  // two branches share tables: two sparse steps != one dense step
   const BwdLayout L = bwd_layout(p, b.B, b.H);
   if (ws_bytes < L.total) return NAIS_ERR_WORKSPACE;
   char* base = reinterpret_cast<char*>(ws);
@@ -718,16 +738,26 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
   NAIS_COUNT_LAUNCH(1);
     }
     // embedding rows
-    const bool want_hist = br.w_poi > 0 && g.hist_poi[bi];
-    const bool want_tgt = br.w_poi > 0 && g.tgt_poi[bi];
-    const bool want_reg = br.w_reg > 0 && g.reg[bi];
+    // a table is processed if it has a gradient destination or a fused-optimizer state
+    const bool want_hist = br.w_poi > 0 && (g.hist_poi[bi] || (opt && opt->sum_hist_poi[bi]));
+    const bool want_tgt = br.w_poi > 0 && (g.tgt_poi[bi] || (opt && opt->sum_tgt_poi[bi]));
+    const bool want_reg = br.w_reg > 0 && (g.reg[bi] || (opt && opt->sum_reg[bi]));
+    auto dest = [&](float* grad, const float* param, float* sum) {
+      SegOut o;
+      o.out = grad;
+      o.param = (opt && sum) ? const_cast<float*>(param) : nullptr;
+      o.sum = sum;
+      o.lr = opt ? opt->lr : 0.f;
+      o.eps = opt ? opt->eps : 0.f;
+      return o;
+    };
     const int64_t n_thr = n_cells > b.B ? n_cells : b.B;
     make_keys_kernel<<<(unsigned)((n_thr + 255) / 256), 256, 0, stream>>>(b, 0, want_hist ? kin : nullptr, vin,
                                                                          want_tgt ? kin2 : nullptr, vin2,
                                                                          nullptr, nullptr);
   NAIS_COUNT_LAUNCH(1);
     size_t cb = L.cub_bytes;
-    auto seg = [&](int* ki, uint32_t* vi, int64_t n, int off, int w, float* out, int bits) {
+    auto seg = [&](int* ki, uint32_t* vi, int64_t n, int off, int w, SegOut out, int bits) {
       cub::DeviceRadixSort::SortPairs(base + L.cub, cb, ki, kout, vi, vout, (int)n, 0, bits, stream);
       const int64_t nch = (n + SEG_CHUNK - 1) / SEG_CHUNK;
       int* pk = reinterpret_cast<int*>(base + L.pkey);
@@ -740,12 +770,13 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
       NAIS_COUNT_LAUNCH(1);
     };
     auto bits_for = [](int n) { int bts = 1; while ((1ll << bts) < n && bts < 31) ++bts; return bts; };
-    if (want_hist) seg(kin, vin, n_cells, 0, br.w_poi, g.hist_poi[bi], bits_for(p.item_num));
-    if (want_tgt) seg(kin2, vin2, b.B, 0, br.w_poi, g.tgt_poi[bi], bits_for(p.item_num));
+    if (want_hist) seg(kin, vin, n_cells, 0, br.w_poi, dest(g.hist_poi[bi], br.hist_poi, opt ? opt->sum_hist_poi[bi] : nullptr), bits_for(p.item_num));
+    if (want_tgt) seg(kin2, vin2, b.B, 0, br.w_poi, dest(g.tgt_poi[bi], br.tgt_poi, opt ? opt->sum_tgt_poi[bi] : nullptr), bits_for(p.item_num));
     if (want_reg) {
       make_keys_kernel<<<(unsigned)((n_thr + 255) / 256), 256, 0, stream>>>(b, 1, nullptr, nullptr, nullptr, nullptr, kin, vin);
   NAIS_COUNT_LAUNCH(1);
-      seg(kin, vin, n_cells + b.B, br.w_poi, br.w_reg, g.reg[bi], bits_for(p.region_num));
+      // (history-side and target-side region rows are one table in every variant: hist_reg == tgt_reg)
+      seg(kin, vin, n_cells + b.B, br.w_poi, br.w_reg, dest(g.reg[bi], br.hist_reg, opt ? opt->sum_reg[bi] : nullptr), bits_for(p.region_num));
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;

@@ -15,7 +15,8 @@ int choose_splits(int n_users, int64_t range);
 // nais_bwd.cu
 size_t pairs_bwd_workspace_bytes(const NaisParams& p, int64_t B, int H);
 int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score_parts, const float* row_sum,
-                     const float* dscore, const NaisGrads& g, void* ws, size_t ws_bytes, cudaStream_t stream);
+                     const float* dscore, const NaisGrads& g, const NaisAdagrad* opt, void* ws, size_t ws_bytes,
+                     cudaStream_t stream);
 // nais_tc.cu
 size_t fullrank_tc_workspace_bytes(const NaisParams& p, int n_users, int64_t nnz, int64_t poi_begin, int64_t poi_end, int k,
                                    int precision);
@@ -142,7 +143,25 @@ int nais_pairs_backward(const NaisParams* p, const NaisPairs* batch, const float
   if (!score_parts || !row_sum || !dscore || !workspace) return NAIS_ERR_NULL;
   if (!aligned16(workspace)) return NAIS_ERR_ALIGN;
   if (workspace_bytes < pairs_bwd_workspace_bytes(*p, batch->B, batch->H)) return NAIS_ERR_WORKSPACE;
-  return launch_pairs_bwd(*p, *batch, score_parts, row_sum, dscore, *grads, workspace, workspace_bytes,
+  return launch_pairs_bwd(*p, *batch, score_parts, row_sum, dscore, *grads, nullptr, workspace, workspace_bytes,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int nais_pairs_backward_adagrad(const NaisParams* p, const NaisPairs* batch, const float* score_parts, const float* row_sum,
+                                const float* dscore, const NaisGrads* grads, const NaisAdagrad* opt, void* workspace,
+                                size_t workspace_bytes, nais_stream_t stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  rc = check_pairs(p, batch);
+  if (rc) return rc;
+  if (!grads || !opt) return NAIS_ERR_NULL;
+  if (p->n_branch != 1) return NAIS_ERR_MODE;
+  if (!(opt->lr >= 0.f) || !(opt->eps >= 0.f)) return NAIS_ERR_MODE;
+  if (batch->B == 0) return 0;
+  if (!score_parts || !row_sum || !dscore || !workspace) return NAIS_ERR_NULL;
+  if (!aligned16(workspace)) return NAIS_ERR_ALIGN;
+  if (workspace_bytes < pairs_bwd_workspace_bytes(*p, batch->B, batch->H)) return NAIS_ERR_WORKSPACE;
+  return launch_pairs_bwd(*p, *batch, score_parts, row_sum, dscore, *grads, opt, workspace, workspace_bytes,
                           static_cast<cudaStream_t>(stream));
 }
 

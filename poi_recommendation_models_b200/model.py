@@ -70,6 +70,48 @@ class _NAISBase(nn.Module):
         P = self._params()
         return ops.pairs_score(self.variant, float(self.beta), tuple(P.values()), hist, tgt, hreg, treg, aux, drop_p, seed)
 
+    def fused_adagrad_step(self, optimizer: torch.optim.Adagrad, label, hist, tgt, hreg=None, treg=None, aux=None) -> torch.Tensor:
+        """One training step of run.py:248-254 (`zero_grad -> forward -> BCELoss -> backward -> Adagrad.step`) with the
+        embedding tables stepped by the row-sparse Adagrad fused into the backward's segment reduce: no dense
+        [N, D/2] gradient is zero-filled, written or read, and only the touched rows of the tables and of the optimizer's
+        `state['sum']` move.  With the reference's `weight_decay = 0` (run.py:833) this IS the dense step (SURVEY.md §7
+        'Dense Adagrad semantic'); other settings raise.  The MLP / dist-layer parameters go through `optimizer.step()` as
+        usual.  Returns the loss (same value `loss_func(forward(...), label)` gives)."""
+        if not isinstance(optimizer, torch.optim.Adagrad):
+            raise RuntimeError("fused_adagrad_step needs torch.optim.Adagrad (run.py:225)")
+        P = self._params()
+        group_of = {id(p): g for g in optimizer.param_groups for p in g["params"]}
+        sums, lr, eps = {}, None, None
+        for name in ops._TABLES:
+            if name not in P:
+                continue
+            g = group_of.get(id(P[name]))
+            if g is None:
+                raise RuntimeError(f"{name} is not in the optimizer")
+            if g["weight_decay"] != 0 or g["lr_decay"] != 0 or g.get("maximize", False):
+                raise RuntimeError("row-sparse Adagrad equals the dense step only for weight_decay = lr_decay = 0")
+            if lr is not None and (lr, eps) != (g["lr"], g["eps"]):
+                raise RuntimeError("embedding tables must share lr / eps")
+            lr, eps = g["lr"], g["eps"]
+            sums[name] = optimizer.state[P[name]]["sum"]
+        drop = (0.0, 0)
+        if self._dropout_on_l1 and self.training and self.drop.p > 0:
+            drop = (float(self.drop.p), int(torch.randint(0, 2 ** 62, (1,)).item()))
+            self.last_dropout_seed = drop[1]
+        optimizer.zero_grad(set_to_none=True)
+        with torch.no_grad():
+            score, row_sum, parts = ops.pairs_forward_raw(self.variant, float(self.beta), P, hist, tgt, hreg, treg, aux, drop)
+        s = score.detach().requires_grad_(True)  # dL/dscore through torch's own sigmoid + BCELoss ([B]-sized, exact semantics)
+        loss = self.loss_func(torch.sigmoid(s), label)
+        loss.backward()
+        with torch.no_grad():
+            G = ops.pairs_backward_adagrad(self.variant, float(self.beta), P, sums, lr, eps, hist, tgt, hreg, treg, aux, row_sum,
+                                           parts, s.grad, drop)
+        for name, grad in G.items():
+            P[name].grad = grad.to(P[name].dtype)
+        optimizer.step()  # the tables have no .grad: torch skips them
+        return loss.detach()
+
     def get_mask(self, user_history, target_item):
         return user_history != target_item.reshape([len(target_item), 1])
 

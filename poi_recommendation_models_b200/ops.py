@@ -193,6 +193,62 @@ def pairs_score(variant: str, beta: float, params: Sequence[torch.Tensor], hist,
     return _PairsFunction.apply(variant, beta, (float(dropout_p), int(dropout_seed)), hist, tgt, hreg, treg, aux, *params)
 
 
+_TABLES = ("embed_history.weight", "embed_target.weight", "embed_region.weight")
+
+
+def pairs_backward_adagrad(variant: str, beta: float, P: Dict[str, torch.Tensor], sums: Dict[str, torch.Tensor], lr: float,
+                           eps: float, hist, tgt, hreg, treg, aux, row_sum, parts, dscore, drop=(0.0, 0)) -> Dict[str, torch.Tensor]:
+    """Backward of `pairs_score` with the embedding tables stepped in place by a row-sparse Adagrad fused into the
+    sorted-segment reduce (nais_pairs_backward_adagrad; replaces run.py:252-254 for `embed_*`): `sums[name]` is the
+    optimizer's `state['sum']` of table `name`; P[name] and sums[name] of every touched row are updated, nothing dense is
+    written.  Returns the gradients of the remaining (MLP / dist layer) parameters."""
+    from ._lib import NaisAdagrad
+    dev = _need_cuda(hist, tgt, dscore, *P.values())
+    lib = _lib.load()
+    keep: List[torch.Tensor] = []
+    with torch.cuda.device(dev):
+        p = build_params(variant, P, beta, keep, *drop)
+        if p.n_branch != 1:
+            raise RuntimeError("fused Adagrad: one-branch variants only")
+        b = _pairs_struct(hist, tgt, hreg, treg, aux, keep)
+        G = {n: torch.zeros_like(t, dtype=torch.float32, memory_format=torch.contiguous_format) for n, t in P.items() if n not in _TABLES}
+        g = NaisGrads()
+        g.w1[0], g.b1[0], g.w2[0] = (G["attn_layer1.weight"].data_ptr(), G["attn_layer1.bias"].data_ptr(), G["attn_layer2.weight"].data_ptr())
+        if "dist_layer.weight" in G:
+            g.dist_w, g.dist_b = G["dist_layer.weight"].data_ptr(), G["dist_layer.bias"].data_ptr()
+        o = NaisAdagrad()
+        o.lr, o.eps = float(lr), float(eps)
+        for name, field in zip(_TABLES, (o.sum_hist_poi, o.sum_tgt_poi, o.sum_reg)):
+            if name in P:
+                st = sums[name]
+                if st.dtype != torch.float32 or not st.is_contiguous() or st.shape != P[name].shape or not P[name].is_contiguous():
+                    raise RuntimeError(f"fused Adagrad: {name} and its state must be contiguous float32 of the same shape")
+                field[0] = st.data_ptr()
+        ws_bytes = lib.nais_pairs_backward_workspace_bytes(C.byref(p), b.B, b.H)
+        ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
+        ds = _f32(dscore)
+        _lib.check(lib.nais_pairs_backward_adagrad(C.byref(p), C.byref(b), parts.data_ptr(), row_sum.data_ptr(), ds.data_ptr(),
+                                                   C.byref(g), C.byref(o), ws.data_ptr(), ws_bytes, _stream()),
+                   "nais_pairs_backward_adagrad")
+    return G
+
+
+def pairs_forward_raw(variant: str, beta: float, P: Dict[str, torch.Tensor], hist, tgt, hreg, treg, aux, drop=(0.0, 0)):
+    """(score[B], row_sum, parts) of nais_pairs_forward without autograd bookkeeping (the fused train step keeps them)."""
+    dev = _need_cuda(hist, tgt, *P.values())
+    lib = _lib.load()
+    keep: List[torch.Tensor] = []
+    with torch.cuda.device(dev):
+        p = build_params(variant, P, beta, keep, *drop)
+        b = _pairs_struct(hist, tgt, hreg, treg, aux, keep)
+        score = torch.empty(b.B, device=dev, dtype=torch.float32)
+        row_sum = torch.empty(p.n_branch, b.B, device=dev, dtype=torch.float32)
+        parts = torch.empty(p.n_branch, b.B, device=dev, dtype=torch.float32)
+        _lib.check(lib.nais_pairs_forward(C.byref(p), C.byref(b), score.data_ptr(), row_sum.data_ptr(), parts.data_ptr(),
+                                          _stream()), "nais_pairs_forward")
+    return score, row_sum, parts
+
+
 def dropout_keep_mask(seed: int, B: int, H: int, hid: int, p: float):
     """The keep-mask the kernels use, on the host (numpy bool [B,H,hid]) — for tests / reproducing a step."""
     import numpy as np

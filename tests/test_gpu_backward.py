@@ -113,6 +113,51 @@ def test_train_steps_match_reference_flow():
         np.testing.assert_allclose(v.cpu().double().numpy(), ref, rtol=0, atol=2e-5, err_msg=k)
 
 
+@pytest.mark.parametrize("variant", ["region_distance", "basic", "distance"])
+def test_fused_row_sparse_adagrad_equals_dense_steps(variant):
+    """`fused_adagrad_step` (row-sparse Adagrad inside the embedding-gradient segment reduce) against the
+    reference flow on the same module class: zero_grad -> forward -> BCELoss -> backward -> dense torch.optim.Adagrad.step
+    (run.py:248-254).  Parameters AND optimizer state after every step must agree; untouched table rows must not move."""
+    import copy
+    import random
+    from poi_recommendation_models_b200 import batches as PB
+    N, D, hid, beta = 400, 64, 64, 0.5
+    data = synthetic.make_checkins(4, N, seed=19, hist_len=None, max_hist=25, min_hist=4, median_hist=10)
+    sd = orc.init_state(variant, N, D, hid, data.region_num, 1, seed=6, style="trained")
+    m_dense = util.make_model(variant, sd, beta).eval()   # (eval: the dropout variants would draw different masks)
+    m_fused = copy.deepcopy(m_dense)
+    o_dense = torch.optim.Adagrad(m_dense.parameters(), lr=0.01, weight_decay=0.0)
+    o_fused = torch.optim.Adagrad(m_fused.parameters(), lr=0.01, weight_decay=0.0)
+    csr = data.train_csr()
+    before = {k: v.clone() for k, v in m_fused.state_dict().items()}
+    touched = set()
+    for step in range(6):
+        u = step % 4
+        random.seed(70 + step)
+        hist, tgt, label, hreg, treg = PB.get_NAIS_batch_region(csr, N, u, 4, data.region)
+        ll = PB.lat_lon_pairs(data.coords, tgt.cpu().numpy(), hist.cpu().numpy())
+        touched |= set(hist.flatten().tolist())
+        args = {"region_distance": (hist, tgt, hreg, treg, ll), "basic": (hist, tgt), "distance": (hist, tgt, hreg, treg, ll)}[variant]
+        kw = {"region_distance": dict(hreg=hreg, treg=treg, aux=ll), "basic": {}, "distance": dict(aux=ll)}[variant]
+        o_dense.zero_grad()
+        loss_d = m_dense.loss_func(m_dense(*args), label)
+        loss_d.backward()
+        o_dense.step()
+        loss_f = m_fused.fused_adagrad_step(o_fused, label, hist, tgt, **kw)
+        assert abs(loss_f.item() - loss_d.item()) <= 1e-6 * abs(loss_d.item()) + 1e-7
+        for (n, pd), (_, pf) in zip(m_dense.named_parameters(), m_fused.named_parameters()):
+            np.testing.assert_allclose(pf.detach().cpu().numpy(), pd.detach().cpu().numpy(), rtol=0, atol=2e-6, err_msg=f"{n} step {step}")
+            sd_, sf_ = o_dense.state[pd]["sum"], o_fused.state[pf]["sum"]
+            np.testing.assert_allclose(sf_.cpu().numpy(), sd_.cpu().numpy(), rtol=1e-4, atol=1e-9, err_msg=f"sum {n} step {step}")
+            assert pf.grad is None or not n.startswith("embed_"), n  # no dense table gradient was ever materialised
+    # rows no batch touched are bit-identical to the start
+    eh = m_fused.state_dict()["embed_history.weight"]
+    untouched = sorted(set(range(N)) - touched)
+    assert len(untouched) > 0 and torch.equal(eh[untouched], before["embed_history.weight"][untouched])
+    with pytest.raises(RuntimeError):
+        m_fused.fused_adagrad_step(torch.optim.Adagrad(m_fused.parameters(), lr=0.01, weight_decay=1e-7), label, hist, tgt, **kw)
+
+
 @pytest.mark.parametrize("variant", ["basic", "region"])
 def test_train_mode_dropout_forward_and_gradients(variant):
     """relu(drop(attn_layer1(x))) of NAIS_basic / NAIS_regionEmbedding in train mode (model.py:71,162): the fused
