@@ -10,6 +10,8 @@
  *   validation.py:84-127   per-user candidate loop + torch.topk            -> nais_fullrank_topk
  *   torch.cat/topk merge across catalogue shards (new, multi-GPU)          -> nais_topk_merge
  *   eval_metrics.py:36-69  set-overlap counts behind precision/recall/hit@k  -> nais_hits_at_k
+ *   run.py:252-254         embedding_dense_backward + dense Adagrad.step      -> nais_pairs_backward_adagrad
+ *   powerLaw.py:85-92      PowerLaw.predict over a candidate list             -> nais_powerlaw_logscore
  *
  * Conventions
  *   - every pointer is a DEVICE pointer into memory owned by the caller (PyTorch tensors); the library never
@@ -196,6 +198,13 @@ NAIS_API int nais_topk_merge(const float* in_score, const int32_t* in_id, int32_
 NAIS_API int nais_hits_at_k(const int32_t* rec, int32_t n_users, int32_t k_rec, const int64_t* pos_offsets,
                             const int32_t* pos_items, const int32_t* k_list, int32_t n_k, int32_t* hits,
                             nais_stream_t stream);
+
+/* Power-law geographical score of powerLaw.py:57-92 (PowerLaw.predict), in log space, for every user against the POIs
+ * [poi_begin, poi_end):  out_logg[u, j - poi_begin] = sum_{h in history(u)} ln(a * max(0.01, d_km(h, j))^b),  a > 0.
+ * d_km = powerLaw.dist (great circle, R = 6371 km, 0 below 1e-6 degrees) from the centred float32 coordinates of
+ * NaisCatalog / NaisUsers.  The caller exponentiates relative to the per-user maximum (run.py:55-59 `normalize`). */
+NAIS_API int nais_powerlaw_logscore(const NaisCatalog* cat, const NaisUsers* users, int64_t poi_begin, int64_t poi_end, float a,
+                           float b, float* out_logg, nais_stream_t stream);
 
 /* Same scoring pass, but also writes every pre-sigmoid score: all_scores[n_users, poi_end-poi_begin] (history items are
  * scored with their own cell masked, like a training positive).  For parity checks of the fused path on small cases. */

@@ -72,6 +72,42 @@ __global__ void fill_empty_topk_kernel(float* s, int32_t* id, size_t n) {
 
 // hits[u,i] = | set(pos(u)) & set(rec[u,:k_i]) | : one warp per user; duplicates in either list count once, like the
 // reference's Python set intersection (eval_metrics.py:40-42).
+// log of the power-law geographical score of powerLaw.py:85-92: G(u, j) = prod_{h in visited(u)} a * max(0.01, d(h, j))^b
+//   log G = sum_h (ln a + b * ln max(0.01, d_km(h, j)))      (a product of ~100 factors leaves fp32 / fp64 range; its log does not)
+// One thread per candidate, the user's history coordinates staged through shared memory in tiles of 256.
+__global__ void powerlaw_logscore_kernel(NaisCatalog cat, NaisUsers users, int64_t poi_begin, int64_t poi_end, float ln_a, float b,
+                                         float* __restrict__ out) {
+  __shared__ float s_la[256], s_lo[256], s_cos[256];
+  const int u = blockIdx.y;
+  const int64_t hb = users.offsets[u];
+  const int H = (int)(users.offsets[u + 1] - hb);
+  const int64_t j = poi_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = j < poi_end;
+  float cla = 0.f, clo = 0.f, ccos = 1.f;
+  if (valid) {
+    cla = __ldg(cat.coords + 2 * (j - cat.row_base));
+    clo = __ldg(cat.coords + 2 * (j - cat.row_base) + 1);
+    ccos = cosf((cat.center_lat + cla) * 0.017453292519943295f);
+  }
+  float acc = 0.f;
+  for (int h0 = 0; h0 < H; h0 += 256) {
+    __syncthreads();
+    if (h0 + (int)threadIdx.x < H) {
+      const float la = __ldg(users.coords + 2 * (hb + h0 + threadIdx.x)), lo = __ldg(users.coords + 2 * (hb + h0 + threadIdx.x) + 1);
+      s_la[threadIdx.x] = la;
+      s_lo[threadIdx.x] = lo;
+      s_cos[threadIdx.x] = cosf((cat.center_lat + la) * 0.017453292519943295f);
+    }
+    __syncthreads();
+    const int n = min(256, H - h0);
+    for (int i = 0; i < n; ++i) {
+      const float d = fmaxf(0.01f, dist_km_f(cla, clo, s_la[i], s_lo[i], ccos, s_cos[i]));
+      acc += fmaf(b, logf(d), ln_a);
+    }
+  }
+  if (valid) out[(size_t)u * (poi_end - poi_begin) + (j - poi_begin)] = acc;
+}
+
 __global__ void hits_at_k_kernel(const int32_t* __restrict__ rec, int n_users, int k_rec, const int64_t* __restrict__ po,
                                  const int32_t* __restrict__ pi, const int32_t* __restrict__ k_list, int n_k, int32_t* hits) {
   const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -243,6 +279,19 @@ int nais_hits_at_k(const int32_t* rec, int32_t n_users, int32_t k_rec, const int
   const int64_t threads = (int64_t)n_users * 32;
   hits_at_k_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(rec, n_users, k_rec, pos_offsets,
                                                                                                   pos_items, k_list, n_k, hits);
+  NAIS_COUNT_LAUNCH(1);
+  return (int)cudaGetLastError();
+}
+
+int nais_powerlaw_logscore(const NaisCatalog* cat, const NaisUsers* users, int64_t poi_begin, int64_t poi_end, float a, float b,
+                           float* out_logg, nais_stream_t stream) {
+  if (!cat || !users) return NAIS_ERR_NULL;
+  if (users->n_users < 0 || poi_begin < cat->row_base || poi_end < poi_begin || poi_end > cat->row_base + cat->n_rows) return NAIS_ERR_SHAPE;
+  if (!(a > 0.f)) return NAIS_ERR_MODE;
+  if (users->n_users == 0 || poi_end == poi_begin) return 0;
+  if (!cat->coords || !users->coords || !users->offsets || !out_logg) return NAIS_ERR_NULL;
+  dim3 grid((unsigned)((poi_end - poi_begin + 255) / 256), (unsigned)users->n_users);
+  powerlaw_logscore_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*cat, *users, poi_begin, poi_end, logf(a), b, out_logg);
   NAIS_COUNT_LAUNCH(1);
   return (int)cudaGetLastError();
 }
