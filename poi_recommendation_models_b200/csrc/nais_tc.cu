@@ -29,6 +29,8 @@
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
 
+#include <type_traits>
+
 #include "nais_common.cuh"
 #include "umma.cuh"
 
@@ -53,6 +55,7 @@ constexpr int HMETA = 512;      // history items whose id/coords are staged in s
 struct Geo {
   int D, hid, lanes, split;
   int mix;       // NAIS_PREC_TC_MIX: lo section of A tiles / B chunks = e5m2(hi) | e5m2(lo) byte planes, two ext k-chunks
+  int ts;        // MIX at D = hid = 64: the TMEM-A kernel (fullrank_ts_kernel) runs; its ext k-chunks use another K-slot order
   int kx;        // D / 8 x k-chunks
   int hch;       // history items per chunk / MMA step: 2 (hid <= 64) or 1 (hid 96, 128: a cell's hidden columns are split
                  // between the two warps of a lane quarter and their partial sums exchanged through shared memory)
@@ -119,6 +122,7 @@ __host__ inline bool make_geo(const NaisParams& p, int precision, Geo& g) {
   g.tpc = g.kp == 1 ? TPC : 2;  // compile-time constant per kernel instantiation (kSinglePart)
   g.smem_bytes = g.tpc * g.a_tile + g.stages * g.stage_bytes + NBUF * 2 * TM * 16 + 4096 + SORTN * 8 + 3 * HMETA * 4 + 4 * TM * 4 + 256 + 128 +
                  (g.kp == 1 ? 9 * TPC * TM * 4 : 0);  // D <= 64 has room for a private `comb`; D > 64 aliases it on A_ext + zero
+  g.ts = g.mix && g.D == 64 && g.hid == 64 && g.kp == 1 && g.hch == 2 && g.nrow == 144 && getenv("NAIS_TC_TMEM_A") != nullptr;  // opt-in: see DESIGN.md §3
   return g.smem_bytes <= 227 * 1024;
 }
 
@@ -144,6 +148,7 @@ __device__ __forceinline__ bool user_in_pass(int gate, int use_mix, int H) {
 // workspace header: [0,64) maxes (uint bits) | [64,128) Scales | perm[128] int | ck[128] float | u[128] float
 constexpr int HDR_BYTES = 4096;
 constexpr int HDR_PERM = 128, HDR_CK = HDR_PERM + 128 * 4, HDR_U = HDR_CK + 128 * 4;
+constexpr int HDR_ROUND = 3072;  // two item counters (MIX pass, SPLIT pass) of the round barrier; the header is zeroed per call
 
 __global__ void absmax_kernel(const float* __restrict__ x, size_t n, unsigned* out) {
   float m = 0.f;
@@ -393,7 +398,15 @@ __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g, const un
         split_f16(w0, h0, l0);
         split_f16(w1, h1, l1);
         split_f16(wb, hb, lb2);
-        if (hs >= 0) {
+        if (hs >= 0 && g.ts) {
+          // TMEM-A kernel: A_ext = one 8-half block per history slot, [g_hi g_hi' | g_lo g_lo' | g_hi g_hi' | 1 1] for slot 0
+          // (k-chunk e0) and [... | 0 0] for slot 1 (k-chunk e1); the shared (1, 1) pair sits at e0[6], e0[7]
+          __half* eb = hs == 0 ? e0 : e1;
+          eb[0] = h0, eb[1] = h1;   // x g_hi
+          eb[2] = h0, eb[3] = h1;   // x g_lo
+          eb[4] = l0, eb[5] = l1;   // x g_hi
+          e0[6] = hb, e0[7] = lb2;  // x (1, 1)
+        } else if (hs >= 0) {
           e0[2 * hs] = h0;
           e0[2 * hs + 1] = h1;
           e0[4] = hb;
@@ -529,7 +542,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       mbar_init(&b_empty[i], 1);
     }
     for (int i = 0; i < NBUF; ++i) {
-      mbar_init(&e_full[i], ARRIVE_WARPS);
+      mbar_init(&e_full[i], kFastEpi ? ARRIVE_WARPS / 2 : ARRIVE_WARPS);  // fast epilogue: one warp of each slot pair writes the row
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_full[NBUF + i], 1);
       mbar_init(&acc_empty[i], ARRIVE_WARPS);
@@ -839,9 +852,16 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
         // Every step index is then (chunk, t) with buffer == t, so the t loop unrolls with compile-time TMEM / A_ext
         // addresses, the per-chunk history lookups leave the step body, and this group's acc_full parity is one bit that
         // flips once per own chunk.  ~150 issue slots per warp-step instead of ~340 (the MIX mode is epilogue-issue bound).
-        const unsigned char* ebase = sE + r * 16 + hs * 4;
-        // A_ext of (chunk pc, tile t): 2 sigmoids -> hi/lo halves.  sAe / (1 + 2^z) = 1 / (1/sAe + 2^(z - log2 sAe))
-        auto produce_f = [&](int t, bool on, float hla, float hlo, float cla, float clo) {
+        // A_ext of (chunk pc, tile t).  The row of a candidate is 16 bytes per k-chunk; a thread that stored only its own
+        // history slot's 4 bytes made every store 4-way bank conflicted (lanes are 16 B apart), and those conflicts cost the
+        // shared-memory port ~60 clk per step that the MMAs' operand fetches need.  So ONE warp of each (slot 0, slot 1) pair
+        // builds the whole row — both slots, 4 sigmoids — and writes it with two conflict-free 16-byte stores; the pair
+        // splits the tiles (tile 0: slot-0 warp, tile 1: slot-1 warp, tile 2: alternating with the chunk).
+        //   split / fast: [hi plane | lo plane] rows (g0 g1 | g0' g1' | 1 0 0 0) ; mix: [k-chunk 0 | k-chunk 1] rows
+        //   (g_hi g_hi' 1 1 0 0) and (g_lo g_lo' | g_hi g_hi')      sAe / (1 + 2^z) = 1 / (1/sAe + 2^(z - log2 sAe))
+        unsigned char* const ebase = sE + r * 16;
+        const uint32_t one16 = (uint32_t)__half_as_ushort(__float2half(sc.sAe));
+        auto sig2 = [&](bool on, float hla, float hlo, float cla, float clo, uint32_t& hi, uint32_t& lo) {
           float g0 = 0.f, g1 = 0.f;
           if (on) {
             const float l0 = fabsf(cla - hla), l1 = fabsf(clo - hlo);
@@ -852,10 +872,23 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
           const __half2 hi2 = __floats2half2_rn(g0, g1);
           const float2 hif = __half22float2(hi2);
           const __half2 lo2 = __floats2half2_rn(g0 - hif.x, g1 - hif.y);
-          unsigned char* eb = const_cast<unsigned char*>(ebase) + t * (2 * TM * 16);
-          *reinterpret_cast<__half2*>(eb) = hi2;
-          *reinterpret_cast<__half2*>(eb + TM * 16) = lo2;
-          if (g.mix) *reinterpret_cast<__half2*>(eb + TM * 16 + 8) = hi2;
+          hi = *reinterpret_cast<const uint32_t*>(&hi2);
+          lo = *reinterpret_cast<const uint32_t*>(&lo2);
+        };
+        // pc: the chunk the block is for; this warp produces tile t of it iff mine(pc, t)
+        auto mine = [&](int pc, int t) { return t == 2 ? (((pc >> 1) & 1) == hs) : (t == hs); };
+        auto produce_f = [&](int t, bool on0, bool on1, const float (&hc)[4], float cla, float clo) {
+          uint32_t h0, l0, h1, l1;
+          sig2(on0, hc[0], hc[1], cla, clo, h0, l0);
+          sig2(on1, hc[2], hc[3], cla, clo, h1, l1);
+          unsigned char* eb = ebase + t * (2 * TM * 16);
+          if (g.mix) {
+            *reinterpret_cast<uint4*>(eb) = make_uint4(h0, h1, one16 * 0x10001u, 0u);
+            *reinterpret_cast<uint4*>(eb + TM * 16) = make_uint4(l0, l1, h0, h1);
+          } else {
+            *reinterpret_cast<uint4*>(eb) = make_uint4(h0, h1, one16, 0u);
+            *reinterpret_cast<uint4*>(eb + TM * 16) = make_uint4(l0, l1, 0u, 0u);
+          }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(&e_full[t]);
@@ -873,11 +906,13 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
 #pragma unroll
         for (int t = 0; t < TPC; ++t) jt[t] = jid[t] < A.poi_end ? (int)jid[t] : -2;
         if (egrp == 0 && nchunks > 0) {  // prologue: chunk 0's A_ext
-          const bool on = g.lanes && hs < H;
-          float la = 0.f, lo = 0.f;
-          if (on) hist_coords(hs, la, lo);
+          const bool on0 = g.lanes && 0 < H, on1 = g.lanes && 1 < H;
+          float hc[4] = {0.f, 0.f, 0.f, 0.f};
+          if (on0) hist_coords(0, hc[0], hc[1]);
+          if (on1) hist_coords(1, hc[2], hc[3]);
 #pragma unroll
-          for (int t = 0; t < TPC; ++t) produce_f(t, on, la, lo, clat[t], clon[t]);
+          for (int t = 0; t < TPC; ++t)
+            if (mine(0, t)) produce_f(t, on0, on1, hc, clat[t], clon[t]);
         }
         const uint32_t tb_main = tmem + lane_addr + (uint32_t)(hs * 64), tb_aux = tmem + lane_addr + 128u + (uint32_t)(2 * hs);
         for (int c = egrp; c < nchunks; c += 2) {
@@ -886,9 +921,10 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
           int hist_id = -1;
           if (hvalid) hist_id = h < HMETA ? hm_id[h] : __ldg(A.users.items + hb + h);
           const bool pn = c + 1 < nchunks;            // this group refills the A_ext buffers for the other group's next chunk
-          const bool pon = pn && g.lanes && (h + 2 < H);
-          float nla = 0.f, nlo = 0.f;
-          if (pon) hist_coords(h + 2, nla, nlo);
+          const bool pon0 = pn && g.lanes && (2 * c + 2 < H), pon1 = pn && g.lanes && (2 * c + 3 < H);
+          float nhc[4] = {0.f, 0.f, 0.f, 0.f};
+          if (pon0) hist_coords(2 * c + 2, nhc[0], nhc[1]);
+          if (pon1) hist_coords(2 * c + 3, nhc[2], nhc[3]);
 #pragma unroll
           for (int t = 0; t < TPC; ++t) {
             mbar_wait(&acc_full[egrp * NBUF + t], fph);
@@ -929,7 +965,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
             tmem_ld2(tb_aux + t * ACC_STRIDE, aux);
             tmem_ld16(tb_main + t * ACC_STRIDE, va);
             tmem_ld16(tb_main + t * ACC_STRIDE + 16, vb);
-            if (pn) produce_f(t, pon, nla, nlo, clat[t], clon[t]);
+            if (pn && mine(c + 1, t)) produce_f(t, pon0, pon1, nhc, clat[t], clon[t]);
             tmem_wait_ld16(va);
             tmem_wait_ld16(vb);
             blk(va, 0);
@@ -1169,6 +1205,452 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
   if (warp == EPI_WARPS) tmem_dealloc(tmem, 512);
 }
 
+
+// =====================================================================================================================
+// TMEM-A kernel (D = hid = 64, MIX precision): every A operand lives in TENSOR MEMORY.
+//
+// ncu on the smem-operand kernel above: the shared-memory port is the limiter — per step 9 MMAs x (4 KB of A + 4.6 KB of B)
+// = 612 clk at 128 B/clk, + 108 clk of bulk-copy writes (B chunks) + 105 LSU wavefronts (A_ext stores, 4-way bank
+// conflicted) = 825 clk against 649 clk of MMA math, measured 850.  A is the same for all 64 chunks of an item, so it does
+// not belong in the operand stream at all: here the epilogue warps move the item's three candidate tiles into TMEM once
+// (the producer warp prefetches the packed tile image into a shared-memory staging area during the previous item; its
+// 16-byte column groups are exactly 4 TMEM columns: LDS.128 -> tcgen05.st, lane = candidate row), write the per-step A_ext columns with
+// tcgen05.st as well (no shared-memory stores, no proxy fence), and the MMAs take A from TMEM (tcgen05.mma [d], [a], b_desc).
+// Shared memory then only streams B: 9 x 36 + 108 = 432 clk per step, under the MMA math.  The 96 KB the A tiles
+// occupied become two more B stages.  (tests/umma_probe_ts.cu: layout + 72 clk per MMA.)
+//
+// TMEM columns: [0,288) two accumulators x 144 | [288,480) three A tiles x (32 fp16-pair + 16 e5m2(hi) + 16 e5m2(lo) columns)
+//               | [480,496) two A_ext buffers x 8.
+// Two accumulators, so the epilogue group of a step is its parity (group g drains accumulator g and refills A_ext buffer
+// g for ITS next step); partial sums are still keyed by chunk parity (q = (g + n0 + t) & 1) and combined in that order,
+// which keeps results bit-identical between sharded / sliced / whole runs.
+namespace ts {
+constexpr int STAGES = 2;
+constexpr int NROW = 144;
+constexpr int BCHUNK = 2 * 9 * NROW * 16;  // 41 472 B: hi plane 10 k-chunks + e5m2(hi) 4 + e5m2(lo) 4
+constexpr int COL_A = 288, COL_EXT = 480, A_COLS = 64;
+constexpr int ATILE = 2 * 8 * TM * 16;       // 32 KB: the MIX candidate-tile image of pack_candidates_kernel, [16 column groups][128 rows][16 B]
+constexpr int SMEM_BYTES = STAGES * BCHUNK + TPC * ATILE + SORTN * 8 + 4 * 3 * TPC * TM * 4 + 3 * HMETA * 4 + 64 + 256 + 64;
+}  // namespace ts
+
+__global__ void __launch_bounds__(THREADS, 1) fullrank_ts_kernel(const __grid_constant__ MainArgs A) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const Geo& g = A.g;
+  unsigned char* sB = smem;
+  unsigned char* sA = sB + ts::STAGES * ts::BCHUNK;                                                  // staged tile images of the NEXT item
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(sA + TPC * ts::ATILE);           // [SORTN]
+  float* comb = reinterpret_cast<float*>(keys + SORTN);                                            // [4 parts][3 arrays][TPC][TM]
+  int* hm_id = reinterpret_cast<int*>(comb + 4 * 3 * TPC * TM);
+  float* hm_la = reinterpret_cast<float*>(hm_id + HMETA);
+  float* hm_lo = hm_la + HMETA;
+  float* sgn_mixed = hm_lo + HMETA;                                                                // [16]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sgn_mixed + 16);
+  uint64_t* b_full = bars;                       // [STAGES]
+  uint64_t* b_empty = bars + ts::STAGES;         // [STAGES]
+  uint64_t* e_full = bars + 2 * ts::STAGES;      // [2]  A_ext written (8 warps of the group)
+  uint64_t* acc_full = e_full + 2;               // [2]  MMAs of a step complete
+  uint64_t* acc_empty = acc_full + 2;            // [2]  accumulator in registers (8 warps)
+  uint64_t* a_ready = acc_empty + 2;             // A tiles of the item are in TMEM (16 warps)
+  uint64_t* a_free = a_ready + 1;                // every MMA of the item has completed
+  uint64_t* sa_full = a_free + 1;                // staged tile images landed (bulk copy)
+  uint64_t* sa_empty = sa_full + 1;              // ... and were moved to TMEM (16 warps)
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(sa_empty + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const Scales sc = *reinterpret_cast<const Scales*>(A.hdr + 64);
+  if (A.gate == 1 && !sc.use_mix) return;
+
+  if (tid < 16) sgn_mixed[tid] = ((sc.npos & ~15) + tid < sc.npos) ? 1.f : -1.f;
+  if (tid == 0) {
+    for (int i = 0; i < ts::STAGES; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&e_full[i], ARRIVE_WARPS);
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], ARRIVE_WARPS);
+    }
+    mbar_init(a_ready, EPI_WARPS);
+    mbar_init(a_free, 1);
+    mbar_init(sa_full, 1);
+    mbar_init(sa_empty, EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == EPI_WARPS) tmem_alloc(tslot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  const int64_t cb0 = chunk_base(A.users.offsets, 0, 2);
+  auto in_pass = [&](int u) { return user_in_pass(A.gate, sc.use_mix, (int)(A.users.offsets[u + 1] - A.users.offsets[u])); };
+
+  if (warp == EPI_WARPS + 1) {
+    // =================================================== bulk-copy producer ========================================
+    uint32_t bstep = 0, it_n = 0;
+    const uint64_t pol = l2_policy_evict_last();
+    for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x) {
+      const int u = (int)(item / A.groups), grp = (int)(item % A.groups);
+      if (!in_pass(u)) continue;
+      const uint32_t it = it_n++;
+      mbar_wait(sa_empty, (it & 1u) ^ 1u);  // the staging area was drained at the start of the previous item: this prefetches
+      if (elect_one()) {
+        mbar_expect_tx(sa_full, (uint32_t)(TPC * ts::ATILE));
+        for (int t = 0; t < TPC; ++t)
+          bulk_g2s_hint(sA + (size_t)t * ts::ATILE, A.Pimg + ((size_t)grp * TPC + t) * ts::ATILE, (uint32_t)ts::ATILE, sa_full, pol);
+      }
+      __syncwarp();
+      const int64_t cbu = __shfl_sync(0xffffffffu, chunk_base(A.users.offsets, u, 2) - cb0, 0);
+      const int nchunks = __shfl_sync(0xffffffffu, user_chunks(A.users.offsets, u, 2, cb0, A.max_chunks), 0);
+      const unsigned char* src = A.Bimg + (size_t)cbu * ts::BCHUNK;
+      for (int c = 0; c < nchunks; ++c, ++bstep) {
+        const uint32_t st = bstep % ts::STAGES;
+        mbar_wait(&b_empty[st], ((bstep / ts::STAGES) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&b_full[st], (uint32_t)ts::BCHUNK);
+          bulk_g2s_hint(sB + (size_t)st * ts::BCHUNK, src + (size_t)c * ts::BCHUNK, (uint32_t)ts::BCHUNK, &b_full[st], pol);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == EPI_WARPS) {
+    // =================================================== MMA issuer ================================================
+    constexpr uint32_t kBLbo = ts::NROW * 16, kBStep = (2 * kBLbo) >> 4, kStage = ts::BCHUNK >> 4;
+    constexpr uint32_t idN = idesc_f16(TM, ts::NROW), idN8 = idesc_e5m2(TM, ts::NROW);
+    constexpr uint32_t b8h = (10 * kBLbo) >> 4, b8l = (14 * kBLbo) >> 4;  // e5m2(hi) / e5m2(lo) planes of a chunk
+    const uint32_t hi_word = (uint32_t)(smem_desc(0, 0, 128) >> 32);
+    auto mk = [&](uint32_t lo) { return ((uint64_t)hi_word << 32) | lo; };
+    const uint32_t sb0 = smem_u32(sB);
+    const uint32_t B_hi = ((sb0 >> 4) & 0x3FFFu) | (((kBLbo >> 4) & 0x3FFFu) << 16);
+    uint32_t it_n = 0, n = 0, bstep = 0;
+    for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x) {
+      const int u = (int)(item / A.groups);
+      if (!in_pass(u)) continue;
+      const uint32_t it = it_n++;
+      const int nchunks = __shfl_sync(0xffffffffu, user_chunks(A.users.offsets, u, 2, cb0, A.max_chunks), 0);
+      mbar_wait(a_ready, it & 1);
+      tc_fence_after();
+      for (int c = 0; c < nchunks; ++c, ++bstep) {
+        const uint32_t st = bstep % ts::STAGES;
+        mbar_wait(&b_full[st], (bstep / ts::STAGES) & 1);
+        const uint32_t bh = B_hi + st * kStage;
+#pragma unroll
+        for (int t = 0; t < TPC; ++t, ++n) {
+          const uint32_t buf = n & 1u, use = n >> 1;
+          const uint32_t d_t = tmem + buf * ts::NROW;
+          const uint32_t a_t = tmem + ts::COL_A + t * ts::A_COLS;
+          mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u);
+          mbar_wait(&e_full[buf], use & 1u);
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int s2 = 0; s2 < 4; ++s2) mma_f16_ts(d_t, a_t + s2 * 8, mk(bh + s2 * kBStep), idN, s2 != 0);
+            mma_f16_ts(d_t, tmem + ts::COL_EXT + buf * 8, mk(bh + 4 * kBStep), idN, 1);  // ext: hi-plane k-chunks 8, 9
+#pragma unroll
+            for (int s8 = 0; s8 < 2; ++s8) mma_f8_ts(d_t, a_t + 32 + s8 * 8, mk(bh + b8l + s8 * kBStep), idN8, 1);
+#pragma unroll
+            for (int s8 = 0; s8 < 2; ++s8) mma_f8_ts(d_t, a_t + 48 + s8 * 8, mk(bh + b8h + s8 * kBStep), idN8, 1);
+            mma_commit(&acc_full[buf]);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) mma_commit(&b_empty[st]);
+        __syncwarp();
+      }
+      if (elect_one()) mma_commit(a_free);
+      __syncwarp();
+    }
+  } else {
+    // =================================================== epilogue warps ============================================
+    const int egrp = warp >> 3, qd = warp & 3, hs = (warp >> 2) & 1;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    const NaisBranch& br = A.p.branch[0];
+    const float nl2e = -1.4426950408889634f, dsc = A.p.dist_scale * nl2e;
+    const float w00 = g.lanes ? __ldg(A.p.dist_w + 0) * dsc : 0.f, w01 = g.lanes ? __ldg(A.p.dist_w + 1) * dsc : 0.f;
+    const float w10 = g.lanes ? __ldg(A.p.dist_w + 2) * dsc : 0.f, w11 = g.lanes ? __ldg(A.p.dist_w + 3) * dsc : 0.f;
+    const float bd0s = (g.lanes ? __ldg(A.p.dist_b + 0) * nl2e : 0.f) - log2f(sc.sAe);
+    const float bd1s = (g.lanes ? __ldg(A.p.dist_b + 1) * nl2e : 0.f) - log2f(sc.sAe);
+    const float inv_sAe = 1.f / sc.sAe, c_a2 = sc.inv_sigma * 1.4426950408889634f, beta = A.p.beta;
+    const int nposb = sc.npos >> 4, nposm = sc.npos & 15;
+    // the constant column of an A_ext block: slot hs 0 carries (1, 1) * sAe (pairs with hi / lo of the bias), slot 1 zeros
+    const uint32_t ext_const = hs == 0 ? ((uint32_t)__half_as_ushort(__float2half(sc.sAe)) * 0x10001u) : 0u;
+    const uint32_t t_ext = tmem + lane_addr + ts::COL_EXT + egrp * 8 + hs * 4;
+    const uint32_t t_main = tmem + lane_addr + egrp * ts::NROW + hs * 64, t_aux = tmem + lane_addr + egrp * ts::NROW + 128 + 2 * hs;
+    uint32_t n0 = 0, gph = 0, it_n = 0;
+
+    for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x) {
+      const int u = (int)(item / A.groups), grp = (int)(item % A.groups);
+      const int64_t hb = A.users.offsets[u];
+      const int H = (int)(A.users.offsets[u + 1] - hb);
+      if (!user_in_pass(A.gate, sc.use_mix, H)) {
+        if (tid == 0) atomicAdd(reinterpret_cast<unsigned*>(const_cast<unsigned char*>(A.hdr) + HDR_ROUND) + (A.gate == 0 ? 1 : 0), 1u);
+        continue;
+      }
+      const uint32_t it = it_n++;
+      const int nchunks = user_chunks(A.users.offsets, u, 2, cb0, A.max_chunks);
+      const int nsteps = nchunks * TPC;
+      if (tid == 0) {
+        // Round barrier across the persistent CTAs: CTA b takes items b, b + grid, ... so every CTA is on the same ~1.4 users at
+        // the same time and their operand chunks are fetched from DRAM once and re-read from L2 by the other ~100 CTAs —
+        // but only while the CTAs stay within ~20 us of each other (the stream through L2 is 3.5 TB/s).  All CTAs are
+        // co-resident (grid <= SM count, 1 CTA per SM), so waiting for the others cannot deadlock; items this pass skips
+        // were counted when they were skipped.
+        // (split barrier: a CTA arrives when the step loop of an item ends, below, and waits here, before the next item's
+        // first operand fetches matter, for every item of the earlier rounds; the item epilogue overlaps the wait)
+        unsigned* cnt = reinterpret_cast<unsigned*>(const_cast<unsigned char*>(A.hdr) + HDR_ROUND) + (A.gate == 0 ? 1 : 0);
+        const int64_t before = (item / gridDim.x) * (int64_t)gridDim.x;
+        const unsigned target = (unsigned)(A.n_items < before ? A.n_items : before);
+        unsigned seen;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+        } while (seen < target);
+      }
+      epi_bar();
+      for (int i = tid; i < H && i < HMETA; i += EPI_THREADS) {
+        hm_id[i] = __ldg(A.users.items + hb + i);
+        hm_la[i] = g.lanes ? __ldg(A.users.coords + 2 * (hb + i)) : 0.f;
+        hm_lo[i] = g.lanes ? __ldg(A.users.coords + 2 * (hb + i) + 1) : 0.f;
+      }
+      float clat[TPC], clon[TPC], sumE[TPC], sumES[TPC];
+      int jt[TPC];
+      bool excl[TPC];
+#pragma unroll
+      for (int t = 0; t < TPC; ++t) {
+        const int64_t j = A.poi_begin + ((int64_t)grp * TPC + t) * TM + r;
+        const bool v = j < A.poi_end;
+        jt[t] = v ? (int)j : -2;
+        clat[t] = (v && g.lanes) ? __ldg(A.cat.coords + 2 * (j - A.cat.row_base)) : 0.f;
+        clon[t] = (v && g.lanes) ? __ldg(A.cat.coords + 2 * (j - A.cat.row_base) + 1) : 0.f;
+        sumE[t] = 0.f;
+        sumES[t] = 0.f;
+        excl[t] = false;
+      }
+      // ---- the item's three candidate tiles: staging area -> TMEM (warp / 4 = tile; the 4th warp of a lane quarter has none) ---
+      mbar_wait(a_free, (it & 1u) ^ 1u);
+      mbar_wait(sa_full, it & 1u);
+      tc_fence_after();
+      {
+        const int ta = warp >> 2;
+        if (ta < TPC) {
+          const unsigned char* src = sA + (size_t)ta * ts::ATILE + (size_t)r * 16;
+          const uint32_t t_a = tmem + lane_addr + ts::COL_A + ta * ts::A_COLS;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {  // 4 column groups (16 TMEM columns) per store
+            uint32_t c16[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 x = *reinterpret_cast<const uint4*>(src + (size_t)(q4 * 4 + i) * TM * 16);
+              c16[4 * i] = x.x, c16[4 * i + 1] = x.y, c16[4 * i + 2] = x.z, c16[4 * i + 3] = x.w;
+            }
+            tmem_st16(t_a + q4 * 16, c16);
+          }
+          tmem_wait_st();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(a_ready);
+          mbar_arrive(sa_empty);
+        }
+      }
+      epi_bar();  // history meta staged
+
+      auto hist_coords = [&](int h, float& la, float& lo) {
+        if (h < HMETA) {
+          la = hm_la[h];
+          lo = hm_lo[h];
+        } else {
+          la = __ldg(A.users.coords + 2 * (hb + h));
+          lo = __ldg(A.users.coords + 2 * (hb + h) + 1);
+        }
+      };
+      // A_ext block of (chunk pc, tile slot) for this thread's (row, history slot): [g_hi | g_lo | g_hi | const] -> 4 TMEM columns
+      auto produce = [&](int pc, float cla, float clo) {
+        const int h = 2 * pc + hs;
+        float g0 = 0.f, g1 = 0.f;
+        if (g.lanes && h < H) {
+          float hla, hlo;
+          hist_coords(h, hla, hlo);
+          const float l0 = fabsf(cla - hla), l1 = fabsf(clo - hlo);
+          const float z0 = fmaf(l1, w01, fmaf(l0, w00, bd0s)), z1 = fmaf(l1, w11, fmaf(l0, w10, bd1s));
+          g0 = rcp_approx(ex2_approx(z0) + inv_sAe);
+          g1 = rcp_approx(ex2_approx(z1) + inv_sAe);
+        }
+        const __half2 hi2 = __floats2half2_rn(g0, g1);
+        const float2 hif = __half22float2(hi2);
+        const __half2 lo2 = __floats2half2_rn(g0 - hif.x, g1 - hif.y);
+        uint32_t col[4];
+        col[0] = *reinterpret_cast<const uint32_t*>(&hi2);
+        col[1] = *reinterpret_cast<const uint32_t*>(&lo2);
+        col[2] = col[0];
+        col[3] = ext_const;
+        tmem_st4(t_ext, col);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&e_full[egrp]);
+      };
+      // One step of this group: tile T (compile time), chunk c.  `more` / (nc, NT): the group's next step, whose A_ext
+      // block this thread writes once the accumulator has been handed back.
+      auto step = [&](auto T_, int c, bool more, int nc, auto NT_) {
+        constexpr int T = decltype(T_)::value, NT = decltype(NT_)::value;
+        const int h = 2 * c + hs;
+        const bool hvalid = h < H;
+        int hist_id = -1;
+        if (hvalid) hist_id = h < HMETA ? hm_id[h] : __ldg(A.users.items + hb + h);
+        mbar_wait(&acc_full[egrp], gph);
+        gph ^= 1u;
+        tc_fence_after();
+        uint32_t aux[2], va[16], vb[16];
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+        auto blk = [&](const uint32_t(&v)[16], int b) {
+          if (b < nposb) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              p0 += fabsf(__uint_as_float(v[i]));
+              p1 += fabsf(__uint_as_float(v[i + 1]));
+              p2 += fabsf(__uint_as_float(v[i + 2]));
+              p3 += fabsf(__uint_as_float(v[i + 3]));
+            }
+          } else if (b > nposb || nposm == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              q0 += fabsf(__uint_as_float(v[i]));
+              q1 += fabsf(__uint_as_float(v[i + 1]));
+              q2 += fabsf(__uint_as_float(v[i + 2]));
+              q3 += fabsf(__uint_as_float(v[i + 3]));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 sg = *reinterpret_cast<const float4*>(sgn_mixed + i);
+              p0 = fmaf(fabsf(__uint_as_float(v[i])), sg.x, p0);
+              p1 = fmaf(fabsf(__uint_as_float(v[i + 1])), sg.y, p1);
+              p2 = fmaf(fabsf(__uint_as_float(v[i + 2])), sg.z, p2);
+              p3 = fmaf(fabsf(__uint_as_float(v[i + 3])), sg.w, p3);
+            }
+          }
+        };
+        // the issuer waits for two things before this accumulator's next step: the accumulator in registers (first) and
+        // the next A_ext block (right after); the FADD tail of this step overlaps the next MMAs
+        tmem_ld2(t_aux, aux);
+        tmem_ld16(t_main, va);
+        tmem_ld16(t_main + 16, vb);
+        tmem_wait_ld16(va);
+        tmem_wait_ld16(vb);
+        blk(va, 0);
+        tmem_ld16(t_main + 32, va);
+        blk(vb, 1);
+        tmem_ld16(t_main + 48, vb);
+        tmem_wait_ld16(va);
+        tmem_wait_ld16(vb);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[egrp]);
+        if (more) produce(nc, clat[NT], clon[NT]);
+        blk(va, 2);
+        blk(vb, 3);
+        const float asum = ((p0 + p1) + (p2 + p3)) - ((q0 + q1) + (q2 + q3));
+        const float S = __uint_as_float(aux[0]) * sc.inv_s;
+        const float a2 = (__uint_as_float(aux[1]) + asum) * c_a2;
+        const bool same = hist_id == jt[T];
+        const float e = (hvalid && !same) ? ex2_approx(a2) : 0.f;
+        sumE[T] += e;
+        sumES[T] = fmaf(e, S, sumES[T]);
+        excl[T] = excl[T] || (hvalid && same);
+      };
+      // The group owns the local steps ls0, ls0 + 2, ...; (chunk, tile) = (ls / 3, ls % 3) repeats every 3 own steps = 2 chunks:
+      //   ls0 = 0: (c,0) (c,2) (c+1,1) | ...      ls0 = 1: (c,1) (c+1,0) (c+1,2) | ...
+      auto run = [&](auto L0_) {
+        constexpr int L0 = decltype(L0_)::value;
+        using I0 = std::integral_constant<int, L0>;
+        using I1 = std::integral_constant<int, (L0 + 2) % 3>;
+        using I2 = std::integral_constant<int, (L0 + 4) % 3>;
+        constexpr int dc1 = (L0 + 2) / 3, dc2 = (L0 + 4) / 3;
+        if (L0 < nsteps) produce(0, clat[L0], clon[L0]);
+        for (int ls = L0, c = 0; ls < nsteps; ls += 6, c += 2) {
+          step(I0{}, c, ls + 2 < nsteps, c + dc1, I1{});
+          if (ls + 2 >= nsteps) break;
+          step(I1{}, c + dc1, ls + 4 < nsteps, c + dc2, I2{});
+          if (ls + 4 >= nsteps) break;
+          step(I2{}, c + dc2, ls + 6 < nsteps, c + 2, I0{});
+        }
+      };
+      if (((egrp - n0) & 1u) == 0) run(std::integral_constant<int, 0>{});
+      else run(std::integral_constant<int, 1>{});
+      if (tid == 0) atomicAdd(reinterpret_cast<unsigned*>(const_cast<unsigned char*>(A.hdr) + HDR_ROUND) + (A.gate == 0 ? 1 : 0), 1u);
+      // ---- item epilogue: 4 partial states per candidate, keyed by (chunk parity, history slot), combined in key order -----
+#pragma unroll
+      for (int t2 = 0; t2 < TPC; ++t2) {
+        const int part = (int)(((egrp + n0 + t2) & 1u) * 2u) + hs;  // chunk parity this group covered for tile t2
+        comb[(part * 3 + 0) * TPC * TM + t2 * TM + r] = sumE[t2];
+        comb[(part * 3 + 1) * TPC * TM + t2 * TM + r] = sumES[t2];
+        comb[(part * 3 + 2) * TPC * TM + t2 * TM + r] = excl[t2] ? 1.f : 0.f;
+      }
+      n0 += (uint32_t)nsteps;
+      epi_bar();
+      const bool small_k = A.k <= 32;
+      if (warp < 4) {
+        unsigned long long kreg[TPC];
+#pragma unroll
+        for (int t2 = 0; t2 < TPC; ++t2) {
+          float E = 0.f, ES = 0.f;
+          bool ex = false;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            E += comb[(q * 3 + 0) * TPC * TM + t2 * TM + r];
+            ES += comb[(q * 3 + 1) * TPC * TM + t2 * TM + r];
+            ex = ex || comb[(q * 3 + 2) * TPC * TM + t2 * TM + r] != 0.f;
+          }
+          const float score = ES / powf(E, beta);
+          const bool valid = jt[t2] >= 0;
+          if (A.all_scores && valid) A.all_scores[(size_t)u * (A.poi_end - A.poi_begin) + (jt[t2] - A.poi_begin)] = score;
+          kreg[t2] = (valid && !(A.exclude && ex)) ? make_key(score, jt[t2]) : 0ull;
+          if (!small_k) keys[t2 * TM + r] = kreg[t2];
+        }
+        if (small_k) {
+          unsigned long long a = warp_sort_desc(kreg[0], lane);
+          a = warp_fold_top32(a, warp_sort_desc(kreg[1], lane), lane);
+          a = warp_fold_top32(a, warp_sort_desc(kreg[2], lane), lane);
+          keys[r] = a;
+        } else {
+          for (int i = TPC * TM + r; i < SORTN; i += TM) keys[i] = 0ull;
+        }
+      }
+      epi_bar();
+      if (small_k) {
+        if (warp == 0) {
+          unsigned long long a = warp_fold_top32(keys[lane], keys[32 + lane], lane);
+          a = warp_fold_top32(a, warp_fold_top32(keys[64 + lane], keys[96 + lane], lane), lane);
+          if (lane < A.k) A.part_keys[((size_t)u * A.groups + grp) * A.k + lane] = a;
+        }
+        continue;
+      }
+      for (int kk = 2; kk <= SORTN; kk <<= 1) {
+        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+          for (int i = tid; i < SORTN; i += EPI_THREADS) {
+            const int ixj = i ^ jj;
+            if (ixj > i) {
+              const unsigned long long x = keys[i], y = keys[ixj];
+              const bool desc = (i & kk) == 0;
+              if (desc ? (x < y) : (x > y)) {
+                keys[i] = y;
+                keys[ixj] = x;
+              }
+            }
+          }
+          epi_bar();
+        }
+      }
+      for (int i = tid; i < A.k; i += EPI_THREADS) A.part_keys[((size_t)u * A.groups + grp) * A.k + i] = keys[i];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == EPI_WARPS) tmem_dealloc(tmem, 512);
+}
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1313,10 +1795,15 @@ int launch_fullrank_tc(const NaisParams& p, const NaisCatalog& cat, const NaisUs
                                               : (fix == 1 ? tc::fullrank_tc_kernel<true, 2, 1> : tc::fullrank_tc_kernel<true, 2, 0>))
                                   : tc::fullrank_tc_kernel<true, 1, 0>)
                    : (gg.hch == 2 ? tc::fullrank_tc_kernel<false, 2, 0> : tc::fullrank_tc_kernel<false, 1, 0>);
-    cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gg.smem_bytes);
+    int smem_bytes = gg.smem_bytes;
+    if (gg.ts) {
+      kern = tc::fullrank_ts_kernel;
+      smem_bytes = tc::ts::SMEM_BYTES;
+    }
+    cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e2 != cudaSuccess) return (int)e2;
     const int grid = (int)(A.n_items < sms ? A.n_items : sms);
-    kern<<<grid, tc::THREADS, gg.smem_bytes, stream>>>(A);
+    kern<<<grid, tc::THREADS, smem_bytes, stream>>>(A);
     NAIS_COUNT_LAUNCH(1);
     e2 = cudaGetLastError();
     return e2 == cudaSuccess ? 0 : (int)e2;
