@@ -493,7 +493,10 @@ __device__ __forceinline__ unsigned long long warp_fold_top32(unsigned long long
 // specialised epilogue step loop (needs kSinglePart and kHch == 2).
 template <bool kSinglePart, int kHch, int kFix>
 __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_constant__ MainArgs A) {
-  constexpr bool kFastEpi = kFix != 0;
+  constexpr bool kFastEpi = kFix == 1 || kFix == 2;
+  // kFix == 3: D = hid = 128 (the reference's default, run.py:837-838) in SPLIT / MIX: the generic code paths below with the
+  // shape constants known at compile time, so the K-part / K-step loops of the issuer unroll and its descriptors fold
+  constexpr bool kD128 = kFix == 3;
   extern __shared__ __align__(128) unsigned char smem[];
   const Geo& g = A.g;
   unsigned char* sA = smem;
@@ -603,7 +606,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
     // UTCHMMA in an R2UR waterfall loop, ~130 clk per MMA).
     // A B chunk arrives in g.kp K-parts (one smem stage each); the tpc accumulators of a chunk stay open across the
     // parts, the ext K-step and the commit come with the last part.
-    if constexpr (kFix != 0) {
+    if constexpr (kFastEpi) {
       // ---- static issuer: D = hid = 64, N = 144, K-steps 4 (fp16) + 1 (ext) [+ 2 + 2 e5m2], stages = 2, buffer == tile ----
       constexpr bool kMix = kFix == 2;
       constexpr uint32_t kNrow = 144, kALbo = TM * 16, kBLbo = kNrow * 16;
@@ -681,21 +684,23 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       }
     } else
     {
-      const uint32_t idN = idesc_f16(TM, g.nrow), id16 = idesc_f16(TM, 16), idN8 = idesc_e5m2(TM, g.nrow);
+      const int nrow_c = kD128 ? 144 : g.nrow, a_plane_c = kD128 ? 16 * TM * 16 : g.a_plane, a_tile_c = kD128 ? 32 * TM * 16 : g.a_tile;
+      const int stage_bytes_c = kD128 ? 10 * 144 * 16 : g.stage_bytes, stages_c = kD128 ? 3 : g.stages;
+      const uint32_t idN = idesc_f16(TM, nrow_c), id16 = idesc_f16(TM, 16), idN8 = idesc_e5m2(TM, nrow_c);
       const uint32_t zaddr = smem_u32(sZ);
-      const uint32_t a_lbo = TM * 16, b_lbo = g.nrow * 16, l_lbo = 16 * 16;
+      const uint32_t a_lbo = TM * 16, b_lbo = nrow_c * 16, l_lbo = 16 * 16;
       const uint32_t a_step = (2 * a_lbo) >> 4, b_step = (2 * b_lbo) >> 4, l_step = (2 * l_lbo) >> 4;
       const uint32_t hi_word = (uint32_t)(smem_desc(0, 0, 128) >> 32);  // SBO = 128 B, version 1, no swizzle
       auto lo_of = [](uint32_t addr, uint32_t lbo) { return ((addr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); };
       auto mk = [&](uint32_t lo) { return ((uint64_t)hi_word << 32) | lo; };
       const uint32_t sa0 = smem_u32(sA), sb0 = smem_u32(sB), se0 = smem_u32(sE);
       // low words for index 0 and the per-index deltas (all linear in the tile / buffer / stage index)
-      const uint32_t A_hi0 = lo_of(sa0, a_lbo), A_lo0 = lo_of(sa0 + g.a_plane, a_lbo), A_d = (uint32_t)g.a_tile >> 4;
+      const uint32_t A_hi0 = lo_of(sa0, a_lbo), A_lo0 = lo_of(sa0 + a_plane_c, a_lbo), A_d = (uint32_t)a_tile_c >> 4;
       const uint32_t E_hi0 = lo_of(se0, zaddr - se0), E_lo0 = lo_of(se0 + TM * 16, zaddr - se0 - TM * 16);
       const uint32_t E_d = (uint32_t)((2 * TM * 16) >> 4) - ((uint32_t)((2 * TM * 16) >> 4) << 16);  // wraps: LBO shrinks as the start grows
-      const uint32_t sbytes = (uint32_t)g.stage_bytes >> 4;
+      const uint32_t sbytes = (uint32_t)stage_bytes_c >> 4;
       const uint32_t B_d = sbytes, Bz_d = sbytes - (sbytes << 16);  // plain / zero-aliased-LBO descriptors, per stage
-      const int kcp = g.kc_part, ks_part = kcp / 2;
+      const int kcp = kD128 ? 4 : g.kc_part, ks_part = kcp / 2;
       const bool split = g.split != 0, mix = g.mix != 0;
       // stage-0 low words.  Inside a stage: hi plane (nkc x k-chunks) then the lo section; nkc = kcp (+1 or, mix, +2 in the last part)
       const uint32_t B_hi0 = lo_of(sb0, b_lbo);
@@ -704,7 +709,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       // B lo section = [e5m2(hi) : kcp/2 k-chunks | e5m2(lo) : kcp/2 k-chunks].  The ext step is one fp16 MMA over two real
       // k-chunks (A_ext buffer = [chunk 0 | chunk 1], B ext chunks kcp, kcp+1 of the hi plane): plain LBOs, no zero alias.
       const int ks8 = kcp / 4;
-      const uint32_t A8_0 = lo_of(sa0 + g.a_plane, a_lbo), A8l_0 = lo_of(sa0 + g.a_plane + g.a_plane / 2, a_lbo);
+      const uint32_t A8_0 = lo_of(sa0 + a_plane_c, a_lbo), A8l_0 = lo_of(sa0 + a_plane_c + a_plane_c / 2, a_lbo);
       const uint32_t Em_0 = lo_of(se0, TM * 16), Em_d = (uint32_t)((2 * TM * 16) >> 4);
       const uint32_t Bem_0 = lo_of(sb0 + kcp * b_lbo, b_lbo);
       const uint32_t bex = sb0 + kcp * b_lbo;                                                       // ext k-chunk, hi plane (last part)
@@ -723,8 +728,9 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
         const int nchunks = __shfl_sync(0xffffffffu, user_chunks(A.users.offsets, u, kHch, cb0, A.max_chunks), 0);
         mbar_wait(a_full, it & 1);
         for (int c = 0; c < nchunks; ++c, n += (uint32_t)tpc) {
-          const int kp_m = kSinglePart ? 1 : g.kp;
-          for (int pp = 0; pp < kp_m; ++pp) {
+          const int kp_m = kSinglePart ? 1 : (kD128 ? 4 : g.kp);
+#pragma unroll
+          for (int pp = 0; pp < (kD128 ? 4 : kp_m); ++pp) {
             const bool lastp = kSinglePart ? true : pp == kp_m - 1;
             mbar_wait(&b_full[st], stph);
             const uint32_t lo_off = lastp ? lo_off_last : lo_off_mid;
@@ -778,7 +784,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
             }
             if (elect_one()) mma_commit(&b_empty[st]);
             __syncwarp();
-            if (++st == (uint32_t)g.stages) {
+            if (++st == (uint32_t)stages_c) {
               st = 0;
               stph ^= 1;
             }
@@ -1794,7 +1800,11 @@ int launch_fullrank_tc(const NaisParams& p, const NaisCatalog& cat, const NaisUs
         gg.kp == 1 ? (gg.hch == 2 ? (fix == 2 ? tc::fullrank_tc_kernel<true, 2, 2>
                                               : (fix == 1 ? tc::fullrank_tc_kernel<true, 2, 1> : tc::fullrank_tc_kernel<true, 2, 0>))
                                   : tc::fullrank_tc_kernel<true, 1, 0>)
-                   : (gg.hch == 2 ? tc::fullrank_tc_kernel<false, 2, 0> : tc::fullrank_tc_kernel<false, 1, 0>);
+                   : (gg.hch == 2 ? tc::fullrank_tc_kernel<false, 2, 0>
+                               : (gg.D == 128 && gg.hid == 128 && gg.kp == 4 && gg.nrow == 144 && gg.stages == 3 && (gg.mix || gg.split) &&
+                                          !getenv("NAIS_TC_GENERIC")
+                                      ? tc::fullrank_tc_kernel<false, 1, 3>
+                                      : tc::fullrank_tc_kernel<false, 1, 0>));
     int smem_bytes = gg.smem_bytes;
     if (gg.ts) {
       kern = tc::fullrank_ts_kernel;
