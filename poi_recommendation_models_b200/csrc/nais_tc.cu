@@ -1239,7 +1239,12 @@ constexpr int ATILE = 2 * 8 * TM * 16;       // 32 KB: the MIX candidate-tile im
 constexpr int SMEM_BYTES = STAGES * BCHUNK + TPC * ATILE + SORTN * 8 + 4 * 3 * TPC * TM * 4 + 3 * HMETA * 4 + 64 + 256 + 64;
 }  // namespace ts
 
-__global__ void __launch_bounds__(THREADS, 1) fullrank_ts_kernel(const __grid_constant__ MainArgs A) {
+// 19 warps: 16 epilogue, warp 16 / warp 18 = MMA issuers of the even / odd steps (= accumulator 0 / 1), warp 17 = producer.
+// With two accumulators the hand-back of accumulator g and the issue of its next step must fit inside the OTHER
+// accumulator's MMA time; an issuer per accumulator sits on its barriers and starts the moment they open, instead of first
+// finishing the other step's 9 MMAs.
+constexpr int TS_THREADS = THREADS + 32;
+__global__ void __launch_bounds__(TS_THREADS, 1) fullrank_ts_kernel(const __grid_constant__ MainArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   const Geo& g = A.g;
   unsigned char* sB = smem;
@@ -1270,7 +1275,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_ts_kernel(const __grid_co
   if (tid == 0) {
     for (int i = 0; i < ts::STAGES; ++i) {
       mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);
+      mbar_init(&b_empty[i], 2);  // both issuers commit: every chunk's 3 steps include both parities
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&e_full[i], ARRIVE_WARPS);
@@ -1278,7 +1283,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_ts_kernel(const __grid_co
       mbar_init(&acc_empty[i], ARRIVE_WARPS);
     }
     mbar_init(a_ready, EPI_WARPS);
-    mbar_init(a_free, 1);
+    mbar_init(a_free, 2);
     mbar_init(sa_full, 1);
     mbar_init(sa_empty, EPI_WARPS);
     fence_barrier_init();
@@ -1320,8 +1325,9 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_ts_kernel(const __grid_co
         __syncwarp();
       }
     }
-  } else if (warp == EPI_WARPS) {
-    // =================================================== MMA issuer ================================================
+  } else if (warp == EPI_WARPS || warp == EPI_WARPS + 2) {
+    // =================================================== MMA issuers (one per accumulator) ==========================
+    const uint32_t par = warp == EPI_WARPS ? 0u : 1u;
     constexpr uint32_t kBLbo = ts::NROW * 16, kBStep = (2 * kBLbo) >> 4, kStage = ts::BCHUNK >> 4;
     constexpr uint32_t idN = idesc_f16(TM, ts::NROW), idN8 = idesc_e5m2(TM, ts::NROW);
     constexpr uint32_t b8h = (10 * kBLbo) >> 4, b8l = (14 * kBLbo) >> 4;  // e5m2(hi) / e5m2(lo) planes of a chunk
@@ -1343,7 +1349,8 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_ts_kernel(const __grid_co
         const uint32_t bh = B_hi + st * kStage;
 #pragma unroll
         for (int t = 0; t < TPC; ++t, ++n) {
-          const uint32_t buf = n & 1u, use = n >> 1;
+          if ((n & 1u) != par) continue;
+          const uint32_t buf = par, use = n >> 1;
           const uint32_t d_t = tmem + buf * ts::NROW;
           const uint32_t a_t = tmem + ts::COL_A + t * ts::A_COLS;
           mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u);
@@ -1813,7 +1820,7 @@ int launch_fullrank_tc(const NaisParams& p, const NaisCatalog& cat, const NaisUs
     cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e2 != cudaSuccess) return (int)e2;
     const int grid = (int)(A.n_items < sms ? A.n_items : sms);
-    kern<<<grid, tc::THREADS, smem_bytes, stream>>>(A);
+    kern<<<grid, gg.ts ? tc::TS_THREADS : tc::THREADS, smem_bytes, stream>>>(A);
     NAIS_COUNT_LAUNCH(1);
     e2 = cudaGetLastError();
     return e2 == cudaSuccess ? 0 : (int)e2;
