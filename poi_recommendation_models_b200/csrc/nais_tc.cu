@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       mbar_init(&b_empty[i], 1);
     }
     for (int i = 0; i < NBUF; ++i) {
-      mbar_init(&e_full[i], kFastEpi ? ARRIVE_WARPS / 2 : ARRIVE_WARPS);  // fast epilogue: one warp of each slot pair writes the row
+      mbar_init(&e_full[i], ARRIVE_WARPS);
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_full[NBUF + i], 1);
       mbar_init(&acc_empty[i], ARRIVE_WARPS);
@@ -858,16 +858,9 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
         // Every step index is then (chunk, t) with buffer == t, so the t loop unrolls with compile-time TMEM / A_ext
         // addresses, the per-chunk history lookups leave the step body, and this group's acc_full parity is one bit that
         // flips once per own chunk.  ~150 issue slots per warp-step instead of ~340 (the MIX mode is epilogue-issue bound).
-        // A_ext of (chunk pc, tile t).  The row of a candidate is 16 bytes per k-chunk; a thread that stored only its own
-        // history slot's 4 bytes made every store 4-way bank conflicted (lanes are 16 B apart), and those conflicts cost the
-        // shared-memory port ~60 clk per step that the MMAs' operand fetches need.  So ONE warp of each (slot 0, slot 1) pair
-        // builds the whole row — both slots, 4 sigmoids — and writes it with two conflict-free 16-byte stores; the pair
-        // splits the tiles (tile 0: slot-0 warp, tile 1: slot-1 warp, tile 2: alternating with the chunk).
-        //   split / fast: [hi plane | lo plane] rows (g0 g1 | g0' g1' | 1 0 0 0) ; mix: [k-chunk 0 | k-chunk 1] rows
-        //   (g_hi g_hi' 1 1 0 0) and (g_lo g_lo' | g_hi g_hi')      sAe / (1 + 2^z) = 1 / (1/sAe + 2^(z - log2 sAe))
-        unsigned char* const ebase = sE + r * 16;
-        const uint32_t one16 = (uint32_t)__half_as_ushort(__float2half(sc.sAe));
-        auto sig2 = [&](bool on, float hla, float hlo, float cla, float clo, uint32_t& hi, uint32_t& lo) {
+        const unsigned char* ebase = sE + r * 16 + hs * 4;
+        // A_ext of (chunk pc, tile t): 2 sigmoids -> hi/lo halves.  sAe / (1 + 2^z) = 1 / (1/sAe + 2^(z - log2 sAe))
+        auto produce_f = [&](int t, bool on, float hla, float hlo, float cla, float clo) {
           float g0 = 0.f, g1 = 0.f;
           if (on) {
             const float l0 = fabsf(cla - hla), l1 = fabsf(clo - hlo);
@@ -878,23 +871,10 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
           const __half2 hi2 = __floats2half2_rn(g0, g1);
           const float2 hif = __half22float2(hi2);
           const __half2 lo2 = __floats2half2_rn(g0 - hif.x, g1 - hif.y);
-          hi = *reinterpret_cast<const uint32_t*>(&hi2);
-          lo = *reinterpret_cast<const uint32_t*>(&lo2);
-        };
-        // pc: the chunk the block is for; this warp produces tile t of it iff mine(pc, t)
-        auto mine = [&](int pc, int t) { return t == 2 ? (((pc >> 1) & 1) == hs) : (t == hs); };
-        auto produce_f = [&](int t, bool on0, bool on1, const float (&hc)[4], float cla, float clo) {
-          uint32_t h0, l0, h1, l1;
-          sig2(on0, hc[0], hc[1], cla, clo, h0, l0);
-          sig2(on1, hc[2], hc[3], cla, clo, h1, l1);
-          unsigned char* eb = ebase + t * (2 * TM * 16);
-          if (g.mix) {
-            *reinterpret_cast<uint4*>(eb) = make_uint4(h0, h1, one16 * 0x10001u, 0u);
-            *reinterpret_cast<uint4*>(eb + TM * 16) = make_uint4(l0, l1, h0, h1);
-          } else {
-            *reinterpret_cast<uint4*>(eb) = make_uint4(h0, h1, one16, 0u);
-            *reinterpret_cast<uint4*>(eb + TM * 16) = make_uint4(l0, l1, 0u, 0u);
-          }
+          unsigned char* eb = const_cast<unsigned char*>(ebase) + t * (2 * TM * 16);
+          *reinterpret_cast<__half2*>(eb) = hi2;
+          *reinterpret_cast<__half2*>(eb + TM * 16) = lo2;
+          if (g.mix) *reinterpret_cast<__half2*>(eb + TM * 16 + 8) = hi2;
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(&e_full[t]);
@@ -912,13 +892,11 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
 #pragma unroll
         for (int t = 0; t < TPC; ++t) jt[t] = jid[t] < A.poi_end ? (int)jid[t] : -2;
         if (egrp == 0 && nchunks > 0) {  // prologue: chunk 0's A_ext
-          const bool on0 = g.lanes && 0 < H, on1 = g.lanes && 1 < H;
-          float hc[4] = {0.f, 0.f, 0.f, 0.f};
-          if (on0) hist_coords(0, hc[0], hc[1]);
-          if (on1) hist_coords(1, hc[2], hc[3]);
+          const bool on = g.lanes && hs < H;
+          float la = 0.f, lo = 0.f;
+          if (on) hist_coords(hs, la, lo);
 #pragma unroll
-          for (int t = 0; t < TPC; ++t)
-            if (mine(0, t)) produce_f(t, on0, on1, hc, clat[t], clon[t]);
+          for (int t = 0; t < TPC; ++t) produce_f(t, on, la, lo, clat[t], clon[t]);
         }
         const uint32_t tb_main = tmem + lane_addr + (uint32_t)(hs * 64), tb_aux = tmem + lane_addr + 128u + (uint32_t)(2 * hs);
         for (int c = egrp; c < nchunks; c += 2) {
@@ -927,10 +905,9 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
           int hist_id = -1;
           if (hvalid) hist_id = h < HMETA ? hm_id[h] : __ldg(A.users.items + hb + h);
           const bool pn = c + 1 < nchunks;            // this group refills the A_ext buffers for the other group's next chunk
-          const bool pon0 = pn && g.lanes && (2 * c + 2 < H), pon1 = pn && g.lanes && (2 * c + 3 < H);
-          float nhc[4] = {0.f, 0.f, 0.f, 0.f};
-          if (pon0) hist_coords(2 * c + 2, nhc[0], nhc[1]);
-          if (pon1) hist_coords(2 * c + 3, nhc[2], nhc[3]);
+          const bool pon = pn && g.lanes && (h + 2 < H);
+          float nla = 0.f, nlo = 0.f;
+          if (pon) hist_coords(h + 2, nla, nlo);
 #pragma unroll
           for (int t = 0; t < TPC; ++t) {
             mbar_wait(&acc_full[egrp * NBUF + t], fph);
@@ -971,7 +948,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
             tmem_ld2(tb_aux + t * ACC_STRIDE, aux);
             tmem_ld16(tb_main + t * ACC_STRIDE, va);
             tmem_ld16(tb_main + t * ACC_STRIDE + 16, vb);
-            if (pn && mine(c + 1, t)) produce_f(t, pon0, pon1, nhc, clat[t], clon[t]);
+            if (pn) produce_f(t, pon, nla, nlo, clat[t], clon[t]);
             tmem_wait_ld16(va);
             tmem_wait_ld16(vb);
             blk(va, 0);
