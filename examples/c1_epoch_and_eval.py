@@ -33,7 +33,7 @@ def main():
     ap.add_argument("--pois", type=int, default=38333)
     ap.add_argument("--ref-train-users", type=int, default=24)
     ap.add_argument("--ref-eval-users", type=int, default=8)
-    ap.add_argument("--precision", default="tc_split")
+    ap.add_argument("--precision", default="auto")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     D = hid = 64
@@ -88,6 +88,22 @@ def main():
     torch.cuda.synchronize()
     t_train_dev = time.perf_counter() - t0
 
+    # ---- ... and with the row-sparse Adagrad fused into the backward's segment reduce (f2): no dense table gradients ------
+    model3 = M.NAIS_region_distance_Embedding(args.pois, D, hid, beta, data.region_num, 1).to(dev)
+    model3.load_state_dict(sd0)
+    opt3 = torch.optim.Adagrad(model3.parameters(), lr=lr, weight_decay=0.0)
+    bt3 = PB.DeviceBatcher(csr, data.region, data.coords, device=dev, seed=0)
+    model3.train()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    loss3 = torch.zeros((), device=dev)
+    for u in order:
+        hist, tgt, label, hreg, treg, ll = bt3.batch(u, num_ng)
+        loss3 += model3.fused_adagrad_step(opt3, label, hist, tgt, hreg, treg, ll)
+    torch.cuda.synchronize()
+    t_train_fused = time.perf_counter() - t0
+    fused_vs_dense = max(float((a.detach() - b.detach()).abs().max()) for a, b in zip(model3.parameters(), model2.parameters()))
+
     # ---- oracle replay of the first steps (float64, same RNG stream) ---------------------------------------------------
     random.setstate(rng_state)
     ref_sd, ref_sum = {k: v.double() for k, v in sd0.items()}, None
@@ -138,6 +154,8 @@ def main():
         "train": {"gpu_s": t_train, "gpu_users_per_s": args.users / t_train, "epoch_loss_sum": loss_sum,
                   "device_batcher_gpu_s": t_train_dev, "device_batcher_users_per_s": args.users / t_train_dev,
                   "device_batcher_epoch_loss_sum": float(loss2),
+                  "fused_adagrad_gpu_s": t_train_fused, "fused_adagrad_users_per_s": args.users / t_train_fused,
+                  "fused_adagrad_epoch_loss_sum": float(loss3), "fused_vs_dense_max_abs_param_diff_after_epoch": fused_vs_dense,
                   "oracle_users_per_s": args.ref_train_users / t_ref_train, "oracle_users": args.ref_train_users,
                   "max_abs_param_diff_after_oracle_steps": train_diff},
         "eval": {"gpu_s": t_eval, "gpu_users_per_s": args.users / t_eval, "precision": args.precision,
