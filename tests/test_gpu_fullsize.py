@@ -1,5 +1,5 @@
-"""Parity at BASELINE.json's full C2 size (40 000 POIs, history 128, D = hid = 64, top-20), where the float64 oracle is too
-slow to run: size-independent properties of the fused tensor path —
+"""Parity at BASELINE.json's full C2 size (40 000 POIs, history 128, D = hid = 64, top-20) and full C4 catalogue (1 000 000
+POIs), where the CPU oracle is too slow to run: size-independent properties of the fused tensor path —
   * its top-20 lists are valid top-20s of the exact-FP32 kernel's scores outside 1e-4 tie bands (two independent kernels:
     tcgen05 fp16/e5m2 operands vs CUDA-core FP32 FFMA; the FP32 kernel itself is pinned against the oracle at small sizes),
   * its scores agree with the FP32 kernel's on every one of 40 000 x users pairs within the condition-aware 1e-4,
@@ -104,3 +104,44 @@ def test_c2_shards_slices_and_idempotence(c2):
     assert torch.equal(mi, full[1]) and torch.equal(ms, full[0])
     sl = ops.fullrank_topk(m.variant, 0.5, m._params(), m._catalog, users.slice(37, 111), k, precision="tc_auto")
     assert torch.equal(sl[1], full[1][37:111]) and torch.equal(sl[0], full[0][37:111])
+
+
+def test_c4_million_poi_catalogue_shards_and_lists():
+    """C4's catalogue (1 000 000 POIs, 256 MB of embedding tables): eight 125 000-POI range shards + merge == one range
+    (bitwise), the tensor path's top-20 lists are valid top-20s of the FP32 kernel's scores, and one user's million scores
+    are within the condition-aware 1e-4 of the float64 oracle."""
+    from poi_recommendation_models_b200.distributed import shard_range
+    N, H, D, hid, U, k = 1000000, 128, 64, 64, 6, 20
+    coords, region, R = synthetic.make_catalog(N, seed=0)
+    g = torch.Generator().manual_seed(1)
+    torch.manual_seed(1)
+    m = M.NAIS_region_distance_Embedding(N, D, hid, 0.5, R, 1)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if name.startswith("embed_"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.3)
+            elif name.endswith(".bias"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+    m = m.cuda().eval()
+    m.set_catalog(region=region, coords=coords)
+    hist = bench.synth_histories(U, N, H, seed=2)
+    users = m.make_users(np.arange(0, (U + 1) * H, H, dtype=np.int64), hist.reshape(-1))
+    full = ops.fullrank_topk(m.variant, 0.5, m._params(), m._catalog, users, k, precision="tc_auto")
+    parts = [ops.fullrank_topk(m.variant, 0.5, m._params(), m._catalog, users, k, *shard_range(N, r, 8), precision="tc_auto") for r in range(8)]
+    ms, mi = ops.topk_merge(torch.stack([p[0] for p in parts], 1), torch.stack([p[1] for p in parts], 1))
+    assert torch.equal(mi, full[1]) and torch.equal(ms, full[0])
+    sub = users.slice(0, 2)
+    ref = ops.fullrank_scores(m.variant, 0.5, m._params(), m._catalog, sub, precision="fp32").cpu().numpy().astype(np.float64)
+    i_tc = full[1].cpu().numpy()
+    for u in range(2):
+        r = ref[u].copy()
+        r[hist[u]] = -np.inf
+        kth = np.sort(r)[::-1][k - 1]
+        got = r[i_tc[u]]
+        assert (got >= kth - util.TOL * max(abs(kth), 1e-30)).all() and not set(i_tc[u].tolist()) & set(hist[u].tolist())
+        assert np.all(np.abs(np.sort(got)[::-1] - np.sort(r)[::-1][:k]) <= util.TOL * np.maximum(np.abs(got), 1e-30))
+    got0 = ops.fullrank_scores(m.variant, 0.5, m._params(), m._catalog, users.slice(0, 1), precision="tc_auto").cpu().numpy().astype(np.float64)[0]
+    o_s, o_scale = _oracle_on_gpu(m, coords, region, hist[0], np.arange(N), chunk=4000)
+    err_tc, err_fp32 = util.cond_err(got0, o_s, o_scale), util.cond_err(ref[0], o_s, o_scale)
+    assert err_tc < util.TOL and err_fp32 < 1e-5, (err_tc, err_fp32)
+    print("C4 catalogue (1M POIs) conditioned error vs float64 oracle:", {"tc_auto": err_tc, "fp32": err_fp32})
