@@ -491,7 +491,8 @@ __device__ __forceinline__ unsigned long long warp_fold_top32(unsigned long long
 // precision with every tile constant known at compile time: a fully unrolled MMA issue sequence (descriptor = base +
 // immediate; the generic issuer spends ~15 instructions per MMA, which paces the kernel once a step is 9 MMAs) and the
 // specialised epilogue step loop (needs kSinglePart and kHch == 2).
-template <bool kSinglePart, int kHch, int kFix>
+// kS: the static shape D = hid = kS of kFix 1 / 2 (64: the headline workload; 32: the small end of the C5 sweep).
+template <bool kSinglePart, int kHch, int kFix, int kS = 64>
 __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_constant__ MainArgs A) {
   constexpr bool kFastEpi = kFix == 1 || kFix == 2;
   // kFix == 3: D = hid = 128 (the reference's default, run.py:837-838) in SPLIT / MIX: the generic code paths below with the
@@ -607,12 +608,13 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
     // A B chunk arrives in g.kp K-parts (one smem stage each); the tpc accumulators of a chunk stay open across the
     // parts, the ext K-step and the commit come with the last part.
     if constexpr (kFastEpi) {
-      // ---- static issuer: D = hid = 64, N = 144, K-steps 4 (fp16) + 1 (ext) [+ 2 + 2 e5m2], stages = 2, buffer == tile ----
+      // ---- static issuer: D = hid = kS, N = 2 kS + 16, K-steps kS/16 (fp16) + 1 (ext) [+ 2 x kS/32 e5m2], stages = 2, buffer == tile ----
       constexpr bool kMix = kFix == 2;
-      constexpr uint32_t kNrow = 144, kALbo = TM * 16, kBLbo = kNrow * 16;
+      constexpr uint32_t kKx = kS / 8, kK16 = kS / 16, kK32 = kS / 32;               // x k-chunks, fp16 / e5m2 K-steps
+      constexpr uint32_t kNrow = 2 * kS + 16, kALbo = TM * 16, kBLbo = kNrow * 16;  // 144 (kS = 64) / 80 (32)
       constexpr uint32_t kAStep = (2 * kALbo) >> 4, kBStep = (2 * kBLbo) >> 4;      // one K-step = two 16-byte k-chunks
-      constexpr uint32_t kAPlane = 8 * TM * 16, kATile = (2 * kAPlane) >> 4;        // (16-byte units)
-      constexpr uint32_t kStage = (2 * 9 * kNrow * 16) >> 4;
+      constexpr uint32_t kAPlane = kKx * TM * 16, kATile = (2 * kAPlane) >> 4;      // (16-byte units)
+      constexpr uint32_t kStage = (2 * (kKx + 1) * kNrow * 16) >> 4;
       constexpr uint32_t kExtBuf = (2 * TM * 16) >> 4;
       constexpr uint32_t idN = idesc_f16(TM, kNrow), idN8 = idesc_e5m2(TM, kNrow);
       const uint32_t zaddr = smem_u32(sZ);
@@ -628,8 +630,8 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       constexpr uint32_t kEz = kExtBuf - (kExtBuf << 16), kBz = kStage - (kStage << 16);
       const uint32_t E_mx = lo_of(se0, TM * 16);                            // mix: [chunk 0 | chunk 1]
       const uint32_t B_hi = lo_of(sb0, kBLbo);
-      const uint32_t Bx_hi = lo_of(sb0 + 8 * kBLbo, zaddr - (sb0 + 8 * kBLbo));     // split: ext chunk of the hi plane
-      const uint32_t Bx_lo = lo_of(sb0 + 17 * kBLbo, zaddr - (sb0 + 17 * kBLbo));   //        ... of the lo plane (9 + 8)
+      const uint32_t Bx_hi = lo_of(sb0 + kKx * kBLbo, zaddr - (sb0 + kKx * kBLbo));                  // split: ext chunk of the hi plane
+      const uint32_t Bx_lo = lo_of(sb0 + (2 * kKx + 1) * kBLbo, zaddr - (sb0 + (2 * kKx + 1) * kBLbo));  //  ... of the lo plane
       uint32_t it_n = 0, cc = 0, st = 0, stph = 0;
       for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x) {
         const int u = (int)(item / A.groups);
@@ -652,22 +654,22 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
-              for (int s2 = 0; s2 < 4; ++s2) mma_f16(d_t, mk(ah + s2 * kAStep), mk(bh + s2 * kBStep), idN, s2 != 0);
+              for (int s2 = 0; s2 < (int)kK16; ++s2) mma_f16(d_t, mk(ah + s2 * kAStep), mk(bh + s2 * kBStep), idN, s2 != 0);
               if constexpr (kMix) {
-                mma_f16(d_t, mk(E_mx + t * kExtBuf), mk(bh + 4 * kBStep), idN, 1);               // ext: hi-plane chunks 8, 9
-                constexpr uint32_t b8h = (10 * kBLbo) >> 4, b8l = (14 * kBLbo) >> 4;              // e5m2(hi) / e5m2(lo) planes
+                mma_f16(d_t, mk(E_mx + t * kExtBuf), mk(bh + kK16 * kBStep), idN, 1);            // ext: hi-plane chunks kKx, kKx + 1
+                constexpr uint32_t b8h = ((kKx + 2) * kBLbo) >> 4, b8l = ((kKx + 2 + kKx / 2) * kBLbo) >> 4;  // e5m2(hi) / e5m2(lo) planes
 #pragma unroll
-                for (int s8 = 0; s8 < 2; ++s8) mma_f8(d_t, mk(al + s8 * kAStep), mk(bh + b8l + s8 * kBStep), idN8, 1);
+                for (int s8 = 0; s8 < (int)kK32; ++s8) mma_f8(d_t, mk(al + s8 * kAStep), mk(bh + b8l + s8 * kBStep), idN8, 1);
 #pragma unroll
-                for (int s8 = 0; s8 < 2; ++s8) mma_f8(d_t, mk(al8 + s8 * kAStep), mk(bh + b8h + s8 * kBStep), idN8, 1);
+                for (int s8 = 0; s8 < (int)kK32; ++s8) mma_f8(d_t, mk(al8 + s8 * kAStep), mk(bh + b8h + s8 * kBStep), idN8, 1);
               } else {
-                constexpr uint32_t blo = (9 * kBLbo) >> 4;                                        // lo plane
+                constexpr uint32_t blo = ((kKx + 1) * kBLbo) >> 4;                                // lo plane
                 mma_f16(d_t, mk(E_hi + t * kEz), mk(bxh), idN, 1);
 #pragma unroll
-                for (int s2 = 0; s2 < 4; ++s2) mma_f16(d_t, mk(ah + s2 * kAStep), mk(bh + blo + s2 * kBStep), idN, 1);
+                for (int s2 = 0; s2 < (int)kK16; ++s2) mma_f16(d_t, mk(ah + s2 * kAStep), mk(bh + blo + s2 * kBStep), idN, 1);
                 mma_f16(d_t, mk(E_hi + t * kEz), mk(bxl), idN, 1);
 #pragma unroll
-                for (int s2 = 0; s2 < 4; ++s2) mma_f16(d_t, mk(al + s2 * kAStep), mk(bh + s2 * kBStep), idN, 1);
+                for (int s2 = 0; s2 < (int)kK16; ++s2) mma_f16(d_t, mk(al + s2 * kAStep), mk(bh + s2 * kBStep), idN, 1);
                 mma_f16(d_t, mk(E_lo + t * kEz), mk(bxh), idN, 1);
               }
               mma_commit(&accf[t]);
@@ -898,7 +900,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
 #pragma unroll
           for (int t = 0; t < TPC; ++t) produce_f(t, on, la, lo, clat[t], clon[t]);
         }
-        const uint32_t tb_main = tmem + lane_addr + (uint32_t)(hs * 64), tb_aux = tmem + lane_addr + 128u + (uint32_t)(2 * hs);
+        const uint32_t tb_main = tmem + lane_addr + (uint32_t)(hs * kS), tb_aux = tmem + lane_addr + (uint32_t)(2 * kS) + (uint32_t)(2 * hs);
         for (int c = egrp; c < nchunks; c += 2) {
           const int h = 2 * c + hs;
           const bool hvalid = h < H;
@@ -951,17 +953,24 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
             if (pn) produce_f(t, pon, nla, nlo, clat[t], clon[t]);
             tmem_wait_ld16(va);
             tmem_wait_ld16(vb);
-            blk(va, 0);
-            tmem_ld16(tb_main + t * ACC_STRIDE + 32, va);
-            blk(vb, 1);
-            tmem_ld16(tb_main + t * ACC_STRIDE + 48, vb);
-            tmem_wait_ld16(va);
-            tmem_wait_ld16(vb);
+            if constexpr (kS == 64) {
+              blk(va, 0);
+              tmem_ld16(tb_main + t * ACC_STRIDE + 32, va);
+              blk(vb, 1);
+              tmem_ld16(tb_main + t * ACC_STRIDE + 48, vb);
+              tmem_wait_ld16(va);
+              tmem_wait_ld16(vb);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[t]);
-            blk(va, 2);
-            blk(vb, 3);
+            if constexpr (kS == 64) {
+              blk(va, 2);
+              blk(vb, 3);
+            } else {  // hid = 32: the slot's 32 columns are already in registers
+              blk(va, 0);
+              blk(vb, 1);
+            }
             const float asum = ((p0 + p1) + (p2 + p3)) - ((q0 + q1) + (q2 + q3));
             const float S = __uint_as_float(aux[0]) * sc.inv_s;
             const float a2 = (__uint_as_float(aux[1]) + asum) * c_a2;
@@ -1777,12 +1786,12 @@ int launch_fullrank_tc(const NaisParams& p, const NaisCatalog& cat, const NaisUs
     A.max_chunks = max_chunks;
     A.gate = gate;
     // static D = hid = 64 instantiations (the reference's C1/C2 shape): 1 = SPLIT, 2 = MIX
-    const int fix = (gg.D == 64 && gg.hid == 64 && gg.kp == 1 && gg.hch == 2 && gg.nrow == 144 && gg.stages == 2 && !getenv("NAIS_TC_GENERIC"))
-                        ? (gg.mix ? 2 : (gg.split ? 1 : 0))
-                        : 0;
+    const bool s64 = gg.D == 64 && gg.hid == 64 && gg.nrow == 144, s32 = gg.D == 32 && gg.hid == 32 && gg.nrow == 80;
+    const int fix = ((s64 || s32) && gg.kp == 1 && gg.hch == 2 && gg.stages == 2 && !getenv("NAIS_TC_GENERIC")) ? (gg.mix ? 2 : (gg.split ? 1 : 0)) : 0;
     void (*kern)(const tc::MainArgs) =
-        gg.kp == 1 ? (gg.hch == 2 ? (fix == 2 ? tc::fullrank_tc_kernel<true, 2, 2>
-                                              : (fix == 1 ? tc::fullrank_tc_kernel<true, 2, 1> : tc::fullrank_tc_kernel<true, 2, 0>))
+        gg.kp == 1 ? (gg.hch == 2 ? (fix == 2 ? (s64 ? tc::fullrank_tc_kernel<true, 2, 2, 64> : tc::fullrank_tc_kernel<true, 2, 2, 32>)
+                                              : (fix == 1 ? (s64 ? tc::fullrank_tc_kernel<true, 2, 1, 64> : tc::fullrank_tc_kernel<true, 2, 1, 32>)
+                                                          : tc::fullrank_tc_kernel<true, 2, 0>))
                                   : tc::fullrank_tc_kernel<true, 1, 0>)
                    : (gg.hch == 2 ? tc::fullrank_tc_kernel<false, 2, 0>
                                : (gg.D == 128 && gg.hid == 128 && gg.kp == 4 && gg.nrow == 144 && gg.stages == 3 && (gg.mix || gg.split) &&
