@@ -268,3 +268,32 @@ def test_tc_auto_gate_per_user_and_weight_scale():
     choice, err = run(big)
     assert choice["use_mix"] == 0 and choice["rho"] > 256, choice
     assert err < util.TOL, err
+
+
+def test_fullrank_topk_is_cuda_graph_capturable():
+    """The C ABI only enqueues on the given stream (no allocation, no synchronisation, no host read-back — the tc_auto
+    precision gate runs on the device), so a whole ranking call can be captured in a CUDA graph and replayed."""
+    N = 1500
+    coords, region, R, sd = _case(N, seed=9)
+    m = util.make_model("region_distance", sd, 0.5)
+    m.set_catalog(region=region, coords=coords)
+    rng = np.random.default_rng(1)
+    lens = [20, 5, 33, 16]
+    indptr = np.concatenate([[0], np.cumsum(lens)])
+    users = m.make_users(indptr, np.concatenate([rng.choice(N, n, replace=False) for n in lens]))
+    P = m._params()
+    for prec in ("tc_auto", "fp32"):
+        eager = ops.fullrank_topk("region_distance", 0.5, P, m._catalog, users, 10, precision=prec)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            ops.fullrank_topk("region_distance", 0.5, P, m._catalog, users, 10, precision=prec)  # warm-up outside the capture
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            s_g, i_g = ops.fullrank_topk("region_distance", 0.5, P, m._catalog, users, 10, precision=prec)
+        s_g.fill_(0)
+        i_g.fill_(0)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(i_g, eager[1]) and torch.equal(s_g, eager[0]), prec
