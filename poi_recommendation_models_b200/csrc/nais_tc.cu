@@ -1365,7 +1365,6 @@ __global__ void __launch_bounds__(TS_THREADS, 1) fullrank_ts_kernel(const __grid
     const int egrp = warp >> 3, qd = warp & 3, hs = (warp >> 2) & 1;
     const int r = qd * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-    const NaisBranch& br = A.p.branch[0];
     const float nl2e = -1.4426950408889634f, dsc = A.p.dist_scale * nl2e;
     const float w00 = g.lanes ? __ldg(A.p.dist_w + 0) * dsc : 0.f, w01 = g.lanes ? __ldg(A.p.dist_w + 1) * dsc : 0.f;
     const float w10 = g.lanes ? __ldg(A.p.dist_w + 2) * dsc : 0.f, w11 = g.lanes ? __ldg(A.p.dist_w + 3) * dsc : 0.f;
