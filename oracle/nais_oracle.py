@@ -295,6 +295,35 @@ def hitrate_at_k(actual, predicted, k: int) -> float:
     return tot / n
 
 
+def precision_at_k_per_sample(actual, predicted, k: int) -> float:
+    """(number of entries of `predicted` that are in `actual`) / k (eval_metrics.py:29-34): no cut at k, repeats count."""
+    n = 0
+    for x in predicted:
+        if x in actual:
+            n += 1
+    return n / (k + 0.0)
+
+
+def apk(actual, predicted, k: int = 10) -> float:
+    """Average precision at k (eval_metrics.py:70-101): sum over ranks i < k of hits(i)/(i+1) at first occurrences of
+    relevant items, divided by min(|actual|, k); 0.0 when `actual` is empty."""
+    if len(predicted) > k:
+        predicted = predicted[:k]
+    score, hits = 0.0, 0.0
+    for i, x in enumerate(predicted):
+        if x in actual and x not in predicted[:i]:
+            hits += 1.0
+            score += hits / (i + 1.0)
+    if not actual:
+        return 0.0
+    return score / min(len(actual), k)
+
+
+def mapk(actual, predicted, k: int = 10) -> float:
+    """numpy mean of apk over users (eval_metrics.py:105-125)."""
+    return float(np.mean([apk(a, p, k) for a, p in zip(actual, predicted)]))
+
+
 def ndcg_at_k(actual, predicted, k: int) -> float:
     """Binary NDCG@k.  NOT in the reference (no NDCG anywhere); project-defined once, here and in
     the product alike: DCG = sum_{i<k} [rec_i in pos]/log2(i+2); IDCG = sum_{i<min(k,|pos|)} 1/log2(i+2); mean over

@@ -1,4 +1,5 @@
-"""Drop-in for the reference's `eval_metrics.py` (precision/recall/hit-rate @k, eval_metrics.py:3-69).
+"""Drop-in for the reference's `eval_metrics.py` (precision/recall/hit-rate @k, eval_metrics.py:3-69; the per-sample
+precision and average-precision helpers, eval_metrics.py:29-34, 70-125).
 
 Numbers are bit-identical to the reference functions: the per-user hit counts are the same integers and they are
 accumulated as Python floats in the same user order with the same divisions.  `evaluate_mp` keeps the reference's
@@ -47,6 +48,33 @@ def hitrate_at_k(actual, predicted, topk):
                 s += 1
             n += 1
     return s / n
+
+
+def precision_at_k_per_sample(actual, predicted, topk):
+    """One user's precision (eval_metrics.py:29-34): every entry of `predicted` found in `actual` counts — the list is
+    NOT cut to `topk` and repeated entries count again, exactly like the reference; `topk` is only the denominator."""
+    return sum(1 for place in predicted if place in actual) / (topk + 0.0)
+
+
+def apk(actual, predicted, k=10):
+    """Average precision at k of one ranked list (eval_metrics.py:70-101): a position scores hits_so_far / position when
+    its item is relevant and has not appeared earlier in the list; normalised by min(|actual|, k); 0.0 without positives."""
+    ranked = predicted[:k] if len(predicted) > k else predicted
+    seen, hits, score = [], 0.0, 0.0
+    for pos, item in enumerate(ranked, start=1):
+        if item in actual and item not in seen:
+            hits += 1.0
+            score += hits / float(pos)
+        seen.append(item)
+    if not actual:
+        return 0.0
+    return score / min(len(actual), k)
+
+
+def mapk(actual, predicted, k=10):
+    """Mean of `apk` over users (eval_metrics.py:105-125); numpy mean like the reference, so the same float64."""
+    import numpy as np
+    return np.mean([apk(a, p, k) for a, p in zip(actual, predicted)])
 
 
 def ndcg_at_k(actual, predicted, topk):

@@ -115,6 +115,31 @@ def test_metrics_bit_identical_to_reference():
             assert PM.hitrate_at_k(actual, pred, k) == ref.hitrate_at_k(actual, pred, k)
 
 
+def test_rank_metrics_bit_identical_to_reference(golden_dir):
+    """apk / mapk / precision_at_k_per_sample drop-ins vs the golden written by the unmodified eval_metrics.py:29-34, 70-125
+    (repeated ids in the ranked list, users without positives, lists shorter than k) and vs the live reference."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mk_rank", os.path.join(golden_dir, "make_golden_rank_metrics.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    g = np.load(os.path.join(golden_dir, "rank_metrics.npz"))
+    actual, predicted = mk.make_lists()
+    for j, k in enumerate(g["ks"].tolist()):
+        for u, (a, p) in enumerate(zip(actual, predicted)):
+            assert PM.apk(a, p, k) == g["apk"][u, j] == orc.apk(a, p, k)
+            assert PM.precision_at_k_per_sample(a, p, k) == g["pps"][u, j]
+        assert PM.mapk(actual, predicted, k) == g["mapk"][j]
+    assert PM.apk([1, 2], [2, 1]) == 1.0 and PM.apk([], [1, 2]) == 0.0
+    if ref_shim.reference_available():
+        ref = ref_shim.load_reference("eval_metrics")
+        rng = np.random.default_rng(5)
+        a2 = [rng.choice(60, rng.integers(0, 7), replace=False).tolist() for _ in range(100)]
+        p2 = [rng.integers(0, 60, 25).tolist() for _ in range(100)]  # with repeats
+        for k in (3, 10, 25, 40):
+            assert PM.mapk(a2, p2, k) == ref.mapk(a2, p2, k)
+            assert all(PM.precision_at_k_per_sample(a, p, k) == ref.precision_at_k_per_sample(a, p, k) for a, p in zip(a2, p2))
+
+
 def test_synthetic_checkins_are_consistent():
     d = synthetic.make_checkins(20, 800, seed=1)
     assert d.indptr[-1] == len(d.indices) and d.region.max() + 1 == d.region_num

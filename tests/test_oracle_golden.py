@@ -95,6 +95,21 @@ def test_geo_matches_reference(golden_dir):
     assert np.array_equal(got[:, 0, :], z["absdiff"].astype(np.float32))
 
 
+def test_rank_metrics_match_reference(golden_dir):
+    """precision_at_k_per_sample / apk / mapk (eval_metrics.py:29-34, 70-125): oracle == reference outputs, bit for bit."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mk_rank", os.path.join(golden_dir, "make_golden_rank_metrics.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    g = np.load(os.path.join(golden_dir, "rank_metrics.npz"))
+    actual, predicted = mk.make_lists()
+    for j, k in enumerate(g["ks"].tolist()):
+        for u, (a, p) in enumerate(zip(actual, predicted)):
+            assert orc.apk(a, p, k) == g["apk"][u, j]
+            assert orc.precision_at_k_per_sample(a, p, k) == g["pps"][u, j]
+        assert orc.mapk(actual, predicted, k) == g["mapk"][j]
+
+
 def test_metric_edge_cases():
     actual = [[1, 2], [], [5]]
     pred = [[2, 9, 1], [3, 4, 5], [6, 7, 8]]
