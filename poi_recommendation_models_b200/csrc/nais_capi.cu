@@ -78,10 +78,10 @@ __global__ void fill_empty_topk_kernel(float* s, int32_t* id, size_t n) {
 __global__ void powerlaw_logscore_kernel(NaisCatalog cat, NaisUsers users, int64_t poi_begin, int64_t poi_end, float ln_a, float b,
                                          float* __restrict__ out) {
   __shared__ float s_la[256], s_lo[256], s_cos[256];
-  const int u = blockIdx.y;
+  const int u = blockIdx.x;  // users on grid.x (no 65 535 limit), candidate blocks on grid.y
   const int64_t hb = users.offsets[u];
   const int H = (int)(users.offsets[u + 1] - hb);
-  const int64_t j = poi_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t j = poi_begin + (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
   const bool valid = j < poi_end;
   float cla = 0.f, clo = 0.f, ccos = 1.f;
   if (valid) {
@@ -290,7 +290,8 @@ int nais_powerlaw_logscore(const NaisCatalog* cat, const NaisUsers* users, int64
   if (!(a > 0.f)) return NAIS_ERR_MODE;
   if (users->n_users == 0 || poi_end == poi_begin) return 0;
   if (!cat->coords || !users->coords || !users->offsets || !out_logg) return NAIS_ERR_NULL;
-  dim3 grid((unsigned)((poi_end - poi_begin + 255) / 256), (unsigned)users->n_users);
+  if ((poi_end - poi_begin + 255) / 256 > 65535) return NAIS_ERR_SHAPE;  // > 16.7 M candidates in one call: pass sub-ranges
+  dim3 grid((unsigned)users->n_users, (unsigned)((poi_end - poi_begin + 255) / 256));
   powerlaw_logscore_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*cat, *users, poi_begin, poi_end, logf(a), b, out_logg);
   NAIS_COUNT_LAUNCH(1);
   return (int)cudaGetLastError();

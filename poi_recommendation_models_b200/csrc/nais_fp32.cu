@@ -607,11 +607,11 @@ int launch_topk_merge(const unsigned long long* in_keys, const float* in_score, 
 }
 
 
-// Keys -> keys (or final score/id) merge of blocks of `lpb` lists; grid (blocks, users).
+// Keys -> keys (or final score/id) merge of blocks of `lpb` lists; grid (users, blocks): users on grid.x (no 65 535 limit).
 __global__ void topk_merge_keys_kernel(const unsigned long long* __restrict__ in, int n_lists, int k, int lpb, int n2,
                                        unsigned long long* out_keys, float* out_score, int32_t* out_id) {
   extern __shared__ __align__(16) unsigned long long mk[];
-  const int u = blockIdx.y, b = blockIdx.x;
+  const int u = blockIdx.x, b = blockIdx.y;
   const int l0 = b * lpb, l1 = min(n_lists, l0 + lpb);
   const int n = (l1 - l0) * k;
   const unsigned long long* src = in + ((size_t)u * n_lists + l0) * k;
@@ -646,7 +646,7 @@ int launch_topk_merge_keys_multi(unsigned long long* keys, unsigned long long* s
     int n2 = 1;
     while (n2 < lpb * k) n2 <<= 1;
     const bool last = blocks == 1;
-    dim3 grid(blocks, n_users);
+    dim3 grid(n_users, blocks);
     const int threads = n2 >= 1024 ? 512 : (n2 < 64 ? 64 : n2 / 2);
     topk_merge_keys_kernel<<<grid, threads, (size_t)n2 * 8, stream>>>(src, n_lists, k, lpb, n2, last ? nullptr : dst, out_score, out_id);
     NAIS_COUNT_LAUNCH(1);

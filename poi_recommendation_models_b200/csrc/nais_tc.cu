@@ -296,7 +296,7 @@ __device__ __forceinline__ int64_t chunk_base(const int64_t* offsets, int u, int
   return hch == 2 ? (offsets[u] + u) >> 1 : offsets[u];
 }
 
-// User operand: grid (chunk slot, user).  One thread = (row n, k-chunk c) -> 8 fp16 (hi) + 8 fp16 (lo).
+// User operand: grid (user, chunk slot) — users ride grid.x, which has no 65 535 limit.  One thread = (row n, k-chunk c) -> 8 fp16 (hi) + 8 fp16 (lo).
 __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g, const unsigned char* hdr, unsigned char* Bimg,
                                   int64_t max_chunks, int gate) {
   const NaisBranch& br = p.branch[0];
@@ -304,7 +304,7 @@ __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g, const un
   const int* perm = reinterpret_cast<const int*>(hdr + HDR_PERM);
   const float* ck = reinterpret_cast<const float*>(hdr + HDR_CK);
   const float* uu = reinterpret_cast<const float*>(hdr + HDR_U);
-  const int u = blockIdx.y;
+  const int u = blockIdx.x;
   const int64_t hb = users.offsets[u];
   const int H = (int)(users.offsets[u + 1] - hb);
   if (!user_in_pass(gate, sc->use_mix, H)) return;  // the other pass of NAIS_PREC_TC_AUTO packs (and scores) this user
@@ -312,7 +312,7 @@ __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g, const un
   const int nchunks = (H + hch - 1) / hch;
   const int D = g.D, hid = g.hid, ldw = D + g.lanes;
   __shared__ float q[2][128];
-  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+  for (int chunk = blockIdx.y; chunk < nchunks; chunk += gridDim.y) {
     __syncthreads();
     for (int i = threadIdx.x; i < hch * D; i += blockDim.x) {
       const int hs = i / D, d = i - hs * D, h = hch * chunk + hs;
@@ -1762,7 +1762,7 @@ int launch_fullrank_tc(const NaisParams& p, const NaisCatalog& cat, const NaisUs
     tc::pack_candidates_kernel<<<n_tiles_pad, 256, 0, stream>>>(p, cat, poi_begin, poi_end, gg, hdr, pimg, gate);
     NAIS_COUNT_LAUNCH(1);
     {
-      dim3 grid(64, users.n_users);
+      dim3 grid(users.n_users, 64);
       tc::pack_users_kernel<<<grid, 256, 0, stream>>>(p, users, gg, hdr, bimg, max_chunks, gate);
       NAIS_COUNT_LAUNCH(1);
     }

@@ -342,7 +342,9 @@ def fullrank_topk(variant: str, beta: float, P: Dict[str, torch.Tensor], cat: De
                                           prec, out_s.data_ptr(), out_i.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
                    "nais_fullrank_topk")
         if precision != "fp32" and ws_bytes >= 128:
-            _LAST_TC_HEADER[0] = ws[64:128]  # device-side scales / precision gate of this call (read lazily, see below)
+            # device-side scales / precision gate of this call, read lazily by last_tc_choice(); a 64-byte copy, not a view:
+            # a view would pin the whole (up to 8 GiB) workspace until the next call
+            _LAST_TC_HEADER[0] = ws[64:128].clone()
     return out_s, out_i
 
 

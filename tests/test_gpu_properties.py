@@ -297,3 +297,26 @@ def test_fullrank_topk_is_cuda_graph_capturable():
         graph.replay()
         torch.cuda.synchronize()
         assert torch.equal(i_g, eager[1]) and torch.equal(s_g, eager[0]), prec
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tc_split", "tc_auto"])
+def test_more_than_65535_users_in_one_call(prec):
+    """User batches beyond CUDA's 65 535 grid.y limit: users ride grid.x in every kernel of the ranking call.  66 000 short
+    users against a thin catalogue; the lists of the first / middle / last users equal a small call on those users alone."""
+    N, U, H, k = 256, 66000, 3, 5
+    coords, region, R, sd = _case(N, seed=11)
+    m = util.make_model("region_distance", sd, 0.5)
+    m.set_catalog(region=region, coords=coords)
+    rng = np.random.default_rng(12)
+    hist = (rng.integers(0, N - H, (U, 1)) + np.arange(H)[None, :]).astype(np.int64)  # distinct items per user
+    indptr = np.arange(0, (U + 1) * H, H, dtype=np.int64)
+    s_all, i_all = m.predict_topk((indptr, hist.reshape(-1)), k, precision=prec)
+    pick = np.array([0, 1, 32767, 65534, 65535, 65536, U - 1])
+    s_few, i_few = m.predict_topk((np.arange(0, (len(pick) + 1) * H, H, dtype=np.int64), hist[pick].reshape(-1)), k, precision=prec)
+    torch.cuda.synchronize()
+    assert torch.equal(i_all[pick], i_few)
+    assert torch.equal(s_all[pick], s_few)
+    from poi_recommendation_models_b200 import powerlaw
+    geo = powerlaw.log_scores(m._catalog, m.make_users(indptr, hist.reshape(-1)), 0.5, -1.2)
+    few = powerlaw.log_scores(m._catalog, m.make_users(np.arange(0, (len(pick) + 1) * H, H, dtype=np.int64), hist[pick].reshape(-1)), 0.5, -1.2)
+    assert torch.equal(geo[pick], few)
