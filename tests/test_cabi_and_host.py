@@ -177,3 +177,33 @@ def test_whole_module_pickle_roundtrip(tmp_path):
         for (k1, v1), (k2, v2) in zip(m.state_dict().items(), m2.state_dict().items()):
             assert k1 == k2 and torch.equal(v1, v2)
         assert m2._catalog.n_rows == 40 and torch.equal(m2._catalog.region, m._catalog.region)
+
+
+def test_ctypes_mirrors_match_the_header_layout(tmp_path):
+    """Every struct of include/nais_b200.h, compiled by gcc as plain C, has the size and field offsets of its ctypes mirror
+    in _lib.py — a drifted mirror would make the library read garbage past the struct (no compute call involved)."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from poi_recommendation_models_b200 import _lib as L
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    structs = ["NaisBranch", "NaisParams", "NaisPairs", "NaisGrads", "NaisAdagrad", "NaisCatalog", "NaisUsers"]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "nais_b200.h"', 'int main(void) {']
+    for s in structs:
+        cls = getattr(L, s)
+        lines.append(f'  printf("{s} %zu\\n", sizeof({s}));')
+        for f, _ in cls._fields_:
+            lines.append(f'  printf("{s}.{f} %zu\\n", offsetof({s}, {f}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", f"-I{inc}", str(src), "-o", str(exe)], check=True)
+    got = dict(ln.split() for ln in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for s in structs:
+        cls = getattr(L, s)
+        assert int(got[s]) == C.sizeof(cls), s
+        for f, _ in cls._fields_:
+            assert int(got[f"{s}.{f}"]) == getattr(cls, f).offset, (s, f)
