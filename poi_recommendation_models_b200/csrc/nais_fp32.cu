@@ -620,7 +620,7 @@ __global__ void topk_merge_keys_kernel(const unsigned long long* __restrict__ in
   bitonic_sort_desc(mk, n2);
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
     if (out_keys) {
-      out_keys[((size_t)u * gridDim.x + b) * k + i] = mk[i];
+      out_keys[((size_t)u * gridDim.y + b) * k + i] = mk[i];
     } else {
       float sc;
       int id;
