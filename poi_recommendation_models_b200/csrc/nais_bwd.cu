@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
   const int tid = threadIdx.x, cell = tid & (TC - 1), half = tid >> 7;
   const int tk = tid & 15, tj = tid >> 4;
   const int n_chunks = (H <= TC) ? 1 : (H + TC - 1) / TC;
+  const bool vec4 = rows_vec4(br, D >> 1);  // 128-bit embedding-row gathers
+  const bool w1_vec2 = (reinterpret_cast<uintptr_t>(br.w1) & 7u) == 0;  // ldw = D + lanes is even: rows of W are 8-byte aligned
 
   // persistent accumulators
   float acc3[NKB * DB][4][4];
@@ -135,11 +137,29 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
           rg = br.w_reg ? A.b.hreg[cidx] : 0;
           const float* qp = br.hist_poi + (size_t)it * br.w_poi;
           const float* qr = br.hist_reg + (size_t)rg * br.w_reg;
-          for (int d = d0; d < d1; ++d) {
-            float q = (d < br.w_poi) ? __ldg(qp + d) : __ldg(qr + d - br.w_poi);
-            float x = q * ps[r * D + d];
-            As[d * TCP + cell] = x;
-            ssum += x;
+          if (vec4) {  // 128-bit row loads (same products, same summation order as the scalar walk and as the forward)
+            const float* pr = ps + r * D;
+#pragma unroll 4
+            for (int d = d0; d < d1; d += 4) {
+              const float4 q = ldg_row4(qp, qr, br.w_poi, d);
+              const float4 t = *reinterpret_cast<const float4*>(pr + d);
+              const float x0 = q.x * t.x, x1 = q.y * t.y, x2 = q.z * t.z, x3 = q.w * t.w;
+              As[d * TCP + cell] = x0;
+              As[(d + 1) * TCP + cell] = x1;
+              As[(d + 2) * TCP + cell] = x2;
+              As[(d + 3) * TCP + cell] = x3;
+              ssum += x0;
+              ssum += x1;
+              ssum += x2;
+              ssum += x3;
+            }
+          } else {
+            for (int d = d0; d < d1; ++d) {
+              float q = (d < br.w_poi) ? __ldg(qp + d) : __ldg(qr + d - br.w_poi);
+              float x = q * ps[r * D + d];
+              As[d * TCP + cell] = x;
+              ssum += x;
+            }
           }
         } else {
           for (int d = d0; d < d1; ++d) As[d * TCP + cell] = 0.f;
@@ -374,7 +394,13 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
             float4 a0 = *reinterpret_cast<const float4*>(ap + k * TCP);
             float4 a1 = *reinterpret_cast<const float4*>(ap + k * TCP + 4);
             const float* wr = wp + (size_t)k * ldw;
-            const float bv[4] = {__ldg(wr), __ldg(wr + 1), __ldg(wr + 2), __ldg(wr + 3)};
+            float bv[4];
+            if (w1_vec2) {  // two 64-bit loads instead of four 32-bit ones (this loop issues most of the kernel's L1 requests)
+              const float2 w01 = __ldg(reinterpret_cast<const float2*>(wr)), w23 = __ldg(reinterpret_cast<const float2*>(wr + 2));
+              bv[0] = w01.x, bv[1] = w01.y, bv[2] = w23.x, bv[3] = w23.y;
+            } else {
+              bv[0] = __ldg(wr), bv[1] = __ldg(wr + 1), bv[2] = __ldg(wr + 2), bv[3] = __ldg(wr + 3);
+            }
             const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -389,14 +415,24 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
             if (rr >= 0) {
               const float gwv = gw[c];
               const int it = citem[c], rg = creg[c];
+              float qv[4];
+              if (vec4) {
+                const float4 q4 = ldg_row4(br.hist_poi + (size_t)it * br.w_poi, br.hist_reg + (size_t)rg * br.w_reg, br.w_poi, d0);
+                qv[0] = q4.x, qv[1] = q4.y, qv[2] = q4.z, qv[3] = q4.w;
+              } else {
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                  const int d = d0 + cc;
+                  qv[cc] = (d < br.w_poi) ? __ldg(br.hist_poi + (size_t)it * br.w_poi + d)
+                                          : __ldg(br.hist_reg + (size_t)rg * br.w_reg + (d - br.w_poi));
+                }
+              }
 #pragma unroll
               for (int cc = 0; cc < 4; ++cc) {
                 const int d = d0 + cc;
                 const float full = dx[i][cc] + gwv;
-                const float q = (d < br.w_poi) ? __ldg(br.hist_poi + (size_t)it * br.w_poi + d)
-                                               : __ldg(br.hist_reg + (size_t)rg * br.w_reg + (d - br.w_poi));
                 o[cc] = full * ps[rr * D + d];
-                dpv[cc] = full * q;
+                dpv[cc] = full * qv[cc];
               }
               const int64_t ci = (H <= TC) ? (row0 + rr) * (int64_t)H + (c - rr * H) : row0 * (int64_t)H + ch * TC + c;
               *reinterpret_cast<float4*>(A.ws_dq + ci * D + d0) = make_float4(o[0], o[1], o[2], o[3]);

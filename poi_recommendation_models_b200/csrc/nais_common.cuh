@@ -77,6 +77,17 @@ __host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
 
 __device__ __forceinline__ float sigmoidf_exact(float z) { return 1.0f / (1.0f + expf(-z)); }
 
+// Embedding-row gathers of the pair kernels use 128-bit loads when every row is 16-byte aligned: both widths a multiple
+// of 4 floats (so a group of 4 never straddles the POI | region boundary at w_poi) and 16-byte aligned table bases.
+__host__ __device__ inline bool rows_vec4(const NaisBranch& br, int half_split) {
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  return (br.w_poi & 3) == 0 && (br.w_reg & 3) == 0 && (half_split & 3) == 0 && al(br.hist_poi) && al(br.hist_reg);
+}
+// 4 consecutive elements d..d+3 (d % 4 == 0) of the concatenated history row [hist_poi[item] ; hist_reg[region]]
+__device__ __forceinline__ float4 ldg_row4(const float* qp, const float* qr, int w_poi, int d) {
+  return __ldg(reinterpret_cast<const float4*>(d < w_poi ? qp + d : qr + (d - w_poi)));
+}
+
 // Great-circle km from centred coordinates, haversine form (well conditioned in fp32 for short distances; equals the
 // reference's law-of-cosines value powerLaw.py:7-21 mathematically, incl. its 1e-6 short-circuit).
 __device__ __forceinline__ float dist_km_f(float lat1, float lon1, float lat2, float lon2, float coslat1, float coslat2) {

@@ -218,6 +218,7 @@ __global__ void __launch_bounds__(NT, 2) pairs_fwd_kernel(const __grid_constant_
   for (int bi = 0; bi < p.n_branch; ++bi) {
     const NaisBranch& br = p.branch[bi];
     const int D = br.w_poi + br.w_reg;
+    const bool vec4 = rows_vec4(br, D >> 1) && (Dmax & 3) == 0;
     if (p.dist_mode == NAIS_DIST_KM && p.dist_buckets == 1) {
       if (tid == 0) km_c = km_coef(p, D, 0.f);
     }
@@ -257,11 +258,29 @@ __global__ void __launch_bounds__(NT, 2) pairs_fwd_kernel(const __grid_constant_
           const int64_t reg = br.w_reg ? A.b.hreg[cidx] : 0;
           const float* qp = br.hist_poi + (size_t)item * br.w_poi;
           const float* qr = br.hist_reg + (size_t)reg * br.w_reg;
-          for (int d = d0; d < d1; ++d) {
-            float q = (d < br.w_poi) ? __ldg(qp + d) : __ldg(qr + d - br.w_poi);
-            float x = q * ps[r * Dmax + d];
-            s.As[d * TCP + cell] = x;
-            ssum += x;
+          if (vec4) {  // 128-bit row loads: 4x fewer L1 requests than the scalar walk, same products in the same order
+            const float* pr = ps + r * Dmax;
+#pragma unroll 4
+            for (int d = d0; d < d1; d += 4) {
+              const float4 q = ldg_row4(qp, qr, br.w_poi, d);
+              const float4 t = *reinterpret_cast<const float4*>(pr + d);
+              const float x0 = q.x * t.x, x1 = q.y * t.y, x2 = q.z * t.z, x3 = q.w * t.w;
+              s.As[d * TCP + cell] = x0;
+              s.As[(d + 1) * TCP + cell] = x1;
+              s.As[(d + 2) * TCP + cell] = x2;
+              s.As[(d + 3) * TCP + cell] = x3;
+              ssum += x0;
+              ssum += x1;
+              ssum += x2;
+              ssum += x3;
+            }
+          } else {
+            for (int d = d0; d < d1; ++d) {
+              float q = (d < br.w_poi) ? __ldg(qp + d) : __ldg(qr + d - br.w_poi);
+              float x = q * ps[r * Dmax + d];
+              s.As[d * TCP + cell] = x;
+              ssum += x;
+            }
           }
         } else {
           for (int d = d0; d < d1; ++d) s.As[d * TCP + cell] = 0.f;
