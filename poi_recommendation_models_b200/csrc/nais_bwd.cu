@@ -56,8 +56,8 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
   float* dvp = dac + TC;                     // [16][HP] dv partials
   float* ps = dvp + 16 * HP;                 // [BWD_MAXROWS][D]
   float* dpacc = ps + BWD_MAXROWS * D;       // [BWD_MAXROWS][D]
-  float* rowv = dpacc + BWD_MAXROWS * D;     // [3][BWD_MAXROWS] S, score, G
-  float* red = rowv + 3 * BWD_MAXROWS;       // [8][NT/32] final block reduce scratch
+  float* rowv = dpacc + BWD_MAXROWS * D;     // [4][BWD_MAXROWS] S, score, G, S^beta
+  float* red = rowv + 4 * BWD_MAXROWS;       // [8][NT/32] final block reduce scratch
   int* citem = reinterpret_cast<int*>(red + 8 * (NT / 32));  // [TC] history item id per cell
   int* creg = citem + TC;                                   // [TC]
   int* crow = creg + TC;                                    // [TC] row slot per cell (-1 invalid)
@@ -109,7 +109,9 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
       dpacc[r * D + d] = 0.f;
     }
     if (tid < nrows) {
-      rowv[tid] = A.row_sum[row0 + tid];
+      const float S_row = A.row_sum[row0 + tid];
+      rowv[tid] = S_row;
+      rowv[3 * BWD_MAXROWS + tid] = powf(S_row, p.beta);  // once per row instead of once per (cell, hidden-lane)
       rowv[BWD_MAXROWS + tid] = A.parts[row0 + tid];
       rowv[2 * BWD_MAXROWS + tid] = A.dscore[row0 + tid];
     }
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
           if (m) {
             const float S = rowv[rr], sc = rowv[BWD_MAXROWS + rr], G = rowv[2 * BWD_MAXROWS + rr];
             const float e = expf(a);
-            const float w = e / powf(S, p.beta);
+            const float w = e / rowv[3 * BWD_MAXROWS + rr];
             const float s = sp[c] + sp[TC + c];
             dav = G * (w * s - p.beta * (e / S) * sc);
             gwv = G * w;
@@ -712,7 +714,7 @@ template <int NKB, int DB>
 static int launch_bwd_tile(const BwdArgs& A, int D, int grid, cudaStream_t stream) {
   constexpr int HP = NKB * KB;
   const size_t fl = (size_t)D * TCP + (size_t)HP * TCP + (size_t)D * KB + NKB * 4 * KB + 8 * TC + 16 * HP +
-                    2 * (size_t)BWD_MAXROWS * D + 3 * BWD_MAXROWS + 8 * (NT / 32);
+                    2 * (size_t)BWD_MAXROWS * D + 4 * BWD_MAXROWS + 8 * (NT / 32);
   const size_t smem = fl * 4 + 3 * TC * 4 + TC * 8 + 8;
   cudaError_t e = cudaFuncSetAttribute(pairs_bwd_kernel<NKB, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
