@@ -207,3 +207,24 @@ def test_ctypes_mirrors_match_the_header_layout(tmp_path):
         assert int(got[s]) == C.sizeof(cls), s
         for f, _ in cls._fields_:
             assert int(got[f"{s}.{f}"]) == getattr(cls, f).offset, (s, f)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to ours): one JSON line with the contract's keys on
+    rank 0; any other rank exits 0 without work or output."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "tiny", "--steps", "1", "--warmup", "1",
+           "--cpu-users", "1"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    out = subprocess.run(cmd, check=True, capture_output=True, text=True, env=env, timeout=300).stdout.strip().splitlines()
+    line = json.loads(out[-1])
+    assert line["impl"] == "reference" and line["metric"] == "fullrank_eval_users_per_sec" and line["unit"] == "users/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env1 = dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run(cmd, check=True, capture_output=True, text=True, env=env1, timeout=300)
+    assert r.stdout.strip() == ""
