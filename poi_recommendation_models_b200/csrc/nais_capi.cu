@@ -24,6 +24,10 @@ int launch_fullrank_tc(const NaisParams& p, const NaisCatalog& cat, const NaisUs
                        int64_t poi_end, int k, int exclude, int precision, float* out_score, int32_t* out_id,
                        float* all_scores, void* ws, size_t ws_bytes, cudaStream_t stream);
 bool tc_supported(const NaisParams& p, int precision);
+// nais_pairs_tc.cu (opt-in: NAIS_PAIRS_TC=1)
+bool pairs_tc_wanted();
+bool pairs_tc_supported(const NaisParams& p, const NaisPairs& b);
+int launch_pairs_fwd_tc(const NaisParams& p, const NaisPairs& b, float* score, float* row_sum, float* parts, cudaStream_t stream);
 }  // namespace nais
 
 namespace nais { unsigned long long g_launches = 0; }
@@ -159,6 +163,8 @@ int nais_pairs_forward(const NaisParams* p, const NaisPairs* batch, float* score
   rc = check_pairs(p, batch);
   if (rc) return rc;
   if (batch->B && !score) return NAIS_ERR_NULL;
+  if (batch->B && pairs_tc_wanted() && pairs_tc_supported(*p, *batch))  // tcgen05 contraction; same outputs within fp32 rounding
+    return launch_pairs_fwd_tc(*p, *batch, score, row_sum, score_parts, static_cast<cudaStream_t>(stream));
   return launch_pairs_fwd(*p, *batch, score, row_sum, score_parts, static_cast<cudaStream_t>(stream));
 }
 

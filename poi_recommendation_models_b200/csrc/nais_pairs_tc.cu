@@ -1,0 +1,329 @@
+// Pair forward (model.py:246-297) with the attention-MLP contraction on tcgen05 — opt-in (NAIS_PAIRS_TC=1), one branch,
+// D <= 64, hid <= 128, lat/lon or no distance mode, no dropout; everything else stays on the FP32 kernel (nais_fp32.cu).
+//
+// A training row has its own history, so unlike full-rank scoring there is no per-user operand to reuse: the GEMM is
+//     T[cell, k] = sum_d X[cell, d] * W[k, d],      X[cell, :] = q_cell (.) p_row       (M = 128 cells, N = hid, K = D)
+// with the CONSTANT operand W (packed once per CTA into shared memory, hi/lo fp16 planes) and the A operand built per tile by
+// the CTA itself: thread = cell gathers its history row with 128-bit loads, forms x in fp32, scales the row by its own
+// power of two (one TMEM lane = one cell, so the epilogue un-scales per lane), splits hi/lo and writes the 16-byte k-chunks
+// of the canonical K-major SWIZZLE_NONE image (umma.cuh) — consecutive threads write consecutive 16 B, no bank conflicts.
+// Three MMA passes (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM) give fp32-grade products.  Bias, the two distance
+// lanes, ReLU, the second layer, exp, mask and the row sums are the epilogue (fp32 CUDA cores, thread = cell = TMEM lane).
+// The similarity s = sum_d x_d is summed in fp32 by the building thread.  Four CTAs per SM overlap build / MMA / epilogue.
+#include <cstdlib>
+
+#include "nais_common.cuh"
+#include "umma.cuh"
+
+namespace nais {
+namespace ptc {
+using namespace umma;
+
+constexpr int PT = 128;        // threads per CTA = cells per tile = TMEM lanes
+constexpr int PMAXROWS = 16;   // rows (targets) sharing one tile when H is small
+
+struct Args {
+  NaisParams p;
+  NaisPairs b;
+  float* score;    // [B]
+  float* row_sum;  // [B] or NULL
+  float* parts;    // [B] or NULL
+  int rows_per_tile;
+  uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ float pow2_scale(float amax, int target_exp) {
+  // power of two s with amax * s in [2^(target_exp-1), 2^target_exp); exponent clamped so 1/s stays a normal float
+  if (!(amax > 0.f)) return 1.f;
+  int e;
+  frexpf(amax, &e);  // amax = f * 2^e, f in [0.5, 1)
+  int k = target_exp - e;
+  k = k > 40 ? 40 : (k < -40 ? -40 : k);
+  return ldexpf(1.f, k);
+}
+
+template <int D>
+__global__ void __launch_bounds__(PT, (D > 48) ? 3 : 4) pairs_fwd_tc_kernel(const __grid_constant__ Args A) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const NaisParams& p = A.p;
+  const NaisBranch& br = p.branch[0];
+  const int hid = p.hid, H = A.b.H;
+  const int lanes = (p.dist_mode == NAIS_DIST_LATLON) ? 2 : 0, ldw = D + lanes;
+  constexpr int KC = D / 8;                // 16-byte k-chunks along K
+  constexpr int A_PLANE = KC * PT * 16;    // one fp16 plane of the X tile
+  const int w_plane = KC * hid * 16;       // one fp16 plane of W
+  uint8_t* sA = smem;                      // [hi | lo][KC][128 rows][16 B]
+  uint8_t* sWi = sA + 2 * A_PLANE;         // [hi | lo][KC][hid rows][16 B]
+  float* kc = reinterpret_cast<float*>(sWi + 2 * w_plane);  // [4][hid] b1, w2, w1[:, D], w1[:, D+1]
+  float* ps = kc + 4 * hid;                // [PMAXROWS][D] target vectors of the rows of this tile
+  float* red_e = ps + PMAXROWS * D;        // [PT] masked exp per cell
+  float* red_es = red_e + PT;              // [PT] masked exp * similarity
+  float* row_e = red_es + PT;              // [PMAXROWS]
+  float* row_es = row_e + PMAXROWS;        // [PMAXROWS]
+  float* wred = row_es + PMAXROWS;         // [8] per-warp |W| maxima
+  uint64_t* bar = reinterpret_cast<uint64_t*>(wred + 8);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tslot, A.tmem_cols);
+
+  // ---- constant operand: W[:, :D] * wscale as hi/lo fp16 planes, plus the per-hidden-unit constants -------------------------
+  float wmax = 0.f;
+  for (int i = tid; i < hid * D; i += PT) {
+    const int k = i / D, d = i - k * D;
+    wmax = fmaxf(wmax, fabsf(__ldg(br.w1 + (size_t)k * ldw + d)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+  if (lane == 0) wred[warp] = wmax;
+  __syncthreads();
+  wmax = fmaxf(fmaxf(wred[0], wred[1]), fmaxf(wred[2], wred[3]));
+  const float wscale = pow2_scale(wmax, 9);  // |W| * wscale < 512
+  const float inv_wscale = 1.f / wscale;
+  for (int i = tid; i < hid * KC; i += PT) {
+    const int c = i / hid, k = i - c * hid;  // consecutive threads -> consecutive rows -> consecutive 16 B
+    __align__(16) __half hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_f16(__ldg(br.w1 + (size_t)k * ldw + c * 8 + e) * wscale, hi[e], lo[e]);
+    *reinterpret_cast<uint4*>(sWi + ((size_t)c * hid + k) * 16) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(sWi + w_plane + ((size_t)c * hid + k) * 16) = *reinterpret_cast<const uint4*>(lo);
+  }
+  for (int k = tid; k < hid; k += PT) {
+    kc[k] = __ldg(br.b1 + k);
+    kc[hid + k] = __ldg(br.w2 + k);
+    kc[2 * hid + k] = lanes ? __ldg(br.w1 + (size_t)k * ldw + D) : 0.f;
+    kc[3 * hid + k] = lanes ? __ldg(br.w1 + (size_t)k * ldw + D + 1) : 0.f;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);  // warp w owns TMEM lanes 32w .. 32w+31
+  const bool vec4 = rows_vec4(br, 4);
+
+  const int n_chunks = (H <= PT) ? 1 : (H + PT - 1) / PT;
+  const int64_t n_items = (A.b.B + A.rows_per_tile - 1) / A.rows_per_tile;
+  uint32_t phase = 0;
+  for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int64_t row0 = item * A.rows_per_tile;
+    const int nrows = (int)min((int64_t)A.rows_per_tile, A.b.B - row0);
+    for (int i = tid; i < nrows * D; i += PT) {
+      const int r = i / D, d = i - r * D;
+      ps[r * D + d] = (d < br.w_poi) ? __ldg(br.tgt_poi + (size_t)A.b.tgt[row0 + r] * br.w_poi + d)
+                                     : __ldg(br.tgt_reg + (size_t)A.b.treg[row0 + r] * br.w_reg + (d - br.w_poi));
+    }
+    if (tid < PMAXROWS) {
+      row_e[tid] = 0.f;
+      row_es[tid] = 0.f;
+    }
+    __syncthreads();
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      int r, h;
+      bool valid;
+      if (H <= PT) {
+        r = tid / H;
+        h = tid - r * H;
+        valid = r < nrows;
+      } else {
+        r = 0;
+        h = ch * PT + tid;
+        valid = h < H;
+      }
+      const int64_t cidx = valid ? (row0 + r) * (int64_t)H + h : 0;
+      // ---- build this cell's row of X -------------------------------------------------------------------------------------
+      float x[D];
+      float ssum = 0.f, amax = 0.f, g0 = 0.f, g1 = 0.f;
+      bool live = false;  // valid and not masked (history item != target)
+      if (valid) {
+        const int64_t it = A.b.hist[cidx];
+        const int64_t rg = br.w_reg ? A.b.hreg[cidx] : 0;
+        const float* qp = br.hist_poi + (size_t)it * br.w_poi;
+        const float* qr = br.hist_reg + (size_t)rg * br.w_reg;
+        const float* pr = ps + r * D;
+        if (vec4) {
+#pragma unroll
+          for (int d = 0; d < D; d += 4) {
+            const float4 q = ldg_row4(qp, qr, br.w_poi, d);
+            const float4 t = *reinterpret_cast<const float4*>(pr + d);
+            x[d] = q.x * t.x;
+            x[d + 1] = q.y * t.y;
+            x[d + 2] = q.z * t.z;
+            x[d + 3] = q.w * t.w;
+          }
+        } else {
+#pragma unroll
+          for (int d = 0; d < D; ++d) x[d] = ((d < br.w_poi) ? __ldg(qp + d) : __ldg(qr + (d - br.w_poi))) * pr[d];
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          ssum += x[d];
+          amax = fmaxf(amax, fabsf(x[d]));
+        }
+        if (lanes) {
+          const float l0 = A.b.aux[cidx * 2] * p.dist_scale, l1 = A.b.aux[cidx * 2 + 1] * p.dist_scale;
+          g0 = sigmoidf_exact(fmaf(l1, __ldg(p.dist_w + 1), fmaf(l0, __ldg(p.dist_w + 0), __ldg(p.dist_b + 0))));
+          g1 = sigmoidf_exact(fmaf(l1, __ldg(p.dist_w + 3), fmaf(l0, __ldg(p.dist_w + 2), __ldg(p.dist_b + 1))));
+        }
+        live = it != A.b.tgt[row0 + r];
+      } else {
+#pragma unroll
+        for (int d = 0; d < D; ++d) x[d] = 0.f;
+      }
+      const float xscale = pow2_scale(amax, 9);
+      const float inv = (1.f / xscale) * inv_wscale;  // both exact powers of two
+#pragma unroll
+      for (int c = 0; c < KC; ++c) {
+        __align__(16) __half hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_f16(x[c * 8 + e] * xscale, hi[e], lo[e]);
+        *reinterpret_cast<uint4*>(sA + ((size_t)c * PT + tid) * 16) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(sA + A_PLANE + ((size_t)c * PT + tid) * 16) = *reinterpret_cast<const uint4*>(lo);
+      }
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the MMA's async-proxy reads
+      __syncthreads();
+      // ---- T = X W^T: hi*hi + hi*lo + lo*hi, one elected thread issues, completion arrives on `bar` ---------------------------
+      if (warp == 0) {
+        if (elect_one()) {
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sA), w0 = smem_u32(sWi);
+          const uint32_t idesc = idesc_f16(PT, hid);
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t ab = a0 + (pass == 2 ? A_PLANE : 0), wb = w0 + (pass == 1 ? w_plane : 0);
+#pragma unroll
+            for (int s = 0; s < D / 16; ++s)
+              mma_f16(tmem, smem_desc(ab + s * 2 * PT * 16, PT * 16, 128), smem_desc(wb + s * 2 * hid * 16, hid * 16, 128), idesc,
+                      (pass | s) != 0);
+          }
+          mma_commit(bar);
+        }
+        __syncwarp();
+      }
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+      tc_fence_after();
+      // ---- epilogue: thread = cell = TMEM lane ------------------------------------------------------------------------------------
+      float a = 0.f;
+      for (int c0 = 0; c0 < hid; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tlane + c0, v);
+        tmem_wait_ld16(v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int k = c0 + i;
+          float t = fmaf(__uint_as_float(v[i]), inv, kc[k]);
+          if (lanes) t = fmaf(kc[3 * hid + k], g1, fmaf(kc[2 * hid + k], g0, t));
+          a = fmaf(kc[hid + k], fmaxf(t, 0.f), a);
+        }
+      }
+      tc_fence_before();  // TMEM reads ordered before the barrier that precedes the next tile's MMAs
+      float e = 0.f, es = 0.f;
+      if (live) {  // masked cells stay exactly 0 even if exp overflows (reference: exp_A * mask, then * history)
+        e = expf(a);
+        es = e * ssum;
+      }
+      red_e[tid] = e;
+      red_es[tid] = es;
+      __syncthreads();
+      for (int rr = warp; rr < ((H <= PT) ? nrows : 1); rr += PT / 32) {
+        const int c0 = (H <= PT) ? rr * H : 0;
+        const int cn = (H <= PT) ? H : min(PT, H - ch * PT);
+        float se = 0.f, ses = 0.f;
+        for (int c = lane; c < cn; c += 32) {
+          se += red_e[c0 + c];
+          ses += red_es[c0 + c];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          se += __shfl_xor_sync(0xffffffffu, se, o);
+          ses += __shfl_xor_sync(0xffffffffu, ses, o);
+        }
+        if (lane == 0) {
+          row_e[rr] += se;
+          row_es[rr] += ses;
+        }
+      }
+      __syncthreads();
+    }
+    if (tid < nrows) {
+      const float S = row_e[tid];
+      const float sc = row_es[tid] / powf(S, p.beta);
+      A.score[row0 + tid] = sc;
+      if (A.row_sum) A.row_sum[row0 + tid] = S;
+      if (A.parts) A.parts[row0 + tid] = sc;
+    }
+    __syncthreads();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, A.tmem_cols);
+}
+
+template <int D>
+static int launch(const Args& A, int hid, int64_t n_items, int sms, cudaStream_t stream) {
+  const size_t smem = 2 * (size_t)(D / 8) * PT * 16 + 2 * (size_t)(D / 8) * hid * 16 +
+                      (4 * (size_t)hid + PMAXROWS * D + 2 * PT + 2 * PMAXROWS + 8) * 4 + 16;
+  cudaError_t e = cudaFuncSetAttribute(pairs_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  // TMEM: tmem_cols per CTA, 512 per SM -> the resident-CTA count must not exceed 512 / tmem_cols or an alloc would spin
+  const int per_sm = (int)(512 / A.tmem_cols) < 4 ? (int)(512 / A.tmem_cols) : 4;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pairs_fwd_tc_kernel<D>, PT, smem);
+  if (e != cudaSuccess) return (int)e;
+  if (occ < 1) return NAIS_ERR_SHAPE;
+  const int64_t cap = (int64_t)sms * (occ < per_sm ? occ : per_sm);
+  const int grid = (int)(n_items < cap ? n_items : cap);
+  pairs_fwd_tc_kernel<D><<<grid, PT, smem, stream>>>(A);
+  NAIS_COUNT_LAUNCH(1);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace ptc
+
+bool pairs_tc_wanted() {
+  const char* v = getenv("NAIS_PAIRS_TC");
+  return v && v[0] && v[0] != '0';
+}
+
+bool pairs_tc_supported(const NaisParams& p, const NaisPairs& b) {
+  if (p.n_branch != 1 || b.B < 1) return false;
+  const int D = p.branch[0].w_poi + p.branch[0].w_reg;
+  if (D != 16 && D != 32 && D != 48 && D != 64) return false;
+  if (p.hid < 16 || p.hid > 128 || (p.hid & 15)) return false;
+  if (p.dist_mode == NAIS_DIST_KM || p.dropout_p > 0.f) return false;
+  return true;
+}
+
+int launch_pairs_fwd_tc(const NaisParams& p, const NaisPairs& b, float* score, float* row_sum, float* parts, cudaStream_t stream) {
+  int dev = 0, major = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) return NAIS_ERR_ARCH;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  ptc::Args A;
+  A.p = p;
+  A.b = b;
+  A.score = score;
+  A.row_sum = row_sum;
+  A.parts = parts;
+  int rpt = (b.H <= ptc::PT) ? ptc::PT / b.H : 1;
+  if (rpt > ptc::PMAXROWS) rpt = ptc::PMAXROWS;
+  A.rows_per_tile = rpt;
+  A.tmem_cols = p.hid <= 32 ? 32u : (p.hid <= 64 ? 64u : 128u);
+  const int64_t n_items = (b.B + rpt - 1) / rpt;
+  const int D = p.branch[0].w_poi + p.branch[0].w_reg;
+  switch (D) {
+    case 16: return ptc::launch<16>(A, p.hid, n_items, sms, stream);
+    case 32: return ptc::launch<32>(A, p.hid, n_items, sms, stream);
+    case 48: return ptc::launch<48>(A, p.hid, n_items, sms, stream);
+    case 64: return ptc::launch<64>(A, p.hid, n_items, sms, stream);
+    default: return NAIS_ERR_SHAPE;
+  }
+}
+
+}  // namespace nais

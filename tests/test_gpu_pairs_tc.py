@@ -1,0 +1,109 @@
+"""GPU parity of the tensor-core pair forward (csrc/nais_pairs_tc.cu, opt-in NAIS_PAIRS_TC=1): the same C-ABI entry point
+`nais_pairs_forward`, the same oracle and tolerance as the FP32 kernel's tests, plus closeness to the FP32 kernel itself and
+gradients through the (FP32) backward that consumes the tensor-core forward's saved row sums."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import nais_testutil as util
+from oracle import nais_oracle as orc
+from poi_recommendation_models_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture
+def pairs_tc(monkeypatch):
+    monkeypatch.setenv("NAIS_PAIRS_TC", "1")  # read by the library on every nais_pairs_forward call
+    yield
+    monkeypatch.delenv("NAIS_PAIRS_TC", raising=False)
+
+
+def _case(variant, N, D, hid, B, H, seed, style="trained"):
+    rng = np.random.default_rng(seed)
+    coords, region, R = synthetic.make_catalog(N, seed=seed)
+    sd = orc.init_state(variant, N, D, hid, R, 1, seed=seed + 1, style=style)
+    hist = np.stack([rng.choice(N, H, replace=False) for _ in range(B)]).astype(np.int64)
+    tgt = rng.integers(0, N, B).astype(np.int64)
+    if H > 1:
+        tgt[::3] = hist[::3, H // 2]  # live mask, like a training positive
+    aux = orc.latlon_abs_diff(coords, tgt, hist) if orc.VARIANTS[variant]["dist"] == "latlon" else None
+    return sd, hist, tgt, region, aux
+
+
+def _both(variant, sd, beta, hist, tgt, region, aux, monkeypatch):
+    m = util.make_model(variant, sd, beta)
+    args = (_dev(hist), _dev(tgt), _dev(region[hist]), _dev(region[tgt]), None if aux is None else _dev(aux))
+    with torch.no_grad():
+        monkeypatch.setenv("NAIS_PAIRS_TC", "1")
+        s_tc = util.call(m, variant, *args).cpu().numpy()
+        monkeypatch.setenv("NAIS_PAIRS_TC", "0")
+        s_fp = util.call(m, variant, *args).cpu().numpy()
+    ref, scale = orc.attention_network_with_scale(sd, variant, beta, torch.from_numpy(hist), torch.from_numpy(tgt),
+                                                  torch.from_numpy(region[hist]), torch.from_numpy(region[tgt]),
+                                                  None if aux is None else torch.from_numpy(aux), dtype=torch.float64)
+    return s_tc, s_fp, ref.numpy(), scale.numpy()
+
+
+@pytest.mark.parametrize("H", [1, 3, 13, 100, 128, 129, 300])
+def test_pairs_tc_history_lengths(H, monkeypatch):
+    sd, hist, tgt, region, aux = _case("region_distance", 900, 64, 64, 37, H, seed=H)
+    s_tc, s_fp, ref, scale = _both("region_distance", sd, 0.5, hist, tgt, region, aux, monkeypatch)
+    assert not np.array_equal(s_tc, s_fp) or H == 1, "the tensor-core path did not run (results bit-identical to FP32)"
+    assert util.cond_err(s_tc, ref, scale) < util.TOL
+    assert util.cond_err(s_tc, ref, scale) <= max(4 * util.cond_err(s_fp, ref, scale), 5e-6)  # fp32-grade, not just < 1e-4
+
+
+@pytest.mark.parametrize("variant,D,hid", [("region_distance", 32, 32), ("region_distance", 64, 128), ("region_distance", 16, 48),
+                                           ("basic", 64, 64), ("region", 48, 64), ("distance", 64, 64)])
+def test_pairs_tc_variants_and_shapes(variant, D, hid, monkeypatch):
+    sd, hist, tgt, region, aux = _case(variant, 500, D, hid, 300, 21, seed=D + hid)
+    s_tc, s_fp, ref, scale = _both(variant, sd, 0.7, hist, tgt, region, aux, monkeypatch)
+    assert util.cond_err(s_tc, ref, scale) < util.TOL
+    assert util.cond_err(s_tc, ref, scale) <= max(4 * util.cond_err(s_fp, ref, scale), 5e-6)
+
+
+@pytest.mark.parametrize("scale_e,scale_w", [(1e-4, 1.0), (30.0, 0.01), (1.0, 50.0)])
+def test_pairs_tc_row_scaling_extremes(scale_e, scale_w, monkeypatch):
+    """Per-row power-of-two scaling of X and the global one of W: tiny / huge embeddings and weights keep fp32-grade products."""
+    sd, hist, tgt, region, aux = _case("region_distance", 400, 64, 64, 64, 50, seed=9)
+    sd = {k: v.clone() for k, v in sd.items()}
+    for k in sd:
+        if k.startswith("embed_"):
+            sd[k] *= scale_e
+    sd["attn_layer1.weight"][:, :64] *= scale_w
+    s_tc, s_fp, ref, scale = _both("region_distance", sd, 0.5, hist, tgt, region, aux, monkeypatch)
+    ok = np.isfinite(ref)
+    assert ok.any()
+    assert util.cond_err(s_tc[ok], ref[ok], scale[ok]) < util.TOL
+    assert util.cond_err(s_tc[ok], ref[ok], scale[ok]) <= max(4 * util.cond_err(s_fp[ok], ref[ok], scale[ok]), 5e-6)
+
+
+def test_pairs_tc_c3_shape_forward_and_gradients(pairs_tc):
+    """C3-shaped batch (own history per row, H = 128, D = hid = 64): forward vs the float64 oracle on every row, and the
+    gradients (FP32 backward fed by the tensor-core forward's saved row sums) vs the oracle's autograd."""
+    B, H, N, D, hid, beta = 512, 128, 3000, 64, 64, 0.5
+    sd, hist, tgt, region, aux = _case("region_distance", N, D, hid, B, H, seed=21)
+    rng = np.random.default_rng(5)
+    dscore = rng.normal(size=B)
+    m = util.make_model("region_distance", sd, beta)
+    s = m.attention_network(_dev(hist), _dev(tgt), _dev(region[hist]), _dev(region[tgt]), _dev(aux))
+    (s * _dev(dscore).float()).sum().backward()
+    ref_s, ref = orc.grads(sd, "region_distance", beta, torch.from_numpy(hist), torch.from_numpy(tgt), torch.from_numpy(region[hist]),
+                           torch.from_numpy(region[tgt]), torch.from_numpy(aux), torch.from_numpy(dscore))
+    _, scale = orc.attention_network_with_scale(sd, "region_distance", beta, torch.from_numpy(hist), torch.from_numpy(tgt),
+                                                torch.from_numpy(region[hist]), torch.from_numpy(region[tgt]),
+                                                torch.from_numpy(aux), dtype=torch.float64)
+    assert util.cond_err(s.detach().cpu().numpy(), ref_s.numpy(), scale.numpy()) < util.TOL
+    ref = {k: v.numpy() for k, v in ref.items()}
+    ref.setdefault("embed_distance.weight", np.zeros((1, D)))
+    for name, p in m.named_parameters():
+        r = np.asarray(ref[name], dtype=np.float64)
+        g = np.zeros_like(r) if p.grad is None else p.grad.detach().cpu().double().numpy()
+        assert np.abs(g - r).max() <= 2e-4 * np.abs(r).max() + 1e-12, name
