@@ -21,6 +21,7 @@ using namespace umma;
 
 constexpr int PT = 128;        // threads per CTA = cells per tile = TMEM lanes
 constexpr int PMAXROWS = 16;   // rows (targets) sharing one tile when H is small
+constexpr int STG_STRIDE = 144;  // bytes per staged row segment: 32 floats + 16 B skew (conflict-free per-thread read-back)
 
 struct Args {
   NaisParams p;
@@ -139,25 +140,67 @@ __global__ void __launch_bounds__(PT, (D > 48) ? 3 : 4) pairs_fwd_tc_kernel(cons
       float x[D];
       float ssum = 0.f, amax = 0.f, g0 = 0.f, g1 = 0.f;
       bool live = false;  // valid and not masked (history item != target)
+      int it32 = 0, rg32 = 0;  // POI / region id of this cell (ids fit int32: item_num is int32); row 0 for padding cells
       if (valid) {
-        const int64_t it = A.b.hist[cidx];
-        const int64_t rg = br.w_reg ? A.b.hreg[cidx] : 0;
-        const float* qp = br.hist_poi + (size_t)it * br.w_poi;
-        const float* qr = br.hist_reg + (size_t)rg * br.w_reg;
-        const float* pr = ps + r * D;
-        if (vec4) {
+        it32 = (int)A.b.hist[cidx];
+        rg32 = br.w_reg ? (int)A.b.hreg[cidx] : 0;
+      }
+      if (vec4) {
+        // Warp-cooperative gather: consecutive lanes read consecutive 16 B of the SAME table row, so one request covers whole
+        // 128-byte lines (4 rows of 32 floats) instead of 32 lines x 16 B — the per-thread pattern kept the kernel waiting on
+        // L1 requests in flight.  Rows are staged in this warp's slice of the (free) A-image area with a 16-byte skew per row,
+        // then each thread reads its own row back conflict-free.
+        uint8_t* stg = sA + (size_t)(warp * 32) * STG_STRIDE;
 #pragma unroll
-          for (int d = 0; d < D; d += 4) {
-            const float4 q = ldg_row4(qp, qr, br.w_poi, d);
-            const float4 t = *reinterpret_cast<const float4*>(pr + d);
-            x[d] = q.x * t.x;
-            x[d + 1] = q.y * t.y;
-            x[d + 2] = q.z * t.z;
-            x[d + 3] = q.w * t.w;
+        for (int s0 = 0; s0 < D; s0 += 32) {
+          constexpr int full_seg = 32;
+          const int segw = (D - s0 < full_seg) ? (D - s0) : full_seg;
+          const int P = segw / 4;  // 16-byte parts per row in this segment
+          float4 v[full_seg / 4];
+#pragma unroll
+          for (int q = 0; q < full_seg / 4; ++q) {  // all P loads of this lane are in flight before the first store
+            if (q < P) {
+              const int idx = lane + 32 * q, c = idx / P, part = idx - c * P;
+              const int ci = __shfl_sync(0xffffffffu, it32, c), cr = __shfl_sync(0xffffffffu, rg32, c);
+              v[q] = ldg_row4(br.hist_poi + (size_t)ci * br.w_poi, br.hist_reg + (size_t)cr * br.w_reg, br.w_poi, s0 + 4 * part);
+            }
           }
-        } else {
 #pragma unroll
-          for (int d = 0; d < D; ++d) x[d] = ((d < br.w_poi) ? __ldg(qp + d) : __ldg(qr + (d - br.w_poi))) * pr[d];
+          for (int q = 0; q < full_seg / 4; ++q) {
+            if (q < P) {
+              const int idx = lane + 32 * q, c = idx / P, part = idx - c * P;
+              *reinterpret_cast<float4*>(stg + (size_t)c * STG_STRIDE + part * 16) = v[q];
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int j4 = 0; j4 < full_seg / 4; ++j4) {
+            if (4 * j4 < segw) {
+              const float4 v = *reinterpret_cast<const float4*>(stg + (size_t)lane * STG_STRIDE + j4 * 16);
+              x[s0 + 4 * j4] = v.x;
+              x[s0 + 4 * j4 + 1] = v.y;
+              x[s0 + 4 * j4 + 2] = v.z;
+              x[s0 + 4 * j4 + 3] = v.w;
+            }
+          }
+          __syncwarp();
+        }
+        __syncthreads();  // every warp is done with the staging slices before anyone writes the A image over them
+      } else if (valid) {
+        const float* qp = br.hist_poi + (size_t)it32 * br.w_poi;
+        const float* qr = br.hist_reg + (size_t)rg32 * br.w_reg;
+#pragma unroll
+        for (int d = 0; d < D; ++d) x[d] = (d < br.w_poi) ? __ldg(qp + d) : __ldg(qr + (d - br.w_poi));
+      }
+      if (valid) {
+        const float* pr = ps + r * D;
+#pragma unroll
+        for (int d = 0; d < D; d += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(pr + d);
+          x[d] *= t.x;
+          x[d + 1] *= t.y;
+          x[d + 2] *= t.z;
+          x[d + 3] *= t.w;
         }
 #pragma unroll
         for (int d = 0; d < D; ++d) {
@@ -169,7 +212,7 @@ __global__ void __launch_bounds__(PT, (D > 48) ? 3 : 4) pairs_fwd_tc_kernel(cons
           g0 = sigmoidf_exact(fmaf(l1, __ldg(p.dist_w + 1), fmaf(l0, __ldg(p.dist_w + 0), __ldg(p.dist_b + 0))));
           g1 = sigmoidf_exact(fmaf(l1, __ldg(p.dist_w + 3), fmaf(l0, __ldg(p.dist_w + 2), __ldg(p.dist_b + 1))));
         }
-        live = it != A.b.tgt[row0 + r];
+        live = (int64_t)it32 != A.b.tgt[row0 + r];
       } else {
 #pragma unroll
         for (int d = 0; d < D; ++d) x[d] = 0.f;
