@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(PT, (D > 48) ? 3 : 4) pairs_fwd_tc_kernel(cons
   float* wred = row_es + PMAXROWS;         // [8] per-warp |W| maxima
   uint64_t* bar = reinterpret_cast<uint64_t*>(wred + 8);
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint8_t* stg_all = reinterpret_cast<uint8_t*>(bar + 2);  // [PT][STG_STRIDE] row staging of the cooperative gather (16-B aligned)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -148,9 +149,9 @@ __global__ void __launch_bounds__(PT, (D > 48) ? 3 : 4) pairs_fwd_tc_kernel(cons
       if (vec4) {
         // Warp-cooperative gather: consecutive lanes read consecutive 16 B of the SAME table row, so one request covers whole
         // 128-byte lines (4 rows of 32 floats) instead of 32 lines x 16 B — the per-thread pattern kept the kernel waiting on
-        // L1 requests in flight.  Rows are staged in this warp's slice of the (free) A-image area with a 16-byte skew per row,
-        // then each thread reads its own row back conflict-free.
-        uint8_t* stg = sA + (size_t)(warp * 32) * STG_STRIDE;
+        // L1 requests in flight.  Rows are staged in this warp's private slice of `stg_all` with a 16-byte skew per row, then
+        // each thread reads its own row back conflict-free (only __syncwarp between the two).
+        uint8_t* stg = stg_all + (size_t)(warp * 32) * STG_STRIDE;
 #pragma unroll
         for (int s0 = 0; s0 < D; s0 += 32) {
           constexpr int full_seg = 32;
@@ -185,7 +186,6 @@ __global__ void __launch_bounds__(PT, (D > 48) ? 3 : 4) pairs_fwd_tc_kernel(cons
           }
           __syncwarp();
         }
-        __syncthreads();  // every warp is done with the staging slices before anyone writes the A image over them
       } else if (valid) {
         const float* qp = br.hist_poi + (size_t)it32 * br.w_poi;
         const float* qr = br.hist_reg + (size_t)rg32 * br.w_reg;
@@ -310,16 +310,19 @@ __global__ void __launch_bounds__(PT, (D > 48) ? 3 : 4) pairs_fwd_tc_kernel(cons
 template <int D>
 static int launch(const Args& A, int hid, int64_t n_items, int sms, cudaStream_t stream) {
   const size_t smem = 2 * (size_t)(D / 8) * PT * 16 + 2 * (size_t)(D / 8) * hid * 16 +
-                      (4 * (size_t)hid + PMAXROWS * D + 2 * PT + 2 * PMAXROWS + 8) * 4 + 16;
+                      (4 * (size_t)hid + PMAXROWS * D + 2 * PT + 2 * PMAXROWS + 8) * 4 + 16 + (size_t)PT * STG_STRIDE;
   cudaError_t e = cudaFuncSetAttribute(pairs_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  // TMEM: tmem_cols per CTA, 512 per SM -> the resident-CTA count must not exceed 512 / tmem_cols or an alloc would spin
-  const int per_sm = (int)(512 / A.tmem_cols) < 4 ? (int)(512 / A.tmem_cols) : 4;
-  int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pairs_fwd_tc_kernel<D>, PT, smem);
+  e = cudaFuncSetAttribute(pairs_fwd_tc_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return (int)e;
-  if (occ < 1) return NAIS_ERR_SHAPE;
-  const int64_t cap = (int64_t)sms * (occ < per_sm ? occ : per_sm);
+  // Persistent grid: as many CTAs as can be co-resident — the kernel's register budget (3 per SM for D = 64, else 4), shared
+  // memory, and TMEM (tmem_cols of the SM's 512 columns per CTA; a CTA beyond that would simply wait in tcgen05.alloc).
+  int per_sm = (D > 48) ? 3 : 4;
+  const int by_tmem = (int)(512 / A.tmem_cols), by_smem = (int)((227 * 1024) / (smem + 1024));
+  per_sm = per_sm < by_tmem ? per_sm : by_tmem;
+  per_sm = per_sm < by_smem ? per_sm : by_smem;
+  if (per_sm < 1) return NAIS_ERR_SHAPE;
+  const int64_t cap = (int64_t)sms * per_sm;
   const int grid = (int)(n_items < cap ? n_items : cap);
   pairs_fwd_tc_kernel<D><<<grid, PT, smem, stream>>>(A);
   NAIS_COUNT_LAUNCH(1);
