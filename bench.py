@@ -128,9 +128,10 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None}
 
 
-def cpu_arm(cfg, n_users, seed=0, warm=1):
+def cpu_arm(cfg, n_users, seed=0, warm=1, keep=None):
     """The reference's CPU path (oracle port of validation.py:84-127: chunks of 2048, torch.cat, torch.topk(50)) on the
-    host cores, all threads.  Returns users/s over `n_users` users after `warm` warm-up users."""
+    host cores, all threads.  Returns users/s over `n_users` users after `warm` warm-up users.  `keep` (a dict) receives the
+    weights, inputs and the oracle's lists / full score vectors of the timed users, for `parity_block`."""
     import torch
     from oracle import nais_oracle as orc  # CPU arm only
     from poi_recommendation_models_b200 import synthetic
@@ -142,11 +143,46 @@ def cpu_arm(cfg, n_users, seed=0, warm=1):
     with torch.no_grad():
         for u in range(warm):
             orc.fullrank_user(sd, "region_distance", BETA, cat, hist[u], 50)
+        outs = []
         t0 = time.perf_counter()
         for u in range(warm, warm + n_users):
-            orc.fullrank_user(sd, "region_distance", BETA, cat, hist[u], 50)
+            outs.append(orc.fullrank_user(sd, "region_distance", BETA, cat, hist[u], 50, return_all=keep is not None))
         dt = time.perf_counter() - t0
+    if keep is not None:
+        keep.update(sd=sd, coords=coords, region=region, R=R, hist=hist[warm:warm + n_users], outs=outs)
     return n_users / dt, dt, torch.get_num_threads()
+
+
+def parity_block(dev, cfg, kept, precision):
+    """SURVEY.md §8(d) 'results-parity checks reported with every throughput number': the CPU arm's users scored again by the
+    CUDA path with the SAME weights; our top-50 lists against the oracle's (validation.py:84-127 flow, fp32 torch CPU).
+    Never raises: a failure is reported in the block, the throughput line stands."""
+    try:
+        import torch
+        from poi_recommendation_models_b200 import model as M
+        N, D, hid, H = cfg["pois"], cfg["D"], cfg["hid"], cfg["hist"]
+        m = M.NAIS_region_distance_Embedding(N, D, hid, BETA, kept["R"], 1)
+        m.load_state_dict(kept["sd"])
+        m = m.to(dev).eval()
+        m.set_catalog(region=kept["region"], coords=kept["coords"])
+        hist = kept["hist"]
+        n = len(hist)
+        s, ids = m.predict_topk((np.arange(0, (n + 1) * H, H, dtype=np.int64), hist.reshape(-1)), 50, precision=precision)
+        s, ids = s.cpu().numpy(), ids.cpu().numpy()
+        exact, overlap, valid, rel = 0, 0, True, 0.0
+        for u, (rec, val, cand, pred) in enumerate(kept["outs"]):
+            exact += int([int(i) for i in rec] == ids[u].tolist())
+            overlap += len(set(int(i) for i in rec) & set(ids[u].tolist()))
+            by_id = dict(zip(cand.tolist(), pred.tolist()))
+            mine = np.array([by_id[int(i)] for i in ids[u]], dtype=np.float64)  # the oracle's score of each POI we list
+            kth = float(val[-1])
+            valid = valid and bool((mine >= kth - 1e-4 * abs(kth)).all())
+            rel = max(rel, float(np.max(np.abs(s[u].astype(np.float64) - val) / np.maximum(np.abs(val), 1e-30))))
+        return {"users": n, "k": 50, "lists_identical": exact, "id_overlap": overlap / (50.0 * n),
+                "valid_topk_of_oracle_scores_within_1e-4": valid, "max_rel_err_of_ranked_scores": rel,
+                "against": "oracle port of validation.py:84-127 on the host (fp32 torch CPU), same weights and histories"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 def run_reference(args, cfg, rank, world):
@@ -459,7 +495,9 @@ def main():
         if kern_ms:
             line["roofline"]["hbm_frac"] = alg_bytes / (kern_ms / 1000.0) / 1e9 / peaks["hbm"]
         if not args.no_cpu_baseline and world == 1:
-            v, dt, threads = cpu_arm(cfg, max(1, args.cpu_users))
+            kept = {}
+            v, dt, threads = cpu_arm(cfg, max(1, args.cpu_users), keep=kept)
+            line["parity"] = parity_block(dev, cfg, kept, args.precision)
             line["cpu_baseline"] = {"value": v, "unit": "users/s", "cores": threads, "kind": "port",
                                     "sample": f"{args.cpu_users} users x {N} POIs (H={H}), {dt:.1f} s, oracle port of validation.py:84-127 (chunk 2048, torch CPU, top-50)"}
         print(json.dumps(line), flush=True)
