@@ -10,29 +10,17 @@
 // Math (SURVEY.md §7 'Backward'):  dscore/da_h = w_h s_h - beta (E_h/S) score ;  dt_k = da v_k [t_k > 0]
 #include <cub/device/device_radix_sort.cuh>
 
+#include "nais_bwd_args.cuh"
 #include "nais_common.cuh"
 
 namespace nais {
 
-constexpr int BWD_MAXROWS = 16;
 
-struct BwdArgs {
-  NaisParams p;
-  NaisPairs b;
-  int bi;                 // branch
-  const float* parts;     // [B] per-branch score of this branch
-  const float* row_sum;   // [B]
-  const float* dscore;    // [B]
-  float* ws_dq;           // [B*H, D]
-  float* ws_dp;           // [B, D]
-  float* ws_part;         // [grid, part_stride]
-  int part_stride;
-  int rows_per_tile;
-  int64_t n_items;        // work items (tiles of rows)
-};
 
-// layout of one CTA's parameter partial: w1 [hid][D+lanes] | b1 [hid] | w2 [hid] | dist_w[4] dist_b[2] km[1] pad[1]
-__host__ __device__ inline int part_floats(int hid, int D, int lanes) { return hid * (D + lanes) + 2 * hid + 8; }
+// nais_pairs_tc_bwd.cu (opt-in: NAIS_PAIRS_TC_BWD=1): same workspace outputs as pairs_bwd_kernel
+bool pairs_tc_bwd_wanted();
+bool pairs_tc_bwd_supported(const NaisParams& p, const NaisPairs& b);
+int launch_pairs_bwd_tc(const BwdArgs& A, int D, int grid, cudaStream_t stream);
 
 template <int NKB, int DB>
 __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(const __grid_constant__ BwdArgs A) {
@@ -762,7 +750,8 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
     int grid = (int)(A.n_items < L.grid ? A.n_items : L.grid);
     int rc;
     const int nkb = p.hid <= 64 ? 1 : 2, db = D <= 64 ? 1 : 2;
-    if (nkb == 1 && db == 1) rc = launch_bwd_tile<1, 1>(A, D, grid, stream);
+    if (pairs_tc_bwd_wanted() && pairs_tc_bwd_supported(p, b)) rc = launch_pairs_bwd_tc(A, D, grid, stream);  // opt-in: tcgen05
+    else if (nkb == 1 && db == 1) rc = launch_bwd_tile<1, 1>(A, D, grid, stream);
     else if (nkb == 1) rc = launch_bwd_tile<1, 2>(A, D, grid, stream);
     else if (db == 1) rc = launch_bwd_tile<2, 1>(A, D, grid, stream);
     else rc = launch_bwd_tile<2, 2>(A, D, grid, stream);

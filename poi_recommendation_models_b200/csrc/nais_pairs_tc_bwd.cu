@@ -1,0 +1,461 @@
+// Backward of the pair scorer with all three contractions on tcgen05 — opt-in (NAIS_PAIRS_TC_BWD=1), one branch,
+// hidden_size = 64, D in {32, 64}, lat/lon or no distance mode, no dropout; everything else stays on the FP32 kernel (nais_bwd.cu).
+// It writes the SAME workspace as pairs_bwd_kernel (dq rows, dp rows, one parameter partial per CTA), so the deterministic
+// param_reduce and the sorted-segment embedding reduce that follow are shared.
+//
+// Tile = 128 cells (one row's history at H = 128).  Operands are bf16 two-term splits (hi*hi + hi*lo + lo*hi, fp32 accumulation
+// in TMEM) with NO scaling anywhere: dW is a contraction over cells accumulated across all tiles of the CTA, so no per-row
+// scale could be undone (examples/precision_emulation_backward.py: every gradient within 7e-6 of its tensor maximum, bar 2e-4).
+//
+//   GEMM1  T[cell,k]  = sum_d X[cell,d] W[k,d]            A = X image (K-major), B = W image (K-major)            -> TMEM cols 0..63
+//   epi 1  a, e, da, gw; dt = da v [t > 0] -> DT image; dg -> dist-layer partials; sum_cell da relu(t) -> dv (shuffle halving)
+//   GEMM2  dX[cell,d] = sum_k dt[cell,k] W[k,d]           A = DT image (K-major), B = W image read MN-major       -> cols 64..127
+//   GEMM3  dW[k,n]   += sum_cell dt[cell,k] Xe[cell,n]    A = DT image, B = X image, BOTH read MN-major (transpose bits;
+//          Xe = [X | 1 g0 g1]: the ext chunk yields db1 and the two lane columns of dW)  M = 64 -> cols 128..199, row m in
+//          TMEM lane 32*(m/16) + m%16 (tests/umma_probe_mn.cu); accumulated across the tiles of the persistent CTA
+//   epi 2  dq = (dX + gw) (.) p -> workspace; (dX + gw) (.) q -> smem scratch -> per-row dp sums
+#include <cuda_bf16.h>
+
+#include <cstdlib>
+
+#include "nais_bwd_args.cuh"
+#include "umma.cuh"
+
+namespace nais {
+namespace ptcb {
+using namespace umma;
+
+constexpr int PT = 128;          // threads = cells per tile = TMEM lanes
+constexpr int HID = 64;          // hidden_size of this version
+constexpr int STG_STRIDE = 144;  // staged row segment: 32 floats + 16 B skew
+constexpr int DP_STRIDE = 132;   // cells per d-row of the dp scratch (aliased on the X image)
+constexpr uint32_t TMEM_COLS = 256, COL_T = 0, COL_DX = 64, COL_DW = 128;
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+// kind::f16 with bf16 operands, fp32 accumulate; a_mn / b_mn = 1 reads that operand MN-major (transposed)
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+// 8 fp32 -> one 16-byte k-chunk per plane
+__device__ __forceinline__ void store_chunk_bf16(uint8_t* hi_plane, uint8_t* lo_plane, size_t off, const float (&v)[8]) {
+  __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) split_bf16(v[e], hi[e], lo[e]);
+  *reinterpret_cast<uint4*>(hi_plane + off) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(lo_plane + off) = *reinterpret_cast<const uint4*>(lo);
+}
+
+// Warp-cooperative gather of the 32-float segment [s0, s0+segw) of the 32 history rows of this warp's cells (ids it32 / rg32 held
+// per lane) into q[0..segw): whole 128-byte lines per request, staged with a 16-byte skew, read back by the owning lane.
+template <int SEGW>
+__device__ __forceinline__ void gather_segment(const NaisBranch& br, int it32, int rg32, int s0, uint8_t* stg, int lane, float (&q)[32]) {
+  constexpr int P = SEGW / 4;
+  float4 v[P];
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const int idx = lane + 32 * j, c = idx / P, part = idx - c * P;
+    const int ci = __shfl_sync(0xffffffffu, it32, c), cr = __shfl_sync(0xffffffffu, rg32, c);
+    v[j] = ldg_row4(br.hist_poi + (size_t)ci * br.w_poi, br.hist_reg + (size_t)cr * br.w_reg, br.w_poi, s0 + 4 * part);
+  }
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const int idx = lane + 32 * j, c = idx / P, part = idx - c * P;
+    *reinterpret_cast<float4*>(stg + (size_t)c * STG_STRIDE + part * 16) = v[j];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const float4 t = *reinterpret_cast<const float4*>(stg + (size_t)lane * STG_STRIDE + j * 16);
+    q[4 * j] = t.x;
+    q[4 * j + 1] = t.y;
+    q[4 * j + 2] = t.z;
+    q[4 * j + 3] = t.w;
+  }
+  __syncwarp();
+}
+
+template <int D>
+__global__ void __launch_bounds__(PT, 2) pairs_bwd_tc_kernel(const __grid_constant__ BwdArgs A) {
+  static_assert(D == 32 || D == 64, "segments of 32");
+  extern __shared__ __align__(128) uint8_t smem[];
+  const NaisParams& p = A.p;
+  const NaisBranch& br = p.branch[A.bi];
+  const int H = A.b.H;
+  const int lanes = (p.dist_mode == NAIS_DIST_LATLON) ? 2 : 0, ldw = D + lanes;
+  constexpr int XC = D / 8 + 1;                 // k-chunks of the X image: D/8 + the ext chunk [1 g0 g1 0 0 0 0 0]
+  constexpr int X_PLANE = XC * PT * 16, W_PLANE = (D / 8) * HID * 16, DT_PLANE = (HID / 8) * PT * 16;
+  uint8_t* sX = smem;                           // [hi | lo][XC][128 cells][16 B]      (dp scratch aliases it after GEMM3)
+  uint8_t* sW = sX + 2 * X_PLANE;               // [hi | lo][D/8][64 hidden][16 B]
+  uint8_t* sDT = sW + 2 * W_PLANE;              // [hi | lo][8][128 cells][16 B]       (row staging aliases it outside GEMM2/3)
+  float* kc = reinterpret_cast<float*>(sDT + 2 * DT_PLANE);  // [4][HID] b1, w2, w1[:, D], w1[:, D+1]
+  float* ps = kc + 4 * HID;                     // [BWD_MAXROWS][D]
+  float* dpacc = ps + BWD_MAXROWS * D;          // [BWD_MAXROWS][D]
+  float* rowv = dpacc + BWD_MAXROWS * D;        // [4][BWD_MAXROWS] S, score, G, S^beta
+  float* dvs = rowv + 4 * BWD_MAXROWS;          // [4 warps][HID]
+  float* red = dvs + 4 * HID;                   // [8][4]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(red + 32);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
+  float* dps = reinterpret_cast<float*>(sX);    // [D][DP_STRIDE]
+  static_assert(D * DP_STRIDE * 4 <= 2 * X_PLANE, "dp scratch must fit in the X image");
+  static_assert(PT * STG_STRIDE <= 2 * DT_PLANE, "row staging must fit in the DT image");
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tslot, TMEM_COLS);
+  for (int i = tid; i < HID * (D / 8); i += PT) {
+    const int c = i / HID, k = i - c * HID;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = __ldg(br.w1 + (size_t)k * ldw + c * 8 + e);
+    store_chunk_bf16(sW, sW + W_PLANE, ((size_t)c * HID + k) * 16, v);
+  }
+  for (int k = tid; k < HID; k += PT) {
+    kc[k] = __ldg(br.b1 + k);
+    kc[HID + k] = __ldg(br.w2 + k);
+    kc[2 * HID + k] = lanes ? __ldg(br.w1 + (size_t)k * ldw + D) : 0.f;
+    kc[3 * HID + k] = lanes ? __ldg(br.w1 + (size_t)k * ldw + D + 1) : 0.f;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+  uint8_t* stg = sDT + (size_t)(warp * 32) * STG_STRIDE;
+
+  float pd[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // dist_w[4], dist_b[2] partials of this thread's cells
+  float dv_acc[2] = {0.f, 0.f};                  // dw2 partial of hidden units dv_k0, dv_k0 + 1 over this warp's cells
+  const int dv_k0 = 32 * ((lane >> 4) & 1) + 16 * ((lane >> 3) & 1) + 8 * ((lane >> 2) & 1) + 4 * ((lane >> 1) & 1) + 2 * (lane & 1);
+  const int n_chunks = (H <= PT) ? 1 : (H + PT - 1) / PT;
+  uint32_t phase = 0, dw_started = 0;
+
+  for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x) {
+    const int64_t row0 = item * A.rows_per_tile;
+    const int nrows = (int)min((int64_t)A.rows_per_tile, A.b.B - row0);
+    for (int i = tid; i < nrows * D; i += PT) {
+      const int r = i / D, d = i - r * D;
+      ps[i] = (d < br.w_poi) ? __ldg(br.tgt_poi + (size_t)A.b.tgt[row0 + r] * br.w_poi + d)
+                             : __ldg(br.tgt_reg + (size_t)A.b.treg[row0 + r] * br.w_reg + (d - br.w_poi));
+      dpacc[i] = 0.f;
+    }
+    if (tid < nrows) {
+      const float S = A.row_sum[row0 + tid];
+      rowv[tid] = S;
+      rowv[BWD_MAXROWS + tid] = A.parts[row0 + tid];
+      rowv[2 * BWD_MAXROWS + tid] = A.dscore[row0 + tid];
+      rowv[3 * BWD_MAXROWS + tid] = powf(S, p.beta);
+    }
+    __syncthreads();
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      int r, h;
+      bool valid;
+      if (H <= PT) {
+        r = tid / H;
+        h = tid - r * H;
+        valid = r < nrows;
+      } else {
+        r = 0;
+        h = ch * PT + tid;
+        valid = h < H;
+      }
+      const int64_t cidx = valid ? (row0 + r) * (int64_t)H + h : 0;
+      int it32 = 0, rg32 = 0;
+      float l0r = 0.f, l1r = 0.f;
+      bool live = false;
+      if (valid) {
+        it32 = (int)A.b.hist[cidx];
+        rg32 = br.w_reg ? (int)A.b.hreg[cidx] : 0;
+        if (lanes) {
+          l0r = A.b.aux[cidx * 2];
+          l1r = A.b.aux[cidx * 2 + 1];
+        }
+        live = (int64_t)it32 != A.b.tgt[row0 + r];
+      }
+      float g0 = 0.f, g1 = 0.f;
+      if (valid && lanes) {
+        const float a0 = l0r * p.dist_scale, a1 = l1r * p.dist_scale;
+        g0 = sigmoidf_exact(fmaf(a1, __ldg(p.dist_w + 1), fmaf(a0, __ldg(p.dist_w + 0), __ldg(p.dist_b + 0))));
+        g1 = sigmoidf_exact(fmaf(a1, __ldg(p.dist_w + 3), fmaf(a0, __ldg(p.dist_w + 2), __ldg(p.dist_b + 1))));
+      }
+      // ---- X image (bf16 hi/lo, unscaled) + similarity -----------------------------------------------------------------------------
+      float ssum = 0.f;
+      const float* pr = ps + (valid ? r : 0) * D;
+#pragma unroll
+      for (int s0 = 0; s0 < D; s0 += 32) {
+        float q[32];
+        gather_segment<32>(br, it32, rg32, s0, stg, lane, q);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float x[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            x[e] = valid ? q[c * 8 + e] * pr[s0 + c * 8 + e] : 0.f;
+            ssum += x[e];
+          }
+          store_chunk_bf16(sX, sX + X_PLANE, ((size_t)(s0 / 8 + c) * PT + tid) * 16, x);
+        }
+      }
+      {
+        const float ext[8] = {valid ? 1.f : 0.f, g0, g1, 0.f, 0.f, 0.f, 0.f, 0.f};
+        store_chunk_bf16(sX, sX + X_PLANE, ((size_t)(D / 8) * PT + tid) * 16, ext);
+      }
+      fence_proxy_async();
+      __syncthreads();  // X image complete; every warp is done with its staging slice (aliased on the DT image)
+      // ---- GEMM1: T = X W^T -----------------------------------------------------------------------------------------------------------
+      if (warp == 0) {
+        if (elect_one()) {
+          tc_fence_after();
+          const uint32_t x0 = smem_u32(sX), w0 = smem_u32(sW);
+          const uint32_t idesc = idesc_bf16(PT, HID, 0, 0);
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t ab = x0 + (pass == 2 ? X_PLANE : 0), wb = w0 + (pass == 1 ? W_PLANE : 0);
+#pragma unroll
+            for (int s = 0; s < D / 16; ++s)
+              mma_f16(tmem + COL_T, smem_desc(ab + s * 2 * PT * 16, PT * 16, 128), smem_desc(wb + s * 2 * HID * 16, HID * 16, 128), idesc,
+                      (pass | s) != 0);
+          }
+          mma_commit(bar);
+        }
+        __syncwarp();
+      }
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+      tc_fence_after();
+      // ---- epilogue 1: thread = cell = TMEM lane ----------------------------------------------------------------------------------------
+      float a = 0.f;
+      for (int c0 = 0; c0 < HID; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tlane + COL_T + c0, v);
+        tmem_wait_ld16(v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int k = c0 + i;
+          float t = __uint_as_float(v[i]) + kc[k];
+          if (lanes) t = fmaf(kc[3 * HID + k], g1, fmaf(kc[2 * HID + k], g0, t));
+          a = fmaf(kc[HID + k], fmaxf(t, 0.f), a);
+        }
+      }
+      float dav = 0.f, gwv = 0.f;
+      if (live) {
+        const float S = rowv[r], sc = rowv[BWD_MAXROWS + r], G = rowv[2 * BWD_MAXROWS + r], Sb = rowv[3 * BWD_MAXROWS + r];
+        const float e = expf(a);
+        const float w = e / Sb;
+        dav = G * (w * ssum - p.beta * (e / S) * sc);
+        gwv = G * w;
+      }
+      float dvv[HID];
+      float dg0 = 0.f, dg1 = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < HID; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tlane + COL_T + c0, v);
+        tmem_wait_ld16(v);
+        float dt[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int k = c0 + i;
+          float t = __uint_as_float(v[i]) + kc[k];
+          if (lanes) t = fmaf(kc[3 * HID + k], g1, fmaf(kc[2 * HID + k], g0, t));
+          dvv[k] = dav * fmaxf(t, 0.f);
+          dt[i] = (t > 0.f) ? dav * kc[HID + k] : 0.f;
+          dg0 = fmaf(dt[i], kc[2 * HID + k], dg0);
+          dg1 = fmaf(dt[i], kc[3 * HID + k], dg1);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float c8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) c8[e] = dt[j * 8 + e];
+          store_chunk_bf16(sDT, sDT + DT_PLANE, ((size_t)(c0 / 8 + j) * PT + tid) * 16, c8);
+        }
+      }
+      if (lanes) {  // dist layer: z = Wd (scale * ll) + bd, g = sigmoid(z)
+        const float dz0 = dg0 * g0 * (1.f - g0), dz1 = dg1 * g1 * (1.f - g1);
+        const float a0 = l0r * p.dist_scale, a1 = l1r * p.dist_scale;
+        pd[0] = fmaf(dz0, a0, pd[0]);
+        pd[1] = fmaf(dz0, a1, pd[1]);
+        pd[2] = fmaf(dz1, a0, pd[2]);
+        pd[3] = fmaf(dz1, a1, pd[3]);
+        pd[4] += dz0;
+        pd[5] += dz1;
+      }
+      // dw2[k] += sum over this warp's cells of da * relu(t_k): shuffle halving, 62 shuffles for all 64 hidden units
+#pragma unroll
+      for (int st = 0; st < 5; ++st) {
+        const int n = HID >> st, m = 16 >> st;
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < HID / 2; ++i) {
+          if (i < n / 2) {
+            const float send = up ? dvv[i] : dvv[i + n / 2];
+            const float keep = up ? dvv[i + n / 2] : dvv[i];
+            dvv[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+          }
+        }
+      }
+      dv_acc[0] += dvv[0];
+      dv_acc[1] += dvv[1];
+      tc_fence_before();
+      fence_proxy_async();
+      __syncthreads();  // DT image complete
+      // ---- GEMM2: dX = dt W   and   GEMM3: dW += dt^T [X | 1 g0 g1] ---------------------------------------------------------------------
+      if (warp == 0) {
+        if (elect_one()) {
+          tc_fence_after();
+          const uint32_t x0 = smem_u32(sX), w0 = smem_u32(sW), t0 = smem_u32(sDT);
+          const uint32_t id2 = idesc_bf16(PT, D, 0, 1), id3 = idesc_bf16(HID, D + 8, 1, 1);
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t ab = t0 + (pass == 2 ? DT_PLANE : 0), wb = w0 + (pass == 1 ? W_PLANE : 0);
+#pragma unroll
+            for (int s = 0; s < HID / 16; ++s)  // K = hidden units 16s..16s+15: DT k-chunks 2s, 2s+1; W image rows 16s.. (+256 B)
+              mma_f16(tmem + COL_DX, smem_desc(ab + s * 2 * PT * 16, PT * 16, 128), smem_desc(wb + s * 256, 128, HID * 16), id2,
+                      (pass | s) != 0);
+          }
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t ab = t0 + (pass == 2 ? DT_PLANE : 0), xb = x0 + (pass == 1 ? X_PLANE : 0);
+#pragma unroll
+            for (int s = 0; s < PT / 16; ++s)  // K = cells 16s..16s+15 of both images (+256 B); mn blocks at the k-chunk stride
+              mma_f16(tmem + COL_DW, smem_desc(ab + s * 256, 128, PT * 16), smem_desc(xb + s * 256, 128, PT * 16), id3,
+                      (dw_started | pass | s) != 0);
+          }
+          mma_commit(bar);
+        }
+        __syncwarp();
+      }
+      dw_started = 1u;
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+      tc_fence_after();
+      // ---- epilogue 2: dq rows to the workspace, dp contributions to the scratch (aliased on the X image) -----------------------------
+#pragma unroll
+      for (int s0 = 0; s0 < D; s0 += 32) {
+        float q[32];
+        gather_segment<32>(br, it32, rg32, s0, stg, lane, q);
+#pragma unroll
+        for (int c0 = 0; c0 < 32; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(tlane + COL_DX + s0 + c0, v);
+          tmem_wait_ld16(v);
+          float o[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int d = s0 + c0 + i;
+            const float full = __uint_as_float(v[i]) + gwv;
+            o[i] = full * pr[d];
+            dps[(size_t)d * DP_STRIDE + tid] = valid ? full * q[c0 + i] : 0.f;
+          }
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              *reinterpret_cast<float4*>(A.ws_dq + cidx * D + s0 + c0 + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncthreads();
+      {
+        const int nr = (H <= PT) ? nrows : 1;
+        for (int i = tid; i < nr * D; i += PT) {
+          const int rr = i / D, d = i - rr * D;
+          const int c0 = (H <= PT) ? rr * H : 0;
+          const int cn = (H <= PT) ? H : min(PT, H - ch * PT);
+          float sacc = 0.f;
+          for (int c = 0; c < cn; ++c) sacc += dps[(size_t)d * DP_STRIDE + c0 + c];
+          dpacc[rr * D + d] += sacc;
+        }
+      }
+      __syncthreads();  // scratch (X image) and staging (DT image) are free again
+    }
+    for (int i = tid; i < nrows * D; i += PT) A.ws_dp[(row0 + i / D) * D + (i % D)] = dpacc[i];
+    __syncthreads();
+  }
+
+  // ---- this CTA's parameter partial: w1 [hid][ldw] | b1 | w2 | dist_w[4] dist_b[2] km pad --------------------------------------------
+  float* part = A.ws_part + (size_t)blockIdx.x * A.part_stride;
+  tc_fence_after();
+  {
+    const int m = 16 * warp + (lane & 15);  // the M = 64 accumulator keeps row m in TMEM lane 32*(m/16) + m%16
+    for (int c0 = 0; c0 < D + 16; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tlane + COL_DW + c0, v);
+      tmem_wait_ld16(v);
+      if (lane < 16) {
+        if (c0 < D) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) part[(size_t)m * ldw + c0 + i] = __uint_as_float(v[i]);
+        } else {  // ext chunk: [sum dt * 1, sum dt * g0, sum dt * g1]
+          part[HID * ldw + m] = __uint_as_float(v[0]);
+          if (lanes) {
+            part[(size_t)m * ldw + D] = __uint_as_float(v[1]);
+            part[(size_t)m * ldw + D + 1] = __uint_as_float(v[2]);
+          }
+        }
+      }
+    }
+  }
+  dvs[warp * HID + dv_k0] = dv_acc[0];
+  dvs[warp * HID + dv_k0 + 1] = dv_acc[1];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    float v = pd[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[q * 4 + warp] = v;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < HID) part[HID * ldw + HID + tid] = dvs[tid] + dvs[HID + tid] + dvs[2 * HID + tid] + dvs[3 * HID + tid];
+  if (tid < 7) part[HID * ldw + 2 * HID + tid] = tid < 6 ? red[tid * 4] + red[tid * 4 + 1] + red[tid * 4 + 2] + red[tid * 4 + 3] : 0.f;
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+template <int D>
+static int launch(const BwdArgs& A, int grid, cudaStream_t stream) {
+  constexpr size_t smem = 2 * (size_t)(D / 8 + 1) * PT * 16 + 2 * (size_t)(D / 8) * HID * 16 + 2 * (size_t)(HID / 8) * PT * 16 +
+                          (4 * HID + 2 * BWD_MAXROWS * D + 4 * BWD_MAXROWS + 4 * HID + 32) * 4 + 16;
+  cudaError_t e = cudaFuncSetAttribute(pairs_bwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(pairs_bwd_tc_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return (int)e;
+  pairs_bwd_tc_kernel<D><<<grid, PT, smem, stream>>>(A);
+  NAIS_COUNT_LAUNCH(1);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace ptcb
+
+bool pairs_tc_bwd_wanted() {
+  const char* v = getenv("NAIS_PAIRS_TC_BWD");
+  return v && v[0] && v[0] != '0';
+}
+
+bool pairs_tc_bwd_supported(const NaisParams& p, const NaisPairs& b) {
+  if (p.n_branch != 1 || b.B < 1 || p.hid != ptcb::HID) return false;
+  const NaisBranch& br = p.branch[0];
+  const int D = br.w_poi + br.w_reg;
+  if (D != 32 && D != 64) return false;
+  if (p.dist_mode == NAIS_DIST_KM || p.dropout_p > 0.f) return false;
+  if (!rows_vec4(br, 4)) return false;
+  int dev = 0, major = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  return major == 10;
+}
+
+// grid <= 2 CTAs per SM (256 TMEM columns each); every CTA owns at least one tile (the caller passes min(n_items, grid))
+int launch_pairs_bwd_tc(const BwdArgs& A, int D, int grid, cudaStream_t stream) {
+  return D == 32 ? ptcb::launch<32>(A, grid, stream) : ptcb::launch<64>(A, grid, stream);
+}
+
+}  // namespace nais

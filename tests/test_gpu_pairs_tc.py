@@ -107,3 +107,61 @@ def test_pairs_tc_c3_shape_forward_and_gradients(pairs_tc):
         r = np.asarray(ref[name], dtype=np.float64)
         g = np.zeros_like(r) if p.grad is None else p.grad.detach().cpu().double().numpy()
         assert np.abs(g - r).max() <= 2e-4 * np.abs(r).max() + 1e-12, name
+
+
+def _grads_gpu(sd, beta, hist, tgt, region, aux, dscore):
+    m = util.make_model("region_distance", sd, beta)
+    s = m.attention_network(_dev(hist), _dev(tgt), _dev(region[hist]), _dev(region[tgt]), _dev(aux))
+    (s * _dev(dscore).float()).sum().backward()
+    torch.cuda.synchronize()
+    return {n: (None if p.grad is None else p.grad.detach().cpu().double().numpy()) for n, p in m.named_parameters()}
+
+
+@pytest.mark.parametrize("B,H,D", [(256, 128, 64), (150, 21, 64), (40, 300, 64), (100, 50, 32)])
+def test_pairs_tc_backward_matches_oracle(B, H, D, monkeypatch):
+    """Tensor-core backward (csrc/nais_pairs_tc_bwd.cu, NAIS_PAIRS_TC_BWD=1: bf16 two-term splits, dW accumulated in TMEM through
+    MN-major reads of the operand images) against the oracle's float64 autograd, with the gradient bar of the FP32 backward's
+    tests (per tensor 2e-4 of its maximum); and it must not be the FP32 backward in disguise."""
+    sd, hist, tgt, region, aux = _case("region_distance", 3000, D, 64, B, H, seed=B + H)
+    dscore = np.random.default_rng(7).normal(size=B)
+    monkeypatch.setenv("NAIS_PAIRS_TC_BWD", "1")
+    g_tc = _grads_gpu(sd, 0.5, hist, tgt, region, aux, dscore)
+    monkeypatch.setenv("NAIS_PAIRS_TC_BWD", "0")
+    g_fp = _grads_gpu(sd, 0.5, hist, tgt, region, aux, dscore)
+    _, ref = orc.grads(sd, "region_distance", 0.5, torch.from_numpy(hist), torch.from_numpy(tgt), torch.from_numpy(region[hist]),
+                       torch.from_numpy(region[tgt]), torch.from_numpy(aux), torch.from_numpy(dscore))
+    ref = {k: v.numpy() for k, v in ref.items()}
+    ref.setdefault("embed_distance.weight", np.zeros((1, D)))
+    assert not np.array_equal(g_tc["attn_layer1.weight"], g_fp["attn_layer1.weight"]), "the tensor-core backward did not run"
+    worst = {}
+    for name, r in ref.items():
+        r = np.asarray(r, dtype=np.float64)
+        g = np.zeros_like(r) if g_tc.get(name) is None else g_tc[name]
+        worst[name] = float(np.abs(g - r).max() / max(np.abs(r).max(), 1e-300))
+    print("tc backward, max err / max|ref| per tensor:", {k: f"{v:.1e}" for k, v in worst.items()})
+    for name, v in worst.items():
+        if np.abs(ref[name]).max() > 0:
+            assert v <= 2e-4, (name, v)
+
+
+def test_pairs_tc_backward_timing(monkeypatch, capsys):
+    """Not a pass/fail timing: prints the C3-shaped backward (4096 rows x H = 128) in both modes for the round log."""
+    sd, hist, tgt, region, aux = _case("region_distance", 40000, 64, 64, 4096, 128, seed=3)
+    m = util.make_model("region_distance", sd, 0.5)
+    args = (_dev(hist), _dev(tgt), _dev(region[hist]), _dev(region[tgt]), _dev(aux))
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("NAIS_PAIRS_TC_BWD", mode)
+        ts = []
+        for it in range(4):
+            m.zero_grad(set_to_none=True)
+            s = m.attention_network(*args).sum()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            s.backward()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        out[mode] = min(ts[1:])
+    with capsys.disabled():
+        print(f"\nC3-shaped backward incl. reduces: fp32 {out['0']:.3f} ms, tensor-core {out['1']:.3f} ms")
