@@ -263,6 +263,28 @@ def run_train(args, dev, lib, peaks, rank, world):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    launches_timed = int(lib.nais_launch_count() - l0)  # this library's kernels inside the timed region only
+    # the same step with the opt-in tensor-core pair kernels (NAIS_PAIRS_TC / NAIS_PAIRS_TC_BWD are read by the library per call)
+    tc_opt = None
+    if world == 1:
+        try:
+            os.environ["NAIS_PAIRS_TC"] = os.environ["NAIS_PAIRS_TC_BWD"] = "1"
+            for _ in range(args.warmup):
+                step()
+            torch.cuda.synchronize()
+            a3, b3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a3.record()
+            for _ in range(args.steps):
+                loss_tc = step()
+            b3.record()
+            torch.cuda.synchronize()
+            tc_opt = {"ms_per_step": a3.elapsed_time(b3) / args.steps, "loss": float(loss_tc.detach()),
+                      "note": "NAIS_PAIRS_TC=1 NAIS_PAIRS_TC_BWD=1: pair forward and backward contractions on tcgen05 (opt-in)"}
+        except Exception as e:  # noqa: BLE001
+            tc_opt = {"error": f"{type(e).__name__}: {e}"}
+        finally:
+            os.environ.pop("NAIS_PAIRS_TC", None)
+            os.environ.pop("NAIS_PAIRS_TC_BWD", None)
     # the whole reference step (run.py:248-254: zero_grad, forward, BCELoss, backward, Adagrad.step) on 8192 pairs:
     # dense torch.optim.Adagrad over the [N, D/2] tables vs the row-sparse Adagrad fused into the segment reduce (f2),
     # at C3's catalogue (40k POIs: 5 MB tables) and at C4's (1M POIs: 128 MB tables, where the dense step is HBM traffic)
@@ -315,7 +337,7 @@ def run_train(args, dev, lib, peaks, rank, world):
                           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                           "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
                           "config": {"workload": "C3: 4096 (user,pos,neg) triples, H=128, D=hid=64, fwd+bwd (FP32 kernels)"},
-                          "gpu_launches": int(lib.nais_launch_count() - l0), "loss": float(loss.detach()), "full_step": full,
+                          "gpu_launches": launches_timed, "loss": float(loss.detach()), "tc_opt_in": tc_opt, "full_step": full,
                           "roofline": {"bound": "fp32-ffma", "achieved": tf, "unit": "TFLOP/s",
                                        "note": "algorithmic 4F per cell; CUDA-core path (tensor-core backward is next-round work)"}}), flush=True)
 
