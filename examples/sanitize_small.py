@@ -38,10 +38,17 @@ def main():
         else:
             s = m.attention_network(hist, tgt, reg[hist], reg[tgt], ll)
         s.sum().backward()
+        if name == "NAIS_region_distance_Embedding":  # the opt-in tensor-core pair kernels (forward + backward)
+            os.environ["NAIS_PAIRS_TC"] = os.environ["NAIS_PAIRS_TC_BWD"] = "1"
+            m.zero_grad(set_to_none=True)
+            m.eval()  # no dropout on this class anyway; eval keeps the shapes the tensor-core path supports
+            m.attention_network(hist, tgt, reg[hist], reg[tgt], ll).sum().backward()
+            os.environ.pop("NAIS_PAIRS_TC")
+            os.environ.pop("NAIS_PAIRS_TC_BWD")
         m.eval()
         m.set_catalog(region=data.region, coords=data.coords)
         users = m.make_users(data.indptr, data.indices)
-        precs = ("fp32",) if "disentangled" in name else ("fp32", "tc_split", "tc_fast")
+        precs = ("fp32",) if "disentangled" in name else ("fp32", "tc_split", "tc_mix", "tc_fast")
         outs = []
         for prec in precs:
             outs.append(ops.fullrank_topk(m.variant, 0.5, m._params(), m._catalog, users, 10, precision=prec))
