@@ -75,6 +75,23 @@ def test_validation_flow_matches_reference(golden_dir):
     assert np.array_equal(np.array([pv, rv, hv, pt, rt, ht]), z["metrics"])  # bit-identical python floats
 
 
+@pytest.mark.parametrize("variant", ["basic", "region"])
+def test_sibling_validators_match_reference(golden_dir, variant):
+    """validation.NAIS_validation (validation.py:7-31, chunks of 1024) and NAIS_region_validation (:34-59): the oracle's full-rank
+    flow gives the reference's recommended lists and metrics for the sibling scorers too."""
+    z = _load(golden_dir, f"validation_{variant}.npz")
+    sd = _sd(z, "sd.")
+    cat = orc.Catalog(z["coords"], z["region"])
+    rec = orc.fullrank(sd, variant, float(z["beta"]), cat, z["indptr"], z["indices"], topk=50, chunk=1024)
+    assert np.array_equal(np.array(rec), z["rec"])
+    val = [z["val_flat"][z["val_ptr"][u]:z["val_ptr"][u + 1]].tolist() for u in range(int(z["U"]))]
+    test = [z["test_flat"][z["test_ptr"][u]:z["test_ptr"][u + 1]].tolist() for u in range(int(z["U"]))]
+    k_list = z["k_list"].tolist()
+    pv, rv, hv = orc.evaluate(val, rec, k_list)
+    pt, rt, ht = orc.evaluate(test, rec, k_list)
+    assert np.array_equal(np.array([pv, rv, hv, pt, rt, ht]), z["metrics"])
+
+
 def test_batches_match_reference(golden_dir):
     z = _load(golden_dir, "batches.npz")
     for u in range(4):
