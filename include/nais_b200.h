@@ -17,7 +17,9 @@
  *   - every pointer is a DEVICE pointer into memory owned by the caller (PyTorch tensors); the library never
  *     allocates, frees or synchronises, and enqueues only on the given stream;
  *   - return 0 = OK; negative = argument error found before any launch (see NAIS_ERR_*); positive = cudaError_t;
- *   - all entry points are stateless and re-entrant; one host thread per GPU is the intended use;
+ *   - all entry points are stateless and re-entrant (no environment variables, no hidden switches: every option is an
+ *     argument or a struct field declared here); one host thread per GPU is the intended use.  The one piece of library-owned
+ *     device state is a 4-byte "bad index" word per device, see nais_poll_bad_index;
  *   - no C++ types, no torch types: plain pointers and sizes.
  */
 #ifndef NAIS_B200_H_
@@ -30,7 +32,7 @@
 extern "C" {
 #endif
 
-#define NAIS_ABI_VERSION 1
+#define NAIS_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define NAIS_API __attribute__((visibility("default")))
@@ -49,6 +51,15 @@ extern "C" {
 #define NAIS_PREC_TC_FAST 2  /* tcgen05 fp16 MMA, single pass (11-bit operands), fp32 accumulate in TMEM */
 #define NAIS_PREC_TC_MIX 3   /* tcgen05 fp16 MMA for hi*hi + two e5m2 (kind::f8f6f4) MMAs for the hi*lo, lo*hi corrections */
 #define NAIS_PREC_TC_AUTO 4  /* MIX when a device-side bound on the logit scale keeps its error 4x under 1e-4, else SPLIT */
+#define NAIS_PREC_MASK 0xff
+/* OR-ed into `precision`: run the tensor path's run-time-shape kernel even where a compile-time-shape instantiation exists
+ * (D = hid = 32 / 64 / 128).  Same results bit for bit; the parity suite uses it to cover both code paths. */
+#define NAIS_PREC_FLAG_GENERIC 0x100
+
+/* NaisParams::pairs_precision — which kernels nais_pairs_forward / nais_pairs_backward[_adagrad] run */
+#define NAIS_PAIRS_AUTO 0 /* tcgen05 kernels wherever the shape has them (see the entry points), FP32 CUDA-core kernels elsewhere */
+#define NAIS_PAIRS_FP32 1 /* always the FP32 CUDA-core kernels */
+#define NAIS_PAIRS_TC 2   /* tcgen05 kernels; NAIS_ERR_SHAPE if the shape has none */
 
 #define NAIS_ERR_NULL -1      /* required pointer is NULL */
 #define NAIS_ERR_SHAPE -2     /* unsupported / inconsistent dimension */
@@ -56,6 +67,7 @@ extern "C" {
 #define NAIS_ERR_WORKSPACE -4 /* workspace too small (ask nais_*_workspace_bytes) */
 #define NAIS_ERR_MODE -5      /* unknown mode / flag combination */
 #define NAIS_ERR_ARCH -6      /* device is not sm_100 (tensor path) */
+#define NAIS_ERR_INDEX -7     /* a POI / region id was outside its table (reported by nais_poll_bad_index) */
 
 typedef void* nais_stream_t; /* cudaStream_t */
 
@@ -95,6 +107,8 @@ typedef struct NaisParams {
    * forward and backward of one step must be given the same seed.  Pair API only. */
   float dropout_p;
   uint64_t dropout_seed;
+  int32_t pairs_precision; /* NAIS_PAIRS_* (pair API only) */
+  int32_t reserved0;
 } NaisParams;
 
 /* A batch of explicit (history row, target) pairs: the argument list of model.forward (model.py:231). */
@@ -185,6 +199,49 @@ NAIS_API size_t nais_fullrank_workspace_bytes(const NaisParams* p, int32_t n_use
 NAIS_API int nais_fullrank_topk(const NaisParams* p, const NaisCatalog* cat, const NaisUsers* users, int64_t poi_begin,
                        int64_t poi_end, int32_t k, int32_t exclude_history, int32_t precision, float* out_score, int32_t* out_id, void* workspace, size_t workspace_bytes,
                        nais_stream_t stream);
+
+/* ---- planned full-rank scoring: the per-model / per-catalogue constants are computed ONCE --------------------------------------
+ * nais_fullrank_topk recomputes, on every call, things that only depend on the weights and the catalogue range: the table maxima
+ * and power-of-two scales, the hidden-unit permutation, and the packed candidate image (tensor path).  An evaluation scores many
+ * user batches against the same weights (validation.py:69 loops over all users with a frozen model), so:
+ *
+ *   plan = caller-owned device buffer of nais_fullrank_plan_bytes(...) bytes
+ *   nais_fullrank_prepare(...)        once per (weights, catalogue range, precision); enqueued on `stream`, never synchronises
+ *   nais_fullrank_topk_planned(...)   per user batch: packs the users' operand, scores, block top-k, merge
+ *
+ * The plan is read-only at call time (several streams may score against one plan).  It is valid until a parameter tensor, the
+ * catalogue arrays or the range change; the caller re-prepares after an optimizer step.  NAIS_PREC_FP32 needs no plan
+ * (plan_bytes = 0, plan may be NULL).  Results are bit-identical to nais_fullrank_topk. */
+NAIS_API size_t nais_fullrank_plan_bytes(const NaisParams* p, int64_t poi_begin, int64_t poi_end, int32_t precision);
+NAIS_API int nais_fullrank_prepare(const NaisParams* p, const NaisCatalog* cat, int64_t poi_begin, int64_t poi_end,
+                                   int32_t precision, void* plan, size_t plan_bytes, nais_stream_t stream);
+/* Workspace of a planned call (no candidate image inside: smaller than nais_fullrank_workspace_bytes). */
+NAIS_API size_t nais_fullrank_planned_workspace_bytes(const NaisParams* p, int32_t n_users, int64_t nnz, int64_t poi_begin,
+                                                      int64_t poi_end, int32_t k, int32_t precision);
+/* Outputs: out_score / out_id as nais_fullrank_topk (both or neither may be NULL) and / or out_keys [n_users, k]: the packed
+ * ranking keys (ordered(score) << 32 | ~id; 0 = no entry) that nais_topk_merge_keys consumes — one 8-byte word per entry, so
+ * the per-shard lists of a range-sharded catalogue travel in ONE all-gather. */
+NAIS_API int nais_fullrank_topk_planned(const NaisParams* p, const NaisCatalog* cat, const NaisUsers* users, int64_t poi_begin,
+                                        int64_t poi_end, int32_t k, int32_t exclude_history, int32_t precision, const void* plan,
+                                        size_t plan_bytes, uint64_t* out_keys, float* out_score, int32_t* out_id, void* workspace,
+                                        size_t workspace_bytes, nais_stream_t stream);
+
+/* Merge n_lists key lists per user into one (score desc, id asc — the order of nais_fullrank_topk).  List l of user u starts at
+ * in_keys + u * user_stride + l * list_stride (strides in 8-byte words), so the [world, n_users, k] buffer an all-gather
+ * produces is merged in place: user_stride = k, list_stride = n_users * k.  out_keys / (out_score, out_id): either may be NULL. */
+NAIS_API int nais_topk_merge_keys(const uint64_t* in_keys, int64_t user_stride, int64_t list_stride, int32_t n_users,
+                                  int32_t n_lists, int32_t k, uint64_t* out_keys, float* out_score, int32_t* out_id,
+                                  nais_stream_t stream);
+
+/* Out-of-range ids.  nn.Embedding raises IndexError on an id outside its table (the reference's behaviour for a bad batch or
+ * a region_num mismatch).  The kernels cannot raise and the library never synchronises, so: every id read by the pair kernels
+ * (hist, tgt, hreg, treg) and by the user-operand pack of the full-rank path is range-checked on the device; an out-of-range
+ * id is never used as an address (reads fall back to row 0, its gradient contribution is dropped, no table / optimizer row
+ * is written for it) and sets the device's bad-index word.  nais_poll_bad_index enqueues, on `stream`, a copy of that word
+ * into *host_flag (pinned host memory recommended: then the call is asynchronous) followed by its reset; once the stream has
+ * reached that point, *host_flag != 0 means some kernel enqueued before the poll saw a bad id -> the caller raises
+ * (NAIS_ERR_INDEX).  Returns 0 or a cudaError_t. */
+NAIS_API int nais_poll_bad_index(int32_t* host_flag, nais_stream_t stream);
 
 /* Merge n_lists sorted top-k lists per user (e.g. one per catalogue shard after an all-gather) into one.
  * in_score/in_id: [n_users, n_lists, k]; out: [n_users, k].  Same order rule as nais_fullrank_topk. */

@@ -9,9 +9,14 @@ LIB_PATH = os.path.join(HERE, "libnais_b200.so")
 
 DIST_NONE, DIST_LATLON, DIST_KM = 0, 1, 2
 PREC_FP32, PREC_TC_SPLIT, PREC_TC_FAST, PREC_TC_MIX, PREC_TC_AUTO = 0, 1, 2, 3, 4
+PREC_FLAG_GENERIC = 0x100  # run-time-shape tensor kernel even where a compile-time-shape instantiation exists
 PRECISIONS = {"fp32": PREC_FP32, "tc_split": PREC_TC_SPLIT, "tc_fast": PREC_TC_FAST, "tc_mix": PREC_TC_MIX,
               "tc_auto": PREC_TC_AUTO}
+PRECISIONS.update({k + "_generic": v | PREC_FLAG_GENERIC for k, v in list(PRECISIONS.items()) if k != "fp32"})
+PAIRS_PRECISIONS = {"auto": 0, "fp32": 1, "tc": 2}  # NAIS_PAIRS_*
+ERR_INDEX = -7
 
+ABI_VERSION = 2  # NAIS_ABI_VERSION of include/nais_b200.h
 c_float_p = C.c_void_p  # device pointers travel as integers
 
 
@@ -25,7 +30,7 @@ class NaisParams(C.Structure):
                 ("region_num", C.c_int32), ("dist_mode", C.c_int32), ("dist_scale", C.c_float), ("dist_w", C.c_void_p),
                 ("dist_b", C.c_void_p), ("dist_embed", C.c_void_p), ("dist_buckets", C.c_int32),
                 ("dist_bucket_km", C.c_float), ("beta", C.c_float), ("dropout_p", C.c_float),
-                ("dropout_seed", C.c_uint64)]
+                ("dropout_seed", C.c_uint64), ("pairs_precision", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class NaisPairs(C.Structure):
@@ -80,6 +85,17 @@ SYMBOLS = {
                                  C.c_void_p]),
     "nais_topk_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),
+    "nais_fullrank_plan_bytes": (C.c_size_t, [C.POINTER(NaisParams), C.c_int64, C.c_int64, C.c_int32]),
+    "nais_fullrank_prepare": (C.c_int, [C.POINTER(NaisParams), C.POINTER(NaisCatalog), C.c_int64, C.c_int64, C.c_int32,
+                                        C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nais_fullrank_planned_workspace_bytes": (C.c_size_t, [C.POINTER(NaisParams), C.c_int32, C.c_int64, C.c_int64, C.c_int64,
+                                                           C.c_int32, C.c_int32]),
+    "nais_fullrank_topk_planned": (C.c_int, [C.POINTER(NaisParams), C.POINTER(NaisCatalog), C.POINTER(NaisUsers), C.c_int64,
+                                             C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nais_topk_merge_keys": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nais_poll_bad_index": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 
 _lib = None
@@ -99,7 +115,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.nais_abi_version() != 1:
+    if lib.nais_abi_version() != ABI_VERSION:
         raise RuntimeError("libnais_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -17,8 +17,7 @@ namespace nais {
 
 
 
-// nais_pairs_tc_bwd.cu (opt-in: NAIS_PAIRS_TC_BWD=1): same workspace outputs as pairs_bwd_kernel
-bool pairs_tc_bwd_wanted();
+// nais_pairs_tc_bwd.cu: same workspace outputs as pairs_bwd_kernel
 bool pairs_tc_bwd_supported(const NaisParams& p, const NaisPairs& b);
 int launch_pairs_bwd_tc(const BwdArgs& A, int D, int grid, cudaStream_t stream);
 
@@ -92,8 +91,8 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
     __syncthreads();
     for (int i = tid; i < nrows * D; i += NT) {
       int r = i / D, d = i - r * D;
-      ps[r * D + d] = (d < br.w_poi) ? __ldg(br.tgt_poi + (size_t)A.b.tgt[row0 + r] * br.w_poi + d)
-                                     : __ldg(br.tgt_reg + (size_t)A.b.treg[row0 + r] * br.w_reg + (d - br.w_poi));
+      ps[r * D + d] = (d < br.w_poi) ? __ldg(br.tgt_poi + (size_t)checked_id(A.b.tgt[row0 + r], p.item_num, A.bad) * br.w_poi + d)
+                                     : __ldg(br.tgt_reg + (size_t)checked_id(A.b.treg[row0 + r], p.region_num, A.bad) * br.w_reg + (d - br.w_poi));
       dpacc[r * D + d] = 0.f;
     }
     if (tid < nrows) {
@@ -123,8 +122,8 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
         float ssum = 0.f;
         int64_t it = 0, rg = 0;
         if (valid) {
-          it = A.b.hist[cidx];
-          rg = br.w_reg ? A.b.hreg[cidx] : 0;
+          it = checked_id(A.b.hist[cidx], p.item_num, A.bad);
+          rg = br.w_reg ? checked_id(A.b.hreg[cidx], p.region_num, A.bad) : 0;
           const float* qp = br.hist_poi + (size_t)it * br.w_poi;
           const float* qr = br.hist_reg + (size_t)rg * br.w_reg;
           if (vec4) {  // 128-bit row loads (same products, same summation order as the scalar walk and as the forward)
@@ -520,27 +519,30 @@ __global__ void param_reduce_kernel(const float* __restrict__ parts, int n_parts
 }
 
 // Keys for the three gathers.  src encodes where the contribution row lives: cell index (dq) or B*H + row (dp).
-__global__ void make_keys_kernel(NaisPairs b, int want_reg, int* k_hist, uint32_t* v_hist, int* k_tgt, uint32_t* v_tgt,
-                                 int* k_reg, uint32_t* v_reg) {
+// An id outside its table gets the key `n_rows` (one past the last row): it sorts behind every real row and the segment
+// reduce drops it, so no table / optimizer row is written for it (the kernels that read it raised the bad-index word).
+__device__ __forceinline__ int key_of(int64_t id, int n_rows) { return (uint64_t)id < (uint64_t)n_rows ? (int)id : n_rows; }
+__global__ void make_keys_kernel(NaisPairs b, int want_reg, int item_num, int region_num, int* k_hist, uint32_t* v_hist, int* k_tgt,
+                                 uint32_t* v_tgt, int* k_reg, uint32_t* v_reg) {
   const int64_t n_cells = b.B * (int64_t)b.H;
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n_cells) {
     if (k_hist) {
-      k_hist[i] = (int)b.hist[i];
+      k_hist[i] = key_of(b.hist[i], item_num);
       v_hist[i] = (uint32_t)i;
     }
     if (want_reg) {
-      k_reg[i] = (int)b.hreg[i];
+      k_reg[i] = key_of(b.hreg[i], region_num);
       v_reg[i] = (uint32_t)i;
     }
   }
   if (i < b.B) {
     if (k_tgt) {
-      k_tgt[i] = (int)b.tgt[i];
+      k_tgt[i] = key_of(b.tgt[i], item_num);
       v_tgt[i] = (uint32_t)(n_cells + i);
     }
     if (want_reg) {
-      k_reg[n_cells + i] = (int)b.treg[i];
+      k_reg[n_cells + i] = key_of(b.treg[i], region_num);
       v_reg[n_cells + i] = (uint32_t)(n_cells + i);
     }
   }
@@ -578,9 +580,13 @@ __device__ __forceinline__ const float* seg_row(uint32_t s, int64_t n_cells, con
   return (s < n_cells) ? ws_dq + (size_t)s * D : ws_dp + (size_t)(s - n_cells) * D;
 }
 
+// Pass 1 is a gather of 128-byte .. 512-byte rows in sorted order — HBM-bound once enough loads are in flight: the chunk's keys /
+// sources are read once (coalesced, two per lane) and handed around by shuffles, and the rows are fetched SEG_ILP at a time
+// before the (serial, branchy) run bookkeeping touches them.  (r1: one row load in flight per warp = 20 % of the HBM peak.)
+constexpr int SEG_ILP = 8;
 __global__ void segment_reduce_pass1_kernel(const int* __restrict__ keys, const uint32_t* __restrict__ src, int64_t n,
                                             int64_t n_cells, const float* __restrict__ ws_dq,
-                                            const float* __restrict__ ws_dp, int D, int off, int w, SegOut out,
+                                            const float* __restrict__ ws_dp, int D, int off, int w, int n_rows, SegOut out,
                                             int* __restrict__ part_key, int* __restrict__ part_start,
                                             float* __restrict__ part_rows) {
   const int64_t chunk = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -588,14 +594,26 @@ __global__ void segment_reduce_pass1_kernel(const int* __restrict__ keys, const 
   const int64_t start = chunk * SEG_CHUNK;
   if (start >= n) return;
   const int64_t end = min(n, start + SEG_CHUNK);
+  const int cnt = (int)(end - start);
   if (lane < 2) part_key[2 * chunk + lane] = -1;
+  // this lane's two entries of the chunk, and the neighbours' keys that decide whether a boundary run continues
+  int kreg[2];
+  uint32_t sreg[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int64_t i = start + lane + 32 * q;
+    kreg[q] = i < end ? keys[i] : -1;
+    sreg[q] = i < end ? src[i] : 0u;
+  }
+  const int key_before = start > 0 ? keys[start - 1] : -1, key_after = end < n ? keys[end] : -1;
   __syncwarp();
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  int cur = keys[start];
+  int cur = __shfl_sync(0xffffffffu, kreg[0], 0);
   bool first = true;
   auto flush = [&](bool last) {
-    const bool left = first && start > 0 && keys[start - 1] == cur;
-    const bool right = last && end < n && keys[end] == cur;
+    if (cur >= n_rows) return;  // ids outside the table (make_keys_kernel): dropped
+    const bool left = first && cur == key_before;
+    const bool right = last && cur == key_after;
     if (!left && !right) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -611,19 +629,34 @@ __global__ void segment_reduce_pass1_kernel(const int* __restrict__ keys, const 
         if (lane + 32 * i < w) part_rows[(size_t)slot * w + lane + 32 * i] = acc[i];
     }
   };
-  for (int64_t i = start; i < end; ++i) {
-    const int k = keys[i];
-    if (k != cur) {
-      flush(false);
-      first = false;
-      cur = k;
+  for (int j0 = 0; j0 < cnt; j0 += SEG_ILP) {
+    float rows[SEG_ILP][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = 0.f;
+    for (int u = 0; u < SEG_ILP; ++u) {
+      const int j = j0 + u;
+      const uint32_t sj = __shfl_sync(0xffffffffu, (j & 32) ? sreg[1] : sreg[0], j & 31);
+      if (j < cnt) {
+        const float* row = seg_row(sj, n_cells, ws_dq, ws_dp, D) + off;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rows[u][q] = (lane + 32 * q < w) ? __ldg(row + lane + 32 * q) : 0.f;
+      }
     }
-    const float* row = seg_row(src[i], n_cells, ws_dq, ws_dp, D) + off;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (lane + 32 * j < w) acc[j] += row[lane + 32 * j];
+    for (int u = 0; u < SEG_ILP; ++u) {
+      const int j = j0 + u;
+      const int k = __shfl_sync(0xffffffffu, (j & 32) ? kreg[1] : kreg[0], j & 31);
+      if (j < cnt) {
+        if (k != cur) {
+          flush(false);
+          first = false;
+          cur = k;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[q] = 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] += rows[u][q];
+      }
+    }
   }
   flush(true);
 }
@@ -652,7 +685,7 @@ __global__ void segment_reduce_pass2_kernel(const int* __restrict__ part_key, co
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct BwdLayout {
-  size_t dq, dp, part, keys[6], cub, pkey, pstart, prows, total;
+  size_t dq, dp, part, keys[8], cub, pkey, pstart, prows, total;
   int64_t n_chunks;
   int grid, stride;
   size_t cub_bytes;
@@ -675,7 +708,7 @@ static BwdLayout bwd_layout(const NaisParams& p, int64_t B, int H) {
   L.stride = part_floats(p.hid, D, lanes);
   L.part = o;
   o += align_up((size_t)L.grid * L.stride * 4);
-  for (int i = 0; i < 6; ++i) {  // keys_in, vals_in, keys_out, vals_out (x1), sized for the largest list; reused
+  for (int i = 0; i < 8; ++i) {  // three (keys, sources) input lists + one sorted output pair, each sized for the largest list
     L.keys[i] = o;
     o += align_up((size_t)n_max * 4);
   }
@@ -750,7 +783,10 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
     int grid = (int)(A.n_items < L.grid ? A.n_items : L.grid);
     int rc;
     const int nkb = p.hid <= 64 ? 1 : 2, db = D <= 64 ? 1 : 2;
-    if (pairs_tc_bwd_wanted() && pairs_tc_bwd_supported(p, b)) rc = launch_pairs_bwd_tc(A, D, grid, stream);  // opt-in: tcgen05
+    A.bad = bad_index_flag();
+    const bool tc_ok = pairs_tc_bwd_supported(p, b);
+    if (p.pairs_precision == NAIS_PAIRS_TC && !tc_ok) return NAIS_ERR_SHAPE;
+    if (p.pairs_precision != NAIS_PAIRS_FP32 && tc_ok) rc = launch_pairs_bwd_tc(A, D, grid, stream);  // tcgen05 (bf16 two-term splits)
     else if (nkb == 1 && db == 1) rc = launch_bwd_tile<1, 1>(A, D, grid, stream);
     else if (nkb == 1) rc = launch_bwd_tile<1, 2>(A, D, grid, stream);
     else if (db == 1) rc = launch_bwd_tile<2, 1>(A, D, grid, stream);
@@ -779,32 +815,31 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
       return o;
     };
     const int64_t n_thr = n_cells > b.B ? n_cells : b.B;
-    make_keys_kernel<<<(unsigned)((n_thr + 255) / 256), 256, 0, stream>>>(b, 0, want_hist ? kin : nullptr, vin,
-                                                                         want_tgt ? kin2 : nullptr, vin2,
-                                                                         nullptr, nullptr);
-  NAIS_COUNT_LAUNCH(1);
+    int* kin3 = reinterpret_cast<int*>(base + L.keys[6]);
+    uint32_t* vin3 = reinterpret_cast<uint32_t*>(base + L.keys[7]);
+    make_keys_kernel<<<(unsigned)((n_thr + 255) / 256), 256, 0, stream>>>(b, want_reg ? 1 : 0, p.item_num, p.region_num,
+                                                                         want_hist ? kin : nullptr, vin, want_tgt ? kin2 : nullptr,
+                                                                         vin2, kin3, vin3);
+    NAIS_COUNT_LAUNCH(1);
     size_t cb = L.cub_bytes;
-    auto seg = [&](int* ki, uint32_t* vi, int64_t n, int off, int w, SegOut out, int bits) {
+    auto seg = [&](int* ki, uint32_t* vi, int64_t n, int off, int w, int n_rows, SegOut out) {
+      int bits = 1;  // keys are 0 .. n_rows (n_rows = the "drop" key of an out-of-range id)
+      while ((1ll << bits) <= n_rows && bits < 31) ++bits;
       cub::DeviceRadixSort::SortPairs(base + L.cub, cb, ki, kout, vi, vout, (int)n, 0, bits, stream);
       const int64_t nch = (n + SEG_CHUNK - 1) / SEG_CHUNK;
       int* pk = reinterpret_cast<int*>(base + L.pkey);
       int* pst = reinterpret_cast<int*>(base + L.pstart);
       float* pr = reinterpret_cast<float*>(base + L.prows);
       segment_reduce_pass1_kernel<<<(unsigned)((nch * 32 + 255) / 256), 256, 0, stream>>>(kout, vout, n, n_cells, A.ws_dq, A.ws_dp,
-                                                                                        D, off, w, out, pk, pst, pr);
+                                                                                        D, off, w, n_rows, out, pk, pst, pr);
       NAIS_COUNT_LAUNCH(1);
       segment_reduce_pass2_kernel<<<(unsigned)((2 * nch * 32 + 255) / 256), 256, 0, stream>>>(pk, pst, pr, nch, w, out);
       NAIS_COUNT_LAUNCH(1);
     };
-    auto bits_for = [](int n) { int bts = 1; while ((1ll << bts) < n && bts < 31) ++bts; return bts; };
-    if (want_hist) seg(kin, vin, n_cells, 0, br.w_poi, dest(g.hist_poi[bi], br.hist_poi, opt ? opt->sum_hist_poi[bi] : nullptr), bits_for(p.item_num));
-    if (want_tgt) seg(kin2, vin2, b.B, 0, br.w_poi, dest(g.tgt_poi[bi], br.tgt_poi, opt ? opt->sum_tgt_poi[bi] : nullptr), bits_for(p.item_num));
-    if (want_reg) {
-      make_keys_kernel<<<(unsigned)((n_thr + 255) / 256), 256, 0, stream>>>(b, 1, nullptr, nullptr, nullptr, nullptr, kin, vin);
-  NAIS_COUNT_LAUNCH(1);
-      // (history-side and target-side region rows are one table in every variant: hist_reg == tgt_reg)
-      seg(kin, vin, n_cells + b.B, br.w_poi, br.w_reg, dest(g.reg[bi], br.hist_reg, opt ? opt->sum_reg[bi] : nullptr), bits_for(p.region_num));
-    }
+    if (want_hist) seg(kin, vin, n_cells, 0, br.w_poi, p.item_num, dest(g.hist_poi[bi], br.hist_poi, opt ? opt->sum_hist_poi[bi] : nullptr));
+    if (want_tgt) seg(kin2, vin2, b.B, 0, br.w_poi, p.item_num, dest(g.tgt_poi[bi], br.tgt_poi, opt ? opt->sum_tgt_poi[bi] : nullptr));
+    // (history-side and target-side region rows are one table in every variant: hist_reg == tgt_reg)
+    if (want_reg) seg(kin3, vin3, n_cells + b.B, br.w_poi, br.w_reg, p.region_num, dest(g.reg[bi], br.hist_reg, opt ? opt->sum_reg[bi] : nullptr));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }

@@ -20,6 +20,7 @@ struct BwdArgs {
   int part_stride;
   int rows_per_tile;
   int64_t n_items;        // work items (tiles of rows)
+  int* bad;               // the library's bad-index word (nais_common.cuh)
 };
 
 // layout of one CTA's parameter partial: w1 [hid][D+lanes] | b1 [hid] | w2 [hid] | dist_w[4] dist_b[2] km[1] pad[1]

@@ -11,6 +11,10 @@ int launch_fullrank_fp32(const NaisParams& p, const NaisCatalog& cat, const Nais
                          void* ws, size_t ws_bytes, cudaStream_t stream);
 int launch_topk_merge(const unsigned long long* in_keys, const float* in_score, const int32_t* in_id, int n_users,
                       int n_lists, int k, float* out_score, int32_t* out_id, cudaStream_t stream);
+int launch_topk_merge_keys_multi(const unsigned long long* keys, unsigned long long* scratch, int64_t user_stride, int64_t list_stride,
+                                 int n_users, int n_lists, int k, unsigned long long* out_keys, float* out_score, int32_t* out_id,
+                                 cudaStream_t stream);
+int merge_scratch_lists(int n_lists, int k);
 int choose_splits(int n_users, int64_t range);
 // nais_bwd.cu
 size_t pairs_bwd_workspace_bytes(const NaisParams& p, int64_t B, int H);
@@ -24,13 +28,30 @@ int launch_fullrank_tc(const NaisParams& p, const NaisCatalog& cat, const NaisUs
                        int64_t poi_end, int k, int exclude, int precision, float* out_score, int32_t* out_id,
                        float* all_scores, void* ws, size_t ws_bytes, cudaStream_t stream);
 bool tc_supported(const NaisParams& p, int precision);
-// nais_pairs_tc.cu (opt-in: NAIS_PAIRS_TC=1)
-bool pairs_tc_wanted();
+size_t fullrank_tc_plan_bytes(const NaisParams& p, int64_t poi_begin, int64_t poi_end, int precision);
+size_t fullrank_tc_call_workspace_bytes(const NaisParams& p, int n_users, int64_t nnz, int64_t poi_begin, int64_t poi_end, int k,
+                                        int precision);
+int fullrank_tc_prepare(const NaisParams& p, const NaisCatalog& cat, int64_t poi_begin, int64_t poi_end, int precision, void* plan,
+                        size_t plan_bytes, cudaStream_t stream);
+int fullrank_tc_run(const NaisParams& p, const NaisCatalog& cat, const NaisUsers& users, int64_t poi_begin, int64_t poi_end, int k,
+                    int exclude, int precision, const void* plan, size_t plan_bytes, unsigned long long* out_keys, float* out_score,
+                    int32_t* out_id, float* all_scores, void* ws, size_t ws_bytes, cudaStream_t stream);
+// nais_pairs_tc.cu
 bool pairs_tc_supported(const NaisParams& p, const NaisPairs& b);
 int launch_pairs_fwd_tc(const NaisParams& p, const NaisPairs& b, float* score, float* row_sum, float* parts, cudaStream_t stream);
 }  // namespace nais
 
-namespace nais { unsigned long long g_launches = 0; }
+namespace nais {
+unsigned long long g_launches = 0;
+// The one piece of library-owned device state: raised by any kernel that meets an id outside its table (nais_common.cuh
+// checked_id), read and reset by nais_poll_bad_index.  Static device storage: one word per device, nothing is allocated.
+__device__ int g_bad_index = 0;
+int* bad_index_flag() {
+  int* ptr = nullptr;
+  cudaGetSymbolAddress(reinterpret_cast<void**>(&ptr), g_bad_index);
+  return ptr;
+}
+}  // namespace nais
 using namespace nais;
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -51,6 +72,7 @@ static int check_params(const NaisParams* p) {
   if (p->dist_mode == NAIS_DIST_LATLON && (!p->dist_w || !p->dist_b)) return NAIS_ERR_NULL;
   if (p->dist_mode == NAIS_DIST_KM && (!p->dist_embed || p->dist_buckets < 1)) return NAIS_ERR_NULL;
   if (p->dist_mode == NAIS_DIST_KM && p->dist_buckets > 1 && !(p->dist_bucket_km > 0.f)) return NAIS_ERR_MODE;
+  if (p->pairs_precision < NAIS_PAIRS_AUTO || p->pairs_precision > NAIS_PAIRS_TC) return NAIS_ERR_MODE;
   return 0;
 }
 
@@ -64,6 +86,16 @@ static int check_pairs(const NaisParams* p, const NaisPairs* b) {
   if (need_reg && (!b->hreg || !b->treg)) return NAIS_ERR_NULL;
   if (p->dist_mode != NAIS_DIST_NONE && !b->aux) return NAIS_ERR_NULL;
   return 0;
+}
+
+static size_t fp32_workspace_bytes(int n_users, int64_t poi_begin, int64_t poi_end, int k) {
+  const int s = choose_splits(n_users, poi_end - poi_begin);
+  return 1024 + (size_t)n_users * 8 + (s > 1 ? (size_t)n_users * s * k * sizeof(unsigned long long) : 0);
+}
+
+__global__ void pack_keys_kernel(const float* __restrict__ s, const int32_t* __restrict__ id, size_t n, unsigned long long* keys) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) keys[i] = id[i] >= 0 ? make_key(s[i], id[i]) : 0ull;
 }
 
 __global__ void fill_empty_topk_kernel(float* s, int32_t* id, size_t n) {
@@ -150,6 +182,7 @@ const char* nais_strerror(int code) {
     case NAIS_ERR_WORKSPACE: return "nais: workspace too small";
     case NAIS_ERR_MODE: return "nais: unknown mode or unsupported flag combination";
     case NAIS_ERR_ARCH: return "nais: tensor path needs an sm_100 device";
+    case NAIS_ERR_INDEX: return "nais: index out of range in a POI / region id tensor";
     default: break;
   }
   if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
@@ -163,7 +196,10 @@ int nais_pairs_forward(const NaisParams* p, const NaisPairs* batch, float* score
   rc = check_pairs(p, batch);
   if (rc) return rc;
   if (batch->B && !score) return NAIS_ERR_NULL;
-  if (batch->B && pairs_tc_wanted() && pairs_tc_supported(*p, *batch))  // tcgen05 contraction; same outputs within fp32 rounding
+  if (batch->B == 0) return 0;
+  const bool tc_ok = pairs_tc_supported(*p, *batch);
+  if (p->pairs_precision == NAIS_PAIRS_TC && !tc_ok) return NAIS_ERR_SHAPE;
+  if (p->pairs_precision != NAIS_PAIRS_FP32 && tc_ok)  // tcgen05 contraction (fp16 two-term splits): fp32-grade products
     return launch_pairs_fwd_tc(*p, *batch, score, row_sum, score_parts, static_cast<cudaStream_t>(stream));
   return launch_pairs_fwd(*p, *batch, score, row_sum, score_parts, static_cast<cudaStream_t>(stream));
 }
@@ -220,18 +256,114 @@ static int check_fullrank(const NaisParams* p, const NaisCatalog* cat, const Nai
   const bool work = users->n_users > 0 && poi_end > poi_begin;
   if (work && need_reg && (!cat->region || !users->region)) return NAIS_ERR_NULL;
   if (work && p->dist_mode != NAIS_DIST_NONE && (!cat->coords || !users->coords)) return NAIS_ERR_NULL;
-  if (p->dist_mode == NAIS_DIST_KM && precision != NAIS_PREC_FP32) return NAIS_ERR_MODE;  // fused haversine: FP32 path only
-  if (precision < NAIS_PREC_FP32 || precision > NAIS_PREC_TC_AUTO) return NAIS_ERR_MODE;
-  if (precision != NAIS_PREC_FP32 && !tc_supported(*p, precision)) return NAIS_ERR_SHAPE;
+  const int prec = precision & NAIS_PREC_MASK;
+  if (precision & ~(NAIS_PREC_MASK | NAIS_PREC_FLAG_GENERIC)) return NAIS_ERR_MODE;
+  if (prec < NAIS_PREC_FP32 || prec > NAIS_PREC_TC_AUTO) return NAIS_ERR_MODE;
+  if (p->dist_mode == NAIS_DIST_KM && prec != NAIS_PREC_FP32) return NAIS_ERR_MODE;  // fused haversine: FP32 path only
+  if (prec != NAIS_PREC_FP32 && !tc_supported(*p, precision)) return NAIS_ERR_SHAPE;
   return 0;
 }
 
 size_t nais_fullrank_workspace_bytes(const NaisParams* p, int32_t n_users, int64_t nnz, int64_t poi_begin,
                                      int64_t poi_end, int32_t k, int32_t precision) {
   if (check_params(p) || n_users < 0 || poi_end < poi_begin || k < 1) return 0;
-  if (precision != NAIS_PREC_FP32) return fullrank_tc_workspace_bytes(*p, n_users, nnz, poi_begin, poi_end, k, precision);
-  const int s = choose_splits(n_users, poi_end - poi_begin);
-  return 1024 + (size_t)n_users * 8 + (s > 1 ? (size_t)n_users * s * k * sizeof(unsigned long long) : 0);
+  if ((precision & NAIS_PREC_MASK) != NAIS_PREC_FP32) return fullrank_tc_workspace_bytes(*p, n_users, nnz, poi_begin, poi_end, k, precision);
+  return fp32_workspace_bytes(n_users, poi_begin, poi_end, k);
+}
+
+size_t nais_fullrank_plan_bytes(const NaisParams* p, int64_t poi_begin, int64_t poi_end, int32_t precision) {
+  if (check_params(p) || poi_end < poi_begin || (precision & NAIS_PREC_MASK) == NAIS_PREC_FP32) return 0;
+  return fullrank_tc_plan_bytes(*p, poi_begin, poi_end, precision);
+}
+
+size_t nais_fullrank_planned_workspace_bytes(const NaisParams* p, int32_t n_users, int64_t nnz, int64_t poi_begin, int64_t poi_end,
+                                             int32_t k, int32_t precision) {
+  if (check_params(p) || n_users < 0 || poi_end < poi_begin || k < 1) return 0;
+  if ((precision & NAIS_PREC_MASK) != NAIS_PREC_FP32)
+    return fullrank_tc_call_workspace_bytes(*p, n_users, nnz, poi_begin, poi_end, k, precision) + 1024 + (size_t)n_users * 8;
+  return fp32_workspace_bytes(n_users, poi_begin, poi_end, k) + (size_t)n_users * k * 12 + 512;  // + score / id staging for out_keys
+}
+
+int nais_fullrank_prepare(const NaisParams* p, const NaisCatalog* cat, int64_t poi_begin, int64_t poi_end, int32_t precision,
+                          void* plan, size_t plan_bytes, nais_stream_t stream) {
+  NaisUsers none = {};
+  int rc = check_fullrank(p, cat, &none, poi_begin, poi_end, precision);
+  if (rc) return rc;
+  if ((precision & NAIS_PREC_MASK) == NAIS_PREC_FP32 || poi_end == poi_begin) return 0;  // nothing to precompute
+  if (!plan) return NAIS_ERR_NULL;
+  if (!aligned16(plan)) return NAIS_ERR_ALIGN;
+  const NaisBranch& br = p->branch[0];
+  if (br.w_reg > 0 && !cat->region) return NAIS_ERR_NULL;
+  return fullrank_tc_prepare(*p, *cat, poi_begin, poi_end, precision, plan, plan_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int nais_fullrank_topk_planned(const NaisParams* p, const NaisCatalog* cat, const NaisUsers* users, int64_t poi_begin,
+                               int64_t poi_end, int32_t k, int32_t exclude_history, int32_t precision, const void* plan,
+                               size_t plan_bytes, uint64_t* out_keys, float* out_score, int32_t* out_id, void* workspace,
+                               size_t workspace_bytes, nais_stream_t stream) {
+  int rc = check_fullrank(p, cat, users, poi_begin, poi_end, precision);
+  if (rc) return rc;
+  if (k < 1 || k > KCAP) return NAIS_ERR_SHAPE;
+  if (users->n_users == 0) return 0;
+  if ((!out_score) != (!out_id) || (!out_score && !out_keys) || !workspace) return NAIS_ERR_NULL;
+  if (!aligned16(workspace)) return NAIS_ERR_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(out_keys);
+  const size_t n = (size_t)users->n_users * k;
+  if (poi_end == poi_begin) {  // empty shard: every list is padding
+    if (out_score) {
+      fill_empty_topk_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out_score, out_id, n);
+      NAIS_COUNT_LAUNCH(1);
+    }
+    if (keys) {
+      cudaError_t e = cudaMemsetAsync(keys, 0, n * 8, st);
+      if (e != cudaSuccess) return (int)e;
+    }
+    return (int)cudaGetLastError();
+  }
+  if ((precision & NAIS_PREC_MASK) != NAIS_PREC_FP32)
+    return fullrank_tc_run(*p, *cat, *users, poi_begin, poi_end, k, exclude_history, precision, plan, plan_bytes, keys, out_score,
+                           out_id, nullptr, workspace, workspace_bytes, st);
+  // FP32 kernel: no plan.  It writes score / id; keys (if wanted) are re-packed from them.
+  float* sc = out_score;
+  int32_t* id = out_id;
+  char* rest = reinterpret_cast<char*>(workspace);
+  size_t rest_bytes = workspace_bytes;
+  if (!sc) {  // stage score / id at the head of the workspace
+    const size_t head = (n * 8 + 255) & ~size_t(255);
+    if (workspace_bytes < head) return NAIS_ERR_WORKSPACE;
+    sc = reinterpret_cast<float*>(workspace);
+    id = reinterpret_cast<int32_t*>(sc + n);
+    rest += head;
+    rest_bytes -= head;
+  }
+  rc = launch_fullrank_fp32(*p, *cat, *users, poi_begin, poi_end, k, exclude_history, sc, id, nullptr, rest, rest_bytes, st);
+  if (rc || !keys) return rc;
+  pack_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sc, id, n, keys);
+  NAIS_COUNT_LAUNCH(1);
+  return (int)cudaGetLastError();
+}
+
+int nais_topk_merge_keys(const uint64_t* in_keys, int64_t user_stride, int64_t list_stride, int32_t n_users, int32_t n_lists,
+                         int32_t k, uint64_t* out_keys, float* out_score, int32_t* out_id, nais_stream_t stream) {
+  if (n_users < 0 || n_lists < 1 || k < 1 || k > KCAP || user_stride < k || list_stride < k) return NAIS_ERR_SHAPE;
+  if (n_users == 0) return 0;
+  if (!in_keys || (!out_score) != (!out_id) || (!out_score && !out_keys)) return NAIS_ERR_NULL;
+  if (merge_scratch_lists(n_lists, k) != 0) return NAIS_ERR_SHAPE;  // one level: n_lists * k <= 8192 (shards of a node, not tiles)
+  return launch_topk_merge_keys_multi(reinterpret_cast<const unsigned long long*>(in_keys), nullptr, user_stride, list_stride, n_users,
+                                      n_lists, k, reinterpret_cast<unsigned long long*>(out_keys), out_score, out_id,
+                                      static_cast<cudaStream_t>(stream));
+}
+
+int nais_poll_bad_index(int32_t* host_flag, nais_stream_t stream) {
+  if (!host_flag) return NAIS_ERR_NULL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int* flag = bad_index_flag();
+  if (!flag) return (int)cudaGetLastError();
+  cudaError_t e = cudaMemcpyAsync(host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(flag, 0, sizeof(int), st);
+  return (int)e;
 }
 
 int nais_fullrank_topk(const NaisParams* p, const NaisCatalog* cat, const NaisUsers* users, int64_t poi_begin,
@@ -249,7 +381,7 @@ int nais_fullrank_topk(const NaisParams* p, const NaisCatalog* cat, const NaisUs
     NAIS_COUNT_LAUNCH(1);
     return (int)cudaGetLastError();
   }
-  if (precision == NAIS_PREC_FP32)
+  if ((precision & NAIS_PREC_MASK) == NAIS_PREC_FP32)
     return launch_fullrank_fp32(*p, *cat, *users, poi_begin, poi_end, k, exclude_history, out_score, out_id, nullptr,
                                 workspace, workspace_bytes, st);
   return launch_fullrank_tc(*p, *cat, *users, poi_begin, poi_end, k, exclude_history, precision, out_score, out_id,
@@ -270,7 +402,7 @@ int nais_fullrank_scores(const NaisParams* p, const NaisCatalog* cat, const Nais
   int32_t* id = reinterpret_cast<int32_t*>(sc + users->n_users);
   char* rest = reinterpret_cast<char*>(workspace) + head;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (precision == NAIS_PREC_FP32)
+  if ((precision & NAIS_PREC_MASK) == NAIS_PREC_FP32)
     return launch_fullrank_fp32(*p, *cat, *users, poi_begin, poi_end, 1, 0, sc, id, all_scores, rest,
                                 workspace_bytes - head, st);
   return launch_fullrank_tc(*p, *cat, *users, poi_begin, poi_end, 1, 0, precision, sc, id, all_scores, rest,

@@ -11,6 +11,17 @@ namespace nais {
 extern unsigned long long g_launches;
 #define NAIS_COUNT_LAUNCH(n) (__atomic_fetch_add(&::nais::g_launches, (unsigned long long)(n), __ATOMIC_RELAXED))
 
+// Device address (current device) of the library's 4-byte bad-index word (nais_capi.cu); every launcher passes it to its kernel.
+int* bad_index_flag();
+// An id as the kernels use it: inside [0, n) or replaced by 0 with the bad-index word set (include/nais_b200.h,
+// nais_poll_bad_index).  `ok` tells the caller to drop the contribution of this id (backward) instead of crediting row 0.
+__device__ __forceinline__ int checked_id(long long v, int n, int* bad, bool* ok = nullptr) {
+  const bool in = (unsigned long long)v < (unsigned long long)n;
+  if (!in && bad) *bad = 1;
+  if (ok) *ok = in;
+  return in ? (int)v : 0;
+}
+
 constexpr int TC = 128;   // cells (history item x candidate pairs) per tile of the FP32 tile-GEMM
 constexpr int TCP = 132;  // padded cell stride of cell-major smem rows (16B-aligned, breaks bank regularity)
 constexpr int KB = 64;    // hidden units per k-block

@@ -180,6 +180,7 @@ struct PairsFwdArgs {
   float* row_sum;  // [n_branch,B] or NULL
   float* parts;    // [n_branch,B] per-branch score or NULL
   int rows_per_tile;
+  int* bad;        // the library's bad-index word (nais_common.cuh)
 };
 
 constexpr int MAXROWS = 16;  // rows (targets) sharing one 128-cell tile when H is small
@@ -226,9 +227,8 @@ __global__ void __launch_bounds__(NT, 2) pairs_fwd_kernel(const __grid_constant_
     // target vectors
     for (int i = tid; i < nrows * D; i += NT) {
       int r = i / D, d = i - r * D;
-      int64_t t = A.b.tgt[row0 + r];
-      ps[r * Dmax + d] = (d < br.w_poi) ? __ldg(br.tgt_poi + (size_t)t * br.w_poi + d)
-                                        : __ldg(br.tgt_reg + (size_t)A.b.treg[row0 + r] * br.w_reg + (d - br.w_poi));
+      ps[r * Dmax + d] = (d < br.w_poi) ? __ldg(br.tgt_poi + (size_t)checked_id(A.b.tgt[row0 + r], p.item_num, A.bad) * br.w_poi + d)
+                                        : __ldg(br.tgt_reg + (size_t)checked_id(A.b.treg[row0 + r], p.region_num, A.bad) * br.w_reg + (d - br.w_poi));
     }
     if (tid < MAXROWS) {
       row_e[tid] = 0.f;
@@ -254,8 +254,8 @@ __global__ void __launch_bounds__(NT, 2) pairs_fwd_kernel(const __grid_constant_
         const int d0 = half ? (D >> 1) : 0, d1 = half ? D : (D >> 1);
         float ssum = 0.f;
         if (valid) {
-          const int64_t item = A.b.hist[cidx];
-          const int64_t reg = br.w_reg ? A.b.hreg[cidx] : 0;
+          const int item = checked_id(A.b.hist[cidx], p.item_num, A.bad);
+          const int reg = br.w_reg ? checked_id(A.b.hreg[cidx], p.region_num, A.bad) : 0;
           const float* qp = br.hist_poi + (size_t)item * br.w_poi;
           const float* qr = br.hist_reg + (size_t)reg * br.w_reg;
           if (vec4) {  // 128-bit row loads: 4x fewer L1 requests than the scalar walk, same products in the same order
@@ -580,6 +580,7 @@ int launch_pairs_fwd(const NaisParams& p, const NaisPairs& b, float* score, floa
   A.score = score;
   A.row_sum = row_sum;
   A.parts = parts;
+  A.bad = bad_index_flag();
   int rpt = (b.H <= TC) ? TC / b.H : 1;
   if (rpt > MAXROWS) rpt = MAXROWS;
   A.rows_per_tile = rpt;
@@ -626,21 +627,29 @@ int launch_topk_merge(const unsigned long long* in_keys, const float* in_score, 
 }
 
 
-// Keys -> keys (or final score/id) merge of blocks of `lpb` lists; grid (users, blocks): users on grid.x (no 65 535 limit).
-__global__ void topk_merge_keys_kernel(const unsigned long long* __restrict__ in, int n_lists, int k, int lpb, int n2,
-                                       unsigned long long* out_keys, float* out_score, int32_t* out_id) {
+// Keys -> keys (and / or final score, id) merge of blocks of `lpb` lists; grid (users, blocks): users on grid.x (no 65 535
+// limit).  List l of user u starts at in + u * user_stride + l * list_stride (8-byte words).
+__global__ void topk_merge_keys_kernel(const unsigned long long* __restrict__ in, long long user_stride, long long list_stride,
+                                       int n_lists, int k, int lpb, int n2, unsigned long long* out_keys, int final_level,
+                                       float* out_score, int32_t* out_id) {
   extern __shared__ __align__(16) unsigned long long mk[];
   const int u = blockIdx.x, b = blockIdx.y;
   const int l0 = b * lpb, l1 = min(n_lists, l0 + lpb);
   const int n = (l1 - l0) * k;
-  const unsigned long long* src = in + ((size_t)u * n_lists + l0) * k;
-  for (int i = threadIdx.x; i < n2; i += blockDim.x) mk[i] = i < n ? src[i] : 0ull;
+  const unsigned long long* src = in + (size_t)u * user_stride;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    unsigned long long v = 0ull;
+    if (i < n) {
+      const int l = i / k;
+      v = src[(size_t)(l0 + l) * list_stride + (i - l * k)];
+    }
+    mk[i] = v;
+  }
   __syncthreads();
   bitonic_sort_desc(mk, n2);
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
-    if (out_keys) {
-      out_keys[((size_t)u * gridDim.y + b) * k + i] = mk[i];
-    } else {
+    if (out_keys) out_keys[((size_t)u * gridDim.y + b) * k + i] = mk[i];
+    if (final_level && out_score) {
       float sc;
       int id;
       split_key(mk[i], sc, id);
@@ -650,32 +659,52 @@ __global__ void topk_merge_keys_kernel(const unsigned long long* __restrict__ in
   }
 }
 
-// Hierarchical merge of [n_users][n_lists][k] keys (ping-pong between `keys` and `scratch`).
-int launch_topk_merge_keys_multi(unsigned long long* keys, unsigned long long* scratch, int n_users, int n_lists, int k,
-                                 float* out_score, int32_t* out_id, cudaStream_t stream) {
+// Hierarchical merge of n_lists key lists per user: a level merges blocks of lpb = min(256, 8192 / k) lists; intermediate
+// levels write to `scratch` one after the other (merge_scratch_lists(n_lists, k) lists per user in total; NULL is fine when
+// one level suffices).  The last level writes out_keys and / or score + id.
+int merge_scratch_lists(int n_lists, int k) {
+  int lpb = 8192 / k;
+  lpb = lpb > 256 ? 256 : (lpb < 2 ? 2 : lpb);
+  int total = 0;
+  while (n_lists > lpb) {
+    n_lists = (n_lists + lpb - 1) / lpb;
+    total += n_lists;
+  }
+  return total;
+}
+int launch_topk_merge_keys_multi(const unsigned long long* keys, unsigned long long* scratch, int64_t user_stride, int64_t list_stride,
+                                 int n_users, int n_lists, int k, unsigned long long* out_keys, float* out_score, int32_t* out_id,
+                                 cudaStream_t stream) {
   if (n_users == 0) return 0;
   cudaError_t e = cudaFuncSetAttribute(topk_merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8);
   if (e != cudaSuccess) return (int)e;
-  unsigned long long *src = keys, *dst = scratch;
+  const unsigned long long* src = keys;
+  unsigned long long* dst = scratch;
   while (true) {
     int lpb = 8192 / k;
-    if (lpb > 64) lpb = 64;
+    if (lpb > 256) lpb = 256;
+    if (lpb < 2) lpb = 2;
     if (lpb > n_lists) lpb = n_lists;
     const int blocks = (n_lists + lpb - 1) / lpb;
     int n2 = 1;
     while (n2 < lpb * k) n2 <<= 1;
+    if (n2 > 8192) return NAIS_ERR_SHAPE;
     const bool last = blocks == 1;
+    if (!last && !dst) return NAIS_ERR_WORKSPACE;
     dim3 grid(n_users, blocks);
     const int threads = n2 >= 1024 ? 512 : (n2 < 64 ? 64 : n2 / 2);
-    topk_merge_keys_kernel<<<grid, threads, (size_t)n2 * 8, stream>>>(src, n_lists, k, lpb, n2, last ? nullptr : dst, out_score, out_id);
+    topk_merge_keys_kernel<<<grid, threads, (size_t)n2 * 8, stream>>>(src, user_stride, list_stride, n_lists, k, lpb, n2,
+                                                                      last ? out_keys : dst, last ? 1 : 0, out_score, out_id);
     NAIS_COUNT_LAUNCH(1);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     if (last) return 0;
+    // next level: [u][blocks][k] contiguous in dst; its output goes behind it
     n_lists = blocks;
-    unsigned long long* t = src;
+    user_stride = (int64_t)blocks * k;
+    list_stride = k;
     src = dst;
-    dst = t;
+    dst = dst + (size_t)n_users * blocks * k;
   }
 }
 

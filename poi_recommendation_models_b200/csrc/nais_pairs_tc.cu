@@ -1,5 +1,6 @@
-// Pair forward (model.py:246-297) with the attention-MLP contraction on tcgen05 — opt-in (NAIS_PAIRS_TC=1), one branch,
-// D <= 64, hid <= 128, lat/lon or no distance mode, no dropout; everything else stays on the FP32 kernel (nais_fp32.cu).
+// Pair forward (model.py:246-297) with the attention-MLP contraction on tcgen05 — the default of nais_pairs_forward
+// (NaisParams::pairs_precision = NAIS_PAIRS_AUTO) for one branch, D in {16, 32, 48, 64}, hid <= 128 (multiple of 16), lat/lon or
+// no distance mode, no dropout; everything else runs the FP32 kernel (nais_fp32.cu).
 //
 // A training row has its own history, so unlike full-rank scoring there is no per-user operand to reuse: the GEMM is
 //     T[cell, k] = sum_d X[cell, d] * W[k, d],      X[cell, :] = q_cell (.) p_row       (M = 128 cells, N = hid, K = D)
@@ -31,6 +32,7 @@ struct Args {
   float* parts;    // [B] or NULL
   int rows_per_tile;
   uint32_t tmem_cols;
+  int* bad;  // the library's bad-index word (nais_common.cuh)
 };
 
 __device__ __forceinline__ float pow2_scale(float amax, int target_exp) {
@@ -116,8 +118,8 @@ __global__ void __launch_bounds__(PT, (D > 48) ? 3 : 4) pairs_fwd_tc_kernel(cons
     const int nrows = (int)min((int64_t)A.rows_per_tile, A.b.B - row0);
     for (int i = tid; i < nrows * D; i += PT) {
       const int r = i / D, d = i - r * D;
-      ps[r * D + d] = (d < br.w_poi) ? __ldg(br.tgt_poi + (size_t)A.b.tgt[row0 + r] * br.w_poi + d)
-                                     : __ldg(br.tgt_reg + (size_t)A.b.treg[row0 + r] * br.w_reg + (d - br.w_poi));
+      ps[r * D + d] = (d < br.w_poi) ? __ldg(br.tgt_poi + (size_t)checked_id(A.b.tgt[row0 + r], p.item_num, A.bad) * br.w_poi + d)
+                                     : __ldg(br.tgt_reg + (size_t)checked_id(A.b.treg[row0 + r], p.region_num, A.bad) * br.w_reg + (d - br.w_poi));
     }
     if (tid < PMAXROWS) {
       row_e[tid] = 0.f;
@@ -143,8 +145,8 @@ __global__ void __launch_bounds__(PT, (D > 48) ? 3 : 4) pairs_fwd_tc_kernel(cons
       bool live = false;  // valid and not masked (history item != target)
       int it32 = 0, rg32 = 0;  // POI / region id of this cell (ids fit int32: item_num is int32); row 0 for padding cells
       if (valid) {
-        it32 = (int)A.b.hist[cidx];
-        rg32 = br.w_reg ? (int)A.b.hreg[cidx] : 0;
+        it32 = checked_id(A.b.hist[cidx], p.item_num, A.bad);
+        rg32 = br.w_reg ? checked_id(A.b.hreg[cidx], p.region_num, A.bad) : 0;
       }
       if (vec4) {
         // Warp-cooperative gather: consecutive lanes read consecutive 16 B of the SAME table row, so one request covers whole
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(PT, (D > 48) ? 3 : 4) pairs_fwd_tc_kernel(cons
           g0 = sigmoidf_exact(fmaf(l1, __ldg(p.dist_w + 1), fmaf(l0, __ldg(p.dist_w + 0), __ldg(p.dist_b + 0))));
           g1 = sigmoidf_exact(fmaf(l1, __ldg(p.dist_w + 3), fmaf(l0, __ldg(p.dist_w + 2), __ldg(p.dist_b + 1))));
         }
-        live = (int64_t)it32 != A.b.tgt[row0 + r];
+        live = A.b.hist[cidx] != A.b.tgt[row0 + r];
       } else {
 #pragma unroll
         for (int d = 0; d < D; ++d) x[d] = 0.f;
@@ -331,11 +333,6 @@ static int launch(const Args& A, int hid, int64_t n_items, int sms, cudaStream_t
 
 }  // namespace ptc
 
-bool pairs_tc_wanted() {
-  const char* v = getenv("NAIS_PAIRS_TC");
-  return v && v[0] && v[0] != '0';
-}
-
 bool pairs_tc_supported(const NaisParams& p, const NaisPairs& b) {
   if (p.n_branch != 1 || b.B < 1) return false;
   const int D = p.branch[0].w_poi + p.branch[0].w_reg;
@@ -357,6 +354,7 @@ int launch_pairs_fwd_tc(const NaisParams& p, const NaisPairs& b, float* score, f
   A.score = score;
   A.row_sum = row_sum;
   A.parts = parts;
+  A.bad = bad_index_flag();
   int rpt = (b.H <= ptc::PT) ? ptc::PT / b.H : 1;
   if (rpt > ptc::PMAXROWS) rpt = ptc::PMAXROWS;
   A.rows_per_tile = rpt;

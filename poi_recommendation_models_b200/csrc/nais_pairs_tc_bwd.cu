@@ -1,5 +1,6 @@
-// Backward of the pair scorer with all three contractions on tcgen05 — opt-in (NAIS_PAIRS_TC_BWD=1), one branch,
-// hidden_size = 64, D in {32, 64}, lat/lon or no distance mode, no dropout; everything else stays on the FP32 kernel (nais_bwd.cu).
+// Backward of the pair scorer with all three contractions on tcgen05 — the default of nais_pairs_backward[_adagrad]
+// (NaisParams::pairs_precision = NAIS_PAIRS_AUTO) for one branch, hidden_size = 64, D in {32, 64}, lat/lon or no distance mode,
+// no dropout, 16-byte aligned table rows; everything else runs the FP32 kernel (nais_bwd.cu).
 // It writes the SAME workspace as pairs_bwd_kernel (dq rows, dp rows, one parameter partial per CTA), so the deterministic
 // param_reduce and the sorted-segment embedding reduce that follow are shared.
 //
@@ -142,8 +143,8 @@ __global__ void __launch_bounds__(PT, 2) pairs_bwd_tc_kernel(const __grid_consta
     const int nrows = (int)min((int64_t)A.rows_per_tile, A.b.B - row0);
     for (int i = tid; i < nrows * D; i += PT) {
       const int r = i / D, d = i - r * D;
-      ps[i] = (d < br.w_poi) ? __ldg(br.tgt_poi + (size_t)A.b.tgt[row0 + r] * br.w_poi + d)
-                             : __ldg(br.tgt_reg + (size_t)A.b.treg[row0 + r] * br.w_reg + (d - br.w_poi));
+      ps[i] = (d < br.w_poi) ? __ldg(br.tgt_poi + (size_t)checked_id(A.b.tgt[row0 + r], p.item_num, A.bad) * br.w_poi + d)
+                             : __ldg(br.tgt_reg + (size_t)checked_id(A.b.treg[row0 + r], p.region_num, A.bad) * br.w_reg + (d - br.w_poi));
       dpacc[i] = 0.f;
     }
     if (tid < nrows) {
@@ -171,13 +172,13 @@ __global__ void __launch_bounds__(PT, 2) pairs_bwd_tc_kernel(const __grid_consta
       float l0r = 0.f, l1r = 0.f;
       bool live = false;
       if (valid) {
-        it32 = (int)A.b.hist[cidx];
-        rg32 = br.w_reg ? (int)A.b.hreg[cidx] : 0;
+        it32 = checked_id(A.b.hist[cidx], p.item_num, A.bad);
+        rg32 = br.w_reg ? checked_id(A.b.hreg[cidx], p.region_num, A.bad) : 0;
         if (lanes) {
           l0r = A.b.aux[cidx * 2];
           l1r = A.b.aux[cidx * 2 + 1];
         }
-        live = (int64_t)it32 != A.b.tgt[row0 + r];
+        live = A.b.hist[cidx] != A.b.tgt[row0 + r];
       }
       float g0 = 0.f, g1 = 0.f;
       if (valid && lanes) {
@@ -434,11 +435,6 @@ static int launch(const BwdArgs& A, int grid, cudaStream_t stream) {
 }
 
 }  // namespace ptcb
-
-bool pairs_tc_bwd_wanted() {
-  const char* v = getenv("NAIS_PAIRS_TC_BWD");
-  return v && v[0] && v[0] != '0';
-}
 
 bool pairs_tc_bwd_supported(const NaisParams& p, const NaisPairs& b) {
   if (p.n_branch != 1 || b.B < 1 || p.hid != ptcb::HID) return false;

@@ -55,7 +55,6 @@ constexpr int HMETA = 512;      // history items whose id/coords are staged in s
 struct Geo {
   int D, hid, lanes, split;
   int mix;       // NAIS_PREC_TC_MIX: lo section of A tiles / B chunks = e5m2(hi) | e5m2(lo) byte planes, two ext k-chunks
-  int ts;        // MIX at D = hid = 64: the TMEM-A kernel (fullrank_ts_kernel) runs; its ext k-chunks use another K-slot order
   int kx;        // D / 8 x k-chunks
   int hch;       // history items per chunk / MMA step: 2 (hid <= 64) or 1 (hid 96, 128: a cell's hidden columns are split
                  // between the two warps of a lane quarter and their partial sums exchanged through shared memory)
@@ -122,7 +121,6 @@ __host__ inline bool make_geo(const NaisParams& p, int precision, Geo& g) {
   g.tpc = g.kp == 1 ? TPC : 2;  // compile-time constant per kernel instantiation (kSinglePart)
   g.smem_bytes = g.tpc * g.a_tile + g.stages * g.stage_bytes + NBUF * 2 * TM * 16 + 4096 + SORTN * 8 + 3 * HMETA * 4 + 4 * TM * 4 + 256 + 128 +
                  (g.kp == 1 ? 9 * TPC * TM * 4 : 0);  // D <= 64 has room for a private `comb`; D > 64 aliases it on A_ext + zero
-  g.ts = g.mix && g.D == 64 && g.hid == 64 && g.kp == 1 && g.hch == 2 && g.nrow == 144 && getenv("NAIS_TC_TMEM_A") != nullptr;  // opt-in: see DESIGN.md §3
   return g.smem_bytes <= 227 * 1024;
 }
 
@@ -148,7 +146,6 @@ __device__ __forceinline__ bool user_in_pass(int gate, int use_mix, int H) {
 // workspace header: [0,64) maxes (uint bits) | [64,128) Scales | perm[128] int | ck[128] float | u[128] float
 constexpr int HDR_BYTES = 4096;
 constexpr int HDR_PERM = 128, HDR_CK = HDR_PERM + 128 * 4, HDR_U = HDR_CK + 128 * 4;
-constexpr int HDR_ROUND = 3072;  // two item counters (MIX pass, SPLIT pass) of the round barrier; the header is zeroed per call
 
 __global__ void absmax_kernel(const float* __restrict__ x, size_t n, unsigned* out) {
   float m = 0.f;
@@ -258,10 +255,9 @@ __device__ __forceinline__ uint2 pack_e5m2(const __half* h) {
 
 // Candidate tiles: image [tile][plane hi|lo][k-chunk][row][8 x fp16] of p_j * sA.  One thread = (row, k-chunk).
 __global__ void pack_candidates_kernel(NaisParams p, NaisCatalog cat, int64_t poi_begin, int64_t poi_end, Geo g,
-                                       const unsigned char* hdr, unsigned char* Pimg, int gate) {
+                                       const unsigned char* hdr, unsigned char* Pimg) {
   const NaisBranch& br = p.branch[0];
   const Scales* sc = reinterpret_cast<const Scales*>(hdr + 64);
-  if (gate == 1 && !sc->use_mix) return;  // NAIS_PREC_TC_AUTO: no user takes the MIX pass
   const float sA = sc->sA;
   const int tile = blockIdx.x;
   for (int i = threadIdx.x; i < TM * g.kx; i += blockDim.x) {
@@ -297,8 +293,11 @@ __device__ __forceinline__ int64_t chunk_base(const int64_t* offsets, int u, int
 }
 
 // User operand: grid (user, chunk slot) — users ride grid.x, which has no 65 535 limit.  One thread = (row n, k-chunk c) -> 8 fp16 (hi) + 8 fp16 (lo).
-__global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g, const unsigned char* hdr, unsigned char* Bimg,
-                                  int64_t max_chunks, int gate) {
+// NAIS_PREC_TC_AUTO (two_pass): every user is packed in the image format of the pass that scores it — `g` (MIX geometry) for
+// the users of pass 1, `gs` (SPLIT geometry, same image sizes) for those of pass 0 — and pass_flags[pass] is raised so a pass
+// without users exits at once.  Otherwise everybody takes `g`.
+__global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g_mix, Geo g_split, int two_pass, const unsigned char* hdr,
+                                  unsigned char* Bimg, int64_t max_chunks, int* pass_flags, int* bad) {
   const NaisBranch& br = p.branch[0];
   const Scales* sc = reinterpret_cast<const Scales*>(hdr + 64);
   const int* perm = reinterpret_cast<const int*>(hdr + HDR_PERM);
@@ -307,7 +306,12 @@ __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g, const un
   const int u = blockIdx.x;
   const int64_t hb = users.offsets[u];
   const int H = (int)(users.offsets[u + 1] - hb);
-  if (!user_in_pass(gate, sc->use_mix, H)) return;  // the other pass of NAIS_PREC_TC_AUTO packs (and scores) this user
+  int pass = 1;
+  if (two_pass) {
+    pass = user_in_pass(1, sc->use_mix, H) ? 1 : 0;
+    if (threadIdx.x == 0 && blockIdx.y == 0) pass_flags[pass] = 1;  // (benign race: every writer stores 1)
+  }
+  const Geo& g = pass ? g_mix : g_split;
   const int hch = g.hch, aux0 = g.aux0;
   const int nchunks = (H + hch - 1) / hch;
   const int D = g.D, hid = g.hid, ldw = D + g.lanes;
@@ -319,8 +323,8 @@ __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g, const un
       float v = 0.f;
       if (h < H) {
         const int64_t e = hb + h;
-        v = (d < br.w_poi) ? __ldg(br.hist_poi + (size_t)__ldg(users.items + e) * br.w_poi + d)
-                           : __ldg(br.hist_reg + (size_t)__ldg(users.region + e) * br.w_reg + (d - br.w_poi));
+        v = (d < br.w_poi) ? __ldg(br.hist_poi + (size_t)checked_id(__ldg(users.items + e), p.item_num, bad) * br.w_poi + d)
+                           : __ldg(br.hist_reg + (size_t)checked_id(__ldg(users.region + e), p.region_num, bad) * br.w_reg + (d - br.w_poi));
       }
       q[hs][d] = v;
     }
@@ -398,15 +402,7 @@ __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g, const un
         split_f16(w0, h0, l0);
         split_f16(w1, h1, l1);
         split_f16(wb, hb, lb2);
-        if (hs >= 0 && g.ts) {
-          // TMEM-A kernel: A_ext = one 8-half block per history slot, [g_hi g_hi' | g_lo g_lo' | g_hi g_hi' | 1 1] for slot 0
-          // (k-chunk e0) and [... | 0 0] for slot 1 (k-chunk e1); the shared (1, 1) pair sits at e0[6], e0[7]
-          __half* eb = hs == 0 ? e0 : e1;
-          eb[0] = h0, eb[1] = h1;   // x g_hi
-          eb[2] = h0, eb[3] = h1;   // x g_lo
-          eb[4] = l0, eb[5] = l1;   // x g_hi
-          e0[6] = hb, e0[7] = lb2;  // x (1, 1)
-        } else if (hs >= 0) {
+        if (hs >= 0) {
           e0[2 * hs] = h0;
           e0[2 * hs + 1] = h1;
           e0[4] = hb;
@@ -456,7 +452,8 @@ struct MainArgs {
   unsigned long long* part_keys;  // [n_users, groups, k]
   float* all_scores;              // optional [n_users, range]
   int64_t max_chunks;             // chunk slots the operand image holds (users beyond it are truncated, never read out of bounds)
-  int gate;                       // -1: always run; 0 / 1: run only if Scales::use_mix has this value (NAIS_PREC_TC_AUTO)
+  int gate;                       // -1: one pass scores every user; 0 / 1: the SPLIT / MIX pass of NAIS_PREC_TC_AUTO
+  const int* pass_flags;          // [2] raised by pack_users_kernel for every pass that has users (gate >= 0)
 };
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
@@ -525,7 +522,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const Scales sc = *reinterpret_cast<const Scales*>(A.hdr + 64);
-  if (A.gate == 1 && !sc.use_mix) return;  // NAIS_PREC_TC_AUTO, no user takes the MIX pass: whole grid, before any barrier
+  if (A.gate >= 0 && !A.pass_flags[A.gate]) return;  // NAIS_PREC_TC_AUTO, no user takes this pass: whole grid, before any barrier
 
   // ---- one-time setup ---------------------------------------------------------------------------------------------
   // A_ext (3 x hi|lo planes) and the zero region: everything 0 except column 4 of each hi plane = 1.0 * sAe (bias lane)
@@ -1198,457 +1195,6 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
 }
 
 
-// =====================================================================================================================
-// TMEM-A kernel (D = hid = 64, MIX precision): every A operand lives in TENSOR MEMORY.
-//
-// ncu on the smem-operand kernel above: the shared-memory port is the limiter — per step 9 MMAs x (4 KB of A + 4.6 KB of B)
-// = 612 clk at 128 B/clk, + 108 clk of bulk-copy writes (B chunks) + 105 LSU wavefronts (A_ext stores, 4-way bank
-// conflicted) = 825 clk against 649 clk of MMA math, measured 850.  A is the same for all 64 chunks of an item, so it does
-// not belong in the operand stream at all: here the epilogue warps move the item's three candidate tiles into TMEM once
-// (the producer warp prefetches the packed tile image into a shared-memory staging area during the previous item; its
-// 16-byte column groups are exactly 4 TMEM columns: LDS.128 -> tcgen05.st, lane = candidate row), write the per-step A_ext columns with
-// tcgen05.st as well (no shared-memory stores, no proxy fence), and the MMAs take A from TMEM (tcgen05.mma [d], [a], b_desc).
-// Shared memory then only streams B: 9 x 36 + 108 = 432 clk per step, under the MMA math.  The 96 KB the A tiles
-// occupied become two more B stages.  (tests/umma_probe_ts.cu: layout + 72 clk per MMA.)
-//
-// TMEM columns: [0,288) two accumulators x 144 | [288,480) three A tiles x (32 fp16-pair + 16 e5m2(hi) + 16 e5m2(lo) columns)
-//               | [480,496) two A_ext buffers x 8.
-// Two accumulators, so the epilogue group of a step is its parity (group g drains accumulator g and refills A_ext buffer
-// g for ITS next step); partial sums are still keyed by chunk parity (q = (g + n0 + t) & 1) and combined in that order,
-// which keeps results bit-identical between sharded / sliced / whole runs.
-namespace ts {
-constexpr int STAGES = 2;
-constexpr int NROW = 144;
-constexpr int BCHUNK = 2 * 9 * NROW * 16;  // 41 472 B: hi plane 10 k-chunks + e5m2(hi) 4 + e5m2(lo) 4
-constexpr int COL_A = 288, COL_EXT = 480, A_COLS = 64;
-constexpr int ATILE = 2 * 8 * TM * 16;       // 32 KB: the MIX candidate-tile image of pack_candidates_kernel, [16 column groups][128 rows][16 B]
-constexpr int SMEM_BYTES = STAGES * BCHUNK + TPC * ATILE + SORTN * 8 + 4 * 3 * TPC * TM * 4 + 3 * HMETA * 4 + 64 + 256 + 64;
-}  // namespace ts
-
-// 19 warps: 16 epilogue, warp 16 / warp 18 = MMA issuers of the even / odd steps (= accumulator 0 / 1), warp 17 = producer.
-// With two accumulators the hand-back of accumulator g and the issue of its next step must fit inside the OTHER
-// accumulator's MMA time; an issuer per accumulator sits on its barriers and starts the moment they open, instead of first
-// finishing the other step's 9 MMAs.
-constexpr int TS_THREADS = THREADS + 32;
-__global__ void __launch_bounds__(TS_THREADS, 1) fullrank_ts_kernel(const __grid_constant__ MainArgs A) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  const Geo& g = A.g;
-  unsigned char* sB = smem;
-  unsigned char* sA = sB + ts::STAGES * ts::BCHUNK;                                                  // staged tile images of the NEXT item
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(sA + TPC * ts::ATILE);           // [SORTN]
-  float* comb = reinterpret_cast<float*>(keys + SORTN);                                            // [4 parts][3 arrays][TPC][TM]
-  int* hm_id = reinterpret_cast<int*>(comb + 4 * 3 * TPC * TM);
-  float* hm_la = reinterpret_cast<float*>(hm_id + HMETA);
-  float* hm_lo = hm_la + HMETA;
-  float* sgn_mixed = hm_lo + HMETA;                                                                // [16]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sgn_mixed + 16);
-  uint64_t* b_full = bars;                       // [STAGES]
-  uint64_t* b_empty = bars + ts::STAGES;         // [STAGES]
-  uint64_t* e_full = bars + 2 * ts::STAGES;      // [2]  A_ext written (8 warps of the group)
-  uint64_t* acc_full = e_full + 2;               // [2]  MMAs of a step complete
-  uint64_t* acc_empty = acc_full + 2;            // [2]  accumulator in registers (8 warps)
-  uint64_t* a_ready = acc_empty + 2;             // A tiles of the item are in TMEM (16 warps)
-  uint64_t* a_free = a_ready + 1;                // every MMA of the item has completed
-  uint64_t* sa_full = a_free + 1;                // staged tile images landed (bulk copy)
-  uint64_t* sa_empty = sa_full + 1;              // ... and were moved to TMEM (16 warps)
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(sa_empty + 1);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const Scales sc = *reinterpret_cast<const Scales*>(A.hdr + 64);
-  if (A.gate == 1 && !sc.use_mix) return;
-
-  if (tid < 16) sgn_mixed[tid] = ((sc.npos & ~15) + tid < sc.npos) ? 1.f : -1.f;
-  if (tid == 0) {
-    for (int i = 0; i < ts::STAGES; ++i) {
-      mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 2);  // both issuers commit: every chunk's 3 steps include both parities
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&e_full[i], ARRIVE_WARPS);
-      mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], ARRIVE_WARPS);
-    }
-    mbar_init(a_ready, EPI_WARPS);
-    mbar_init(a_free, 2);
-    mbar_init(sa_full, 1);
-    mbar_init(sa_empty, EPI_WARPS);
-    fence_barrier_init();
-  }
-  if (warp == EPI_WARPS) tmem_alloc(tslot, 512);
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tslot;
-  const int64_t cb0 = chunk_base(A.users.offsets, 0, 2);
-  auto in_pass = [&](int u) { return user_in_pass(A.gate, sc.use_mix, (int)(A.users.offsets[u + 1] - A.users.offsets[u])); };
-
-  if (warp == EPI_WARPS + 1) {
-    // =================================================== bulk-copy producer ========================================
-    uint32_t bstep = 0, it_n = 0;
-    const uint64_t pol = l2_policy_evict_last();
-    for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x) {
-      const int u = (int)(item / A.groups), grp = (int)(item % A.groups);
-      if (!in_pass(u)) continue;
-      const uint32_t it = it_n++;
-      mbar_wait(sa_empty, (it & 1u) ^ 1u);  // the staging area was drained at the start of the previous item: this prefetches
-      if (elect_one()) {
-        mbar_expect_tx(sa_full, (uint32_t)(TPC * ts::ATILE));
-        for (int t = 0; t < TPC; ++t)
-          bulk_g2s_hint(sA + (size_t)t * ts::ATILE, A.Pimg + ((size_t)grp * TPC + t) * ts::ATILE, (uint32_t)ts::ATILE, sa_full, pol);
-      }
-      __syncwarp();
-      const int64_t cbu = __shfl_sync(0xffffffffu, chunk_base(A.users.offsets, u, 2) - cb0, 0);
-      const int nchunks = __shfl_sync(0xffffffffu, user_chunks(A.users.offsets, u, 2, cb0, A.max_chunks), 0);
-      const unsigned char* src = A.Bimg + (size_t)cbu * ts::BCHUNK;
-      for (int c = 0; c < nchunks; ++c, ++bstep) {
-        const uint32_t st = bstep % ts::STAGES;
-        mbar_wait(&b_empty[st], ((bstep / ts::STAGES) & 1) ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(&b_full[st], (uint32_t)ts::BCHUNK);
-          bulk_g2s_hint(sB + (size_t)st * ts::BCHUNK, src + (size_t)c * ts::BCHUNK, (uint32_t)ts::BCHUNK, &b_full[st], pol);
-        }
-        __syncwarp();
-      }
-    }
-  } else if (warp == EPI_WARPS || warp == EPI_WARPS + 2) {
-    // =================================================== MMA issuers (one per accumulator) ==========================
-    const uint32_t par = warp == EPI_WARPS ? 0u : 1u;
-    constexpr uint32_t kBLbo = ts::NROW * 16, kBStep = (2 * kBLbo) >> 4, kStage = ts::BCHUNK >> 4;
-    constexpr uint32_t idN = idesc_f16(TM, ts::NROW), idN8 = idesc_e5m2(TM, ts::NROW);
-    constexpr uint32_t b8h = (10 * kBLbo) >> 4, b8l = (14 * kBLbo) >> 4;  // e5m2(hi) / e5m2(lo) planes of a chunk
-    const uint32_t hi_word = (uint32_t)(smem_desc(0, 0, 128) >> 32);
-    auto mk = [&](uint32_t lo) { return ((uint64_t)hi_word << 32) | lo; };
-    const uint32_t sb0 = smem_u32(sB);
-    const uint32_t B_hi = ((sb0 >> 4) & 0x3FFFu) | (((kBLbo >> 4) & 0x3FFFu) << 16);
-    uint32_t it_n = 0, n = 0, bstep = 0;
-    for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x) {
-      const int u = (int)(item / A.groups);
-      if (!in_pass(u)) continue;
-      const uint32_t it = it_n++;
-      const int nchunks = __shfl_sync(0xffffffffu, user_chunks(A.users.offsets, u, 2, cb0, A.max_chunks), 0);
-      mbar_wait(a_ready, it & 1);
-      tc_fence_after();
-      for (int c = 0; c < nchunks; ++c, ++bstep) {
-        const uint32_t st = bstep % ts::STAGES;
-        mbar_wait(&b_full[st], (bstep / ts::STAGES) & 1);
-        const uint32_t bh = B_hi + st * kStage;
-#pragma unroll
-        for (int t = 0; t < TPC; ++t, ++n) {
-          if ((n & 1u) != par) continue;
-          const uint32_t buf = par, use = n >> 1;
-          const uint32_t d_t = tmem + buf * ts::NROW;
-          const uint32_t a_t = tmem + ts::COL_A + t * ts::A_COLS;
-          mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u);
-          mbar_wait(&e_full[buf], use & 1u);
-          tc_fence_after();
-          if (elect_one()) {
-#pragma unroll
-            for (int s2 = 0; s2 < 4; ++s2) mma_f16_ts(d_t, a_t + s2 * 8, mk(bh + s2 * kBStep), idN, s2 != 0);
-            mma_f16_ts(d_t, tmem + ts::COL_EXT + buf * 8, mk(bh + 4 * kBStep), idN, 1);  // ext: hi-plane k-chunks 8, 9
-#pragma unroll
-            for (int s8 = 0; s8 < 2; ++s8) mma_f8_ts(d_t, a_t + 32 + s8 * 8, mk(bh + b8l + s8 * kBStep), idN8, 1);
-#pragma unroll
-            for (int s8 = 0; s8 < 2; ++s8) mma_f8_ts(d_t, a_t + 48 + s8 * 8, mk(bh + b8h + s8 * kBStep), idN8, 1);
-            mma_commit(&acc_full[buf]);
-          }
-          __syncwarp();
-        }
-        if (elect_one()) mma_commit(&b_empty[st]);
-        __syncwarp();
-      }
-      if (elect_one()) mma_commit(a_free);
-      __syncwarp();
-    }
-  } else {
-    // =================================================== epilogue warps ============================================
-    const int egrp = warp >> 3, qd = warp & 3, hs = (warp >> 2) & 1;
-    const int r = qd * 32 + lane;
-    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-    const float nl2e = -1.4426950408889634f, dsc = A.p.dist_scale * nl2e;
-    const float w00 = g.lanes ? __ldg(A.p.dist_w + 0) * dsc : 0.f, w01 = g.lanes ? __ldg(A.p.dist_w + 1) * dsc : 0.f;
-    const float w10 = g.lanes ? __ldg(A.p.dist_w + 2) * dsc : 0.f, w11 = g.lanes ? __ldg(A.p.dist_w + 3) * dsc : 0.f;
-    const float bd0s = (g.lanes ? __ldg(A.p.dist_b + 0) * nl2e : 0.f) - log2f(sc.sAe);
-    const float bd1s = (g.lanes ? __ldg(A.p.dist_b + 1) * nl2e : 0.f) - log2f(sc.sAe);
-    const float inv_sAe = 1.f / sc.sAe, c_a2 = sc.inv_sigma * 1.4426950408889634f, beta = A.p.beta;
-    const int nposb = sc.npos >> 4, nposm = sc.npos & 15;
-    // the constant column of an A_ext block: slot hs 0 carries (1, 1) * sAe (pairs with hi / lo of the bias), slot 1 zeros
-    const uint32_t ext_const = hs == 0 ? ((uint32_t)__half_as_ushort(__float2half(sc.sAe)) * 0x10001u) : 0u;
-    const uint32_t t_ext = tmem + lane_addr + ts::COL_EXT + egrp * 8 + hs * 4;
-    const uint32_t t_main = tmem + lane_addr + egrp * ts::NROW + hs * 64, t_aux = tmem + lane_addr + egrp * ts::NROW + 128 + 2 * hs;
-    uint32_t n0 = 0, gph = 0, it_n = 0;
-
-    for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x) {
-      const int u = (int)(item / A.groups), grp = (int)(item % A.groups);
-      const int64_t hb = A.users.offsets[u];
-      const int H = (int)(A.users.offsets[u + 1] - hb);
-      if (!user_in_pass(A.gate, sc.use_mix, H)) {
-        if (tid == 0) atomicAdd(reinterpret_cast<unsigned*>(const_cast<unsigned char*>(A.hdr) + HDR_ROUND) + (A.gate == 0 ? 1 : 0), 1u);
-        continue;
-      }
-      const uint32_t it = it_n++;
-      const int nchunks = user_chunks(A.users.offsets, u, 2, cb0, A.max_chunks);
-      const int nsteps = nchunks * TPC;
-      if (tid == 0) {
-        // Round barrier across the persistent CTAs: CTA b takes items b, b + grid, ... so every CTA is on the same ~1.4 users at
-        // the same time and their operand chunks are fetched from DRAM once and re-read from L2 by the other ~100 CTAs —
-        // but only while the CTAs stay within ~20 us of each other (the stream through L2 is 3.5 TB/s).  All CTAs are
-        // co-resident (grid <= SM count, 1 CTA per SM), so waiting for the others cannot deadlock; items this pass skips
-        // were counted when they were skipped.
-        // (split barrier: a CTA arrives when the step loop of an item ends, below, and waits here, before the next item's
-        // first operand fetches matter, for every item of the earlier rounds; the item epilogue overlaps the wait)
-        unsigned* cnt = reinterpret_cast<unsigned*>(const_cast<unsigned char*>(A.hdr) + HDR_ROUND) + (A.gate == 0 ? 1 : 0);
-        const int64_t before = (item / gridDim.x) * (int64_t)gridDim.x;
-        const unsigned target = (unsigned)(A.n_items < before ? A.n_items : before);
-        unsigned seen;
-        do {
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
-        } while (seen < target);
-      }
-      epi_bar();
-      for (int i = tid; i < H && i < HMETA; i += EPI_THREADS) {
-        hm_id[i] = __ldg(A.users.items + hb + i);
-        hm_la[i] = g.lanes ? __ldg(A.users.coords + 2 * (hb + i)) : 0.f;
-        hm_lo[i] = g.lanes ? __ldg(A.users.coords + 2 * (hb + i) + 1) : 0.f;
-      }
-      float clat[TPC], clon[TPC], sumE[TPC], sumES[TPC];
-      int jt[TPC];
-      bool excl[TPC];
-#pragma unroll
-      for (int t = 0; t < TPC; ++t) {
-        const int64_t j = A.poi_begin + ((int64_t)grp * TPC + t) * TM + r;
-        const bool v = j < A.poi_end;
-        jt[t] = v ? (int)j : -2;
-        clat[t] = (v && g.lanes) ? __ldg(A.cat.coords + 2 * (j - A.cat.row_base)) : 0.f;
-        clon[t] = (v && g.lanes) ? __ldg(A.cat.coords + 2 * (j - A.cat.row_base) + 1) : 0.f;
-        sumE[t] = 0.f;
-        sumES[t] = 0.f;
-        excl[t] = false;
-      }
-      // ---- the item's three candidate tiles: staging area -> TMEM (warp / 4 = tile; the 4th warp of a lane quarter has none) ---
-      mbar_wait(a_free, (it & 1u) ^ 1u);
-      mbar_wait(sa_full, it & 1u);
-      tc_fence_after();
-      {
-        const int ta = warp >> 2;
-        if (ta < TPC) {
-          const unsigned char* src = sA + (size_t)ta * ts::ATILE + (size_t)r * 16;
-          const uint32_t t_a = tmem + lane_addr + ts::COL_A + ta * ts::A_COLS;
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {  // 4 column groups (16 TMEM columns) per store
-            uint32_t c16[16];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 x = *reinterpret_cast<const uint4*>(src + (size_t)(q4 * 4 + i) * TM * 16);
-              c16[4 * i] = x.x, c16[4 * i + 1] = x.y, c16[4 * i + 2] = x.z, c16[4 * i + 3] = x.w;
-            }
-            tmem_st16(t_a + q4 * 16, c16);
-          }
-          tmem_wait_st();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(a_ready);
-          mbar_arrive(sa_empty);
-        }
-      }
-      epi_bar();  // history meta staged
-
-      auto hist_coords = [&](int h, float& la, float& lo) {
-        if (h < HMETA) {
-          la = hm_la[h];
-          lo = hm_lo[h];
-        } else {
-          la = __ldg(A.users.coords + 2 * (hb + h));
-          lo = __ldg(A.users.coords + 2 * (hb + h) + 1);
-        }
-      };
-      // A_ext block of (chunk pc, tile slot) for this thread's (row, history slot): [g_hi | g_lo | g_hi | const] -> 4 TMEM columns
-      auto produce = [&](int pc, float cla, float clo) {
-        const int h = 2 * pc + hs;
-        float g0 = 0.f, g1 = 0.f;
-        if (g.lanes && h < H) {
-          float hla, hlo;
-          hist_coords(h, hla, hlo);
-          const float l0 = fabsf(cla - hla), l1 = fabsf(clo - hlo);
-          const float z0 = fmaf(l1, w01, fmaf(l0, w00, bd0s)), z1 = fmaf(l1, w11, fmaf(l0, w10, bd1s));
-          g0 = rcp_approx(ex2_approx(z0) + inv_sAe);
-          g1 = rcp_approx(ex2_approx(z1) + inv_sAe);
-        }
-        const __half2 hi2 = __floats2half2_rn(g0, g1);
-        const float2 hif = __half22float2(hi2);
-        const __half2 lo2 = __floats2half2_rn(g0 - hif.x, g1 - hif.y);
-        uint32_t col[4];
-        col[0] = *reinterpret_cast<const uint32_t*>(&hi2);
-        col[1] = *reinterpret_cast<const uint32_t*>(&lo2);
-        col[2] = col[0];
-        col[3] = ext_const;
-        tmem_st4(t_ext, col);
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&e_full[egrp]);
-      };
-      // One step of this group: tile T (compile time), chunk c.  `more` / (nc, NT): the group's next step, whose A_ext
-      // block this thread writes once the accumulator has been handed back.
-      auto step = [&](auto T_, int c, bool more, int nc, auto NT_) {
-        constexpr int T = decltype(T_)::value, NT = decltype(NT_)::value;
-        const int h = 2 * c + hs;
-        const bool hvalid = h < H;
-        int hist_id = -1;
-        if (hvalid) hist_id = h < HMETA ? hm_id[h] : __ldg(A.users.items + hb + h);
-        mbar_wait(&acc_full[egrp], gph);
-        gph ^= 1u;
-        tc_fence_after();
-        uint32_t aux[2], va[16], vb[16];
-        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-        auto blk = [&](const uint32_t(&v)[16], int b) {
-          if (b < nposb) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              p0 += fabsf(__uint_as_float(v[i]));
-              p1 += fabsf(__uint_as_float(v[i + 1]));
-              p2 += fabsf(__uint_as_float(v[i + 2]));
-              p3 += fabsf(__uint_as_float(v[i + 3]));
-            }
-          } else if (b > nposb || nposm == 0) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              q0 += fabsf(__uint_as_float(v[i]));
-              q1 += fabsf(__uint_as_float(v[i + 1]));
-              q2 += fabsf(__uint_as_float(v[i + 2]));
-              q3 += fabsf(__uint_as_float(v[i + 3]));
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 sg = *reinterpret_cast<const float4*>(sgn_mixed + i);
-              p0 = fmaf(fabsf(__uint_as_float(v[i])), sg.x, p0);
-              p1 = fmaf(fabsf(__uint_as_float(v[i + 1])), sg.y, p1);
-              p2 = fmaf(fabsf(__uint_as_float(v[i + 2])), sg.z, p2);
-              p3 = fmaf(fabsf(__uint_as_float(v[i + 3])), sg.w, p3);
-            }
-          }
-        };
-        // the issuer waits for two things before this accumulator's next step: the accumulator in registers (first) and
-        // the next A_ext block (right after); the FADD tail of this step overlaps the next MMAs
-        tmem_ld2(t_aux, aux);
-        tmem_ld16(t_main, va);
-        tmem_ld16(t_main + 16, vb);
-        tmem_wait_ld16(va);
-        tmem_wait_ld16(vb);
-        blk(va, 0);
-        tmem_ld16(t_main + 32, va);
-        blk(vb, 1);
-        tmem_ld16(t_main + 48, vb);
-        tmem_wait_ld16(va);
-        tmem_wait_ld16(vb);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[egrp]);
-        if (more) produce(nc, clat[NT], clon[NT]);
-        blk(va, 2);
-        blk(vb, 3);
-        const float asum = ((p0 + p1) + (p2 + p3)) - ((q0 + q1) + (q2 + q3));
-        const float S = __uint_as_float(aux[0]) * sc.inv_s;
-        const float a2 = (__uint_as_float(aux[1]) + asum) * c_a2;
-        const bool same = hist_id == jt[T];
-        const float e = (hvalid && !same) ? ex2_approx(a2) : 0.f;
-        sumE[T] += e;
-        sumES[T] = fmaf(e, S, sumES[T]);
-        excl[T] = excl[T] || (hvalid && same);
-      };
-      // The group owns the local steps ls0, ls0 + 2, ...; (chunk, tile) = (ls / 3, ls % 3) repeats every 3 own steps = 2 chunks:
-      //   ls0 = 0: (c,0) (c,2) (c+1,1) | ...      ls0 = 1: (c,1) (c+1,0) (c+1,2) | ...
-      auto run = [&](auto L0_) {
-        constexpr int L0 = decltype(L0_)::value;
-        using I0 = std::integral_constant<int, L0>;
-        using I1 = std::integral_constant<int, (L0 + 2) % 3>;
-        using I2 = std::integral_constant<int, (L0 + 4) % 3>;
-        constexpr int dc1 = (L0 + 2) / 3, dc2 = (L0 + 4) / 3;
-        if (L0 < nsteps) produce(0, clat[L0], clon[L0]);
-        for (int ls = L0, c = 0; ls < nsteps; ls += 6, c += 2) {
-          step(I0{}, c, ls + 2 < nsteps, c + dc1, I1{});
-          if (ls + 2 >= nsteps) break;
-          step(I1{}, c + dc1, ls + 4 < nsteps, c + dc2, I2{});
-          if (ls + 4 >= nsteps) break;
-          step(I2{}, c + dc2, ls + 6 < nsteps, c + 2, I0{});
-        }
-      };
-      if (((egrp - n0) & 1u) == 0) run(std::integral_constant<int, 0>{});
-      else run(std::integral_constant<int, 1>{});
-      if (tid == 0) atomicAdd(reinterpret_cast<unsigned*>(const_cast<unsigned char*>(A.hdr) + HDR_ROUND) + (A.gate == 0 ? 1 : 0), 1u);
-      // ---- item epilogue: 4 partial states per candidate, keyed by (chunk parity, history slot), combined in key order -----
-#pragma unroll
-      for (int t2 = 0; t2 < TPC; ++t2) {
-        const int part = (int)(((egrp + n0 + t2) & 1u) * 2u) + hs;  // chunk parity this group covered for tile t2
-        comb[(part * 3 + 0) * TPC * TM + t2 * TM + r] = sumE[t2];
-        comb[(part * 3 + 1) * TPC * TM + t2 * TM + r] = sumES[t2];
-        comb[(part * 3 + 2) * TPC * TM + t2 * TM + r] = excl[t2] ? 1.f : 0.f;
-      }
-      n0 += (uint32_t)nsteps;
-      epi_bar();
-      const bool small_k = A.k <= 32;
-      if (warp < 4) {
-        unsigned long long kreg[TPC];
-#pragma unroll
-        for (int t2 = 0; t2 < TPC; ++t2) {
-          float E = 0.f, ES = 0.f;
-          bool ex = false;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            E += comb[(q * 3 + 0) * TPC * TM + t2 * TM + r];
-            ES += comb[(q * 3 + 1) * TPC * TM + t2 * TM + r];
-            ex = ex || comb[(q * 3 + 2) * TPC * TM + t2 * TM + r] != 0.f;
-          }
-          const float score = ES / powf(E, beta);
-          const bool valid = jt[t2] >= 0;
-          if (A.all_scores && valid) A.all_scores[(size_t)u * (A.poi_end - A.poi_begin) + (jt[t2] - A.poi_begin)] = score;
-          kreg[t2] = (valid && !(A.exclude && ex)) ? make_key(score, jt[t2]) : 0ull;
-          if (!small_k) keys[t2 * TM + r] = kreg[t2];
-        }
-        if (small_k) {
-          unsigned long long a = warp_sort_desc(kreg[0], lane);
-          a = warp_fold_top32(a, warp_sort_desc(kreg[1], lane), lane);
-          a = warp_fold_top32(a, warp_sort_desc(kreg[2], lane), lane);
-          keys[r] = a;
-        } else {
-          for (int i = TPC * TM + r; i < SORTN; i += TM) keys[i] = 0ull;
-        }
-      }
-      epi_bar();
-      if (small_k) {
-        if (warp == 0) {
-          unsigned long long a = warp_fold_top32(keys[lane], keys[32 + lane], lane);
-          a = warp_fold_top32(a, warp_fold_top32(keys[64 + lane], keys[96 + lane], lane), lane);
-          if (lane < A.k) A.part_keys[((size_t)u * A.groups + grp) * A.k + lane] = a;
-        }
-        continue;
-      }
-      for (int kk = 2; kk <= SORTN; kk <<= 1) {
-        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-          for (int i = tid; i < SORTN; i += EPI_THREADS) {
-            const int ixj = i ^ jj;
-            if (ixj > i) {
-              const unsigned long long x = keys[i], y = keys[ixj];
-              const bool desc = (i & kk) == 0;
-              if (desc ? (x < y) : (x > y)) {
-                keys[i] = y;
-                keys[ixj] = x;
-              }
-            }
-          }
-          epi_bar();
-        }
-      }
-      for (int i = tid; i < A.k; i += EPI_THREADS) A.part_keys[((size_t)u * A.groups + grp) * A.k + i] = keys[i];
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == EPI_WARPS) tmem_dealloc(tmem, 512);
-}
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1656,87 +1202,103 @@ __global__ void __launch_bounds__(TS_THREADS, 1) fullrank_ts_kernel(const __grid
 // ---------------------------------------------------------------------------------------------------------------------
 int launch_topk_merge(const unsigned long long* in_keys, const float* in_score, const int32_t* in_id, int n_users,
                       int n_lists, int k, float* out_score, int32_t* out_id, cudaStream_t stream);
-int launch_topk_merge_keys_multi(unsigned long long* keys, unsigned long long* scratch, int n_users, int n_lists, int k,
-                                 float* out_score, int32_t* out_id, cudaStream_t stream);
+int launch_topk_merge_keys_multi(const unsigned long long* keys, unsigned long long* scratch, int64_t user_stride, int64_t list_stride,
+                                 int n_users, int n_lists, int k, unsigned long long* out_keys, float* out_score, int32_t* out_id,
+                                 cudaStream_t stream);
+int merge_scratch_lists(int n_lists, int k);
 
 static inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
-struct TcLayout {
-  size_t hdr, pimg, bimg, keys, scratch, total;
+// ---- plan: what depends on the weights and the catalogue range only -----------------------------------------------------------
+//   [header 4 KB: table maxima | Scales | perm | c_k | u_d] [candidate image of the (first) pass] [AUTO: candidate image of the SPLIT pass]
+struct PlanLayout {
+  tc::Geo g, gs;       // geometry of the single pass / of AUTO's MIX pass; gs: AUTO's SPLIT pass
+  bool two_pass;       // NAIS_PREC_TC_AUTO on a shape that has a MIX geometry
   int groups, n_tiles_pad;
-  int64_t max_chunks;
+  size_t hdr, pimg, pimg2, total;
 };
 
-static bool tc_layout(const NaisParams& p, int n_users, int64_t nnz, int64_t poi_begin, int64_t poi_end, int k, int precision,
-                      tc::Geo& g, TcLayout& L) {
-  if (!tc::make_geo(p, precision, g)) return false;
+static bool plan_layout(const NaisParams& p, int64_t poi_begin, int64_t poi_end, int precision, PlanLayout& L) {
+  const int prec = precision & NAIS_PREC_MASK;
+  if (!tc::make_geo(p, prec, L.g)) return false;
+  L.two_pass = false;
+  if (prec == NAIS_PREC_TC_AUTO) {
+    if (!tc::make_geo(p, NAIS_PREC_TC_SPLIT, L.gs)) return false;
+    // make_geo(AUTO) gives the MIX geometry where an e5m2 K-step exists; the two passes then share every size
+    L.two_pass = L.g.mix != 0;
+    if (L.two_pass && (L.gs.a_tile != L.g.a_tile || L.gs.b_chunk != L.g.b_chunk || L.gs.tpc != L.g.tpc || L.gs.hch != L.g.hch)) return false;
+  } else {
+    L.gs = L.g;
+  }
   const int64_t range = poi_end - poi_begin;
   const int64_t tiles = (range + tc::TM - 1) / tc::TM;
-  L.groups = (int)((tiles + g.tpc - 1) / g.tpc);
+  L.groups = (int)((tiles + L.g.tpc - 1) / L.g.tpc);
   if (L.groups < 1) L.groups = 1;
-  L.n_tiles_pad = L.groups * g.tpc;
-  L.max_chunks = (g.hch == 2 ? (nnz + n_users) / 2 : nnz) + 2;
+  L.n_tiles_pad = L.groups * L.g.tpc;
   size_t o = 0;
   L.hdr = o;
   o += tc::HDR_BYTES;
   L.pimg = o;
-  o += al256((size_t)L.n_tiles_pad * g.a_tile);
-  L.bimg = o;
-  o += al256((size_t)L.max_chunks * g.b_chunk);
-  L.keys = o;
-  o += al256((size_t)n_users * L.groups * k * 8);
-  L.scratch = o;
-  o += al256((size_t)n_users * ((L.groups + 63) / 64) * k * 8);
+  o += al256((size_t)L.n_tiles_pad * L.g.a_tile);
+  L.pimg2 = o;
+  if (L.two_pass) o += al256((size_t)L.n_tiles_pad * L.g.a_tile);
   L.total = o;
   return true;
 }
 
+// ---- per-call workspace: [pass flags 256 B] [user operand image: everything that is left] [per-item keys] [merge scratch] -------
+static inline size_t call_keys_bytes(int n_users, int groups, int k) { return al256((size_t)n_users * groups * k * 8); }
+static inline size_t call_scratch_bytes(int n_users, int groups, int k) {
+  return al256((size_t)n_users * merge_scratch_lists(groups, k) * k * 8 + 8);
+}
+
 bool tc_supported(const NaisParams& p, int precision) {
   tc::Geo g;
-  return tc::make_geo(p, precision, g);
+  return tc::make_geo(p, precision & NAIS_PREC_MASK, g);
+}
+
+size_t fullrank_tc_plan_bytes(const NaisParams& p, int64_t poi_begin, int64_t poi_end, int precision) {
+  PlanLayout L;
+  return plan_layout(p, poi_begin, poi_end, precision, L) ? L.total : 0;
+}
+
+size_t fullrank_tc_call_workspace_bytes(const NaisParams& p, int n_users, int64_t nnz, int64_t poi_begin, int64_t poi_end, int k,
+                                        int precision) {
+  PlanLayout L;
+  if (!plan_layout(p, poi_begin, poi_end, precision, L)) return 0;
+  const int64_t max_chunks = (L.g.hch == 2 ? (nnz + n_users) / 2 : nnz) + 2;
+  return 256 + al256((size_t)max_chunks * L.g.b_chunk) + call_keys_bytes(n_users, L.groups, k) + call_scratch_bytes(n_users, L.groups, k);
 }
 
 size_t fullrank_tc_workspace_bytes(const NaisParams& p, int n_users, int64_t nnz, int64_t poi_begin, int64_t poi_end, int k,
                                    int precision) {
-  tc::Geo g;
-  TcLayout L;
-  if (!tc_layout(p, n_users, nnz, poi_begin, poi_end, k, precision, g, L)) return 0;
-  return L.total + 1024 + (size_t)n_users * 8;
+  const size_t a = fullrank_tc_plan_bytes(p, poi_begin, poi_end, precision);
+  const size_t b = fullrank_tc_call_workspace_bytes(p, n_users, nnz, poi_begin, poi_end, k, precision);
+  return (a && b) ? a + b + 1024 + (size_t)n_users * 8 : 0;
 }
 
-int launch_fullrank_tc(const NaisParams& p, const NaisCatalog& cat, const NaisUsers& users, int64_t poi_begin,
-                       int64_t poi_end, int k, int exclude, int precision, float* out_score, int32_t* out_id,
-                       float* all_scores, void* ws, size_t ws_bytes, cudaStream_t stream) {
-  if (users.n_users == 0 || poi_end <= poi_begin) return 0;
+static int check_arch(int& sms) {
   int dev = 0, major = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
   if (major != 10) return NAIS_ERR_ARCH;
-  // nnz is not known to the library (offsets live on the device): the caller sized the workspace with it; recover the
-  // chunk capacity from the workspace size instead.
-  tc::Geo g;
-  if (!tc::make_geo(p, precision, g)) return NAIS_ERR_SHAPE;
-  const int64_t range = poi_end - poi_begin;
-  const int64_t tiles = (range + tc::TM - 1) / tc::TM;
-  const int groups = (int)((tiles + g.tpc - 1) / g.tpc);
-  const int n_tiles_pad = groups * g.tpc;
-  unsigned char* base = reinterpret_cast<unsigned char*>(ws);
-  size_t o = 0;
-  unsigned char* hdr = base + o;
-  o += tc::HDR_BYTES;
-  unsigned char* pimg = base + o;
-  o += al256((size_t)n_tiles_pad * g.a_tile);
-  const size_t keys_bytes = al256((size_t)users.n_users * groups * k * 8);
-  const size_t scratch_bytes = al256((size_t)users.n_users * ((groups + 63) / 64) * k * 8);
-  if (ws_bytes < o + keys_bytes + scratch_bytes + g.b_chunk) return NAIS_ERR_WORKSPACE;
-  const size_t bimg_bytes = (ws_bytes - o - keys_bytes - scratch_bytes) / 256 * 256;
-  unsigned char* bimg = base + o;
-  o += bimg_bytes;
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(base + o);
-  o += keys_bytes;
-  unsigned long long* scratch = reinterpret_cast<unsigned long long*>(base + o);
-  const int64_t max_chunks = (int64_t)(bimg_bytes / g.b_chunk);
+  sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return 0;
+}
 
+// Once per (weights, catalogue range, precision): table maxima -> scales / permutation -> candidate image(s).
+int fullrank_tc_prepare(const NaisParams& p, const NaisCatalog& cat, int64_t poi_begin, int64_t poi_end, int precision, void* plan,
+                        size_t plan_bytes, cudaStream_t stream) {
+  if (poi_end <= poi_begin) return 0;
+  int sms;
+  int rc = check_arch(sms);
+  if (rc) return rc;
+  PlanLayout L;
+  if (!plan_layout(p, poi_begin, poi_end, precision, L)) return NAIS_ERR_SHAPE;
+  if (plan_bytes < L.total) return NAIS_ERR_WORKSPACE;
+  unsigned char* base = reinterpret_cast<unsigned char*>(plan);
+  unsigned char* hdr = base + L.hdr;
   const NaisBranch& br = p.branch[0];
   cudaError_t e = cudaMemsetAsync(hdr, 0, tc::HDR_BYTES, stream);
   if (e != cudaSuccess) return (int)e;
@@ -1744,7 +1306,7 @@ int launch_fullrank_tc(const NaisParams& p, const NaisCatalog& cat, const NaisUs
   auto amax = [&](const float* x, size_t n, unsigned* out) {
     if (!x || n == 0) return;
     int blocks = (int)((n + 255) / 256);
-    if (blocks > 592) blocks = 592;
+    if (blocks > 4 * sms) blocks = 4 * sms;
     tc::absmax_kernel<<<blocks, 256, 0, stream>>>(x, n, out);
     NAIS_COUNT_LAUNCH(1);
   };
@@ -1754,18 +1316,72 @@ int launch_fullrank_tc(const NaisParams& p, const NaisCatalog& cat, const NaisUs
   amax(br.hist_reg, (size_t)p.region_num * br.w_reg, mx + 3);
   tc::scales_kernel<<<1, 256, 0, stream>>>(p, hdr);
   NAIS_COUNT_LAUNCH(1);
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // one precision = one pass; NAIS_PREC_TC_AUTO = the MIX pass and the SPLIT pass back to back, each gated on the device-side
-  // flag (the library never synchronises, so the choice cannot come back to the host; the losing pass exits at once)
-  auto run = [&](const tc::Geo& gg, int gate) -> int {
-    tc::pack_candidates_kernel<<<n_tiles_pad, 256, 0, stream>>>(p, cat, poi_begin, poi_end, gg, hdr, pimg, gate);
+  tc::pack_candidates_kernel<<<L.n_tiles_pad, 256, 0, stream>>>(p, cat, poi_begin, poi_end, L.g, hdr, base + L.pimg);
+  NAIS_COUNT_LAUNCH(1);
+  if (L.two_pass) {
+    tc::pack_candidates_kernel<<<L.n_tiles_pad, 256, 0, stream>>>(p, cat, poi_begin, poi_end, L.gs, hdr, base + L.pimg2);
     NAIS_COUNT_LAUNCH(1);
-    {
-      dim3 grid(users.n_users, 64);
-      tc::pack_users_kernel<<<grid, 256, 0, stream>>>(p, users, gg, hdr, bimg, max_chunks, gate);
-      NAIS_COUNT_LAUNCH(1);
-    }
+  }
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+typedef void (*MainKernel)(const tc::MainArgs);
+
+// compile-time-shape instantiations: kFix 1 / 2 = D = hid = 64 or 32 in SPLIT / MIX, kFix 3 = D = hid = 128 (generic code paths,
+// constants folded); everything else (and NAIS_PREC_FLAG_GENERIC) runs the run-time-shape kernels
+static MainKernel pick_kernel(const tc::Geo& gg, bool generic) {
+  const bool s64 = gg.D == 64 && gg.hid == 64 && gg.nrow == 144, s32 = gg.D == 32 && gg.hid == 32 && gg.nrow == 80;
+  const int fix = ((s64 || s32) && gg.kp == 1 && gg.hch == 2 && gg.stages == 2 && !generic) ? (gg.mix ? 2 : (gg.split ? 1 : 0)) : 0;
+  if (gg.kp == 1) {
+    if (gg.hch != 2) return tc::fullrank_tc_kernel<true, 1, 0>;
+    if (fix == 2) return s64 ? tc::fullrank_tc_kernel<true, 2, 2, 64> : tc::fullrank_tc_kernel<true, 2, 2, 32>;
+    if (fix == 1) return s64 ? tc::fullrank_tc_kernel<true, 2, 1, 64> : tc::fullrank_tc_kernel<true, 2, 1, 32>;
+    return tc::fullrank_tc_kernel<true, 2, 0>;
+  }
+  if (gg.hch == 2) return tc::fullrank_tc_kernel<false, 2, 0>;
+  if (gg.D == 128 && gg.hid == 128 && gg.kp == 4 && gg.nrow == 144 && gg.stages == 3 && (gg.mix || gg.split) && !generic)
+    return tc::fullrank_tc_kernel<false, 1, 3>;
+  return tc::fullrank_tc_kernel<false, 1, 0>;
+}
+
+// Per user batch: user operand image -> scoring pass(es) -> merge of the per-item lists.
+int fullrank_tc_run(const NaisParams& p, const NaisCatalog& cat, const NaisUsers& users, int64_t poi_begin, int64_t poi_end, int k,
+                    int exclude, int precision, const void* plan, size_t plan_bytes, unsigned long long* out_keys, float* out_score,
+                    int32_t* out_id, float* all_scores, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (users.n_users == 0 || poi_end <= poi_begin) return 0;
+  int sms;
+  int rc = check_arch(sms);
+  if (rc) return rc;
+  PlanLayout L;
+  if (!plan_layout(p, poi_begin, poi_end, precision, L)) return NAIS_ERR_SHAPE;
+  if (!plan || plan_bytes < L.total) return NAIS_ERR_WORKSPACE;
+  const unsigned char* pbase = reinterpret_cast<const unsigned char*>(plan);
+  const unsigned char* hdr = pbase + L.hdr;
+  // nnz is not known to the library (offsets live on the device): the caller sized the workspace with it; the chunk capacity
+  // of the operand image is whatever the workspace leaves after the fixed-size parts.
+  const size_t keys_bytes = call_keys_bytes(users.n_users, L.groups, k), scratch_bytes = call_scratch_bytes(users.n_users, L.groups, k);
+  if (ws_bytes < 256 + keys_bytes + scratch_bytes + (size_t)L.g.b_chunk) return NAIS_ERR_WORKSPACE;
+  unsigned char* base = reinterpret_cast<unsigned char*>(ws);
+  int* pass_flags = reinterpret_cast<int*>(base);
+  const size_t bimg_bytes = (ws_bytes - 256 - keys_bytes - scratch_bytes) / 256 * 256;
+  unsigned char* bimg = base + 256;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(base + 256 + bimg_bytes);
+  unsigned long long* scratch = reinterpret_cast<unsigned long long*>(base + 256 + bimg_bytes + keys_bytes);
+  const int64_t max_chunks = (int64_t)(bimg_bytes / L.g.b_chunk);
+  cudaError_t e;
+  if (L.two_pass) {
+    e = cudaMemsetAsync(pass_flags, 0, 8, stream);
+    if (e != cudaSuccess) return (int)e;
+  }
+  {
+    dim3 grid(users.n_users, 64);
+    tc::pack_users_kernel<<<grid, 256, 0, stream>>>(p, users, L.g, L.gs, L.two_pass ? 1 : 0, hdr, bimg, max_chunks, pass_flags,
+                                                   bad_index_flag());
+    NAIS_COUNT_LAUNCH(1);
+  }
+  const bool generic = (precision & NAIS_PREC_FLAG_GENERIC) != 0;
+  auto run = [&](const tc::Geo& gg, const unsigned char* pimg, int gate) -> int {
     tc::MainArgs A;
     A.p = p;
     A.cat = cat;
@@ -1775,8 +1391,8 @@ int launch_fullrank_tc(const NaisParams& p, const NaisCatalog& cat, const NaisUs
     A.poi_end = poi_end;
     A.k = k;
     A.exclude = exclude;
-    A.groups = groups;
-    A.n_items = (int64_t)users.n_users * groups;
+    A.groups = L.groups;
+    A.n_items = (int64_t)users.n_users * L.groups;
     A.hdr = hdr;
     A.Pimg = pimg;
     A.Bimg = bimg;
@@ -1784,47 +1400,42 @@ int launch_fullrank_tc(const NaisParams& p, const NaisCatalog& cat, const NaisUs
     A.all_scores = all_scores;
     A.max_chunks = max_chunks;
     A.gate = gate;
-    // static D = hid = 64 instantiations (the reference's C1/C2 shape): 1 = SPLIT, 2 = MIX
-    const bool s64 = gg.D == 64 && gg.hid == 64 && gg.nrow == 144, s32 = gg.D == 32 && gg.hid == 32 && gg.nrow == 80;
-    const int fix = ((s64 || s32) && gg.kp == 1 && gg.hch == 2 && gg.stages == 2 && !getenv("NAIS_TC_GENERIC")) ? (gg.mix ? 2 : (gg.split ? 1 : 0)) : 0;
-    void (*kern)(const tc::MainArgs) =
-        gg.kp == 1 ? (gg.hch == 2 ? (fix == 2 ? (s64 ? tc::fullrank_tc_kernel<true, 2, 2, 64> : tc::fullrank_tc_kernel<true, 2, 2, 32>)
-                                              : (fix == 1 ? (s64 ? tc::fullrank_tc_kernel<true, 2, 1, 64> : tc::fullrank_tc_kernel<true, 2, 1, 32>)
-                                                          : tc::fullrank_tc_kernel<true, 2, 0>))
-                                  : tc::fullrank_tc_kernel<true, 1, 0>)
-                   : (gg.hch == 2 ? tc::fullrank_tc_kernel<false, 2, 0>
-                               : (gg.D == 128 && gg.hid == 128 && gg.kp == 4 && gg.nrow == 144 && gg.stages == 3 && (gg.mix || gg.split) &&
-                                          !getenv("NAIS_TC_GENERIC")
-                                      ? tc::fullrank_tc_kernel<false, 1, 3>
-                                      : tc::fullrank_tc_kernel<false, 1, 0>));
-    int smem_bytes = gg.smem_bytes;
-    if (gg.ts) {
-      kern = tc::fullrank_ts_kernel;
-      smem_bytes = tc::ts::SMEM_BYTES;
-    }
-    cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    A.pass_flags = pass_flags;
+    MainKernel kern = pick_kernel(gg, generic);
+    cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gg.smem_bytes);
     if (e2 != cudaSuccess) return (int)e2;
     const int grid = (int)(A.n_items < sms ? A.n_items : sms);
-    kern<<<grid, gg.ts ? tc::TS_THREADS : tc::THREADS, smem_bytes, stream>>>(A);
+    kern<<<grid, tc::THREADS, gg.smem_bytes, stream>>>(A);
     NAIS_COUNT_LAUNCH(1);
     e2 = cudaGetLastError();
     return e2 == cudaSuccess ? 0 : (int)e2;
   };
-  if (precision == NAIS_PREC_TC_AUTO) {
-    tc::Geo gs;
-    if (!tc::make_geo(p, NAIS_PREC_TC_SPLIT, gs)) return NAIS_ERR_SHAPE;
-    if (g.mix) {  // make_geo(AUTO) gave the MIX geometry: same image sizes as SPLIT, so the two passes share the workspace
-      if (gs.a_tile != g.a_tile || gs.b_chunk != g.b_chunk) return NAIS_ERR_SHAPE;
-      int rc = run(g, 1);
-      if (rc) return rc;
-    }
-    int rc = run(gs, g.mix ? 0 : -1);  // users the MIX pass left out (short histories; everyone if the gate is closed)
+  if (L.two_pass) {
+    // the MIX pass and the SPLIT pass back to back; each user belongs to one (decided on the device: the library never
+    // synchronises, so the choice cannot come back to the host); a pass nobody takes is one launch that exits at once
+    rc = run(L.g, pbase + L.pimg, 1);
     if (rc) return rc;
+    rc = run(L.gs, pbase + L.pimg2, 0);
   } else {
-    int rc = run(g, -1);
-    if (rc) return rc;
+    rc = run(L.g, pbase + L.pimg, -1);
   }
-  return launch_topk_merge_keys_multi(keys, scratch, users.n_users, groups, k, out_score, out_id, stream);
+  if (rc) return rc;
+  return launch_topk_merge_keys_multi(keys, scratch, (int64_t)L.groups * k, k, users.n_users, L.groups, k, out_keys, out_score, out_id,
+                                      stream);
+}
+
+// The unplanned entry: plan at the head of the workspace, prepared on every call.
+int launch_fullrank_tc(const NaisParams& p, const NaisCatalog& cat, const NaisUsers& users, int64_t poi_begin,
+                       int64_t poi_end, int k, int exclude, int precision, float* out_score, int32_t* out_id,
+                       float* all_scores, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (users.n_users == 0 || poi_end <= poi_begin) return 0;
+  const size_t plan_bytes = fullrank_tc_plan_bytes(p, poi_begin, poi_end, precision);
+  if (!plan_bytes) return NAIS_ERR_SHAPE;
+  if (ws_bytes < plan_bytes + 512) return NAIS_ERR_WORKSPACE;
+  int rc = fullrank_tc_prepare(p, cat, poi_begin, poi_end, precision, ws, plan_bytes, stream);
+  if (rc) return rc;
+  return fullrank_tc_run(p, cat, users, poi_begin, poi_end, k, exclude, precision, ws, plan_bytes, nullptr, out_score, out_id,
+                         all_scores, reinterpret_cast<unsigned char*>(ws) + plan_bytes, ws_bytes - plan_bytes, stream);
 }
 
 }  // namespace nais

@@ -1,16 +1,23 @@
-"""Multi-GPU plumbing for full-rank evaluation (one process per GPU, `torch.distributed`).
+"""Multi-GPU plumbing (one process per GPU, `torch.distributed`): range-sharded full-rank evaluation and data-parallel
+training.
 
-The (user, candidate) pairs are independent — the beta-softmax normalises over the user's *history*, not over
+Evaluation.  The (user, candidate) pairs are independent — the beta-softmax normalises over the user's *history*, not over
 candidates — so the catalogue is split into contiguous POI ranges (and, when the catalogue is too small
 for `world` useful shards, the user batch into slices: `grid_shape`); each rank scores its users against its own range
-with the fused kernel, keeps a local top-k, and ONE collective per user batch exchanges the lists: an all-gather of [U,k] (fp32 score, int32 global id) = U*k*8*world bytes per rank, followed by an
-on-device merge (`nais_topk_merge`, same order rule as the single-GPU top-k, so results are identical to one GPU).
+with the fused kernel (against a `nais_fullrank_prepare` plan of its range, built once per model), keeps a local top-k as
+packed 8-byte ranking keys, and ONE collective per user batch exchanges them: `all_gather_into_tensor` of [U, k] int64 =
+U*k*8*world bytes per rank.  The gathered [world, U, k] buffer is merged in place by `nais_topk_merge_keys` (same order rule
+as the single-GPU top-k, so results are identical to one GPU).
+
+Training.  Data parallel over rows: dense all-reduce of the gradients (`allreduce_gradients`), or — for catalogues where the
+dense tables are hundreds of MB — the touched-row exchange of `SparseRowExchange` (all-gather of (row id, gradient row) lists
+and a row-sparse Adagrad on the union, SURVEY.md §8e 'Train partitioning').
 
 The reference has no distributed code at all; this module is new.
 """
 from __future__ import annotations
 
-from typing import Callable, Optional, Tuple
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -28,15 +35,12 @@ def shard_range(n: int, rank: int, world: int, align: int = 128) -> Tuple[int, i
     return lo, max(lo, hi)
 
 
-def gather_lists(score: torch.Tensor, ids: torch.Tensor, world: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    """all-gather [U,k] lists from every rank into [U, world, k] (rank-major along dim 1)."""
-    U, k = score.shape
-    gs = torch.empty(world, U, k, dtype=score.dtype, device=score.device)
-    gi = torch.empty(world, U, k, dtype=ids.dtype, device=ids.device)
-    # list form: supported by both nccl and gloo (all_gather_into_tensor is nccl-only)
-    dist.all_gather(list(gs.unbind(0)), score.contiguous())
-    dist.all_gather(list(gi.unbind(0)), ids.contiguous())
-    return gs.permute(1, 0, 2).contiguous(), gi.permute(1, 0, 2).contiguous()
+def gather_keys(keys: torch.Tensor, world: int) -> torch.Tensor:
+    """ONE all-gather of the per-rank key lists [U, k] int64 -> [world, U, k] (rank-major)."""
+    U, k = keys.shape
+    out = torch.empty(world * U, k, dtype=keys.dtype, device=keys.device)
+    dist.all_gather_into_tensor(out, keys.contiguous())
+    return out.view(world, U, k)
 
 
 def grid_shape(n_items: int, world: int, min_shard_pois: int) -> Tuple[int, int]:
@@ -51,34 +55,46 @@ def grid_shape(n_items: int, world: int, min_shard_pois: int) -> Tuple[int, int]
     return gc, world // gc
 
 
+def _merge_cuda(keys: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    return ops.topk_merge_keys(keys)
+
+
 class ShardedRanker:
     """predict_topk over a range-sharded catalogue (x user-sliced batches when the catalogue is small, `grid_shape`).
     `local_topk` / `merge` / `slice_users` are injectable so the host-side logic can be exercised with the gloo backend on
-    CPU (tests/test_distributed_cpu.py); the defaults are the CUDA ops.  rank = user_slice * catalogue_shards + shard."""
+    CPU (tests/test_distributed_cpu.py); the defaults are the CUDA ops.  rank = user_slice * catalogue_shards + shard.
+
+    local_topk(users, k, lo, hi, precision) -> keys [U, k] int64, or (score [U,k], id [U,k]) which is packed here
+    merge(keys [L, U, k]) -> (score [U, k], id [U, k])"""
 
     def __init__(self, model, rank: int = 0, world: int = 1, local_topk: Optional[Callable] = None,
-                 merge: Optional[Callable] = None, min_shard_pois: int = 32768, slice_users: Optional[Callable] = None):
+                 merge: Optional[Callable] = None, min_shard_pois: int = 32768, slice_users: Optional[Callable] = None,
+                 grid: Optional[Tuple[int, int]] = None):
         self.model, self.rank, self.world = model, rank, world
         self.n = model.item_num
-        self.gc, self.gu = grid_shape(self.n, world, min_shard_pois)
+        self.gc, self.gu = grid if grid is not None else grid_shape(self.n, world, min_shard_pois)
+        if self.gc * self.gu != world:
+            raise ValueError(f"grid {self.gc} x {self.gu} does not cover {world} ranks")
         self.rc, self.ru = rank % self.gc, rank // self.gc
         self.lo, self.hi = shard_range(self.n, self.rc, self.gc)
         self._local = local_topk or self._cuda_local
-        self._merge = merge or ops.topk_merge
+        self._merge = merge or _merge_cuda
         self._slice = slice_users or (lambda users, u0, u1: users.slice(u0, u1))
         self.events = []
 
     def _cuda_local(self, users, k, lo, hi, precision):
         m = self.model
-        return ops.fullrank_topk(m.variant, float(m.beta), m._params(), m._catalog, users, k, lo, hi, True, precision)
+        plan = m.ranking_plan(precision, lo, hi)  # built on the first batch, reused while the weights stand
+        return ops.fullrank_topk(m.variant, float(m.beta), m._params(), m._catalog, users, k, lo, hi, True, plan.precision, plan,
+                                 return_keys=self.world > 1)  # one GPU: the merge kernel writes score / id itself
 
     def kernel_name(self, precision: str) -> str:
         return {"fp32": "fullrank_fp32_kernel"}.get(precision, "fullrank_tc_kernel")
 
     @property
     def parallelism(self) -> str:
-        return f"{self.gc} catalogue range shard(s) x {self.gu} user slice(s), all-gather of the top-k lists" + (
-            " + on-device merge" if self.gc > 1 else "")
+        return (f"{self.gc} catalogue range shard(s) x {self.gu} user slice(s), one all-gather of the packed top-k keys" +
+                (" + on-device merge" if self.gc > 1 else ""))
 
     @property
     def last_kernel_ms(self) -> Optional[float]:
@@ -95,27 +111,30 @@ class ShardedRanker:
         return u0, min(n_users, u0 + per), per
 
     def _score_and_exchange(self, users, n_users: int, k: int, precision: str, timed: bool):
-        """`users` = this rank's slice.  Local fused scoring + top-k, then ONE all-gather of the lists and (catalogue
-        shards > 1) the on-device merge; every rank returns the lists of the whole batch [n_users, k]."""
+        """`users` = this rank's slice.  Local fused scoring + top-k, then ONE all-gather of the key lists and the
+        on-device merge / unpack; every rank returns the lists of the whole batch [n_users, k]."""
         u0, u1, per = self.user_range(n_users)
         if timed:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-        s, i = self._local(users, k, self.lo, self.hi, precision)
+        keys = self._local(users, k, self.lo, self.hi, precision)
         if timed:
             b.record()
             self.events = [(a, b)]
         if self.world == 1:
-            return s, i
-        if s.shape[0] < per:  # last slice: pad with "no entry" rows
-            s = torch.cat([s, s.new_full((per - s.shape[0], k), float("-inf"))])
-            i = torch.cat([i, i.new_full((per - i.shape[0], k), -1)])
-        gs, gi = gather_lists(s, i, self.world)                      # [per, world, k], rank-major along dim 1
-        gs = gs.view(per, self.gu, self.gc, k).permute(1, 0, 2, 3).reshape(self.gu * per, self.gc, k)[:n_users]
-        gi = gi.view(per, self.gu, self.gc, k).permute(1, 0, 2, 3).reshape(self.gu * per, self.gc, k)[:n_users]
-        if self.gc == 1:
-            return gs[:, 0].contiguous(), gi[:, 0].contiguous()
-        return self._merge(gs.contiguous(), gi.contiguous())
+            return keys if isinstance(keys, tuple) else self._merge(keys.unsqueeze(0))
+        if isinstance(keys, tuple):
+            keys = ops.lists_to_keys(*keys)
+        if keys.shape[0] < per:  # last slice: pad with "no entry" rows (key 0)
+            keys = torch.cat([keys, keys.new_zeros((per - keys.shape[0], k))])
+        g = gather_keys(keys, self.world)                      # [world, per, k], rank = slice * gc + shard
+        if self.gu == 1:
+            return self._merge(g)
+        if self.gc == 1:  # user slices only: the gathered buffer IS the batch in user order; one unpack of [gu * per, k]
+            s_, i_ = self._merge(g.view(1, self.gu * per, k))
+            return s_[:n_users], i_[:n_users]
+        outs = [self._merge(g[s * self.gc:(s + 1) * self.gc]) for s in range(self.gu)]  # one [gc, per, k] block per slice
+        return torch.cat([o[0] for o in outs])[:n_users], torch.cat([o[1] for o in outs])[:n_users]
 
     def topk(self, users, k: int, precision: str = "auto"):
         """`users`: the whole batch (DeviceUsers), resident on every rank."""

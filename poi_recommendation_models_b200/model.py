@@ -40,6 +40,11 @@ class _NAISBase(nn.Module):
         self.beta = beta
         self.hidden_size = hidden_size
         self._catalog: Optional[ops.DeviceCatalog] = None
+        self._plans: Dict[tuple, ops.FullrankPlan] = {}
+        self._plan_epoch = 0  # bumped by every in-place parameter update torch's version counters do not see
+        # which kernels forward / backward run: "auto" = tcgen05 where the shape has them (one branch, D in {16..64}, hid <= 128;
+        # backward: hid = 64, D in {32, 64}), else the FP32 CUDA-core kernels; "fp32" / "tc" force one (NaisParams::pairs_precision)
+        self.pairs_precision = "auto"
 
     def _acts(self):
         self.relu = nn.ReLU()
@@ -68,7 +73,8 @@ class _NAISBase(nn.Module):
             drop_p, seed = float(self.drop.p), int(torch.randint(0, 2 ** 62, (1,)).item())
             self.last_dropout_seed = seed
         P = self._params()
-        return ops.pairs_score(self.variant, float(self.beta), tuple(P.values()), hist, tgt, hreg, treg, aux, drop_p, seed)
+        return ops.pairs_score(self.variant, float(self.beta), tuple(P.values()), hist, tgt, hreg, treg, aux, drop_p, seed,
+                               getattr(self, "pairs_precision", "auto"))
 
     def fused_adagrad_step(self, optimizer: torch.optim.Adagrad, label, hist, tgt, hreg=None, treg=None, aux=None) -> torch.Tensor:
         """One training step of run.py:248-254 (`zero_grad -> forward -> BCELoss -> backward -> Adagrad.step`) with the
@@ -94,9 +100,10 @@ class _NAISBase(nn.Module):
                 raise RuntimeError("embedding tables must share lr / eps")
             lr, eps = g["lr"], g["eps"]
             sums[name] = optimizer.state[P[name]]["sum"]
-        drop = (0.0, 0)
+        pp = getattr(self, "pairs_precision", "auto")
+        drop = (0.0, 0, pp)
         if self._dropout_on_l1 and self.training and self.drop.p > 0:
-            drop = (float(self.drop.p), int(torch.randint(0, 2 ** 62, (1,)).item()))
+            drop = (float(self.drop.p), int(torch.randint(0, 2 ** 62, (1,)).item()), pp)
             self.last_dropout_seed = drop[1]
         optimizer.zero_grad(set_to_none=True)
         with torch.no_grad():
@@ -110,6 +117,7 @@ class _NAISBase(nn.Module):
         for name, grad in G.items():
             P[name].grad = grad.to(P[name].dtype)
         optimizer.step()  # the tables have no .grad: torch skips them
+        self._plan_epoch = getattr(self, "_plan_epoch", 0) + 1  # the kernel stepped the tables behind torch's version counters
         return loss.detach()
 
     def get_mask(self, user_history, target_item):
@@ -134,6 +142,42 @@ class _NAISBase(nn.Module):
             crd = torch.as_tensor((c - np.array(center)).astype(np.float32), device=dev)
         n = len(reg) if reg is not None else (len(crd) if crd is not None else self.item_num - row_base)
         self._catalog = ops.DeviceCatalog(reg, crd, row_base, n, center)
+        self._plans = {}
+
+    def _apply(self, fn, *args, **kwargs):
+        # .cuda() / .to(device): the catalogue arrays follow the parameters (a catalogue left behind on another device would
+        # reach the kernels as a foreign pointer), and every ranking plan is dropped
+        super()._apply(fn, *args, **kwargs)
+        cat = getattr(self, "_catalog", None)
+        if cat is not None:
+            dev = next(self.parameters()).device
+            mv = lambda t: None if t is None else t.to(dev)
+            self._catalog = ops.DeviceCatalog(mv(cat.region), mv(cat.coords), cat.row_base, cat.n_rows, cat.center)
+        self._plans = {}
+        return self
+
+    def __getstate__(self):
+        st = super().__getstate__() if hasattr(nn.Module, "__getstate__") else self.__dict__.copy()
+        st = dict(st)
+        st["_plans"] = {}  # derived device buffers (up to hundreds of MB): rebuilt on first use, never pickled
+        return st
+
+    def ranking_plan(self, precision: str = "auto", poi_begin: int = 0, poi_end: Optional[int] = None) -> ops.FullrankPlan:
+        """The `nais_fullrank_prepare` plan of the current weights for a catalogue range, built on first use and reused until a
+        parameter changes (torch's per-tensor version counters + `_plan_epoch`), the catalogue is replaced or the model
+        moves: an evaluation (validation.py:69, one frozen model, every user) pays the per-model constants once."""
+        if self._catalog is None:
+            raise RuntimeError("call set_catalog(region, coords) first")
+        P = self._params()
+        poi_end = self.item_num if poi_end is None else poi_end
+        key = (precision, poi_begin, poi_end, getattr(self, "_plan_epoch", 0), float(self.beta)) + tuple(
+            (t.data_ptr(), t._version) for t in P.values())
+        plan = self._plans.get((precision, poi_begin, poi_end))
+        if plan is None or plan.key != key:
+            plan = ops.fullrank_prepare(self.variant, float(self.beta), P, self._catalog, poi_begin, poi_end, precision)
+            plan.key = key
+            self._plans[(precision, poi_begin, poi_end)] = plan
+        return plan
 
     def make_users(self, indptr, indices) -> ops.DeviceUsers:
         """CSR histories (train_matrix.indptr / .indices, validation.py:86) -> device arrays with region ids and
@@ -146,6 +190,8 @@ class _NAISBase(nn.Module):
         it = torch.as_tensor(np.asarray(indices), dtype=torch.int64, device=dev)
         if cat.row_base != 0 and (cat.region is not None or cat.coords is not None):
             raise RuntimeError("history gathering needs the full catalogue on this device (row_base == 0)")
+        if it.numel() and (int(it.min()) < 0 or int(it.max()) >= self.item_num):  # what nn.Embedding would raise on (host-side: this
+            raise IndexError("history item id outside [0, item_num)")              # call builds device arrays from host CSR anyway)
         reg = cat.region[it] if cat.region is not None else None
         crd = cat.coords[it].contiguous() if cat.coords is not None else None
         return ops.DeviceUsers(off, it.to(torch.int32), reg, crd, len(indptr) - 1, int(len(indices)),
@@ -161,8 +207,9 @@ class _NAISBase(nn.Module):
         "tc_split", "tc_mix", "tc_fast" (ops.resolve_precision, include/nais_b200.h NAIS_PREC_*)."""
         if not isinstance(users, ops.DeviceUsers):
             users = self.make_users(*users)
+        plan = self.ranking_plan(precision, poi_begin, poi_end)
         s, i = ops.fullrank_topk(self.variant, float(self.beta), self._params(), self._catalog, users, k, poi_begin,
-                                 poi_end, exclude_history, precision)
+                                 poi_end, exclude_history, plan.precision, plan)
         return torch.sigmoid(s), i.to(torch.int64)
 
 

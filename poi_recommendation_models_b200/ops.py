@@ -12,8 +12,8 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (DIST_KM, DIST_LATLON, DIST_NONE, PRECISIONS, NaisBranch, NaisCatalog, NaisGrads, NaisPairs,
-                   NaisParams, NaisUsers)
+from ._lib import (DIST_KM, DIST_LATLON, DIST_NONE, PAIRS_PRECISIONS, PRECISIONS, NaisBranch, NaisCatalog, NaisGrads,
+                   NaisPairs, NaisParams, NaisUsers)
 
 # parameter names per variant, in the reference's state_dict naming (SURVEY.md §5 checkpoint row)
 VARIANT_PARAMS: Dict[str, Tuple[str, ...]] = {
@@ -61,9 +61,71 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# Out-of-range ids (nn.Embedding raises IndexError; the kernels cannot): every pair call enqueues a poll of the library's
+# device-side bad-index word into pinned host memory (nais_poll_bad_index: an async 4-byte copy, no synchronisation) and
+# looks at the polls that have completed since — so a bad id raises on a LATER call of this module, or at once with
+# `check_indices(sync=True)`.  The kernels themselves never use such an id as an address (include/nais_b200.h).
+# ----------------------------------------------------------------------------------------------------------------------
+_POLL_SLOTS = 64
+_POLLS: Dict[int, dict] = {}  # device index -> {"buf": pinned int32 [_POLL_SLOTS], "next": slot, "inflight": [(slot, event)]}
+
+
+def _poll_state(dev: torch.device) -> dict:
+    st = _POLLS.get(dev.index or 0)
+    if st is None:
+        st = {"buf": torch.zeros(_POLL_SLOTS, dtype=torch.int32).pin_memory(), "next": 0, "inflight": []}
+        _POLLS[dev.index or 0] = st
+    return st
+
+
+def _poll_bad_index(dev: torch.device) -> None:
+    if torch.cuda.is_current_stream_capturing():
+        return  # inside a CUDA graph capture: the word stays raised on the device until the next poll outside a graph
+    st = _poll_state(dev)
+    check_indices(dev, sync=len(st["inflight"]) >= _POLL_SLOTS - 1)
+    slot = st["next"]
+    st["next"] = (slot + 1) % _POLL_SLOTS
+    _lib.check(_lib.load().nais_poll_bad_index(st["buf"].data_ptr() + 4 * slot, _stream()), "nais_poll_bad_index")
+    ev = torch.cuda.Event()
+    ev.record()
+    st["inflight"].append((slot, ev))
+
+
+def check_indices(dev=None, sync: bool = False) -> None:
+    """Raise IndexError if a kernel enqueued before a completed poll met a POI / region id outside its table (what
+    nn.Embedding raises in the reference).  `sync=True` first polls once more and waits for every poll in flight."""
+    devs = list(_POLLS) if dev is None else [torch.device(dev).index or 0]
+    bad = False
+    for d in devs:
+        st = _POLLS.get(d)
+        if st is None:
+            if not sync:
+                continue
+            st = _poll_state(torch.device("cuda", d))
+        if sync and not torch.cuda.is_current_stream_capturing():
+            with torch.cuda.device(d):
+                slot = st["next"]
+                st["next"] = (slot + 1) % _POLL_SLOTS
+                _lib.check(_lib.load().nais_poll_bad_index(st["buf"].data_ptr() + 4 * slot, _stream()), "nais_poll_bad_index")
+                ev = torch.cuda.Event()
+                ev.record()
+                st["inflight"].append((slot, ev))
+        q = st["inflight"]
+        while q and (sync or q[0][1].query()):
+            slot, ev = q.pop(0)
+            ev.synchronize()
+            bad = bad or bool(st["buf"][slot].item())
+            st["buf"][slot] = 0
+    if bad:
+        raise IndexError("index out of range in a NAIS id tensor (a POI or region id outside its embedding table; detected on "
+                         "the device by an earlier kernel — no table row was read or written through it)")
+
+
 def build_params(variant: str, P: Dict[str, torch.Tensor], beta: float, keep: List[torch.Tensor],
-                 dropout_p: float = 0.0, dropout_seed: int = 0) -> NaisParams:
-    """NaisParams for a reference-shaped parameter dict.  Contiguous copies are appended to `keep` to stay alive."""
+                 dropout_p: float = 0.0, dropout_seed: int = 0, pairs_precision: str = "auto") -> NaisParams:
+    """NaisParams for a reference-shaped parameter dict.  Contiguous copies are appended to `keep` to stay alive.
+    `pairs_precision`: "auto" (tcgen05 pair kernels where the shape has them), "fp32", "tc" (NAIS_PAIRS_*)."""
     def g(name):
         t = _f32(P[name].detach())
         keep.append(t)
@@ -78,6 +140,7 @@ def build_params(variant: str, P: Dict[str, torch.Tensor], beta: float, keep: Li
     p.dist_mode, p.dist_scale, p.beta = mode, scale, float(beta)
     p.dist_buckets, p.dist_bucket_km, p.region_num, p.n_branch = 1, 1.0, 0, 1
     p.dropout_p, p.dropout_seed = float(dropout_p), int(dropout_seed)
+    p.pairs_precision = PAIRS_PRECISIONS[pairs_precision]
     b0 = p.branch[0]
     b0.hist_poi, b0.tgt_poi, b0.w_poi, b0.w_reg = eh.data_ptr(), et.data_ptr(), eh.shape[1], 0
     b0.w1, b0.b1, b0.w2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr()
@@ -140,6 +203,7 @@ class _PairsFunction(torch.autograd.Function):
             parts = torch.empty(p.n_branch, B, device=dev, dtype=torch.float32)
             _lib.check(lib.nais_pairs_forward(C.byref(p), C.byref(b), score.data_ptr(), row_sum.data_ptr(),
                                               parts.data_ptr(), _stream()), "nais_pairs_forward")
+            _poll_bad_index(dev)
         ctx.variant, ctx.beta, ctx.drop = variant, beta, drop
         ctx.save_for_backward(hist, tgt, hreg if hreg is not None else torch.empty(0), treg if treg is not None else torch.empty(0),
                               aux if aux is not None else torch.empty(0), row_sum, parts, *params)
@@ -181,23 +245,26 @@ class _PairsFunction(torch.autograd.Function):
             ds = _f32(dscore)
             _lib.check(lib.nais_pairs_backward(C.byref(p), C.byref(b), parts.data_ptr(), row_sum.data_ptr(), ds.data_ptr(),
                                                C.byref(g), ws.data_ptr(), ws_bytes, _stream()), "nais_pairs_backward")
+            _poll_bad_index(dev)
         grads = tuple(G[n].to(P[n].dtype) if ctx.needs_input_grad[8 + i] else None for i, n in enumerate(names))
         return (None, None, None, None, None, None, None, None) + grads
 
 
 def pairs_score(variant: str, beta: float, params: Sequence[torch.Tensor], hist, tgt, hreg=None, treg=None, aux=None,
-                dropout_p: float = 0.0, dropout_seed: int = 0):
+                dropout_p: float = 0.0, dropout_seed: int = 0, pairs_precision: str = "auto"):
     """Pre-sigmoid scores [B] of explicit pairs (differentiable w.r.t. `params`, ordered as VARIANT_PARAMS[variant]).
     `dropout_p > 0` applies the train-mode dropout of NAIS_basic / NAIS_regionEmbedding (model.py:71,162) with the
-    counter-based mask of NaisParams::dropout_seed; backward regenerates the same mask."""
-    return _PairsFunction.apply(variant, beta, (float(dropout_p), int(dropout_seed)), hist, tgt, hreg, treg, aux, *params)
+    counter-based mask of NaisParams::dropout_seed; backward regenerates the same mask.  `pairs_precision`: "auto" = the
+    tcgen05 forward / backward kernels where the shape has them (else the FP32 kernels), "fp32", "tc"."""
+    return _PairsFunction.apply(variant, beta, (float(dropout_p), int(dropout_seed), pairs_precision), hist, tgt, hreg, treg, aux,
+                                *params)
 
 
 _TABLES = ("embed_history.weight", "embed_target.weight", "embed_region.weight")
 
 
 def pairs_backward_adagrad(variant: str, beta: float, P: Dict[str, torch.Tensor], sums: Dict[str, torch.Tensor], lr: float,
-                           eps: float, hist, tgt, hreg, treg, aux, row_sum, parts, dscore, drop=(0.0, 0)) -> Dict[str, torch.Tensor]:
+                           eps: float, hist, tgt, hreg, treg, aux, row_sum, parts, dscore, drop=(0.0, 0, "auto")) -> Dict[str, torch.Tensor]:
     """Backward of `pairs_score` with the embedding tables stepped in place by a row-sparse Adagrad fused into the
     sorted-segment reduce (nais_pairs_backward_adagrad; replaces run.py:252-254 for `embed_*`): `sums[name]` is the
     optimizer's `state['sum']` of table `name`; P[name] and sums[name] of every touched row are updated, nothing dense is
@@ -230,10 +297,11 @@ def pairs_backward_adagrad(variant: str, beta: float, P: Dict[str, torch.Tensor]
         _lib.check(lib.nais_pairs_backward_adagrad(C.byref(p), C.byref(b), parts.data_ptr(), row_sum.data_ptr(), ds.data_ptr(),
                                                    C.byref(g), C.byref(o), ws.data_ptr(), ws_bytes, _stream()),
                    "nais_pairs_backward_adagrad")
+        _poll_bad_index(dev)
     return G
 
 
-def pairs_forward_raw(variant: str, beta: float, P: Dict[str, torch.Tensor], hist, tgt, hreg, treg, aux, drop=(0.0, 0)):
+def pairs_forward_raw(variant: str, beta: float, P: Dict[str, torch.Tensor], hist, tgt, hreg, treg, aux, drop=(0.0, 0, "auto")):
     """(score[B], row_sum, parts) of nais_pairs_forward without autograd bookkeeping (the fused train step keeps them)."""
     dev = _need_cuda(hist, tgt, *P.values())
     lib = _lib.load()
@@ -246,6 +314,7 @@ def pairs_forward_raw(variant: str, beta: float, P: Dict[str, torch.Tensor], his
         parts = torch.empty(p.n_branch, b.B, device=dev, dtype=torch.float32)
         _lib.check(lib.nais_pairs_forward(C.byref(p), C.byref(b), score.data_ptr(), row_sum.data_ptr(), parts.data_ptr(),
                                           _stream()), "nais_pairs_forward")
+        _poll_bad_index(dev)
     return score, row_sum, parts
 
 
@@ -294,10 +363,12 @@ class DeviceUsers:
                            None if self.coords is None else self.coords[a:b], u1 - u0, b - a, ho[u0:u1 + 1] - a)
 
 
-def _structs(cat: DeviceCatalog, users: DeviceUsers):
+def _structs(cat: DeviceCatalog, users: Optional[DeviceUsers]):
     c = NaisCatalog()
     c.region, c.coords, c.row_base, c.n_rows = _ptr(cat.region), _ptr(cat.coords), cat.row_base, cat.n_rows
     c.center_lat, c.center_lon = float(cat.center[0]), float(cat.center[1])
+    if users is None:
+        return c, None
     u = NaisUsers()
     u.offsets, u.items, u.region, u.coords, u.n_users = (_ptr(users.offsets), _ptr(users.items), _ptr(users.region),
                                                          _ptr(users.coords), users.n_users)
@@ -307,73 +378,193 @@ def _structs(cat: DeviceCatalog, users: DeviceUsers):
 WORKSPACE_LIMIT_BYTES = 8 << 30  # user batches whose workspace would exceed this are scored in slices
 
 
-def resolve_precision(lib, p, precision: str) -> str:
+def _tensor_path_device(dev: torch.device) -> bool:
+    return torch.cuda.get_device_capability(dev)[0] == 10  # tcgen05 / TMEM: sm_100 family only
+
+
+def resolve_precision(lib, p, precision: str, dev: Optional[torch.device] = None) -> str:
     """"auto" = the tensor-core path with its device-side MIX/SPLIT gate ("tc_auto") wherever the model shape has one
-    (one attention branch, D and hid up to 128 in steps of 16/32, lat/lon or no distance mode), else the FP32 kernel."""
+    (one attention branch, D and hid up to 128 in steps of 16/32, lat/lon or no distance mode) and the device is sm_100,
+    else the FP32 kernel."""
     if precision != "auto":
         return precision
+    if dev is not None and not _tensor_path_device(dev):
+        return "fp32"
     return "tc_auto" if lib.nais_fullrank_workspace_bytes(C.byref(p), 1, 1, 0, min(128, p.item_num), 1, PRECISIONS["tc_auto"]) else "fp32"
 
 
-def fullrank_topk(variant: str, beta: float, P: Dict[str, torch.Tensor], cat: DeviceCatalog, users: DeviceUsers, k: int,
-                  poi_begin: int = 0, poi_end: Optional[int] = None, exclude_history: bool = True,
-                  precision: str = "fp32") -> Tuple[torch.Tensor, torch.Tensor]:
-    """(score[U,k] pre-sigmoid descending, id[U,k] int32 global POI ids; -inf / -1 padding)."""
-    dev = _need_cuda(users.offsets, users.items, *P.values())
+@dataclass
+class FullrankPlan:
+    """Everything `nais_fullrank_topk` would recompute per call although it depends only on the weights and the catalogue
+    range (table maxima, scales, hidden-unit permutation, packed candidate image; include/nais_b200.h
+    `nais_fullrank_prepare`).  Valid until a parameter, the catalogue or the range changes."""
+    buf: Optional[torch.Tensor]  # device bytes (None: FP32 precision needs no plan)
+    precision: str
+    poi_begin: int
+    poi_end: int
+    key: tuple = ()
+
+    @property
+    def nbytes(self) -> int:
+        return 0 if self.buf is None else self.buf.numel()
+
+    def tc_choice(self) -> Optional[Dict[str, float]]:
+        """What the device-side gate of this plan decided: `rho` (bound on the logit scale) and `use_mix` (1 = the fp16 +
+        e5m2-correction kernels score every user with at least `min_hist_for_mix` history items under "tc_auto", 0 = the
+        three-pass fp16 split scores everyone).  Synchronises."""
+        if self.buf is None:
+            return None
+        host = self.buf[64:128].cpu()
+        return {"rho": float(host[44:48].view(torch.float32).item()), "use_mix": int(host[48:52].view(torch.int32).item()),
+                "min_hist_for_mix": 16}  # kMixRhoMax = 256 / kMixMinHist = 16 in csrc/nais_tc.cu
+
+
+def fullrank_prepare(variant: str, beta: float, P: Dict[str, torch.Tensor], cat: "DeviceCatalog", poi_begin: int = 0,
+                     poi_end: Optional[int] = None, precision: str = "auto") -> FullrankPlan:
+    """Build the plan of (weights, catalogue range, precision): once per evaluation, not once per user batch."""
+    dev = _need_cuda(cat.region, cat.coords, *P.values())
     lib = _lib.load()
     keep: List[torch.Tensor] = []
     with torch.cuda.device(dev):
         p = build_params(variant, P, beta, keep)
         poi_end = p.item_num if poi_end is None else poi_end
-        precision = resolve_precision(lib, p, precision)
+        precision = resolve_precision(lib, p, precision, dev)
         prec = PRECISIONS[precision]
-        ws_bytes = lib.nais_fullrank_workspace_bytes(C.byref(p), users.n_users, users.nnz, poi_begin, poi_end, k, prec)
+        nbytes = lib.nais_fullrank_plan_bytes(C.byref(p), poi_begin, poi_end, prec)
+        if precision == "fp32" or poi_end <= poi_begin:
+            return FullrankPlan(None, precision, poi_begin, poi_end)
+        if nbytes == 0:
+            raise RuntimeError(f"precision {precision!r} has no tensor path for this model shape")
+        buf = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        c, _ = _structs(cat, None)
+        _lib.check(lib.nais_fullrank_prepare(C.byref(p), C.byref(c), poi_begin, poi_end, prec, buf.data_ptr(), nbytes, _stream()),
+                   "nais_fullrank_prepare")
+    _LAST_TC_PLAN[0] = FullrankPlan(buf, precision, poi_begin, poi_end)
+    return _LAST_TC_PLAN[0]
+
+
+def fullrank_topk(variant: str, beta: float, P: Dict[str, torch.Tensor], cat: DeviceCatalog, users: DeviceUsers, k: int,
+                  poi_begin: int = 0, poi_end: Optional[int] = None, exclude_history: bool = True,
+                  precision: str = "fp32", plan: Optional[FullrankPlan] = None, return_keys: bool = False):
+    """(score[U,k] pre-sigmoid descending, id[U,k] int32 global POI ids; -inf / -1 padding) — or, with `return_keys`, the
+    packed ranking keys [U,k] int64 (bit pattern of the uint64 keys `topk_merge_keys` consumes).  `plan`: a
+    `fullrank_prepare` result for the same weights / range / precision; without one the constants are recomputed by this
+    call (`nais_fullrank_topk`)."""
+    dev = _need_cuda(users.offsets, users.items, users.region, users.coords, cat.region, cat.coords, *P.values())
+    lib = _lib.load()
+    keep: List[torch.Tensor] = []
+    with torch.cuda.device(dev):
+        p = build_params(variant, P, beta, keep)
+        poi_end = p.item_num if poi_end is None else poi_end
+        if plan is not None:
+            if (plan.poi_begin, plan.poi_end) != (poi_begin, poi_end):
+                raise RuntimeError("the plan was prepared for another catalogue range")
+            precision = plan.precision
+        precision = resolve_precision(lib, p, precision, dev)
+        prec = PRECISIONS[precision]
+        planned = plan is not None or return_keys
+        if planned:
+            ws_bytes = lib.nais_fullrank_planned_workspace_bytes(C.byref(p), users.n_users, users.nnz, poi_begin, poi_end, k, prec)
+        else:
+            ws_bytes = lib.nais_fullrank_workspace_bytes(C.byref(p), users.n_users, users.nnz, poi_begin, poi_end, k, prec)
         if ws_bytes > WORKSPACE_LIMIT_BYTES and users.host_offsets is not None and users.n_users > 1:
             n_slices = min(users.n_users, -(-ws_bytes // WORKSPACE_LIMIT_BYTES))
             step = -(-users.n_users // n_slices)
             parts = [fullrank_topk(variant, beta, P, cat, users.slice(u0, min(users.n_users, u0 + step)), k, poi_begin, poi_end,
-                                   exclude_history, precision) for u0 in range(0, users.n_users, step)]
+                                   exclude_history, precision, plan, return_keys) for u0 in range(0, users.n_users, step)]
+            if return_keys:
+                return torch.cat(parts)
             return torch.cat([a for a, _ in parts]), torch.cat([b for _, b in parts])
+        if planned and plan is None:
+            plan = fullrank_prepare(variant, beta, P, cat, poi_begin, poi_end, precision)
         c, u = _structs(cat, users)
-        out_s = torch.empty(users.n_users, k, device=dev, dtype=torch.float32)
-        out_i = torch.empty(users.n_users, k, device=dev, dtype=torch.int32)
         ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
-        _lib.check(lib.nais_fullrank_topk(C.byref(p), C.byref(c), C.byref(u), poi_begin, poi_end, k, int(exclude_history),
-                                          prec, out_s.data_ptr(), out_i.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
-                   "nais_fullrank_topk")
-        if precision != "fp32" and ws_bytes >= 128:
-            # device-side scales / precision gate of this call, read lazily by last_tc_choice(); a 64-byte copy, not a view:
-            # a view would pin the whole (up to 8 GiB) workspace until the next call
-            _LAST_TC_HEADER[0] = ws[64:128].clone()
-    return out_s, out_i
+        if return_keys:
+            out_k = torch.empty(users.n_users, k, device=dev, dtype=torch.int64)
+            out_s = out_i = None
+        else:
+            out_k = None
+            out_s = torch.empty(users.n_users, k, device=dev, dtype=torch.float32)
+            out_i = torch.empty(users.n_users, k, device=dev, dtype=torch.int32)
+        if planned:
+            _lib.check(lib.nais_fullrank_topk_planned(C.byref(p), C.byref(c), C.byref(u), poi_begin, poi_end, k, int(exclude_history),
+                                                      prec, _ptr(plan.buf), plan.nbytes, _ptr(out_k), _ptr(out_s), _ptr(out_i),
+                                                      ws.data_ptr(), ws_bytes, _stream()), "nais_fullrank_topk_planned")
+        else:
+            _lib.check(lib.nais_fullrank_topk(C.byref(p), C.byref(c), C.byref(u), poi_begin, poi_end, k, int(exclude_history),
+                                              prec, out_s.data_ptr(), out_i.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
+                       "nais_fullrank_topk")
+            if precision != "fp32" and ws_bytes >= 128 and users.n_users and poi_end > poi_begin:
+                # device-side scales / precision gate of this call (the plan sits at the head of the workspace), read lazily by
+                # last_tc_choice(); a 128-byte copy, not a view: a view would pin the whole (up to 8 GiB) workspace
+                _LAST_TC_PLAN[0] = FullrankPlan(ws[:128].clone(), precision, poi_begin, poi_end)
+    return out_k if return_keys else (out_s, out_i)
 
 
-_LAST_TC_HEADER: List[Optional[torch.Tensor]] = [None]
+_LAST_TC_PLAN: List[Optional[FullrankPlan]] = [None]
 
 
 def last_tc_choice() -> Optional[Dict[str, float]]:
-    """What the last tensor-path call decided on the device: `rho` (bound on the logit scale) and `use_mix` (1 = the
-    fp16 + e5m2-correction kernels ran under precision="tc_auto" for every user with at least `min_hist_for_mix` history
-    items, 0 = the three-pass fp16 split for everyone).  Synchronises."""
-    h = _LAST_TC_HEADER[0]
-    if h is None:
-        return None
-    host = h.cpu()
-    return {"rho": float(host[44:48].view(torch.float32).item()), "use_mix": int(host[48:52].view(torch.int32).item()),
-            "min_hist_for_mix": 16}  # kMixRhoMax = 256 / kMixMinHist = 16 in csrc/nais_tc.cu
+    """`FullrankPlan.tc_choice()` of the last tensor-path plan built or call made.  Synchronises."""
+    return None if _LAST_TC_PLAN[0] is None else _LAST_TC_PLAN[0].tc_choice()
+
+
+def topk_merge_keys(keys: torch.Tensor, want_keys: bool = False):
+    """Merge key lists [L, U, k] (int64 bit patterns of the uint64 ranking keys; L = one list per catalogue shard, exactly
+    the layout `all_gather_into_tensor` produces) into (score [U,k], id [U,k] int32) — or the merged keys [U,k]."""
+    dev = _need_cuda(keys)
+    L, U, k = keys.shape
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        kk = keys.contiguous()
+        if want_keys:
+            out_k = torch.empty(U, k, device=dev, dtype=torch.int64)
+            out_s = out_i = None
+        else:
+            out_k = None
+            out_s = torch.empty(U, k, device=dev, dtype=torch.float32)
+            out_i = torch.empty(U, k, device=dev, dtype=torch.int32)
+        _lib.check(lib.nais_topk_merge_keys(kk.data_ptr(), k, U * k, U, L, k, _ptr(out_k), _ptr(out_s), _ptr(out_i), _stream()),
+                   "nais_topk_merge_keys")
+    return out_k if want_keys else (out_s, out_i)
+
+
+def keys_to_lists(keys: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Unpack ranking keys (ordered(score) << 32 | (0xFFFFFFFF - id), 0 = no entry; csrc/nais_common.cuh make_key) into
+    (score float32, id int32; -inf / -1 padding).  Bit arithmetic on the int64 bit patterns: works on any device (the gloo
+    CPU tests of the sharding logic use it); the CUDA path never needs it — nais_topk_merge_keys writes score / id itself."""
+    o = (keys >> 32) & 0xFFFFFFFF
+    bits = torch.where((o & 0x80000000) != 0, o & 0x7FFFFFFF, (~o) & 0xFFFFFFFF)
+    score = torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).to(torch.int32).view(torch.float32).clone()
+    ids = (0xFFFFFFFF - (keys & 0xFFFFFFFF)).to(torch.int32)
+    empty = keys == 0
+    score[empty] = float("-inf")
+    ids[empty] = -1
+    return score, ids
+
+
+def lists_to_keys(score: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    """Inverse of `keys_to_lists` (same packing as make_key: NaN ranks as -inf, id < 0 = no entry -> key 0)."""
+    sc = torch.where(torch.isnan(score), torch.full_like(score, float("-inf")), score).to(torch.float32).contiguous()
+    u = sc.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    o = torch.where((u & 0x80000000) != 0, (~u) & 0xFFFFFFFF, u | 0x80000000)
+    lo = 0xFFFFFFFF - ids.to(torch.int64)
+    hi = torch.where(o >= 2 ** 31, o - 2 ** 32, o)  # the top half as a signed 32-bit value, so the shift stays inside int64
+    keys = (hi << 32) | lo
+    return torch.where(ids < 0, torch.zeros_like(keys), keys)
 
 
 def fullrank_scores(variant: str, beta: float, P: Dict[str, torch.Tensor], cat: DeviceCatalog, users: DeviceUsers,
                     poi_begin: int = 0, poi_end: Optional[int] = None, precision: str = "fp32") -> torch.Tensor:
     """All pre-sigmoid scores [U, poi_end-poi_begin] through the fused path (small cases / parity checks)."""
-    dev = _need_cuda(users.offsets, users.items, *P.values())
+    dev = _need_cuda(users.offsets, users.items, users.region, users.coords, cat.region, cat.coords, *P.values())
     lib = _lib.load()
     keep: List[torch.Tensor] = []
     with torch.cuda.device(dev):
         p = build_params(variant, P, beta, keep)
         poi_end = p.item_num if poi_end is None else poi_end
         c, u = _structs(cat, users)
-        precision = resolve_precision(lib, p, precision)
+        precision = resolve_precision(lib, p, precision, dev)
         prec = PRECISIONS[precision]
         out = torch.empty(users.n_users, poi_end - poi_begin, device=dev, dtype=torch.float32)
         ws_bytes = lib.nais_fullrank_workspace_bytes(C.byref(p), users.n_users, users.nnz, poi_begin, poi_end, 1, prec)

@@ -25,7 +25,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert declared and declared == set(_lib.SYMBOLS), (declared ^ set(_lib.SYMBOLS))
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.nais_abi_version() == 1
+    assert lib.nais_abi_version() == 2
     assert b"workspace" in lib.nais_strerror(-4)
     assert lib.nais_launch_count() >= 0
 

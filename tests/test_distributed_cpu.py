@@ -48,6 +48,7 @@ def _worker_body(rank, world, port, q, min_shard, want_grid):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from types import SimpleNamespace
+    from poi_recommendation_models_b200 import ops
     from poi_recommendation_models_b200.distributed import ShardedRanker, allreduce_gradients, shard_range
     N, U, k = 1000, 7, 20  # 7 users: the last user slice is ragged and gets padded for the gather
     rng = np.random.default_rng(0)  # same scores on every rank
@@ -68,7 +69,11 @@ def _worker_body(rank, world, port, q, min_shard, want_grid):
         return SimpleNamespace(offsets=users.offsets, n_users=u1 - u0, ids=users.ids[u0:u1])
 
     model = SimpleNamespace(item_num=N)
-    r = ShardedRanker(model, rank, world, local_topk=local_topk, merge=_merge_ref, min_shard_pois=min_shard, slice_users=slice_users)
+    def merge(keys):  # [L, U, k] packed keys, the layout of the single all-gather -> reference merge of the unpacked lists
+        gs, gi = ops.keys_to_lists(keys)
+        return _merge_ref(gs.permute(1, 0, 2).contiguous(), gi.permute(1, 0, 2).contiguous())
+
+    r = ShardedRanker(model, rank, world, local_topk=local_topk, merge=merge, min_shard_pois=min_shard, slice_users=slice_users)
     users = SimpleNamespace(offsets=torch.zeros(1), n_users=U, ids=np.arange(U))
     s, i = r.topk(users, k)
     ref_order = [np.lexsort((np.arange(N), -scores[u]))[:k] for u in range(U)]
