@@ -38,13 +38,11 @@ def main():
         else:
             s = m.attention_network(hist, tgt, reg[hist], reg[tgt], ll)
         s.sum().backward()
-        if name == "NAIS_region_distance_Embedding":  # the opt-in tensor-core pair kernels (forward + backward)
-            os.environ["NAIS_PAIRS_TC"] = os.environ["NAIS_PAIRS_TC_BWD"] = "1"
+        if name == "NAIS_region_distance_Embedding":  # the run above took the tensor-core pair kernels (default); now the FP32 ones
+            m.pairs_precision = "fp32"
             m.zero_grad(set_to_none=True)
-            m.eval()  # no dropout on this class anyway; eval keeps the shapes the tensor-core path supports
             m.attention_network(hist, tgt, reg[hist], reg[tgt], ll).sum().backward()
-            os.environ.pop("NAIS_PAIRS_TC")
-            os.environ.pop("NAIS_PAIRS_TC_BWD")
+            m.pairs_precision = "auto"
         m.eval()
         m.set_catalog(region=data.region, coords=data.coords)
         users = m.make_users(data.indptr, data.indices)

@@ -53,7 +53,8 @@ extern "C" {
 #define NAIS_PREC_TC_AUTO 4  /* MIX when a device-side bound on the logit scale keeps its error 4x under 1e-4, else SPLIT */
 #define NAIS_PREC_MASK 0xff
 /* OR-ed into `precision`: run the tensor path's run-time-shape kernel even where a compile-time-shape instantiation exists
- * (D = hid = 32 / 64 / 128).  Same results bit for bit; the parity suite uses it to cover both code paths. */
+ * (D = hid = 32 / 64 / 128).  Same math, another epilogue instruction order (results agree to fp32 rounding); the parity
+ * suite uses it to cover both code paths. */
 #define NAIS_PREC_FLAG_GENERIC 0x100
 
 /* NaisParams::pairs_precision — which kernels nais_pairs_forward / nais_pairs_backward[_adagrad] run */
@@ -162,16 +163,25 @@ NAIS_API const char* nais_strerror(int code);
 /* Number of kernels this library has launched in this process (diagnostic; bench.py reports it as gpu_launches). */
 NAIS_API uint64_t nais_launch_count(void);
 
-/* score[b] = attention_network(pairs)  (pre-sigmoid, model.py:246-297).  Saved for backward (either may be NULL):
- * row_sum[n_branch,B] = sum_h E_bh, score_parts[n_branch,B] = per-branch score (their sum over branches is score). */
+/* Which kernels the pair entry points run for (p, batch): *fwd_tc / *bwd_tc = 1 for the tcgen05 kernels, 0 for the FP32 CUDA-core
+ * kernels (NaisParams::pairs_precision, the shape and the device decide; nothing is launched).  Returns 0 or NAIS_ERR_*. */
+NAIS_API int nais_pairs_dispatch(const NaisParams* p, const NaisPairs* batch, int32_t* fwd_tc, int32_t* bwd_tc);
+
+/* score[b] = attention_network(pairs)  (pre-sigmoid, model.py:246-297).  Saved for backward (each may be NULL):
+ * row_sum[n_branch,B] = sum_h E_bh, score_parts[n_branch,B] = per-branch score (their sum over branches is score),
+ * act_mask[B*H] = the ReLU pattern of attn_layer1: bit k of word (b*H + h) is set iff hidden unit k of that cell was active
+ * (t_k > 0).  act_mask is written only by the tcgen05 forward with hid <= 64 (nais_pairs_dispatch: fwd_tc); the tcgen05
+ * backward then takes the unit-step of ReLU from it instead of thresholding its own recomputed t (bf16 two-term splits:
+ * ~1e-5 relative, enough to flip a unit that sits on the kink and move a gradient by one cell's whole contribution). */
 NAIS_API int nais_pairs_forward(const NaisParams* p, const NaisPairs* batch, float* score, float* row_sum, float* score_parts,
-                       nais_stream_t stream);
+                       uint64_t* act_mask, nais_stream_t stream);
 
 NAIS_API size_t nais_pairs_backward_workspace_bytes(const NaisParams* p, int64_t B, int32_t H);
-/* Given dscore[B] = dL/dscore, write every parameter gradient.  score/row_sum are the forward outputs. */
+/* Given dscore[B] = dL/dscore, write every parameter gradient.  score_parts / row_sum / act_mask are the forward's outputs
+ * (act_mask: NULL unless the tcgen05 forward wrote it). */
 NAIS_API int nais_pairs_backward(const NaisParams* p, const NaisPairs* batch, const float* score_parts, const float* row_sum,
-                        const float* dscore, const NaisGrads* grads, void* workspace, size_t workspace_bytes,
-                        nais_stream_t stream);
+                        const uint64_t* act_mask, const float* dscore, const NaisGrads* grads, void* workspace,
+                        size_t workspace_bytes, nais_stream_t stream);
 
 /* Row-sparse Adagrad fused into the embedding-gradient segment reduce.  Replaces, for the embedding tables, the dense
  * `embedding_dense_backward` + `torch.optim.Adagrad.step()` of run.py:225,252-254 (weight_decay = 0, lr_decay = 0: a row
@@ -187,8 +197,8 @@ typedef struct NaisAdagrad {
 } NaisAdagrad;
 /* Same as nais_pairs_backward (MLP / dist-layer gradients go to `grads`; table pointers in `grads` may be NULL). */
 NAIS_API int nais_pairs_backward_adagrad(const NaisParams* p, const NaisPairs* batch, const float* score_parts,
-                                const float* row_sum, const float* dscore, const NaisGrads* grads, const NaisAdagrad* opt,
-                                void* workspace, size_t workspace_bytes, nais_stream_t stream);
+                                const float* row_sum, const uint64_t* act_mask, const float* dscore, const NaisGrads* grads,
+                                const NaisAdagrad* opt, void* workspace, size_t workspace_bytes, nais_stream_t stream);
 
 /* Workspace for nais_fullrank_topk / nais_fullrank_scores: n_users and nnz = offsets[n_users] are host-known. */
 NAIS_API size_t nais_fullrank_workspace_bytes(const NaisParams* p, int32_t n_users, int64_t nnz, int64_t poi_begin,

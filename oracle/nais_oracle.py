@@ -218,10 +218,43 @@ class Catalog:
     region: np.ndarray  # [N] int64 — businessRegionEmbedList (run.py:218-223)
 
 
+def reference_model(variant: str, sd: Dict[str, torch.Tensor], beta: float):
+    """An instance of the UNMODIFIED reference class of `variant` (model.py, imported through oracle/ref_shim.py from
+    /root/reference or from the oracle/_ref snapshot) holding the weights `sd`, on the CPU in eval mode; None when no
+    reference is reachable.  `fullrank_user(..., model=...)` then times / checks the reference's own forward."""
+    from . import ref_shim
+    if not ref_shim.reference_available():
+        return None
+    ref = ref_shim.load_reference("model")
+    cls = getattr(ref, VARIANTS[variant]["cls"])
+    N = sd["embed_history.weight"].shape[0]
+    hid = sd["attn_layer1.weight"].shape[0]
+    D = sd["attn_layer1.weight"].shape[1] - (2 if VARIANTS[variant]["dist"] == "latlon" else 0)
+    R = sd["embed_region.weight"].shape[0] if "embed_region.weight" in sd else 1
+    if variant == "basic":
+        m = cls(N, D, hid, beta)
+    elif variant == "region":
+        m = cls(N, D, hid, beta, R)
+    else:
+        m = cls(N, D, hid, beta, R, sd["embed_distance.weight"].shape[0] if "embed_distance.weight" in sd else 1)
+    m.load_state_dict(sd, strict=True)
+    return m.cpu().eval()
+
+
+def _reference_forward(model, variant, hist, tgt, hreg, treg, aux):
+    if variant == "basic":
+        return model(hist, tgt)
+    if variant == "region":
+        return model(hist, tgt, hreg, treg)
+    return model(hist, tgt, hreg, treg, aux)
+
+
 def fullrank_user(sd, variant, beta, cat: Catalog, history: Sequence[int], topk: int = 50, chunk: int = 2048,
-                  dtype=torch.float32, return_all: bool = False):
+                  dtype=torch.float32, return_all: bool = False, model=None):
     """One iteration of the user loop of NAIS_region_distance_validation (validation.py:84-127):
-    candidates = all - history, scored in chunks of `chunk`, concatenated, torch.topk on post-sigmoid scores."""
+    candidates = all - history, scored in chunks of `chunk`, concatenated, torch.topk on post-sigmoid scores.
+    `model`: a `reference_model(...)` — the chunks then go through the reference's own `forward` (the loop around it is
+    this restatement either way: the reference's validator wants a dense [N,N,2] latlon_mat, 25 GB at N = 40 000)."""
     history = np.asarray(history, dtype=np.int64)
     cand = test_candidates(history, len(cat.region))
     v = VARIANTS[variant]
@@ -240,7 +273,11 @@ def fullrank_user(sd, variant, beta, cat: Catalog, history: Sequence[int], topk:
             c = cat.coords
             aux = torch.from_numpy(dist_km(c[tg][:, None, 0], c[tg][:, None, 1], c[history][None, :, 0],
                                            c[history][None, :, 1]).astype(np.float32))
-        preds.append(forward(sd, variant, beta, hist, torch.from_numpy(tg), hreg, treg, aux, dtype))
+        if model is not None:
+            with torch.no_grad():
+                preds.append(_reference_forward(model, variant, hist, torch.from_numpy(tg), hreg, treg, aux))
+        else:
+            preds.append(forward(sd, variant, beta, hist, torch.from_numpy(tg), hreg, treg, aux, dtype))
     pred = torch.cat(preds)
     k = min(topk, len(cand))
     val, idx = torch.topk(pred, k)

@@ -4,8 +4,9 @@ The reference (`/root/reference/model.py:4-6`) imports three packages that are n
 (`torch_geometric`, `torchmetrics`, `haversine`).  None of them is used by any NAIS class on the hot path, so we
 register empty stand-ins in `sys.modules` and import the reference modules from where they lie.  Nothing is copied.
 
-Used only by `tests/golden/make_golden.py` and by CPU tests that are skipped when `/root/reference` is absent
-(it does not exist on the GPU box).  The product package never imports this file.
+Used only by `tests/golden/make_golden.py`, by CPU tests that are skipped when no reference is reachable, and by the CPU arm
+of `bench.py` (`cpu_baseline.kind = "reference"`: the unmodified `model.py` classes, from /root/reference here or from the
+`oracle/_ref/` snapshot on the GPU box).  The product package never imports this file.
 """
 from __future__ import annotations
 
@@ -14,7 +15,10 @@ import os
 import sys
 import types
 
-REFERENCE_DIR = os.environ.get("NAIS_REFERENCE_DIR", "/root/reference")
+# where the unmodified modules are read from: the reference checkout if it exists (this container), else the snapshot that
+# oracle/make_ref.py took of it (the GPU box has no /root/reference; oracle/_ref/ travels there, git-ignored)
+_SNAPSHOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_DIR = os.environ.get("NAIS_REFERENCE_DIR") or ("/root/reference" if os.path.isfile("/root/reference/model.py") else _SNAPSHOT)
 
 
 def reference_available() -> bool:

@@ -64,13 +64,14 @@ SYMBOLS = {
     "nais_abi_version": (C.c_int, []),
     "nais_strerror": (C.c_char_p, [C.c_int]),
     "nais_launch_count": (C.c_uint64, []),
+    "nais_pairs_dispatch": (C.c_int, [C.POINTER(NaisParams), C.POINTER(NaisPairs), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "nais_pairs_forward": (C.c_int, [C.POINTER(NaisParams), C.POINTER(NaisPairs), C.c_void_p, C.c_void_p, C.c_void_p,
-                                     C.c_void_p]),
+                                     C.c_void_p, C.c_void_p]),
     "nais_pairs_backward_workspace_bytes": (C.c_size_t, [C.POINTER(NaisParams), C.c_int64, C.c_int32]),
-    "nais_pairs_backward": (C.c_int, [C.POINTER(NaisParams), C.POINTER(NaisPairs), C.c_void_p, C.c_void_p, C.c_void_p,
+    "nais_pairs_backward": (C.c_int, [C.POINTER(NaisParams), C.POINTER(NaisPairs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.POINTER(NaisGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
     "nais_pairs_backward_adagrad": (C.c_int, [C.POINTER(NaisParams), C.POINTER(NaisPairs), C.c_void_p, C.c_void_p, C.c_void_p,
-                                              C.POINTER(NaisGrads), C.POINTER(NaisAdagrad), C.c_void_p, C.c_size_t,
+                                              C.c_void_p, C.POINTER(NaisGrads), C.POINTER(NaisAdagrad), C.c_void_p, C.c_size_t,
                                               C.c_void_p]),
     "nais_powerlaw_logscore": (C.c_int, [C.POINTER(NaisCatalog), C.POINTER(NaisUsers), C.c_int64, C.c_int64, C.c_float, C.c_float,
                                          C.c_void_p, C.c_void_p]),

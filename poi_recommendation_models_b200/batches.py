@@ -89,8 +89,7 @@ class DeviceBatcher:
 
     def __init__(self, train_matrix, businessRegionEmbedList, place_coords, device=None, seed=0):
         dev = torch.device(device or _device())
-        csr = train_matrix.tocsr()
-        csr.sort_indices()
+        csr = train_matrix.tocsr()  # as stored (never reordered in place: `tocsr()` of a CSR matrix is the caller's object)
         self.num_poi = csr.shape[1]
         self.indptr = np.asarray(csr.indptr, dtype=np.int64)
         self.indices = torch.from_numpy(np.asarray(csr.indices, dtype=np.int64)).to(dev)

@@ -424,7 +424,8 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
                 dpv[cc] = full * qv[cc];
               }
               const int64_t ci = (H <= TC) ? (row0 + rr) * (int64_t)H + (c - rr * H) : row0 * (int64_t)H + ch * TC + c;
-              *reinterpret_cast<float4*>(A.ws_dq + ci * D + d0) = make_float4(o[0], o[1], o[2], o[3]);
+              store_dq4(A, br.w_poi, br.w_reg, A.dq_h ? __ldg(A.pos_h + ci) : 0u, A.dq_r ? __ldg(A.pos_r + ci) : 0u, d0,
+                        make_float4(o[0], o[1], o[2], o[3]));
             }
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) As[(size_t)(d0 + cc) * TCP + c] = dpv[cc];
@@ -446,7 +447,11 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
       }
     }
     __syncthreads();
-    for (int i = tid; i < nrows * D; i += NT) A.ws_dp[(row0 + i / D) * D + (i % D)] = dpacc[i];
+    for (int i = tid; i < nrows * D; i += NT) {
+      const int64_t row = row0 + i / D;
+      store_dp(A, br.w_poi, br.w_reg, A.dp_t ? __ldg(A.pos_t + row) : 0u, A.dq_r ? __ldg(A.pos_r + A.b.B * (int64_t)H + row) : 0u, i % D,
+               dpacc[i]);
+    }
   }
 
   // ---- flush this CTA's parameter partials --------------------------------------------------------------------------
@@ -518,11 +523,11 @@ __global__ void param_reduce_kernel(const float* __restrict__ parts, int n_parts
   }
 }
 
-// Keys for the three gathers.  src encodes where the contribution row lives: cell index (dq) or B*H + row (dp).
+// Keys of the three embedding-row reductions.  src encodes where a contribution row comes from: cell index (dq) or B*H + row (dp).
 // An id outside its table gets the key `n_rows` (one past the last row): it sorts behind every real row and the segment
 // reduce drops it, so no table / optimizer row is written for it (the kernels that read it raised the bad-index word).
 __device__ __forceinline__ int key_of(int64_t id, int n_rows) { return (uint64_t)id < (uint64_t)n_rows ? (int)id : n_rows; }
-__global__ void make_keys_kernel(NaisPairs b, int want_reg, int item_num, int region_num, int* k_hist, uint32_t* v_hist, int* k_tgt,
+__global__ void make_keys_kernel(NaisPairs b, int item_num, int region_num, int* k_hist, uint32_t* v_hist, int* k_tgt,
                                  uint32_t* v_tgt, int* k_reg, uint32_t* v_reg) {
   const int64_t n_cells = b.B * (int64_t)b.H;
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -531,7 +536,7 @@ __global__ void make_keys_kernel(NaisPairs b, int want_reg, int item_num, int re
       k_hist[i] = key_of(b.hist[i], item_num);
       v_hist[i] = (uint32_t)i;
     }
-    if (want_reg) {
+    if (k_reg) {
       k_reg[i] = key_of(b.hreg[i], region_num);
       v_reg[i] = (uint32_t)i;
     }
@@ -539,21 +544,31 @@ __global__ void make_keys_kernel(NaisPairs b, int want_reg, int item_num, int re
   if (i < b.B) {
     if (k_tgt) {
       k_tgt[i] = key_of(b.tgt[i], item_num);
-      v_tgt[i] = (uint32_t)(n_cells + i);
+      v_tgt[i] = (uint32_t)i;
     }
-    if (want_reg) {
+    if (k_reg) {
       k_reg[n_cells + i] = key_of(b.treg[i], region_num);
       v_reg[n_cells + i] = (uint32_t)(n_cells + i);
     }
   }
 }
 
-// Embedding-row gradients: out[key, 0:w] = sum of the contribution rows of every sorted entry with that key.
-// Two deterministic passes, no atomics:
-//   pass 1  one warp per chunk of SEG_CHUNK consecutive sorted entries accumulates runs of equal keys in order;
-//           a run that lies strictly inside its chunk is complete and is written to the table row directly, the
-//           (at most two) runs that touch a chunk boundary go to partial slots [2*chunk] (first run) / [2*chunk+1]
-//           (last run) together with a flag saying whether the run STARTS in this chunk;
+// pos[src] = rank of that contribution in key order (the inverse of the sorted source lists): where the backward tile kernel
+// writes the row.
+__global__ void invert_perm_kernel(const uint32_t* __restrict__ s_hist, int64_t n_hist, uint32_t* pos_h, const uint32_t* __restrict__ s_tgt,
+                                   int64_t n_tgt, uint32_t* pos_t, const uint32_t* __restrict__ s_reg, int64_t n_reg, uint32_t* pos_r) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (s_hist && i < n_hist) pos_h[s_hist[i]] = (uint32_t)i;
+  if (s_tgt && i < n_tgt) pos_t[s_tgt[i]] = (uint32_t)i;
+  if (s_reg && i < n_reg) pos_r[s_reg[i]] = (uint32_t)i;
+}
+
+// Embedding-row gradients: out[key, 0:w] = sum of the contribution rows of every sorted entry with that key; entry i's row is
+// rows[i, 0:w] (the tile kernel wrote it there).  Two deterministic passes, no atomics:
+//   pass 1  one warp per chunk of SEG_CHUNK consecutive entries accumulates runs of equal keys in order; a run that lies
+//           strictly inside its chunk is complete and is written to the table row directly, the (at most two) runs that touch
+//           a chunk boundary go to partial slots [2*chunk] (first run) / [2*chunk+1] (last run) together with a flag saying
+//           whether the run STARTS in this chunk;
 //   pass 2  one warp per starting partial adds the following chunks' continuing first-run partials, in chunk order.
 constexpr int SEG_CHUNK = 64;
 
@@ -576,18 +591,15 @@ __device__ __forceinline__ void seg_store(const SegOut& o, size_t idx, float g) 
   }
 }
 
-__device__ __forceinline__ const float* seg_row(uint32_t s, int64_t n_cells, const float* ws_dq, const float* ws_dp, int D) {
-  return (s < n_cells) ? ws_dq + (size_t)s * D : ws_dp + (size_t)(s - n_cells) * D;
-}
-
-// Pass 1 is a gather of 128-byte .. 512-byte rows in sorted order — HBM-bound once enough loads are in flight: the chunk's keys /
-// sources are read once (coalesced, two per lane) and handed around by shuffles, and the rows are fetched SEG_ILP at a time
-// before the (serial, branchy) run bookkeeping touches them.  (r1: one row load in flight per warp = 20 % of the HBM peak.)
+// Pass 1 streams the rows in order (a chunk is SEG_CHUNK * w * 4 contiguous bytes).  r2 profile of the first version (one
+// shuffle + compare + branch + four predicated loads / adds per entry): 50 warp instructions per entry, issue-bound at 1.8 TB/s.
+// Now: the chunk's 64 keys sit two per lane, ONE pair of ballots marks where runs start, and each run is a branch-free
+// accumulation of its rows (SEG_ILP loads in flight, added in entry order: same sums, bit for bit) — ~4 instructions per entry.
+// NQ = ceil(w / 32) floats per lane (w <= 128).
 constexpr int SEG_ILP = 8;
-__global__ void segment_reduce_pass1_kernel(const int* __restrict__ keys, const uint32_t* __restrict__ src, int64_t n,
-                                            int64_t n_cells, const float* __restrict__ ws_dq,
-                                            const float* __restrict__ ws_dp, int D, int off, int w, int n_rows, SegOut out,
-                                            int* __restrict__ part_key, int* __restrict__ part_start,
+template <int NQ>
+__global__ void segment_reduce_pass1_kernel(const int* __restrict__ keys, int64_t n, const float* __restrict__ rows, int w, int n_rows,
+                                            SegOut out, int* __restrict__ part_key, int* __restrict__ part_start,
                                             float* __restrict__ part_rows) {
   const int64_t chunk = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -596,71 +608,63 @@ __global__ void segment_reduce_pass1_kernel(const int* __restrict__ keys, const 
   const int64_t end = min(n, start + SEG_CHUNK);
   const int cnt = (int)(end - start);
   if (lane < 2) part_key[2 * chunk + lane] = -1;
-  // this lane's two entries of the chunk, and the neighbours' keys that decide whether a boundary run continues
-  int kreg[2];
-  uint32_t sreg[2];
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int64_t i = start + lane + 32 * q;
-    kreg[q] = i < end ? keys[i] : -1;
-    sreg[q] = i < end ? src[i] : 0u;
-  }
+  const int k0 = lane < cnt ? keys[start + lane] : -1, k1 = 32 + lane < cnt ? keys[start + 32 + lane] : -1;
   const int key_before = start > 0 ? keys[start - 1] : -1, key_after = end < n ? keys[end] : -1;
-  __syncwarp();
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  int cur = __shfl_sync(0xffffffffu, kreg[0], 0);
-  bool first = true;
-  auto flush = [&](bool last) {
-    if (cur >= n_rows) return;  // ids outside the table (make_keys_kernel): dropped
-    const bool left = first && cur == key_before;
-    const bool right = last && cur == key_after;
-    if (!left && !right) {
+  // bit j of `starts` = entry j begins a run (entry 0 always does)
+  const int p0 = __shfl_up_sync(0xffffffffu, k0, 1), last0 = __shfl_sync(0xffffffffu, k0, 31), p1 = __shfl_up_sync(0xffffffffu, k1, 1);
+  const unsigned m0 = __ballot_sync(0xffffffffu, lane < cnt && (lane == 0 || k0 != p0));
+  const unsigned m1 = __ballot_sync(0xffffffffu, 32 + lane < cnt && k1 != (lane == 0 ? last0 : p1));
+  const unsigned long long starts = (unsigned long long)m0 | ((unsigned long long)m1 << 32);
+  const float* base = rows + (size_t)start * w;
+  bool col[NQ];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (lane + 32 * i < w) seg_store(out, (size_t)cur * w + lane + 32 * i, acc[i]);
-    } else {
-      const int64_t slot = 2 * chunk + (first ? 0 : 1);
-      if (lane == 0) {
-        part_key[slot] = cur;
-        part_start[slot] = left ? 0 : 1;
-      }
+  for (int q = 0; q < NQ; ++q) col[q] = lane + 32 * q < w;
+  int a = 0;
+  while (a < cnt) {
+    const unsigned long long rest = a + 1 < 64 ? (starts >> (a + 1)) : 0ull;
+    const int b = rest ? a + 1 + __ffsll((long long)rest) - 1 : cnt;  // the run is [a, b)
+    const int key = a < 32 ? __shfl_sync(0xffffffffu, k0, a) : __shfl_sync(0xffffffffu, k1, a - 32);
+    float acc[NQ];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (lane + 32 * i < w) part_rows[(size_t)slot * w + lane + 32 * i] = acc[i];
+    for (int q = 0; q < NQ; ++q) acc[q] = 0.f;
+    for (int j0 = a; j0 < b; j0 += SEG_ILP) {
+      float r[SEG_ILP][NQ];
+#pragma unroll
+      for (int u = 0; u < SEG_ILP; ++u)
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) r[u][q] = (j0 + u < b && col[q]) ? __ldcs(base + (size_t)(j0 + u) * w + lane + 32 * q) : 0.f;
+#pragma unroll
+      for (int u = 0; u < SEG_ILP; ++u)
+        if (j0 + u < b) {  // (skipped, not "+ 0": -0.f + 0.f would flip a sign bit the serial sum keeps)
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) acc[q] += r[u][q];
+        }
     }
-  };
-  for (int j0 = 0; j0 < cnt; j0 += SEG_ILP) {
-    float rows[SEG_ILP][4];
+    if (key < n_rows) {  // ids outside the table (make_keys_kernel) are dropped
+      const bool left = a == 0 && key == key_before, right = b == cnt && key == key_after;
+      if (!left && !right) {
 #pragma unroll
-    for (int u = 0; u < SEG_ILP; ++u) {
-      const int j = j0 + u;
-      const uint32_t sj = __shfl_sync(0xffffffffu, (j & 32) ? sreg[1] : sreg[0], j & 31);
-      if (j < cnt) {
-        const float* row = seg_row(sj, n_cells, ws_dq, ws_dp, D) + off;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) rows[u][q] = (lane + 32 * q < w) ? __ldg(row + lane + 32 * q) : 0.f;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < SEG_ILP; ++u) {
-      const int j = j0 + u;
-      const int k = __shfl_sync(0xffffffffu, (j & 32) ? kreg[1] : kreg[0], j & 31);
-      if (j < cnt) {
-        if (k != cur) {
-          flush(false);
-          first = false;
-          cur = k;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) acc[q] = 0.f;
+        for (int q = 0; q < NQ; ++q)
+          if (col[q]) seg_store(out, (size_t)key * w + lane + 32 * q, acc[q]);
+      } else {
+        const int64_t slot = 2 * chunk + (a == 0 ? 0 : 1);
+        if (lane == 0) {
+          part_key[slot] = key;
+          part_start[slot] = left ? 0 : 1;
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[q] += rows[u][q];
+        for (int q = 0; q < NQ; ++q)
+          if (col[q]) part_rows[(size_t)slot * w + lane + 32 * q] = acc[q];
       }
     }
+    a = b;
   }
-  flush(true);
 }
 
+// Pass 2: one warp per partial that STARTS a run; the chunks that continue it are found 32 at a time (one ballot, no chain of
+// dependent loads: a hot row spanning hundreds of chunks used to be one warp walking them one by one) and their partial rows
+// are added in chunk order.
+template <int NQ>
 __global__ void segment_reduce_pass2_kernel(const int* __restrict__ part_key, const int* __restrict__ part_start,
                                             const float* __restrict__ part_rows, int64_t n_chunks, int w, SegOut out) {
   const int64_t slot = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -668,24 +672,43 @@ __global__ void segment_reduce_pass2_kernel(const int* __restrict__ part_key, co
   if (slot >= 2 * n_chunks) return;
   const int key = part_key[slot];
   if (key < 0 || !part_start[slot]) return;
-  float acc[4];
+  bool col[NQ];
+  float acc[NQ];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) acc[i] = (lane + 32 * i < w) ? part_rows[(size_t)slot * w + lane + 32 * i] : 0.f;
-  for (int64_t c = (slot >> 1) + 1; c < n_chunks && part_key[2 * c] == key && !part_start[2 * c]; ++c) {
+  for (int q = 0; q < NQ; ++q) {
+    col[q] = lane + 32 * q < w;
+    acc[q] = col[q] ? part_rows[(size_t)slot * w + lane + 32 * q] : 0.f;
+  }
+  for (int64_t c0 = (slot >> 1) + 1; c0 < n_chunks; c0 += 32) {
+    const int64_t c = c0 + lane;
+    const bool cont = c < n_chunks && part_key[2 * c] == key && !part_start[2 * c];
+    const unsigned m = __ballot_sync(0xffffffffu, cont);
+    const int len = (m == 0xffffffffu) ? 32 : __ffs((int)~m) - 1;  // contiguous prefix of continuing chunks
+    for (int j0 = 0; j0 < len; j0 += SEG_ILP) {
+      float r[SEG_ILP][NQ];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (lane + 32 * i < w) acc[i] += part_rows[(size_t)(2 * c) * w + lane + 32 * i];
+      for (int u = 0; u < SEG_ILP; ++u)
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) r[u][q] = (j0 + u < len && col[q]) ? part_rows[(size_t)(2 * (c0 + j0 + u)) * w + lane + 32 * q] : 0.f;
+#pragma unroll
+      for (int u = 0; u < SEG_ILP; ++u)
+        if (j0 + u < len) {
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) acc[q] += r[u][q];
+        }
+    }
+    if (len < 32) break;
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    if (lane + 32 * i < w) seg_store(out, (size_t)key * w + lane + 32 * i, acc[i]);
+  for (int q = 0; q < NQ; ++q)
+    if (col[q]) seg_store(out, (size_t)key * w + lane + 32 * q, acc[q]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct BwdLayout {
-  size_t dq, dp, part, keys[8], cub, pkey, pstart, prows, total;
+  size_t dq_h, dq_r, dp_t, part, kin[3], vin[3], kout[3], vout[3], pos[3], cub, pkey, pstart, prows, total;
   int64_t n_chunks;
   int grid, stride;
   size_t cub_bytes;
@@ -693,24 +716,37 @@ struct BwdLayout {
 
 static int bwd_grid() { return 148 * 2; }
 
+// lists: 0 = history ids (B*H entries), 1 = target ids (B), 2 = region ids of both (B*H + B)
 static BwdLayout bwd_layout(const NaisParams& p, int64_t B, int H) {
   BwdLayout L;
-  int D = 0;
-  for (int i = 0; i < p.n_branch; ++i) D = D > p.branch[i].w_poi + p.branch[i].w_reg ? D : p.branch[i].w_poi + p.branch[i].w_reg;
+  int D = 0, w_poi = 0, w_reg = 0;
+  for (int i = 0; i < p.n_branch; ++i) {
+    const NaisBranch& br = p.branch[i];
+    D = D > br.w_poi + br.w_reg ? D : br.w_poi + br.w_reg;
+    w_poi = w_poi > br.w_poi ? w_poi : br.w_poi;
+    w_reg = w_reg > br.w_reg ? w_reg : br.w_reg;
+  }
   const int lanes = p.dist_mode == NAIS_DIST_LATLON ? 2 : 0;
   const int64_t n_cells = B * H, n_max = n_cells + B;
+  const int64_t n_of[3] = {n_cells, B, n_max};
   size_t o = 0;
-  L.dq = o;
-  o += align_up((size_t)n_cells * D * 4);
-  L.dp = o;
-  o += align_up((size_t)B * D * 4);
+  L.dq_h = o;
+  o += align_up((size_t)n_cells * w_poi * 4);
+  L.dq_r = o;
+  o += align_up((size_t)n_max * w_reg * 4);
+  L.dp_t = o;
+  o += align_up((size_t)B * w_poi * 4);
   L.grid = bwd_grid();
   L.stride = part_floats(p.hid, D, lanes);
   L.part = o;
   o += align_up((size_t)L.grid * L.stride * 4);
-  for (int i = 0; i < 8; ++i) {  // three (keys, sources) input lists + one sorted output pair, each sized for the largest list
-    L.keys[i] = o;
-    o += align_up((size_t)n_max * 4);
+  for (int i = 0; i < 3; ++i) {
+    const size_t bytes = align_up((size_t)n_of[i] * 4);
+    L.kin[i] = o, o += bytes;
+    L.vin[i] = o, o += bytes;
+    L.kout[i] = o, o += bytes;
+    L.vout[i] = o, o += bytes;
+    L.pos[i] = o, o += bytes;
   }
   size_t cb = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, cb, (const int*)nullptr, (int*)nullptr, (const uint32_t*)nullptr,
@@ -719,12 +755,13 @@ static BwdLayout bwd_layout(const NaisParams& p, int64_t B, int H) {
   L.cub = o;
   o += align_up(cb);
   L.n_chunks = (n_max + SEG_CHUNK - 1) / SEG_CHUNK;
+  const int wmax = w_poi > w_reg ? w_poi : w_reg;
   L.pkey = o;
   o += align_up((size_t)2 * L.n_chunks * 4);
   L.pstart = o;
   o += align_up((size_t)2 * L.n_chunks * 4);
   L.prows = o;
-  o += align_up((size_t)2 * L.n_chunks * D * 4);
+  o += align_up((size_t)2 * L.n_chunks * wmax * 4);
   L.total = o;
   return L;
 }
@@ -745,8 +782,8 @@ static int launch_bwd_tile(const BwdArgs& A, int D, int grid, cudaStream_t strea
 }
 
 int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score_parts, const float* row_sum,
-                     const float* dscore, const NaisGrads& g, const NaisAdagrad* opt, void* ws, size_t ws_bytes,
-                     cudaStream_t stream) {
+                     const unsigned long long* act_mask, const float* dscore, const NaisGrads& g, const NaisAdagrad* opt, void* ws,
+                     size_t ws_bytes, cudaStream_t stream) {
   if (b.B * (int64_t)b.H + b.B >= 0x7fffffffLL) return NAIS_ERR_SHAPE;
   if (opt && p.n_branch != 1) return NAIS_ERR_MODE;  // two branches share tables: two sparse steps != one dense step
   const BwdLayout L = bwd_layout(p, b.B, b.H);
@@ -754,17 +791,40 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
   char* base = reinterpret_cast<char*>(ws);
   const int lanes = p.dist_mode == NAIS_DIST_LATLON ? 2 : 0;
   const int64_t n_cells = b.B * (int64_t)b.H;
-  int* kin = reinterpret_cast<int*>(base + L.keys[0]);
-  uint32_t* vin = reinterpret_cast<uint32_t*>(base + L.keys[1]);
-  int* kout = reinterpret_cast<int*>(base + L.keys[2]);
-  uint32_t* vout = reinterpret_cast<uint32_t*>(base + L.keys[3]);
-  int* kin2 = reinterpret_cast<int*>(base + L.keys[4]);
-  uint32_t* vin2 = reinterpret_cast<uint32_t*>(base + L.keys[5]);
+  const int64_t n_of[3] = {n_cells, b.B, n_cells + b.B};
+  auto I = [&](size_t off) { return reinterpret_cast<int*>(base + off); };
+  auto U = [&](size_t off) { return reinterpret_cast<uint32_t*>(base + off); };
 
   for (int bi = 0; bi < p.n_branch; ++bi) {
     const NaisBranch& br = p.branch[bi];
     const int D = br.w_poi + br.w_reg;
     if (D > 128 || p.hid > 128) return NAIS_ERR_SHAPE;  // backward tiles: D, hid <= 128 in this version
+    // a table is processed if it has a gradient destination or a fused-optimizer state
+    const bool want[3] = {br.w_poi > 0 && (g.hist_poi[bi] || (opt && opt->sum_hist_poi[bi])),
+                          br.w_poi > 0 && (g.tgt_poi[bi] || (opt && opt->sum_tgt_poi[bi])),
+                          br.w_reg > 0 && (g.reg[bi] || (opt && opt->sum_reg[bi]))};
+    // ---- 1. sort the ids, invert the permutations: every contribution row gets its slot in key order -----------------------
+    if (want[0] || want[1] || want[2]) {
+      const int64_t n_thr = n_cells > b.B ? n_cells : b.B;
+      make_keys_kernel<<<(unsigned)((n_thr + 255) / 256), 256, 0, stream>>>(
+          b, p.item_num, p.region_num, want[0] ? I(L.kin[0]) : nullptr, U(L.vin[0]), want[1] ? I(L.kin[1]) : nullptr, U(L.vin[1]),
+          want[2] ? I(L.kin[2]) : nullptr, U(L.vin[2]));
+      NAIS_COUNT_LAUNCH(1);
+      size_t cb = L.cub_bytes;
+      for (int t = 0; t < 3; ++t) {
+        if (!want[t]) continue;
+        const int n_rows = t == 2 ? p.region_num : p.item_num;
+        int bits = 1;  // keys are 0 .. n_rows (n_rows = the "drop" key of an out-of-range id)
+        while ((1ll << bits) <= n_rows && bits < 31) ++bits;
+        cub::DeviceRadixSort::SortPairs(base + L.cub, cb, I(L.kin[t]), I(L.kout[t]), U(L.vin[t]), U(L.vout[t]), (int)n_of[t], 0, bits,
+                                        stream);
+      }
+      invert_perm_kernel<<<(unsigned)((n_of[2] + 255) / 256), 256, 0, stream>>>(
+          want[0] ? U(L.vout[0]) : nullptr, n_of[0], U(L.pos[0]), want[1] ? U(L.vout[1]) : nullptr, n_of[1], U(L.pos[1]),
+          want[2] ? U(L.vout[2]) : nullptr, n_of[2], U(L.pos[2]));
+      NAIS_COUNT_LAUNCH(1);
+    }
+    // ---- 2. the tile kernel ------------------------------------------------------------------------------------------------
     BwdArgs A;
     A.p = p;
     A.b = b;
@@ -772,8 +832,13 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
     A.parts = score_parts + (size_t)bi * b.B;
     A.row_sum = row_sum + (size_t)bi * b.B;
     A.dscore = dscore;
-    A.ws_dq = reinterpret_cast<float*>(base + L.dq);
-    A.ws_dp = reinterpret_cast<float*>(base + L.dp);
+    A.act_mask = (p.n_branch == 1 && p.hid <= 64) ? act_mask : nullptr;
+    A.dq_h = want[0] ? reinterpret_cast<float*>(base + L.dq_h) : nullptr;
+    A.dp_t = want[1] ? reinterpret_cast<float*>(base + L.dp_t) : nullptr;
+    A.dq_r = want[2] ? reinterpret_cast<float*>(base + L.dq_r) : nullptr;
+    A.pos_h = U(L.pos[0]);
+    A.pos_t = U(L.pos[1]);
+    A.pos_r = U(L.pos[2]);
     A.ws_part = reinterpret_cast<float*>(base + L.part);
     A.part_stride = L.stride;
     int rpt = (b.H <= TC) ? TC / b.H : 1;
@@ -798,13 +863,9 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
                                                               g.w2[bi], bi == 0 ? g.dist_w : nullptr,
                                                               bi == 0 ? g.dist_b : nullptr,
                                                               p.dist_mode == NAIS_DIST_KM ? g.dist_embed : nullptr, D, bi > 0);
-  NAIS_COUNT_LAUNCH(1);
+      NAIS_COUNT_LAUNCH(1);
     }
-    // embedding rows
-    // a table is processed if it has a gradient destination or a fused-optimizer state
-    const bool want_hist = br.w_poi > 0 && (g.hist_poi[bi] || (opt && opt->sum_hist_poi[bi]));
-    const bool want_tgt = br.w_poi > 0 && (g.tgt_poi[bi] || (opt && opt->sum_tgt_poi[bi]));
-    const bool want_reg = br.w_reg > 0 && (g.reg[bi] || (opt && opt->sum_reg[bi]));
+    // ---- 3. embedding rows: stream the key-ordered contribution rows ----------------------------------------------------------
     auto dest = [&](float* grad, const float* param, float* sum) {
       SegOut o;
       o.out = grad;
@@ -814,32 +875,29 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
       o.eps = opt ? opt->eps : 0.f;
       return o;
     };
-    const int64_t n_thr = n_cells > b.B ? n_cells : b.B;
-    int* kin3 = reinterpret_cast<int*>(base + L.keys[6]);
-    uint32_t* vin3 = reinterpret_cast<uint32_t*>(base + L.keys[7]);
-    make_keys_kernel<<<(unsigned)((n_thr + 255) / 256), 256, 0, stream>>>(b, want_reg ? 1 : 0, p.item_num, p.region_num,
-                                                                         want_hist ? kin : nullptr, vin, want_tgt ? kin2 : nullptr,
-                                                                         vin2, kin3, vin3);
-    NAIS_COUNT_LAUNCH(1);
-    size_t cb = L.cub_bytes;
-    auto seg = [&](int* ki, uint32_t* vi, int64_t n, int off, int w, int n_rows, SegOut out) {
-      int bits = 1;  // keys are 0 .. n_rows (n_rows = the "drop" key of an out-of-range id)
-      while ((1ll << bits) <= n_rows && bits < 31) ++bits;
-      cub::DeviceRadixSort::SortPairs(base + L.cub, cb, ki, kout, vi, vout, (int)n, 0, bits, stream);
+    auto seg = [&](int t, const float* rows, int w, int n_rows, SegOut out) {
+      const int64_t n = n_of[t];
       const int64_t nch = (n + SEG_CHUNK - 1) / SEG_CHUNK;
-      int* pk = reinterpret_cast<int*>(base + L.pkey);
-      int* pst = reinterpret_cast<int*>(base + L.pstart);
+      int* pk = I(L.pkey);
+      int* pst = I(L.pstart);
       float* pr = reinterpret_cast<float*>(base + L.prows);
-      segment_reduce_pass1_kernel<<<(unsigned)((nch * 32 + 255) / 256), 256, 0, stream>>>(kout, vout, n, n_cells, A.ws_dq, A.ws_dp,
-                                                                                        D, off, w, n_rows, out, pk, pst, pr);
-      NAIS_COUNT_LAUNCH(1);
-      segment_reduce_pass2_kernel<<<(unsigned)((2 * nch * 32 + 255) / 256), 256, 0, stream>>>(pk, pst, pr, nch, w, out);
-      NAIS_COUNT_LAUNCH(1);
+      const unsigned g1 = (unsigned)((nch * 32 + 255) / 256), g2 = (unsigned)((2 * nch * 32 + 255) / 256);
+      if (w <= 32) {
+        segment_reduce_pass1_kernel<1><<<g1, 256, 0, stream>>>(I(L.kout[t]), n, rows, w, n_rows, out, pk, pst, pr);
+        segment_reduce_pass2_kernel<1><<<g2, 256, 0, stream>>>(pk, pst, pr, nch, w, out);
+      } else if (w <= 64) {
+        segment_reduce_pass1_kernel<2><<<g1, 256, 0, stream>>>(I(L.kout[t]), n, rows, w, n_rows, out, pk, pst, pr);
+        segment_reduce_pass2_kernel<2><<<g2, 256, 0, stream>>>(pk, pst, pr, nch, w, out);
+      } else {
+        segment_reduce_pass1_kernel<4><<<g1, 256, 0, stream>>>(I(L.kout[t]), n, rows, w, n_rows, out, pk, pst, pr);
+        segment_reduce_pass2_kernel<4><<<g2, 256, 0, stream>>>(pk, pst, pr, nch, w, out);
+      }
+      NAIS_COUNT_LAUNCH(2);
     };
-    if (want_hist) seg(kin, vin, n_cells, 0, br.w_poi, p.item_num, dest(g.hist_poi[bi], br.hist_poi, opt ? opt->sum_hist_poi[bi] : nullptr));
-    if (want_tgt) seg(kin2, vin2, b.B, 0, br.w_poi, p.item_num, dest(g.tgt_poi[bi], br.tgt_poi, opt ? opt->sum_tgt_poi[bi] : nullptr));
+    if (want[0]) seg(0, A.dq_h, br.w_poi, p.item_num, dest(g.hist_poi[bi], br.hist_poi, opt ? opt->sum_hist_poi[bi] : nullptr));
+    if (want[1]) seg(1, A.dp_t, br.w_poi, p.item_num, dest(g.tgt_poi[bi], br.tgt_poi, opt ? opt->sum_tgt_poi[bi] : nullptr));
     // (history-side and target-side region rows are one table in every variant: hist_reg == tgt_reg)
-    if (want_reg) seg(kin3, vin3, n_cells + b.B, br.w_poi, br.w_reg, p.region_num, dest(g.reg[bi], br.hist_reg, opt ? opt->sum_reg[bi] : nullptr));
+    if (want[2]) seg(2, A.dq_r, br.w_reg, p.region_num, dest(g.reg[bi], br.hist_reg, opt ? opt->sum_reg[bi] : nullptr));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }

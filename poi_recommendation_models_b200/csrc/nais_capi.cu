@@ -19,8 +19,9 @@ int choose_splits(int n_users, int64_t range);
 // nais_bwd.cu
 size_t pairs_bwd_workspace_bytes(const NaisParams& p, int64_t B, int H);
 int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score_parts, const float* row_sum,
-                     const float* dscore, const NaisGrads& g, const NaisAdagrad* opt, void* ws, size_t ws_bytes,
-                     cudaStream_t stream);
+                     const unsigned long long* act_mask, const float* dscore, const NaisGrads& g, const NaisAdagrad* opt, void* ws,
+                     size_t ws_bytes, cudaStream_t stream);
+bool pairs_tc_bwd_supported(const NaisParams& p, const NaisPairs& b);
 // nais_tc.cu
 size_t fullrank_tc_workspace_bytes(const NaisParams& p, int n_users, int64_t nnz, int64_t poi_begin, int64_t poi_end, int k,
                                    int precision);
@@ -38,7 +39,8 @@ int fullrank_tc_run(const NaisParams& p, const NaisCatalog& cat, const NaisUsers
                     int32_t* out_id, float* all_scores, void* ws, size_t ws_bytes, cudaStream_t stream);
 // nais_pairs_tc.cu
 bool pairs_tc_supported(const NaisParams& p, const NaisPairs& b);
-int launch_pairs_fwd_tc(const NaisParams& p, const NaisPairs& b, float* score, float* row_sum, float* parts, cudaStream_t stream);
+int launch_pairs_fwd_tc(const NaisParams& p, const NaisPairs& b, float* score, float* row_sum, float* parts,
+                        unsigned long long* act_mask, cudaStream_t stream);
 }  // namespace nais
 
 namespace nais {
@@ -189,18 +191,40 @@ const char* nais_strerror(int code) {
   return "nais: unknown error";
 }
 
+static bool device_is_sm100() {
+  int dev = 0, major = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  return major == 10;
+}
+
+int nais_pairs_dispatch(const NaisParams* p, const NaisPairs* batch, int32_t* fwd_tc, int32_t* bwd_tc) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  if (!batch || !fwd_tc || !bwd_tc) return NAIS_ERR_NULL;
+  if (batch->B < 0 || batch->H < 1) return NAIS_ERR_SHAPE;
+  NaisPairs b = *batch;
+  if (b.B == 0) b.B = 1;  // the choice does not depend on the row count
+  const bool f_ok = pairs_tc_supported(*p, b) && device_is_sm100(), b_ok = pairs_tc_bwd_supported(*p, b);
+  if (p->pairs_precision == NAIS_PAIRS_TC && !f_ok) return NAIS_ERR_SHAPE;  // (a forced tcgen05 backward reports its own shape error)
+  *fwd_tc = (p->pairs_precision != NAIS_PAIRS_FP32 && f_ok) ? 1 : 0;
+  *bwd_tc = (p->pairs_precision != NAIS_PAIRS_FP32 && b_ok) ? 1 : 0;
+  return 0;
+}
+
 int nais_pairs_forward(const NaisParams* p, const NaisPairs* batch, float* score, float* row_sum, float* score_parts,
-                       nais_stream_t stream) {
+                       uint64_t* act_mask, nais_stream_t stream) {
   int rc = check_params(p);
   if (rc) return rc;
   rc = check_pairs(p, batch);
   if (rc) return rc;
   if (batch->B && !score) return NAIS_ERR_NULL;
   if (batch->B == 0) return 0;
-  const bool tc_ok = pairs_tc_supported(*p, *batch);
+  const bool tc_ok = pairs_tc_supported(*p, *batch) && device_is_sm100();
   if (p->pairs_precision == NAIS_PAIRS_TC && !tc_ok) return NAIS_ERR_SHAPE;
   if (p->pairs_precision != NAIS_PAIRS_FP32 && tc_ok)  // tcgen05 contraction (fp16 two-term splits): fp32-grade products
-    return launch_pairs_fwd_tc(*p, *batch, score, row_sum, score_parts, static_cast<cudaStream_t>(stream));
+    return launch_pairs_fwd_tc(*p, *batch, score, row_sum, score_parts, reinterpret_cast<unsigned long long*>(act_mask),
+                               static_cast<cudaStream_t>(stream));
   return launch_pairs_fwd(*p, *batch, score, row_sum, score_parts, static_cast<cudaStream_t>(stream));
 }
 
@@ -210,8 +234,8 @@ size_t nais_pairs_backward_workspace_bytes(const NaisParams* p, int64_t B, int32
 }
 
 int nais_pairs_backward(const NaisParams* p, const NaisPairs* batch, const float* score_parts, const float* row_sum,
-                        const float* dscore, const NaisGrads* grads, void* workspace, size_t workspace_bytes,
-                        nais_stream_t stream) {
+                        const uint64_t* act_mask, const float* dscore, const NaisGrads* grads, void* workspace,
+                        size_t workspace_bytes, nais_stream_t stream) {
   int rc = check_params(p);
   if (rc) return rc;
   rc = check_pairs(p, batch);
@@ -221,13 +245,13 @@ int nais_pairs_backward(const NaisParams* p, const NaisPairs* batch, const float
   if (!score_parts || !row_sum || !dscore || !workspace) return NAIS_ERR_NULL;
   if (!aligned16(workspace)) return NAIS_ERR_ALIGN;
   if (workspace_bytes < pairs_bwd_workspace_bytes(*p, batch->B, batch->H)) return NAIS_ERR_WORKSPACE;
-  return launch_pairs_bwd(*p, *batch, score_parts, row_sum, dscore, *grads, nullptr, workspace, workspace_bytes,
-                          static_cast<cudaStream_t>(stream));
+  return launch_pairs_bwd(*p, *batch, score_parts, row_sum, reinterpret_cast<const unsigned long long*>(act_mask), dscore, *grads,
+                          nullptr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int nais_pairs_backward_adagrad(const NaisParams* p, const NaisPairs* batch, const float* score_parts, const float* row_sum,
-                                const float* dscore, const NaisGrads* grads, const NaisAdagrad* opt, void* workspace,
-                                size_t workspace_bytes, nais_stream_t stream) {
+                                const uint64_t* act_mask, const float* dscore, const NaisGrads* grads, const NaisAdagrad* opt,
+                                void* workspace, size_t workspace_bytes, nais_stream_t stream) {
   int rc = check_params(p);
   if (rc) return rc;
   rc = check_pairs(p, batch);
@@ -239,8 +263,8 @@ int nais_pairs_backward_adagrad(const NaisParams* p, const NaisPairs* batch, con
   if (!score_parts || !row_sum || !dscore || !workspace) return NAIS_ERR_NULL;
   if (!aligned16(workspace)) return NAIS_ERR_ALIGN;
   if (workspace_bytes < pairs_bwd_workspace_bytes(*p, batch->B, batch->H)) return NAIS_ERR_WORKSPACE;
-  return launch_pairs_bwd(*p, *batch, score_parts, row_sum, dscore, *grads, opt, workspace, workspace_bytes,
-                          static_cast<cudaStream_t>(stream));
+  return launch_pairs_bwd(*p, *batch, score_parts, row_sum, reinterpret_cast<const unsigned long long*>(act_mask), dscore, *grads,
+                          opt, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 static int check_fullrank(const NaisParams* p, const NaisCatalog* cat, const NaisUsers* users, int64_t poi_begin,

@@ -30,6 +30,7 @@ struct Args {
   float* score;    // [B]
   float* row_sum;  // [B] or NULL
   float* parts;    // [B] or NULL
+  unsigned long long* act_mask;  // [B*H] ReLU pattern per cell (hid <= 64) or NULL
   int rows_per_tile;
   uint32_t tmem_cols;
   int* bad;  // the library's bad-index word (nais_common.cuh)
@@ -254,18 +255,24 @@ __global__ void __launch_bounds__(PT, (D > 48) ? 3 : 4) pairs_fwd_tc_kernel(cons
       tc_fence_after();
       // ---- epilogue: thread = cell = TMEM lane ------------------------------------------------------------------------------------
       float a = 0.f;
+      uint32_t act_lo = 0u, act_hi = 0u;  // ReLU pattern of this cell (hidden units 0..31 / 32..63), saved for the backward
       for (int c0 = 0; c0 < hid; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(tlane + c0, v);
         tmem_wait_ld16(v);
+        uint32_t bits = 0u;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int k = c0 + i;
           float t = fmaf(__uint_as_float(v[i]), inv, kc[k]);
           if (lanes) t = fmaf(kc[3 * hid + k], g1, fmaf(kc[2 * hid + k], g0, t));
+          bits |= (t > 0.f ? 1u : 0u) << i;
           a = fmaf(kc[hid + k], fmaxf(t, 0.f), a);
         }
+        if (c0 < 32) act_lo |= bits << c0;
+        else if (c0 < 64) act_hi |= bits << (c0 - 32);
       }
+      if (A.act_mask && valid) A.act_mask[cidx] = ((unsigned long long)act_hi << 32) | act_lo;
       tc_fence_before();  // TMEM reads ordered before the barrier that precedes the next tile's MMAs
       float e = 0.f, es = 0.f;
       if (live) {  // masked cells stay exactly 0 even if exp overflows (reference: exp_A * mask, then * history)
@@ -342,7 +349,8 @@ bool pairs_tc_supported(const NaisParams& p, const NaisPairs& b) {
   return true;
 }
 
-int launch_pairs_fwd_tc(const NaisParams& p, const NaisPairs& b, float* score, float* row_sum, float* parts, cudaStream_t stream) {
+int launch_pairs_fwd_tc(const NaisParams& p, const NaisPairs& b, float* score, float* row_sum, float* parts,
+                        unsigned long long* act_mask, cudaStream_t stream) {
   int dev = 0, major = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
@@ -354,6 +362,7 @@ int launch_pairs_fwd_tc(const NaisParams& p, const NaisPairs& b, float* score, f
   A.score = score;
   A.row_sum = row_sum;
   A.parts = parts;
+  A.act_mask = p.hid <= 64 ? act_mask : nullptr;
   A.bad = bad_index_flag();
   int rpt = (b.H <= ptc::PT) ? ptc::PT / b.H : 1;
   if (rpt > ptc::PMAXROWS) rpt = ptc::PMAXROWS;

@@ -171,7 +171,10 @@ __global__ void __launch_bounds__(PT, 2) pairs_bwd_tc_kernel(const __grid_consta
       int it32 = 0, rg32 = 0;
       float l0r = 0.f, l1r = 0.f;
       bool live = false;
+      uint32_t pos_h = 0u, pos_r = 0u;  // where this cell's dq halves go (key order); loaded early, used in epilogue 2
       if (valid) {
+        if (A.dq_h) pos_h = __ldg(A.pos_h + cidx);
+        if (A.dq_r) pos_r = __ldg(A.pos_r + cidx);
         it32 = checked_id(A.b.hist[cidx], p.item_num, A.bad);
         rg32 = br.w_reg ? checked_id(A.b.hreg[cidx], p.region_num, A.bad) : 0;
         if (lanes) {
@@ -253,6 +256,10 @@ __global__ void __launch_bounds__(PT, 2) pairs_bwd_tc_kernel(const __grid_consta
         dav = G * (w * ssum - p.beta * (e / S) * sc);
         gwv = G * w;
       }
+      // unit step of ReLU: the forward's saved pattern when there is one (its t is accurate to ~2e-7; this kernel's recomputed t,
+      // from bf16 two-term splits, only to ~1e-5 — a unit on the kink would flip and move the gradients by this cell's whole term)
+      const bool have_mask = A.act_mask != nullptr;
+      const unsigned long long am = (have_mask && valid) ? __ldg(A.act_mask + cidx) : 0ull;
       float dvv[HID];
       float dg0 = 0.f, dg1 = 0.f;
 #pragma unroll
@@ -267,7 +274,8 @@ __global__ void __launch_bounds__(PT, 2) pairs_bwd_tc_kernel(const __grid_consta
           float t = __uint_as_float(v[i]) + kc[k];
           if (lanes) t = fmaf(kc[3 * HID + k], g1, fmaf(kc[2 * HID + k], g0, t));
           dvv[k] = dav * fmaxf(t, 0.f);
-          dt[i] = (t > 0.f) ? dav * kc[HID + k] : 0.f;
+          const bool on = have_mask ? ((am >> k) & 1ull) != 0ull : t > 0.f;
+          dt[i] = on ? dav * kc[HID + k] : 0.f;
           dg0 = fmaf(dt[i], kc[2 * HID + k], dg0);
           dg1 = fmaf(dt[i], kc[3 * HID + k], dg1);
         }
@@ -359,7 +367,7 @@ __global__ void __launch_bounds__(PT, 2) pairs_bwd_tc_kernel(const __grid_consta
           if (valid) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4)
-              *reinterpret_cast<float4*>(A.ws_dq + cidx * D + s0 + c0 + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+              store_dq4(A, br.w_poi, br.w_reg, pos_h, pos_r, s0 + c0 + i, make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]));
           }
         }
       }
@@ -378,7 +386,11 @@ __global__ void __launch_bounds__(PT, 2) pairs_bwd_tc_kernel(const __grid_consta
       }
       __syncthreads();  // scratch (X image) and staging (DT image) are free again
     }
-    for (int i = tid; i < nrows * D; i += PT) A.ws_dp[(row0 + i / D) * D + (i % D)] = dpacc[i];
+    for (int i = tid; i < nrows * D; i += PT) {
+      const int64_t row = row0 + i / D;
+      store_dp(A, br.w_poi, br.w_reg, A.dp_t ? __ldg(A.pos_t + row) : 0u, A.dq_r ? __ldg(A.pos_r + A.b.B * (int64_t)H + row) : 0u, i % D,
+               dpacc[i]);
+    }
     __syncthreads();
   }
 

@@ -107,13 +107,13 @@ class _NAISBase(nn.Module):
             self.last_dropout_seed = drop[1]
         optimizer.zero_grad(set_to_none=True)
         with torch.no_grad():
-            score, row_sum, parts = ops.pairs_forward_raw(self.variant, float(self.beta), P, hist, tgt, hreg, treg, aux, drop)
+            score, row_sum, parts, mask = ops.pairs_forward_raw(self.variant, float(self.beta), P, hist, tgt, hreg, treg, aux, drop)
         s = score.detach().requires_grad_(True)  # dL/dscore through torch's own sigmoid + BCELoss ([B]-sized, exact semantics)
         loss = self.loss_func(torch.sigmoid(s), label)
         loss.backward()
         with torch.no_grad():
             G = ops.pairs_backward_adagrad(self.variant, float(self.beta), P, sums, lr, eps, hist, tgt, hreg, treg, aux, row_sum,
-                                           parts, s.grad, drop)
+                                           parts, s.grad, drop, act_mask=mask)
         for name, grad in G.items():
             P[name].grad = grad.to(P[name].dtype)
         optimizer.step()  # the tables have no .grad: torch skips them

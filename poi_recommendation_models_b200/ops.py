@@ -184,6 +184,33 @@ def _pairs_struct(hist, tgt, hreg, treg, aux, keep) -> NaisPairs:
     return b
 
 
+def pairs_dispatch(p: NaisParams, b: NaisPairs) -> Tuple[bool, bool]:
+    """(forward on tcgen05?, backward on tcgen05?) for these parameters and this batch (nais_pairs_dispatch)."""
+    f, g = C.c_int32(0), C.c_int32(0)
+    _lib.check(_lib.load().nais_pairs_dispatch(C.byref(p), C.byref(b), C.byref(f), C.byref(g)), "nais_pairs_dispatch")
+    return bool(f.value), bool(g.value)
+
+
+def _forward_launch(lib, p: NaisParams, b: NaisPairs, dev, want_mask: bool = True):
+    """nais_pairs_forward -> (score, row_sum, parts, act_mask): act_mask is the ReLU pattern the tcgen05 forward saves for the
+    tcgen05 backward (int64 [B*H]; None when the FP32 forward runs or hid > 64)."""
+    B = b.B
+    score = torch.empty(B, device=dev, dtype=torch.float32)
+    row_sum = torch.empty(p.n_branch, B, device=dev, dtype=torch.float32)
+    parts = torch.empty(p.n_branch, B, device=dev, dtype=torch.float32)
+    mask = None
+    if want_mask and B and p.n_branch == 1 and p.hid <= 64 and pairs_dispatch(p, b)[0]:
+        mask = torch.empty(B * b.H, device=dev, dtype=torch.int64)
+    _lib.check(lib.nais_pairs_forward(C.byref(p), C.byref(b), score.data_ptr(), row_sum.data_ptr(), parts.data_ptr(), _ptr(mask),
+                                      _stream()), "nais_pairs_forward")
+    return score, row_sum, parts, mask
+
+
+def _fwd_bwd(pairs_precision):
+    """`pairs_precision` is one name for both directions or a (forward, backward) pair."""
+    return (pairs_precision, pairs_precision) if isinstance(pairs_precision, str) else tuple(pairs_precision)
+
+
 class _PairsFunction(torch.autograd.Function):
     """score = attention_network(pairs).  forward -> nais_pairs_forward, backward -> nais_pairs_backward."""
 
@@ -195,59 +222,69 @@ class _PairsFunction(torch.autograd.Function):
         lib = _lib.load()
         keep: List[torch.Tensor] = []
         with torch.cuda.device(dev):
-            p = build_params(variant, P, beta, keep, *drop)
+            p = build_params(variant, P, beta, keep, drop[0], drop[1], _fwd_bwd(drop[2])[0])
             b = _pairs_struct(hist, tgt, hreg, treg, aux, keep)
-            B = b.B
-            score = torch.empty(B, device=dev, dtype=torch.float32)
-            row_sum = torch.empty(p.n_branch, B, device=dev, dtype=torch.float32)
-            parts = torch.empty(p.n_branch, B, device=dev, dtype=torch.float32)
-            _lib.check(lib.nais_pairs_forward(C.byref(p), C.byref(b), score.data_ptr(), row_sum.data_ptr(),
-                                              parts.data_ptr(), _stream()), "nais_pairs_forward")
+            need_bwd = any(t.requires_grad for t in params)
+            score, row_sum, parts, mask = _forward_launch(lib, p, b, dev, want_mask=need_bwd)
             _poll_bad_index(dev)
         ctx.variant, ctx.beta, ctx.drop = variant, beta, drop
         ctx.save_for_backward(hist, tgt, hreg if hreg is not None else torch.empty(0), treg if treg is not None else torch.empty(0),
-                              aux if aux is not None else torch.empty(0), row_sum, parts, *params)
-        ctx.has = (hreg is not None, treg is not None, aux is not None)
+                              aux if aux is not None else torch.empty(0), row_sum, parts,
+                              mask if mask is not None else torch.empty(0), *params)
+        ctx.has = (hreg is not None, treg is not None, aux is not None, mask is not None)
         return score
 
     @staticmethod
     def backward(ctx, dscore):
-        hist, tgt, hreg, treg, aux, row_sum, parts, *params = ctx.saved_tensors
+        hist, tgt, hreg, treg, aux, row_sum, parts, mask, *params = ctx.saved_tensors
         hreg = hreg if ctx.has[0] else None
         treg = treg if ctx.has[1] else None
         aux = aux if ctx.has[2] else None
-        variant = ctx.variant
-        names = VARIANT_PARAMS[variant]
+        mask = mask if ctx.has[3] else None
+        names = VARIANT_PARAMS[ctx.variant]
         P = dict(zip(names, params))
-        dev = dscore.device
-        lib = _lib.load()
-        keep: List[torch.Tensor] = []
-        with torch.cuda.device(dev):
-            p = build_params(variant, P, ctx.beta, keep, *ctx.drop)
-            b = _pairs_struct(hist, tgt, hreg, treg, aux, keep)
-            G = {n: torch.zeros_like(t, dtype=torch.float32, memory_format=torch.contiguous_format) for n, t in P.items()}
-            g = NaisGrads()
-            g.hist_poi[0], g.tgt_poi[0] = G["embed_history.weight"].data_ptr(), G["embed_target.weight"].data_ptr()
-            g.w1[0], g.b1[0], g.w2[0] = (G["attn_layer1.weight"].data_ptr(), G["attn_layer1.bias"].data_ptr(),
-                                         G["attn_layer2.weight"].data_ptr())
-            if variant in ("region", "region_distance"):
-                g.reg[0] = G["embed_region.weight"].data_ptr()
-            if "dist_layer.weight" in G:
-                g.dist_w, g.dist_b = G["dist_layer.weight"].data_ptr(), G["dist_layer.bias"].data_ptr()
-            if variant == "disentangled":
-                g.reg[1] = G["embed_region.weight"].data_ptr()
-                g.w1[1], g.b1[1], g.w2[1] = (G["region_attn_layer1.weight"].data_ptr(),
-                                             G["region_attn_layer1.bias"].data_ptr(),
-                                             G["region_attn_layer2.weight"].data_ptr())
-                g.dist_embed = G["embed_distance.weight"].data_ptr()
-            ws_bytes = lib.nais_pairs_backward_workspace_bytes(C.byref(p), b.B, b.H)
-            ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
-            ds = _f32(dscore)
-            _lib.check(lib.nais_pairs_backward(C.byref(p), C.byref(b), parts.data_ptr(), row_sum.data_ptr(), ds.data_ptr(),
-                                               C.byref(g), ws.data_ptr(), ws_bytes, _stream()), "nais_pairs_backward")
-            _poll_bad_index(dev)
+        G = pairs_backward_raw(ctx.variant, ctx.beta, P, hist, tgt, hreg, treg, aux, row_sum, parts, dscore, ctx.drop, act_mask=mask)
         grads = tuple(G[n].to(P[n].dtype) if ctx.needs_input_grad[8 + i] else None for i, n in enumerate(names))
         return (None, None, None, None, None, None, None, None) + grads
+
+
+def pairs_backward_raw(variant: str, beta: float, P: Dict[str, torch.Tensor], hist, tgt, hreg, treg, aux, row_sum, parts, dscore,
+                       drop=(0.0, 0, "auto"), tables: bool = True, act_mask: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """nais_pairs_backward: every parameter gradient of `pairs_score` given dscore [B] and the forward's saved row sums / per-
+    branch scores (/ ReLU pattern `act_mask`, when the tcgen05 forward produced one), as a dict of dense float32 tensors (zero
+    rows for untouched table rows).  `tables=False` skips the embedding tables (no sort, no segment reduce): the attention-MLP /
+    dist-layer gradients only."""
+    dev = _need_cuda(hist, tgt, dscore, *P.values())
+    lib = _lib.load()
+    keep: List[torch.Tensor] = []
+    with torch.cuda.device(dev):
+        p = build_params(variant, P, beta, keep, drop[0], drop[1], _fwd_bwd(drop[2])[1])
+        b = _pairs_struct(hist, tgt, hreg, treg, aux, keep)
+        G = {n: torch.zeros_like(t, dtype=torch.float32, memory_format=torch.contiguous_format) for n, t in P.items()
+             if tables or n not in _TABLES}
+        g = NaisGrads()
+        if tables:
+            g.hist_poi[0], g.tgt_poi[0] = G["embed_history.weight"].data_ptr(), G["embed_target.weight"].data_ptr()
+        g.w1[0], g.b1[0], g.w2[0] = (G["attn_layer1.weight"].data_ptr(), G["attn_layer1.bias"].data_ptr(),
+                                     G["attn_layer2.weight"].data_ptr())
+        if variant in ("region", "region_distance") and tables:
+            g.reg[0] = G["embed_region.weight"].data_ptr()
+        if "dist_layer.weight" in G:
+            g.dist_w, g.dist_b = G["dist_layer.weight"].data_ptr(), G["dist_layer.bias"].data_ptr()
+        if variant == "disentangled":
+            if tables:
+                g.reg[1] = G["embed_region.weight"].data_ptr()
+            g.w1[1], g.b1[1], g.w2[1] = (G["region_attn_layer1.weight"].data_ptr(),
+                                         G["region_attn_layer1.bias"].data_ptr(),
+                                         G["region_attn_layer2.weight"].data_ptr())
+            g.dist_embed = G["embed_distance.weight"].data_ptr()
+        ws_bytes = lib.nais_pairs_backward_workspace_bytes(C.byref(p), b.B, b.H)
+        ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
+        ds = _f32(dscore)
+        _lib.check(lib.nais_pairs_backward(C.byref(p), C.byref(b), parts.data_ptr(), row_sum.data_ptr(), _ptr(act_mask), ds.data_ptr(),
+                                           C.byref(g), ws.data_ptr(), ws_bytes, _stream()), "nais_pairs_backward")
+        _poll_bad_index(dev)
+    return G
 
 
 def pairs_score(variant: str, beta: float, params: Sequence[torch.Tensor], hist, tgt, hreg=None, treg=None, aux=None,
@@ -264,7 +301,8 @@ _TABLES = ("embed_history.weight", "embed_target.weight", "embed_region.weight")
 
 
 def pairs_backward_adagrad(variant: str, beta: float, P: Dict[str, torch.Tensor], sums: Dict[str, torch.Tensor], lr: float,
-                           eps: float, hist, tgt, hreg, treg, aux, row_sum, parts, dscore, drop=(0.0, 0, "auto")) -> Dict[str, torch.Tensor]:
+                           eps: float, hist, tgt, hreg, treg, aux, row_sum, parts, dscore, drop=(0.0, 0, "auto"),
+                           act_mask: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """Backward of `pairs_score` with the embedding tables stepped in place by a row-sparse Adagrad fused into the
     sorted-segment reduce (nais_pairs_backward_adagrad; replaces run.py:252-254 for `embed_*`): `sums[name]` is the
     optimizer's `state['sum']` of table `name`; P[name] and sums[name] of every touched row are updated, nothing dense is
@@ -274,7 +312,7 @@ def pairs_backward_adagrad(variant: str, beta: float, P: Dict[str, torch.Tensor]
     lib = _lib.load()
     keep: List[torch.Tensor] = []
     with torch.cuda.device(dev):
-        p = build_params(variant, P, beta, keep, *drop)
+        p = build_params(variant, P, beta, keep, drop[0], drop[1], _fwd_bwd(drop[2])[1])
         if p.n_branch != 1:
             raise RuntimeError("fused Adagrad: one-branch variants only")
         b = _pairs_struct(hist, tgt, hreg, treg, aux, keep)
@@ -294,28 +332,25 @@ def pairs_backward_adagrad(variant: str, beta: float, P: Dict[str, torch.Tensor]
         ws_bytes = lib.nais_pairs_backward_workspace_bytes(C.byref(p), b.B, b.H)
         ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
         ds = _f32(dscore)
-        _lib.check(lib.nais_pairs_backward_adagrad(C.byref(p), C.byref(b), parts.data_ptr(), row_sum.data_ptr(), ds.data_ptr(),
-                                                   C.byref(g), C.byref(o), ws.data_ptr(), ws_bytes, _stream()),
+        _lib.check(lib.nais_pairs_backward_adagrad(C.byref(p), C.byref(b), parts.data_ptr(), row_sum.data_ptr(), _ptr(act_mask),
+                                                   ds.data_ptr(), C.byref(g), C.byref(o), ws.data_ptr(), ws_bytes, _stream()),
                    "nais_pairs_backward_adagrad")
         _poll_bad_index(dev)
     return G
 
 
 def pairs_forward_raw(variant: str, beta: float, P: Dict[str, torch.Tensor], hist, tgt, hreg, treg, aux, drop=(0.0, 0, "auto")):
-    """(score[B], row_sum, parts) of nais_pairs_forward without autograd bookkeeping (the fused train step keeps them)."""
+    """(score[B], row_sum, parts, act_mask) of nais_pairs_forward without autograd bookkeeping (the fused train step keeps
+    them for its backward; act_mask is None unless the tcgen05 forward ran)."""
     dev = _need_cuda(hist, tgt, *P.values())
     lib = _lib.load()
     keep: List[torch.Tensor] = []
     with torch.cuda.device(dev):
-        p = build_params(variant, P, beta, keep, *drop)
+        p = build_params(variant, P, beta, keep, drop[0], drop[1], _fwd_bwd(drop[2])[0])
         b = _pairs_struct(hist, tgt, hreg, treg, aux, keep)
-        score = torch.empty(b.B, device=dev, dtype=torch.float32)
-        row_sum = torch.empty(p.n_branch, b.B, device=dev, dtype=torch.float32)
-        parts = torch.empty(p.n_branch, b.B, device=dev, dtype=torch.float32)
-        _lib.check(lib.nais_pairs_forward(C.byref(p), C.byref(b), score.data_ptr(), row_sum.data_ptr(), parts.data_ptr(),
-                                          _stream()), "nais_pairs_forward")
+        score, row_sum, parts, mask = _forward_launch(lib, p, b, dev)
         _poll_bad_index(dev)
-    return score, row_sum, parts
+    return score, row_sum, parts, mask
 
 
 def dropout_keep_mask(seed: int, B: int, H: int, hid: int, p: float):

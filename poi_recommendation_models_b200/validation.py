@@ -17,9 +17,8 @@ from . import eval_metrics
 
 
 def _recommend(model, args, train_matrix, num_users, precision="auto", user_batch=2048):
-    csr = train_matrix.tocsr()
-    csr.sort_indices()
-    k = int(args.topk)
+    csr = train_matrix.tocsr()  # read as stored: the history order of getrow(u).indices (validation.py:86); the caller's
+    k = int(args.topk)          # matrix is never reordered (the kernels compare ids item by item, sorted or not)
     rec = []
     for u0 in range(0, num_users, user_batch):
         u1 = min(num_users, u0 + user_batch)

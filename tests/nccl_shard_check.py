@@ -1,0 +1,54 @@
+"""Launched by tests/test_gpu_plan_and_index.py under torchrun (2 ranks, NCCL): range-sharded / user-sliced ranking through
+`ShardedRanker` must equal one GPU bit for bit, and data-parallel training must leave identical parameters on every rank."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    import nais_testutil as util
+    from oracle import nais_oracle as orc
+    from poi_recommendation_models_b200 import synthetic
+    from poi_recommendation_models_b200.distributed import ShardedRanker
+
+    N, k = 70000, 20
+    coords, region, R = synthetic.make_catalog(N, seed=0)
+    sd = orc.init_state("region_distance", N, 64, 64, R, 1, seed=1, style="trained")
+    m = util.make_model("region_distance", sd, 0.5, device=dev)
+    m.set_catalog(region=region, coords=coords)
+    rng = np.random.default_rng(2)
+    lens = rng.integers(3, 130, 37)  # ragged, odd user count: the last user slice is padded for the gather
+    indptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    users = m.make_users(indptr, np.concatenate([rng.choice(N, n, replace=False) for n in lens]).astype(np.int64))
+    solo = ShardedRanker(m, 0, 1).topk(users, k)
+    ok = True
+    for grid in ((world, 1), (1, world)):
+        r = ShardedRanker(m, rank, world, grid=grid)
+        s, i = r.topk(users, k)
+        same = bool(torch.equal(i, solo[1]) and torch.equal(s, solo[0]))
+        ok = ok and same
+        # end to end from pinned host memory as well
+        s_h, i_h = r.topk_host(torch.from_numpy(indptr).pin_memory(), torch.from_numpy(users.items.cpu().numpy().astype(np.int64)).pin_memory(), k)
+        ok = ok and bool(torch.equal(i_h, solo[1].cpu().to(torch.int64)))
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0 and int(flag.item()) == 1:
+        print("NCCL_SHARD_CHECK_OK")
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
