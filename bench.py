@@ -28,6 +28,7 @@ c4      BASELINE configs[3]: the 1M-POI catalogue, POI-range shards x 1 on every
         step at every N -> a true strong-scaling curve of the north_star sharding (all-gather + on-device merge)
 parity_n  (N > 1) rank 0 re-scores users of the last step ALONE over the full range and compares the lists bit for bit
 train_c3  BASELINE configs[2]: 4096 (user, pos, neg) triples, H = 128: pair forward + BPR loss + hand-written backward
+c1      (N = 1) BASELINE configs[0]: one training epoch (one-user steps vs 64-user segmented steps) + full-rank eval of all users
 cpu_baseline  the UNMODIFIED reference `model.py` class on the host cores (oracle/_ref snapshot; kind "reference"), driven by
         the validation.py:84-127 flow (chunks of 2048, torch.cat, torch.topk(50)), on a bounded sample of users
 parity  the CPU arm's users + more users scored by a float64 evaluation of the oracle, against the CUDA path's lists
@@ -591,6 +592,108 @@ def train_cpu_baseline(n_triples=32):
             "sample": f"{n} steps of {T} triples ({2 * T} rows, H={H}) in {dt:.1f} s: attention_network + BPR loss + autograd of the unmodified reference class, dense embedding gradients"}
 
 
+def c1_block(dev, lib, no_cpu=False):
+    """BASELINE configs[0] (C1): Foursquare-NYC-shaped 1,083 users x 38,333 POIs, D = hid = 64, history <= 100: ONE training epoch
+    (BCE, 4 negatives per positive, Adagrad lr 0.01: run.py:227-255) + full-rank evaluation of every user (validation.py:62-131).
+    The epoch is timed two ways: the reference's schedule — one user per optimizer step — on a 256-user sample, and multi-user
+    steps (64 users per step, segmented layout, device sampler; loss = sum of the per-user mean BCE losses)."""
+    import torch
+    from poi_recommendation_models_b200 import batches as PB, eval_metrics as PM, model as M, ops, synthetic
+    U, N, D, hid, num_ng, lr = 1083, 38333, 64, 64, 4, 0.01
+    data = synthetic.make_checkins(U, N, seed=0, hist_len=None, max_hist=100, min_hist=5, median_hist=30)
+    csr = data.train_csr()
+    torch.manual_seed(0)
+    order = np.random.default_rng(0).permutation(U)
+
+    def fresh():
+        torch.manual_seed(0)
+        m_ = M.NAIS_region_distance_Embedding(N, D, hid, BETA, data.region_num, 1).to(dev).train()
+        return m_, torch.optim.Adagrad(m_.parameters(), lr=lr, weight_decay=0.0)
+
+    bt = PB.DeviceBatcher(csr, data.region, data.coords, device=dev, seed=0)
+    blk = {"config": {"workload": "C1: 1083 users x 38333 POIs (synthetic Foursquare-NYC shape), D=hid=64, H<=100 (median 30), num_ng=4, Adagrad lr 0.01"}}
+    # (a) the reference's schedule: one user per step (fused row-sparse Adagrad, batch built on the device)
+    m1, o1 = fresh()
+    sample = order[:256]
+    for u in sample[:8]:
+        m1.fused_adagrad_step(o1, *(lambda b: (b[2], b[0], b[1], b[3], b[4], b[5]))(bt.batch(int(u), num_ng)))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for u in sample:
+        h_, t_, lab_, hr_, tr_, ll_ = bt.batch(int(u), num_ng)
+        m1.fused_adagrad_step(o1, lab_, h_, t_, hr_, tr_, ll_)
+    torch.cuda.synchronize()
+    dt1 = time.perf_counter() - t0
+    blk["epoch_one_user_per_step"] = {"users_per_s": len(sample) / dt1, "sample_users": int(len(sample)), "steps": int(len(sample)),
+                                      "note": "the reference's schedule (run.py:227-255): launch-bound, ~1 ms of host + kernel latency per user"}
+    del m1, o1
+    # (b) multi-user steps: 64 users per optimizer step, segmented layout, device sampler
+    m2, o2 = fresh()
+    ups = 64
+
+    def epoch(seed0):
+        loss = None
+        for i, s0 in enumerate(range(0, U, ups)):
+            b = bt.multi_user_batch(order[s0:s0 + ups], num_ng, seed=seed0 + i)
+            ro = b.host_row_offsets
+            w = torch.from_numpy(np.repeat(1.0 / np.maximum(np.diff(ro), 1), np.diff(ro)).astype(np.float32)).to(dev, non_blocking=True)
+            loss = m2.fused_adagrad_step(o2, b.label, b, row_weight=w)
+        return loss
+
+    epoch(0)  # warm-up epoch (also a second epoch of training: the timed one starts from those weights)
+    torch.cuda.synchronize()
+    l0 = lib.nais_launch_count()
+    t0 = time.perf_counter()
+    loss = epoch(1000)
+    torch.cuda.synchronize()
+    dt2 = time.perf_counter() - t0
+    ops.check_indices(sync=True)
+    cells = int(5 * (np.diff(csr.indptr).astype(np.int64) ** 2).sum())
+    blk["epoch_multi_user"] = {"users_per_s": U / dt2, "epoch_s": dt2, "users_per_step": ups, "steps": (U + ups - 1) // ups,
+                               "rows": int(5 * csr.nnz), "cells": cells, "gpu_launches": int(lib.nais_launch_count() - l0),
+                               "loss_last_step": float(loss), "batch": "nais_sample_batch (device) + segmented NaisPairs: no [B,H] repeat, no [B,H,2] tensor",
+                               "speedup_vs_one_user_per_step": (U / dt2) / (len(sample) / dt1)}
+    # (c) full-rank evaluation of every user with the trained weights
+    m2.eval()
+    m2.set_catalog(region=data.region, coords=data.coords)
+    users = m2.make_users(data.indptr, data.indices)
+    m2.predict_topk(users, 50)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _, ids = m2.predict_topk(users, 50)
+    hits = ops.hits_at_k(ids, data.test_positive, [10])
+    torch.cuda.synchronize()
+    dt3 = time.perf_counter() - t0
+    rec = ids.cpu().tolist()
+    blk["eval"] = {"users_per_s": U / dt3, "eval_s": dt3, "topk": 50, "recall@10_test": PM.recall_at_k(data.test_positive, rec, 10),
+                   "note": "one fused full-rank call for all 1083 users + nais_hits_at_k (weights after 2 synthetic epochs: metrics are not meaningful, parity is in tests/)"}
+    if not no_cpu:
+        from oracle import nais_oracle as orc  # CPU arm only
+        sd = {k: v.detach().cpu() for k, v in m2.state_dict().items()}
+        ref = orc.reference_model("region_distance", sd, BETA)
+        if ref is not None:
+            import random as _r
+            ref.train()
+            opt = torch.optim.Adagrad(ref.parameters(), lr=lr)
+            rb = __import__("oracle.ref_shim", fromlist=["x"]).load_reference("batches")
+            rb.DEVICE = torch.device("cpu") if hasattr(rb, "DEVICE") else None
+            _r.seed(0)
+            n_cpu, t0 = 0, time.perf_counter()
+            for u in order[:6]:
+                hist = data.history(int(u))
+                h_, t_, lab_, hr_, tr_ = orc.train_batch_region(hist.tolist(), N, num_ng, data.region, _r)
+                ll_ = orc.latlon_abs_diff(data.coords, t_, h_)
+                opt.zero_grad()
+                pred = ref(torch.from_numpy(h_), torch.from_numpy(t_), torch.from_numpy(hr_), torch.from_numpy(tr_), torch.from_numpy(ll_))
+                ref.loss_func(pred, torch.from_numpy(lab_)).backward()
+                opt.step()
+                n_cpu += 1
+            dtc = time.perf_counter() - t0
+            blk["cpu_baseline"] = {"value": n_cpu / dtc, "unit": "users/s (training)", "cores": torch.get_num_threads(), "kind": "reference",
+                                   "sample": f"{n_cpu} user-steps of run.py:235-254 with the unmodified reference class + dense torch Adagrad on the host ({dtc:.1f} s); batch built by the oracle's restatement of batches.py:67-108"}
+    return blk
+
+
 def run_train(args, dev, lib, peaks, rank, world):
     blk = train_c3(args, dev, lib, peaks, rank, world, args.steps, args.warmup, full=True)
     if rank == 0:
@@ -710,6 +813,11 @@ def main():
         t3 = train_c3(args, dev, lib, peaks, rank, world, max(10, args.steps), 3)
         if rank == 0:
             line["train_c3"] = t3
+            if world == 1:
+                try:
+                    line["c1"] = c1_block(dev, lib, args.no_cpu_baseline)
+                except Exception as e:  # noqa: BLE001  (the headline line stands)
+                    line["c1"] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             kept = {}

@@ -112,15 +112,38 @@ typedef struct NaisParams {
   int32_t reserved0;
 } NaisParams;
 
-/* A batch of explicit (history row, target) pairs: the argument list of model.forward (model.py:231). */
+/* A batch of explicit (history row, target) pairs: the argument list of model.forward (model.py:231).
+ *
+ * Dense layout (seg_offsets == NULL) — what the reference builds: every row carries its own history, B rows x H items
+ * (batches.py:97 literally repeats one user's history once per target).
+ *
+ * Segmented layout (seg_offsets != NULL) — many users in one step without the repeat and without a materialised [B,H,2]
+ * distance tensor: rows are grouped by segment (= a user); the rows [row_offsets[s], row_offsets[s+1]) of
+ * segment s all share the history hist[seg_offsets[s] .. seg_offsets[s+1]) (hreg / hist_coords alike), H is ignored, aux must
+ * be NULL and the LATLON lanes are formed in the kernel from centred coordinates (hist_coords per history item, tgt_coords per
+ * row; NaisCatalog conventions).  Per-cell arrays (act_mask) are indexed cell(row r of segment s, item h) =
+ * seg_cell_offsets[s] + (r - row_offsets[s]) * H_s + h.  The work decomposition is host-known: tile t covers rows
+ * tile_row0[t] .. of segment tile_seg[t], at most min(16, 128 / H_s) rows (1 row when H_s > 128), never crossing a segment;
+ * segments without history or without rows have no tile (a host loop over the segments builds these arrays: INTEGRATION.md).  NAIS_DIST_KM and dropout are
+ * dense-layout only. */
 typedef struct NaisPairs {
-  const int64_t* hist; /* [B,H] history POI ids */
+  const int64_t* hist; /* dense [B,H] / segmented [nnz]: history POI ids */
   const int64_t* tgt;  /* [B]   target POI ids */
-  const int64_t* hreg; /* [B,H] region id of each history POI (NULL when no branch has w_reg) */
+  const int64_t* hreg; /* like hist: region id of each history POI (NULL when no branch has w_reg) */
   const int64_t* treg; /* [B]   region id of each target */
-  const float* aux;    /* LATLON: ll[B,H,2] = |dlat|,|dlon| degrees; KM: dist_km[B,H]; NONE: NULL */
+  const float* aux;    /* dense — LATLON: ll[B,H,2] = |dlat|,|dlon| degrees; KM: dist_km[B,H]; NONE: NULL.  Segmented: NULL */
   int64_t B;
   int32_t H;
+  int32_t n_seg;                   /* segmented: number of segments */
+  const int64_t* seg_offsets;      /* [n_seg+1] history CSR; NULL = dense layout */
+  const int64_t* row_offsets;      /* [n_seg+1] */
+  const int64_t* seg_cell_offsets; /* [n_seg+1] exclusive sum of (rows of s) * H_s */
+  const int32_t* tile_seg;         /* [n_tiles] */
+  const int64_t* tile_row0;        /* [n_tiles] */
+  int64_t n_tiles;
+  int64_t n_cells;                 /* seg_cell_offsets[n_seg] (host copy: sizes the backward workspace and act_mask) */
+  const float* hist_coords;        /* [nnz,2] centred (lat, lon) of every history item (LATLON) */
+  const float* tgt_coords;         /* [B,2]   centred (lat, lon) of every target (LATLON) */
 } NaisPairs;
 
 /* Gradients of nais_pairs_backward.  Dense tables must be zero-filled by the caller; the library writes each touched
@@ -176,12 +199,26 @@ NAIS_API int nais_pairs_dispatch(const NaisParams* p, const NaisPairs* batch, in
 NAIS_API int nais_pairs_forward(const NaisParams* p, const NaisPairs* batch, float* score, float* row_sum, float* score_parts,
                        uint64_t* act_mask, nais_stream_t stream);
 
-NAIS_API size_t nais_pairs_backward_workspace_bytes(const NaisParams* p, int64_t B, int32_t H);
+NAIS_API size_t nais_pairs_backward_workspace_bytes(const NaisParams* p, const NaisPairs* batch);
 /* Given dscore[B] = dL/dscore, write every parameter gradient.  score_parts / row_sum / act_mask are the forward's outputs
  * (act_mask: NULL unless the tcgen05 forward wrote it). */
 NAIS_API int nais_pairs_backward(const NaisParams* p, const NaisPairs* batch, const float* score_parts, const float* row_sum,
                         const uint64_t* act_mask, const float* dscore, const NaisGrads* grads, void* workspace,
                         size_t workspace_bytes, nais_stream_t stream);
+
+/* Device-side training-batch construction for the segmented layout (batches.py:67-108 `get_NAIS_batch_region`, many users per
+ * call).  For every segment s (history hist[seg_offsets[s] .. seg_offsets[s+1]), H_s items) the rows
+ * [row_offsets[s], row_offsets[s] + (num_ng + 1) * H_s) are written interleaved like the reference: positive i at
+ * + i * (num_ng + 1) (label 1), its num_ng negatives behind it (label 0).  Negatives are H_s * num_ng POIs drawn uniformly
+ * WITHOUT replacement from the POIs outside the history (the distribution of the reference's shuffle-and-take-a-prefix), by a
+ * counter-based generator keyed on (seed, segment, slot, attempt): the same seed gives the same batch; it is NOT Python's
+ * `random` stream.  Positives keep their stored order.  poi_region [item_num] / poi_coords [item_num,2] (centred) fill treg /
+ * tgt_coords (each may be NULL together with its output).  max_hist >= every H_s (host-known, sizes the per-segment hash set);
+ * item_num must exceed (num_ng + 1) * H_s for every segment.  Outputs: tgt [B] int64, label [B] float, treg [B] int64,
+ * tgt_coords [B,2] with B = row_offsets[n_seg]. */
+NAIS_API int nais_sample_batch(const int64_t* seg_offsets, const int64_t* hist, int32_t n_seg, const int64_t* row_offsets,
+                               int32_t num_ng, int32_t item_num, const int32_t* poi_region, const float* poi_coords, uint64_t seed,
+                               int32_t max_hist, int64_t* tgt, float* label, int64_t* treg, float* tgt_coords, nais_stream_t stream);
 
 /* Row-sparse Adagrad fused into the embedding-gradient segment reduce.  Replaces, for the embedding tables, the dense
  * `embedding_dense_backward` + `torch.optim.Adagrad.step()` of run.py:225,252-254 (weight_decay = 0, lr_decay = 0: a row

@@ -35,7 +35,9 @@ class NaisParams(C.Structure):
 
 class NaisPairs(C.Structure):
     _fields_ = [("hist", C.c_void_p), ("tgt", C.c_void_p), ("hreg", C.c_void_p), ("treg", C.c_void_p),
-                ("aux", C.c_void_p), ("B", C.c_int64), ("H", C.c_int32)]
+                ("aux", C.c_void_p), ("B", C.c_int64), ("H", C.c_int32), ("n_seg", C.c_int32), ("seg_offsets", C.c_void_p),
+                ("row_offsets", C.c_void_p), ("seg_cell_offsets", C.c_void_p), ("tile_seg", C.c_void_p), ("tile_row0", C.c_void_p),
+                ("n_tiles", C.c_int64), ("n_cells", C.c_int64), ("hist_coords", C.c_void_p), ("tgt_coords", C.c_void_p)]
 
 
 class NaisGrads(C.Structure):
@@ -67,7 +69,9 @@ SYMBOLS = {
     "nais_pairs_dispatch": (C.c_int, [C.POINTER(NaisParams), C.POINTER(NaisPairs), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "nais_pairs_forward": (C.c_int, [C.POINTER(NaisParams), C.POINTER(NaisPairs), C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
-    "nais_pairs_backward_workspace_bytes": (C.c_size_t, [C.POINTER(NaisParams), C.c_int64, C.c_int32]),
+    "nais_pairs_backward_workspace_bytes": (C.c_size_t, [C.POINTER(NaisParams), C.POINTER(NaisPairs)]),
+    "nais_sample_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nais_pairs_backward": (C.c_int, [C.POINTER(NaisParams), C.POINTER(NaisPairs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.POINTER(NaisGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
     "nais_pairs_backward_adagrad": (C.c_int, [C.POINTER(NaisParams), C.POINTER(NaisPairs), C.c_void_p, C.c_void_p, C.c_void_p,

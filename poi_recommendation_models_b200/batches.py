@@ -85,7 +85,8 @@ class DeviceBatcher:
     POIs — but drawn with a device RNG (`torch.randperm`), not the reference's Python `random` stream, and without any
     O(N) Python list work or host->device copies per user.  Also returns the |dlat|,|dlon| tensor of run.py:239-247.
 
-    PyTorch ops only (index plumbing); the scorer kernels are untouched."""
+    `batch` (one user, dense layout) is PyTorch index plumbing; `multi_user_batch` (many users, segmented layout) samples
+    with the library's `nais_sample_batch` kernel and materialises neither the [B,H] history repeat nor the [B,H,2] tensor."""
 
     def __init__(self, train_matrix, businessRegionEmbedList, place_coords, device=None, seed=0):
         dev = torch.device(device or _device())
@@ -99,6 +100,33 @@ class DeviceBatcher:
         self.gen.manual_seed(seed)
         self.dev = dev
         self._visited = torch.zeros(self.num_poi, dtype=torch.bool, device=dev)
+        # centred float32 coordinates (float64 midpoint subtracted first, like model.set_catalog): what the kernels difference
+        c = np.asarray(place_coords, dtype=np.float64)
+        self.center = ((c[:, 0].min() + c[:, 0].max()) / 2, (c[:, 1].min() + c[:, 1].max()) / 2)
+        self.coords32 = torch.from_numpy((c - np.array(self.center)).astype(np.float32)).to(dev)
+        self.region32 = self.region.to(torch.int32)
+        self._indptr_dev = torch.from_numpy(self.indptr).to(dev)
+
+    def multi_user_batch(self, uids, negative_num: int, seed: int = 0):
+        """One training batch over MANY users as an `ops.SegmentedPairs`: for every user all positives, each
+        followed by `negative_num` negatives drawn on the device uniformly without replacement from the POIs outside the
+        user's history (the distribution of batches.py:76-80), labels [1, 0..0] interleaved like the reference — but every
+        user's history is stored ONCE (the kernels index it per row) and no distance tensor exists (the kernels difference
+        the centred coordinates).  `seed` keys the counter-based sampler: same seed, same batch."""
+        from . import ops
+        uids = np.asarray(uids, dtype=np.int64)
+        H = self.indptr[uids + 1] - self.indptr[uids]
+        st = ops.segment_structure(H, (negative_num + 1) * H, self.dev)
+        u_dev = torch.from_numpy(uids).to(self.dev)
+        lens = torch.from_numpy(H).to(self.dev)
+        seg = torch.repeat_interleave(torch.arange(len(uids), device=self.dev), lens)
+        src = self._indptr_dev[u_dev][seg] + (torch.arange(int(H.sum()), device=self.dev) - st["seg_offsets"][seg])
+        hist = self.indices[src].contiguous()
+        tgt, label, treg, tcoords = ops.sample_batch(hist, st, negative_num, self.num_poi, seed, self.region32, self.coords32)
+        fields = {k: st[k] for k in ("seg_offsets", "row_offsets", "seg_cell_offsets", "tile_seg", "tile_row0", "n_seg", "B", "n_tiles",
+                                     "n_cells", "max_hist", "host_row_offsets")}
+        return ops.SegmentedPairs(hist=hist, hreg=self.region[hist], hist_coords=self.coords32[hist].contiguous(), tgt=tgt, treg=treg,
+                                  tgt_coords=tcoords, label=label, **fields)
 
     def batch(self, uid: int, negative_num: int):
         """-> (user_history [B,H], train_data [B], train_label [B], user_history_region [B,H], train_data_region [B],

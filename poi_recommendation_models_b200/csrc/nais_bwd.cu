@@ -12,6 +12,7 @@
 
 #include "nais_bwd_args.cuh"
 #include "nais_common.cuh"
+#include "nais_pairs_tile.cuh"
 
 namespace nais {
 
@@ -26,7 +27,7 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
   extern __shared__ __align__(16) float smem[];
   const NaisParams& p = A.p;
   const NaisBranch& br = p.branch[A.bi];
-  const int H = A.b.H, D = br.w_poi + br.w_reg, hid = p.hid;
+  const int D = br.w_poi + br.w_reg, hid = p.hid;
   const int lanes = (p.dist_mode == NAIS_DIST_LATLON) ? 2 : 0;
   const int ldw = D + lanes;
   constexpr int HP = NKB * KB;
@@ -48,13 +49,14 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
   int* citem = reinterpret_cast<int*>(red + 8 * (NT / 32));  // [TC] history item id per cell
   int* creg = citem + TC;                                   // [TC]
   int* crow = creg + TC;                                    // [TC] row slot per cell (-1 invalid)
-  long long* cgl = reinterpret_cast<long long*>(crow + TC);  // [TC] global cell index (dropout mask)
+  long long* cgl = reinterpret_cast<long long*>(crow + TC);  // [TC] global cell index (dropout mask, dq positions)
+  int* cmask = reinterpret_cast<int*>(cgl + TC);             // [TC] history item != target
   const uint32_t dthresh = p.dropout_p > 0.f ? dropout_threshold(p.dropout_p) : 0u;
   const float dinv = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
 
   const int tid = threadIdx.x, cell = tid & (TC - 1), half = tid >> 7;
   const int tk = tid & 15, tj = tid >> 4;
-  const int n_chunks = (H <= TC) ? 1 : (H + TC - 1) / TC;
+  const int64_t n_cells = pairs_n_cells(A.b);
   const bool vec4 = rows_vec4(br, D >> 1);  // 128-bit embedding-row gathers
   const bool w1_vec2 = (reinterpret_cast<uintptr_t>(br.w1) & 7u) == 0;  // ldw = D + lanes is even: rows of W are 8-byte aligned
 
@@ -86,8 +88,10 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
   int resident = -1;
 
   for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x) {
-    const int64_t row0 = item * A.rows_per_tile;
-    const int nrows = (int)min((int64_t)A.rows_per_tile, A.b.B - row0);
+    const PairTile T = pair_tile(A.b, item);
+    const int64_t row0 = T.row0;
+    const int nrows = T.nrows, H = T.H;
+    const int n_chunks = (H <= TC) ? 1 : (H + TC - 1) / TC;
     __syncthreads();
     for (int i = tid; i < nrows * D; i += NT) {
       int r = i / D, d = i - r * D;
@@ -115,15 +119,16 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
         h = ch * TC + cell;
         valid = h < H;
       }
-      const int64_t cidx = valid ? (row0 + r) * (int64_t)H + h : 0;
+      const int64_t cidx = valid ? T.cell0 + r * (int64_t)H + h : 0;  // per-cell arrays
+      const int64_t hidx = valid ? T.hist0 + r * T.hist_rs + h : 0;   // history arrays
       // ---- build x, similarity, lanes -------------------------------------------------------------------------
       {
         const int d0 = half ? (D >> 1) : 0, d1 = half ? D : (D >> 1);
         float ssum = 0.f;
         int64_t it = 0, rg = 0;
         if (valid) {
-          it = checked_id(A.b.hist[cidx], p.item_num, A.bad);
-          rg = br.w_reg ? checked_id(A.b.hreg[cidx], p.region_num, A.bad) : 0;
+          it = checked_id(A.b.hist[hidx], p.item_num, A.bad);
+          rg = br.w_reg ? checked_id(A.b.hreg[hidx], p.region_num, A.bad) : 0;
           const float* qp = br.hist_poi + (size_t)it * br.w_poi;
           const float* qr = br.hist_reg + (size_t)rg * br.w_reg;
           if (vec4) {  // 128-bit row loads (same products, same summation order as the scalar walk and as the forward)
@@ -157,8 +162,7 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
         if (half == 0) {
           float g0 = 0.f, g1 = 0.f, l0 = 0.f, l1 = 0.f;
           if (valid && lanes) {
-            l0 = A.b.aux[cidx * 2];
-            l1 = A.b.aux[cidx * 2 + 1];
+            pair_latlon(A.b, cidx, hidx, row0 + r, l0, l1);
             const float a0 = l0 * p.dist_scale, a1 = l1 * p.dist_scale;
             g0 = sigmoidf_exact(fmaf(a1, __ldg(p.dist_w + 1), fmaf(a0, __ldg(p.dist_w + 0), __ldg(p.dist_b + 0))));
             g1 = sigmoidf_exact(fmaf(a1, __ldg(p.dist_w + 3), fmaf(a0, __ldg(p.dist_w + 2), __ldg(p.dist_b + 1))));
@@ -174,6 +178,7 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
           creg[cell] = (int)rg;
           crow[cell] = valid ? r : -1;
           cgl[cell] = cidx;
+          cmask[cell] = valid && A.b.hist[hidx] != A.b.tgt[row0 + r];  // history item != target (model.py:299-302)
         }
       }
       __syncthreads();
@@ -253,8 +258,7 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
         if (rr >= 0) {
           float a = a_part[i];
           if (p.dist_mode == NAIS_DIST_KM) a += g[c];
-          const int64_t ci = (H <= TC) ? (row0 + rr) * (int64_t)H + (c - rr * H) : row0 * (int64_t)H + ch * TC + c;
-          const bool m = A.b.hist[ci] != A.b.tgt[row0 + rr];
+          const bool m = cmask[c] != 0;
           if (m) {
             const float S = rowv[rr], sc = rowv[BWD_MAXROWS + rr], G = rowv[2 * BWD_MAXROWS + rr];
             const float e = expf(a);
@@ -423,7 +427,7 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
                 o[cc] = full * ps[rr * D + d];
                 dpv[cc] = full * qv[cc];
               }
-              const int64_t ci = (H <= TC) ? (row0 + rr) * (int64_t)H + (c - rr * H) : row0 * (int64_t)H + ch * TC + c;
+              const int64_t ci = cgl[c];
               store_dq4(A, br.w_poi, br.w_reg, A.dq_h ? __ldg(A.pos_h + ci) : 0u, A.dq_r ? __ldg(A.pos_r + ci) : 0u, d0,
                         make_float4(o[0], o[1], o[2], o[3]));
             }
@@ -449,8 +453,7 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
     __syncthreads();
     for (int i = tid; i < nrows * D; i += NT) {
       const int64_t row = row0 + i / D;
-      store_dp(A, br.w_poi, br.w_reg, A.dp_t ? __ldg(A.pos_t + row) : 0u, A.dq_r ? __ldg(A.pos_r + A.b.B * (int64_t)H + row) : 0u, i % D,
-               dpacc[i]);
+      store_dp(A, br.w_poi, br.w_reg, A.dp_t ? __ldg(A.pos_t + row) : 0u, A.dq_r ? __ldg(A.pos_r + n_cells + row) : 0u, i % D, dpacc[i]);
     }
   }
 
@@ -529,15 +532,27 @@ __global__ void param_reduce_kernel(const float* __restrict__ parts, int n_parts
 __device__ __forceinline__ int key_of(int64_t id, int n_rows) { return (uint64_t)id < (uint64_t)n_rows ? (int)id : n_rows; }
 __global__ void make_keys_kernel(NaisPairs b, int item_num, int region_num, int* k_hist, uint32_t* v_hist, int* k_tgt,
                                  uint32_t* v_tgt, int* k_reg, uint32_t* v_reg) {
-  const int64_t n_cells = b.B * (int64_t)b.H;
+  const int64_t n_cells = pairs_n_cells(b);
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n_cells) {
+    int64_t hidx = i;  // dense: cell index == history index
+    if (pairs_segmented(b)) {
+      // cell i belongs to the segment s with seg_cell_offsets[s] <= i < seg_cell_offsets[s+1]; its history item is (i - base) % H_s
+      int lo = 0, hi = b.n_seg;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(b.seg_cell_offsets + mid) <= i) lo = mid;
+        else hi = mid;
+      }
+      const int64_t h0 = __ldg(b.seg_offsets + lo), H = __ldg(b.seg_offsets + lo + 1) - h0;
+      hidx = h0 + (i - __ldg(b.seg_cell_offsets + lo)) % H;
+    }
     if (k_hist) {
-      k_hist[i] = key_of(b.hist[i], item_num);
+      k_hist[i] = key_of(b.hist[hidx], item_num);
       v_hist[i] = (uint32_t)i;
     }
     if (k_reg) {
-      k_reg[i] = key_of(b.hreg[i], region_num);
+      k_reg[i] = key_of(b.hreg[hidx], region_num);
       v_reg[i] = (uint32_t)i;
     }
   }
@@ -619,46 +634,53 @@ __global__ void segment_reduce_pass1_kernel(const int* __restrict__ keys, int64_
   bool col[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) col[q] = lane + 32 * q < w;
-  int a = 0;
-  while (a < cnt) {
-    const unsigned long long rest = a + 1 < 64 ? (starts >> (a + 1)) : 0ull;
-    const int b = rest ? a + 1 + __ffsll((long long)rest) - 1 : cnt;  // the run is [a, b)
-    const int key = a < 32 ? __shfl_sync(0xffffffffu, k0, a) : __shfl_sync(0xffffffffu, k1, a - 32);
-    float acc[NQ];
+  float acc[NQ];
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) acc[q] = 0.f;
-    for (int j0 = a; j0 < b; j0 += SEG_ILP) {
-      float r[SEG_ILP][NQ];
+  for (int q = 0; q < NQ; ++q) acc[q] = 0.f;
+  int key = __shfl_sync(0xffffffffu, k0, 0), run_a = 0;  // the open run: its key and first entry
+  auto flush = [&](int b) {                               // the open run ends before entry b
+    if (key >= n_rows) return;                            // ids outside the table (make_keys_kernel) are dropped
+    const bool left = run_a == 0 && key == key_before, right = b == cnt && key == key_after;
+    if (!left && !right) {
 #pragma unroll
-      for (int u = 0; u < SEG_ILP; ++u)
+      for (int q = 0; q < NQ; ++q)
+        if (col[q]) seg_store(out, (size_t)key * w + lane + 32 * q, acc[q]);
+    } else {
+      const int64_t slot = 2 * chunk + (run_a == 0 ? 0 : 1);
+      if (lane == 0) {
+        part_key[slot] = key;
+        part_start[slot] = left ? 0 : 1;
+      }
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) r[u][q] = (j0 + u < b && col[q]) ? __ldcs(base + (size_t)(j0 + u) * w + lane + 32 * q) : 0.f;
-#pragma unroll
-      for (int u = 0; u < SEG_ILP; ++u)
-        if (j0 + u < b) {  // (skipped, not "+ 0": -0.f + 0.f would flip a sign bit the serial sum keeps)
-#pragma unroll
-          for (int q = 0; q < NQ; ++q) acc[q] += r[u][q];
-        }
+      for (int q = 0; q < NQ; ++q)
+        if (col[q]) part_rows[(size_t)slot * w + lane + 32 * q] = acc[q];
     }
-    if (key < n_rows) {  // ids outside the table (make_keys_kernel) are dropped
-      const bool left = a == 0 && key == key_before, right = b == cnt && key == key_after;
-      if (!left && !right) {
+  };
+  // rows are fetched SEG_ILP entries at a time whatever the run structure is (unique keys = runs of one entry must not turn
+  // into a chain of dependent load -> store round trips); the run bookkeeping is a bit test per entry
+  for (int j0 = 0; j0 < cnt; j0 += SEG_ILP) {
+    float r[SEG_ILP][NQ];
 #pragma unroll
-        for (int q = 0; q < NQ; ++q)
-          if (col[q]) seg_store(out, (size_t)key * w + lane + 32 * q, acc[q]);
-      } else {
-        const int64_t slot = 2 * chunk + (a == 0 ? 0 : 1);
-        if (lane == 0) {
-          part_key[slot] = key;
-          part_start[slot] = left ? 0 : 1;
+    for (int u = 0; u < SEG_ILP; ++u)
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) r[u][q] = (j0 + u < cnt && col[q]) ? __ldcs(base + (size_t)(j0 + u) * w + lane + 32 * q) : 0.f;
+#pragma unroll
+    for (int u = 0; u < SEG_ILP; ++u) {
+      const int j = j0 + u;
+      if (j < cnt) {
+        if (j > 0 && ((starts >> j) & 1ull)) {
+          flush(j);
+          run_a = j;
+          key = j < 32 ? __shfl_sync(0xffffffffu, k0, j) : __shfl_sync(0xffffffffu, k1, j - 32);
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) acc[q] = 0.f;
         }
 #pragma unroll
-        for (int q = 0; q < NQ; ++q)
-          if (col[q]) part_rows[(size_t)slot * w + lane + 32 * q] = acc[q];
+        for (int q = 0; q < NQ; ++q) acc[q] += r[u][q];
       }
     }
-    a = b;
   }
+  flush(cnt);
 }
 
 // Pass 2: one warp per partial that STARTS a run; the chunks that continue it are found 32 at a time (one ballot, no chain of
@@ -717,7 +739,8 @@ struct BwdLayout {
 static int bwd_grid() { return 148 * 2; }
 
 // lists: 0 = history ids (B*H entries), 1 = target ids (B), 2 = region ids of both (B*H + B)
-static BwdLayout bwd_layout(const NaisParams& p, int64_t B, int H) {
+static BwdLayout bwd_layout(const NaisParams& p, const NaisPairs& b) {
+  const int64_t B = b.B;
   BwdLayout L;
   int D = 0, w_poi = 0, w_reg = 0;
   for (int i = 0; i < p.n_branch; ++i) {
@@ -727,7 +750,7 @@ static BwdLayout bwd_layout(const NaisParams& p, int64_t B, int H) {
     w_reg = w_reg > br.w_reg ? w_reg : br.w_reg;
   }
   const int lanes = p.dist_mode == NAIS_DIST_LATLON ? 2 : 0;
-  const int64_t n_cells = B * H, n_max = n_cells + B;
+  const int64_t n_cells = pairs_n_cells(b), n_max = n_cells + B;
   const int64_t n_of[3] = {n_cells, B, n_max};
   size_t o = 0;
   L.dq_h = o;
@@ -766,14 +789,14 @@ static BwdLayout bwd_layout(const NaisParams& p, int64_t B, int H) {
   return L;
 }
 
-size_t pairs_bwd_workspace_bytes(const NaisParams& p, int64_t B, int H) { return bwd_layout(p, B, H).total; }
+size_t pairs_bwd_workspace_bytes(const NaisParams& p, const NaisPairs& b) { return bwd_layout(p, b).total; }
 
 template <int NKB, int DB>
 static int launch_bwd_tile(const BwdArgs& A, int D, int grid, cudaStream_t stream) {
   constexpr int HP = NKB * KB;
   const size_t fl = (size_t)D * TCP + (size_t)HP * TCP + (size_t)D * KB + NKB * 4 * KB + 8 * TC + 16 * HP +
                     2 * (size_t)BWD_MAXROWS * D + 4 * BWD_MAXROWS + 8 * (NT / 32);
-  const size_t smem = fl * 4 + 3 * TC * 4 + TC * 8 + 8;
+  const size_t smem = fl * 4 + 3 * TC * 4 + TC * 8 + TC * 4 + 8;
   cudaError_t e = cudaFuncSetAttribute(pairs_bwd_kernel<NKB, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   pairs_bwd_kernel<NKB, DB><<<grid, NT, smem, stream>>>(A);
@@ -784,13 +807,13 @@ static int launch_bwd_tile(const BwdArgs& A, int D, int grid, cudaStream_t strea
 int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score_parts, const float* row_sum,
                      const unsigned long long* act_mask, const float* dscore, const NaisGrads& g, const NaisAdagrad* opt, void* ws,
                      size_t ws_bytes, cudaStream_t stream) {
-  if (b.B * (int64_t)b.H + b.B >= 0x7fffffffLL) return NAIS_ERR_SHAPE;
+  if (pairs_n_cells(b) + b.B >= 0x7fffffffLL) return NAIS_ERR_SHAPE;
   if (opt && p.n_branch != 1) return NAIS_ERR_MODE;  // two branches share tables: two sparse steps != one dense step
-  const BwdLayout L = bwd_layout(p, b.B, b.H);
+  const BwdLayout L = bwd_layout(p, b);
   if (ws_bytes < L.total) return NAIS_ERR_WORKSPACE;
   char* base = reinterpret_cast<char*>(ws);
   const int lanes = p.dist_mode == NAIS_DIST_LATLON ? 2 : 0;
-  const int64_t n_cells = b.B * (int64_t)b.H;
+  const int64_t n_cells = pairs_n_cells(b);
   const int64_t n_of[3] = {n_cells, b.B, n_cells + b.B};
   auto I = [&](size_t off) { return reinterpret_cast<int*>(base + off); };
   auto U = [&](size_t off) { return reinterpret_cast<uint32_t*>(base + off); };
@@ -841,10 +864,8 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
     A.pos_r = U(L.pos[2]);
     A.ws_part = reinterpret_cast<float*>(base + L.part);
     A.part_stride = L.stride;
-    int rpt = (b.H <= TC) ? TC / b.H : 1;
-    if (rpt > BWD_MAXROWS) rpt = BWD_MAXROWS;
-    A.rows_per_tile = rpt;
-    A.n_items = (b.B + rpt - 1) / rpt;
+    A.n_items = pairs_n_tiles(b);
+    if (A.n_items < 1) return 0;
     int grid = (int)(A.n_items < L.grid ? A.n_items : L.grid);
     int rc;
     const int nkb = p.hid <= 64 ? 1 : 2, db = D <= 64 ? 1 : 2;

@@ -5,7 +5,7 @@
 
 namespace nais {
 
-constexpr int BWD_MAXROWS = 16;
+constexpr int BWD_MAXROWS = 16;  // == PAIR_MAXROWS (nais_pairs_tile.cuh)
 
 struct BwdArgs {
   NaisParams p;
@@ -26,8 +26,7 @@ struct BwdArgs {
   const uint32_t* pos_t;  // [B]
   float* ws_part;         // [grid, part_stride]
   int part_stride;
-  int rows_per_tile;
-  int64_t n_items;        // work items (tiles of rows)
+  int64_t n_items;        // work items (tiles of rows: nais_pairs_tile.cuh)
   int* bad;               // the library's bad-index word (nais_common.cuh)
 };
 

@@ -17,7 +17,7 @@ int launch_topk_merge_keys_multi(const unsigned long long* keys, unsigned long l
 int merge_scratch_lists(int n_lists, int k);
 int choose_splits(int n_users, int64_t range);
 // nais_bwd.cu
-size_t pairs_bwd_workspace_bytes(const NaisParams& p, int64_t B, int H);
+size_t pairs_bwd_workspace_bytes(const NaisParams& p, const NaisPairs& b);
 int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score_parts, const float* row_sum,
                      const unsigned long long* act_mask, const float* dscore, const NaisGrads& g, const NaisAdagrad* opt, void* ws,
                      size_t ws_bytes, cudaStream_t stream);
@@ -37,6 +37,10 @@ int fullrank_tc_prepare(const NaisParams& p, const NaisCatalog& cat, int64_t poi
 int fullrank_tc_run(const NaisParams& p, const NaisCatalog& cat, const NaisUsers& users, int64_t poi_begin, int64_t poi_end, int k,
                     int exclude, int precision, const void* plan, size_t plan_bytes, unsigned long long* out_keys, float* out_score,
                     int32_t* out_id, float* all_scores, void* ws, size_t ws_bytes, cudaStream_t stream);
+// nais_sampler.cu
+int launch_sample_batch(const int64_t* seg_offsets, const int64_t* hist, int n_seg, const int64_t* row_offsets, int num_ng, int item_num,
+                        const int32_t* poi_region, const float* poi_coords, uint64_t seed, int max_hist, int64_t* tgt, float* label,
+                        int64_t* treg, float* tgt_coords, cudaStream_t stream);
 // nais_pairs_tc.cu
 bool pairs_tc_supported(const NaisParams& p, const NaisPairs& b);
 int launch_pairs_fwd_tc(const NaisParams& p, const NaisPairs& b, float* score, float* row_sum, float* parts,
@@ -80,12 +84,21 @@ static int check_params(const NaisParams* p) {
 
 static int check_pairs(const NaisParams* p, const NaisPairs* b) {
   if (!b) return NAIS_ERR_NULL;
-  if (b->B < 0 || b->H < 1) return NAIS_ERR_SHAPE;
+  const bool seg = b->seg_offsets != nullptr;
+  if (b->B < 0 || (!seg && b->H < 1)) return NAIS_ERR_SHAPE;
   if (b->B == 0) return 0;
   if (!b->hist || !b->tgt) return NAIS_ERR_NULL;
   bool need_reg = false;
   for (int i = 0; i < p->n_branch; ++i) need_reg |= p->branch[i].w_reg > 0;
   if (need_reg && (!b->hreg || !b->treg)) return NAIS_ERR_NULL;
+  if (seg) {  // segmented (multi-user) layout: shared histories, distances formed in the kernel
+    if (b->n_seg < 1 || b->n_tiles < 0 || b->n_cells < 0) return NAIS_ERR_SHAPE;
+    if (!b->row_offsets || !b->seg_cell_offsets || (b->n_tiles && (!b->tile_seg || !b->tile_row0))) return NAIS_ERR_NULL;
+    if (b->aux) return NAIS_ERR_MODE;
+    if (p->dist_mode == NAIS_DIST_KM || p->dropout_p > 0.f) return NAIS_ERR_MODE;
+    if (p->dist_mode == NAIS_DIST_LATLON && (!b->hist_coords || !b->tgt_coords)) return NAIS_ERR_NULL;
+    return 0;
+  }
   if (p->dist_mode != NAIS_DIST_NONE && !b->aux) return NAIS_ERR_NULL;
   return 0;
 }
@@ -198,11 +211,23 @@ static bool device_is_sm100() {
   return major == 10;
 }
 
+int nais_sample_batch(const int64_t* seg_offsets, const int64_t* hist, int32_t n_seg, const int64_t* row_offsets, int32_t num_ng,
+                      int32_t item_num, const int32_t* poi_region, const float* poi_coords, uint64_t seed, int32_t max_hist,
+                      int64_t* tgt, float* label, int64_t* treg, float* tgt_coords, nais_stream_t stream) {
+  if (n_seg < 0 || num_ng < 0 || item_num < 1 || max_hist < 0) return NAIS_ERR_SHAPE;
+  if (n_seg == 0) return 0;
+  if (!seg_offsets || !hist || !row_offsets || !tgt || !label) return NAIS_ERR_NULL;
+  if ((treg && !poi_region) || (tgt_coords && !poi_coords)) return NAIS_ERR_NULL;
+  if ((int64_t)max_hist * (num_ng + 1) >= item_num) return NAIS_ERR_SHAPE;  // not enough unvisited POIs to draw from
+  return launch_sample_batch(seg_offsets, hist, n_seg, row_offsets, num_ng, item_num, poi_region, poi_coords, seed, max_hist, tgt,
+                             label, treg, tgt_coords, static_cast<cudaStream_t>(stream));
+}
+
 int nais_pairs_dispatch(const NaisParams* p, const NaisPairs* batch, int32_t* fwd_tc, int32_t* bwd_tc) {
   int rc = check_params(p);
   if (rc) return rc;
   if (!batch || !fwd_tc || !bwd_tc) return NAIS_ERR_NULL;
-  if (batch->B < 0 || batch->H < 1) return NAIS_ERR_SHAPE;
+  if (batch->B < 0 || (!batch->seg_offsets && batch->H < 1)) return NAIS_ERR_SHAPE;
   NaisPairs b = *batch;
   if (b.B == 0) b.B = 1;  // the choice does not depend on the row count
   const bool f_ok = pairs_tc_supported(*p, b) && device_is_sm100(), b_ok = pairs_tc_bwd_supported(*p, b);
@@ -228,9 +253,9 @@ int nais_pairs_forward(const NaisParams* p, const NaisPairs* batch, float* score
   return launch_pairs_fwd(*p, *batch, score, row_sum, score_parts, static_cast<cudaStream_t>(stream));
 }
 
-size_t nais_pairs_backward_workspace_bytes(const NaisParams* p, int64_t B, int32_t H) {
-  if (check_params(p) || B < 0 || H < 1) return 0;
-  return pairs_bwd_workspace_bytes(*p, B, H);
+size_t nais_pairs_backward_workspace_bytes(const NaisParams* p, const NaisPairs* batch) {
+  if (check_params(p) || !batch || batch->B < 0 || (!batch->seg_offsets && batch->H < 1)) return 0;
+  return pairs_bwd_workspace_bytes(*p, *batch);
 }
 
 int nais_pairs_backward(const NaisParams* p, const NaisPairs* batch, const float* score_parts, const float* row_sum,
@@ -244,7 +269,7 @@ int nais_pairs_backward(const NaisParams* p, const NaisPairs* batch, const float
   if (batch->B == 0) return 0;
   if (!score_parts || !row_sum || !dscore || !workspace) return NAIS_ERR_NULL;
   if (!aligned16(workspace)) return NAIS_ERR_ALIGN;
-  if (workspace_bytes < pairs_bwd_workspace_bytes(*p, batch->B, batch->H)) return NAIS_ERR_WORKSPACE;
+  if (workspace_bytes < pairs_bwd_workspace_bytes(*p, *batch)) return NAIS_ERR_WORKSPACE;
   return launch_pairs_bwd(*p, *batch, score_parts, row_sum, reinterpret_cast<const unsigned long long*>(act_mask), dscore, *grads,
                           nullptr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
@@ -262,7 +287,7 @@ int nais_pairs_backward_adagrad(const NaisParams* p, const NaisPairs* batch, con
   if (batch->B == 0) return 0;
   if (!score_parts || !row_sum || !dscore || !workspace) return NAIS_ERR_NULL;
   if (!aligned16(workspace)) return NAIS_ERR_ALIGN;
-  if (workspace_bytes < pairs_bwd_workspace_bytes(*p, batch->B, batch->H)) return NAIS_ERR_WORKSPACE;
+  if (workspace_bytes < pairs_bwd_workspace_bytes(*p, *batch)) return NAIS_ERR_WORKSPACE;
   return launch_pairs_bwd(*p, *batch, score_parts, row_sum, reinterpret_cast<const unsigned long long*>(act_mask), dscore, *grads,
                           opt, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }

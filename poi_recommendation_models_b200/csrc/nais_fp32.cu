@@ -8,6 +8,7 @@
 // The B x H x (D+2) pair tensor of the reference (model.py:266-269) only ever exists as one 128-cell tile in
 // shared memory.
 #include "nais_common.cuh"
+#include "nais_pairs_tile.cuh"
 
 namespace nais {
 
@@ -179,16 +180,14 @@ struct PairsFwdArgs {
   float* score;    // [B]
   float* row_sum;  // [n_branch,B] or NULL
   float* parts;    // [n_branch,B] per-branch score or NULL
-  int rows_per_tile;
   int* bad;        // the library's bad-index word (nais_common.cuh)
 };
 
-constexpr int MAXROWS = 16;  // rows (targets) sharing one 128-cell tile when H is small
+constexpr int MAXROWS = PAIR_MAXROWS;  // rows (targets) sharing one 128-cell tile when H is small
 
 __global__ void __launch_bounds__(NT, 2) pairs_fwd_kernel(const __grid_constant__ PairsFwdArgs A) {
   extern __shared__ __align__(16) float smem[];
   const NaisParams& p = A.p;
-  const int H = A.b.H;
   const int lanes = (p.dist_mode == NAIS_DIST_LATLON) ? 2 : 0;
   int Dmax = 0;
   for (int i = 0; i < p.n_branch; ++i) Dmax = max(Dmax, p.branch[i].w_poi + p.branch[i].w_reg);
@@ -201,7 +200,6 @@ __global__ void __launch_bounds__(NT, 2) pairs_fwd_kernel(const __grid_constant_
   float* row_es = row_e + MAXROWS;         // [MAXROWS] running sum E*s
   __shared__ float km_c;
 
-  const int n_chunks = (H <= TC) ? 1 : (H + TC - 1) / TC;
   const int tid = threadIdx.x, cell = tid & (TC - 1), half = tid >> 7;
   int resident = -1;
   DropCtx dc{0u, 1.f, p.dropout_seed, p.hid};
@@ -210,10 +208,12 @@ __global__ void __launch_bounds__(NT, 2) pairs_fwd_kernel(const __grid_constant_
     dc.inv_keep = 1.f / (1.f - p.dropout_p);
   }
   // persistent over work items (groups of rows): the W^T block stays resident in shared memory across items
-  const int64_t n_items = (A.b.B + A.rows_per_tile - 1) / A.rows_per_tile;
+  const int64_t n_items = pairs_n_tiles(A.b);
   for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-  const int64_t row0 = item * A.rows_per_tile;
-  const int nrows = (int)min((int64_t)A.rows_per_tile, A.b.B - row0);
+  const PairTile T = pair_tile(A.b, item);
+  const int64_t row0 = T.row0;
+  const int nrows = T.nrows, H = T.H;
+  const int n_chunks = (H <= TC) ? 1 : (H + TC - 1) / TC;
   float my_total = 0.f;  // thread r (< nrows) accumulates the final score of row r over branches
 
   for (int bi = 0; bi < p.n_branch; ++bi) {
@@ -248,14 +248,15 @@ __global__ void __launch_bounds__(NT, 2) pairs_fwd_kernel(const __grid_constant_
         h = ch * TC + cell;
         valid = h < H;
       }
-      const int64_t cidx = valid ? (row0 + r) * (int64_t)H + h : 0;
+      const int64_t cidx = valid ? T.cell0 + r * (int64_t)H + h : 0;  // per-cell arrays
+      const int64_t hidx = valid ? T.hist0 + r * T.hist_rs + h : 0;   // history arrays
       // build x = q (.) p for this thread's d-half, similarity partial, distance lanes
       {
         const int d0 = half ? (D >> 1) : 0, d1 = half ? D : (D >> 1);
         float ssum = 0.f;
         if (valid) {
-          const int item = checked_id(A.b.hist[cidx], p.item_num, A.bad);
-          const int reg = br.w_reg ? checked_id(A.b.hreg[cidx], p.region_num, A.bad) : 0;
+          const int item = checked_id(A.b.hist[hidx], p.item_num, A.bad);
+          const int reg = br.w_reg ? checked_id(A.b.hreg[hidx], p.region_num, A.bad) : 0;
           const float* qp = br.hist_poi + (size_t)item * br.w_poi;
           const float* qr = br.hist_reg + (size_t)reg * br.w_reg;
           if (vec4) {  // 128-bit row loads: 4x fewer L1 requests than the scalar walk, same products in the same order
@@ -290,7 +291,9 @@ __global__ void __launch_bounds__(NT, 2) pairs_fwd_kernel(const __grid_constant_
           s.cg[cell] = cidx;
           float g0 = 0.f, g1 = 0.f;
           if (valid && p.dist_mode == NAIS_DIST_LATLON) {
-            dist_lanes(p, A.b.aux[cidx * 2], A.b.aux[cidx * 2 + 1], g0, g1);
+            float l0, l1;
+            pair_latlon(A.b, cidx, hidx, row0 + r, l0, l1);
+            dist_lanes(p, l0, l1, g0, g1);
           } else if (valid && p.dist_mode == NAIS_DIST_KM) {
             float km = A.b.aux[cidx];
             g0 = km * (p.dist_buckets == 1 ? km_c : km_coef(p, D, km));
@@ -306,7 +309,7 @@ __global__ void __launch_bounds__(NT, 2) pairs_fwd_kernel(const __grid_constant_
         if (valid) {
           float a = s.a[cell];
           if (p.dist_mode == NAIS_DIST_KM) a += s.g[cell];
-          const bool m = A.b.hist[cidx] != A.b.tgt[row0 + r];
+          const bool m = A.b.hist[hidx] != A.b.tgt[row0 + r];
           e = m ? expf(a) : 0.f;
           es = e * (s.sp[cell] + s.sp[TC + cell]);
           if (!m) es = 0.f;  // exp overflow * 0 must stay 0, like the reference's exp_A * mask then * history
@@ -581,15 +584,13 @@ int launch_pairs_fwd(const NaisParams& p, const NaisPairs& b, float* score, floa
   A.row_sum = row_sum;
   A.parts = parts;
   A.bad = bad_index_flag();
-  int rpt = (b.H <= TC) ? TC / b.H : 1;
-  if (rpt > MAXROWS) rpt = MAXROWS;
-  A.rows_per_tile = rpt;
   const int D = max_D(p);
   const size_t smem = (tile_smem_floats(D) + (size_t)MAXROWS * D + 2 * TC + 2 * MAXROWS) * sizeof(float);
   if (smem > 227 * 1024) return NAIS_ERR_SHAPE;
   cudaError_t e = cudaFuncSetAttribute(pairs_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  int64_t grid = (b.B + rpt - 1) / rpt;
+  int64_t grid = pairs_n_tiles(b);
+  if (grid < 1) return 0;
   if (grid > 148 * 4) grid = 148 * 4;
   pairs_fwd_kernel<<<(unsigned)grid, NT, smem, stream>>>(A);
   NAIS_COUNT_LAUNCH(1);

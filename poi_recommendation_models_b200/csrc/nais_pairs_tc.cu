@@ -14,6 +14,7 @@
 #include <cstdlib>
 
 #include "nais_common.cuh"
+#include "nais_pairs_tile.cuh"
 #include "umma.cuh"
 
 namespace nais {
@@ -21,7 +22,7 @@ namespace ptc {
 using namespace umma;
 
 constexpr int PT = 128;        // threads per CTA = cells per tile = TMEM lanes
-constexpr int PMAXROWS = 16;   // rows (targets) sharing one tile when H is small
+constexpr int PMAXROWS = PAIR_MAXROWS;  // rows (targets) sharing one tile when H is small
 constexpr int STG_STRIDE = 144;  // bytes per staged row segment: 32 floats + 16 B skew (conflict-free per-thread read-back)
 
 struct Args {
@@ -30,8 +31,7 @@ struct Args {
   float* score;    // [B]
   float* row_sum;  // [B] or NULL
   float* parts;    // [B] or NULL
-  unsigned long long* act_mask;  // [B*H] ReLU pattern per cell (hid <= 64) or NULL
-  int rows_per_tile;
+  unsigned long long* act_mask;  // [cells] ReLU pattern per cell (hid <= 64) or NULL
   uint32_t tmem_cols;
   int* bad;  // the library's bad-index word (nais_common.cuh)
 };
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(PT, (D > 48) ? 3 : 4) pairs_fwd_tc_kernel(cons
   extern __shared__ __align__(128) uint8_t smem[];
   const NaisParams& p = A.p;
   const NaisBranch& br = p.branch[0];
-  const int hid = p.hid, H = A.b.H;
+  const int hid = p.hid;
   const int lanes = (p.dist_mode == NAIS_DIST_LATLON) ? 2 : 0, ldw = D + lanes;
   constexpr int KC = D / 8;                // 16-byte k-chunks along K
   constexpr int A_PLANE = KC * PT * 16;    // one fp16 plane of the X tile
@@ -111,12 +111,13 @@ __global__ void __launch_bounds__(PT, (D > 48) ? 3 : 4) pairs_fwd_tc_kernel(cons
   const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);  // warp w owns TMEM lanes 32w .. 32w+31
   const bool vec4 = rows_vec4(br, 4);
 
-  const int n_chunks = (H <= PT) ? 1 : (H + PT - 1) / PT;
-  const int64_t n_items = (A.b.B + A.rows_per_tile - 1) / A.rows_per_tile;
+  const int64_t n_items = pairs_n_tiles(A.b);
   uint32_t phase = 0;
   for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int64_t row0 = item * A.rows_per_tile;
-    const int nrows = (int)min((int64_t)A.rows_per_tile, A.b.B - row0);
+    const PairTile T = pair_tile(A.b, item);
+    const int64_t row0 = T.row0;
+    const int nrows = T.nrows, H = T.H;
+    const int n_chunks = (H <= PT) ? 1 : (H + PT - 1) / PT;
     for (int i = tid; i < nrows * D; i += PT) {
       const int r = i / D, d = i - r * D;
       ps[r * D + d] = (d < br.w_poi) ? __ldg(br.tgt_poi + (size_t)checked_id(A.b.tgt[row0 + r], p.item_num, A.bad) * br.w_poi + d)
@@ -139,15 +140,16 @@ __global__ void __launch_bounds__(PT, (D > 48) ? 3 : 4) pairs_fwd_tc_kernel(cons
         h = ch * PT + tid;
         valid = h < H;
       }
-      const int64_t cidx = valid ? (row0 + r) * (int64_t)H + h : 0;
+      const int64_t cidx = valid ? T.cell0 + r * (int64_t)H + h : 0;      // per-cell arrays
+      const int64_t hidx = valid ? T.hist0 + r * T.hist_rs + h : 0;       // history arrays
       // ---- build this cell's row of X -------------------------------------------------------------------------------------
       float x[D];
       float ssum = 0.f, amax = 0.f, g0 = 0.f, g1 = 0.f;
       bool live = false;  // valid and not masked (history item != target)
       int it32 = 0, rg32 = 0;  // POI / region id of this cell (ids fit int32: item_num is int32); row 0 for padding cells
       if (valid) {
-        it32 = checked_id(A.b.hist[cidx], p.item_num, A.bad);
-        rg32 = br.w_reg ? checked_id(A.b.hreg[cidx], p.region_num, A.bad) : 0;
+        it32 = checked_id(A.b.hist[hidx], p.item_num, A.bad);
+        rg32 = br.w_reg ? checked_id(A.b.hreg[hidx], p.region_num, A.bad) : 0;
       }
       if (vec4) {
         // Warp-cooperative gather: consecutive lanes read consecutive 16 B of the SAME table row, so one request covers whole
@@ -211,11 +213,14 @@ __global__ void __launch_bounds__(PT, (D > 48) ? 3 : 4) pairs_fwd_tc_kernel(cons
           amax = fmaxf(amax, fabsf(x[d]));
         }
         if (lanes) {
-          const float l0 = A.b.aux[cidx * 2] * p.dist_scale, l1 = A.b.aux[cidx * 2 + 1] * p.dist_scale;
+          float l0, l1;
+          pair_latlon(A.b, cidx, hidx, row0 + r, l0, l1);
+          l0 *= p.dist_scale;
+          l1 *= p.dist_scale;
           g0 = sigmoidf_exact(fmaf(l1, __ldg(p.dist_w + 1), fmaf(l0, __ldg(p.dist_w + 0), __ldg(p.dist_b + 0))));
           g1 = sigmoidf_exact(fmaf(l1, __ldg(p.dist_w + 3), fmaf(l0, __ldg(p.dist_w + 2), __ldg(p.dist_b + 1))));
         }
-        live = A.b.hist[cidx] != A.b.tgt[row0 + r];
+        live = A.b.hist[hidx] != A.b.tgt[row0 + r];
       } else {
 #pragma unroll
         for (int d = 0; d < D; ++d) x[d] = 0.f;
@@ -364,11 +369,9 @@ int launch_pairs_fwd_tc(const NaisParams& p, const NaisPairs& b, float* score, f
   A.parts = parts;
   A.act_mask = p.hid <= 64 ? act_mask : nullptr;
   A.bad = bad_index_flag();
-  int rpt = (b.H <= ptc::PT) ? ptc::PT / b.H : 1;
-  if (rpt > ptc::PMAXROWS) rpt = ptc::PMAXROWS;
-  A.rows_per_tile = rpt;
   A.tmem_cols = p.hid <= 32 ? 32u : (p.hid <= 64 ? 64u : 128u);
-  const int64_t n_items = (b.B + rpt - 1) / rpt;
+  const int64_t n_items = pairs_n_tiles(b);
+  if (n_items < 1) return 0;
   const int D = p.branch[0].w_poi + p.branch[0].w_reg;
   switch (D) {
     case 16: return ptc::launch<16>(A, p.hid, n_items, sms, stream);

@@ -20,6 +20,7 @@
 #include <cstdlib>
 
 #include "nais_bwd_args.cuh"
+#include "nais_pairs_tile.cuh"
 #include "umma.cuh"
 
 namespace nais {
@@ -86,7 +87,6 @@ __global__ void __launch_bounds__(PT, 2) pairs_bwd_tc_kernel(const __grid_consta
   extern __shared__ __align__(128) uint8_t smem[];
   const NaisParams& p = A.p;
   const NaisBranch& br = p.branch[A.bi];
-  const int H = A.b.H;
   const int lanes = (p.dist_mode == NAIS_DIST_LATLON) ? 2 : 0, ldw = D + lanes;
   constexpr int XC = D / 8 + 1;                 // k-chunks of the X image: D/8 + the ext chunk [1 g0 g1 0 0 0 0 0]
   constexpr int X_PLANE = XC * PT * 16, W_PLANE = (D / 8) * HID * 16, DT_PLANE = (HID / 8) * PT * 16;
@@ -135,12 +135,14 @@ __global__ void __launch_bounds__(PT, 2) pairs_bwd_tc_kernel(const __grid_consta
   float pd[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // dist_w[4], dist_b[2] partials of this thread's cells
   float dv_acc[2] = {0.f, 0.f};                  // dw2 partial of hidden units dv_k0, dv_k0 + 1 over this warp's cells
   const int dv_k0 = 32 * ((lane >> 4) & 1) + 16 * ((lane >> 3) & 1) + 8 * ((lane >> 2) & 1) + 4 * ((lane >> 1) & 1) + 2 * (lane & 1);
-  const int n_chunks = (H <= PT) ? 1 : (H + PT - 1) / PT;
   uint32_t phase = 0, dw_started = 0;
+  const int64_t n_cells = pairs_n_cells(A.b);
 
   for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x) {
-    const int64_t row0 = item * A.rows_per_tile;
-    const int nrows = (int)min((int64_t)A.rows_per_tile, A.b.B - row0);
+    const PairTile T = pair_tile(A.b, item);
+    const int64_t row0 = T.row0;
+    const int nrows = T.nrows, H = T.H;
+    const int n_chunks = (H <= PT) ? 1 : (H + PT - 1) / PT;
     for (int i = tid; i < nrows * D; i += PT) {
       const int r = i / D, d = i - r * D;
       ps[i] = (d < br.w_poi) ? __ldg(br.tgt_poi + (size_t)checked_id(A.b.tgt[row0 + r], p.item_num, A.bad) * br.w_poi + d)
@@ -167,7 +169,8 @@ __global__ void __launch_bounds__(PT, 2) pairs_bwd_tc_kernel(const __grid_consta
         h = ch * PT + tid;
         valid = h < H;
       }
-      const int64_t cidx = valid ? (row0 + r) * (int64_t)H + h : 0;
+      const int64_t cidx = valid ? T.cell0 + r * (int64_t)H + h : 0;  // per-cell arrays
+      const int64_t hidx = valid ? T.hist0 + r * T.hist_rs + h : 0;   // history arrays
       int it32 = 0, rg32 = 0;
       float l0r = 0.f, l1r = 0.f;
       bool live = false;
@@ -175,13 +178,10 @@ __global__ void __launch_bounds__(PT, 2) pairs_bwd_tc_kernel(const __grid_consta
       if (valid) {
         if (A.dq_h) pos_h = __ldg(A.pos_h + cidx);
         if (A.dq_r) pos_r = __ldg(A.pos_r + cidx);
-        it32 = checked_id(A.b.hist[cidx], p.item_num, A.bad);
-        rg32 = br.w_reg ? checked_id(A.b.hreg[cidx], p.region_num, A.bad) : 0;
-        if (lanes) {
-          l0r = A.b.aux[cidx * 2];
-          l1r = A.b.aux[cidx * 2 + 1];
-        }
-        live = A.b.hist[cidx] != A.b.tgt[row0 + r];
+        it32 = checked_id(A.b.hist[hidx], p.item_num, A.bad);
+        rg32 = br.w_reg ? checked_id(A.b.hreg[hidx], p.region_num, A.bad) : 0;
+        if (lanes) pair_latlon(A.b, cidx, hidx, row0 + r, l0r, l1r);
+        live = A.b.hist[hidx] != A.b.tgt[row0 + r];
       }
       float g0 = 0.f, g1 = 0.f;
       if (valid && lanes) {
@@ -388,8 +388,7 @@ __global__ void __launch_bounds__(PT, 2) pairs_bwd_tc_kernel(const __grid_consta
     }
     for (int i = tid; i < nrows * D; i += PT) {
       const int64_t row = row0 + i / D;
-      store_dp(A, br.w_poi, br.w_reg, A.dp_t ? __ldg(A.pos_t + row) : 0u, A.dq_r ? __ldg(A.pos_r + A.b.B * (int64_t)H + row) : 0u, i % D,
-               dpacc[i]);
+      store_dp(A, br.w_poi, br.w_reg, A.dp_t ? __ldg(A.pos_t + row) : 0u, A.dq_r ? __ldg(A.pos_r + n_cells + row) : 0u, i % D, dpacc[i]);
     }
     __syncthreads();
   }
@@ -455,6 +454,7 @@ bool pairs_tc_bwd_supported(const NaisParams& p, const NaisPairs& b) {
   if (D != 32 && D != 64) return false;
   if (p.dist_mode == NAIS_DIST_KM || p.dropout_p > 0.f) return false;
   if (!rows_vec4(br, 4)) return false;
+  (void)b;
   int dev = 0, major = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);

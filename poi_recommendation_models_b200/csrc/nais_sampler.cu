@@ -1,0 +1,155 @@
+// Device-side training-batch construction: the negative sampling and target / label layout of
+// batches.py:67-108 `get_NAIS_batch_region`, for MANY users per call, without the O(N) Python set difference + shuffle per
+// user (0.034 s per user at N = 38k) and without any host -> device copy of the batch.
+//
+// Per segment (= user) s with history items hist[seg_offsets[s] .. seg_offsets[s+1]) (H_s of them) the kernel emits
+// (num_ng + 1) * H_s rows starting at row_offsets[s], interleaved like the reference (batches.py:84-95):
+//     [p_0, n_0,1 .. n_0,g, p_1, n_1,1 .. ]      label 1 for the positive, 0 for its g = num_ng negatives
+// Negatives: H_s * num_ng POIs drawn uniformly WITHOUT replacement from the POIs the user has not visited.  The reference
+// shuffles the whole complement and takes a prefix (batches.py:77-80) — the same distribution.  Here: rejection sampling
+// against a per-segment hash set in shared memory that holds the history and everything drawn so far, with a counter-based
+// generator keyed by (seed, segment, slot, attempt): reproducible for a given seed, independent of scheduling (a warp works
+// on 32 slots at a time; membership is tested before any insert of the round, duplicates inside the round are resolved in
+// favour of the lowest lane).  Positives keep their stored order (the reference shuffles them: row order changes no sum).
+#include "nais_common.cuh"
+
+namespace nais {
+namespace smp {
+
+constexpr int WARPS = 4;  // segments per CTA
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint32_t slot_of(uint32_t v, uint32_t cap_mask) { return (v * 0x9E3779B1u) & cap_mask; }
+
+// open addressing, keys stored as v + 1 (0 = empty)
+__device__ __forceinline__ bool set_contains(const uint32_t* tab, uint32_t cap_mask, uint32_t v) {
+  for (uint32_t i = slot_of(v, cap_mask);; i = (i + 1) & cap_mask) {
+    const uint32_t e = tab[i];
+    if (e == 0u) return false;
+    if (e == v + 1u) return true;
+  }
+}
+__device__ __forceinline__ void set_insert(uint32_t* tab, uint32_t cap_mask, uint32_t v) {
+  for (uint32_t i = slot_of(v, cap_mask);; i = (i + 1) & cap_mask) {
+    const uint32_t old = atomicCAS(&tab[i], 0u, v + 1u);
+    if (old == 0u || old == v + 1u) return;
+  }
+}
+
+struct Args {
+  const int64_t* seg_offsets;
+  const int64_t* hist;
+  const int64_t* row_offsets;
+  int n_seg, num_ng, item_num;
+  const int32_t* poi_region;  // [item_num] or NULL
+  const float* poi_coords;    // [item_num, 2] centred or NULL
+  uint64_t seed;
+  int64_t* tgt;
+  float* label;
+  int64_t* treg;      // or NULL
+  float* tgt_coords;  // or NULL
+  uint32_t cap;       // hash capacity per segment (power of two >= 2 * max rows of a segment + 2 * max history)
+  int* bad;
+};
+
+__global__ void __launch_bounds__(WARPS * 32) sample_batch_kernel(const Args A) {
+  extern __shared__ uint32_t tabs[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * WARPS + warp;
+  if (s >= A.n_seg) return;
+  uint32_t* tab = tabs + (size_t)warp * A.cap;
+  const uint32_t mask = A.cap - 1u;
+  for (uint32_t i = lane; i < A.cap; i += 32) tab[i] = 0u;
+  __syncwarp();
+  const int64_t h0 = A.seg_offsets[s];
+  const int H = (int)(A.seg_offsets[s + 1] - h0);
+  const int64_t row0 = A.row_offsets[s];
+  const int g = A.num_ng;
+  auto emit = [&](int64_t row, int poi, float lab) {
+    A.tgt[row] = poi;
+    A.label[row] = lab;
+    if (A.treg) A.treg[row] = A.poi_region ? __ldg(A.poi_region + poi) : 0;
+    if (A.tgt_coords) {
+      A.tgt_coords[2 * row] = A.poi_coords ? __ldg(A.poi_coords + 2 * poi) : 0.f;
+      A.tgt_coords[2 * row + 1] = A.poi_coords ? __ldg(A.poi_coords + 2 * poi + 1) : 0.f;
+    }
+  };
+  // history -> hash set, positives -> their rows
+  for (int i = lane; i < H; i += 32) {
+    const int poi = checked_id(A.hist[h0 + i], A.item_num, A.bad);
+    set_insert(tab, mask, (uint32_t)poi);
+    emit(row0 + (int64_t)i * (g + 1), poi, 1.f);
+  }
+  __syncwarp();
+  // negatives: slot n = i * g + (j - 1) -> row row0 + i * (g + 1) + j
+  const int M = H * g;
+  for (int base = 0; base < M; base += 32) {
+    const int n = base + lane;
+    bool pending = n < M;
+    uint32_t attempt = 0;
+    int cand = 0;
+    while (__any_sync(0xffffffffu, pending)) {
+      bool ok = false;
+      if (pending) {
+        const uint64_t z = mix64(A.seed + 0x9E3779B97F4A7C15ull * (((uint64_t)(uint32_t)s << 32) | (uint32_t)n) + 0xD1B54A32D192ED03ull * (attempt + 1));
+        cand = (int)(((z >> 32) * (uint64_t)A.item_num) >> 32);
+        ok = !set_contains(tab, mask, (uint32_t)cand);
+      }
+      // duplicates inside this round: the lowest lane keeps the candidate
+      const unsigned same = __match_any_sync(0xffffffffu, ok ? cand : -1 - lane);
+      ok = ok && (__ffs((int)same) - 1 == lane);
+      __syncwarp();
+      if (ok) {
+        set_insert(tab, mask, (uint32_t)cand);
+        const int i = n / g, j = n - i * g;
+        emit(row0 + (int64_t)i * (g + 1) + 1 + j, cand, 0.f);
+        pending = false;
+      }
+      ++attempt;
+      __syncwarp();
+      if (attempt > 4096u) {  // (only if the user has visited almost the whole catalogue) give up: a valid, harmless row
+        if (pending) emit(row0 + (int64_t)(n / g) * (g + 1) + 1 + (n % g), cand, 0.f);
+        break;
+      }
+    }
+  }
+}
+
+}  // namespace smp
+
+int launch_sample_batch(const int64_t* seg_offsets, const int64_t* hist, int n_seg, const int64_t* row_offsets, int num_ng, int item_num,
+                        const int32_t* poi_region, const float* poi_coords, uint64_t seed, int max_hist, int64_t* tgt, float* label,
+                        int64_t* treg, float* tgt_coords, cudaStream_t stream) {
+  if (n_seg == 0) return 0;
+  smp::Args A;
+  A.seg_offsets = seg_offsets;
+  A.hist = hist;
+  A.row_offsets = row_offsets;
+  A.n_seg = n_seg;
+  A.num_ng = num_ng;
+  A.item_num = item_num;
+  A.poi_region = poi_region;
+  A.poi_coords = poi_coords;
+  A.seed = seed;
+  A.tgt = tgt;
+  A.label = label;
+  A.treg = treg;
+  A.tgt_coords = tgt_coords;
+  A.bad = bad_index_flag();
+  uint32_t need = 2u * (uint32_t)max_hist * (uint32_t)(num_ng + 1), cap = 64;
+  while (cap < need) cap <<= 1;
+  A.cap = cap;
+  const size_t smem = (size_t)smp::WARPS * cap * sizeof(uint32_t);
+  if (smem > 200 * 1024) return NAIS_ERR_SHAPE;  // histories beyond ~1200 items x 5: sample those users on the host
+  cudaError_t e = cudaFuncSetAttribute(smp::sample_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  smp::sample_batch_kernel<<<(n_seg + smp::WARPS - 1) / smp::WARPS, smp::WARPS * 32, smem, stream>>>(A);
+  NAIS_COUNT_LAUNCH(1);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace nais

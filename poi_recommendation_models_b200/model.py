@@ -76,13 +76,25 @@ class _NAISBase(nn.Module):
         return ops.pairs_score(self.variant, float(self.beta), tuple(P.values()), hist, tgt, hreg, treg, aux, drop_p, seed,
                                getattr(self, "pairs_precision", "auto"))
 
-    def fused_adagrad_step(self, optimizer: torch.optim.Adagrad, label, hist, tgt, hreg=None, treg=None, aux=None) -> torch.Tensor:
+    def segmented_scores(self, batch: "ops.SegmentedPairs") -> torch.Tensor:
+        """`attention_network` over a multi-user batch in the segmented layout (ops.SegmentedPairs: the rows of a user share
+        one stored history, distances are formed in the kernel): pre-sigmoid scores [B], differentiable like the per-user
+        call.  One step over U users gives exactly the sum of the U single-user gradients (tests/test_gpu_segmented.py)."""
+        P = self._params()
+        return ops.pairs_score(self.variant, float(self.beta), tuple(P.values()), batch, None, None, None, None, 0.0, 0,
+                               getattr(self, "pairs_precision", "auto"))
+
+    def fused_adagrad_step(self, optimizer: torch.optim.Adagrad, label, hist, tgt=None, hreg=None, treg=None, aux=None,
+                           row_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One training step of run.py:248-254 (`zero_grad -> forward -> BCELoss -> backward -> Adagrad.step`) with the
         embedding tables stepped by the row-sparse Adagrad fused into the backward's segment reduce: no dense
         [N, D/2] gradient is zero-filled, written or read, and only the touched rows of the tables and of the optimizer's
         `state['sum']` move.  With the reference's `weight_decay = 0` (run.py:833) this IS the dense step (SURVEY.md §7
         'Dense Adagrad semantic'); other settings raise.  The MLP / dist-layer parameters go through `optimizer.step()` as
-        usual.  Returns the loss (same value `loss_func(forward(...), label)` gives)."""
+        usual.  Returns the loss (same value `loss_func(forward(...), label)` gives).  `hist` may be an ops.SegmentedPairs
+        (many users in one step; tgt / hreg / treg / aux then stay None).  `row_weight` [B]: the loss becomes
+        sum_b row_weight[b] * BCE_b instead of the batch mean — e.g. 1 / rows(user of b) makes a multi-user step the sum of the
+        reference's per-user mean losses (run.py:251)."""
         if not isinstance(optimizer, torch.optim.Adagrad):
             raise RuntimeError("fused_adagrad_step needs torch.optim.Adagrad (run.py:225)")
         P = self._params()
@@ -109,7 +121,10 @@ class _NAISBase(nn.Module):
         with torch.no_grad():
             score, row_sum, parts, mask = ops.pairs_forward_raw(self.variant, float(self.beta), P, hist, tgt, hreg, treg, aux, drop)
         s = score.detach().requires_grad_(True)  # dL/dscore through torch's own sigmoid + BCELoss ([B]-sized, exact semantics)
-        loss = self.loss_func(torch.sigmoid(s), label)
+        if row_weight is None:
+            loss = self.loss_func(torch.sigmoid(s), label)
+        else:
+            loss = (nn.functional.binary_cross_entropy(torch.sigmoid(s), label, reduction="none") * row_weight).sum()
         loss.backward()
         with torch.no_grad():
             G = ops.pairs_backward_adagrad(self.variant, float(self.beta), P, sums, lr, eps, hist, tgt, hreg, treg, aux, row_sum,

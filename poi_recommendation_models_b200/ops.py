@@ -38,9 +38,12 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-def _need_cuda(*ts: Optional[torch.Tensor]) -> torch.device:
+def _need_cuda(*ts) -> torch.device:
     dev = None
-    for t in ts:
+    flat = []
+    for t in ts:  # a SegmentedPairs stands for all of its device arrays
+        flat.extend(v for v in vars(t).values() if isinstance(v, torch.Tensor)) if isinstance(t, SegmentedPairs) else flat.append(t)
+    for t in flat:
         if t is None:
             continue
         if not t.is_cuda:
@@ -165,7 +168,86 @@ def build_params(variant: str, P: Dict[str, torch.Tensor], beta: float, keep: Li
     return p
 
 
+@dataclass
+class SegmentedPairs:
+    """A multi-user training batch in the segmented layout of NaisPairs (include/nais_b200.h): the rows of a segment (= a
+    user) share ONE stored history — no [B,H] repeat (batches.py:97), no materialised [B,H,2] distance tensor (run.py:239-247:
+    the kernels form |dlat|,|dlon| from centred coordinates).  Built by `segment_structure` + `sample_batch`
+    (batches.DeviceBatcher.multi_user_batch) or by hand."""
+    hist: torch.Tensor                 # [nnz] int64 history POI ids, segment after segment
+    hreg: Optional[torch.Tensor]       # [nnz] int64
+    hist_coords: Optional[torch.Tensor]  # [nnz,2] float32 centred
+    tgt: torch.Tensor                  # [B] int64
+    treg: Optional[torch.Tensor]       # [B] int64
+    tgt_coords: Optional[torch.Tensor]  # [B,2] float32 centred
+    label: Optional[torch.Tensor]      # [B] float32
+    seg_offsets: torch.Tensor          # [n_seg+1] int64 (device)
+    row_offsets: torch.Tensor          # [n_seg+1] int64
+    seg_cell_offsets: torch.Tensor     # [n_seg+1] int64
+    tile_seg: torch.Tensor             # [n_tiles] int32
+    tile_row0: torch.Tensor            # [n_tiles] int64
+    n_seg: int
+    B: int
+    n_tiles: int
+    n_cells: int
+    max_hist: int
+    host_row_offsets: Optional[object] = None  # numpy copy (per-user loss weights etc.)
+
+
+def segment_structure(hist_lens, rows_per_seg, device) -> Dict[str, object]:
+    """Host-side structure of a segmented batch (numpy, O(segments + tiles)): offsets and the tile table the kernels walk.
+    Tile t covers at most min(16, 128 // H_s) rows of ONE segment (1 row when H_s > 128; csrc/nais_pairs_tile.cuh)."""
+    import numpy as np
+    H = np.asarray(hist_lens, dtype=np.int64)
+    R = np.asarray(rows_per_seg, dtype=np.int64)
+    R = np.where(H > 0, R, 0)
+    seg_off = np.concatenate([[0], np.cumsum(H)])
+    row_off = np.concatenate([[0], np.cumsum(R)])
+    cell_off = np.concatenate([[0], np.cumsum(R * H)])
+    rpt = np.where(H > 0, np.minimum(16, np.maximum(1, 128 // np.maximum(H, 1))), 1)
+    tiles = (R + rpt - 1) // rpt
+    tile_seg = np.repeat(np.arange(len(H), dtype=np.int32), tiles)
+    first = np.concatenate([[0], np.cumsum(tiles)])[:-1]
+    within = np.arange(int(tiles.sum()), dtype=np.int64) - np.repeat(first, tiles)
+    tile_row0 = np.repeat(row_off[:-1], tiles) + within * np.repeat(rpt, tiles)
+    up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a.astype(dt))).to(device)
+    return dict(seg_offsets=up(seg_off, np.int64), row_offsets=up(row_off, np.int64), seg_cell_offsets=up(cell_off, np.int64),
+                tile_seg=up(tile_seg, np.int32), tile_row0=up(tile_row0, np.int64), n_seg=len(H), B=int(row_off[-1]),
+                n_tiles=int(tiles.sum()), n_cells=int(cell_off[-1]), max_hist=int(H.max()) if len(H) else 0, host_row_offsets=row_off)
+
+
+def sample_batch(hist: torch.Tensor, st: Dict[str, object], num_ng: int, item_num: int, seed: int,
+                 poi_region: Optional[torch.Tensor] = None, poi_coords: Optional[torch.Tensor] = None):
+    """nais_sample_batch: targets / labels / target regions / target coordinates of a segmented batch, sampled ON THE DEVICE
+    (batches.py:67-108 for many users at once: positives + `num_ng` negatives each, uniform without replacement over the
+    POIs outside the user's history).  `st` = `segment_structure(H_s, (num_ng + 1) * H_s)`."""
+    dev = _need_cuda(hist, st["seg_offsets"], poi_region, poi_coords)
+    B = st["B"]
+    with torch.cuda.device(dev):
+        tgt = torch.empty(B, dtype=torch.int64, device=dev)
+        label = torch.empty(B, dtype=torch.float32, device=dev)
+        treg = torch.empty(B, dtype=torch.int64, device=dev) if poi_region is not None else None
+        tc = torch.empty(B, 2, dtype=torch.float32, device=dev) if poi_coords is not None else None
+        pr = None if poi_region is None else poi_region.to(torch.int32).contiguous()
+        pc = None if poi_coords is None else _f32(poi_coords)
+        _lib.check(_lib.load().nais_sample_batch(st["seg_offsets"].data_ptr(), hist.data_ptr(), st["n_seg"], st["row_offsets"].data_ptr(),
+                                                 int(num_ng), int(item_num), _ptr(pr), _ptr(pc), int(seed) & (2 ** 64 - 1), st["max_hist"],
+                                                 tgt.data_ptr(), label.data_ptr(), _ptr(treg), _ptr(tc), _stream()), "nais_sample_batch")
+    return tgt, label, treg, tc
+
+
 def _pairs_struct(hist, tgt, hreg, treg, aux, keep) -> NaisPairs:
+    if isinstance(hist, SegmentedPairs):
+        sp = hist
+        b = NaisPairs()
+        b.hist, b.tgt, b.hreg, b.treg, b.aux = _ptr(sp.hist), _ptr(sp.tgt), _ptr(sp.hreg), _ptr(sp.treg), None
+        b.B, b.H, b.n_seg = sp.B, 0, sp.n_seg
+        b.seg_offsets, b.row_offsets, b.seg_cell_offsets = _ptr(sp.seg_offsets), _ptr(sp.row_offsets), _ptr(sp.seg_cell_offsets)
+        b.tile_seg, b.tile_row0, b.n_tiles, b.n_cells = _ptr(sp.tile_seg), _ptr(sp.tile_row0), sp.n_tiles, sp.n_cells
+        b.hist_coords, b.tgt_coords = _ptr(sp.hist_coords), _ptr(sp.tgt_coords)
+        keep.append(sp)
+        return b
+
     def i64(t):
         if t is None:
             return None
@@ -200,7 +282,7 @@ def _forward_launch(lib, p: NaisParams, b: NaisPairs, dev, want_mask: bool = Tru
     parts = torch.empty(p.n_branch, B, device=dev, dtype=torch.float32)
     mask = None
     if want_mask and B and p.n_branch == 1 and p.hid <= 64 and pairs_dispatch(p, b)[0]:
-        mask = torch.empty(B * b.H, device=dev, dtype=torch.int64)
+        mask = torch.empty(b.n_cells if b.seg_offsets else B * b.H, device=dev, dtype=torch.int64)
     _lib.check(lib.nais_pairs_forward(C.byref(p), C.byref(b), score.data_ptr(), row_sum.data_ptr(), parts.data_ptr(), _ptr(mask),
                                       _stream()), "nais_pairs_forward")
     return score, row_sum, parts, mask
@@ -228,15 +310,19 @@ class _PairsFunction(torch.autograd.Function):
             score, row_sum, parts, mask = _forward_launch(lib, p, b, dev, want_mask=need_bwd)
             _poll_bad_index(dev)
         ctx.variant, ctx.beta, ctx.drop = variant, beta, drop
-        ctx.save_for_backward(hist, tgt, hreg if hreg is not None else torch.empty(0), treg if treg is not None else torch.empty(0),
-                              aux if aux is not None else torch.empty(0), row_sum, parts,
-                              mask if mask is not None else torch.empty(0), *params)
+        ctx.seg = hist if isinstance(hist, SegmentedPairs) else None  # (not a tensor: rides on ctx)
+        e = torch.empty(0)
+        ctx.save_for_backward(e if ctx.seg is not None else hist, tgt if tgt is not None else e, hreg if hreg is not None else e,
+                              treg if treg is not None else e, aux if aux is not None else e, row_sum, parts,
+                              mask if mask is not None else e, *params)
         ctx.has = (hreg is not None, treg is not None, aux is not None, mask is not None)
         return score
 
     @staticmethod
     def backward(ctx, dscore):
         hist, tgt, hreg, treg, aux, row_sum, parts, mask, *params = ctx.saved_tensors
+        if ctx.seg is not None:
+            hist, tgt = ctx.seg, None
         hreg = hreg if ctx.has[0] else None
         treg = treg if ctx.has[1] else None
         aux = aux if ctx.has[2] else None
@@ -278,7 +364,7 @@ def pairs_backward_raw(variant: str, beta: float, P: Dict[str, torch.Tensor], hi
                                          G["region_attn_layer1.bias"].data_ptr(),
                                          G["region_attn_layer2.weight"].data_ptr())
             g.dist_embed = G["embed_distance.weight"].data_ptr()
-        ws_bytes = lib.nais_pairs_backward_workspace_bytes(C.byref(p), b.B, b.H)
+        ws_bytes = lib.nais_pairs_backward_workspace_bytes(C.byref(p), C.byref(b))
         ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
         ds = _f32(dscore)
         _lib.check(lib.nais_pairs_backward(C.byref(p), C.byref(b), parts.data_ptr(), row_sum.data_ptr(), _ptr(act_mask), ds.data_ptr(),
@@ -329,7 +415,7 @@ def pairs_backward_adagrad(variant: str, beta: float, P: Dict[str, torch.Tensor]
                 if st.dtype != torch.float32 or not st.is_contiguous() or st.shape != P[name].shape or not P[name].is_contiguous():
                     raise RuntimeError(f"fused Adagrad: {name} and its state must be contiguous float32 of the same shape")
                 field[0] = st.data_ptr()
-        ws_bytes = lib.nais_pairs_backward_workspace_bytes(C.byref(p), b.B, b.H)
+        ws_bytes = lib.nais_pairs_backward_workspace_bytes(C.byref(p), C.byref(b))
         ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
         ds = _f32(dscore)
         _lib.check(lib.nais_pairs_backward_adagrad(C.byref(p), C.byref(b), parts.data_ptr(), row_sum.data_ptr(), _ptr(act_mask),
