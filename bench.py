@@ -500,7 +500,67 @@ def train_c3(args, dev, lib, peaks, rank, world, steps, warmup, full=False):
                        "segment_reduce_bytes": red_bytes, "peak_source": f"{peaks['which']} (MEASURED_PEAKS.json)"}
     if full and world == 1:
         blk["full_step"] = full_step_block(args, dev, m, hist, tgt, hreg, treg, ll, R, T, N, H, D, hid)
+    if full:
+        blk["dp_1m"] = dp_large_catalogue_block(args, dev, rank, world, T, H, D, hid)
     return blk
+
+
+def dp_large_catalogue_block(args, dev, rank, world, T, H, D, hid):
+    """Data-parallel optimizer step at C4's catalogue (1M POIs: 2 x 128 MB embedding tables + 45 MB region table), 8192 rows per
+    rank, BCE + Adagrad: dense gradients + ONE flat all-reduce (266 MB) + dense torch Adagrad, against the touched-row exchange
+    (`distributed.SparseRowExchange`: row-compacted gradients, all-gather of (id, row) lists, row-sparse Adagrad on the union)."""
+    import torch
+    import torch.distributed as dist
+    from poi_recommendation_models_b200 import model as M, synthetic
+    from poi_recommendation_models_b200.distributed import SparseRowExchange, allreduce_gradients
+    n_big = 1000000
+    c2np, r2np, R2 = synthetic.make_catalog(n_big, seed=0)
+    hn = synth_histories(T, n_big, H, seed=5 + rank)
+    h2 = torch.from_numpy(np.concatenate([hn, hn])).to(dev)
+    t2 = torch.from_numpy(np.concatenate([hn[:, 0], (hn[:, 1] + 1) % n_big])).to(dev)
+    r2, c2 = torch.from_numpy(r2np).to(dev), torch.from_numpy(c2np).to(dev)
+    ll2 = (c2[t2][:, None, :] - c2[h2]).abs().float().contiguous()
+    hr2, tr2 = r2[h2], r2[t2]
+    label = torch.cat([torch.ones(T), torch.zeros(T)]).to(dev)
+    out = {"rows_per_gpu": 2 * T, "pois": n_big, "n_gpus": world}
+    for kind in ("dense_allreduce", "sparse_row_exchange"):
+        torch.manual_seed(2)
+        m2 = M.NAIS_region_distance_Embedding(n_big, D, hid, BETA, R2, 1).to(dev).train()
+        opt = torch.optim.Adagrad(m2.parameters(), lr=0.01, weight_decay=0.0)
+        ex = SparseRowExchange(m2, opt, world) if kind == "sparse_row_exchange" else None
+
+        def one():
+            if ex is not None:
+                return ex.step(label, h2, t2, hr2, tr2, ll2)
+            opt.zero_grad()
+            ls_ = m2.loss_func(m2(h2, t2, hr2, tr2, ll2), label)
+            ls_.backward()
+            allreduce_gradients(m2, world)
+            opt.step()
+            return ls_.detach()
+
+        for _ in range(max(2, args.warmup)):
+            one()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a2.record()
+        for _ in range(args.steps):
+            ls = one()
+        b2.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a2.elapsed_time(b2) / args.steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[kind] = {"ms_per_step": float(t.item()), "rows_per_s": 2 * T * world / (float(t.item()) / 1000.0), "loss": float(ls)}
+        if ex is not None:
+            out[kind]["bytes_received_per_step"] = int(ex.last_bytes)
+        else:
+            out[kind]["bytes_allreduced_per_step"] = int(sum(p.numel() for p in m2.parameters()) * 4) if world > 1 else 0
+        del m2, opt, ex
+        torch.cuda.empty_cache()
+    return out
 
 
 def full_step_block(args, dev, m, hist, tgt, hreg, treg, ll, R, T, N, H, D, hid):
@@ -615,8 +675,9 @@ def c1_block(dev, lib, no_cpu=False):
     # (a) the reference's schedule: one user per step (fused row-sparse Adagrad, batch built on the device)
     m1, o1 = fresh()
     sample = order[:256]
-    for u in sample[:8]:
-        m1.fused_adagrad_step(o1, *(lambda b: (b[2], b[0], b[1], b[3], b[4], b[5]))(bt.batch(int(u), num_ng)))
+    for u in sample[:8]:  # warm-up
+        h_, t_, lab_, hr_, tr_, ll_ = bt.batch(int(u), num_ng)
+        m1.fused_adagrad_step(o1, lab_, h_, t_, hr_, tr_, ll_)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for u in sample:
@@ -675,8 +736,6 @@ def c1_block(dev, lib, no_cpu=False):
             import random as _r
             ref.train()
             opt = torch.optim.Adagrad(ref.parameters(), lr=lr)
-            rb = __import__("oracle.ref_shim", fromlist=["x"]).load_reference("batches")
-            rb.DEVICE = torch.device("cpu") if hasattr(rb, "DEVICE") else None
             _r.seed(0)
             n_cpu, t0 = 0, time.perf_counter()
             for u in order[:6]:
@@ -700,7 +759,8 @@ def run_train(args, dev, lib, peaks, rank, world):
         line = {"metric": blk["metric"], "value": blk["value"], "unit": blk["unit"], "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": blk["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": blk["dtype"], "data": "synthetic", "config": blk["config"], "gpu_launches": blk["gpu_launches_per_step"] * args.steps,
-                "loss": blk["loss"], "components_ms": blk["components_ms"], "roofline": blk["roofline"], "full_step": blk.get("full_step")}
+                "loss": blk["loss"], "components_ms": blk["components_ms"], "roofline": blk["roofline"], "full_step": blk.get("full_step"),
+                "dp_1m": blk.get("dp_1m")}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = train_cpu_baseline()
         print(json.dumps(line), flush=True)

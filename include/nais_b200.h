@@ -158,6 +158,14 @@ typedef struct NaisGrads {
   float* dist_w; /* [2,2] */
   float* dist_b; /* [2]   */
   float* dist_embed; /* [dist_buckets, D] */
+  /* Row-compacted table gradients (data-parallel training on catalogues where a dense [item_num, w] gradient is hundreds of
+   * MB): when remap_X[b] != NULL, the gradient of table row r is written to row remap_X[b][r] of X[b] — a caller-sized
+   * [n_touched, w] buffer — instead of row r; the caller fills remap (int32 [table rows]) for the rows its batch touches
+   * (e.g. remap[unique(ids)] = 0..n_touched-1).  Untouched rows are never written in either form.  Ignored by the fused
+   * Adagrad path. */
+  const int32_t* remap_hist_poi[2];
+  const int32_t* remap_tgt_poi[2];
+  const int32_t* remap_reg[2];
 } NaisGrads;
 
 /* Candidate side of full-rank scoring: rows [row_base, row_base+n_rows) of the POI catalogue.  tgt_poi in NaisParams
@@ -205,6 +213,17 @@ NAIS_API size_t nais_pairs_backward_workspace_bytes(const NaisParams* p, const N
 NAIS_API int nais_pairs_backward(const NaisParams* p, const NaisPairs* batch, const float* score_parts, const float* row_sum,
                         const uint64_t* act_mask, const float* dscore, const NaisGrads* grads, void* workspace,
                         size_t workspace_bytes, nais_stream_t stream);
+
+/* One row-sparse Adagrad step from a key-ordered list of (table row id, gradient row) pairs — the union of the touched-row lists
+ * the ranks of a data-parallel step exchange (SURVEY.md §8e 'Train partitioning').  keys [n] int32 ascending (equal ids
+ * adjacent: their rows are summed first, in list order — deterministic, identical on every rank that holds the same list),
+ * rows [n, w].  For every distinct id r with summed gradient g:  sum[r] += g*g ; param[r] -= lr * g / (sqrt(sum[r]) + eps)
+ * (torch.optim.Adagrad, weight_decay = lr_decay = 0).  With sum == NULL the summed rows are written to grad_out[r] instead
+ * (a dense [n_rows, w] table; rows not listed are not touched).  ids outside [0, n_rows) are skipped. */
+NAIS_API size_t nais_rows_adagrad_workspace_bytes(int64_t n, int32_t w);
+NAIS_API int nais_rows_adagrad(const int32_t* keys, const float* rows, int64_t n, int32_t w, int32_t n_rows, float* grad_out,
+                               float* param, float* sum, float lr, float eps, void* workspace, size_t workspace_bytes,
+                               nais_stream_t stream);
 
 /* Device-side training-batch construction for the segmented layout (batches.py:67-108 `get_NAIS_batch_region`, many users per
  * call).  For every segment s (history hist[seg_offsets[s] .. seg_offsets[s+1]), H_s items) the rows

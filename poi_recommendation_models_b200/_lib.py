@@ -43,7 +43,8 @@ class NaisPairs(C.Structure):
 class NaisGrads(C.Structure):
     _fields_ = [("hist_poi", C.c_void_p * 2), ("tgt_poi", C.c_void_p * 2), ("reg", C.c_void_p * 2),
                 ("w1", C.c_void_p * 2), ("b1", C.c_void_p * 2), ("w2", C.c_void_p * 2), ("dist_w", C.c_void_p),
-                ("dist_b", C.c_void_p), ("dist_embed", C.c_void_p)]
+                ("dist_b", C.c_void_p), ("dist_embed", C.c_void_p), ("remap_hist_poi", C.c_void_p * 2),
+                ("remap_tgt_poi", C.c_void_p * 2), ("remap_reg", C.c_void_p * 2)]
 
 
 class NaisAdagrad(C.Structure):
@@ -70,6 +71,9 @@ SYMBOLS = {
     "nais_pairs_forward": (C.c_int, [C.POINTER(NaisParams), C.POINTER(NaisPairs), C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
     "nais_pairs_backward_workspace_bytes": (C.c_size_t, [C.POINTER(NaisParams), C.POINTER(NaisPairs)]),
+    "nais_rows_adagrad_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "nais_rows_adagrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_float, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nais_sample_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                     C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nais_pairs_backward": (C.c_int, [C.POINTER(NaisParams), C.POINTER(NaisPairs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -595,7 +595,9 @@ struct SegOut {
   float* param;
   float* sum;
   float lr, eps;
+  const int32_t* remap;  // out row of table row `key` = remap[key] (row-compacted gradient buffers, NaisGrads::remap_*); NULL: key
 };
+__device__ __forceinline__ size_t seg_row_of(const SegOut& o, int key) { return (o.remap && !o.param) ? (size_t)__ldg(o.remap + key) : (size_t)key; }
 __device__ __forceinline__ void seg_store(const SegOut& o, size_t idx, float g) {
   if (o.param) {
     const float s2 = fmaf(g, g, o.sum[idx]);
@@ -644,7 +646,7 @@ __global__ void segment_reduce_pass1_kernel(const int* __restrict__ keys, int64_
     if (!left && !right) {
 #pragma unroll
       for (int q = 0; q < NQ; ++q)
-        if (col[q]) seg_store(out, (size_t)key * w + lane + 32 * q, acc[q]);
+        if (col[q]) seg_store(out, seg_row_of(out, key) * w + lane + 32 * q, acc[q]);
     } else {
       const int64_t slot = 2 * chunk + (run_a == 0 ? 0 : 1);
       if (lane == 0) {
@@ -723,7 +725,50 @@ __global__ void segment_reduce_pass2_kernel(const int* __restrict__ part_key, co
   }
 #pragma unroll
   for (int q = 0; q < NQ; ++q)
-    if (col[q]) seg_store(out, (size_t)key * w + lane + 32 * q, acc[q]);
+    if (col[q]) seg_store(out, seg_row_of(out, key) * w + lane + 32 * q, acc[q]);
+}
+
+// Both passes over n key-ordered rows (keys ascending, rows[i] belongs to keys[i]).  pk / pst / pr: partial slots for
+// 2 * ceil(n / SEG_CHUNK) boundary runs (keys, start flags, rows of width w).
+static void launch_segment_reduce(const int* keys, int64_t n, const float* rows, int w, int n_rows, const SegOut& out, int* pk, int* pst,
+                                  float* pr, cudaStream_t stream) {
+  const int64_t nch = (n + SEG_CHUNK - 1) / SEG_CHUNK;
+  const unsigned g1 = (unsigned)((nch * 32 + 255) / 256), g2 = (unsigned)((2 * nch * 32 + 255) / 256);
+  if (w <= 32) {
+    segment_reduce_pass1_kernel<1><<<g1, 256, 0, stream>>>(keys, n, rows, w, n_rows, out, pk, pst, pr);
+    segment_reduce_pass2_kernel<1><<<g2, 256, 0, stream>>>(pk, pst, pr, nch, w, out);
+  } else if (w <= 64) {
+    segment_reduce_pass1_kernel<2><<<g1, 256, 0, stream>>>(keys, n, rows, w, n_rows, out, pk, pst, pr);
+    segment_reduce_pass2_kernel<2><<<g2, 256, 0, stream>>>(pk, pst, pr, nch, w, out);
+  } else {
+    segment_reduce_pass1_kernel<4><<<g1, 256, 0, stream>>>(keys, n, rows, w, n_rows, out, pk, pst, pr);
+    segment_reduce_pass2_kernel<4><<<g2, 256, 0, stream>>>(pk, pst, pr, nch, w, out);
+  }
+  NAIS_COUNT_LAUNCH(2);
+}
+
+// nais_rows_adagrad (include/nais_b200.h): key-ordered (id, gradient row) lists -> one row-sparse Adagrad step per distinct id
+size_t rows_adagrad_workspace_bytes(int64_t n, int w) {
+  const int64_t nch = (n + SEG_CHUNK - 1) / SEG_CHUNK;
+  return 2 * ((size_t)2 * nch * 4 + 256) + (size_t)2 * nch * w * 4 + 256;
+}
+int launch_rows_adagrad(const int32_t* keys, const float* rows, int64_t n, int w, int n_rows, float* grad_out, float* param, float* sum,
+                        float lr, float eps, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (n == 0) return 0;
+  if (ws_bytes < rows_adagrad_workspace_bytes(n, w)) return NAIS_ERR_WORKSPACE;
+  const int64_t nch = (n + SEG_CHUNK - 1) / SEG_CHUNK;
+  char* base = reinterpret_cast<char*>(ws);
+  const size_t kb = ((size_t)2 * nch * 4 + 255) / 256 * 256;
+  SegOut o;
+  o.out = grad_out;
+  o.param = sum ? param : nullptr;
+  o.sum = sum;
+  o.lr = lr;
+  o.eps = eps;
+  o.remap = nullptr;
+  launch_segment_reduce(keys, n, rows, w, n_rows, o, reinterpret_cast<int*>(base), reinterpret_cast<int*>(base + kb),
+                        reinterpret_cast<float*>(base + 2 * kb), stream);
+  return (int)cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -887,38 +932,24 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
       NAIS_COUNT_LAUNCH(1);
     }
     // ---- 3. embedding rows: stream the key-ordered contribution rows ----------------------------------------------------------
-    auto dest = [&](float* grad, const float* param, float* sum) {
+    auto dest = [&](float* grad, const float* param, float* sum, const int32_t* remap) {
       SegOut o;
       o.out = grad;
       o.param = (opt && sum) ? const_cast<float*>(param) : nullptr;
       o.sum = sum;
       o.lr = opt ? opt->lr : 0.f;
       o.eps = opt ? opt->eps : 0.f;
+      o.remap = remap;
       return o;
     };
     auto seg = [&](int t, const float* rows, int w, int n_rows, SegOut out) {
-      const int64_t n = n_of[t];
-      const int64_t nch = (n + SEG_CHUNK - 1) / SEG_CHUNK;
-      int* pk = I(L.pkey);
-      int* pst = I(L.pstart);
-      float* pr = reinterpret_cast<float*>(base + L.prows);
-      const unsigned g1 = (unsigned)((nch * 32 + 255) / 256), g2 = (unsigned)((2 * nch * 32 + 255) / 256);
-      if (w <= 32) {
-        segment_reduce_pass1_kernel<1><<<g1, 256, 0, stream>>>(I(L.kout[t]), n, rows, w, n_rows, out, pk, pst, pr);
-        segment_reduce_pass2_kernel<1><<<g2, 256, 0, stream>>>(pk, pst, pr, nch, w, out);
-      } else if (w <= 64) {
-        segment_reduce_pass1_kernel<2><<<g1, 256, 0, stream>>>(I(L.kout[t]), n, rows, w, n_rows, out, pk, pst, pr);
-        segment_reduce_pass2_kernel<2><<<g2, 256, 0, stream>>>(pk, pst, pr, nch, w, out);
-      } else {
-        segment_reduce_pass1_kernel<4><<<g1, 256, 0, stream>>>(I(L.kout[t]), n, rows, w, n_rows, out, pk, pst, pr);
-        segment_reduce_pass2_kernel<4><<<g2, 256, 0, stream>>>(pk, pst, pr, nch, w, out);
-      }
-      NAIS_COUNT_LAUNCH(2);
+      launch_segment_reduce(I(L.kout[t]), n_of[t], rows, w, n_rows, out, I(L.pkey), I(L.pstart), reinterpret_cast<float*>(base + L.prows),
+                            stream);
     };
-    if (want[0]) seg(0, A.dq_h, br.w_poi, p.item_num, dest(g.hist_poi[bi], br.hist_poi, opt ? opt->sum_hist_poi[bi] : nullptr));
-    if (want[1]) seg(1, A.dp_t, br.w_poi, p.item_num, dest(g.tgt_poi[bi], br.tgt_poi, opt ? opt->sum_tgt_poi[bi] : nullptr));
+    if (want[0]) seg(0, A.dq_h, br.w_poi, p.item_num, dest(g.hist_poi[bi], br.hist_poi, opt ? opt->sum_hist_poi[bi] : nullptr, g.remap_hist_poi[bi]));
+    if (want[1]) seg(1, A.dp_t, br.w_poi, p.item_num, dest(g.tgt_poi[bi], br.tgt_poi, opt ? opt->sum_tgt_poi[bi] : nullptr, g.remap_tgt_poi[bi]));
     // (history-side and target-side region rows are one table in every variant: hist_reg == tgt_reg)
-    if (want[2]) seg(2, A.dq_r, br.w_reg, p.region_num, dest(g.reg[bi], br.hist_reg, opt ? opt->sum_reg[bi] : nullptr));
+    if (want[2]) seg(2, A.dq_r, br.w_reg, p.region_num, dest(g.reg[bi], br.hist_reg, opt ? opt->sum_reg[bi] : nullptr, g.remap_reg[bi]));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }

@@ -22,6 +22,9 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
                      const unsigned long long* act_mask, const float* dscore, const NaisGrads& g, const NaisAdagrad* opt, void* ws,
                      size_t ws_bytes, cudaStream_t stream);
 bool pairs_tc_bwd_supported(const NaisParams& p, const NaisPairs& b);
+size_t rows_adagrad_workspace_bytes(int64_t n, int w);
+int launch_rows_adagrad(const int32_t* keys, const float* rows, int64_t n, int w, int n_rows, float* grad_out, float* param, float* sum,
+                        float lr, float eps, void* ws, size_t ws_bytes, cudaStream_t stream);
 // nais_tc.cu
 size_t fullrank_tc_workspace_bytes(const NaisParams& p, int n_users, int64_t nnz, int64_t poi_begin, int64_t poi_end, int k,
                                    int precision);
@@ -209,6 +212,22 @@ static bool device_is_sm100() {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
   return major == 10;
+}
+
+size_t nais_rows_adagrad_workspace_bytes(int64_t n, int32_t w) {
+  if (n < 0 || w < 1 || w > 128) return 0;
+  return rows_adagrad_workspace_bytes(n, w);
+}
+
+int nais_rows_adagrad(const int32_t* keys, const float* rows, int64_t n, int32_t w, int32_t n_rows, float* grad_out, float* param,
+                      float* sum, float lr, float eps, void* workspace, size_t workspace_bytes, nais_stream_t stream) {
+  if (n < 0 || w < 1 || w > 128 || n_rows < 1) return NAIS_ERR_SHAPE;
+  if (n == 0) return 0;
+  if (!keys || !rows || !workspace || (sum ? !param : !grad_out)) return NAIS_ERR_NULL;
+  if (sum && (!(lr >= 0.f) || !(eps >= 0.f))) return NAIS_ERR_MODE;
+  if (!aligned16(workspace)) return NAIS_ERR_ALIGN;
+  return launch_rows_adagrad(keys, rows, n, w, n_rows, grad_out, param, sum, lr, eps, workspace, workspace_bytes,
+                             static_cast<cudaStream_t>(stream));
 }
 
 int nais_sample_batch(const int64_t* seg_offsets, const int64_t* hist, int32_t n_seg, const int64_t* row_offsets, int32_t num_ng,

@@ -181,3 +181,96 @@ def allreduce_gradients(model, world: int) -> None:
         n = g.numel()
         g.copy_(flat[o:o + n].view_as(g))
         o += n
+
+
+class SparseRowExchange:
+    """Data-parallel training step for catalogues where the dense embedding gradients are hundreds of MB (C4: 2 x 128 MB at 1M
+    POIs) — SURVEY.md §8e 'Train partitioning': every rank runs forward + backward on ITS rows with row-compacted table gradients
+    (only the touched rows exist), the ranks all-gather their (row id, gradient row) lists, and every rank applies the same
+    row-sparse Adagrad step to the union (`nais_rows_adagrad`: equal ids summed in rank-major list order, so the replicas stay
+    bit-identical).  The attention-MLP / dist-layer gradients (17 KB) are all-reduced densely and stepped by `optimizer.step()`.
+
+    Loss = mean BCE over the GLOBAL batch (every rank's rows weighted 1 / (world * local rows)), or `row_weight / world`.
+    With weight_decay = lr_decay = 0 (run.py:833) the result equals one dense torch.optim.Adagrad step on the concatenated batch."""
+
+    def __init__(self, model, optimizer: torch.optim.Adagrad, world: int = 1):
+        self.model, self.opt, self.world = model, optimizer, world
+        P = model._params()
+        dev = next(model.parameters()).device
+        self.remaps = {n: torch.zeros(P[n].shape[0], dtype=torch.int32, device=dev) for n in ops._TABLES if n in P}
+        self.last_bytes = 0  # bytes this rank received in the last exchange
+
+    def _hyper(self, P):
+        group_of = {id(p): g for g in self.opt.param_groups for p in g["params"]}
+        sums, lr, eps = {}, None, None
+        for name in self.remaps:
+            g = group_of[id(P[name])]
+            if g["weight_decay"] != 0 or g["lr_decay"] != 0 or g.get("maximize", False):
+                raise RuntimeError("row-sparse Adagrad equals the dense step only for weight_decay = lr_decay = 0")
+            lr, eps = g["lr"], g["eps"]
+            st = self.opt.state[P[name]]
+            if "sum" not in st:  # (torch creates the state in the optimizer's constructor; be safe for exotic subclasses)
+                st["sum"] = torch.full_like(P[name], g.get("initial_accumulator_value", 0.0))
+                st["step"] = torch.tensor(0.0)
+            sums[name] = st["sum"]
+        return sums, lr, eps
+
+    def exchange(self, ids: torch.Tensor, rows: torch.Tensor):
+        """all-gather of one table's (ids, rows): -> (ids [n] in rank-major list order, rows [n, w]) of every rank."""
+        if self.world == 1:
+            return ids, rows
+        n = torch.tensor([ids.numel()], device=ids.device, dtype=torch.int64)
+        counts = torch.empty(self.world, device=ids.device, dtype=torch.int64)
+        dist.all_gather_into_tensor(counts, n)
+        counts = counts.cpu()
+        cap, w = int(counts.max()), rows.shape[1]
+        pi = ids.new_full((cap,), -1)
+        pi[:ids.numel()] = ids
+        pr = rows.new_zeros((cap, w))
+        pr[:ids.numel()] = rows
+        gi = torch.empty(self.world * cap, device=ids.device, dtype=ids.dtype)
+        gr = torch.empty(self.world * cap, w, device=ids.device, dtype=rows.dtype)
+        dist.all_gather_into_tensor(gi, pi)
+        dist.all_gather_into_tensor(gr, pr)
+        self.last_bytes += gi.numel() * 8 + gr.numel() * 4
+        valid = gi >= 0
+        return gi[valid], gr[valid]
+
+    def step(self, label, hist, tgt=None, hreg=None, treg=None, aux=None, row_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+        m = self.model
+        P = m._params()
+        sums, lr, eps = self._hyper(P)
+        pp = getattr(m, "pairs_precision", "auto")
+        drop = (0.0, 0, pp)
+        self.opt.zero_grad(set_to_none=True)
+        with torch.no_grad():
+            score, row_sum, parts, mask = ops.pairs_forward_raw(m.variant, float(m.beta), P, hist, tgt, hreg, treg, aux, drop)
+        s = score.detach().requires_grad_(True)
+        if row_weight is None:
+            loss = m.loss_func(torch.sigmoid(s), label) / self.world
+        else:
+            loss = (torch.nn.functional.binary_cross_entropy(torch.sigmoid(s), label, reduction="none") * row_weight).sum() / self.world
+        loss.backward()
+        self.last_bytes = 0
+        with torch.no_grad():
+            G, sparse = ops.pairs_backward_compact(m.variant, float(m.beta), P, hist, tgt, hreg, treg, aux, row_sum, parts, s.grad,
+                                                   self.remaps, drop, act_mask=mask)
+            for name, (ids, rows) in sparse.items():
+                gi, gr = self.exchange(ids, rows)
+                order = torch.sort(gi, stable=True).indices  # key order; equal ids keep their rank-major order
+                ops.rows_adagrad(gi[order], gr[order], P[name], sums[name], lr, eps)
+            if self.world > 1:
+                flat = torch.cat([g.reshape(-1) for g in G.values()])
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+                o = 0
+                for g in G.values():
+                    g.copy_(flat[o:o + g.numel()].view_as(g))
+                    o += g.numel()
+        for name, grad in G.items():
+            P[name].grad = grad.to(P[name].dtype)
+        self.opt.step()  # MLP / dist layer; the tables have no .grad
+        m._plan_epoch = getattr(m, "_plan_epoch", 0) + 1
+        total = loss.detach().clone()
+        if self.world > 1:
+            dist.all_reduce(total, op=dist.ReduceOp.SUM)
+        return total

@@ -386,6 +386,73 @@ def pairs_score(variant: str, beta: float, params: Sequence[torch.Tensor], hist,
 _TABLES = ("embed_history.weight", "embed_target.weight", "embed_region.weight")
 
 
+def touched_rows(hist, tgt, hreg=None, treg=None) -> Dict[str, torch.Tensor]:
+    """Sorted distinct row ids a pair batch touches in each embedding table (int64) — the rows whose gradient is non-zero."""
+    if isinstance(hist, SegmentedPairs):
+        hist, tgt, hreg, treg = hist.hist, hist.tgt, hist.hreg, hist.treg
+    out = {"embed_history.weight": torch.unique(hist), "embed_target.weight": torch.unique(tgt)}
+    if hreg is not None:
+        out["embed_region.weight"] = torch.unique(torch.cat([hreg.reshape(-1), treg.reshape(-1)]))
+    return out
+
+
+def pairs_backward_compact(variant: str, beta: float, P: Dict[str, torch.Tensor], hist, tgt, hreg, treg, aux, row_sum, parts, dscore,
+                           remaps: Dict[str, torch.Tensor], drop=(0.0, 0, "auto"), act_mask: Optional[torch.Tensor] = None):
+    """Backward with ROW-COMPACTED table gradients (NaisGrads::remap_*): for every embedding table returns (ids int64 [n] sorted,
+    rows float32 [n, w]) of the touched rows only — nothing of size [item_num, w] is allocated, zero-filled or written — plus the
+    dense gradients of the remaining (MLP / dist layer) parameters.  `remaps[name]`: a reusable int32 [table rows] scratch per
+    table (only the touched entries are rewritten per call).  One-branch variants."""
+    dev = _need_cuda(hist, tgt, dscore, *P.values())
+    lib = _lib.load()
+    keep: List[torch.Tensor] = []
+    with torch.cuda.device(dev):
+        p = build_params(variant, P, beta, keep, drop[0], drop[1], _fwd_bwd(drop[2])[1])
+        if p.n_branch != 1:
+            raise RuntimeError("row-compacted gradients: one-branch variants only")
+        b = _pairs_struct(hist, tgt, hreg, treg, aux, keep)
+        ids = touched_rows(hist, tgt, hreg, treg)
+        G = {n: torch.zeros_like(t, dtype=torch.float32, memory_format=torch.contiguous_format) for n, t in P.items() if n not in _TABLES}
+        g = NaisGrads()
+        g.w1[0], g.b1[0], g.w2[0] = (G["attn_layer1.weight"].data_ptr(), G["attn_layer1.bias"].data_ptr(), G["attn_layer2.weight"].data_ptr())
+        if "dist_layer.weight" in G:
+            g.dist_w, g.dist_b = G["dist_layer.weight"].data_ptr(), G["dist_layer.bias"].data_ptr()
+        sparse = {}
+        for name, gf, rf in (("embed_history.weight", g.hist_poi, g.remap_hist_poi), ("embed_target.weight", g.tgt_poi, g.remap_tgt_poi),
+                             ("embed_region.weight", g.reg, g.remap_reg)):
+            if name not in P or name not in ids:
+                continue
+            i_ = ids[name]
+            rm = remaps[name]
+            rm[i_] = torch.arange(i_.numel(), device=dev, dtype=torch.int32)
+            rows = torch.empty(i_.numel(), P[name].shape[1], device=dev, dtype=torch.float32)
+            gf[0], rf[0] = rows.data_ptr(), rm.data_ptr()
+            sparse[name] = (i_, rows)
+        ws_bytes = lib.nais_pairs_backward_workspace_bytes(C.byref(p), C.byref(b))
+        ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
+        ds = _f32(dscore)
+        _lib.check(lib.nais_pairs_backward(C.byref(p), C.byref(b), parts.data_ptr(), row_sum.data_ptr(), _ptr(act_mask), ds.data_ptr(),
+                                           C.byref(g), ws.data_ptr(), ws_bytes, _stream()), "nais_pairs_backward")
+        _poll_bad_index(dev)
+    return G, sparse
+
+
+def rows_adagrad(keys: torch.Tensor, rows: torch.Tensor, param: torch.Tensor, state_sum: torch.Tensor, lr: float, eps: float) -> None:
+    """nais_rows_adagrad: one row-sparse Adagrad step on `param` / `state_sum` (in place) from key-ordered (id, gradient row) pairs;
+    equal ids are summed first, in list order (deterministic)."""
+    dev = _need_cuda(keys, rows, param, state_sum)
+    lib = _lib.load()
+    n, w = rows.shape
+    if not (param.is_contiguous() and state_sum.is_contiguous() and param.dtype == torch.float32 and state_sum.dtype == torch.float32):
+        raise RuntimeError("rows_adagrad: param and its state must be contiguous float32")
+    with torch.cuda.device(dev):
+        k32 = keys.to(torch.int32).contiguous()
+        r = _f32(rows)
+        ws_bytes = lib.nais_rows_adagrad_workspace_bytes(n, w)
+        ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
+        _lib.check(lib.nais_rows_adagrad(k32.data_ptr(), r.data_ptr(), n, w, param.shape[0], None, param.data_ptr(), state_sum.data_ptr(),
+                                         float(lr), float(eps), ws.data_ptr(), ws_bytes, _stream()), "nais_rows_adagrad")
+
+
 def pairs_backward_adagrad(variant: str, beta: float, P: Dict[str, torch.Tensor], sums: Dict[str, torch.Tensor], lr: float,
                            eps: float, hist, tgt, hreg, treg, aux, row_sum, parts, dscore, drop=(0.0, 0, "auto"),
                            act_mask: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:

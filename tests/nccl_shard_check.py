@@ -41,6 +41,36 @@ def main():
         # end to end from pinned host memory as well
         s_h, i_h = r.topk_host(torch.from_numpy(indptr).pin_memory(), torch.from_numpy(users.items.cpu().numpy().astype(np.int64)).pin_memory(), k)
         ok = ok and bool(torch.equal(i_h, solo[1].cpu().to(torch.int64)))
+    # ---- data-parallel training with the touched-row exchange: replicas stay bit-identical and equal the dense global step ----
+    from poi_recommendation_models_b200 import batches as PB
+    from poi_recommendation_models_b200.distributed import SparseRowExchange
+    data = synthetic.make_checkins(16, 5000, seed=3, hist_len=None, max_hist=40, min_hist=3, median_hist=12)
+    csr = data.train_csr()
+    sd2 = orc.init_state("region_distance", 5000, 64, 64, data.region_num, 1, seed=5, style="trained")
+    mt = util.make_model("region_distance", sd2, 0.5, device=dev).train()
+    ot = torch.optim.Adagrad(mt.parameters(), lr=0.05)
+    ex = SparseRowExchange(mt, ot, world)
+    bt = PB.DeviceBatcher(csr, data.region, data.coords, device=dev, seed=0)
+    mref = util.make_model("region_distance", sd2, 0.5, device=dev).train()  # every rank replays the GLOBAL step densely
+    oref = torch.optim.Adagrad(mref.parameters(), lr=0.05)
+    per = 16 // world
+    for it in range(10):
+        bs = [bt.multi_user_batch(np.arange(r * per, (r + 1) * per), 4, seed=100 * it + r) for r in range(world)]
+        mine = bs[rank]
+        w_loc = torch.full((mine.B,), 1.0 / mine.B, device=dev)
+        ex.step(mine.label, mine, row_weight=w_loc)
+        oref.zero_grad()
+        tot = 0
+        for b_ in bs:  # the global loss: mean over ranks of the per-rank mean BCE
+            tot = tot + torch.nn.functional.binary_cross_entropy(torch.sigmoid(mref.segmented_scores(b_)), b_.label) / world
+        tot.backward()
+        oref.step()
+    for (n_, pa), (_, pb) in zip(mt.named_parameters(), mref.named_parameters()):
+        ok = ok and float((pa - pb).abs().max()) <= 2e-5 * max(float(pb.abs().max()), 1e-3)
+        mine_p = pa.detach().clone()
+        other = [torch.empty_like(mine_p) for _ in range(world)]
+        dist.all_gather(other, mine_p)
+        ok = ok and all(torch.equal(o_, other[0]) for o_ in other)  # bit-identical replicas after 10 steps
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0 and int(flag.item()) == 1:

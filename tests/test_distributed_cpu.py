@@ -83,6 +83,17 @@ def _worker_body(rank, world, port, q, min_shard, want_grid):
     ok = ok and (r.gc, r.gu) == want_grid and (r.lo, r.hi) == shard_range(N, rank % r.gc, r.gc)
     if want_grid == (2, 1):
         ok = ok and (r.lo, r.hi) == ((0, 512) if rank == 0 else (512, 1000))
+    # touched-row exchange of the data-parallel training step: ragged (ids, rows) lists from every rank, rank-major order
+    from poi_recommendation_models_b200.distributed import SparseRowExchange
+    ex = SparseRowExchange.__new__(SparseRowExchange)
+    ex.world, ex.last_bytes = world, 0
+    n_mine = 3 + 2 * rank
+    ids = torch.arange(n_mine, dtype=torch.int64) * (rank + 1)
+    rows = torch.full((n_mine, 4), float(rank + 1))
+    gi, gr = ex.exchange(ids, rows)
+    want_i = torch.cat([torch.arange(3 + 2 * r, dtype=torch.int64) * (r + 1) for r in range(world)])
+    want_r = torch.cat([torch.full((3 + 2 * r, 4), float(r + 1)) for r in range(world)])
+    ok = ok and torch.equal(gi, want_i) and torch.equal(gr, want_r)
     # data-parallel gradient averaging
     lin = torch.nn.Linear(4, 3)
     for p_ in lin.parameters():

