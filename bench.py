@@ -522,18 +522,35 @@ def dp_large_catalogue_block(args, dev, rank, world, T, H, D, hid):
     ll2 = (c2[t2][:, None, :] - c2[h2]).abs().float().contiguous()
     hr2, tr2 = r2[h2], r2[t2]
     label = torch.cat([torch.ones(T), torch.zeros(T)]).to(dev)
-    out = {"rows_per_gpu": 2 * T, "pois": n_big, "n_gpus": world}
-    for kind in ("dense_allreduce", "sparse_row_exchange"):
+    out = {"pois": n_big, "n_gpus": world,
+           "shapes": {"c3_rows": "8192 rows per GPU, own history per row (H=128): ~1M cells touch a large part of the tables",
+                      "multi_user_64": "64 users per GPU (H=128 each), 5 rows per positive, segmented layout: ~50k touched rows"}}
+    # the realistic large-catalogue step: a multi-user batch touches thousands of rows, not hundreds of thousands
+    from poi_recommendation_models_b200 import batches as PB
+    import scipy.sparse as sp
+    nu = 64
+    hu = synth_histories(nu, n_big, H, seed=50 + rank)
+    csr = sp.csr_matrix((np.ones(nu * H), hu.reshape(-1), np.arange(0, (nu + 1) * H, H)), shape=(nu, n_big))
+    bt = PB.DeviceBatcher(csr, r2np, c2np, device=dev, seed=0)
+    mb = bt.multi_user_batch(np.arange(nu), 4, seed=rank)
+    for shape, kind in (("c3_rows", "dense_allreduce"), ("c3_rows", "sparse_row_exchange"), ("multi_user_64", "dense_allreduce"),
+                        ("multi_user_64", "sparse_row_exchange")):
         torch.manual_seed(2)
         m2 = M.NAIS_region_distance_Embedding(n_big, D, hid, BETA, R2, 1).to(dev).train()
         opt = torch.optim.Adagrad(m2.parameters(), lr=0.01, weight_decay=0.0)
         ex = SparseRowExchange(m2, opt, world) if kind == "sparse_row_exchange" else None
 
         def one():
-            if ex is not None:
-                return ex.step(label, h2, t2, hr2, tr2, ll2)
-            opt.zero_grad()
-            ls_ = m2.loss_func(m2(h2, t2, hr2, tr2, ll2), label)
+            if shape == "multi_user_64":
+                if ex is not None:
+                    return ex.step(mb.label, mb)
+                opt.zero_grad()
+                ls_ = m2.loss_func(torch.sigmoid(m2.segmented_scores(mb)), mb.label)
+            else:
+                if ex is not None:
+                    return ex.step(label, h2, t2, hr2, tr2, ll2)
+                opt.zero_grad()
+                ls_ = m2.loss_func(m2(h2, t2, hr2, tr2, ll2), label)
             ls_.backward()
             allreduce_gradients(m2, world)
             opt.step()
@@ -553,11 +570,14 @@ def dp_large_catalogue_block(args, dev, rank, world, T, H, D, hid):
         t = torch.tensor([a2.elapsed_time(b2) / args.steps], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        out[kind] = {"ms_per_step": float(t.item()), "rows_per_s": 2 * T * world / (float(t.item()) / 1000.0), "loss": float(ls)}
+        rows_gpu = mb.B if shape == "multi_user_64" else 2 * T
+        key = f"{shape}/{kind}"
+        out[key] = {"ms_per_step": float(t.item()), "rows_per_s": rows_gpu * world / (float(t.item()) / 1000.0), "rows_per_gpu": rows_gpu,
+                    "loss": float(ls)}
         if ex is not None:
-            out[kind]["bytes_received_per_step"] = int(ex.last_bytes)
+            out[key]["bytes_received_per_step"] = int(ex.last_bytes)
         else:
-            out[kind]["bytes_allreduced_per_step"] = int(sum(p.numel() for p in m2.parameters()) * 4) if world > 1 else 0
+            out[key]["bytes_allreduced_per_step"] = int(sum(p.numel() for p in m2.parameters()) * 4) if world > 1 else 0
         del m2, opt, ex
         torch.cuda.empty_cache()
     return out

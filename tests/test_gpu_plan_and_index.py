@@ -200,4 +200,5 @@ def test_nccl_range_shards_equal_one_gpu():
     script = os.path.join(ROOT, "tests", "nccl_shard_check.py")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", str(_free_port()), script], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "NCCL_SHARD_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    diag = "\n".join(ln for ln in r.stderr.splitlines() if ln.startswith("[rank"))
+    assert r.returncode == 0 and "NCCL_SHARD_CHECK_OK" in r.stdout, diag + r.stdout[-1000:] + r.stderr[-1500:]
