@@ -43,7 +43,7 @@ extern "C" {
 /* distance modes */
 #define NAIS_DIST_NONE 0   /* NAIS_basic, NAIS_regionEmbedding */
 #define NAIS_DIST_LATLON 1 /* sigmoid(Linear(2,2)(scale*|dlat,dlon|)) -> 2 extra input lanes of attn_layer1 (model.py:265, :366) */
-#define NAIS_DIST_KM 2     /* logit += dist_km * sum_d embed_distance[bucket,d]  (model.py:497-504; reference uses bucket 0) */
+#define NAIS_DIST_KM 2     /* logit += dist_km * sum_d embed_distance[0,d]  (model.py:497-504) */
 
 /* precision of the attention-MLP contraction in nais_fullrank_topk */
 #define NAIS_PREC_FP32 0     /* FP32 FFMA on CUDA cores (exact path) */
@@ -98,9 +98,9 @@ typedef struct NaisParams {
   float dist_scale;   /* 100 (model.py:265) or 1000 (model.py:366) */
   const float* dist_w; /* [2,2] dist_layer.weight (LATLON) */
   const float* dist_b; /* [2]   dist_layer.bias   (LATLON) */
-  const float* dist_embed; /* [dist_buckets, D] embed_distance.weight (KM) */
-  int32_t dist_buckets;    /* >= 1; reference: 1 */
-  float dist_bucket_km;    /* bucket = min(floor(km / dist_bucket_km), dist_buckets-1); ignored when dist_buckets == 1 */
+  const float* dist_embed; /* [1, D] embed_distance.weight (KM): the reference allocates dist_embed_size rows and reads row 0 only (model.py:497-498) */
+  int32_t dist_buckets;    /* must be 1 (row 0 of embed_distance); anything else is NAIS_ERR_MODE */
+  float dist_bucket_km;    /* reserved (ignored) */
   float beta;              /* smoothing exponent of the softmax denominator (model.py:284-285) */
   /* Train-mode dropout on the attention hidden layer, relu(drop(W x + b)) (NAIS_basic / NAIS_regionEmbedding,
    * model.py:71,162).  0 disables.  Element (pair b, history h, hidden k) is kept iff

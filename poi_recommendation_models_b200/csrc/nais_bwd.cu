@@ -56,7 +56,6 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
 
   const int tid = threadIdx.x, cell = tid & (TC - 1), half = tid >> 7;
   const int tk = tid & 15, tj = tid >> 4;
-  const int64_t n_cells = pairs_n_cells(A.b);
   const bool vec4 = rows_vec4(br, D >> 1);  // 128-bit embedding-row gathers
   const bool w1_vec2 = (reinterpret_cast<uintptr_t>(br.w1) & 7u) == 0;  // ldw = D + lanes is even: rows of W are 8-byte aligned
 
@@ -427,9 +426,7 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
                 o[cc] = full * ps[rr * D + d];
                 dpv[cc] = full * qv[cc];
               }
-              const int64_t ci = cgl[c];
-              store_dq4(A, br.w_poi, br.w_reg, A.dq_h ? __ldg(A.pos_h + ci) : 0u, A.dq_r ? __ldg(A.pos_r + ci) : 0u, d0,
-                        make_float4(o[0], o[1], o[2], o[3]));
+              if (A.ws_dq) *reinterpret_cast<float4*>(A.ws_dq + cgl[c] * D + d0) = make_float4(o[0], o[1], o[2], o[3]);
             }
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) As[(size_t)(d0 + cc) * TCP + c] = dpv[cc];
@@ -451,10 +448,8 @@ __global__ void __launch_bounds__(NT, (NKB * DB <= 1) ? 2 : 1) pairs_bwd_kernel(
       }
     }
     __syncthreads();
-    for (int i = tid; i < nrows * D; i += NT) {
-      const int64_t row = row0 + i / D;
-      store_dp(A, br.w_poi, br.w_reg, A.dp_t ? __ldg(A.pos_t + row) : 0u, A.dq_r ? __ldg(A.pos_r + n_cells + row) : 0u, i % D, dpacc[i]);
-    }
+    if (A.ws_dp)
+      for (int i = tid; i < nrows * D; i += NT) A.ws_dp[(row0 + i / D) * D + (i % D)] = dpacc[i];
   }
 
   // ---- flush this CTA's parameter partials --------------------------------------------------------------------------
@@ -568,18 +563,9 @@ __global__ void make_keys_kernel(NaisPairs b, int item_num, int region_num, int*
   }
 }
 
-// pos[src] = rank of that contribution in key order (the inverse of the sorted source lists): where the backward tile kernel
-// writes the row.
-__global__ void invert_perm_kernel(const uint32_t* __restrict__ s_hist, int64_t n_hist, uint32_t* pos_h, const uint32_t* __restrict__ s_tgt,
-                                   int64_t n_tgt, uint32_t* pos_t, const uint32_t* __restrict__ s_reg, int64_t n_reg, uint32_t* pos_r) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (s_hist && i < n_hist) pos_h[s_hist[i]] = (uint32_t)i;
-  if (s_tgt && i < n_tgt) pos_t[s_tgt[i]] = (uint32_t)i;
-  if (s_reg && i < n_reg) pos_r[s_reg[i]] = (uint32_t)i;
-}
-
-// Embedding-row gradients: out[key, 0:w] = sum of the contribution rows of every sorted entry with that key; entry i's row is
-// rows[i, 0:w] (the tile kernel wrote it there).  Two deterministic passes, no atomics:
+// Embedding-row gradients: out[key, 0:w] = sum of the contribution rows of every sorted entry with that key.  Entry i's row is
+// rows + src[i] * stride (src == NULL: entry i's row is row i — nais_rows_adagrad's key-ordered lists).  Two deterministic
+// passes, no atomics:
 //   pass 1  one warp per chunk of SEG_CHUNK consecutive entries accumulates runs of equal keys in order; a run that lies
 //           strictly inside its chunk is complete and is written to the table row directly, the (at most two) runs that touch
 //           a chunk boundary go to partial slots [2*chunk] (first run) / [2*chunk+1] (last run) together with a flag saying
@@ -608,15 +594,29 @@ __device__ __forceinline__ void seg_store(const SegOut& o, size_t idx, float g) 
   }
 }
 
-// Pass 1 streams the rows in order (a chunk is SEG_CHUNK * w * 4 contiguous bytes).  r2 profile of the first version (one
+// Where the contribution rows of a reduction live: source s < n_cells is cell s's dq row, s >= n_cells is row (s - n_cells)'s
+// dp row; `off` selects the table's column range inside the D-wide row.
+struct SegRows {
+  const float* dq;
+  const float* dp;
+  int64_t n_cells;
+  int D, off;
+};
+__device__ __forceinline__ const float* seg_row_ptr(const SegRows& R, const uint32_t* __restrict__ src, int64_t i) {
+  if (!src) return R.dq + (size_t)i * R.D + R.off;  // key-ordered list: entry i's row is row i
+  const uint32_t s = src[i];
+  return (s < R.n_cells ? R.dq + (size_t)s * R.D : R.dp + (size_t)(s - R.n_cells) * R.D) + R.off;
+}
+
+// Pass 1 reads the rows of its chunk (a chunk is SEG_CHUNK * w * 4 contiguous bytes).  r2 profile of the first version (one
 // shuffle + compare + branch + four predicated loads / adds per entry): 50 warp instructions per entry, issue-bound at 1.8 TB/s.
 // Now: the chunk's 64 keys sit two per lane, ONE pair of ballots marks where runs start, and each run is a branch-free
 // accumulation of its rows (SEG_ILP loads in flight, added in entry order: same sums, bit for bit) — ~4 instructions per entry.
 // NQ = ceil(w / 32) floats per lane (w <= 128).
 constexpr int SEG_ILP = 8;
 template <int NQ>
-__global__ void segment_reduce_pass1_kernel(const int* __restrict__ keys, int64_t n, const float* __restrict__ rows, int w, int n_rows,
-                                            SegOut out, int* __restrict__ part_key, int* __restrict__ part_start,
+__global__ void segment_reduce_pass1_kernel(const int* __restrict__ keys, const uint32_t* __restrict__ src, int64_t n, SegRows R, int w,
+                                            int n_rows, SegOut out, int* __restrict__ part_key, int* __restrict__ part_start,
                                             float* __restrict__ part_rows) {
   const int64_t chunk = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -626,13 +626,15 @@ __global__ void segment_reduce_pass1_kernel(const int* __restrict__ keys, int64_
   const int cnt = (int)(end - start);
   if (lane < 2) part_key[2 * chunk + lane] = -1;
   const int k0 = lane < cnt ? keys[start + lane] : -1, k1 = 32 + lane < cnt ? keys[start + 32 + lane] : -1;
+  // where this lane's two entries' rows live (handed around by shuffles below)
+  const float* r0p = lane < cnt ? seg_row_ptr(R, src, start + lane) : nullptr;
+  const float* r1p = 32 + lane < cnt ? seg_row_ptr(R, src, start + 32 + lane) : nullptr;
   const int key_before = start > 0 ? keys[start - 1] : -1, key_after = end < n ? keys[end] : -1;
   // bit j of `starts` = entry j begins a run (entry 0 always does)
   const int p0 = __shfl_up_sync(0xffffffffu, k0, 1), last0 = __shfl_sync(0xffffffffu, k0, 31), p1 = __shfl_up_sync(0xffffffffu, k1, 1);
   const unsigned m0 = __ballot_sync(0xffffffffu, lane < cnt && (lane == 0 || k0 != p0));
   const unsigned m1 = __ballot_sync(0xffffffffu, 32 + lane < cnt && k1 != (lane == 0 ? last0 : p1));
   const unsigned long long starts = (unsigned long long)m0 | ((unsigned long long)m1 << 32);
-  const float* base = rows + (size_t)start * w;
   bool col[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) col[q] = lane + 32 * q < w;
@@ -663,9 +665,13 @@ __global__ void segment_reduce_pass1_kernel(const int* __restrict__ keys, int64_
   for (int j0 = 0; j0 < cnt; j0 += SEG_ILP) {
     float r[SEG_ILP][NQ];
 #pragma unroll
-    for (int u = 0; u < SEG_ILP; ++u)
+    for (int u = 0; u < SEG_ILP; ++u) {
+      const int j = j0 + u;  // (j0 is a multiple of SEG_ILP = 8: a batch never straddles the two key registers)
+      const unsigned long long pj = __shfl_sync(0xffffffffu, (unsigned long long)(j0 < 32 ? r0p : r1p), j & 31);
+      const float* row = reinterpret_cast<const float*>(pj);
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) r[u][q] = (j0 + u < cnt && col[q]) ? __ldcs(base + (size_t)(j0 + u) * w + lane + 32 * q) : 0.f;
+      for (int q = 0; q < NQ; ++q) r[u][q] = (j < cnt && col[q]) ? __ldcs(row + lane + 32 * q) : 0.f;
+    }
 #pragma unroll
     for (int u = 0; u < SEG_ILP; ++u) {
       const int j = j0 + u;
@@ -730,18 +736,18 @@ __global__ void segment_reduce_pass2_kernel(const int* __restrict__ part_key, co
 
 // Both passes over n key-ordered rows (keys ascending, rows[i] belongs to keys[i]).  pk / pst / pr: partial slots for
 // 2 * ceil(n / SEG_CHUNK) boundary runs (keys, start flags, rows of width w).
-static void launch_segment_reduce(const int* keys, int64_t n, const float* rows, int w, int n_rows, const SegOut& out, int* pk, int* pst,
-                                  float* pr, cudaStream_t stream) {
+static void launch_segment_reduce(const int* keys, const uint32_t* src, int64_t n, const SegRows& rows, int w, int n_rows, const SegOut& out,
+                                  int* pk, int* pst, float* pr, cudaStream_t stream) {
   const int64_t nch = (n + SEG_CHUNK - 1) / SEG_CHUNK;
   const unsigned g1 = (unsigned)((nch * 32 + 255) / 256), g2 = (unsigned)((2 * nch * 32 + 255) / 256);
   if (w <= 32) {
-    segment_reduce_pass1_kernel<1><<<g1, 256, 0, stream>>>(keys, n, rows, w, n_rows, out, pk, pst, pr);
+    segment_reduce_pass1_kernel<1><<<g1, 256, 0, stream>>>(keys, src, n, rows, w, n_rows, out, pk, pst, pr);
     segment_reduce_pass2_kernel<1><<<g2, 256, 0, stream>>>(pk, pst, pr, nch, w, out);
   } else if (w <= 64) {
-    segment_reduce_pass1_kernel<2><<<g1, 256, 0, stream>>>(keys, n, rows, w, n_rows, out, pk, pst, pr);
+    segment_reduce_pass1_kernel<2><<<g1, 256, 0, stream>>>(keys, src, n, rows, w, n_rows, out, pk, pst, pr);
     segment_reduce_pass2_kernel<2><<<g2, 256, 0, stream>>>(pk, pst, pr, nch, w, out);
   } else {
-    segment_reduce_pass1_kernel<4><<<g1, 256, 0, stream>>>(keys, n, rows, w, n_rows, out, pk, pst, pr);
+    segment_reduce_pass1_kernel<4><<<g1, 256, 0, stream>>>(keys, src, n, rows, w, n_rows, out, pk, pst, pr);
     segment_reduce_pass2_kernel<4><<<g2, 256, 0, stream>>>(pk, pst, pr, nch, w, out);
   }
   NAIS_COUNT_LAUNCH(2);
@@ -766,7 +772,13 @@ int launch_rows_adagrad(const int32_t* keys, const float* rows, int64_t n, int w
   o.lr = lr;
   o.eps = eps;
   o.remap = nullptr;
-  launch_segment_reduce(keys, n, rows, w, n_rows, o, reinterpret_cast<int*>(base), reinterpret_cast<int*>(base + kb),
+  SegRows R;
+  R.dq = rows;
+  R.dp = nullptr;
+  R.n_cells = n;
+  R.D = w;
+  R.off = 0;
+  launch_segment_reduce(keys, nullptr, n, R, w, n_rows, o, reinterpret_cast<int*>(base), reinterpret_cast<int*>(base + kb),
                         reinterpret_cast<float*>(base + 2 * kb), stream);
   return (int)cudaGetLastError();
 }
@@ -775,7 +787,7 @@ int launch_rows_adagrad(const int32_t* keys, const float* rows, int64_t n, int w
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct BwdLayout {
-  size_t dq_h, dq_r, dp_t, part, kin[3], vin[3], kout[3], vout[3], pos[3], cub, pkey, pstart, prows, total;
+  size_t dq, dp, part, kin[3], vin[3], kout[3], vout[3], cub, pkey, pstart, prows, total;
   int64_t n_chunks;
   int grid, stride;
   size_t cub_bytes;
@@ -798,12 +810,10 @@ static BwdLayout bwd_layout(const NaisParams& p, const NaisPairs& b) {
   const int64_t n_cells = pairs_n_cells(b), n_max = n_cells + B;
   const int64_t n_of[3] = {n_cells, B, n_max};
   size_t o = 0;
-  L.dq_h = o;
-  o += align_up((size_t)n_cells * w_poi * 4);
-  L.dq_r = o;
-  o += align_up((size_t)n_max * w_reg * 4);
-  L.dp_t = o;
-  o += align_up((size_t)B * w_poi * 4);
+  L.dq = o;
+  o += align_up((size_t)n_cells * D * 4);
+  L.dp = o;
+  o += align_up((size_t)B * D * 4);
   L.grid = bwd_grid();
   L.stride = part_floats(p.hid, D, lanes);
   L.part = o;
@@ -814,7 +824,6 @@ static BwdLayout bwd_layout(const NaisParams& p, const NaisPairs& b) {
     L.vin[i] = o, o += bytes;
     L.kout[i] = o, o += bytes;
     L.vout[i] = o, o += bytes;
-    L.pos[i] = o, o += bytes;
   }
   size_t cb = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, cb, (const int*)nullptr, (int*)nullptr, (const uint32_t*)nullptr,
@@ -871,7 +880,7 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
     const bool want[3] = {br.w_poi > 0 && (g.hist_poi[bi] || (opt && opt->sum_hist_poi[bi])),
                           br.w_poi > 0 && (g.tgt_poi[bi] || (opt && opt->sum_tgt_poi[bi])),
                           br.w_reg > 0 && (g.reg[bi] || (opt && opt->sum_reg[bi]))};
-    // ---- 1. sort the ids, invert the permutations: every contribution row gets its slot in key order -----------------------
+    // ---- 1. sort the ids (they do not depend on the gradients; stable radix sort: equal ids keep cell order) ----------------
     if (want[0] || want[1] || want[2]) {
       const int64_t n_thr = n_cells > b.B ? n_cells : b.B;
       make_keys_kernel<<<(unsigned)((n_thr + 255) / 256), 256, 0, stream>>>(
@@ -887,10 +896,6 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
         cub::DeviceRadixSort::SortPairs(base + L.cub, cb, I(L.kin[t]), I(L.kout[t]), U(L.vin[t]), U(L.vout[t]), (int)n_of[t], 0, bits,
                                         stream);
       }
-      invert_perm_kernel<<<(unsigned)((n_of[2] + 255) / 256), 256, 0, stream>>>(
-          want[0] ? U(L.vout[0]) : nullptr, n_of[0], U(L.pos[0]), want[1] ? U(L.vout[1]) : nullptr, n_of[1], U(L.pos[1]),
-          want[2] ? U(L.vout[2]) : nullptr, n_of[2], U(L.pos[2]));
-      NAIS_COUNT_LAUNCH(1);
     }
     // ---- 2. the tile kernel ------------------------------------------------------------------------------------------------
     BwdArgs A;
@@ -901,12 +906,8 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
     A.row_sum = row_sum + (size_t)bi * b.B;
     A.dscore = dscore;
     A.act_mask = (p.n_branch == 1 && p.hid <= 64) ? act_mask : nullptr;
-    A.dq_h = want[0] ? reinterpret_cast<float*>(base + L.dq_h) : nullptr;
-    A.dp_t = want[1] ? reinterpret_cast<float*>(base + L.dp_t) : nullptr;
-    A.dq_r = want[2] ? reinterpret_cast<float*>(base + L.dq_r) : nullptr;
-    A.pos_h = U(L.pos[0]);
-    A.pos_t = U(L.pos[1]);
-    A.pos_r = U(L.pos[2]);
+    A.ws_dq = (want[0] || want[2]) ? reinterpret_cast<float*>(base + L.dq) : nullptr;
+    A.ws_dp = (want[1] || want[2]) ? reinterpret_cast<float*>(base + L.dp) : nullptr;
     A.ws_part = reinterpret_cast<float*>(base + L.part);
     A.part_stride = L.stride;
     A.n_items = pairs_n_tiles(b);
@@ -931,7 +932,7 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
                                                               p.dist_mode == NAIS_DIST_KM ? g.dist_embed : nullptr, D, bi > 0);
       NAIS_COUNT_LAUNCH(1);
     }
-    // ---- 3. embedding rows: stream the key-ordered contribution rows ----------------------------------------------------------
+    // ---- 3. embedding rows: gather the contribution rows in key order ------------------------------------------------------------
     auto dest = [&](float* grad, const float* param, float* sum, const int32_t* remap) {
       SegOut o;
       o.out = grad;
@@ -942,14 +943,20 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
       o.remap = remap;
       return o;
     };
-    auto seg = [&](int t, const float* rows, int w, int n_rows, SegOut out) {
-      launch_segment_reduce(I(L.kout[t]), n_of[t], rows, w, n_rows, out, I(L.pkey), I(L.pstart), reinterpret_cast<float*>(base + L.prows),
-                            stream);
+    auto seg = [&](int t, int off, int w, int n_rows, SegOut out) {
+      SegRows R;
+      R.dq = t == 1 ? A.ws_dp : A.ws_dq;  // the target list's sources are plain row indices into dp
+      R.dp = A.ws_dp;
+      R.n_cells = t == 1 ? n_of[1] : n_cells;
+      R.D = D;
+      R.off = off;
+      launch_segment_reduce(I(L.kout[t]), U(L.vout[t]), n_of[t], R, w, n_rows, out, I(L.pkey), I(L.pstart),
+                            reinterpret_cast<float*>(base + L.prows), stream);
     };
-    if (want[0]) seg(0, A.dq_h, br.w_poi, p.item_num, dest(g.hist_poi[bi], br.hist_poi, opt ? opt->sum_hist_poi[bi] : nullptr, g.remap_hist_poi[bi]));
-    if (want[1]) seg(1, A.dp_t, br.w_poi, p.item_num, dest(g.tgt_poi[bi], br.tgt_poi, opt ? opt->sum_tgt_poi[bi] : nullptr, g.remap_tgt_poi[bi]));
+    if (want[0]) seg(0, 0, br.w_poi, p.item_num, dest(g.hist_poi[bi], br.hist_poi, opt ? opt->sum_hist_poi[bi] : nullptr, g.remap_hist_poi[bi]));
+    if (want[1]) seg(1, 0, br.w_poi, p.item_num, dest(g.tgt_poi[bi], br.tgt_poi, opt ? opt->sum_tgt_poi[bi] : nullptr, g.remap_tgt_poi[bi]));
     // (history-side and target-side region rows are one table in every variant: hist_reg == tgt_reg)
-    if (want[2]) seg(2, A.dq_r, br.w_reg, p.region_num, dest(g.reg[bi], br.hist_reg, opt ? opt->sum_reg[bi] : nullptr, g.remap_reg[bi]));
+    if (want[2]) seg(2, br.w_poi, br.w_reg, p.region_num, dest(g.reg[bi], br.hist_reg, opt ? opt->sum_reg[bi] : nullptr, g.remap_reg[bi]));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }

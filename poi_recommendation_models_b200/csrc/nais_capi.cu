@@ -80,7 +80,7 @@ static int check_params(const NaisParams* p) {
   }
   if (p->dist_mode == NAIS_DIST_LATLON && (!p->dist_w || !p->dist_b)) return NAIS_ERR_NULL;
   if (p->dist_mode == NAIS_DIST_KM && (!p->dist_embed || p->dist_buckets < 1)) return NAIS_ERR_NULL;
-  if (p->dist_mode == NAIS_DIST_KM && p->dist_buckets > 1 && !(p->dist_bucket_km > 0.f)) return NAIS_ERR_MODE;
+  if (p->dist_mode == NAIS_DIST_KM && p->dist_buckets != 1) return NAIS_ERR_MODE;  // one bucket, like the reference (model.py:497-498)
   if (p->pairs_precision < NAIS_PAIRS_AUTO || p->pairs_precision > NAIS_PAIRS_TC) return NAIS_ERR_MODE;
   return 0;
 }

@@ -321,6 +321,298 @@ __global__ void __launch_bounds__(PT, (D > 48) ? 3 : 4) pairs_fwd_tc_kernel(cons
   if (warp == 0) tmem_dealloc(tmem, A.tmem_cols);
 }
 
+// =====================================================================================================================
+// The headline shape (D = hid = 64) with TWO threads per cell (256 threads): warps 0-3 build / drain the first 32 embedding
+// columns / hidden units of every cell, warps 4-7 the other 32 (warps w and w + 4 share a TMEM lane quarter).  ncu on the
+// 128-thread kernel at C3 (profiles/r2_ncu_pairs_fwd_tc_summary.csv): 168 registers -> 12 warps per SM, issue slots 37 % busy,
+// stalled on the L2 gathers; halving the per-thread row (x[32] instead of x[64]) doubles the warps in flight and halves every
+// serial phase of a tile.  The halves meet twice per tile: the row's scaling maximum + similarity sum, and the logit.
+// =====================================================================================================================
+constexpr int PT2 = 256;
+
+__global__ void __launch_bounds__(PT2, 3) pairs_fwd_tc2_kernel(const __grid_constant__ Args A) {
+  constexpr int D = 64, HIDC = 64, KC = D / 8, A_PLANE = KC * PT * 16, W_PLANE = KC * HIDC * 16;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const NaisParams& p = A.p;
+  const NaisBranch& br = p.branch[0];
+  const int lanes = (p.dist_mode == NAIS_DIST_LATLON) ? 2 : 0, ldw = D + lanes;
+  constexpr int STG_BYTES = 8 * 32 * STG_STRIDE;  // 36 864 B: the row staging of eight warps ALIASES the A image (+ 4 KB of padding):
+  static_assert(STG_BYTES <= 2 * A_PLANE + 4096, "staging must fit in the A image + pad");  // rows are read back before A is written
+  uint8_t* sA = smem;                      // [hi | lo][KC][128 rows][16 B]
+  uint8_t* sWi = sA + 2 * A_PLANE + 4096;  // [hi | lo][KC][64 rows][16 B]
+  float* kc = reinterpret_cast<float*>(sWi + 2 * W_PLANE);  // [64] x {b1, w2, w1[:, D], w1[:, D+1]}
+  float* ps = kc + 4 * HIDC;               // [PMAXROWS][D] target vectors of the rows of this tile
+  float* red_e = ps + PMAXROWS * D;        // [PT] masked exp per cell
+  float* red_es = red_e + PT;              // [PT] masked exp * similarity
+  float* row_e = red_es + PT;              // [PMAXROWS]
+  float* row_es = row_e + PMAXROWS;        // [PMAXROWS]
+  float* wred = row_es + PMAXROWS;         // [8] per-warp |W| maxima
+  float* xmax = wred + 8;                  // [2][PT] |x| maximum of each half of a cell's row
+  float* xsum = xmax + 2 * PT;             // [2][PT] similarity partial of each half
+  float* apart = xsum + 2 * PT;            // [2][PT] logit partial of each half
+  uint32_t* abits = reinterpret_cast<uint32_t*>(apart + 2 * PT);  // [PT] ReLU pattern of hidden units 32..63 (from half 1)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(abits + PT);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint8_t* stg_all = sA;                   // [8 warps][32][STG_STRIDE] row staging of the cooperative gather
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp >> 2, qd = warp & 3, cell = qd * 32 + lane, s0 = 32 * half;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tslot, 64u);
+  // ---- constant operand: W[:, :D] * wscale as hi/lo fp16 planes, plus the per-hidden-unit constants -------------------------
+  float wmax = 0.f;
+  for (int i = tid; i < HIDC * D; i += PT2) {
+    const int k = i / D, d = i - k * D;
+    wmax = fmaxf(wmax, fabsf(__ldg(br.w1 + (size_t)k * ldw + d)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+  if (lane == 0) wred[warp] = wmax;
+  __syncthreads();
+  wmax = fmaxf(fmaxf(fmaxf(wred[0], wred[1]), fmaxf(wred[2], wred[3])), fmaxf(fmaxf(wred[4], wred[5]), fmaxf(wred[6], wred[7])));
+  const float wscale = pow2_scale(wmax, 9);  // |W| * wscale < 512
+  const float inv_wscale = 1.f / wscale;
+  for (int i = tid; i < HIDC * KC; i += PT2) {
+    const int c = i / HIDC, k = i - c * HIDC;
+    __align__(16) __half hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_f16(__ldg(br.w1 + (size_t)k * ldw + c * 8 + e) * wscale, hi[e], lo[e]);
+    *reinterpret_cast<uint4*>(sWi + ((size_t)c * HIDC + k) * 16) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(sWi + W_PLANE + ((size_t)c * HIDC + k) * 16) = *reinterpret_cast<const uint4*>(lo);
+  }
+  for (int k = tid; k < HIDC; k += PT2)  // one 16-byte load per hidden unit in the epilogue: {b1, w2, w1[:, D], w1[:, D+1]}
+    reinterpret_cast<float4*>(kc)[k] = make_float4(__ldg(br.b1 + k), __ldg(br.w2 + k), lanes ? __ldg(br.w1 + (size_t)k * ldw + D) : 0.f,
+                                                   lanes ? __ldg(br.w1 + (size_t)k * ldw + D + 1) : 0.f);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  const uint32_t tlane = tmem + ((uint32_t)(qd * 32) << 16);
+  uint8_t* stg = stg_all + (size_t)(warp * 32) * STG_STRIDE;
+
+  const int64_t n_items = pairs_n_tiles(A.b);
+  uint32_t phase = 0;
+  for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const PairTile T = pair_tile(A.b, item);
+    const int64_t row0 = T.row0;
+    const int nrows = T.nrows, H = T.H;
+    const int n_chunks = (H <= PT) ? 1 : (H + PT - 1) / PT;
+    for (int i = tid; i < nrows * D; i += PT2) {
+      const int r = i / D, d = i - r * D;
+      ps[r * D + d] = (d < br.w_poi) ? __ldg(br.tgt_poi + (size_t)checked_id(A.b.tgt[row0 + r], p.item_num, A.bad) * br.w_poi + d)
+                                     : __ldg(br.tgt_reg + (size_t)checked_id(A.b.treg[row0 + r], p.region_num, A.bad) * br.w_reg + (d - br.w_poi));
+    }
+    if (tid < PMAXROWS) {
+      row_e[tid] = 0.f;
+      row_es[tid] = 0.f;
+    }
+    __syncthreads();
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      int r, h;
+      bool valid;
+      if (H <= PT) {
+        r = cell / H;
+        h = cell - r * H;
+        valid = r < nrows;
+      } else {
+        r = 0;
+        h = ch * PT + cell;
+        valid = h < H;
+      }
+      const int64_t cidx = valid ? T.cell0 + r * (int64_t)H + h : 0;      // per-cell arrays
+      const int64_t hidx = valid ? T.hist0 + r * T.hist_rs + h : 0;       // history arrays
+      // ---- this half of the cell's row of X -----------------------------------------------------------------------------------
+      float x[32];
+      float g0 = 0.f, g1 = 0.f;
+      bool live = false;
+      int it32 = 0, rg32 = 0;
+      if (valid) {
+        it32 = checked_id(A.b.hist[hidx], p.item_num, A.bad);
+        rg32 = br.w_reg ? checked_id(A.b.hreg[hidx], p.region_num, A.bad) : 0;
+      }
+      {
+        // warp-cooperative gather of the 32-float segment [s0, s0 + 32) of this warp's 32 history rows (see the kernel above)
+        constexpr int P = 8;
+        float4 v[P];
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+          const int idx = lane + 32 * q, c = idx / P, part = idx - c * P;
+          const int ci = __shfl_sync(0xffffffffu, it32, c), cr = __shfl_sync(0xffffffffu, rg32, c);
+          v[q] = ldg_row4(br.hist_poi + (size_t)ci * br.w_poi, br.hist_reg + (size_t)cr * br.w_reg, br.w_poi, s0 + 4 * part);
+        }
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+          const int idx = lane + 32 * q, c = idx / P, part = idx - c * P;
+          *reinterpret_cast<float4*>(stg + (size_t)c * STG_STRIDE + part * 16) = v[q];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 t = *reinterpret_cast<const float4*>(stg + (size_t)lane * STG_STRIDE + j4 * 16);
+          x[4 * j4] = t.x;
+          x[4 * j4 + 1] = t.y;
+          x[4 * j4 + 2] = t.z;
+          x[4 * j4 + 3] = t.w;
+        }
+        __syncwarp();
+      }
+      float ssum = 0.f, amax = 0.f;
+      if (valid) {
+        const float* pr = ps + r * D + s0;
+#pragma unroll
+        for (int d = 0; d < 32; d += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(pr + d);
+          x[d] *= t.x;
+          x[d + 1] *= t.y;
+          x[d + 2] *= t.z;
+          x[d + 3] *= t.w;
+        }
+#pragma unroll
+        for (int d = 0; d < 32; ++d) {
+          ssum += x[d];
+          amax = fmaxf(amax, fabsf(x[d]));
+        }
+        if (lanes) {
+          float l0, l1;
+          pair_latlon(A.b, cidx, hidx, row0 + r, l0, l1);
+          l0 *= p.dist_scale;
+          l1 *= p.dist_scale;
+          g0 = sigmoidf_exact(fmaf(l1, __ldg(p.dist_w + 1), fmaf(l0, __ldg(p.dist_w + 0), __ldg(p.dist_b + 0))));
+          g1 = sigmoidf_exact(fmaf(l1, __ldg(p.dist_w + 3), fmaf(l0, __ldg(p.dist_w + 2), __ldg(p.dist_b + 1))));
+        }
+        live = A.b.hist[hidx] != A.b.tgt[row0 + r];
+      } else {
+#pragma unroll
+        for (int d = 0; d < 32; ++d) x[d] = 0.f;
+      }
+      xmax[half * PT + cell] = amax;
+      xsum[half * PT + cell] = ssum;
+      __syncthreads();  // every warp has read its staged rows back (the A image may be written); the halves of a cell meet
+      amax = fmaxf(xmax[cell], xmax[PT + cell]);
+      ssum = xsum[cell] + xsum[PT + cell];
+      const float xscale = pow2_scale(amax, 9);
+      const float inv = (1.f / xscale) * inv_wscale;  // both exact powers of two
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        __align__(16) __half hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_f16(x[c * 8 + e] * xscale, hi[e], lo[e]);
+        *reinterpret_cast<uint4*>(sA + ((size_t)(s0 / 8 + c) * PT + cell) * 16) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(sA + A_PLANE + ((size_t)(s0 / 8 + c) * PT + cell) * 16) = *reinterpret_cast<const uint4*>(lo);
+      }
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the MMA's async-proxy reads
+      __syncthreads();
+      // ---- T = X W^T: hi*hi + hi*lo + lo*hi, one elected thread issues, completion arrives on `bar` ---------------------------
+      if (warp == 0) {
+        if (elect_one()) {
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sA), w0 = smem_u32(sWi);
+          const uint32_t idesc = idesc_f16(PT, HIDC);
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t ab = a0 + (pass == 2 ? A_PLANE : 0), wb = w0 + (pass == 1 ? W_PLANE : 0);
+#pragma unroll
+            for (int s = 0; s < D / 16; ++s)
+              mma_f16(tmem, smem_desc(ab + s * 2 * PT * 16, PT * 16, 128), smem_desc(wb + s * 2 * HIDC * 16, HIDC * 16, 128), idesc,
+                      (pass | s) != 0);
+          }
+          mma_commit(bar);
+        }
+        __syncwarp();
+      }
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+      tc_fence_after();
+      // ---- epilogue: this thread's 32 hidden units of its cell -------------------------------------------------------------------
+      float a = 0.f;
+      uint32_t bits = 0u;
+#pragma unroll
+      for (int c0 = 0; c0 < 32; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tlane + s0 + c0, v);
+        tmem_wait_ld16(v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4 c4 = reinterpret_cast<const float4*>(kc)[s0 + c0 + i];
+          float t = fmaf(__uint_as_float(v[i]), inv, c4.x);
+          if (lanes) t = fmaf(c4.w, g1, fmaf(c4.z, g0, t));
+          bits |= (t > 0.f ? 1u : 0u) << (c0 + i);
+          a = fmaf(c4.y, fmaxf(t, 0.f), a);
+        }
+      }
+      tc_fence_before();  // TMEM reads ordered before the barrier that precedes the next tile's MMAs
+      apart[half * PT + cell] = a;
+      if (half == 1) abits[cell] = bits;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+      if (half == 0) {
+        a = apart[cell] + apart[PT + cell];
+        if (A.act_mask && valid) A.act_mask[cidx] = ((unsigned long long)abits[cell] << 32) | bits;
+        float e = 0.f, es = 0.f;
+        if (live) {  // masked cells stay exactly 0 even if exp overflows (reference: exp_A * mask, then * history)
+          e = expf(a);
+          es = e * ssum;
+        }
+        red_e[cell] = e;
+        red_es[cell] = es;
+      }
+      __syncthreads();
+      for (int rr = warp; rr < ((H <= PT) ? nrows : 1); rr += PT2 / 32) {
+        const int c0 = (H <= PT) ? rr * H : 0;
+        const int cn = (H <= PT) ? H : min(PT, H - ch * PT);
+        float se = 0.f, ses = 0.f;
+        for (int c = lane; c < cn; c += 32) {
+          se += red_e[c0 + c];
+          ses += red_es[c0 + c];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          se += __shfl_xor_sync(0xffffffffu, se, o);
+          ses += __shfl_xor_sync(0xffffffffu, ses, o);
+        }
+        if (lane == 0) {
+          row_e[rr] += se;
+          row_es[rr] += ses;
+        }
+      }
+      __syncthreads();
+    }
+    if (tid < nrows) {
+      const float S = row_e[tid];
+      const float sc = row_es[tid] / powf(S, p.beta);
+      A.score[row0 + tid] = sc;
+      if (A.row_sum) A.row_sum[row0 + tid] = S;
+      if (A.parts) A.parts[row0 + tid] = sc;
+    }
+    __syncthreads();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 64u);
+}
+
+static int launch2(const Args& A, int64_t n_items, int sms, cudaStream_t stream) {
+  constexpr int D = 64, HIDC = 64;
+  const size_t smem = 2 * (size_t)(D / 8) * PT * 16 + 2 * (size_t)(D / 8) * HIDC * 16 +
+                      4096 + (4 * (size_t)HIDC + PMAXROWS * D + 2 * PT + 2 * PMAXROWS + 8 + 6 * PT + PT) * 4 + 16;
+  cudaError_t e = cudaFuncSetAttribute(pairs_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(pairs_fwd_tc2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return (int)e;
+  int per_sm = 3;
+  const int by_smem = (int)((227 * 1024) / (smem + 1024));
+  per_sm = per_sm < by_smem ? per_sm : by_smem;
+  if (per_sm < 1) return NAIS_ERR_SHAPE;
+  const int64_t cap = (int64_t)sms * per_sm;
+  const int grid = (int)(n_items < cap ? n_items : cap);
+  pairs_fwd_tc2_kernel<<<grid, PT2, smem, stream>>>(A);
+  NAIS_COUNT_LAUNCH(1);
+  return (int)cudaGetLastError();
+}
+
 template <int D>
 static int launch(const Args& A, int hid, int64_t n_items, int sms, cudaStream_t stream) {
   const size_t smem = 2 * (size_t)(D / 8) * PT * 16 + 2 * (size_t)(D / 8) * hid * 16 +
@@ -373,6 +665,7 @@ int launch_pairs_fwd_tc(const NaisParams& p, const NaisPairs& b, float* score, f
   const int64_t n_items = pairs_n_tiles(b);
   if (n_items < 1) return 0;
   const int D = p.branch[0].w_poi + p.branch[0].w_reg;
+  if (D == 64 && p.hid == 64 && rows_vec4(p.branch[0], 4)) return ptc::launch2(A, n_items, sms, stream);  // two threads per cell
   switch (D) {
     case 16: return ptc::launch<16>(A, p.hid, n_items, sms, stream);
     case 32: return ptc::launch<32>(A, p.hid, n_items, sms, stream);

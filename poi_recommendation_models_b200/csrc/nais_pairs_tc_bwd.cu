@@ -136,7 +136,6 @@ __global__ void __launch_bounds__(PT, 2) pairs_bwd_tc_kernel(const __grid_consta
   float dv_acc[2] = {0.f, 0.f};                  // dw2 partial of hidden units dv_k0, dv_k0 + 1 over this warp's cells
   const int dv_k0 = 32 * ((lane >> 4) & 1) + 16 * ((lane >> 3) & 1) + 8 * ((lane >> 2) & 1) + 4 * ((lane >> 1) & 1) + 2 * (lane & 1);
   uint32_t phase = 0, dw_started = 0;
-  const int64_t n_cells = pairs_n_cells(A.b);
 
   for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x) {
     const PairTile T = pair_tile(A.b, item);
@@ -174,10 +173,7 @@ __global__ void __launch_bounds__(PT, 2) pairs_bwd_tc_kernel(const __grid_consta
       int it32 = 0, rg32 = 0;
       float l0r = 0.f, l1r = 0.f;
       bool live = false;
-      uint32_t pos_h = 0u, pos_r = 0u;  // where this cell's dq halves go (key order); loaded early, used in epilogue 2
       if (valid) {
-        if (A.dq_h) pos_h = __ldg(A.pos_h + cidx);
-        if (A.dq_r) pos_r = __ldg(A.pos_r + cidx);
         it32 = checked_id(A.b.hist[hidx], p.item_num, A.bad);
         rg32 = br.w_reg ? checked_id(A.b.hreg[hidx], p.region_num, A.bad) : 0;
         if (lanes) pair_latlon(A.b, cidx, hidx, row0 + r, l0r, l1r);
@@ -364,10 +360,10 @@ __global__ void __launch_bounds__(PT, 2) pairs_bwd_tc_kernel(const __grid_consta
             o[i] = full * pr[d];
             dps[(size_t)d * DP_STRIDE + tid] = valid ? full * q[c0 + i] : 0.f;
           }
-          if (valid) {
+          if (valid && A.ws_dq) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4)
-              store_dq4(A, br.w_poi, br.w_reg, pos_h, pos_r, s0 + c0 + i, make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]));
+              *reinterpret_cast<float4*>(A.ws_dq + cidx * D + s0 + c0 + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
           }
         }
       }
@@ -386,10 +382,8 @@ __global__ void __launch_bounds__(PT, 2) pairs_bwd_tc_kernel(const __grid_consta
       }
       __syncthreads();  // scratch (X image) and staging (DT image) are free again
     }
-    for (int i = tid; i < nrows * D; i += PT) {
-      const int64_t row = row0 + i / D;
-      store_dp(A, br.w_poi, br.w_reg, A.dp_t ? __ldg(A.pos_t + row) : 0u, A.dq_r ? __ldg(A.pos_r + n_cells + row) : 0u, i % D, dpacc[i]);
-    }
+    if (A.ws_dp)
+      for (int i = tid; i < nrows * D; i += PT) A.ws_dp[(row0 + i / D) * D + (i % D)] = dpacc[i];
     __syncthreads();
   }
 
@@ -432,6 +426,385 @@ __global__ void __launch_bounds__(PT, 2) pairs_bwd_tc_kernel(const __grid_consta
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
+// =====================================================================================================================
+// The headline shape (D = hid = 64) with TWO threads per cell (256 threads, 2 CTAs per SM).
+//
+// ncu on the 128-thread kernel above at C3 (profiles/r2_ncu_pairs_bwd_tc_summary.csv): 140 M warp instructions, issue slots 24 %
+// busy, 8 warps per SM (255 registers x 128 threads x 2 CTAs fills the register file), stalled on the L2 gathers (long
+// scoreboard 2.8 per issue) and on TMEM / shared memory (short scoreboard 1.5): a latency-bound kernel with nothing to switch
+// to.  Splitting every cell between two threads — warps 0-3 take the first 32 embedding columns / hidden units of a cell, warps
+// 4-7 the other 32; warps w and w + 4 share a TMEM lane quarter — halves the per-thread arrays (<= 128 registers), doubles the
+// warps in flight and halves the length of each serial phase.  The two halves meet three times per tile: the similarity sum,
+// the logit a (needed in full before exp), and the per-row dp reduce.  Same operand images, same MMAs, same workspace outputs.
+// =====================================================================================================================
+constexpr int PT2 = 256;
+
+__global__ void __launch_bounds__(PT2, 2) pairs_bwd_tc2_kernel(const __grid_constant__ BwdArgs A) {
+  constexpr int D = 64;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const NaisParams& p = A.p;
+  const NaisBranch& br = p.branch[A.bi];
+  const int lanes = (p.dist_mode == NAIS_DIST_LATLON) ? 2 : 0, ldw = D + lanes;
+  constexpr int XC = D / 8 + 1;
+  constexpr int X_PLANE = XC * PT * 16, W_PLANE = (D / 8) * HID * 16, DT_PLANE = (HID / 8) * PT * 16;
+  constexpr int STG_BYTES = 8 * 32 * STG_STRIDE;  // eight warps stage 32 rows each: 36 864 B (the DT image is 32 768 B)
+  constexpr int DT_REGION = STG_BYTES > 2 * DT_PLANE ? STG_BYTES : 2 * DT_PLANE;
+  uint8_t* sX = smem;                           // [hi | lo][XC][128 cells][16 B]      (dp scratch aliases it after GEMM3)
+  uint8_t* sW = sX + 2 * X_PLANE;               // [hi | lo][D/8][64 hidden][16 B]
+  uint8_t* sDT = sW + 2 * W_PLANE;              // [hi | lo][8][128 cells][16 B]       (row staging aliases it outside GEMM2/3)
+  float* kc = reinterpret_cast<float*>(sDT + DT_REGION);  // [HID] x {b1, w2, w1[:, D], w1[:, D+1]}
+  float* ps = kc + 4 * HID;                     // [BWD_MAXROWS][D]
+  float* dpacc = ps + BWD_MAXROWS * D;          // [BWD_MAXROWS][D]
+  float* rowv = dpacc + BWD_MAXROWS * D;        // [4][BWD_MAXROWS] S, score, G, S^beta
+  float* dvs = rowv + 4 * BWD_MAXROWS;          // [4 lane quarters][HID]
+  float* red = dvs + 4 * HID;                   // [8][8]
+  float* xsum = red + 64;                       // [2][PT] similarity partial of each half
+  float* asum = xsum + 2 * PT;                  // [2][PT] logit partial of each half
+  uint64_t* bar = reinterpret_cast<uint64_t*>(asum + 2 * PT);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
+  float* dps = reinterpret_cast<float*>(sX);    // [D][DP_STRIDE]
+  static_assert(D * DP_STRIDE * 4 <= 2 * X_PLANE, "dp scratch must fit in the X image");
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp >> 2, qd = warp & 3;   // which 32 columns of the cell / which TMEM lane quarter
+  const int cell = qd * 32 + lane;             // this thread's cell = TMEM lane
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tslot, TMEM_COLS);
+  for (int i = tid; i < HID * (D / 8); i += PT2) {
+    const int c = i / HID, k = i - c * HID;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = __ldg(br.w1 + (size_t)k * ldw + c * 8 + e);
+    store_chunk_bf16(sW, sW + W_PLANE, ((size_t)c * HID + k) * 16, v);
+  }
+  for (int k = tid; k < HID; k += PT2)  // one 16-byte load per hidden unit in the epilogue: {b1, w2, w1[:, D], w1[:, D+1]}
+    reinterpret_cast<float4*>(kc)[k] = make_float4(__ldg(br.b1 + k), __ldg(br.w2 + k), lanes ? __ldg(br.w1 + (size_t)k * ldw + D) : 0.f,
+                                                   lanes ? __ldg(br.w1 + (size_t)k * ldw + D + 1) : 0.f);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  const uint32_t tlane = tmem + ((uint32_t)(qd * 32) << 16);
+  uint8_t* stg = sDT + (size_t)(warp * 32) * STG_STRIDE;
+  const int s0 = 32 * half;  // this thread's embedding columns [s0, s0 + 32) and hidden units [s0, s0 + 32)
+
+  float pd[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // dist_w[4], dist_b[2] partials (this thread's hidden units of its cells)
+  float dv_acc = 0.f;                            // dw2 partial of hidden unit s0 + lane over this warp's cells
+  uint32_t phase = 0, dw_started = 0;
+
+  for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x) {
+    const PairTile T = pair_tile(A.b, item);
+    const int64_t row0 = T.row0;
+    const int nrows = T.nrows, H = T.H;
+    const int n_chunks = (H <= PT) ? 1 : (H + PT - 1) / PT;
+    for (int i = tid; i < nrows * D; i += PT2) {
+      const int r = i / D, d = i - r * D;
+      ps[i] = (d < br.w_poi) ? __ldg(br.tgt_poi + (size_t)checked_id(A.b.tgt[row0 + r], p.item_num, A.bad) * br.w_poi + d)
+                             : __ldg(br.tgt_reg + (size_t)checked_id(A.b.treg[row0 + r], p.region_num, A.bad) * br.w_reg + (d - br.w_poi));
+      dpacc[i] = 0.f;
+    }
+    if (tid < nrows) {
+      const float S = A.row_sum[row0 + tid];
+      rowv[tid] = S;
+      rowv[BWD_MAXROWS + tid] = A.parts[row0 + tid];
+      rowv[2 * BWD_MAXROWS + tid] = A.dscore[row0 + tid];
+      rowv[3 * BWD_MAXROWS + tid] = powf(S, p.beta);
+    }
+    __syncthreads();
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      int r, h;
+      bool valid;
+      if (H <= PT) {
+        r = cell / H;
+        h = cell - r * H;
+        valid = r < nrows;
+      } else {
+        r = 0;
+        h = ch * PT + cell;
+        valid = h < H;
+      }
+      const int64_t cidx = valid ? T.cell0 + r * (int64_t)H + h : 0;  // per-cell arrays
+      const int64_t hidx = valid ? T.hist0 + r * T.hist_rs + h : 0;   // history arrays
+      int it32 = 0, rg32 = 0;
+      float l0r = 0.f, l1r = 0.f;
+      bool live = false;
+      if (valid) {
+        it32 = checked_id(A.b.hist[hidx], p.item_num, A.bad);
+        rg32 = br.w_reg ? checked_id(A.b.hreg[hidx], p.region_num, A.bad) : 0;
+        if (lanes) pair_latlon(A.b, cidx, hidx, row0 + r, l0r, l1r);
+        live = A.b.hist[hidx] != A.b.tgt[row0 + r];
+      }
+      float g0 = 0.f, g1 = 0.f;
+      if (valid && lanes) {
+        const float a0 = l0r * p.dist_scale, a1 = l1r * p.dist_scale;
+        g0 = sigmoidf_exact(fmaf(a1, __ldg(p.dist_w + 1), fmaf(a0, __ldg(p.dist_w + 0), __ldg(p.dist_b + 0))));
+        g1 = sigmoidf_exact(fmaf(a1, __ldg(p.dist_w + 3), fmaf(a0, __ldg(p.dist_w + 2), __ldg(p.dist_b + 1))));
+      }
+      const unsigned long long am = (A.act_mask && valid) ? __ldg(A.act_mask + cidx) : 0ull;
+      // ---- this half of the X image (bf16 hi/lo, unscaled) + similarity partial -------------------------------------------------------
+      const float* pr = ps + (valid ? r : 0) * D;
+      {
+        float q[32];
+        gather_segment<32>(br, it32, rg32, s0, stg, lane, q);
+        float ssum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float x[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            x[e] = valid ? q[c * 8 + e] * pr[s0 + c * 8 + e] : 0.f;
+            ssum += x[e];
+          }
+          store_chunk_bf16(sX, sX + X_PLANE, ((size_t)(s0 / 8 + c) * PT + cell) * 16, x);
+        }
+        xsum[half * PT + cell] = ssum;
+        if (half == 0) {
+          const float ext[8] = {valid ? 1.f : 0.f, g0, g1, 0.f, 0.f, 0.f, 0.f, 0.f};
+          store_chunk_bf16(sX, sX + X_PLANE, ((size_t)(D / 8) * PT + cell) * 16, ext);
+        }
+      }
+      fence_proxy_async();
+      __syncthreads();  // X image complete; every warp is done with its staging slice (aliased on the DT image)
+      // ---- GEMM1: T = X W^T -----------------------------------------------------------------------------------------------------------
+      if (warp == 0) {
+        if (elect_one()) {
+          tc_fence_after();
+          const uint32_t x0 = smem_u32(sX), w0 = smem_u32(sW);
+          const uint32_t idesc = idesc_bf16(PT, HID, 0, 0);
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t ab = x0 + (pass == 2 ? X_PLANE : 0), wb = w0 + (pass == 1 ? W_PLANE : 0);
+#pragma unroll
+            for (int s = 0; s < D / 16; ++s)
+              mma_f16(tmem + COL_T, smem_desc(ab + s * 2 * PT * 16, PT * 16, 128), smem_desc(wb + s * 2 * HID * 16, HID * 16, 128), idesc,
+                      (pass | s) != 0);
+          }
+          mma_commit(bar);
+        }
+        __syncwarp();
+      }
+      const float ssum = xsum[cell] + xsum[PT + cell];  // (the same sum, in the same order, in both threads of the cell)
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+      tc_fence_after();
+      // ---- epilogue 1: this thread's 32 hidden units of its cell -------------------------------------------------------------------------
+      float tv[32];
+      {
+        float ap = 0.f;
+#pragma unroll
+        for (int c0 = 0; c0 < 32; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(tlane + COL_T + s0 + c0, v);
+          tmem_wait_ld16(v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float4 c4 = reinterpret_cast<const float4*>(kc)[s0 + c0 + i];
+            float t = __uint_as_float(v[i]) + c4.x;
+            if (lanes) t = fmaf(c4.w, g1, fmaf(c4.z, g0, t));
+            tv[c0 + i] = t;
+            ap = fmaf(c4.y, fmaxf(t, 0.f), ap);
+          }
+        }
+        asum[half * PT + cell] = ap;
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");  // the two warps of this lane quarter exchange their halves of a
+      const float a = asum[cell] + asum[PT + cell];
+      float dav = 0.f, gwv = 0.f;
+      if (live) {
+        const float S = rowv[r], sc = rowv[BWD_MAXROWS + r], G = rowv[2 * BWD_MAXROWS + r], Sb = rowv[3 * BWD_MAXROWS + r];
+        const float e = expf(a);
+        const float w = e / Sb;
+        dav = G * (w * ssum - p.beta * (e / S) * sc);
+        gwv = G * w;
+      }
+      const bool have_mask = A.act_mask != nullptr;
+      const uint32_t am32 = (uint32_t)(am >> s0);  // this half's 32 hidden units
+      float dg0 = 0.f, dg1 = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < 32; c0 += 16) {
+        float dt[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int k = s0 + c0 + i;
+          const float4 c4 = reinterpret_cast<const float4*>(kc)[k];
+          const float t = tv[c0 + i];
+          const bool on = have_mask ? ((am32 >> (c0 + i)) & 1u) != 0u : t > 0.f;
+          tv[c0 + i] = dav * fmaxf(t, 0.f);  // -> dw2 contribution of this cell
+          dt[i] = on ? dav * c4.y : 0.f;
+          dg0 = fmaf(dt[i], c4.z, dg0);
+          dg1 = fmaf(dt[i], c4.w, dg1);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float c8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) c8[e] = dt[j * 8 + e];
+          store_chunk_bf16(sDT, sDT + DT_PLANE, ((size_t)((s0 + c0) / 8 + j) * PT + cell) * 16, c8);
+        }
+      }
+      if (lanes) {  // dist layer: z = Wd (scale * ll) + bd, g = sigmoid(z); linear in dg, so the halves' partials simply add up
+        const float dz0 = dg0 * g0 * (1.f - g0), dz1 = dg1 * g1 * (1.f - g1);
+        const float a0 = l0r * p.dist_scale, a1 = l1r * p.dist_scale;
+        pd[0] = fmaf(dz0, a0, pd[0]);
+        pd[1] = fmaf(dz0, a1, pd[1]);
+        pd[2] = fmaf(dz1, a0, pd[2]);
+        pd[3] = fmaf(dz1, a1, pd[3]);
+        pd[4] += dz0;
+        pd[5] += dz1;
+      }
+      // dw2[s0 + k] += sum over this warp's 32 cells of da * relu(t_k): shuffle halving, lane l ends with hidden unit s0 + l
+#pragma unroll
+      for (int st = 0; st < 5; ++st) {
+        const int n = 32 >> st, m = 16 >> st;
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (i < n / 2) {
+            const float send = up ? tv[i] : tv[i + n / 2];
+            const float keep = up ? tv[i + n / 2] : tv[i];
+            tv[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+          }
+        }
+      }
+      dv_acc += tv[0];
+      tc_fence_before();
+      fence_proxy_async();
+      __syncthreads();  // DT image complete
+      // ---- GEMM2: dX = dt W   and   GEMM3: dW += dt^T [X | 1 g0 g1] ---------------------------------------------------------------------
+      if (warp == 0) {
+        if (elect_one()) {
+          tc_fence_after();
+          const uint32_t x0 = smem_u32(sX), w0 = smem_u32(sW), t0 = smem_u32(sDT);
+          const uint32_t id2 = idesc_bf16(PT, D, 0, 1), id3 = idesc_bf16(HID, D + 8, 1, 1);
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t ab = t0 + (pass == 2 ? DT_PLANE : 0), wb = w0 + (pass == 1 ? W_PLANE : 0);
+#pragma unroll
+            for (int s = 0; s < HID / 16; ++s)
+              mma_f16(tmem + COL_DX, smem_desc(ab + s * 2 * PT * 16, PT * 16, 128), smem_desc(wb + s * 256, 128, HID * 16), id2,
+                      (pass | s) != 0);
+          }
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t ab = t0 + (pass == 2 ? DT_PLANE : 0), xb = x0 + (pass == 1 ? X_PLANE : 0);
+#pragma unroll
+            for (int s = 0; s < PT / 16; ++s)
+              mma_f16(tmem + COL_DW, smem_desc(ab + s * 256, 128, PT * 16), smem_desc(xb + s * 256, 128, PT * 16), id3,
+                      (dw_started | pass | s) != 0);
+          }
+          mma_commit(bar);
+        }
+        __syncwarp();
+      }
+      dw_started = 1u;
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+      tc_fence_after();
+      // ---- epilogue 2: this half of the dq row to the workspace, dp contributions to the scratch (aliased on the X image) --------------
+      {
+        float q[32];
+        gather_segment<32>(br, it32, rg32, s0, stg, lane, q);
+#pragma unroll
+        for (int c0 = 0; c0 < 32; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(tlane + COL_DX + s0 + c0, v);
+          tmem_wait_ld16(v);
+          float o[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int d = s0 + c0 + i;
+            const float full = __uint_as_float(v[i]) + gwv;
+            o[i] = full * pr[d];
+            dps[(size_t)d * DP_STRIDE + cell] = valid ? full * q[c0 + i] : 0.f;
+          }
+          if (valid && A.ws_dq) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              *reinterpret_cast<float4*>(A.ws_dq + cidx * D + s0 + c0 + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncthreads();
+      {
+        const int nr = (H <= PT) ? nrows : 1;
+        for (int i = tid; i < nr * D; i += PT2) {
+          const int rr = i / D, d = i - rr * D;
+          const int c0 = (H <= PT) ? rr * H : 0;
+          const int cn = (H <= PT) ? H : min(PT, H - ch * PT);
+          float sacc = 0.f;
+          for (int c = 0; c < cn; ++c) sacc += dps[(size_t)d * DP_STRIDE + c0 + c];
+          dpacc[rr * D + d] += sacc;
+        }
+      }
+      __syncthreads();  // scratch (X image) and staging (DT image) are free again
+    }
+    if (A.ws_dp)
+      for (int i = tid; i < nrows * D; i += PT2) A.ws_dp[(row0 + i / D) * D + (i % D)] = dpacc[i];
+    __syncthreads();
+  }
+
+  // ---- this CTA's parameter partial: w1 [hid][ldw] | b1 | w2 | dist_w[4] dist_b[2] km pad --------------------------------------------
+  float* part = A.ws_part + (size_t)blockIdx.x * A.part_stride;
+  tc_fence_after();
+  if (half == 0) {
+    const int m = 16 * qd + (lane & 15);  // the M = 64 accumulator keeps row m in TMEM lane 32*(m/16) + m%16
+    for (int c0 = 0; c0 < D + 16; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tlane + COL_DW + c0, v);
+      tmem_wait_ld16(v);
+      if (lane < 16) {
+        if (c0 < D) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) part[(size_t)m * ldw + c0 + i] = __uint_as_float(v[i]);
+        } else {  // ext chunk: [sum dt * 1, sum dt * g0, sum dt * g1]
+          part[HID * ldw + m] = __uint_as_float(v[0]);
+          if (lanes) {
+            part[(size_t)m * ldw + D] = __uint_as_float(v[1]);
+            part[(size_t)m * ldw + D + 1] = __uint_as_float(v[2]);
+          }
+        }
+      }
+    }
+  }
+  dvs[qd * HID + s0 + lane] = dv_acc;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    float v = pd[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[q * 8 + warp] = v;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < HID) part[HID * ldw + HID + tid] = dvs[tid] + dvs[HID + tid] + dvs[2 * HID + tid] + dvs[3 * HID + tid];
+  if (tid < 7) {
+    float v = 0.f;
+    if (tid < 6)
+      for (int w = 0; w < 8; ++w) v += red[tid * 8 + w];
+    part[HID * ldw + 2 * HID + tid] = v;
+  }
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+static int launch2(const BwdArgs& A, int grid, cudaStream_t stream) {
+  constexpr int D = 64;
+  constexpr size_t dt_region = (8 * 32 * STG_STRIDE > 2 * (HID / 8) * PT * 16) ? 8 * 32 * STG_STRIDE : 2 * (HID / 8) * PT * 16;
+  constexpr size_t smem = 2 * (size_t)(D / 8 + 1) * PT * 16 + 2 * (size_t)(D / 8) * HID * 16 + dt_region +
+                          (4 * HID + 2 * BWD_MAXROWS * D + 4 * BWD_MAXROWS + 4 * HID + 64 + 4 * PT) * 4 + 16;
+  cudaError_t e = cudaFuncSetAttribute(pairs_bwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(pairs_bwd_tc2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return (int)e;
+  pairs_bwd_tc2_kernel<<<grid, PT2, smem, stream>>>(A);
+  NAIS_COUNT_LAUNCH(1);
+  return (int)cudaGetLastError();
+}
+
 template <int D>
 static int launch(const BwdArgs& A, int grid, cudaStream_t stream) {
   constexpr size_t smem = 2 * (size_t)(D / 8 + 1) * PT * 16 + 2 * (size_t)(D / 8) * HID * 16 + 2 * (size_t)(HID / 8) * PT * 16 +
@@ -463,7 +836,7 @@ bool pairs_tc_bwd_supported(const NaisParams& p, const NaisPairs& b) {
 
 // grid <= 2 CTAs per SM (256 TMEM columns each); every CTA owns at least one tile (the caller passes min(n_items, grid))
 int launch_pairs_bwd_tc(const BwdArgs& A, int D, int grid, cudaStream_t stream) {
-  return D == 32 ? ptcb::launch<32>(A, grid, stream) : ptcb::launch<64>(A, grid, stream);
+  return D == 32 ? ptcb::launch<32>(A, grid, stream) : ptcb::launch2(A, grid, stream);  // D = 64: two threads per cell
 }
 
 }  // namespace nais

@@ -604,7 +604,7 @@ class FullrankPlan:
             return None
         host = self.buf[64:128].cpu()
         return {"rho": float(host[44:48].view(torch.float32).item()), "use_mix": int(host[48:52].view(torch.int32).item()),
-                "min_hist_for_mix": 16}  # kMixRhoMax = 256 / kMixMinHist = 16 in csrc/nais_tc.cu
+                "min_hist_for_mix": 16, "rho_max_for_mix": 128.0}  # kMixRhoMax / kMixMinHist in csrc/nais_tc.cu
 
 
 def fullrank_prepare(variant: str, beta: float, P: Dict[str, torch.Tensor], cat: "DeviceCatalog", poi_begin: int = 0,

@@ -223,7 +223,7 @@ def test_predict_topk_slices_huge_batches(monkeypatch):
 
 def test_tc_auto_gate_per_user_and_weight_scale():
     """precision="tc_auto": a user takes the fp16 + e5m2-correction kernels (MIX) when the device-side bound
-    rho = max|p| * max|B| * sqrt(hid * D) is <= 256 AND the history has >= 16 items (MIX's per-term error averages out over
+    rho = max|p| * max|B| * sqrt(hid * D) is <= 128 AND the history has >= 16 items (MIX's per-term error averages out over
     the history), else the three-pass fp16 split.  Each user's row is bit-identical to calling that mode directly, and
     within tolerance of the float64 oracle; beyond the bound everything falls back to SPLIT."""
     N = 600
@@ -257,7 +257,7 @@ def test_tc_auto_gate_per_user_and_weight_scale():
         return choice, err
 
     choice, err = run(sd)
-    assert choice["use_mix"] == 1 and choice["rho"] < 256 and choice["min_hist_for_mix"] == 16, choice
+    assert choice["use_mix"] == 1 and choice["rho"] < 128 and choice["min_hist_for_mix"] == 16, choice
     assert err < util.TOL, err
     big = {k: v.clone() for k, v in sd.items()}
     for k in big:
