@@ -174,13 +174,12 @@ def allreduce_gradients(model, world: int) -> None:
     if not grads:
         return
     flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    flat.div_(world)
-    o = 0
-    for g in grads:
-        n = g.numel()
-        g.copy_(flat[o:o + n].view_as(g))
-        o += n
+    if flat.is_cuda:
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)  # NCCL averages in the collective
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)  # gloo (CPU tests) has no AVG
+        flat.div_(world)
+    torch._foreach_copy_(grads, [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)])
 
 
 class SparseRowExchange:
