@@ -115,12 +115,22 @@ def log_scores(cat: ops.DeviceCatalog, users: ops.DeviceUsers, a: float, b: floa
 
 @torch.no_grad()
 def rerank_topk(model, users, k: int, a: float, b: float, alpha: float, precision: str = "auto",
-                exclude_history: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+                exclude_history: bool = True, max_slice_bytes: int = 1 << 30) -> Tuple[torch.Tensor, torch.Tensor]:
     """Top-k of (1 - alpha) * forward(...) + alpha * normalize(G) over the whole catalogue minus the history
     (run.py:523-546 with the candidate set of validation.py:87).  G is normalised by its maximum over the user's
-    candidates, in log space: normalize(G)[j] = exp(log G[j] - max_j log G).  Returns (mixed score [U,k], ids [U,k])."""
+    candidates, in log space: normalize(G)[j] = exp(log G[j] - max_j log G).  Returns (mixed score [U,k], ids [U,k]).
+
+    The mix needs every candidate's score (the normaliser is a maximum over the catalogue), so this path does materialise
+    [users, N] score / log-G tiles — but only for a SLICE of users at a time: at most `max_slice_bytes` of temporaries
+    (3 float32 matrices), whatever the batch and the catalogue are (30k users x 1M POIs would be 360 GB at once)."""
     if not isinstance(users, ops.DeviceUsers):
         users = model.make_users(*users)
+    N = model._catalog.n_rows
+    per = max(1, int(max_slice_bytes // (3 * 4 * max(N, 1))))
+    if users.n_users > per and users.host_offsets is not None:
+        parts = [rerank_topk(model, users.slice(u0, min(users.n_users, u0 + per)), k, a, b, alpha, precision, exclude_history,
+                             max_slice_bytes) for u0 in range(0, users.n_users, per)]
+        return torch.cat([v for v, _ in parts]), torch.cat([i for _, i in parts])
     s = ops.fullrank_scores(model.variant, float(model.beta), model._params(), model._catalog, users, precision=precision)
     logg = log_scores(model._catalog, users, a, b)
     if exclude_history:
