@@ -48,10 +48,14 @@ def test_c1_epoch_then_eval_matches_the_oracle(pairs_precision):
     for k in ref_sd:
         if k == "embed_distance.weight":
             continue  # allocated, never read (model.py:204)
-        # Adagrad from a zero accumulator turns a gradient's rounding into +-lr steps for near-zero elements: compare at the
-        # scale of one step, lr (the example's full-size run measures 7e-6 on the tensors' bulk)
-        assert float((got[k] - ref_sd[k]).abs().max()) <= 0.5 * lr, k
-        assert float((got[k] - ref_sd[k]).abs().mean()) <= 2e-5, k
+        # Adagrad from a zero accumulator turns the SIGN of a gradient element into a +-lr step whatever its size, so an element
+        # whose gradient is below the kernels' rounding (3e-7 of the tensor's maximum for the FP32 kernels, ~3e-6 for the tcgen05
+        # ones; single-step gradient parity is pinned at 2e-4 in test_gpu_backward / test_gpu_pairs_tc) may land a whole step
+        # away: the bulk must agree tightly, outliers must be rare and never exceed a couple of steps
+        diff = (got[k] - ref_sd[k]).abs()
+        assert float(diff.mean()) <= 2e-5, (k, float(diff.mean()))
+        assert float((diff > 1e-3).double().mean()) <= 2e-3, (k, float((diff > 1e-3).double().mean()))
+        assert float(diff.max()) <= 4 * lr, (k, float(diff.max()))
     # ---- full-rank evaluation of every user with the GPU-trained weights (validation.py:62-131) -----------------------------
     k_list = [5, 10, 15, 20, 25, 30]
     ns = argparse.Namespace(topk=50, powerlaw_weight=0.2)
