@@ -56,11 +56,11 @@ def main():
                     p.normal_(0, 0.3)
         m = m.to(dev).eval()
         m.set_catalog(region=region, coords=coords)
-        prec = args.precision if D <= 128 else "fp32"
+        prec = args.precision  # every D, hid <= 256 has a tensor tiling (D or hid > 256: ops.resolve_precision falls back to fp32)
         for H in mine:
             F = bench.flops_per_cell(D, hid)
             # size the batch for ~0.1 s per call
-            rate = (3.5e14 if D >= 64 else 1.5e14) if prec != "fp32" else 3.5e13
+            rate = ((3.5e14 if D >= 64 else 1.5e14) if D <= 128 else 2.0e14) if prec != "fp32" else 3.5e13
             users = int(max(148, min(8192, 0.1 * rate / (F * H * N))))
             hist = bench.synth_histories(users, N, H, seed=H)
             indptr = np.arange(0, (users + 1) * H, H, dtype=np.int64)

@@ -56,6 +56,8 @@ struct Geo {
   int D, hid, lanes, split;
   int mix;       // NAIS_PREC_TC_MIX: lo section of A tiles / B chunks = e5m2(hi) | e5m2(lo) byte planes, two ext k-chunks
   int kx;        // D / 8 x k-chunks
+  int hsplit;    // chunks per history item: 1, or 2 for hid = 256 — a chunk then holds ONE HALF (128) of the item's hidden units
+                 // (`hid` below is the per-chunk count); the two halves of a cell are consecutive chunks = the two epilogue groups
   int hch;       // history items per chunk / MMA step: 2 (hid <= 64) or 1 (hid 96, 128: a cell's hidden columns are split
                  // between the two warps of a lane quarter and their partial sums exchanged through shared memory)
   int aux0;      // first S/L row = hch * hid
@@ -77,7 +79,8 @@ __host__ inline bool make_geo(const NaisParams& p, int precision, Geo& g) {
   if (p.n_branch != 1) return false;
   const NaisBranch& br = p.branch[0];
   g.D = br.w_poi + br.w_reg;
-  g.hid = p.hid;
+  g.hsplit = p.hid == 256 ? 2 : 1;
+  g.hid = p.hid / g.hsplit;
   g.lanes = p.dist_mode == NAIS_DIST_LATLON ? 2 : 0;
   g.split = precision == NAIS_PREC_TC_SPLIT;
   g.mix = precision == NAIS_PREC_TC_MIX;
@@ -87,7 +90,7 @@ __host__ inline bool make_geo(const NaisParams& p, int precision, Geo& g) {
     g.split = !g.mix;
   }
   if (g.mix && g.D % 32) return false;  // an e5m2 MMA covers K = 32
-  if (g.D % 16 || g.D < 16 || g.D > 128 || (g.D > 64 && g.D % 32) || g.hid % 16 || g.hid < 16 || g.hid > 128) return false;
+  if (g.D % 16 || g.D < 16 || g.D > 256 || (g.D > 64 && g.D % 32) || g.hid % 16 || g.hid < 16 || g.hid > 128) return false;
   g.hch = g.hid <= 64 ? 2 : 1;
   if (g.hch == 1 && g.hid % 32) return false;
   g.kx = g.D / 8;
@@ -118,8 +121,8 @@ __host__ inline bool make_geo(const NaisParams& p, int precision, Geo& g) {
   }
   // smem: A tiles | B stages | A_ext (hi,lo) x NBUF | zero  (item-end `comb` partials alias A_ext+zero) | keys | hist meta |
   //       partner exchange | barriers
-  g.tpc = g.kp == 1 ? TPC : 2;  // compile-time constant per kernel instantiation (kSinglePart)
-  g.smem_bytes = g.tpc * g.a_tile + g.stages * g.stage_bytes + NBUF * 2 * TM * 16 + 4096 + SORTN * 8 + 3 * HMETA * 4 + 4 * TM * 4 + 256 + 128 +
+  g.tpc = g.kp == 1 ? TPC : (g.D > 128 ? 1 : 2);  // compile-time constant per kernel instantiation (kSinglePart / kFix == 4)
+  g.smem_bytes = g.tpc * g.a_tile + g.stages * g.stage_bytes + NBUF * 2 * TM * 16 + 4096 + SORTN * 8 + 3 * HMETA * 4 + 6 * TM * 4 + 256 + 128 +
                  (g.kp == 1 ? 9 * TPC * TM * 4 : 0);  // D <= 64 has room for a private `comb`; D > 64 aliases it on A_ext + zero
   return g.smem_bytes <= 227 * 1024;
 }
@@ -145,9 +148,10 @@ constexpr int kMixMinHist = 16;
 __device__ __forceinline__ bool user_in_pass(int gate, int use_mix, int H) {
   return gate < 0 || ((use_mix && H >= kMixMinHist) ? 1 : 0) == gate;
 }
-// workspace header: [0,64) maxes (uint bits) | [64,128) Scales | perm[128] int | ck[128] float | u[128] float
+// workspace header: [0,64) maxes (uint bits) | [64,128) Scales | perm[256] int | ck[256] float | u[256] float
 constexpr int HDR_BYTES = 4096;
-constexpr int HDR_PERM = 128, HDR_CK = HDR_PERM + 128 * 4, HDR_U = HDR_CK + 128 * 4;
+constexpr int HDR_PERM = 128, HDR_CK = HDR_PERM + 256 * 4, HDR_U = HDR_CK + 256 * 4;
+static_assert(HDR_U + 256 * 4 <= HDR_BYTES, "header");
 
 __global__ void absmax_kernel(const float* __restrict__ x, size_t n, unsigned* out) {
   float m = 0.f;
@@ -290,8 +294,8 @@ __global__ void pack_candidates_kernel(NaisParams p, NaisCatalog cat, int64_t po
 }
 
 // first chunk slot of user u: users get ceil(H/hch) consecutive slots (hch = 2: (offsets[u] + u) / 2 never overlaps)
-__device__ __forceinline__ int64_t chunk_base(const int64_t* offsets, int u, int hch) {
-  return hch == 2 ? (offsets[u] + u) >> 1 : offsets[u];
+__device__ __forceinline__ int64_t chunk_base(const int64_t* offsets, int u, int hch, int hsplit = 1) {
+  return hch == 2 ? (offsets[u] + u) >> 1 : offsets[u] * hsplit;
 }
 
 // User operand: grid (user, chunk slot) — users ride grid.x, which has no 65 535 limit.  One thread = (row n, k-chunk c) -> 8 fp16 (hi) + 8 fp16 (lo).
@@ -314,14 +318,15 @@ __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g_mix, Geo 
     if (threadIdx.x == 0 && blockIdx.y == 0) pass_flags[pass] = 1;  // (benign race: every writer stores 1)
   }
   const Geo& g = pass ? g_mix : g_split;
-  const int hch = g.hch, aux0 = g.aux0;
-  const int nchunks = (H + hch - 1) / hch;
+  const int hch = g.hch, aux0 = g.aux0, hsplit = g.hsplit;
+  const int nchunks = (H + hch - 1) / hch * hsplit;
   const int D = g.D, hid = g.hid, ldw = D + g.lanes;
-  __shared__ float q[2][128];
+  __shared__ float q[2][256];
   for (int chunk = blockIdx.y; chunk < nchunks; chunk += gridDim.y) {
+    const int hc = chunk / hsplit, half = chunk - hc * hsplit;  // history chunk, and which half of its hidden units this image holds
     __syncthreads();
     for (int i = threadIdx.x; i < hch * D; i += blockDim.x) {
-      const int hs = i / D, d = i - hs * D, h = hch * chunk + hs;
+      const int hs = i / D, d = i - hs * D, h = hch * hc + hs;
       float v = 0.f;
       if (h < H) {
         const int64_t e = hb + h;
@@ -331,7 +336,7 @@ __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g_mix, Geo 
       q[hs][d] = v;
     }
     __syncthreads();
-    const int64_t slot = chunk_base(users.offsets, u, hch) - chunk_base(users.offsets, 0, hch) + chunk;
+    const int64_t slot = chunk_base(users.offsets, u, hch, hsplit) - chunk_base(users.offsets, 0, hch, hsplit) + chunk;
     if (slot >= max_chunks) continue;  // workspace sized with a wrong nnz: never write out of bounds (the main kernel clamps too)
     unsigned char* cb = Bimg + (size_t)slot * g.b_chunk;
     for (int i = threadIdx.x; i < g.nrow * (g.kx + 1); i += blockDim.x) {
@@ -343,12 +348,12 @@ __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g_mix, Geo 
       if (n < aux0) {
         hs = n / hid;
         kind = 0;
-        k = perm[n - hs * hid];
-      } else if (n < aux0 + 2 * hch) {
+        k = perm[half * hid + n - hs * hid];
+      } else if (n < aux0 + 2 * hch && half == 0) {  // S / L rows ride with the first half only (L already sums over ALL hidden units)
         hs = (n - aux0) >> 1;
         kind = 1 + ((n - aux0) & 1);
       }
-      if (kind >= 0 && hch * chunk + hs < H) {
+      if (kind >= 0 && hch * hc + hs < H) {
         if (c < g.kx) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -387,13 +392,13 @@ __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g_mix, Geo 
         //   chunk e0: [2hs+l] = hi(w_l)   [4] = hi(w_b)  [5] = lo(w_b)        A_ext: [2hs+l] = hi(g_l)  [4] = [5] = sAe
         //   chunk e1: [2hs+l] = hi(w_l)   [4+2hs+l] = lo(w_l)                 A_ext: [2hs+l] = lo(g_l)  [4+2hs+l] = hi(g_l)
         float w0 = 0.f, w1 = 0.f, wb = 0.f;
-        if (kind == 0 && hch * chunk + hs < H) {
+        if (kind == 0 && hch * hc + hs < H) {
           if (g.lanes) {
             w0 = ck[k] * __ldg(br.w1 + (size_t)k * ldw + D) * sc->sBe;
             w1 = ck[k] * __ldg(br.w1 + (size_t)k * ldw + D + 1) * sc->sBe;
           }
           wb = ck[k] * __ldg(br.b1 + k) * sc->sBe;
-        } else if (kind == 2 && hch * chunk + hs < H) {
+        } else if (kind == 2 && hch * hc + hs < H) {
           w0 = sc->omega0 * sc->sBe;
           w1 = sc->omega1 * sc->sBe;
           wb = sc->omegab * sc->sBe;
@@ -433,11 +438,12 @@ __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g_mix, Geo 
 }
 
 // chunks of user u that exist in the operand image (== ceil(H / hch) when the workspace was sized correctly)
-__device__ __forceinline__ int user_chunks(const int64_t* offsets, int u, int hch, int64_t cb0, int64_t max_chunks) {
+__device__ __forceinline__ int user_chunks(const int64_t* offsets, int u, int hch, int64_t cb0, int64_t max_chunks, int hsplit = 1) {
   const int H = (int)(offsets[u + 1] - offsets[u]);
-  const int64_t room = max_chunks - (chunk_base(offsets, u, hch) - cb0);
-  const int n = (H + hch - 1) / hch;
-  return (int)(room < n ? (room < 0 ? 0 : room) : n);
+  const int64_t room = max_chunks - (chunk_base(offsets, u, hch, hsplit) - cb0);
+  const int n = (H + hch - 1) / hch * hsplit;
+  const int m = (int)(room < n ? (room < 0 ? 0 : room) : n);
+  return m - m % hsplit;  // both halves of an item or neither (the two epilogue groups meet once per item)
 }
 
 struct MainArgs {
@@ -510,8 +516,8 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
   int* hm_id = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(keys + SORTN) + (kSinglePart ? 9 * TPC * TM * 4 : 0));  // [HMETA]
   float* hm_la = reinterpret_cast<float*>(hm_id + HMETA);
   float* hm_lo = hm_la + HMETA;
-  float* xch = hm_lo + HMETA;                                                   // [2][2][TM] partner-warp exchange (hch = 1)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 4 * TM);
+  float* xch = hm_lo + HMETA;                                                   // [2][3][TM] partner-warp exchange (hch = 1; 3 senders when hsplit = 2)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 6 * TM);
   uint64_t* a_full = bars + 0;
   uint64_t* a_empty = bars + 1;
   uint64_t* b_full = bars + 2;                 // [MAX_STAGES]
@@ -559,8 +565,9 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem = *tslot;
 
-  constexpr int tpc = kSinglePart ? TPC : 2;  // == g.tpc
-  const int64_t cb0 = chunk_base(A.users.offsets, 0, kHch);
+  constexpr int tpc = kSinglePart ? TPC : (kFix == 4 ? 1 : 2);  // == g.tpc (kFix == 4: D > 128, one 128 KB candidate tile resident)
+  const int hsplit = kHch == 1 ? g.hsplit : 1;
+  const int64_t cb0 = chunk_base(A.users.offsets, 0, kHch, hsplit);
 
   if (warp == EPI_WARPS + 1) {
     // =================================================== bulk-copy producer ========================================
@@ -571,8 +578,8 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
         const int u = (int)(item / A.groups), grp = (int)(item % A.groups);
         if (!user_in_pass(A.gate, sc.use_mix, (int)(A.users.offsets[u + 1] - A.users.offsets[u]))) continue;
         const uint32_t it = it_n++;
-        const int64_t cbu = __shfl_sync(0xffffffffu, chunk_base(A.users.offsets, u, kHch) - cb0, 0);
-        const int nchunks = __shfl_sync(0xffffffffu, user_chunks(A.users.offsets, u, kHch, cb0, A.max_chunks), 0);
+        const int64_t cbu = __shfl_sync(0xffffffffu, chunk_base(A.users.offsets, u, kHch, hsplit) - cb0, 0);
+        const int nchunks = __shfl_sync(0xffffffffu, user_chunks(A.users.offsets, u, kHch, cb0, A.max_chunks, hsplit), 0);
         mbar_wait(a_empty, (it & 1) ^ 1);
         if (elect_one()) {
           mbar_expect_tx(a_full, (uint32_t)(tpc * g.a_tile));
@@ -636,7 +643,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
         const int u = (int)(item / A.groups);
         if (!user_in_pass(A.gate, sc.use_mix, (int)(A.users.offsets[u + 1] - A.users.offsets[u]))) continue;
         const uint32_t it = it_n++;
-        const int nchunks = __shfl_sync(0xffffffffu, user_chunks(A.users.offsets, u, kHch, cb0, A.max_chunks), 0);
+        const int nchunks = __shfl_sync(0xffffffffu, user_chunks(A.users.offsets, u, kHch, cb0, A.max_chunks, hsplit), 0);
         mbar_wait(a_full, it & 1);
         for (int c = 0; c < nchunks; ++c, ++cc) {
           mbar_wait(&b_full[st], stph);
@@ -726,7 +733,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
         const int u = (int)(item / A.groups);
         if (!user_in_pass(A.gate, sc.use_mix, (int)(A.users.offsets[u + 1] - A.users.offsets[u]))) continue;
         const uint32_t it = it_n++;
-        const int nchunks = __shfl_sync(0xffffffffu, user_chunks(A.users.offsets, u, kHch, cb0, A.max_chunks), 0);
+        const int nchunks = __shfl_sync(0xffffffffu, user_chunks(A.users.offsets, u, kHch, cb0, A.max_chunks, hsplit), 0);
         mbar_wait(a_full, it & 1);
         for (int c = 0; c < nchunks; ++c, n += (uint32_t)tpc) {
           const int kp_m = kSinglePart ? 1 : (kD128 ? 4 : g.kp);
@@ -814,7 +821,8 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
     constexpr int hch = kHch;
     const int ncols = hch == 2 ? hid : hid / 2;   // accumulator columns this thread sums per step
     const int col0 = hs * ncols;                  // hch = 2: slot hs's hidden units; hch = 1: this warp's half of them
-    const int kidx0 = hch == 2 ? 0 : col0;        // hidden-unit index of column col0 (sign classification)
+    // hidden-unit index (in permuted order, positive v first) of column col0: with hsplit = 2 this group's chunks hold half `egrp`
+    const int kidx0 = hch == 2 ? 0 : col0 + (hsplit == 2 ? egrp * hid : 0);
     auto div_tpc = [&](int x) { return x / tpc; };  // tpc is a compile-time constant: mul-shift, not a runtime division
     uint32_t n0 = 0;  // global index of the current item's first step (same sequence as the MMA warp)
     uint32_t phbits = 0;  // phase parity of this group's acc_full barrier, one bit per buffer
@@ -830,7 +838,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       const int64_t hb = A.users.offsets[u];
       const int H = (int)(A.users.offsets[u + 1] - hb);
       if (!user_in_pass(A.gate, sc.use_mix, H)) continue;
-      const int nchunks = user_chunks(A.users.offsets, u, hch, cb0, A.max_chunks);
+      const int nchunks = user_chunks(A.users.offsets, u, hch, cb0, A.max_chunks, hsplit);
       const int nsteps = nchunks * tpc;
       // stage this user's history ids / coords (previous item's readers are past their last epi_bar)
       epi_bar();
@@ -986,7 +994,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
         auto produce = [&](int m) {
           const int pc = div_tpc(m), pt = m - pc * tpc;
           const uint32_t pbuf = (n0 + (uint32_t)m) % NBUF;
-          const int h = hch == 2 ? 2 * pc + hs : pc;
+          const int h = hch == 2 ? 2 * pc + hs : pc / hsplit;
           float g0 = 0.f, g1 = 0.f;
           if (g.lanes && h < H && (hch == 2 || hs == 0)) {
             float hla, hlo;
@@ -1030,7 +1038,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
           const int ls = c * tpc + t;
           const uint32_t n = n0 + (uint32_t)ls;
           const uint32_t buf = n % NBUF;
-          const int h = hch == 2 ? 2 * c + hs : c;
+          const int h = hch == 2 ? 2 * c + hs : c / hsplit;
           int hist_id = -1;
           if (h < H) hist_id = h < HMETA ? hm_id[h] : __ldg(A.users.items + hb + h);
           mbar_wait(&acc_full[egrp * NBUF + buf], (phbits >> buf) & 1u);
@@ -1087,16 +1095,25 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
           if (ncols > 32) absum(32, ncols >= 64 ? 32 : 16);
           float asum = accp - accn;
-          if (hch == 1) {
+          if (hch == 1 && hsplit == 1) {
             // the other half of this cell's hidden units was summed by the partner warp (same lane quarter)
             float* slot = xch + ((ls & 1) * 2 + egrp) * TM + r;
             if (hs == 1) *slot = asum;
             asm volatile("bar.sync %0, 64;" ::"r"(2 + egrp * 4 + qd) : "memory");
             if (hs == 0) asum += *slot;
+          } else if (hch == 1) {
+            // hid = 256: this cell's 256 hidden units sit in TWO consecutive chunks (= the two groups, same t) x two warps each:
+            // three senders, one 128-thread barrier per lane quarter, group 0 / hs 0 adds them in a fixed order
+            const int par = ((c >> 1) * tpc + t) & 1;
+            float* slots = xch + par * 3 * TM + r;
+            const int sender = egrp * 2 + hs - 1;  // (0,1) -> 0, (1,0) -> 1, (1,1) -> 2
+            if (sender >= 0) slots[sender * TM] = asum;
+            asm volatile("bar.sync %0, 128;" ::"r"(10 + qd) : "memory");
+            if (sender < 0) asum = ((asum + slots[0]) + slots[TM]) + slots[2 * TM];
           }
           const float S = __uint_as_float(aux[0]) * sc.inv_s;
           const float a = (__uint_as_float(aux[1]) + asum) * sc.inv_sigma;
-          if (h < H && (hch == 2 || hs == 0)) {
+          if (h < H && (hch == 2 || hs == 0) && (hsplit == 1 || egrp == 0)) {
             const int64_t j = t == 0 ? jid[0] : (t == 1 ? jid[1] : jid[2]);
             if ((int64_t)hist_id != j) {
               const float e = __expf(a);
@@ -1228,7 +1245,9 @@ static bool plan_layout(const NaisParams& p, int64_t poi_begin, int64_t poi_end,
     if (!tc::make_geo(p, NAIS_PREC_TC_SPLIT, L.gs)) return false;
     // make_geo(AUTO) gives the MIX geometry where an e5m2 K-step exists; the two passes then share every size
     L.two_pass = L.g.mix != 0;
-    if (L.two_pass && (L.gs.a_tile != L.g.a_tile || L.gs.b_chunk != L.g.b_chunk || L.gs.tpc != L.g.tpc || L.gs.hch != L.g.hch)) return false;
+    if (L.two_pass && (L.gs.a_tile != L.g.a_tile || L.gs.b_chunk != L.g.b_chunk || L.gs.tpc != L.g.tpc || L.gs.hch != L.g.hch ||
+                       L.gs.hsplit != L.g.hsplit))
+      return false;
   } else {
     L.gs = L.g;
   }
@@ -1268,7 +1287,7 @@ size_t fullrank_tc_call_workspace_bytes(const NaisParams& p, int n_users, int64_
                                         int precision) {
   PlanLayout L;
   if (!plan_layout(p, poi_begin, poi_end, precision, L)) return 0;
-  const int64_t max_chunks = (L.g.hch == 2 ? (nnz + n_users) / 2 : nnz) + 2;
+  const int64_t max_chunks = (L.g.hch == 2 ? (nnz + n_users) / 2 : nnz * L.g.hsplit) + 2;
   return 256 + al256((size_t)max_chunks * L.g.b_chunk) + call_keys_bytes(n_users, L.groups, k) + call_scratch_bytes(n_users, L.groups, k);
 }
 
@@ -1341,6 +1360,7 @@ static MainKernel pick_kernel(const tc::Geo& gg, bool generic) {
     if (fix == 1) return s64 ? tc::fullrank_tc_kernel<true, 2, 1, 64> : tc::fullrank_tc_kernel<true, 2, 1, 32>;
     return tc::fullrank_tc_kernel<true, 2, 0>;
   }
+  if (gg.tpc == 1) return gg.hch == 2 ? tc::fullrank_tc_kernel<false, 2, 4> : tc::fullrank_tc_kernel<false, 1, 4>;  // D > 128
   if (gg.hch == 2) return tc::fullrank_tc_kernel<false, 2, 0>;
   if (gg.D == 128 && gg.hid == 128 && gg.kp == 4 && gg.nrow == 144 && gg.stages == 3 && (gg.mix || gg.split) && !generic)
     return tc::fullrank_tc_kernel<false, 1, 3>;

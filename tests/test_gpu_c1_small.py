@@ -27,35 +27,60 @@ def test_c1_epoch_then_eval_matches_the_oracle(pairs_precision):
     opt = torch.optim.Adagrad(model.parameters(), lr=lr, weight_decay=0.0)
     order = list(range(U))
     random.shuffle(order)
-    state = random.getstate()
-    # ---- one epoch on the GPU, the reference's loop body (run.py:235-254) ------------------------------------------------
-    for u in order:
+    # ---- one epoch: every step taken TWICE -------------------------------------------------------------------------------
+    # (a) free-running on the GPU — the reference's loop body (run.py:235-254) on the model's own trajectory;
+    # (b) teacher-forced — from the float64 oracle's weights and Adagrad accumulators of that step, one GPU step against the
+    #     oracle's next weights.  A trajectory through ReLU kinks under Adagrad (first updates are +-lr whatever |g| is) amplifies
+    #     rounding differences step over step (measured here: the tcgen05 kernels' 2e-5-of-max gradient rounding grows to 6e-4 of
+    #     mean parameter difference over 48 steps after a kink event around step 7, the FP32 kernels' 1e-6 to 1e-8), so (b) is the
+    #     step-accurate pin and (a) is bounded at the scale of one update.
+    names = [n for n, _ in model.named_parameters()]
+    forced = M.NAIS_region_distance_Embedding(N, D, hid, beta, data.region_num, 1).cuda().train()
+    forced.pairs_precision = pairs_precision
+    fopt = torch.optim.Adagrad(forced.parameters(), lr=lr, weight_decay=0.0)
+    ref_sd, ref_sum = {k: v.double() for k, v in sd0.items()}, None
+    worst_forced = 0.0
+    for step, u in enumerate(order):
+        st = random.getstate()
         hist, tgt, label, hreg, treg = PB.get_NAIS_batch_region(csr, N, u, num_ng, data.region)
         ll = PB.lat_lon_pairs(data.coords, tgt.cpu().numpy(), hist[0].cpu().numpy())
         opt.zero_grad()
         loss = model.loss_func(model(hist, tgt, hreg, treg, ll), label)
         loss.backward()
         opt.step()
-    # ---- the same epoch by the oracle in float64, same RNG stream -----------------------------------------------------------
-    random.setstate(state)
-    ref_sd, ref_sum = {k: v.double() for k, v in sd0.items()}, None
-    for u in order:
+        # (b): load the oracle's state of this step, take the same step
+        forced.load_state_dict({k: v.float() for k, v in ref_sd.items()})
+        for n_, p_ in forced.named_parameters():
+            fopt.state[p_]["sum"].copy_(ref_sum[n_].float() if ref_sum is not None else torch.zeros_like(p_))
+        fopt.zero_grad()
+        forced.loss_func(forced(hist, tgt, hreg, treg, ll), label).backward()
+        fopt.step()
+        random.setstate(st)  # the oracle draws the same batch from the same RNG state
         h, t, lab, hr, tr = orc.train_batch_region(data.history(u).tolist(), N, num_ng, data.region, random)
-        ll = orc.latlon_abs_diff(data.coords, t, h)
+        l2 = orc.latlon_abs_diff(data.coords, t, h)
+        prev = ref_sd
         _, ref_sd, ref_sum = orc.train_step_bce(ref_sd, "region_distance", beta, torch.from_numpy(h), torch.from_numpy(t), torch.from_numpy(hr),
-                                                torch.from_numpy(tr), torch.from_numpy(ll), torch.from_numpy(lab), lr, ref_sum, dtype=torch.float64)
+                                                torch.from_numpy(tr), torch.from_numpy(l2), torch.from_numpy(lab), lr, ref_sum, dtype=torch.float64)
+        fgot = {k: v.detach().cpu().double() for k, v in forced.state_dict().items()}
+        for k in names:
+            if k == "embed_distance.weight":
+                continue  # allocated, never read (model.py:204)
+            upd = (ref_sd[k] - prev[k]).abs().max()  # the size of this step's update of the tensor
+            err = (fgot[k] - ref_sd[k]).abs().max()
+            # one step from identical state: the update agrees to 1e-3 of its own size (an element whose gradient is within
+            # rounding of zero may take a different +-lr first step: bounded by that, and rare)
+            bad = ((fgot[k] - ref_sd[k]).abs() > 1e-3 * max(float(upd), 1e-12)).double().mean()
+            assert float(bad) <= 2e-3, (step, k, float(bad), float(err), float(upd))
+            worst_forced = max(worst_forced, float((fgot[k] - ref_sd[k]).abs().mean()))
+    assert worst_forced <= 2e-6, worst_forced
     got = {k: v.detach().cpu().double() for k, v in model.state_dict().items()}
     for k in ref_sd:
         if k == "embed_distance.weight":
-            continue  # allocated, never read (model.py:204)
-        # Adagrad from a zero accumulator turns the SIGN of a gradient element into a +-lr step whatever its size, so an element
-        # whose gradient is below the kernels' rounding (3e-7 of the tensor's maximum for the FP32 kernels, ~3e-6 for the tcgen05
-        # ones; single-step gradient parity is pinned at 2e-4 in test_gpu_backward / test_gpu_pairs_tc) may land a whole step
-        # away: the bulk must agree tightly, outliers must be rare and never exceed a couple of steps
+            continue
         diff = (got[k] - ref_sd[k]).abs()
-        assert float(diff.mean()) <= 2e-5, (k, float(diff.mean()))
-        assert float((diff > 1e-3).double().mean()) <= 2e-3, (k, float((diff > 1e-3).double().mean()))
-        assert float(diff.max()) <= 4 * lr, (k, float(diff.max()))
+        if pairs_precision == "fp32":
+            assert float(diff.mean()) <= 2e-5, (k, float(diff.mean()))
+        assert float(diff.mean()) <= 0.2 * lr and float(diff.max()) <= 10 * lr, (k, float(diff.mean()), float(diff.max()))
     # ---- full-rank evaluation of every user with the GPU-trained weights (validation.py:62-131) -----------------------------
     k_list = [5, 10, 15, 20, 25, 30]
     ns = argparse.Namespace(topk=50, powerlaw_weight=0.2)

@@ -167,11 +167,13 @@ def test_long_history_beyond_the_smem_staging_window(H):
 
 
 @pytest.mark.parametrize("D,hid", [(64, 128), (64, 96), (32, 128), (48, 32), (16, 16), (32, 64), (128, 128), (128, 64), (96, 96),
-                                   (128, 32), (96, 16)])
+                                   (128, 32), (96, 16), (256, 256), (256, 128), (128, 256), (256, 64), (64, 256), (192, 96)])
 @pytest.mark.parametrize("precision", ["tc_split", "tc_mix", "tc_fast"])
 def test_tensor_path_shapes(D, hid, precision):
     """Every (D, hid) tiling of the tensor-core path: two history items per MMA step for hid <= 64, one for hid 96/128
-    (a cell's hidden columns are split between two warps and exchanged through shared memory)."""
+    (a cell's hidden columns are split between two warps and exchanged through shared memory); hid = 256 as two 128-unit halves
+    in consecutive chunks (the two epilogue groups meet once per cell); D > 128 as up to eight K-parts with one resident
+    candidate tile."""
     U, N = 4, 900
     if precision == "tc_mix" and D % 32:
         pytest.skip("tc_mix: an e5m2 MMA covers K = 32")
