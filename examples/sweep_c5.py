@@ -4,7 +4,7 @@ users/s, pair-scores/s and the fraction of the measured tensor / FP32 roofline p
 are dealt round-robin to the ranks (a sweep is independent replicas: one point per GPU at a time, no collective on the data
 path); rank 0 prints every line.
 
-Tensor-core path (--precision, default tc_auto) where its tiling exists (D, hid <= 128), FP32 CUDA-core path elsewhere.
+Tensor-core path (--precision, default tc_auto) for every D = hid of the sweep (16 ... 256).
     python examples/sweep_c5.py [--pois 40000] > profiles/r2_sweep_c5.jsonl
     torchrun --nproc-per-node 8 examples/sweep_c5.py > profiles/r2_sweep_c5.jsonl
 """

@@ -439,6 +439,21 @@ __global__ void __launch_bounds__(PT, 2) pairs_bwd_tc_kernel(const __grid_consta
 // =====================================================================================================================
 constexpr int PT2 = 256;
 
+// Per-phase clocks of thread 0 (examples/diag_phase_clocks.py builds a private library with -DNAIS_PHASE_CLOCKS; never in the product)
+#ifdef NAIS_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clk[16];
+#define NAIS_PH_INIT long long ph_t = clock64();
+#define NAIS_PH(i)                                                               \
+  if (tid == 0) {                                                                \
+    const long long ph_n = clock64();                                            \
+    atomicAdd(&g_phase_clk[i], (unsigned long long)(ph_n - ph_t));               \
+    ph_t = ph_n;                                                                 \
+  }
+#else
+#define NAIS_PH_INIT
+#define NAIS_PH(i)
+#endif
+
 __global__ void __launch_bounds__(PT2, 2) pairs_bwd_tc2_kernel(const __grid_constant__ BwdArgs A) {
   constexpr int D = 64;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -453,14 +468,23 @@ __global__ void __launch_bounds__(PT2, 2) pairs_bwd_tc2_kernel(const __grid_cons
   uint8_t* sW = sX + 2 * X_PLANE;               // [hi | lo][D/8][64 hidden][16 B]
   uint8_t* sDT = sW + 2 * W_PLANE;              // [hi | lo][8][128 cells][16 B]       (row staging aliases it outside GEMM2/3)
   float* kc = reinterpret_cast<float*>(sDT + DT_REGION);  // [HID] x {b1, w2, w1[:, D], w1[:, D+1]}
-  float* ps = kc + 4 * HID;                     // [BWD_MAXROWS][D]
-  float* dpacc = ps + BWD_MAXROWS * D;          // [BWD_MAXROWS][D]
+  float* ps = kc + 4 * HID;                     // [2][BWD_MAXROWS][D] target vectors of this tile / of the next tile
+  float* dpacc = ps + 2 * BWD_MAXROWS * D;      // [BWD_MAXROWS][D] running dp of rows with more than one chunk
   float* rowv = dpacc + BWD_MAXROWS * D;        // [4][BWD_MAXROWS] S, score, G, S^beta
   float* dvs = rowv + 4 * BWD_MAXROWS;          // [4 lane quarters][HID]
   float* red = dvs + 4 * HID;                   // [8][8]
   float* xsum = red + 64;                       // [2][PT] similarity partial of each half
   float* asum = xsum + 2 * PT;                  // [2][PT] logit partial of each half
-  uint64_t* bar = reinterpret_cast<uint64_t*>(asum + 2 * PT);
+  // inputs of the NEXT work unit, copied one unit ahead with cp.async (see the loop)
+  long long* m_hist = reinterpret_cast<long long*>(asum + 2 * PT);  // [PT] history POI id of each cell      (copied by half 0)
+  long long* m_hreg = m_hist + PT;                                  // [PT] its region id                     (half 1)
+  unsigned long long* m_mask = reinterpret_cast<unsigned long long*>(m_hreg + PT);  // [PT] ReLU pattern     (half 1)
+  long long* m_psid = reinterpret_cast<long long*>(m_mask + PT);    // [PT2] id behind this thread's 16 B of `ps` (private)
+  long long* m_tgt = m_psid + PT2;                                  // [BWD_MAXROWS] target POI id of each row (live mask)
+  float2* m_ll = reinterpret_cast<float2*>(m_tgt + BWD_MAXROWS);    // [PT] |dlat|,|dlon| or the history item's coordinates (half 0)
+  float2* m_tco = m_ll + PT;                                        // [BWD_MAXROWS] target coordinates (segmented layout)
+  float* m_rowv = reinterpret_cast<float*>(m_tco + BWD_MAXROWS);    // [3][BWD_MAXROWS] S, score, dscore of each row
+  uint64_t* bar = reinterpret_cast<uint64_t*>(m_rowv + 4 * BWD_MAXROWS);
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
   float* dps = reinterpret_cast<float*>(sX);    // [D][DP_STRIDE]
   static_assert(D * DP_STRIDE * 4 <= 2 * X_PLANE, "dp scratch must fit in the X image");
@@ -492,260 +516,364 @@ __global__ void __launch_bounds__(PT2, 2) pairs_bwd_tc2_kernel(const __grid_cons
   uint8_t* stg = sDT + (size_t)(warp * 32) * STG_STRIDE;
   const int s0 = 32 * half;  // this thread's embedding columns [s0, s0 + 32) and hidden units [s0, s0 + 32)
 
+  // ---- the input pipeline (per-phase clocks of the unpipelined kernel, profiles/r2_phase_clocks_before.txt: 39 % of a tile's
+  // time was exposed load latency — target id -> target row, history id -> history row — and another 20 % the second gather).
+  // The inputs of work unit u + 1 are copied while unit u computes, with nothing held in registers:
+  //   P1 (after u's inputs are consumed)     ids / lat-lon / ReLU mask / row scalars of u + 1       -> m_* arrays
+  //   P2 (after u's second gather is staged)  history rows of u + 1 -> `stg` (aliases the DT image, free now); target rows -> ps[next]
+  // and u + 1 starts with cp.async.wait_all + one barrier.  The second gather of u's own rows (dp needs them again) is issued
+  // into registers BEFORE the wait for GEMM2/3 and staged after it.
+  auto issue_ids = [&](const PairTile& Tn, int chn) {
+    const PairCell c = pair_cell(Tn, chn, cell);
+    if (c.valid) {
+      if (half == 0) {
+        cp_async8(m_hist + cell, A.b.hist + c.hidx);
+        if (lanes) cp_async8(m_ll + cell, A.b.aux ? A.b.aux + c.cidx * 2 : A.b.hist_coords + c.hidx * 2);
+      } else {
+        if (br.w_reg) cp_async8(m_hreg + cell, A.b.hreg + c.hidx);
+        if (A.act_mask) cp_async8(m_mask + cell, A.act_mask + c.cidx);
+      }
+    }
+    if (tid < Tn.nrows) cp_async8(m_tgt + tid, A.b.tgt + Tn.row0 + tid);
+    if (lanes && !A.b.aux && tid >= 32 && tid < 32 + Tn.nrows) cp_async8(m_tco + (tid - 32), A.b.tgt_coords + (Tn.row0 + tid - 32) * 2);
+    if (chn == 0) {
+      if (tid >= 64 && tid < 64 + Tn.nrows) {
+        const int rr = tid - 64;
+        cp_async4(m_rowv + rr, A.row_sum + Tn.row0 + rr);
+        cp_async4(m_rowv + BWD_MAXROWS + rr, A.parts + Tn.row0 + rr);
+        cp_async4(m_rowv + 2 * BWD_MAXROWS + rr, A.dscore + Tn.row0 + rr);
+      }
+      if (tid * 4 < Tn.nrows * D) {
+        const int r = (tid * 4) / D, d = tid * 4 - r * D;
+        cp_async8(m_psid + tid, (d < br.w_poi ? A.b.tgt : A.b.treg) + Tn.row0 + r);
+      }
+    }
+  };
+  auto issue_rows = [&](const PairTile& Tn, int chn, int pbn) {  // (after cp_async_wait_all + a barrier: the ids are visible)
+    const PairCell c = pair_cell(Tn, chn, cell);
+    int it32 = 0, rg32 = 0;
+    if (c.valid) {
+      it32 = checked_id(m_hist[cell], p.item_num, A.bad);
+      rg32 = br.w_reg ? checked_id(m_hreg[cell], p.region_num, A.bad) : 0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int idx = lane + 32 * q, cc = idx >> 3, part = idx & 7, col = s0 + 4 * part;
+      const int ci = __shfl_sync(0xffffffffu, it32, cc), cr = __shfl_sync(0xffffffffu, rg32, cc);
+      const float* src = col < br.w_poi ? br.hist_poi + (size_t)ci * br.w_poi + col : br.hist_reg + (size_t)cr * br.w_reg + (col - br.w_poi);
+      cp_async16(stg + (size_t)cc * STG_STRIDE + part * 16, src);
+    }
+    if (chn == 0 && tid * 4 < Tn.nrows * D) {
+      const int r = (tid * 4) / D, d = tid * 4 - r * D;
+      const float* src = d < br.w_poi ? br.tgt_poi + (size_t)checked_id(m_psid[tid], p.item_num, A.bad) * br.w_poi + d
+                                      : br.tgt_reg + (size_t)checked_id(m_psid[tid], p.region_num, A.bad) * br.w_reg + (d - br.w_poi);
+      cp_async16(ps + (size_t)pbn * BWD_MAXROWS * D + tid * 4, src);
+    }
+  };
+
   float pd[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // dist_w[4], dist_b[2] partials (this thread's hidden units of its cells)
   float dv_acc = 0.f;                            // dw2 partial of hidden unit s0 + lane over this warp's cells
   uint32_t phase = 0, dw_started = 0;
+  int64_t item = blockIdx.x;  // (the launch gives every CTA at least one tile)
+  int ch = 0, pb = 0;
+  NAIS_PH_INIT
+  {
+    const PairTile T0 = pair_tile(A.b, item);
+    issue_ids(T0, 0);
+    cp_async_wait_all();
+    __syncthreads();
+    issue_rows(T0, 0, 0);
+  }
+  NAIS_PH(0)
 
-  for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x) {
+  while (true) {
     const PairTile T = pair_tile(A.b, item);
     const int64_t row0 = T.row0;
     const int nrows = T.nrows, H = T.H;
-    const int n_chunks = (H <= PT) ? 1 : (H + PT - 1) / PT;
-    for (int i = tid; i < nrows * D; i += PT2) {
-      const int r = i / D, d = i - r * D;
-      ps[i] = (d < br.w_poi) ? __ldg(br.tgt_poi + (size_t)checked_id(A.b.tgt[row0 + r], p.item_num, A.bad) * br.w_poi + d)
-                             : __ldg(br.tgt_reg + (size_t)checked_id(A.b.treg[row0 + r], p.region_num, A.bad) * br.w_reg + (d - br.w_poi));
-      dpacc[i] = 0.f;
-    }
-    if (tid < nrows) {
-      const float S = A.row_sum[row0 + tid];
+    const int n_chunks = pair_chunks(T);
+    const PairCell c = pair_cell(T, ch, cell);
+    const bool valid = c.valid;
+    const int r = c.r;
+    const int64_t cidx = c.cidx;
+    const bool same = ch + 1 < n_chunks;               // the next unit: the next chunk of this tile, or this CTA's next tile
+    const int64_t item_n = same ? item : item + gridDim.x;
+    const int ch_n = same ? ch + 1 : 0, pb_n = same ? pb : pb ^ 1;
+    const bool has_next = item_n < A.n_items;
+
+    cp_async_wait_all();
+    __syncthreads();  // (a) this unit's rows, ids, lat/lon, mask, row scalars and target vectors are in shared memory
+    NAIS_PH(1)
+    if (ch == 0 && tid < nrows) {
+      const float S = m_rowv[tid];
       rowv[tid] = S;
-      rowv[BWD_MAXROWS + tid] = A.parts[row0 + tid];
-      rowv[2 * BWD_MAXROWS + tid] = A.dscore[row0 + tid];
+      rowv[BWD_MAXROWS + tid] = m_rowv[BWD_MAXROWS + tid];
+      rowv[2 * BWD_MAXROWS + tid] = m_rowv[2 * BWD_MAXROWS + tid];
       rowv[3 * BWD_MAXROWS + tid] = powf(S, p.beta);
     }
-    __syncthreads();
-    for (int ch = 0; ch < n_chunks; ++ch) {
-      int r, h;
-      bool valid;
-      if (H <= PT) {
-        r = cell / H;
-        h = cell - r * H;
-        valid = r < nrows;
-      } else {
-        r = 0;
-        h = ch * PT + cell;
-        valid = h < H;
-      }
-      const int64_t cidx = valid ? T.cell0 + r * (int64_t)H + h : 0;  // per-cell arrays
-      const int64_t hidx = valid ? T.hist0 + r * T.hist_rs + h : 0;   // history arrays
-      int it32 = 0, rg32 = 0;
-      float l0r = 0.f, l1r = 0.f;
-      bool live = false;
-      if (valid) {
-        it32 = checked_id(A.b.hist[hidx], p.item_num, A.bad);
-        rg32 = br.w_reg ? checked_id(A.b.hreg[hidx], p.region_num, A.bad) : 0;
-        if (lanes) pair_latlon(A.b, cidx, hidx, row0 + r, l0r, l1r);
-        live = A.b.hist[hidx] != A.b.tgt[row0 + r];
-      }
-      float g0 = 0.f, g1 = 0.f;
-      if (valid && lanes) {
+    int it32 = 0, rg32 = 0;
+    float l0r = 0.f, l1r = 0.f, g0 = 0.f, g1 = 0.f;
+    bool live = false;
+    uint32_t am32 = 0u;
+    if (valid) {
+      const long long hid64 = m_hist[cell];
+      it32 = checked_id(hid64, p.item_num, A.bad);
+      rg32 = br.w_reg ? checked_id(m_hreg[cell], p.region_num, A.bad) : 0;
+      if (lanes) {
+        const float2 hl = m_ll[cell];
+        l0r = hl.x;
+        l1r = hl.y;
+        if (!A.b.aux) {  // (pair_latlon of the segmented layout)
+          const float2 tc = m_tco[r];
+          l0r = fabsf(tc.x - hl.x);
+          l1r = fabsf(tc.y - hl.y);
+        }
         const float a0 = l0r * p.dist_scale, a1 = l1r * p.dist_scale;
         g0 = sigmoidf_exact(fmaf(a1, __ldg(p.dist_w + 1), fmaf(a0, __ldg(p.dist_w + 0), __ldg(p.dist_b + 0))));
         g1 = sigmoidf_exact(fmaf(a1, __ldg(p.dist_w + 3), fmaf(a0, __ldg(p.dist_w + 2), __ldg(p.dist_b + 1))));
       }
-      const unsigned long long am = (A.act_mask && valid) ? __ldg(A.act_mask + cidx) : 0ull;
-      // ---- this half of the X image (bf16 hi/lo, unscaled) + similarity partial -------------------------------------------------------
-      const float* pr = ps + (valid ? r : 0) * D;
-      {
-        float q[32];
-        gather_segment<32>(br, it32, rg32, s0, stg, lane, q);
-        float ssum = 0.f;
+      live = hid64 != m_tgt[r];
+      if (A.act_mask) am32 = (uint32_t)(m_mask[cell] >> s0);  // this half's 32 hidden units
+    }
+    // ---- this half of the X image (bf16 hi/lo, unscaled) + similarity partial -------------------------------------------------------
+    const float* pr = ps + (size_t)pb * BWD_MAXROWS * D + (valid ? r : 0) * D;
+    {
+      float ssum = 0.f;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float x[8];
+      for (int cc = 0; cc < 4; ++cc) {
+        const float4 q0 = *reinterpret_cast<const float4*>(stg + (size_t)lane * STG_STRIDE + cc * 32);
+        const float4 q1 = *reinterpret_cast<const float4*>(stg + (size_t)lane * STG_STRIDE + cc * 32 + 16);
+        const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        float x[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            x[e] = valid ? q[c * 8 + e] * pr[s0 + c * 8 + e] : 0.f;
-            ssum += x[e];
-          }
-          store_chunk_bf16(sX, sX + X_PLANE, ((size_t)(s0 / 8 + c) * PT + cell) * 16, x);
+        for (int e = 0; e < 8; ++e) {
+          x[e] = valid ? qv[e] * pr[s0 + cc * 8 + e] : 0.f;
+          ssum += x[e];
         }
-        xsum[half * PT + cell] = ssum;
-        if (half == 0) {
-          const float ext[8] = {valid ? 1.f : 0.f, g0, g1, 0.f, 0.f, 0.f, 0.f, 0.f};
-          store_chunk_bf16(sX, sX + X_PLANE, ((size_t)(D / 8) * PT + cell) * 16, ext);
+        store_chunk_bf16(sX, sX + X_PLANE, ((size_t)(s0 / 8 + cc) * PT + cell) * 16, x);
+      }
+      xsum[half * PT + cell] = ssum;
+      if (half == 0) {
+        const float ext[8] = {valid ? 1.f : 0.f, g0, g1, 0.f, 0.f, 0.f, 0.f, 0.f};
+        store_chunk_bf16(sX, sX + X_PLANE, ((size_t)(D / 8) * PT + cell) * 16, ext);
+      }
+    }
+    fence_proxy_async();
+    NAIS_PH(2)
+    __syncthreads();  // (b) X image complete; the staged rows and the m_* arrays are consumed
+    NAIS_PH(3)
+    // ---- GEMM1: T = X W^T -----------------------------------------------------------------------------------------------------------
+    if (warp == 0) {
+      if (elect_one()) {
+        tc_fence_after();
+        const uint32_t x0 = smem_u32(sX), w0 = smem_u32(sW);
+        const uint32_t idesc = idesc_bf16(PT, HID, 0, 0);
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t ab = x0 + (pass == 2 ? X_PLANE : 0), wb = w0 + (pass == 1 ? W_PLANE : 0);
+#pragma unroll
+          for (int s = 0; s < D / 16; ++s)
+            mma_f16(tmem + COL_T, smem_desc(ab + s * 2 * PT * 16, PT * 16, 128), smem_desc(wb + s * 2 * HID * 16, HID * 16, 128), idesc,
+                    (pass | s) != 0);
         }
+        mma_commit(bar);
       }
-      fence_proxy_async();
-      __syncthreads();  // X image complete; every warp is done with its staging slice (aliased on the DT image)
-      // ---- GEMM1: T = X W^T -----------------------------------------------------------------------------------------------------------
-      if (warp == 0) {
-        if (elect_one()) {
-          tc_fence_after();
-          const uint32_t x0 = smem_u32(sX), w0 = smem_u32(sW);
-          const uint32_t idesc = idesc_bf16(PT, HID, 0, 0);
-#pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t ab = x0 + (pass == 2 ? X_PLANE : 0), wb = w0 + (pass == 1 ? W_PLANE : 0);
-#pragma unroll
-            for (int s = 0; s < D / 16; ++s)
-              mma_f16(tmem + COL_T, smem_desc(ab + s * 2 * PT * 16, PT * 16, 128), smem_desc(wb + s * 2 * HID * 16, HID * 16, 128), idesc,
-                      (pass | s) != 0);
-          }
-          mma_commit(bar);
-        }
-        __syncwarp();
-      }
-      const float ssum = xsum[cell] + xsum[PT + cell];  // (the same sum, in the same order, in both threads of the cell)
-      mbar_wait(bar, phase);
-      phase ^= 1u;
-      tc_fence_after();
-      // ---- epilogue 1: this thread's 32 hidden units of its cell -------------------------------------------------------------------------
-      float tv[32];
-      {
-        float ap = 0.f;
-#pragma unroll
-        for (int c0 = 0; c0 < 32; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(tlane + COL_T + s0 + c0, v);
-          tmem_wait_ld16(v);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float4 c4 = reinterpret_cast<const float4*>(kc)[s0 + c0 + i];
-            float t = __uint_as_float(v[i]) + c4.x;
-            if (lanes) t = fmaf(c4.w, g1, fmaf(c4.z, g0, t));
-            tv[c0 + i] = t;
-            ap = fmaf(c4.y, fmaxf(t, 0.f), ap);
-          }
-        }
-        asum[half * PT + cell] = ap;
-      }
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");  // the two warps of this lane quarter exchange their halves of a
-      const float a = asum[cell] + asum[PT + cell];
-      float dav = 0.f, gwv = 0.f;
-      if (live) {
-        const float S = rowv[r], sc = rowv[BWD_MAXROWS + r], G = rowv[2 * BWD_MAXROWS + r], Sb = rowv[3 * BWD_MAXROWS + r];
-        const float e = expf(a);
-        const float w = e / Sb;
-        dav = G * (w * ssum - p.beta * (e / S) * sc);
-        gwv = G * w;
-      }
-      const bool have_mask = A.act_mask != nullptr;
-      const uint32_t am32 = (uint32_t)(am >> s0);  // this half's 32 hidden units
-      float dg0 = 0.f, dg1 = 0.f;
+      __syncwarp();
+    }
+    if (has_next) issue_ids(same ? T : pair_tile(A.b, item_n), ch_n);  // P1
+    const float ssum = xsum[cell] + xsum[PT + cell];  // (the same sum, in the same order, in both threads of the cell)
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    tc_fence_after();
+    NAIS_PH(4)
+    // ---- epilogue 1: this thread's 32 hidden units of its cell -------------------------------------------------------------------------
+    float tv[32];
+    {
+      float ap = 0.f;
 #pragma unroll
       for (int c0 = 0; c0 < 32; c0 += 16) {
-        float dt[16];
+        uint32_t v[16];
+        tmem_ld16(tlane + COL_T + s0 + c0, v);
+        tmem_wait_ld16(v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int k = s0 + c0 + i;
-          const float4 c4 = reinterpret_cast<const float4*>(kc)[k];
-          const float t = tv[c0 + i];
-          const bool on = have_mask ? ((am32 >> (c0 + i)) & 1u) != 0u : t > 0.f;
-          tv[c0 + i] = dav * fmaxf(t, 0.f);  // -> dw2 contribution of this cell
-          dt[i] = on ? dav * c4.y : 0.f;
-          dg0 = fmaf(dt[i], c4.z, dg0);
-          dg1 = fmaf(dt[i], c4.w, dg1);
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          float c8[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) c8[e] = dt[j * 8 + e];
-          store_chunk_bf16(sDT, sDT + DT_PLANE, ((size_t)((s0 + c0) / 8 + j) * PT + cell) * 16, c8);
+          const float4 c4 = reinterpret_cast<const float4*>(kc)[s0 + c0 + i];
+          float t = __uint_as_float(v[i]) + c4.x;
+          if (lanes) t = fmaf(c4.w, g1, fmaf(c4.z, g0, t));
+          tv[c0 + i] = t;
+          ap = fmaf(c4.y, fmaxf(t, 0.f), ap);
         }
       }
-      if (lanes) {  // dist layer: z = Wd (scale * ll) + bd, g = sigmoid(z); linear in dg, so the halves' partials simply add up
-        const float dz0 = dg0 * g0 * (1.f - g0), dz1 = dg1 * g1 * (1.f - g1);
-        const float a0 = l0r * p.dist_scale, a1 = l1r * p.dist_scale;
-        pd[0] = fmaf(dz0, a0, pd[0]);
-        pd[1] = fmaf(dz0, a1, pd[1]);
-        pd[2] = fmaf(dz1, a0, pd[2]);
-        pd[3] = fmaf(dz1, a1, pd[3]);
-        pd[4] += dz0;
-        pd[5] += dz1;
-      }
-      // dw2[s0 + k] += sum over this warp's 32 cells of da * relu(t_k): shuffle halving, lane l ends with hidden unit s0 + l
-#pragma unroll
-      for (int st = 0; st < 5; ++st) {
-        const int n = 32 >> st, m = 16 >> st;
-        const bool up = (lane & m) != 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if (i < n / 2) {
-            const float send = up ? tv[i] : tv[i + n / 2];
-            const float keep = up ? tv[i + n / 2] : tv[i];
-            tv[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
-          }
-        }
-      }
-      dv_acc += tv[0];
-      tc_fence_before();
-      fence_proxy_async();
-      __syncthreads();  // DT image complete
-      // ---- GEMM2: dX = dt W   and   GEMM3: dW += dt^T [X | 1 g0 g1] ---------------------------------------------------------------------
-      if (warp == 0) {
-        if (elect_one()) {
-          tc_fence_after();
-          const uint32_t x0 = smem_u32(sX), w0 = smem_u32(sW), t0 = smem_u32(sDT);
-          const uint32_t id2 = idesc_bf16(PT, D, 0, 1), id3 = idesc_bf16(HID, D + 8, 1, 1);
-#pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t ab = t0 + (pass == 2 ? DT_PLANE : 0), wb = w0 + (pass == 1 ? W_PLANE : 0);
-#pragma unroll
-            for (int s = 0; s < HID / 16; ++s)
-              mma_f16(tmem + COL_DX, smem_desc(ab + s * 2 * PT * 16, PT * 16, 128), smem_desc(wb + s * 256, 128, HID * 16), id2,
-                      (pass | s) != 0);
-          }
-#pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t ab = t0 + (pass == 2 ? DT_PLANE : 0), xb = x0 + (pass == 1 ? X_PLANE : 0);
-#pragma unroll
-            for (int s = 0; s < PT / 16; ++s)
-              mma_f16(tmem + COL_DW, smem_desc(ab + s * 256, 128, PT * 16), smem_desc(xb + s * 256, 128, PT * 16), id3,
-                      (dw_started | pass | s) != 0);
-          }
-          mma_commit(bar);
-        }
-        __syncwarp();
-      }
-      dw_started = 1u;
-      mbar_wait(bar, phase);
-      phase ^= 1u;
-      tc_fence_after();
-      // ---- epilogue 2: this half of the dq row to the workspace, dp contributions to the scratch (aliased on the X image) --------------
-      {
-        float q[32];
-        gather_segment<32>(br, it32, rg32, s0, stg, lane, q);
-#pragma unroll
-        for (int c0 = 0; c0 < 32; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(tlane + COL_DX + s0 + c0, v);
-          tmem_wait_ld16(v);
-          float o[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int d = s0 + c0 + i;
-            const float full = __uint_as_float(v[i]) + gwv;
-            o[i] = full * pr[d];
-            dps[(size_t)d * DP_STRIDE + cell] = valid ? full * q[c0 + i] : 0.f;
-          }
-          if (valid && A.ws_dq) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4)
-              *reinterpret_cast<float4*>(A.ws_dq + cidx * D + s0 + c0 + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
-          }
-        }
-      }
-      tc_fence_before();
-      __syncthreads();
-      {
-        const int nr = (H <= PT) ? nrows : 1;
-        for (int i = tid; i < nr * D; i += PT2) {
-          const int rr = i / D, d = i - rr * D;
-          const int c0 = (H <= PT) ? rr * H : 0;
-          const int cn = (H <= PT) ? H : min(PT, H - ch * PT);
-          float sacc = 0.f;
-          for (int c = 0; c < cn; ++c) sacc += dps[(size_t)d * DP_STRIDE + c0 + c];
-          dpacc[rr * D + d] += sacc;
-        }
-      }
-      __syncthreads();  // scratch (X image) and staging (DT image) are free again
+      asum[half * PT + cell] = ap;
     }
-    if (A.ws_dp)
-      for (int i = tid; i < nrows * D; i += PT2) A.ws_dp[(row0 + i / D) * D + (i % D)] = dpacc[i];
-    __syncthreads();
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");  // the two warps of this lane quarter exchange their halves of a
+    NAIS_PH(5)
+    const float a = asum[cell] + asum[PT + cell];
+    float dav = 0.f, gwv = 0.f;
+    if (live) {
+      const float S = rowv[r], sc = rowv[BWD_MAXROWS + r], G = rowv[2 * BWD_MAXROWS + r], Sb = rowv[3 * BWD_MAXROWS + r];
+      const float e = expf(a);
+      const float w = e / Sb;
+      dav = G * (w * ssum - p.beta * (e / S) * sc);
+      gwv = G * w;
+    }
+    const bool have_mask = A.act_mask != nullptr;
+    float dg0 = 0.f, dg1 = 0.f;
+#pragma unroll
+    for (int c0 = 0; c0 < 32; c0 += 16) {
+      float dt[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int k = s0 + c0 + i;
+        const float4 c4 = reinterpret_cast<const float4*>(kc)[k];
+        const float t = tv[c0 + i];
+        const bool on = have_mask ? ((am32 >> (c0 + i)) & 1u) != 0u : t > 0.f;
+        tv[c0 + i] = dav * fmaxf(t, 0.f);  // -> dw2 contribution of this cell
+        dt[i] = on ? dav * c4.y : 0.f;
+        dg0 = fmaf(dt[i], c4.z, dg0);
+        dg1 = fmaf(dt[i], c4.w, dg1);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float c8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) c8[e] = dt[j * 8 + e];
+        store_chunk_bf16(sDT, sDT + DT_PLANE, ((size_t)((s0 + c0) / 8 + j) * PT + cell) * 16, c8);
+      }
+    }
+    if (lanes) {  // dist layer: z = Wd (scale * ll) + bd, g = sigmoid(z); linear in dg, so the halves' partials simply add up
+      const float dz0 = dg0 * g0 * (1.f - g0), dz1 = dg1 * g1 * (1.f - g1);
+      const float a0 = l0r * p.dist_scale, a1 = l1r * p.dist_scale;
+      pd[0] = fmaf(dz0, a0, pd[0]);
+      pd[1] = fmaf(dz0, a1, pd[1]);
+      pd[2] = fmaf(dz1, a0, pd[2]);
+      pd[3] = fmaf(dz1, a1, pd[3]);
+      pd[4] += dz0;
+      pd[5] += dz1;
+    }
+    // dw2[s0 + k] += sum over this warp's 32 cells of da * relu(t_k): shuffle halving, lane l ends with hidden unit s0 + l
+#pragma unroll
+    for (int st = 0; st < 5; ++st) {
+      const int n = 32 >> st, m = 16 >> st;
+      const bool up = (lane & m) != 0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (i < n / 2) {
+          const float send = up ? tv[i] : tv[i + n / 2];
+          const float keep = up ? tv[i + n / 2] : tv[i];
+          tv[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+      }
+    }
+    dv_acc += tv[0];
+    tc_fence_before();
+    fence_proxy_async();
+    __syncthreads();  // (c) DT image complete
+    NAIS_PH(6)
+    // ---- GEMM2: dX = dt W   and   GEMM3: dW += dt^T [X | 1 g0 g1] ---------------------------------------------------------------------
+    if (warp == 0) {
+      if (elect_one()) {
+        tc_fence_after();
+        const uint32_t x0 = smem_u32(sX), w0 = smem_u32(sW), t0 = smem_u32(sDT);
+        const uint32_t id2 = idesc_bf16(PT, D, 0, 1), id3 = idesc_bf16(HID, D + 8, 1, 1);
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t ab = t0 + (pass == 2 ? DT_PLANE : 0), wb = w0 + (pass == 1 ? W_PLANE : 0);
+#pragma unroll
+          for (int s = 0; s < HID / 16; ++s)
+            mma_f16(tmem + COL_DX, smem_desc(ab + s * 2 * PT * 16, PT * 16, 128), smem_desc(wb + s * 256, 128, HID * 16), id2,
+                    (pass | s) != 0);
+        }
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t ab = t0 + (pass == 2 ? DT_PLANE : 0), xb = x0 + (pass == 1 ? X_PLANE : 0);
+#pragma unroll
+          for (int s = 0; s < PT / 16; ++s)
+            mma_f16(tmem + COL_DW, smem_desc(ab + s * 256, 128, PT * 16), smem_desc(xb + s * 256, 128, PT * 16), id3,
+                    (dw_started | pass | s) != 0);
+        }
+        mma_commit(bar);
+      }
+      __syncwarp();
+    }
+    dw_started = 1u;
+    // second gather of this unit's history rows, in flight while the MMAs run (the staging aliases the DT image they read)
+    float4 gv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int idx = lane + 32 * q, cc = idx >> 3, part = idx & 7;
+      const int ci = __shfl_sync(0xffffffffu, it32, cc), cr = __shfl_sync(0xffffffffu, rg32, cc);
+      gv[q] = ldg_row4(br.hist_poi + (size_t)ci * br.w_poi, br.hist_reg + (size_t)cr * br.w_reg, br.w_poi, s0 + 4 * part);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    tc_fence_after();
+    NAIS_PH(7)
+    // ---- epilogue 2: this half of the dq row to the workspace, dp contributions to the scratch (aliased on the X image) --------------
+    {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int idx = lane + 32 * q, cc = idx >> 3, part = idx & 7;
+        *reinterpret_cast<float4*>(stg + (size_t)cc * STG_STRIDE + part * 16) = gv[q];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int c0 = 0; c0 < 32; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tlane + COL_DX + s0 + c0, v);
+        float qv[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 t = *reinterpret_cast<const float4*>(stg + (size_t)lane * STG_STRIDE + (c0 + 4 * j) * 4);
+          qv[4 * j] = t.x;
+          qv[4 * j + 1] = t.y;
+          qv[4 * j + 2] = t.z;
+          qv[4 * j + 3] = t.w;
+        }
+        tmem_wait_ld16(v);
+        float o[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int d = s0 + c0 + i;
+          const float full = __uint_as_float(v[i]) + gwv;
+          o[i] = full * pr[d];
+          dps[(size_t)d * DP_STRIDE + cell] = valid ? full * qv[i] : 0.f;
+        }
+        if (valid && A.ws_dq) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            *reinterpret_cast<float4*>(A.ws_dq + cidx * D + s0 + c0 + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+        }
+      }
+    }
+    if (has_next) cp_async_wait_all();  // (this thread's id copies of the next unit; visible to the others after the barrier)
+    tc_fence_before();
+    NAIS_PH(8)
+    __syncthreads();  // (d) dp scratch complete; staging read back by every warp; next ids visible
+    NAIS_PH(9)
+    if (has_next) issue_rows(same ? T : pair_tile(A.b, item_n), ch_n, pb_n);  // P2
+    // ---- dp of the rows: four threads per (row, column) sum interleaved cells (bank-conflict free), the first keeps the running sum ----
+    {
+      const int nr = (H <= PT) ? nrows : 1;
+      const int cn = (H <= PT) ? H : min(PT, H - ch * PT);
+      for (int i = tid; i < nr * D * 4; i += PT2) {  // (nr * D * 4 is a multiple of 32: whole warps iterate together)
+        const int part = i & 3, rd = i >> 2, rr = rd / D, d = rd - rr * D;
+        const int c0 = (H <= PT) ? rr * H : 0;
+        float sacc = 0.f;
+        for (int cc = part; cc < cn; cc += 4) sacc += dps[(size_t)d * DP_STRIDE + c0 + cc];
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+        if (part == 0) {
+          if (ch > 0) sacc += dpacc[rd];
+          if (same) dpacc[rd] = sacc;
+          else if (A.ws_dp) A.ws_dp[(row0 + rr) * D + d] = sacc;
+        }
+      }
+    }
+    NAIS_PH(10)
+    if (!has_next) break;
+    item = item_n;
+    ch = ch_n;
+    pb = pb_n;
   }
 
   // ---- this CTA's parameter partial: w1 [hid][ldw] | b1 | w2 | dist_w[4] dist_b[2] km pad --------------------------------------------
@@ -795,7 +923,9 @@ static int launch2(const BwdArgs& A, int grid, cudaStream_t stream) {
   constexpr int D = 64;
   constexpr size_t dt_region = (8 * 32 * STG_STRIDE > 2 * (HID / 8) * PT * 16) ? 8 * 32 * STG_STRIDE : 2 * (HID / 8) * PT * 16;
   constexpr size_t smem = 2 * (size_t)(D / 8 + 1) * PT * 16 + 2 * (size_t)(D / 8) * HID * 16 + dt_region +
-                          (4 * HID + 2 * BWD_MAXROWS * D + 4 * BWD_MAXROWS + 4 * HID + 64 + 4 * PT) * 4 + 16;
+                          (4 * HID + 3 * BWD_MAXROWS * D + 4 * BWD_MAXROWS + 4 * HID + 64 + 4 * PT) * 4 +
+                          (3 * (size_t)PT + PT2 + BWD_MAXROWS) * 8 + ((size_t)PT + BWD_MAXROWS) * 8 + 4 * BWD_MAXROWS * 4 + 16;
+  static_assert(2 * (smem + 1024) <= 228 * 1024, "two CTAs per SM");
   cudaError_t e = cudaFuncSetAttribute(pairs_bwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(pairs_bwd_tc2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -840,3 +970,14 @@ int launch_pairs_bwd_tc(const BwdArgs& A, int D, int grid, cudaStream_t stream) 
 }
 
 }  // namespace nais
+
+#ifdef NAIS_PHASE_CLOCKS
+extern "C" __attribute__((visibility("default"))) int nais_debug_phase_bwd(unsigned long long* host16, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(host16, nais::ptcb::g_phase_clk, sizeof(unsigned long long) * 16);
+  if (e == cudaSuccess && reset) {
+    unsigned long long z[16] = {};
+    e = cudaMemcpyToSymbol(nais::ptcb::g_phase_clk, z, sizeof(z));
+  }
+  return (int)e;
+}
+#endif

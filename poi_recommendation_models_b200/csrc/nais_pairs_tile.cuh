@@ -68,4 +68,41 @@ __device__ __forceinline__ void pair_latlon(const NaisPairs& b, int64_t cidx, in
   }
 }
 
+// ---- software pipelining of a tile's inputs (the two-threads-per-cell tcgen05 pair kernels): Ampere-style cp.async into shared
+// memory, issued one work unit ahead; a thread waits for ITS OWN copies with cp_async_wait_all(), other threads' after a barrier.
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// cell `cell` (0..127) of a work unit of those kernels (128 cells = chunk `ch` of a tile; a tile with H > 128 has several chunks,
+// else one): which row of the tile / history position it is, and where its inputs live
+struct PairCell {
+  bool valid;
+  int r, h;
+  int64_t cidx, hidx;
+};
+__device__ __forceinline__ PairCell pair_cell(const PairTile& T, int ch, int cell) {
+  PairCell c;
+  if (T.H <= TC) {
+    c.r = cell / T.H;
+    c.h = cell - c.r * T.H;
+    c.valid = c.r < T.nrows;
+  } else {
+    c.r = 0;
+    c.h = ch * TC + cell;
+    c.valid = c.h < T.H;
+  }
+  c.cidx = c.valid ? T.cell0 + c.r * (int64_t)T.H + c.h : 0;
+  c.hidx = c.valid ? T.hist0 + c.r * T.hist_rs + c.h : 0;
+  return c;
+}
+__device__ __forceinline__ int pair_chunks(const PairTile& T) { return T.H <= TC ? 1 : (T.H + TC - 1) / TC; }
+
 }  // namespace nais
