@@ -969,14 +969,6 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
         }
       return rc;
     }
-    {
-      const int n = p.hid * (D + lanes) + 2 * p.hid + 7;
-      param_reduce_kernel<<<(n + 255) / 256, 256, 0, stream>>>(A.ws_part, grid, L.stride, p.hid, D, lanes, g.w1[bi], g.b1[bi],
-                                                              g.w2[bi], bi == 0 ? g.dist_w : nullptr,
-                                                              bi == 0 ? g.dist_b : nullptr,
-                                                              p.dist_mode == NAIS_DIST_KM ? g.dist_embed : nullptr, D, bi > 0);
-      NAIS_COUNT_LAUNCH(1);
-    }
     // ---- 3. embedding rows: gather the contribution rows in key order ------------------------------------------------------------
     auto dest = [&](float* grad, const float* param, float* sum, const int32_t* remap) {
       SegOut o;
@@ -1002,6 +994,13 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
     if (want[1] || want[2]) cudaEventRecord(side->fork, stream);
     for (int t = 1; t < 3; ++t)
       if (want[t]) cudaStreamWaitEvent(side->s[t - 1], side->fork, 0);
+    {  // the per-CTA parameter partials -> w1 / b1 / w2 / distance-layer gradients, next to the short list
+      const int n = p.hid * (D + lanes) + 2 * p.hid + 7;
+      param_reduce_kernel<<<(n + 255) / 256, 256, 0, stream_of(want[1] ? 1 : (want[2] ? 2 : 0))>>>(
+          A.ws_part, grid, L.stride, p.hid, D, lanes, g.w1[bi], g.b1[bi], g.w2[bi], bi == 0 ? g.dist_w : nullptr,
+          bi == 0 ? g.dist_b : nullptr, p.dist_mode == NAIS_DIST_KM ? g.dist_embed : nullptr, D, bi > 0);
+      NAIS_COUNT_LAUNCH(1);
+    }
     if (want[0]) seg(0, 0, br.w_poi, p.item_num, dest(g.hist_poi[bi], br.hist_poi, opt ? opt->sum_hist_poi[bi] : nullptr, g.remap_hist_poi[bi]));
     if (want[1]) seg(1, 0, br.w_poi, p.item_num, dest(g.tgt_poi[bi], br.tgt_poi, opt ? opt->sum_tgt_poi[bi] : nullptr, g.remap_tgt_poi[bi]));
     // (history-side and target-side region rows are one table in every variant: hist_reg == tgt_reg)
