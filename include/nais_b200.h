@@ -15,11 +15,12 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer into memory owned by the caller (PyTorch tensors); the library never
- *     allocates, frees or synchronises, and enqueues only on the given stream;
+ *     allocates, frees or synchronises, and enqueues only on the given stream (one documented exception: nais_pairs_backward
+ *     forks two library-owned side streams from it and joins them back before it returns);
  *   - return 0 = OK; negative = argument error found before any launch (see NAIS_ERR_*); positive = cudaError_t;
  *   - all entry points are stateless and re-entrant (no environment variables, no hidden switches: every option is an
- *     argument or a struct field declared here); one host thread per GPU is the intended use.  The one piece of library-owned
- *     device state is a 4-byte "bad index" word per device, see nais_poll_bad_index;
+ *     argument or a struct field declared here); one host thread per GPU is the intended use.  Library-owned state per device:
+ *     a 4-byte "bad index" word (nais_poll_bad_index) and the two side streams + three events of nais_pairs_backward;
  *   - no C++ types, no torch types: plain pointers and sizes.
  */
 #ifndef NAIS_B200_H_
@@ -209,7 +210,11 @@ NAIS_API int nais_pairs_forward(const NaisParams* p, const NaisPairs* batch, flo
 
 NAIS_API size_t nais_pairs_backward_workspace_bytes(const NaisParams* p, const NaisPairs* batch);
 /* Given dscore[B] = dL/dscore, write every parameter gradient.  score_parts / row_sum / act_mask are the forward's outputs
- * (act_mask: NULL unless the tcgen05 forward wrote it). */
+ * (act_mask: NULL unless the tcgen05 forward wrote it).
+ * Streams: everything is ordered after the work already in `stream`, and `stream` is ordered after everything this call
+ * enqueues, as for any other entry point — but the sort + reduce of the target-id and region-id lists run on two streams the
+ * library creates once per device (forked from / joined to `stream` with events inside the call; legal under stream capture).
+ * The call holds a process-wide mutex while it enqueues, so concurrent callers on one device share those two streams safely. */
 NAIS_API int nais_pairs_backward(const NaisParams* p, const NaisPairs* batch, const float* score_parts, const float* row_sum,
                         const uint64_t* act_mask, const float* dscore, const NaisGrads* grads, void* workspace,
                         size_t workspace_bytes, nais_stream_t stream);
