@@ -327,7 +327,6 @@ static int check_fullrank(const NaisParams* p, const NaisCatalog* cat, const Nai
   const int prec = precision & NAIS_PREC_MASK;
   if (precision & ~(NAIS_PREC_MASK | NAIS_PREC_FLAG_GENERIC)) return NAIS_ERR_MODE;
   if (prec < NAIS_PREC_FP32 || prec > NAIS_PREC_TC_AUTO) return NAIS_ERR_MODE;
-  if (p->dist_mode == NAIS_DIST_KM && prec != NAIS_PREC_FP32) return NAIS_ERR_MODE;  // fused haversine: FP32 path only
   if (prec != NAIS_PREC_FP32 && !tc_supported(*p, precision)) return NAIS_ERR_SHAPE;
   return 0;
 }

@@ -54,6 +54,7 @@ constexpr int HMETA = 512;      // history items whose id/coords are staged in s
 
 struct Geo {
   int D, hid, lanes, split;
+  int km;        // NAIS_DIST_KM: logit += haversine_km(h, j) * sum_d embed_distance[0, d] in the (run-time-shape) epilogue
   int mix;       // NAIS_PREC_TC_MIX: lo section of A tiles / B chunks = e5m2(hi) | e5m2(lo) byte planes, two ext k-chunks
   int kx;        // D / 8 x k-chunks
   int hsplit;    // chunks per history item: 1, or 2 for hid = 256 — a chunk then holds ONE HALF (128) of the item's hidden units
@@ -84,7 +85,8 @@ __host__ inline bool make_geo(const NaisParams& p, int precision, Geo& g) {
   g.lanes = p.dist_mode == NAIS_DIST_LATLON ? 2 : 0;
   g.split = precision == NAIS_PREC_TC_SPLIT;
   g.mix = precision == NAIS_PREC_TC_MIX;
-  if (p.dist_mode == NAIS_DIST_KM) return false;
+  g.km = p.dist_mode == NAIS_DIST_KM ? 1 : 0;
+  if (g.km && p.dist_buckets != 1) return false;
   if (precision == NAIS_PREC_TC_AUTO) {  // MIX geometry where an e5m2 K-step exists, else SPLIT (same image sizes)
     g.mix = g.D % 32 == 0;
     g.split = !g.mix;
@@ -123,7 +125,8 @@ __host__ inline bool make_geo(const NaisParams& p, int precision, Geo& g) {
   //       partner exchange | barriers
   g.tpc = g.kp == 1 ? TPC : (g.D > 128 ? 1 : 2);  // compile-time constant per kernel instantiation (kSinglePart / kFix == 4)
   g.smem_bytes = g.tpc * g.a_tile + g.stages * g.stage_bytes + NBUF * 2 * TM * 16 + 4096 + SORTN * 8 + 3 * HMETA * 4 + 6 * TM * 4 + 256 + 128 +
-                 (g.kp == 1 ? 9 * TPC * TM * 4 : 0);  // D <= 64 has room for a private `comb`; D > 64 aliases it on A_ext + zero
+                 (g.kp == 1 ? 9 * TPC * TM * 4 : 0) +  // D <= 64 has room for a private `comb`; D > 64 aliases it on A_ext + zero
+                 (g.km ? HMETA * 4 : 0);               // cos(latitude) of the staged history items
   return g.smem_bytes <= 227 * 1024;
 }
 
@@ -459,6 +462,8 @@ struct MainArgs {
   const unsigned char* Bimg;
   unsigned long long* part_keys;  // [n_users, groups, k]
   float* all_scores;              // optional [n_users, range]
+  const float* score_in;          // optional [n_users, range]: added to the score before it is stored / ranked (the other
+                                  // attention branch of the two-branch model, scored by an earlier pass; may alias all_scores)
   int64_t max_chunks;             // chunk slots the operand image holds (users beyond it are truncated, never read out of bounds)
   int gate;                       // -1: one pass scores every user; 0 / 1: the SPLIT / MIX pass of NAIS_PREC_TC_AUTO
   const int* pass_flags;          // [2] raised by pack_users_kernel for every pass that has users (gate >= 0)
@@ -527,6 +532,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
                                                           // wait is only valid if the waiter observes EVERY phase in order
   uint64_t* acc_empty = acc_full + 2 * NBUF;             // [NBUF] accumulator drained
   uint32_t* tslot = reinterpret_cast<uint32_t*>(acc_empty + NBUF);
+  float* hm_cos = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 384);  // [HMETA] (g.km only)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const Scales sc = *reinterpret_cast<const Scales*>(A.hdr + 64);
@@ -817,6 +823,12 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
     const float w10 = g.lanes ? __ldg(A.p.dist_w + 2) * dsc : 0.f, w11 = g.lanes ? __ldg(A.p.dist_w + 3) * dsc : 0.f;
     const float bd0 = g.lanes ? __ldg(A.p.dist_b + 0) * nl2e : 0.f, bd1 = g.lanes ? __ldg(A.p.dist_b + 1) * nl2e : 0.f;
     const float beta = A.p.beta;
+    const bool geo = g.lanes || g.km;
+    // NAIS_DIST_KM (model.py:497-504, the reference only ever reads bucket 0): the coefficient, summed in the FP32 kernel's order
+    float ckm = 0.f;
+    if constexpr (!kFastEpi)
+      if (g.km)
+        for (int d = 0; d < g.D; ++d) ckm += __ldg(A.p.dist_embed + d);
     const int npos = sc.npos, hid = g.hid;
     constexpr int hch = kHch;
     const int ncols = hch == 2 ? hid : hid / 2;   // accumulator columns this thread sums per step
@@ -844,19 +856,24 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       epi_bar();
       for (int i = tid; i < H && i < HMETA; i += EPI_THREADS) {
         hm_id[i] = __ldg(A.users.items + hb + i);
-        hm_la[i] = g.lanes ? __ldg(A.users.coords + 2 * (hb + i)) : 0.f;
-        hm_lo[i] = g.lanes ? __ldg(A.users.coords + 2 * (hb + i) + 1) : 0.f;
+        hm_la[i] = geo ? __ldg(A.users.coords + 2 * (hb + i)) : 0.f;
+        hm_lo[i] = geo ? __ldg(A.users.coords + 2 * (hb + i) + 1) : 0.f;
+        if constexpr (!kFastEpi)
+          if (g.km) hm_cos[i] = cosf((A.cat.center_lat + hm_la[i]) * 0.017453292519943295f);
       }
       // candidates of this thread's row in the item's tiles
-      float clat[TPC], clon[TPC], sumE[TPC], sumES[TPC];
+      float clat[TPC], clon[TPC], ccos[TPC], sumE[TPC], sumES[TPC];
       int64_t jid[TPC];
       bool excl[TPC];
 #pragma unroll
       for (int t = 0; t < TPC; ++t) {
         jid[t] = t < tpc ? A.poi_begin + ((int64_t)grp * tpc + t) * TM + r : A.poi_end;
         const bool v = jid[t] < A.poi_end;
-        clat[t] = (v && g.lanes) ? __ldg(A.cat.coords + 2 * (jid[t] - A.cat.row_base)) : 0.f;
-        clon[t] = (v && g.lanes) ? __ldg(A.cat.coords + 2 * (jid[t] - A.cat.row_base) + 1) : 0.f;
+        clat[t] = (v && geo) ? __ldg(A.cat.coords + 2 * (jid[t] - A.cat.row_base)) : 0.f;
+        clon[t] = (v && geo) ? __ldg(A.cat.coords + 2 * (jid[t] - A.cat.row_base) + 1) : 0.f;
+        ccos[t] = 1.f;
+        if constexpr (!kFastEpi)
+          if (g.km) ccos[t] = cosf((A.cat.center_lat + clat[t]) * 0.017453292519943295f);
         sumE[t] = 0.f;
         sumES[t] = 0.f;
         excl[t] = false;
@@ -1116,7 +1133,24 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
           if (h < H && (hch == 2 || hs == 0) && (hsplit == 1 || egrp == 0)) {
             const int64_t j = t == 0 ? jid[0] : (t == 1 ? jid[1] : jid[2]);
             if ((int64_t)hist_id != j) {
-              const float e = __expf(a);
+              float a_km = a;
+              if (g.km) {  // logit += dist_km * coefficient (haversine from centred coordinates, as the FP32 kernel forms it)
+                float hla, hlo, hcs;
+                if (h < HMETA) {
+                  hla = hm_la[h];
+                  hlo = hm_lo[h];
+                  hcs = hm_cos[h];
+                } else {
+                  hla = __ldg(A.users.coords + 2 * (hb + h));
+                  hlo = __ldg(A.users.coords + 2 * (hb + h) + 1);
+                  hcs = cosf((A.cat.center_lat + hla) * 0.017453292519943295f);
+                }
+                const float cla = t == 0 ? clat[0] : (t == 1 ? clat[1] : clat[2]), clo = t == 0 ? clon[0] : (t == 1 ? clon[1] : clon[2]);
+                const float ccs = t == 0 ? ccos[0] : (t == 1 ? ccos[1] : ccos[2]);
+                const float km = dist_km_f(cla, clo, hla, hlo, ccs, hcs);
+                a_km = fmaf(km, ckm, a);
+              }
+              const float e = g.km ? expf(a_km) : __expf(a);
               if (t == 0) { sumE[0] += e; sumES[0] = fmaf(e, S, sumES[0]); }
               else if (t == 1) { sumE[1] += e; sumES[1] = fmaf(e, S, sumES[1]); }
               else { sumE[2] += e; sumES[2] = fmaf(e, S, sumES[2]); }
@@ -1154,8 +1188,9 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
             ES += comb[(q * 3 + 1) * TPC * TM + t2 * TM + r];
             ex = ex || comb[(q * 3 + 2) * TPC * TM + t2 * TM + r] != 0.f;
           }
-          const float score = ES / powf(E, beta);
+          float score = ES / powf(E, beta);
           const bool valid = jid[t2] < A.poi_end;
+          if (A.score_in && valid) score += A.score_in[(size_t)u * (A.poi_end - A.poi_begin) + (jid[t2] - A.poi_begin)];
           if (A.all_scores && valid) A.all_scores[(size_t)u * (A.poi_end - A.poi_begin) + (jid[t2] - A.poi_begin)] = score;
           kreg[t2] = (valid && !(A.exclude && ex)) ? make_key(score, (int)jid[t2]) : 0ull;
           if (!small_k) keys[t2 * TM + r] = kreg[t2];
@@ -1273,22 +1308,58 @@ static inline size_t call_scratch_bytes(int n_users, int groups, int k) {
   return al256((size_t)n_users * merge_scratch_lists(groups, k) * k * 8 + 8);
 }
 
-bool tc_supported(const NaisParams& p, int precision) {
-  tc::Geo g;
-  return tc::make_geo(p, precision & NAIS_PREC_MASK, g);
+// The two-branch (disentangled) model, model.py:467-534: two independent attentions whose scores add.  Each branch is scored as a
+// one-branch model (its own plan section: scales, permutation, candidate image; its own user operand, built in the same per-call
+// workspace one after the other); the first pass leaves its scores in a [n_users, range] buffer at the head of the workspace
+// (MainArgs::all_scores), the second adds them before it ranks (MainArgs::score_in).
+static NaisParams branch_view(const NaisParams& p, int bi) {
+  NaisParams q = p;
+  q.n_branch = 1;
+  q.branch[0] = p.branch[bi];
+  return q;
+}
+static inline size_t branch_scores_bytes(const NaisParams& p, int n_users, int64_t poi_begin, int64_t poi_end) {
+  return p.n_branch > 1 ? al256((size_t)n_users * (size_t)(poi_end - poi_begin) * 4) : 0;
 }
 
-size_t fullrank_tc_plan_bytes(const NaisParams& p, int64_t poi_begin, int64_t poi_end, int precision) {
+bool tc_supported(const NaisParams& p, int precision) {
+  for (int bi = 0; bi < p.n_branch; ++bi) {
+    tc::Geo g;
+    if (!tc::make_geo(branch_view(p, bi), precision & NAIS_PREC_MASK, g)) return false;
+  }
+  return true;
+}
+
+static size_t plan_bytes_1(const NaisParams& p, int64_t poi_begin, int64_t poi_end, int precision) {
   PlanLayout L;
   return plan_layout(p, poi_begin, poi_end, precision, L) ? L.total : 0;
 }
+size_t fullrank_tc_plan_bytes(const NaisParams& p, int64_t poi_begin, int64_t poi_end, int precision) {
+  size_t total = 0;
+  for (int bi = 0; bi < p.n_branch; ++bi) {
+    const size_t b = plan_bytes_1(branch_view(p, bi), poi_begin, poi_end, precision);
+    if (!b) return 0;
+    total += b;
+  }
+  return total;
+}
 
-size_t fullrank_tc_call_workspace_bytes(const NaisParams& p, int n_users, int64_t nnz, int64_t poi_begin, int64_t poi_end, int k,
-                                        int precision) {
+static size_t call_workspace_bytes_1(const NaisParams& p, int n_users, int64_t nnz, int64_t poi_begin, int64_t poi_end, int k,
+                                     int precision) {
   PlanLayout L;
   if (!plan_layout(p, poi_begin, poi_end, precision, L)) return 0;
   const int64_t max_chunks = (L.g.hch == 2 ? (nnz + n_users) / 2 : nnz * L.g.hsplit) + 2;
   return 256 + al256((size_t)max_chunks * L.g.b_chunk) + call_keys_bytes(n_users, L.groups, k) + call_scratch_bytes(n_users, L.groups, k);
+}
+size_t fullrank_tc_call_workspace_bytes(const NaisParams& p, int n_users, int64_t nnz, int64_t poi_begin, int64_t poi_end, int k,
+                                        int precision) {
+  size_t most = 0;
+  for (int bi = 0; bi < p.n_branch; ++bi) {
+    const size_t b = call_workspace_bytes_1(branch_view(p, bi), n_users, nnz, poi_begin, poi_end, k, precision);
+    if (!b) return 0;
+    most = b > most ? b : most;
+  }
+  return most + branch_scores_bytes(p, n_users, poi_begin, poi_end);
 }
 
 size_t fullrank_tc_workspace_bytes(const NaisParams& p, int n_users, int64_t nnz, int64_t poi_begin, int64_t poi_end, int k,
@@ -1309,8 +1380,8 @@ static int check_arch(int& sms) {
 }
 
 // Once per (weights, catalogue range, precision): table maxima -> scales / permutation -> candidate image(s).
-int fullrank_tc_prepare(const NaisParams& p, const NaisCatalog& cat, int64_t poi_begin, int64_t poi_end, int precision, void* plan,
-                        size_t plan_bytes, cudaStream_t stream) {
+static int prepare_1(const NaisParams& p, const NaisCatalog& cat, int64_t poi_begin, int64_t poi_end, int precision, void* plan,
+                     size_t plan_bytes, cudaStream_t stream) {
   if (poi_end <= poi_begin) return 0;
   int sms;
   int rc = check_arch(sms);
@@ -1347,12 +1418,28 @@ int fullrank_tc_prepare(const NaisParams& p, const NaisCatalog& cat, int64_t poi
   return e == cudaSuccess ? 0 : (int)e;
 }
 
+int fullrank_tc_prepare(const NaisParams& p, const NaisCatalog& cat, int64_t poi_begin, int64_t poi_end, int precision, void* plan,
+                        size_t plan_bytes, cudaStream_t stream) {
+  size_t off = 0;
+  for (int bi = 0; bi < p.n_branch; ++bi) {
+    const NaisParams q = branch_view(p, bi);
+    const size_t b = plan_bytes_1(q, poi_begin, poi_end, precision);
+    if (!b) return NAIS_ERR_SHAPE;
+    if (plan_bytes < off + b) return NAIS_ERR_WORKSPACE;
+    const int rc = prepare_1(q, cat, poi_begin, poi_end, precision, reinterpret_cast<unsigned char*>(plan) + off, b, stream);
+    if (rc) return rc;
+    off += b;
+  }
+  return 0;
+}
+
 typedef void (*MainKernel)(const tc::MainArgs);
 
 // compile-time-shape instantiations: kFix 1 / 2 = D = hid = 64 or 32 in SPLIT / MIX, kFix 3 = D = hid = 128 (generic code paths,
 // constants folded); everything else (and NAIS_PREC_FLAG_GENERIC) runs the run-time-shape kernels
 static MainKernel pick_kernel(const tc::Geo& gg, bool generic) {
   const bool s64 = gg.D == 64 && gg.hid == 64 && gg.nrow == 144, s32 = gg.D == 32 && gg.hid == 32 && gg.nrow == 80;
+  if (gg.km) generic = true;  // the haversine bias lives in the run-time-shape epilogue only
   const int fix = ((s64 || s32) && gg.kp == 1 && gg.hch == 2 && gg.stages == 2 && !generic) ? (gg.mix ? 2 : (gg.split ? 1 : 0)) : 0;
   if (gg.kp == 1) {
     if (gg.hch != 2) return tc::fullrank_tc_kernel<true, 1, 0>;
@@ -1368,9 +1455,9 @@ static MainKernel pick_kernel(const tc::Geo& gg, bool generic) {
 }
 
 // Per user batch: user operand image -> scoring pass(es) -> merge of the per-item lists.
-int fullrank_tc_run(const NaisParams& p, const NaisCatalog& cat, const NaisUsers& users, int64_t poi_begin, int64_t poi_end, int k,
-                    int exclude, int precision, const void* plan, size_t plan_bytes, unsigned long long* out_keys, float* out_score,
-                    int32_t* out_id, float* all_scores, void* ws, size_t ws_bytes, cudaStream_t stream) {
+static int run_1(const NaisParams& p, const NaisCatalog& cat, const NaisUsers& users, int64_t poi_begin, int64_t poi_end, int k,
+                 int exclude, int precision, const void* plan, size_t plan_bytes, unsigned long long* out_keys, float* out_score,
+                 int32_t* out_id, float* all_scores, const float* score_in, bool merge, void* ws, size_t ws_bytes, cudaStream_t stream) {
   if (users.n_users == 0 || poi_end <= poi_begin) return 0;
   int sms;
   int rc = check_arch(sms);
@@ -1420,6 +1507,7 @@ int fullrank_tc_run(const NaisParams& p, const NaisCatalog& cat, const NaisUsers
     A.Bimg = bimg;
     A.part_keys = keys;
     A.all_scores = all_scores;
+    A.score_in = score_in;
     A.max_chunks = max_chunks;
     A.gate = gate;
     A.pass_flags = pass_flags;
@@ -1441,9 +1529,35 @@ int fullrank_tc_run(const NaisParams& p, const NaisCatalog& cat, const NaisUsers
   } else {
     rc = run(L.g, pbase + L.pimg, -1);
   }
-  if (rc) return rc;
+  if (rc || !merge) return rc;
   return launch_topk_merge_keys_multi(keys, scratch, (int64_t)L.groups * k, k, users.n_users, L.groups, k, out_keys, out_score, out_id,
                                       stream);
+}
+
+int fullrank_tc_run(const NaisParams& p, const NaisCatalog& cat, const NaisUsers& users, int64_t poi_begin, int64_t poi_end, int k,
+                    int exclude, int precision, const void* plan, size_t plan_bytes, unsigned long long* out_keys, float* out_score,
+                    int32_t* out_id, float* all_scores, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (users.n_users == 0 || poi_end <= poi_begin) return 0;
+  if (p.n_branch == 1)
+    return run_1(p, cat, users, poi_begin, poi_end, k, exclude, precision, plan, plan_bytes, out_keys, out_score, out_id, all_scores,
+                 nullptr, true, ws, ws_bytes, stream);
+  const size_t sbytes = branch_scores_bytes(p, users.n_users, poi_begin, poi_end);
+  if (!plan || ws_bytes < sbytes + 512) return NAIS_ERR_WORKSPACE;
+  float* sbuf = reinterpret_cast<float*>(ws);  // running sum of the branch scores
+  unsigned char* rest = reinterpret_cast<unsigned char*>(ws) + sbytes;
+  size_t off = 0;
+  for (int bi = 0; bi < p.n_branch; ++bi) {
+    const NaisParams q = branch_view(p, bi);
+    const size_t b = plan_bytes_1(q, poi_begin, poi_end, precision);
+    if (!b) return NAIS_ERR_SHAPE;
+    if (plan_bytes < off + b) return NAIS_ERR_WORKSPACE;
+    const bool last = bi == p.n_branch - 1;
+    const int rc = run_1(q, cat, users, poi_begin, poi_end, k, exclude, precision, reinterpret_cast<const unsigned char*>(plan) + off, b,
+                         out_keys, out_score, out_id, last ? all_scores : sbuf, bi ? sbuf : nullptr, last, rest, ws_bytes - sbytes, stream);
+    if (rc) return rc;
+    off += b;
+  }
+  return 0;
 }
 
 // The unplanned entry: plan at the head of the workspace, prepared on every call.

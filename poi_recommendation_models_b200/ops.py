@@ -572,7 +572,7 @@ def _tensor_path_device(dev: torch.device) -> bool:
 
 def resolve_precision(lib, p, precision: str, dev: Optional[torch.device] = None) -> str:
     """"auto" = the tensor-core path with its device-side MIX/SPLIT gate ("tc_auto") wherever the model shape has one
-    (one attention branch, D and hid up to 256 in steps of 16/32 — csrc/nais_tc.cu make_geo — lat/lon or no distance mode) and the device is sm_100,
+    (every variant of model.py incl. the two-branch disentangled one; D and hid up to 256 in steps of 16/32 — csrc/nais_tc.cu make_geo) and the device is sm_100,
     else the FP32 kernel."""
     if precision != "auto":
         return precision

@@ -114,22 +114,52 @@ def test_fullrank_scores_match_oracle(variant, precision):
         assert util.cond_err(got[u], ref, scale) < PREC_TOL[precision], (u, util.cond_err(got[u], ref, scale))
 
 
-def test_fullrank_disentangled_fused_haversine():
-    """Two-branch disentangled model through the fused FP32 full-rank path: dist_km (powerLaw.dist, law of cosines in
-    float64) is formed in-kernel as a haversine of centred fp32 coordinates."""
-    U, N, beta = 4, 600, 0.5
-    data, sd, m = _fullrank_case("disentangled", U, N, seed=31, D=32, hid=32, hist_len=None, max_hist=30, min_hist=2, median_hist=10)
+@pytest.mark.parametrize("precision", ["fp32", "tc_split", "tc_mix", "tc_auto"])
+@pytest.mark.parametrize("D,hid", [(32, 32), (64, 64), (64, 128)])
+def test_fullrank_disentangled_fused_haversine(precision, D, hid):
+    """Two-branch disentangled model (model.py:467-534) through the fused full-rank paths: dist_km (powerLaw.dist, law of cosines
+    in float64) is formed in-kernel as a haversine of centred fp32 coordinates.  FP32: one kernel loops over both branches.
+    Tensor path: one scoring pass per branch, the second adds the first's scores before it ranks (csrc/nais_tc.cu
+    fullrank_tc_run)."""
+    U, N, beta = 6, 1000, 0.5
+    data, sd, m = _fullrank_case("disentangled", U, N, seed=31, D=D, hid=hid, hist_len=None, max_hist=40, min_hist=2, median_hist=14)
     sd["embed_distance.weight"] = sd["embed_distance.weight"] * 3  # make the distance bias matter (|coef*km| ~ 1)
     m.load_state_dict(sd)
     users = m.make_users(data.indptr, data.indices)
-    got = ops.fullrank_scores("disentangled", beta, m._params(), m._catalog, users).cpu().numpy()
+    got = ops.fullrank_scores("disentangled", beta, m._params(), m._catalog, users, precision=precision).cpu().numpy()
+    refs = []
     for u in range(U):
         ref, scale = util.oracle_user_scores(sd, "disentangled", beta, data.coords, data.region, data.history(u), np.arange(N))
+        refs.append(ref)
         assert util.cond_err(got[u], ref, scale) < util.TOL, (u, util.cond_err(got[u], ref, scale))
-    s, ids = m.predict_topk(users, 10)
+    s, ids = m.predict_topk(users, 10, precision=precision)
     assert ids.shape == (U, 10) and (ids >= 0).all()
-    with pytest.raises(RuntimeError):
-        m.predict_topk(users, 10, precision="tc_split")
+    for u in range(U):
+        ref = 1.0 / (1.0 + np.exp(-refs[u]))
+        ref[data.history(u)] = -1.0
+        util.lists_equal_outside_ties(ids[u].cpu().numpy(), s[u].cpu().numpy(), dict(enumerate(ref.tolist())), 10)
+
+
+def test_fullrank_disentangled_auto_takes_the_tensor_path_and_shards():
+    """precision="auto" resolves to tc_auto for the two-branch model too; two POI-range shards merge to the unsharded list."""
+    U, N, beta, k = 5, 3000, 0.5, 20
+    data, sd, m = _fullrank_case("disentangled", U, N, seed=33, D=64, hid=64, hist_len=None, max_hist=60, min_hist=3, median_hist=20)
+    assert m.ranking_plan("auto").precision == "tc_auto"
+    users = m.make_users(data.indptr, data.indices)
+    s0, i0 = m.predict_topk(users, k)
+    s1, i1 = m.predict_topk(users, k, precision="fp32")
+    for u in range(U):
+        ref, _ = util.oracle_user_scores(sd, "disentangled", beta, data.coords, data.region, data.history(u), np.arange(N))
+        ref = 1.0 / (1.0 + np.exp(-ref))
+        ref[data.history(u)] = -1.0
+        util.lists_equal_outside_ties(i0[u].cpu().numpy(), s0[u].cpu().numpy(), dict(enumerate(ref.tolist())), k)
+        util.lists_equal_outside_ties(i1[u].cpu().numpy(), s1[u].cpu().numpy(), dict(enumerate(ref.tolist())), k)
+    cut = 1408  # a tile boundary is not required
+    sa, ia = m.predict_topk(users, k, poi_begin=0, poi_end=cut)
+    sb, ib = m.predict_topk(users, k, poi_begin=cut, poi_end=N)
+    both_s, both_i = torch.cat([sa, sb], 1), torch.cat([ia, ib], 1)
+    order = torch.argsort(both_s, dim=1, descending=True, stable=True)[:, :k]
+    assert torch.equal(torch.gather(both_i, 1, order), i0) and torch.equal(torch.gather(both_s, 1, order), s0)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tc_split", "tc_mix", "tc_auto"])
