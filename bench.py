@@ -794,7 +794,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=list(WORKLOADS))
     ap.add_argument("--precision", default=os.environ.get("NAIS_BENCH_PRECISION", "tc_auto"),
-                    choices=["fp32", "tc_auto", "tc_split", "tc_mix", "tc_fast"])
+                    choices=["fp32", "tc_auto", "tc_split", "tc_mix", "tc_fast", "tc_auto_onecta", "tc_mix_onecta", "tc_split_onecta"])
     ap.add_argument("--users-per-step", type=int, default=0)
     ap.add_argument("--mode", default="eval", choices=["eval", "train"], help="eval = headline full-rank metric; train = C3 BPR fwd+bwd (triples/s)")
     ap.add_argument("--cpu-users", type=int, default=4, help="users in the bounded CPU-baseline sample")
@@ -829,13 +829,14 @@ def main():
         return
 
     U, N, H, D, hid, k = cfg["users"], cfg["pois"], cfg["hist"], cfg["D"], cfg["hid"], cfg["k"]
-    ups = args.users_per_step or max(148, int({"fp32": 296, "tc_auto": 2368, "tc_split": 2368, "tc_mix": 2368, "tc_fast": 4736}[args.precision] * min(1.0, 40000 / N)))
+    ups = args.users_per_step or max(148, int({"fp32": 296, "tc_fast": 4736}.get(args.precision, 2368) * min(1.0, 40000 / N)))
     ups = min(ups, U)
     n_batches = min(args.steps + args.warmup, max(1, U // ups))
     m, hist_np = make_eval(cfg, dev, n_batches * ups)
     res = time_eval(m, hist_np, cfg, ups, args.steps, args.warmup, args.precision, rank, world, local, dev, lib, sample_clocks=True)
-    eff, choice = args.precision, None
-    if args.precision == "tc_auto":  # the device-side gate picked MIX or SPLIT (no host sync inside the timed regions)
+    prec_base = args.precision[:-7] if args.precision.endswith("_onecta") else args.precision  # "_onecta": one CTA per SM instead of CTA pairs, same math
+    eff, choice = prec_base, None
+    if prec_base == "tc_auto":  # the device-side gate picked MIX or SPLIT (no host sync inside the timed regions)
         plan = next(iter(m._plans.values()), None)
         choice = plan.tc_choice() if plan is not None else None
         eff = "tc_mix" if choice and choice["use_mix"] else "tc_split"
@@ -858,7 +859,7 @@ def main():
     del res, ranker
     if not args.no_blocks and args.config == "C2":
         # ---- the fp32-grade path on the same workload ----------------------------------------------------------------------
-        if args.precision == "tc_auto":
+        if prec_base == "tc_auto":
             r2 = time_eval(m, hist_np, cfg, ups, min(3, args.steps), 1, "tc_split", rank, world, local, dev, lib, e2e=False, parity_users=0)
             if rank == 0:
                 line["value_exact"] = {"value": r2["users_per_s"], "unit": "users/s", "precision": "tc_split", "dtype": DTYPES["tc_split"],
@@ -875,8 +876,8 @@ def main():
         if rank == 0:
             rk = r4["ranker"]
             plan4 = next(iter(m4._plans.values()), None)
-            ch4 = plan4.tc_choice() if (plan4 is not None and args.precision == "tc_auto") else None
-            eff4 = ("tc_mix" if ch4 and ch4["use_mix"] else "tc_split") if args.precision == "tc_auto" else args.precision
+            ch4 = plan4.tc_choice() if (plan4 is not None and prec_base == "tc_auto") else None
+            eff4 = ("tc_mix" if ch4 and ch4["use_mix"] else "tc_split") if prec_base == "tc_auto" else prec_base
             line["c4"] = {"metric": "fullrank_eval_users_per_sec", "value": r4["users_per_s"], "unit": "users/s",
                           "pair_scores_per_sec": r4["users_per_s"] * c4["pois"], "ms_per_step": r4["ms_per_step"], "n_gpus": world,
                           "steps": c_steps, "warmup": c_warm, "scaling": "strong",

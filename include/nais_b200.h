@@ -57,6 +57,13 @@ extern "C" {
  * (D = hid = 32 / 64 / 128).  Same math, another epilogue instruction order (results agree to fp32 rounding); the parity
  * suite uses it to cover both code paths. */
 #define NAIS_PREC_FLAG_GENERIC 0x100
+/* The D = hid = 64 compile-time-shape kernels (one branch, no NAIS_DIST_KM, at least two groups of candidate tiles in the range)
+ * run on CTA PAIRS by default (tcgen05 cta_group::2: the two SMs of a TPC execute one M = 256 MMA per step and each stages half of
+ * every user-operand chunk; +3.5 % users/s at the 1 kW power cap).  OR this flag into `precision` to keep one CTA
+ * per SM: bit-identical results (same products, same summation order per accumulator element); the parity suite compares the two.
+ * A plan prepared with the flag may only be used with the flag (the pair kernels pad the candidate image to an even number of
+ * tile groups); a plan prepared without it serves both. */
+#define NAIS_PREC_FLAG_ONE_CTA 0x200
 
 /* NaisParams::pairs_precision — which kernels nais_pairs_forward / nais_pairs_backward[_adagrad] run */
 #define NAIS_PAIRS_AUTO 0 /* tcgen05 kernels wherever the shape has them (see the entry points), FP32 CUDA-core kernels elsewhere */

@@ -12,7 +12,9 @@ PREC_FP32, PREC_TC_SPLIT, PREC_TC_FAST, PREC_TC_MIX, PREC_TC_AUTO = 0, 1, 2, 3, 
 PREC_FLAG_GENERIC = 0x100  # run-time-shape tensor kernel even where a compile-time-shape instantiation exists
 PRECISIONS = {"fp32": PREC_FP32, "tc_split": PREC_TC_SPLIT, "tc_fast": PREC_TC_FAST, "tc_mix": PREC_TC_MIX,
               "tc_auto": PREC_TC_AUTO}
+PREC_FLAG_ONE_CTA = 0x200  # keep one CTA per SM where the CTA-pair (cta_group::2) kernel would run (D = hid = 64)
 PRECISIONS.update({k + "_generic": v | PREC_FLAG_GENERIC for k, v in list(PRECISIONS.items()) if k != "fp32"})
+PRECISIONS.update({k + "_onecta": v | PREC_FLAG_ONE_CTA for k, v in list(PRECISIONS.items()) if k in ("tc_auto", "tc_split", "tc_mix")})
 PAIRS_PRECISIONS = {"auto": 0, "fp32": 1, "tc": 2}  # NAIS_PAIRS_*
 ERR_INDEX = -7
 

@@ -325,7 +325,7 @@ static int check_fullrank(const NaisParams* p, const NaisCatalog* cat, const Nai
   if (work && need_reg && (!cat->region || !users->region)) return NAIS_ERR_NULL;
   if (work && p->dist_mode != NAIS_DIST_NONE && (!cat->coords || !users->coords)) return NAIS_ERR_NULL;
   const int prec = precision & NAIS_PREC_MASK;
-  if (precision & ~(NAIS_PREC_MASK | NAIS_PREC_FLAG_GENERIC)) return NAIS_ERR_MODE;
+  if (precision & ~(NAIS_PREC_MASK | NAIS_PREC_FLAG_GENERIC | NAIS_PREC_FLAG_ONE_CTA)) return NAIS_ERR_MODE;
   if (prec < NAIS_PREC_FP32 || prec > NAIS_PREC_TC_AUTO) return NAIS_ERR_MODE;
   if (prec != NAIS_PREC_FP32 && !tc_supported(*p, precision)) return NAIS_ERR_SHAPE;
   return 0;

@@ -48,12 +48,13 @@ constexpr int EPI_WARPS = 16;    // two groups of 8 alternate steps
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int ARRIVE_WARPS = 8;  // warps that arrive per step on e_full / acc_empty (one group)
 constexpr int THREADS = (EPI_WARPS + 2) * 32;
-constexpr int MAX_STAGES = 3;
+constexpr int MAX_STAGES = 4;
 constexpr int SORTN = 512;
 constexpr int HMETA = 512;      // history items whose id/coords are staged in smem per item (longer ones: __ldg)
 
 struct Geo {
   int D, hid, lanes, split;
+  int pair;      // CTA pairs (cta_group::2, the headline shape only): a stage holds this CTA's HALF of a B chunk (rows [rank * nrow/2, +nrow/2))
   int km;        // NAIS_DIST_KM: logit += haversine_km(h, j) * sum_d embed_distance[0, d] in the (run-time-shape) epilogue
   int mix;       // NAIS_PREC_TC_MIX: lo section of A tiles / B chunks = e5m2(hi) | e5m2(lo) byte planes, two ext k-chunks
   int kx;        // D / 8 x k-chunks
@@ -85,6 +86,7 @@ __host__ inline bool make_geo(const NaisParams& p, int precision, Geo& g) {
   g.lanes = p.dist_mode == NAIS_DIST_LATLON ? 2 : 0;
   g.split = precision == NAIS_PREC_TC_SPLIT;
   g.mix = precision == NAIS_PREC_TC_MIX;
+  g.pair = 0;
   g.km = p.dist_mode == NAIS_DIST_KM ? 1 : 0;
   if (g.km && p.dist_buckets != 1) return false;
   if (precision == NAIS_PREC_TC_AUTO) {  // MIX geometry where an e5m2 K-step exists, else SPLIT (same image sizes)
@@ -384,12 +386,15 @@ __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g_mix, Geo 
       __half hi[8], lo[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) split_f16(v[e], hi[e], lo[e]);
-      // image = [part][hi plane | lo section][k-chunk in part][row][16 B]; one part = one bulk copy = one smem stage
+      // image = [part][hi plane | lo section][k-chunk in part][row][16 B]; one part = one bulk copy = one smem stage.
+      // g.pair (kp == 1): [half][hi plane | lo section][k-chunk][row % (nrow/2)][16 B] — each CTA of a pair copies its half
       const int part = g.kp == 1 ? 0 : min(c / g.kc_part, g.kp - 1);
       const int cp = c - part * g.kc_part;                          // k-chunk inside the part
       const int nkc = g.kc_part + (part == g.kp - 1 ? 1 + g.mix : 0);  // the last part also holds the ext k-chunk(s)
-      unsigned char* pb = cb + (size_t)part * g.part_bytes;
-      unsigned char* lb = pb + (size_t)nkc * g.nrow * 16;
+      const int nrw = g.pair ? g.nrow / 2 : g.nrow;                 // rows of an image plane
+      const int nn = g.pair ? n % nrw : n;                          // row inside it
+      unsigned char* pb = cb + (size_t)part * g.part_bytes + (g.pair ? (size_t)(n / nrw) * (g.b_chunk / 2) : 0);
+      unsigned char* lb = pb + (size_t)nkc * nrw * 16;
       if (g.mix && c == g.kx) {
         // ext step of the MIX mode, ONE fp16 MMA over 16 K slots with the split inside (w = lane / bias weights * sBe):
         //   chunk e0: [2hs+l] = hi(w_l)   [4] = hi(w_b)  [5] = lo(w_b)        A_ext: [2hs+l] = hi(g_l)  [4] = [5] = sAe
@@ -422,17 +427,17 @@ __global__ void pack_users_kernel(NaisParams p, NaisUsers users, Geo g_mix, Geo 
           e1[4 + 2 * hs] = l0;
           e1[5 + 2 * hs] = l1;
         }
-        *reinterpret_cast<uint4*>(pb + ((size_t)cp * g.nrow + n) * 16) = *reinterpret_cast<uint4*>(e0);
-        *reinterpret_cast<uint4*>(pb + ((size_t)(cp + 1) * g.nrow + n) * 16) = *reinterpret_cast<uint4*>(e1);
+        *reinterpret_cast<uint4*>(pb + ((size_t)cp * nrw + nn) * 16) = *reinterpret_cast<uint4*>(e0);
+        *reinterpret_cast<uint4*>(pb + ((size_t)(cp + 1) * nrw + nn) * 16) = *reinterpret_cast<uint4*>(e1);
         continue;
       }
-      *reinterpret_cast<uint4*>(pb + ((size_t)cp * g.nrow + n) * 16) = *reinterpret_cast<uint4*>(hi);
+      *reinterpret_cast<uint4*>(pb + ((size_t)cp * nrw + nn) * 16) = *reinterpret_cast<uint4*>(hi);
       if (g.mix) {
-        unsigned char* b8 = lb + ((size_t)(cp >> 1) * g.nrow + n) * 16 + (cp & 1) * 8;
+        unsigned char* b8 = lb + ((size_t)(cp >> 1) * nrw + nn) * 16 + (cp & 1) * 8;
         *reinterpret_cast<uint2*>(b8) = pack_e5m2(hi);
-        *reinterpret_cast<uint2*>(b8 + (size_t)(g.kc_part / 2) * g.nrow * 16) = pack_e5m2(lo);
+        *reinterpret_cast<uint2*>(b8 + (size_t)(g.kc_part / 2) * nrw * 16) = pack_e5m2(lo);
       } else if (g.split) {
-        *reinterpret_cast<uint4*>(lb + ((size_t)cp * g.nrow + n) * 16) = *reinterpret_cast<uint4*>(lo);
+        *reinterpret_cast<uint4*>(lb + ((size_t)cp * nrw + nn) * 16) = *reinterpret_cast<uint4*>(lo);
       } else if (n >= aux0 && n < aux0 + 16) {
         *reinterpret_cast<uint4*>(lb + ((size_t)cp * 16 + (n - aux0)) * 16) = *reinterpret_cast<uint4*>(lo);
       }
@@ -455,8 +460,9 @@ struct MainArgs {
   NaisUsers users;
   Geo g;
   int64_t poi_begin, poi_end;
-  int k, exclude, groups;
-  int64_t n_items;
+  int k, exclude, groups;         // groups: candidate-tile groups of the range (pair kernels: rounded up to even, see groups_real)
+  int groups_real;                // groups that exist (the key lists have this many per user)
+  int64_t n_items;                // (user, group) items; pair kernels: (user, pair of groups) items
   const unsigned char* hdr;
   const unsigned char* Pimg;
   const unsigned char* Bimg;
@@ -504,7 +510,13 @@ __device__ __forceinline__ unsigned long long warp_fold_top32(unsigned long long
 // kS: the static shape D = hid = kS of kFix 1 / 2 (64: the headline workload; 32: the small end of the C5 sweep).
 template <bool kSinglePart, int kHch, int kFix, int kS = 64>
 __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_constant__ MainArgs A) {
-  constexpr bool kFastEpi = kFix == 1 || kFix == 2;
+  // kFix == 5 / 6: kFix 1 / 2 on CTA PAIRS (cta_group::2): the two CTAs of a cluster score the same user against two neighbouring
+  // groups of candidate tiles with ONE M = 256 MMA per step — each supplies its 128 candidates (A) and HALF of the user's chunk (B)
+  // from its own shared memory, which takes the operand traffic per MMA from 8.7 KB to 6.3 KB per SM (the measured limiter of the
+  // one-CTA kernel: 94 % of the shared-memory port, tensor pipe 77 % active).  Rank 0 issues; rank 1's MMA warp relays "my operands
+  // have landed" to rank 0's barriers; commits are multicast to both; the epilogue warps of both arrive on rank 0's e_full / acc_empty.
+  constexpr bool kPair = kFix == 5 || kFix == 6;
+  constexpr bool kFastEpi = kFix == 1 || kFix == 2 || kPair;
   // kFix == 3: D = hid = 128 (the reference's default, run.py:837-838) in SPLIT / MIX: the generic code paths below with the
   // shape constants known at compile time, so the K-part / K-step loops of the issuer unroll and its descriptors fold
   constexpr bool kD128 = kFix == 3;
@@ -533,6 +545,13 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
   uint64_t* acc_empty = acc_full + 2 * NBUF;             // [NBUF] accumulator drained
   uint32_t* tslot = reinterpret_cast<uint32_t*>(acc_empty + NBUF);
   float* hm_cos = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 384);  // [HMETA] (g.km only)
+  uint64_t* a_full_peer = reinterpret_cast<uint64_t*>(tslot + 2);  // (pair kernels, rank 0) rank 1's A tiles / B half have landed
+  uint64_t* b_full_peer = a_full_peer + 1;                         // [MAX_STAGES]
+  uint32_t crank = 0;                                              // rank in the CTA pair
+  if constexpr (kPair) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  // one (user, group) item per CTA and iteration; a pair takes the two neighbouring groups 2 * (item % groups/2) + rank
+  const int64_t item0 = kPair ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x, item_step = kPair ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
+  const int groups_it = kPair ? A.groups / 2 : A.groups;  // items per user
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const Scales sc = *reinterpret_cast<const Scales*>(A.hdr + 64);
@@ -557,17 +576,25 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       mbar_init(&b_empty[i], 1);
     }
     for (int i = 0; i < NBUF; ++i) {
-      mbar_init(&e_full[i], ARRIVE_WARPS);
+      mbar_init(&e_full[i], kPair ? 2 * ARRIVE_WARPS : ARRIVE_WARPS);
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_full[NBUF + i], 1);
-      mbar_init(&acc_empty[i], ARRIVE_WARPS);
+      mbar_init(&acc_empty[i], kPair ? 2 * ARRIVE_WARPS : ARRIVE_WARPS);
+    }
+    if (kPair) {
+      mbar_init(a_full_peer, 1);
+      for (int i = 0; i < MAX_STAGES; ++i) mbar_init(&b_full_peer[i], 1);
     }
     fence_barrier_init();
   }
-  if (warp == EPI_WARPS) tmem_alloc(tslot, 512);
+  if (warp == EPI_WARPS) {
+    if constexpr (kPair) tmem_alloc2(tslot, 512);
+    else tmem_alloc(tslot, 512);
+  }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();  // both CTAs' barriers exist before anybody arrives on the other's
   tc_fence_after();
   const uint32_t tmem = *tslot;
 
@@ -580,8 +607,8 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
     // (warp-uniform control flow, one elected lane issues; see the MMA warp)
     {
       uint32_t it_n = 0, bstep = 0;  // it_n counts the items this pass processes (all three roles skip the same ones)
-      for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x) {
-        const int u = (int)(item / A.groups), grp = (int)(item % A.groups);
+      for (int64_t item = item0; item < A.n_items; item += item_step) {
+        const int u = (int)(item / groups_it), grp = kPair ? 2 * (int)(item % groups_it) + (int)crank : (int)(item % groups_it);
         if (!user_in_pass(A.gate, sc.use_mix, (int)(A.users.offsets[u + 1] - A.users.offsets[u]))) continue;
         const uint32_t it = it_n++;
         const int64_t cbu = __shfl_sync(0xffffffffu, chunk_base(A.users.offsets, u, kHch, hsplit) - cb0, 0);
@@ -593,12 +620,12 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
             bulk_g2s(sA + (size_t)t * g.a_tile, A.Pimg + ((size_t)grp * tpc + t) * g.a_tile, (uint32_t)g.a_tile, a_full);
         }
         __syncwarp();
-        const unsigned char* src = A.Bimg + (size_t)cbu * g.b_chunk;
+        const unsigned char* src = A.Bimg + (size_t)cbu * g.b_chunk + (kPair ? (size_t)crank * (g.b_chunk / 2) : 0);
         for (int c = 0; c < nchunks; ++c) {
           const int kp_t = kSinglePart ? 1 : g.kp;
           for (int pp = 0; pp < kp_t; ++pp, ++bstep) {
             const int st = bstep % g.stages;
-            const uint32_t bytes = (uint32_t)(pp == kp_t - 1 ? g.part_last_bytes : g.part_bytes);
+            const uint32_t bytes = kPair ? (uint32_t)(g.b_chunk / 2) : (uint32_t)(pp == kp_t - 1 ? g.part_last_bytes : g.part_bytes);
             mbar_wait(&b_empty[st], ((bstep / g.stages) & 1) ^ 1);
             if (elect_one()) {
               mbar_expect_tx(&b_full[st], bytes);
@@ -621,14 +648,28 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
     // parts, the ext K-step and the commit come with the last part.
     if constexpr (kFastEpi) {
       // ---- static issuer: D = hid = kS, N = 2 kS + 16, K-steps kS/16 (fp16) + 1 (ext) [+ 2 x kS/32 e5m2], stages = 2, buffer == tile ----
-      constexpr bool kMix = kFix == 2;
+      constexpr bool kMix = kFix == 2 || kFix == 6;
+      constexpr uint32_t kStages = kPair ? 4u : 2u;  // B ring depth (== g.stages); pairs: half-chunk stages, same bytes in flight
       constexpr uint32_t kKx = kS / 8, kK16 = kS / 16, kK32 = kS / 32;               // x k-chunks, fp16 / e5m2 K-steps
-      constexpr uint32_t kNrow = 2 * kS + 16, kALbo = TM * 16, kBLbo = kNrow * 16;  // 144 (kS = 64) / 80 (32)
+      constexpr uint32_t kNrow = 2 * kS + 16, kALbo = TM * 16;                       // 144 (kS = 64) / 80 (32)
+      constexpr uint32_t kBLbo = (kPair ? kNrow / 2 : kNrow) * 16;                  // rows of a B image plane in THIS CTA's stage
       constexpr uint32_t kAStep = (2 * kALbo) >> 4, kBStep = (2 * kBLbo) >> 4;      // one K-step = two 16-byte k-chunks
       constexpr uint32_t kAPlane = kKx * TM * 16, kATile = (2 * kAPlane) >> 4;      // (16-byte units)
-      constexpr uint32_t kStage = (2 * (kKx + 1) * kNrow * 16) >> 4;
+      constexpr uint32_t kStage = (2 * (kKx + 1) * kBLbo) >> 4;
       constexpr uint32_t kExtBuf = (2 * TM * 16) >> 4;
-      constexpr uint32_t idN = idesc_f16(TM, kNrow), idN8 = idesc_e5m2(TM, kNrow);
+      constexpr uint32_t idN = idesc_f16(kPair ? 2 * TM : TM, kNrow), idN8 = idesc_e5m2(kPair ? 2 * TM : TM, kNrow);
+      auto mmaH = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+        if constexpr (kPair) mma2_f16(d, a, b, id, acc);
+        else mma_f16(d, a, b, id, acc);
+      };
+      auto mmaQ = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+        if constexpr (kPair) mma2_f8(d, a, b, id, acc);
+        else mma_f8(d, a, b, id, acc);
+      };
+      auto commit = [](uint64_t* bar) {
+        if constexpr (kPair) mma2_commit_multicast(bar, 3);
+        else mma_commit(bar);
+      };
       const uint32_t zaddr = smem_u32(sZ);
       const uint32_t hi_word = (uint32_t)(smem_desc(0, 0, 128) >> 32);  // SBO = 128 B, version 1, no swizzle
       auto lo_of = [](uint32_t addr, uint32_t lbo) { return ((addr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); };
@@ -645,14 +686,30 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
       const uint32_t Bx_hi = lo_of(sb0 + kKx * kBLbo, zaddr - (sb0 + kKx * kBLbo));                  // split: ext chunk of the hi plane
       const uint32_t Bx_lo = lo_of(sb0 + (2 * kKx + 1) * kBLbo, zaddr - (sb0 + (2 * kKx + 1) * kBLbo));  //  ... of the lo plane
       uint32_t it_n = 0, cc = 0, st = 0, stph = 0;
-      for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x) {
-        const int u = (int)(item / A.groups);
+      for (int64_t item = item0; item < A.n_items; item += item_step) {
+        const int u = (int)(item / groups_it);
         if (!user_in_pass(A.gate, sc.use_mix, (int)(A.users.offsets[u + 1] - A.users.offsets[u]))) continue;
         const uint32_t it = it_n++;
         const int nchunks = __shfl_sync(0xffffffffu, user_chunks(A.users.offsets, u, kHch, cb0, A.max_chunks, hsplit), 0);
         mbar_wait(a_full, it & 1);
+        if constexpr (kPair) {
+          if (crank != 0) {  // rank 1: nothing to issue — tell rank 0 when this CTA's A tiles / B halves have landed
+            if (elect_one()) mbar_arrive_cluster(a_full_peer, 0);
+            __syncwarp();
+            for (int c = 0; c < nchunks; ++c) {
+              mbar_wait(&b_full[st], stph);
+              if (elect_one()) mbar_arrive_cluster(&b_full_peer[st], 0);
+              __syncwarp();
+              st = (st + 1u) % kStages;
+              stph ^= (st == 0);
+            }
+            continue;
+          }
+          mbar_wait_cluster(a_full_peer, it & 1);
+        }
         for (int c = 0; c < nchunks; ++c, ++cc) {
           mbar_wait(&b_full[st], stph);
+          if constexpr (kPair) mbar_wait_cluster(&b_full_peer[st], stph);
           const uint32_t cph = cc & 1u;
           const uint32_t bh = B_hi + st * kStage;
           const uint32_t bxh = Bx_hi + st * kBz, bxl = Bx_lo + st * kBz;
@@ -661,39 +718,44 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
           for (int t = 0; t < TPC; ++t) {
             const uint32_t d_t = tmem + t * ACC_STRIDE;
             const uint32_t ah = A_hi + t * kATile, al = A_lo + t * kATile, al8 = A_l8 + t * kATile;
-            mbar_wait(&acc_empty[t], cph ^ 1u);
-            mbar_wait(&e_full[t], cph);
+            if constexpr (kPair) {  // (arrivals come from both CTAs' epilogue warps)
+              mbar_wait_cluster(&acc_empty[t], cph ^ 1u);
+              mbar_wait_cluster(&e_full[t], cph);
+            } else {
+              mbar_wait(&acc_empty[t], cph ^ 1u);
+              mbar_wait(&e_full[t], cph);
+            }
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
-              for (int s2 = 0; s2 < (int)kK16; ++s2) mma_f16(d_t, mk(ah + s2 * kAStep), mk(bh + s2 * kBStep), idN, s2 != 0);
+              for (int s2 = 0; s2 < (int)kK16; ++s2) mmaH(d_t, mk(ah + s2 * kAStep), mk(bh + s2 * kBStep), idN, s2 != 0);
               if constexpr (kMix) {
-                mma_f16(d_t, mk(E_mx + t * kExtBuf), mk(bh + kK16 * kBStep), idN, 1);            // ext: hi-plane chunks kKx, kKx + 1
+                mmaH(d_t, mk(E_mx + t * kExtBuf), mk(bh + kK16 * kBStep), idN, 1);            // ext: hi-plane chunks kKx, kKx + 1
                 constexpr uint32_t b8h = ((kKx + 2) * kBLbo) >> 4, b8l = ((kKx + 2 + kKx / 2) * kBLbo) >> 4;  // e5m2(hi) / e5m2(lo) planes
 #pragma unroll
-                for (int s8 = 0; s8 < (int)kK32; ++s8) mma_f8(d_t, mk(al + s8 * kAStep), mk(bh + b8l + s8 * kBStep), idN8, 1);
+                for (int s8 = 0; s8 < (int)kK32; ++s8) mmaQ(d_t, mk(al + s8 * kAStep), mk(bh + b8l + s8 * kBStep), idN8, 1);
 #pragma unroll
-                for (int s8 = 0; s8 < (int)kK32; ++s8) mma_f8(d_t, mk(al8 + s8 * kAStep), mk(bh + b8h + s8 * kBStep), idN8, 1);
+                for (int s8 = 0; s8 < (int)kK32; ++s8) mmaQ(d_t, mk(al8 + s8 * kAStep), mk(bh + b8h + s8 * kBStep), idN8, 1);
               } else {
                 constexpr uint32_t blo = ((kKx + 1) * kBLbo) >> 4;                                // lo plane
-                mma_f16(d_t, mk(E_hi + t * kEz), mk(bxh), idN, 1);
+                mmaH(d_t, mk(E_hi + t * kEz), mk(bxh), idN, 1);
 #pragma unroll
-                for (int s2 = 0; s2 < (int)kK16; ++s2) mma_f16(d_t, mk(ah + s2 * kAStep), mk(bh + blo + s2 * kBStep), idN, 1);
-                mma_f16(d_t, mk(E_hi + t * kEz), mk(bxl), idN, 1);
+                for (int s2 = 0; s2 < (int)kK16; ++s2) mmaH(d_t, mk(ah + s2 * kAStep), mk(bh + blo + s2 * kBStep), idN, 1);
+                mmaH(d_t, mk(E_hi + t * kEz), mk(bxl), idN, 1);
 #pragma unroll
-                for (int s2 = 0; s2 < (int)kK16; ++s2) mma_f16(d_t, mk(al + s2 * kAStep), mk(bh + s2 * kBStep), idN, 1);
-                mma_f16(d_t, mk(E_lo + t * kEz), mk(bxh), idN, 1);
+                for (int s2 = 0; s2 < (int)kK16; ++s2) mmaH(d_t, mk(al + s2 * kAStep), mk(bh + s2 * kBStep), idN, 1);
+                mmaH(d_t, mk(E_lo + t * kEz), mk(bxh), idN, 1);
               }
-              mma_commit(&accf[t]);
+              commit(&accf[t]);
             }
             __syncwarp();
           }
-          if (elect_one()) mma_commit(&b_empty[st]);
+          if (elect_one()) commit(&b_empty[st]);
           __syncwarp();
-          st ^= 1u;
+          st = (st + 1u) % kStages;
           stph ^= (st == 0);
         }
-        if (elect_one()) mma_commit(a_empty);
+        if (elect_one()) commit(a_empty);
         __syncwarp();
       }
     } else
@@ -845,8 +907,12 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
     const int nposb = npos >> 4, nposm = npos & 15;
     const float* sgn_mixed = xch;  // [16] +-1 of the one 16-column block that holds both signs (xch is unused when hch == 2)
 
-    for (int64_t item = blockIdx.x; item < A.n_items; item += gridDim.x) {
-      const int u = (int)(item / A.groups), grp = (int)(item % A.groups);
+    auto arrive_mma = [&](uint64_t* bar) {  // a barrier the MMA issuer waits on: rank 0's in a pair
+      if constexpr (kPair) mbar_arrive_cluster(bar, 0);
+      else mbar_arrive(bar);
+    };
+    for (int64_t item = item0; item < A.n_items; item += item_step) {
+      const int u = (int)(item / groups_it), grp = kPair ? 2 * (int)(item % groups_it) + (int)crank : (int)(item % groups_it);
       const int64_t hb = A.users.offsets[u];
       const int H = (int)(A.users.offsets[u + 1] - hb);
       if (!user_in_pass(A.gate, sc.use_mix, H)) continue;
@@ -903,7 +969,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
           if (g.mix) *reinterpret_cast<__half2*>(eb + TM * 16 + 8) = hi2;
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&e_full[t]);
+          if (lane == 0) arrive_mma(&e_full[t]);
         };
         auto hist_coords = [&](int h, float& la, float& lo) {
           if (h < HMETA) {
@@ -987,7 +1053,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[t]);
+            if (lane == 0) arrive_mma(&acc_empty[t]);
             if constexpr (kS == 64) {
               blk(va, 2);
               blk(vb, 3);
@@ -1218,7 +1284,7 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
         if (warp == 0) {
           unsigned long long a = warp_fold_top32(keys[lane], keys[32 + lane], lane);
           a = warp_fold_top32(a, warp_fold_top32(keys[64 + lane], keys[96 + lane], lane), lane);
-          if (lane < A.k) A.part_keys[((size_t)u * A.groups + grp) * A.k + lane] = a;
+          if (lane < A.k && grp < A.groups_real) A.part_keys[((size_t)u * A.groups_real + grp) * A.k + lane] = a;
         }
         continue;  // (the next item's first epi_bar orders these reads of `keys` before its writes)
       }
@@ -1239,13 +1305,18 @@ __global__ void __launch_bounds__(THREADS, 1) fullrank_tc_kernel(const __grid_co
           epi_bar();
         }
       }
-      for (int i = tid; i < A.k; i += EPI_THREADS) A.part_keys[((size_t)u * A.groups + grp) * A.k + i] = keys[i];
+      if (grp < A.groups_real)
+        for (int i = tid; i < A.k; i += EPI_THREADS) A.part_keys[((size_t)u * A.groups_real + grp) * A.k + i] = keys[i];
     }
   }
   // ---- teardown ---------------------------------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == EPI_WARPS) tmem_dealloc(tmem, 512);
+  if constexpr (kPair) cluster_sync_all();  // nobody leaves while the other CTA may still signal it or read its operands
+  if (warp == EPI_WARPS) {
+    if constexpr (kPair) tmem_dealloc2(tmem, 512);
+    else tmem_dealloc(tmem, 512);
+  }
 }
 
 
@@ -1268,6 +1339,9 @@ static inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 struct PlanLayout {
   tc::Geo g, gs;       // geometry of the single pass / of AUTO's MIX pass; gs: AUTO's SPLIT pass
   bool two_pass;       // NAIS_PREC_TC_AUTO on a shape that has a MIX geometry
+  bool pair;           // the shape has the CTA-pair kernel (and NAIS_PREC_FLAG_ONE_CTA is not set): the candidate image is padded to
+                       // an even number of tile groups
+  tc::Geo gp, gsp;     // g / gs with the pair kernels' half-chunk stage geometry
   int groups, n_tiles_pad;
   size_t hdr, pimg, pimg2, total;
 };
@@ -1290,7 +1364,22 @@ static bool plan_layout(const NaisParams& p, int64_t poi_begin, int64_t poi_end,
   const int64_t tiles = (range + tc::TM - 1) / tc::TM;
   L.groups = (int)((tiles + L.g.tpc - 1) / L.g.tpc);
   if (L.groups < 1) L.groups = 1;
-  L.n_tiles_pad = L.groups * L.g.tpc;
+  // CTA pairs: the D = hid = 64 compile-time-shape kernels only; a stage then holds half a chunk
+  auto pair_shape = [](const tc::Geo& q) {
+    return q.D == 64 && q.hid == 64 && q.nrow == 144 && q.kp == 1 && q.hch == 2 && q.stages == 2 && !q.km && (q.mix || q.split);
+  };
+  L.pair = !(precision & (NAIS_PREC_FLAG_ONE_CTA | NAIS_PREC_FLAG_GENERIC)) && pair_shape(L.g) && pair_shape(L.gs) && L.groups >= 2;
+  L.gp = L.g;
+  L.gsp = L.gs;
+  if (L.pair)
+    for (tc::Geo* q : {&L.gp, &L.gsp}) {
+      q->pair = 1;
+      q->smem_bytes -= q->stages * q->stage_bytes;
+      q->stage_bytes = q->b_chunk / 2;
+      q->stages = 4;  // half-chunk stages: the same bytes in flight as the one-CTA kernel's two, twice the look-ahead (the relay of
+      q->smem_bytes += q->stages * q->stage_bytes;  // "landed" and the multicast of "free" each cost a trip between the SMs)
+    }
+  L.n_tiles_pad = (L.pair ? (L.groups + 1) / 2 * 2 : L.groups) * L.g.tpc;
   size_t o = 0;
   L.hdr = o;
   o += tc::HDR_BYTES;
@@ -1441,6 +1530,7 @@ static MainKernel pick_kernel(const tc::Geo& gg, bool generic) {
   const bool s64 = gg.D == 64 && gg.hid == 64 && gg.nrow == 144, s32 = gg.D == 32 && gg.hid == 32 && gg.nrow == 80;
   if (gg.km) generic = true;  // the haversine bias lives in the run-time-shape epilogue only
   const int fix = ((s64 || s32) && gg.kp == 1 && gg.hch == 2 && gg.stages == 2 && !generic) ? (gg.mix ? 2 : (gg.split ? 1 : 0)) : 0;
+  if (gg.pair) return gg.mix ? tc::fullrank_tc_kernel<true, 2, 6, 64> : tc::fullrank_tc_kernel<true, 2, 5, 64>;
   if (gg.kp == 1) {
     if (gg.hch != 2) return tc::fullrank_tc_kernel<true, 1, 0>;
     if (fix == 2) return s64 ? tc::fullrank_tc_kernel<true, 2, 2, 64> : tc::fullrank_tc_kernel<true, 2, 2, 32>;
@@ -1483,13 +1573,44 @@ static int run_1(const NaisParams& p, const NaisCatalog& cat, const NaisUsers& u
     e = cudaMemsetAsync(pass_flags, 0, 8, stream);
     if (e != cudaSuccess) return (int)e;
   }
+  const bool generic = (precision & NAIS_PREC_FLAG_GENERIC) != 0;
+  // CTA pairs need two co-scheduled SMs of a TPC with the kernel's shared memory each: asked once per device (a partitioned GPU may
+  // not offer any); without them the one-CTA kernels run on the same plan (its candidate image is a superset)
+  bool use_pair = L.pair;
+  if (use_pair) {
+    static int pair_ok[64];  // 0 unknown, 1 yes, -1 no
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& st = pair_ok[dev & 63];
+    if (st == 0) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2);
+      cfg.blockDim = dim3(tc::THREADS);
+      cfg.dynamicSmemBytes = L.gp.smem_bytes;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      MainKernel kp = pick_kernel(L.gp, false);
+      int n = 0;
+      const bool ok = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, L.gp.smem_bytes) == cudaSuccess &&
+                      cudaOccupancyMaxActiveClusters(&n, kp, &cfg) == cudaSuccess && n >= 1;
+      if (!ok) cudaGetLastError();
+      st = ok ? 1 : -1;
+    }
+    use_pair = st == 1;
+  }
+  const tc::Geo& g1 = use_pair ? L.gp : L.g;
+  const tc::Geo& g2 = use_pair ? L.gsp : L.gs;
   {
     dim3 grid(users.n_users, 64);
-    tc::pack_users_kernel<<<grid, 256, 0, stream>>>(p, users, L.g, L.gs, L.two_pass ? 1 : 0, hdr, bimg, max_chunks, pass_flags,
+    tc::pack_users_kernel<<<grid, 256, 0, stream>>>(p, users, g1, g2, L.two_pass ? 1 : 0, hdr, bimg, max_chunks, pass_flags,
                                                    bad_index_flag());
     NAIS_COUNT_LAUNCH(1);
   }
-  const bool generic = (precision & NAIS_PREC_FLAG_GENERIC) != 0;
   auto run = [&](const tc::Geo& gg, const unsigned char* pimg, int gate) -> int {
     tc::MainArgs A;
     A.p = p;
@@ -1500,8 +1621,9 @@ static int run_1(const NaisParams& p, const NaisCatalog& cat, const NaisUsers& u
     A.poi_end = poi_end;
     A.k = k;
     A.exclude = exclude;
-    A.groups = L.groups;
-    A.n_items = (int64_t)users.n_users * L.groups;
+    A.groups = gg.pair ? (L.groups + 1) / 2 * 2 : L.groups;
+    A.groups_real = L.groups;
+    A.n_items = (int64_t)users.n_users * (gg.pair ? A.groups / 2 : A.groups);
     A.hdr = hdr;
     A.Pimg = pimg;
     A.Bimg = bimg;
@@ -1514,6 +1636,24 @@ static int run_1(const NaisParams& p, const NaisCatalog& cat, const NaisUsers& u
     MainKernel kern = pick_kernel(gg, generic);
     cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gg.smem_bytes);
     if (e2 != cudaSuccess) return (int)e2;
+    if (gg.pair) {  // one cluster of two CTAs (the two SMs of a TPC) per pair item
+      const int pairs = (int)(A.n_items < sms / 2 ? A.n_items : sms / 2);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * pairs);
+      cfg.blockDim = dim3(tc::THREADS);
+      cfg.dynamicSmemBytes = gg.smem_bytes;
+      cfg.stream = stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      e2 = cudaLaunchKernelEx(&cfg, kern, A);
+      NAIS_COUNT_LAUNCH(1);
+      return e2 == cudaSuccess ? 0 : (int)e2;
+    }
     const int grid = (int)(A.n_items < sms ? A.n_items : sms);
     kern<<<grid, tc::THREADS, gg.smem_bytes, stream>>>(A);
     NAIS_COUNT_LAUNCH(1);
@@ -1523,11 +1663,11 @@ static int run_1(const NaisParams& p, const NaisCatalog& cat, const NaisUsers& u
   if (L.two_pass) {
     // the MIX pass and the SPLIT pass back to back; each user belongs to one (decided on the device: the library never
     // synchronises, so the choice cannot come back to the host); a pass nobody takes is one launch that exits at once
-    rc = run(L.g, pbase + L.pimg, 1);
+    rc = run(g1, pbase + L.pimg, 1);
     if (rc) return rc;
-    rc = run(L.gs, pbase + L.pimg2, 0);
+    rc = run(g2, pbase + L.pimg2, 0);
   } else {
-    rc = run(L.g, pbase + L.pimg, -1);
+    rc = run(g1, pbase + L.pimg, -1);
   }
   if (rc || !merge) return rc;
   return launch_topk_merge_keys_multi(keys, scratch, (int64_t)L.groups * k, k, users.n_users, L.groups, k, out_keys, out_score, out_id,

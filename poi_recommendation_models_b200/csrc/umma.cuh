@@ -185,22 +185,29 @@ __device__ __forceinline__ void mma2_commit_multicast(uint64_t* bar, uint16_t ct
                "h"(cta_mask)
                : "memory");
 }
-// arrive (release at cluster scope) on the mbarrier that sits at this CTA-local address in CTA `cta` of the cluster
+// arrive on the mbarrier that sits at this CTA-local address in CTA `cta` of the cluster.  (Default semantics, like CUTLASS's
+// ClusterBarrier::arrive(cta_id): the data the signal stands for is read by the tensor core / async proxy of the SM that wrote it,
+// after the writer's own fence.proxy.async; measured: the .release.cluster / .acquire.cluster forms cost the pair kernel 40 % more
+// clocks per step.)
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");
 }
-// wait on a LOCAL mbarrier whose arrivals come from the other CTA (acquire at cluster scope)
+__device__ __forceinline__ void cluster_sync_all() {  // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// wait on a LOCAL mbarrier whose arrivals come from the other CTA
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
