@@ -28,8 +28,12 @@ def main():
     for name, n, c in sorted(rows, key=lambda r: -(r[2].get("UTCHMMA", 0) + r[2].get("UTCQMMA", 0)) * 100000 - r[1]):
         out.append(f"{name:110s} {n:7d} " + " ".join(f"{c.get(k, 0):7d}" for k in KEYS))
     out += ["", "TOTAL " + " ".join(f"{k}={tot.get(k, 0)}" for k in KEYS)]
+    # the CTA-pair forms (tcgen05 ... cta_group::2) and LDGSTS (cp.async of the pair kernels' input pipeline), whole library
+    mods = collections.Counter(re.findall(r"\b(UTC[A-Z]+(?:\.[A-Z0-9_]+)+|LDGSTS(?:\.[A-Z0-9_]+)*)", txt))
+    out += ["MODIFIERS " + " ".join(f"{k}={v}" for k, v in sorted(mods.items(), key=lambda kv: -kv[1]))]
     with open(os.path.join(ROOT, "profiles", "r2_sass_histogram.txt"), "w") as fh:
         fh.write("\n".join(out) + "\n")
+    print(out[-2])
     print(out[-1])
 
 
