@@ -695,18 +695,23 @@ def c1_block(dev, lib, no_cpu=False):
     # (a) the reference's schedule: one user per step (fused row-sparse Adagrad, batch built on the device)
     m1, o1 = fresh()
     sample = order[:256]
+    def one_user(u):  # device sampler (one segment), then the whole optimizer step in one library call (nais_pairs_train_step)
+        b_ = bt.multi_user_batch(np.array([u]), num_ng, seed=int(u))
+        return m1.fused_adagrad_step(o1, b_.label, b_)
+
     for u in sample[:8]:  # warm-up
-        h_, t_, lab_, hr_, tr_, ll_ = bt.batch(int(u), num_ng)
-        m1.fused_adagrad_step(o1, lab_, h_, t_, hr_, tr_, ll_)
+        one_user(int(u))
     torch.cuda.synchronize()
+    l0 = lib.nais_launch_count()
     t0 = time.perf_counter()
     for u in sample:
-        h_, t_, lab_, hr_, tr_, ll_ = bt.batch(int(u), num_ng)
-        m1.fused_adagrad_step(o1, lab_, h_, t_, hr_, tr_, ll_)
+        one_user(int(u))
     torch.cuda.synchronize()
     dt1 = time.perf_counter() - t0
     blk["epoch_one_user_per_step"] = {"users_per_s": len(sample) / dt1, "sample_users": int(len(sample)), "steps": int(len(sample)),
-                                      "note": "the reference's schedule (run.py:227-255): launch-bound, ~1 ms of host + kernel latency per user"}
+                                      "gpu_launches_per_step": int(lib.nais_launch_count() - l0) / len(sample),
+                                      "note": "the reference's schedule (run.py:227-255), one user per optimizer step: nais_sample_batch + "
+                                              "nais_pairs_train_step (forward, BCE, backward, Adagrad in one call); host-latency bound"}
     del m1, o1
     # (b) multi-user steps: 64 users per optimizer step, segmented layout, device sampler
     m2, o2 = fresh()

@@ -268,6 +268,27 @@ NAIS_API int nais_pairs_backward_adagrad(const NaisParams* p, const NaisPairs* b
                                 const float* row_sum, const uint64_t* act_mask, const float* dscore, const NaisGrads* grads,
                                 const NaisAdagrad* opt, void* workspace, size_t workspace_bytes, nais_stream_t stream);
 
+/* One whole optimizer step of run.py:248-254 — zero_grad, forward, sigmoid + BCELoss, backward, Adagrad.step — in ONE call (the
+ * reference's schedule is one user per step: 17 Python-level ops and ~25 launches per step make it host-bound; this is 8-12
+ * launches and one call).  loss = sum_b w_b * BCE(sigmoid(score_b), label_b) with w_b = row_weight[b], or 1/B when row_weight is
+ * NULL (the batch mean of nn.BCELoss); log terms clamped at -100 and the gradient's denominator at 1e-12 like torch.
+ * Embedding tables: row-sparse Adagrad as in nais_pairs_backward_adagrad (`tables`).  MLP / distance-layer parameters: dense
+ * Adagrad on the optimizer's state['sum'] tensors in `dense`:  sum += g*g ;  param += -lr * (g / (sqrt(sum) + eps))  (torch's
+ * update with weight_decay = lr_decay = 0).  Every parameter NaisParams points to IS written.  One branch only.
+ * loss: device float[1]; score (optional): device float[B], the pre-sigmoid scores of the forward. */
+typedef struct NaisDenseAdagrad {
+  float lr, eps;
+  float* sum_w1;
+  float* sum_b1;
+  float* sum_w2;
+  float* sum_dist_w; /* NULL unless NAIS_DIST_LATLON */
+  float* sum_dist_b;
+} NaisDenseAdagrad;
+NAIS_API size_t nais_pairs_train_step_workspace_bytes(const NaisParams* p, const NaisPairs* batch);
+NAIS_API int nais_pairs_train_step(const NaisParams* p, const NaisPairs* batch, const float* label, const float* row_weight,
+                                   const NaisAdagrad* tables, const NaisDenseAdagrad* dense, float* loss, float* score,
+                                   void* workspace, size_t workspace_bytes, nais_stream_t stream);
+
 /* Workspace for nais_fullrank_topk / nais_fullrank_scores: n_users and nnz = offsets[n_users] are host-known. */
 NAIS_API size_t nais_fullrank_workspace_bytes(const NaisParams* p, int32_t n_users, int64_t nnz, int64_t poi_begin,
                                      int64_t poi_end, int32_t k, int32_t precision);

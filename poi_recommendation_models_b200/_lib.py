@@ -54,6 +54,11 @@ class NaisAdagrad(C.Structure):
                 ("sum_reg", C.c_void_p * 2)]
 
 
+class NaisDenseAdagrad(C.Structure):
+    _fields_ = [("lr", C.c_float), ("eps", C.c_float), ("sum_w1", C.c_void_p), ("sum_b1", C.c_void_p), ("sum_w2", C.c_void_p),
+                ("sum_dist_w", C.c_void_p), ("sum_dist_b", C.c_void_p)]
+
+
 class NaisCatalog(C.Structure):
     _fields_ = [("region", C.c_void_p), ("coords", C.c_void_p), ("row_base", C.c_int64), ("n_rows", C.c_int64),
                 ("center_lat", C.c_float), ("center_lon", C.c_float)]
@@ -73,6 +78,9 @@ SYMBOLS = {
     "nais_pairs_forward": (C.c_int, [C.POINTER(NaisParams), C.POINTER(NaisPairs), C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
     "nais_pairs_backward_workspace_bytes": (C.c_size_t, [C.POINTER(NaisParams), C.POINTER(NaisPairs)]),
+    "nais_pairs_train_step_workspace_bytes": (C.c_size_t, [C.POINTER(NaisParams), C.POINTER(NaisPairs)]),
+    "nais_pairs_train_step": (C.c_int, [C.POINTER(NaisParams), C.POINTER(NaisPairs), C.c_void_p, C.c_void_p, C.POINTER(NaisAdagrad),
+                                        C.POINTER(NaisDenseAdagrad), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nais_rows_adagrad_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "nais_rows_adagrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_float, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p]),

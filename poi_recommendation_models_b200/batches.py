@@ -116,12 +116,11 @@ class DeviceBatcher:
         from . import ops
         uids = np.asarray(uids, dtype=np.int64)
         H = self.indptr[uids + 1] - self.indptr[uids]
-        st = ops.segment_structure(H, (negative_num + 1) * H, self.dev)
-        u_dev = torch.from_numpy(uids).to(self.dev)
-        lens = torch.from_numpy(H).to(self.dev)
-        seg = torch.repeat_interleave(torch.arange(len(uids), device=self.dev), lens)
-        src = self._indptr_dev[u_dev][seg] + (torch.arange(int(H.sum()), device=self.dev) - st["seg_offsets"][seg])
-        hist = self.indices[src].contiguous()
+        # where every history entry of the batch sits in the CSR (host arithmetic: the indptr is here), riding in the same upload
+        seg_off = np.concatenate([[0], np.cumsum(H)])
+        src_h = np.repeat(self.indptr[uids] - seg_off[:-1], H) + np.arange(int(seg_off[-1]), dtype=np.int64)
+        st = ops.segment_structure(H, (negative_num + 1) * H, self.dev, extra=[(src_h, np.int64)])
+        hist = self.indices[st["extra"][0]]
         tgt, label, treg, tcoords = ops.sample_batch(hist, st, negative_num, self.num_poi, seed, self.region32, self.coords32)
         fields = {k: st[k] for k in ("seg_offsets", "row_offsets", "seg_cell_offsets", "tile_seg", "tile_row0", "n_seg", "B", "n_tiles",
                                      "n_cells", "max_hist", "host_row_offsets")}

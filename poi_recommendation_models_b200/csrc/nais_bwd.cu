@@ -754,6 +754,79 @@ static void launch_segment_reduce(const int* keys, const uint32_t* src, int64_t 
   NAIS_COUNT_LAUNCH(2);
 }
 
+// nais_pairs_train_step (include/nais_b200.h): sigmoid + BCELoss forward and backward on the [B] scores, one CTA, a fixed
+// reduction tree (deterministic loss).  x = 1 / (1 + exp(-s)); loss_b = -(y * max(log x, -100) + (1 - y) * max(log(1 - x), -100));
+// dL/ds = w * (x - y) / max((1 - x) * x, 1e-12) * ((1 - x) * x)   — torch's binary_cross_entropy_backward x sigmoid_backward.
+__global__ void __launch_bounds__(1024, 1) bce_dscore_kernel(const float* __restrict__ score, const float* __restrict__ label,
+                                                              const float* __restrict__ row_weight, int64_t B, float* __restrict__ dscore,
+                                                              float* __restrict__ loss) {
+  __shared__ float red[32];
+  const float wmean = 1.f / (float)B;
+  float acc = 0.f;
+  for (int64_t b = threadIdx.x; b < B; b += blockDim.x) {
+    const float s = score[b], y = label[b], w = row_weight ? row_weight[b] : wmean;
+    const float x = 1.f / (1.f + expf(-s));
+    const float l = -(y * fmaxf(logf(x), -100.f) + (1.f - y) * fmaxf(logf(1.f - x), -100.f));
+    acc = fmaf(w, l, acc);
+    const float v = (1.f - x) * x;
+    dscore[b] = (w * (x - y) / fmaxf(v, 1e-12f)) * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) *loss = v;
+  }
+}
+int launch_bce_dscore(const float* score, const float* label, const float* row_weight, int64_t B, float* dscore, float* loss,
+                      cudaStream_t stream) {
+  bce_dscore_kernel<<<1, 1024, 0, stream>>>(score, label, row_weight, B, dscore, loss);
+  NAIS_COUNT_LAUNCH(1);
+  return (int)cudaGetLastError();
+}
+
+// dense Adagrad of up to 5 small tensors in one launch (torch.optim.Adagrad, weight_decay = lr_decay = 0)
+struct DenseAdagradArgs {
+  float* param[5];
+  float* sum[5];
+  const float* grad[5];
+  int n[5];
+  float lr, eps;
+};
+__global__ void dense_adagrad_kernel(const DenseAdagradArgs A) {
+  const int t = blockIdx.y;
+  if (!A.param[t]) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.n[t]; i += gridDim.x * blockDim.x) {
+    const float g = A.grad[t][i];
+    const float s2 = fmaf(g, g, A.sum[t][i]);
+    A.sum[t][i] = s2;
+    A.param[t][i] += -A.lr * (g / (sqrtf(s2) + A.eps));
+  }
+}
+int launch_dense_adagrad(float* const* param, float* const* sum, const float* const* grad, const int* n, float lr, float eps,
+                         cudaStream_t stream) {
+  DenseAdagradArgs A;
+  int nmax = 1;
+  for (int t = 0; t < 5; ++t) {
+    const bool on = param[t] && sum[t] && grad[t] && n[t] > 0;
+    A.param[t] = on ? param[t] : nullptr;
+    A.sum[t] = sum[t];
+    A.grad[t] = grad[t];
+    A.n[t] = n[t];
+    if (on && n[t] > nmax) nmax = n[t];
+  }
+  A.lr = lr;
+  A.eps = eps;
+  dim3 grid((nmax + 255) / 256 < 64 ? (nmax + 255) / 256 : 64, 5);
+  dense_adagrad_kernel<<<grid, 256, 0, stream>>>(A);
+  NAIS_COUNT_LAUNCH(1);
+  return (int)cudaGetLastError();
+}
+
 // nais_rows_adagrad (include/nais_b200.h): key-ordered (id, gradient row) lists -> one row-sparse Adagrad step per distinct id
 size_t rows_adagrad_workspace_bytes(int64_t n, int w) {
   const int64_t nch = (n + SEG_CHUNK - 1) / SEG_CHUNK;

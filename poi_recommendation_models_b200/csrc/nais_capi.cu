@@ -1,7 +1,10 @@
 // extern "C" entry points of libnais_b200.so: argument validation + dispatch.  See include/nais_b200.h.
 #include <cstdio>
 
+#include <cstring>
+
 #include "nais_common.cuh"
+#include "nais_pairs_tile.cuh"
 
 namespace nais {
 // nais_fp32.cu
@@ -46,6 +49,10 @@ int launch_sample_batch(const int64_t* seg_offsets, const int64_t* hist, int n_s
                         int64_t* treg, float* tgt_coords, cudaStream_t stream);
 // nais_pairs_tc.cu
 bool pairs_tc_supported(const NaisParams& p, const NaisPairs& b);
+int launch_bce_dscore(const float* score, const float* label, const float* row_weight, int64_t B, float* dscore, float* loss,
+                      cudaStream_t stream);
+int launch_dense_adagrad(float* const* param, float* const* sum, const float* const* grad, const int* n, float lr, float eps,
+                         cudaStream_t stream);
 int launch_pairs_fwd_tc(const NaisParams& p, const NaisPairs& b, float* score, float* row_sum, float* parts,
                         unsigned long long* act_mask, cudaStream_t stream);
 }  // namespace nais
@@ -309,6 +316,94 @@ int nais_pairs_backward_adagrad(const NaisParams* p, const NaisPairs* batch, con
   if (workspace_bytes < pairs_bwd_workspace_bytes(*p, *batch)) return NAIS_ERR_WORKSPACE;
   return launch_pairs_bwd(*p, *batch, score_parts, row_sum, reinterpret_cast<const unsigned long long*>(act_mask), dscore, *grads,
                           opt, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+// ---- nais_pairs_train_step: forward -> sigmoid + BCE -> backward (tables stepped in the segment reduce) -> dense Adagrad ----------
+namespace {
+inline size_t ts_al(size_t x) { return (x + 255) / 256 * 256; }
+struct TrainStepLayout {
+  size_t score, row_sum, parts, dscore, mask, gw1, gb1, gw2, gdw, gdb, bwd, total;
+};
+TrainStepLayout train_step_layout(const NaisParams& p, const NaisPairs& b) {
+  TrainStepLayout L;
+  const int64_t B = b.B, cells = pairs_n_cells(b);
+  const NaisBranch& br = p.branch[0];
+  const int lanes = p.dist_mode == NAIS_DIST_LATLON ? 2 : 0, ldw = br.w_poi + br.w_reg + lanes;
+  size_t o = 0;
+  L.score = o, o += ts_al((size_t)B * 4);
+  L.row_sum = o, o += ts_al((size_t)B * 4);
+  L.parts = o, o += ts_al((size_t)B * 4);
+  L.dscore = o, o += ts_al((size_t)B * 4);
+  L.mask = o, o += ts_al((size_t)cells * 8);
+  L.gw1 = o, o += ts_al((size_t)p.hid * ldw * 4);
+  L.gb1 = o, o += ts_al((size_t)p.hid * 4);
+  L.gw2 = o, o += ts_al((size_t)p.hid * 4);
+  L.gdw = o, o += 256;
+  L.gdb = o, o += 256;
+  L.bwd = o, o += ts_al(pairs_bwd_workspace_bytes(p, b));
+  L.total = o;
+  return L;
+}
+}  // namespace
+
+size_t nais_pairs_train_step_workspace_bytes(const NaisParams* p, const NaisPairs* batch) {
+  if (check_params(p) || !batch || batch->B < 0 || (!batch->seg_offsets && batch->H < 1) || p->n_branch != 1) return 0;
+  return train_step_layout(*p, *batch).total;
+}
+
+int nais_pairs_train_step(const NaisParams* p, const NaisPairs* batch, const float* label, const float* row_weight,
+                          const NaisAdagrad* tables, const NaisDenseAdagrad* dense, float* loss, float* score_out, void* workspace,
+                          size_t workspace_bytes, nais_stream_t stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  rc = check_pairs(p, batch);
+  if (rc) return rc;
+  if (!tables || !dense || !loss) return NAIS_ERR_NULL;
+  if (p->n_branch != 1 || p->dist_mode == NAIS_DIST_KM) return NAIS_ERR_MODE;
+  if (!(tables->lr >= 0.f) || !(tables->eps >= 0.f) || !(dense->lr >= 0.f) || !(dense->eps >= 0.f)) return NAIS_ERR_MODE;
+  if (batch->B == 0) return 0;
+  if (!label || !workspace || !dense->sum_w1 || !dense->sum_b1 || !dense->sum_w2) return NAIS_ERR_NULL;
+  if (p->dist_mode == NAIS_DIST_LATLON && (!dense->sum_dist_w || !dense->sum_dist_b)) return NAIS_ERR_NULL;
+  if (!aligned16(workspace)) return NAIS_ERR_ALIGN;
+  const TrainStepLayout L = train_step_layout(*p, *batch);
+  if (workspace_bytes < L.total) return NAIS_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* base = reinterpret_cast<char*>(workspace);
+  auto F = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
+  // forward
+  const bool tc_ok = pairs_tc_supported(*p, *batch) && device_is_sm100();
+  if (p->pairs_precision == NAIS_PAIRS_TC && !tc_ok) return NAIS_ERR_SHAPE;
+  const bool fwd_tc = p->pairs_precision != NAIS_PAIRS_FP32 && tc_ok;
+  unsigned long long* mask = (fwd_tc && p->hid <= 64) ? reinterpret_cast<unsigned long long*>(base + L.mask) : nullptr;
+  rc = fwd_tc ? launch_pairs_fwd_tc(*p, *batch, F(L.score), F(L.row_sum), F(L.parts), mask, st)
+              : launch_pairs_fwd(*p, *batch, F(L.score), F(L.row_sum), F(L.parts), st);
+  if (rc) return rc;
+  if (score_out) {
+    cudaError_t e = cudaMemcpyAsync(score_out, F(L.score), (size_t)batch->B * 4, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  rc = launch_bce_dscore(F(L.score), label, row_weight, batch->B, F(L.dscore), loss, st);
+  if (rc) return rc;
+  // backward: MLP / distance-layer gradients to scratch, tables stepped in place
+  NaisGrads g;
+  memset(&g, 0, sizeof(g));
+  g.w1[0] = F(L.gw1);
+  g.b1[0] = F(L.gb1);
+  g.w2[0] = F(L.gw2);
+  if (p->dist_mode == NAIS_DIST_LATLON) {
+    g.dist_w = F(L.gdw);
+    g.dist_b = F(L.gdb);
+  }
+  rc = launch_pairs_bwd(*p, *batch, F(L.parts), F(L.row_sum), mask, F(L.dscore), g, tables, base + L.bwd, workspace_bytes - L.bwd, st);
+  if (rc) return rc;
+  const NaisBranch& br = p->branch[0];
+  const int lanes = p->dist_mode == NAIS_DIST_LATLON ? 2 : 0, ldw = br.w_poi + br.w_reg + lanes;
+  float* const params[5] = {const_cast<float*>(br.w1), const_cast<float*>(br.b1), const_cast<float*>(br.w2),
+                            lanes ? const_cast<float*>(p->dist_w) : nullptr, lanes ? const_cast<float*>(p->dist_b) : nullptr};
+  float* const sums[5] = {dense->sum_w1, dense->sum_b1, dense->sum_w2, dense->sum_dist_w, dense->sum_dist_b};
+  const float* const grads[5] = {g.w1[0], g.b1[0], g.w2[0], g.dist_w, g.dist_b};
+  const int ns[5] = {p->hid * ldw, p->hid, p->hid, 4, 2};
+  return launch_dense_adagrad(params, sums, grads, ns, dense->lr, dense->eps, st);
 }
 
 static int check_fullrank(const NaisParams* p, const NaisCatalog* cat, const NaisUsers* users, int64_t poi_begin,

@@ -117,6 +117,22 @@ class _NAISBase(nn.Module):
         if self._dropout_on_l1 and self.training and self.drop.p > 0:
             drop = (float(self.drop.p), int(torch.randint(0, 2 ** 62, (1,)).item()), pp)
             self.last_dropout_seed = drop[1]
+        # ---- everything in one library call (nais_pairs_train_step) when the step is the reference's: mean / row-weighted BCE,
+        # plain Adagrad on every parameter.  `one_call=False` on the model keeps the op-by-op path below (the parity tests compare).
+        dense = {n: t for n, t in P.items() if n not in ops._TABLES}
+        dgroups = [group_of.get(id(t)) for t in dense.values()]
+        if (getattr(self, "one_call", True) and isinstance(pp, str) and self.variant != "disentangled" and type(self.loss_func) is nn.BCELoss
+                and self.loss_func.reduction == "mean" and self.loss_func.weight is None and all(g is not None for g in dgroups)
+                and all(g["weight_decay"] == 0 and g["lr_decay"] == 0 and not g.get("maximize", False) for g in dgroups)
+                and len({(g["lr"], g["eps"]) for g in dgroups}) == 1 and all(t.dtype == torch.float32 for t in P.values())):
+            optimizer.zero_grad(set_to_none=True)
+            dsum = {n: optimizer.state[t]["sum"] for n, t in dense.items()}
+            loss, _ = ops.pairs_train_step(self.variant, float(self.beta), P, sums, dsum, lr, eps, dgroups[0]["lr"], dgroups[0]["eps"],
+                                           label, hist, tgt, hreg, treg, aux, row_weight, drop)
+            for t in P.values():
+                optimizer.state[t]["step"] += 1
+            self._plan_epoch = getattr(self, "_plan_epoch", 0) + 1
+            return loss[0]
         optimizer.zero_grad(set_to_none=True)
         with torch.no_grad():
             score, row_sum, parts, mask = ops.pairs_forward_raw(self.variant, float(self.beta), P, hist, tgt, hreg, treg, aux, drop)

@@ -82,10 +82,16 @@ def _poll_state(dev: torch.device) -> dict:
     return st
 
 
+_POLL_EVERY = 8  # a poll costs ~90 us of host time (event + pinned read): the word stays raised on the device, nothing is lost
+
+
 def _poll_bad_index(dev: torch.device) -> None:
     if torch.cuda.is_current_stream_capturing():
         return  # inside a CUDA graph capture: the word stays raised on the device until the next poll outside a graph
     st = _poll_state(dev)
+    st["calls"] = st.get("calls", 0) + 1
+    if st["calls"] % _POLL_EVERY != 1 and _POLL_EVERY > 1:
+        return
     check_indices(dev, sync=len(st["inflight"]) >= _POLL_SLOTS - 1)
     slot = st["next"]
     st["next"] = (slot + 1) % _POLL_SLOTS
@@ -194,9 +200,33 @@ class SegmentedPairs:
     host_row_offsets: Optional[object] = None  # numpy copy (per-user loss weights etc.)
 
 
-def segment_structure(hist_lens, rows_per_seg, device) -> Dict[str, object]:
+def _upload_packed(arrays, device):
+    """Several small host index arrays -> the device in ONE copy (a pageable host-to-device copy blocks the host for ~15 us;
+    a one-user batch has five of them): everything rides in one int64 buffer, int32 arrays as a reinterpreted tail."""
+    import numpy as np
+    parts, spans = [], []
+    off = 0
+    for a, dt in arrays:
+        a = np.ascontiguousarray(np.asarray(a).astype(dt))
+        n64 = a.size if dt == np.int64 else (a.size + 1) // 2
+        buf = np.zeros(n64, dtype=np.int64)
+        buf.view(dt)[: a.size] = a
+        parts.append(buf)
+        spans.append((off, a.size, dt))
+        off += n64
+    dev_buf = torch.from_numpy(np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)).to(device)
+    out = []
+    for o, n, dt in spans:
+        n64 = n if dt == np.int64 else (n + 1) // 2
+        t = dev_buf[o:o + n64]
+        out.append(t if dt == np.int64 else t.view(torch.int32)[:n])
+    return out
+
+
+def segment_structure(hist_lens, rows_per_seg, device, extra=()) -> Dict[str, object]:
     """Host-side structure of a segmented batch (numpy, O(segments + tiles)): offsets and the tile table the kernels walk.
-    Tile t covers at most min(16, 128 // H_s) rows of ONE segment (1 row when H_s > 128; csrc/nais_pairs_tile.cuh)."""
+    Tile t covers at most min(16, 128 // H_s) rows of ONE segment (1 row when H_s > 128; csrc/nais_pairs_tile.cuh).
+    `extra`: more (array, dtype) pairs to ride in the same upload (returned under "extra")."""
     import numpy as np
     H = np.asarray(hist_lens, dtype=np.int64)
     R = np.asarray(rows_per_seg, dtype=np.int64)
@@ -210,10 +240,11 @@ def segment_structure(hist_lens, rows_per_seg, device) -> Dict[str, object]:
     first = np.concatenate([[0], np.cumsum(tiles)])[:-1]
     within = np.arange(int(tiles.sum()), dtype=np.int64) - np.repeat(first, tiles)
     tile_row0 = np.repeat(row_off[:-1], tiles) + within * np.repeat(rpt, tiles)
-    up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a.astype(dt))).to(device)
-    return dict(seg_offsets=up(seg_off, np.int64), row_offsets=up(row_off, np.int64), seg_cell_offsets=up(cell_off, np.int64),
-                tile_seg=up(tile_seg, np.int32), tile_row0=up(tile_row0, np.int64), n_seg=len(H), B=int(row_off[-1]),
-                n_tiles=int(tiles.sum()), n_cells=int(cell_off[-1]), max_hist=int(H.max()) if len(H) else 0, host_row_offsets=row_off)
+    up = _upload_packed([(seg_off, np.int64), (row_off, np.int64), (cell_off, np.int64), (tile_row0, np.int64), (tile_seg, np.int32)]
+                        + [(a, dt) for a, dt in extra], device)
+    return dict(seg_offsets=up[0], row_offsets=up[1], seg_cell_offsets=up[2], tile_row0=up[3], tile_seg=up[4], n_seg=len(H),
+                B=int(row_off[-1]), n_tiles=int(tiles.sum()), n_cells=int(cell_off[-1]), max_hist=int(H.max()) if len(H) else 0,
+                host_row_offsets=row_off, host_seg_offsets=seg_off, extra=up[5:])
 
 
 def sample_batch(hist: torch.Tensor, st: Dict[str, object], num_ng: int, item_num: int, seed: int,
@@ -490,6 +521,51 @@ def pairs_backward_adagrad(variant: str, beta: float, P: Dict[str, torch.Tensor]
                    "nais_pairs_backward_adagrad")
         _poll_bad_index(dev)
     return G
+
+
+def pairs_train_step(variant: str, beta: float, P: Dict[str, torch.Tensor], table_sums: Dict[str, torch.Tensor],
+                     dense_sums: Dict[str, torch.Tensor], lr_tables: float, eps_tables: float, lr_dense: float, eps_dense: float,
+                     label: torch.Tensor, hist, tgt=None, hreg=None, treg=None, aux=None, row_weight: Optional[torch.Tensor] = None,
+                     drop=(0.0, 0, "auto"), want_score: bool = False):
+    """nais_pairs_train_step: zero_grad -> forward -> sigmoid + BCELoss -> backward -> Adagrad.step of run.py:248-254 in ONE
+    library call (8-12 launches).  Every tensor of `P` and every `state['sum']` in `table_sums` / `dense_sums` is updated in
+    place.  Returns (loss [1] on the device, pre-sigmoid scores [B] or None)."""
+    from ._lib import NaisAdagrad, NaisDenseAdagrad
+    dev = _need_cuda(hist, tgt, label, *P.values())
+    lib = _lib.load()
+    keep: List[torch.Tensor] = []
+    with torch.cuda.device(dev):
+        p = build_params(variant, P, beta, keep, drop[0], drop[1], drop[2])
+        if p.n_branch != 1:
+            raise RuntimeError("fused train step: one-branch variants only")
+        b = _pairs_struct(hist, tgt, hreg, treg, aux, keep)
+        o = NaisAdagrad()
+        o.lr, o.eps = float(lr_tables), float(eps_tables)
+        for name, field in zip(_TABLES, (o.sum_hist_poi, o.sum_tgt_poi, o.sum_reg)):
+            if name in P:
+                st = table_sums[name]
+                if st.dtype != torch.float32 or not st.is_contiguous() or st.shape != P[name].shape or not P[name].is_contiguous():
+                    raise RuntimeError(f"fused Adagrad: {name} and its state must be contiguous float32 of the same shape")
+                field[0] = st.data_ptr()
+        d = NaisDenseAdagrad()
+        d.lr, d.eps = float(lr_dense), float(eps_dense)
+        for name, attr in (("attn_layer1.weight", "sum_w1"), ("attn_layer1.bias", "sum_b1"), ("attn_layer2.weight", "sum_w2"),
+                           ("dist_layer.weight", "sum_dist_w"), ("dist_layer.bias", "sum_dist_b")):
+            if name in P:
+                st = dense_sums[name]
+                if st.dtype != torch.float32 or not st.is_contiguous() or st.shape != P[name].shape or not P[name].is_contiguous():
+                    raise RuntimeError(f"fused Adagrad: {name} and its state must be contiguous float32 of the same shape")
+                setattr(d, attr, st.data_ptr())
+        lab = _f32(label)
+        rw = None if row_weight is None else _f32(row_weight)
+        ws_bytes = lib.nais_pairs_train_step_workspace_bytes(C.byref(p), C.byref(b))
+        ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
+        loss = torch.empty(1, device=dev, dtype=torch.float32)
+        score = torch.empty(int(b.B), device=dev, dtype=torch.float32) if want_score else None
+        _lib.check(lib.nais_pairs_train_step(C.byref(p), C.byref(b), lab.data_ptr(), _ptr(rw), C.byref(o), C.byref(d), loss.data_ptr(),
+                                             _ptr(score), ws.data_ptr(), ws_bytes, _stream()), "nais_pairs_train_step")
+        _poll_bad_index(dev)
+    return loss, score
 
 
 def pairs_forward_raw(variant: str, beta: float, P: Dict[str, torch.Tensor], hist, tgt, hreg, treg, aux, drop=(0.0, 0, "auto")):
