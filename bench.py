@@ -452,6 +452,8 @@ def train_c3(args, dev, lib, peaks, rank, world, steps, warmup, full=False):
         allreduce_gradients(m, world)
         return loss
 
+    host_ms = [0.0]
+
     def timed(fn, n_w, n_s):
         for _ in range(n_w):
             fn()
@@ -460,10 +462,12 @@ def train_c3(args, dev, lib, peaks, rank, world, steps, warmup, full=False):
             dist.barrier()
         l0 = lib.nais_launch_count()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0 = time.perf_counter()
         a.record()
         for _ in range(n_s):
             r = fn()
         b.record()
+        host_ms[0] = (time.perf_counter() - h0) * 1e3 / n_s  # time the host needs to ENQUEUE a step (>= the device time: host-bound)
         torch.cuda.synchronize()
         t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
         if world > 1:
@@ -471,10 +475,12 @@ def train_c3(args, dev, lib, peaks, rank, world, steps, warmup, full=False):
         return float(t.item()) / n_s, int(lib.nais_launch_count() - l0) // n_s, r
 
     ms, launches, loss = timed(step, warmup, steps)
+    step_host_ms = host_ms[0]
     cells = 2 * T * H
     F = flops_per_cell(D, hid)
     blk = {"metric": "bpr_train_triples_per_sec", "value": T * world / (ms / 1000.0), "unit": "triples/s", "ms_per_step": ms,
            "n_gpus": world, "scaling": "weak", "triples_per_gpu": T, "gpu_launches_per_step": launches, "loss": float(loss.detach()),
+           "host_enqueue_ms_per_step": step_host_ms,
            "dtype": "f16x2-split fwd / bf16x2-split bwd, f32 accumulate (tcgen05); f32 reduces",
            "config": {"workload": "C3: 4096 (user,pos,neg) triples = 8192 rows, own history per row, H=128, D=hid=64, 40k POIs; fwd + BPR loss + bwd of every parameter",
                       "parallelism": "single GPU" if world == 1 else f"data parallel x{world}, dense gradient all-reduce (one flat bucket)",

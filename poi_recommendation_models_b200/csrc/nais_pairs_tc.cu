@@ -422,6 +422,7 @@ __global__ void __launch_bounds__(PT2, 3) pairs_fwd_tc2_kernel(const __grid_cons
   //   P1 (after u's inputs are consumed)  ids / lat-lon of u + 1                  -> m_* arrays           (DRAM latency)
   //   P2 (after u's MMAs are complete)    history rows of u + 1 -> `stg` (aliases the A image, free now); target rows -> ps[next]
   // and u + 1 starts with cp.async.wait_all + one barrier.
+  const RowGather RG = row_gather_init(br, s0, lane, stg, STG_STRIDE);
   auto issue_ids = [&](const PairTile& Tn, int chn) {
     const PairCell c = pair_cell(Tn, chn, cell);
     if (c.valid) {
@@ -443,14 +444,9 @@ __global__ void __launch_bounds__(PT2, 3) pairs_fwd_tc2_kernel(const __grid_cons
       it32 = checked_id(m_hist[tid], p.item_num, A.bad);
       rg32 = br.w_reg ? checked_id(m_hreg[tid], p.region_num, A.bad) : 0;
     }
-    // warp-cooperative gather of the 32-float segment [s0, s0 + 32) of this warp's 32 history rows: 8 lanes cover one row
+    // warp-cooperative gather of the 32-float segment [s0, s0 + 32) of this warp's 32 history rows (nais_pairs_tile.cuh RowGather)
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int idx = lane + 32 * q, cc = idx >> 3, part = idx & 7, col = s0 + 4 * part;
-      const int ci = __shfl_sync(0xffffffffu, it32, cc), cr = __shfl_sync(0xffffffffu, rg32, cc);
-      const float* src = col < br.w_poi ? br.hist_poi + (size_t)ci * br.w_poi + col : br.hist_reg + (size_t)cr * br.w_reg + (col - br.w_poi);
-      cp_async16(stg + (size_t)cc * STG_STRIDE + part * 16, src);
-    }
+    for (int q = 0; q < 8; ++q) cp_async16(RG.dst + (uint32_t)(q * 4 * STG_STRIDE), row_gather_src(RG, it32, rg32, q));
     if (chn == 0 && tid * 4 < Tn.nrows * D) {
       const int r = (tid * 4) / D, d = tid * 4 - r * D;
       const float* src = d < br.w_poi ? br.tgt_poi + (size_t)checked_id(m_psid[tid], p.item_num, A.bad) * br.w_poi + d
@@ -585,10 +581,13 @@ __global__ void __launch_bounds__(PT2, 3) pairs_fwd_tc2_kernel(const __grid_cons
         const float4 c4 = reinterpret_cast<const float4*>(kc)[s0 + c0 + i];
         float t = fmaf(__uint_as_float(v[i]), inv, c4.x);
         if (lanes) t = fmaf(c4.w, g1, fmaf(c4.z, g0, t));
-        bits |= (t > 0.f ? 1u : 0u) << (c0 + i);
+        // t > 0  <=>  the sign bit of (0 - t) is set (IEEE: 0 - (+-0) = +0, so an exact zero counts as inactive like torch's
+        // relu backward); shifted in from the right, un-reversed once below: 2 instructions per unit instead of 5
+        bits = __funnelshift_l(__float_as_uint(0.f - t), bits, 1);
         a = fmaf(c4.y, fmaxf(t, 0.f), a);
       }
     }
+    bits = __brev(bits);
     tc_fence_before();  // TMEM reads ordered before the barrier that precedes the next unit's MMAs
     apart[half * PT + cell] = a;
     if (half == 1) abits[cell] = bits;
@@ -720,7 +719,8 @@ int launch_pairs_fwd_tc(const NaisParams& p, const NaisPairs& b, float* score, f
   const int64_t n_items = pairs_n_tiles(b);
   if (n_items < 1) return 0;
   const int D = p.branch[0].w_poi + p.branch[0].w_reg;
-  if (D == 64 && p.hid == 64 && rows_vec4(p.branch[0], 4)) return ptc::launch2(A, n_items, sms, stream);  // two threads per cell
+  if (D == 64 && p.hid == 64 && rows_vec4(p.branch[0], 4) && pair_gather_uniform(p.branch[0]))
+    return ptc::launch2(A, n_items, sms, stream);  // two threads per cell (a cell's 32-column halves each lie in one table)
   switch (D) {
     case 16: return ptc::launch<16>(A, p.hid, n_items, sms, stream);
     case 32: return ptc::launch<32>(A, p.hid, n_items, sms, stream);

@@ -43,13 +43,22 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn, int b_
          ((uint32_t)(M >> 4) << 24);
 }
 
-// 8 fp32 -> one 16-byte k-chunk per plane
+// 8 fp32 -> one 16-byte k-chunk per plane.  Two values per conversion (F2FP.BF16.PACK_AB on the ALU pipe; the scalar
+// __float2bfloat16_rn is an F2F on the 16-lane conversion unit: 75 of them per thread and work unit were ~20 % of the backward's
+// time), hi back to fp32 by a shift / mask: same roundings, same bits as split_bf16.
 __device__ __forceinline__ void store_chunk_bf16(uint8_t* hi_plane, uint8_t* lo_plane, size_t off, const float (&v)[8]) {
-  __align__(16) __nv_bfloat16 hi[8], lo[8];
+  uint32_t hi[4], lo[4];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) split_bf16(v[e], hi[e], lo[e]);
-  *reinterpret_cast<uint4*>(hi_plane + off) = *reinterpret_cast<const uint4*>(hi);
-  *reinterpret_cast<uint4*>(lo_plane + off) = *reinterpret_cast<const uint4*>(lo);
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);  // .x = low half = v[2e]
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(&h2);
+    const float ha = __uint_as_float(u << 16), hb = __uint_as_float(u & 0xffff0000u);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * e] - ha, v[2 * e + 1] - hb);
+    hi[e] = u;
+    lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+  *reinterpret_cast<uint4*>(hi_plane + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(lo_plane + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 // Warp-cooperative gather of the 32-float segment [s0, s0+segw) of the 32 history rows of this warp's cells (ids it32 / rg32 held
@@ -523,6 +532,7 @@ __global__ void __launch_bounds__(PT2, 2) pairs_bwd_tc2_kernel(const __grid_cons
   //   P2 (after u's second gather is staged)  history rows of u + 1 -> `stg` (aliases the DT image, free now); target rows -> ps[next]
   // and u + 1 starts with cp.async.wait_all + one barrier.  The second gather of u's own rows (dp needs them again) is issued
   // into registers BEFORE the wait for GEMM2/3 and staged after it.
+  const RowGather RG = row_gather_init(br, s0, lane, stg, STG_STRIDE);
   auto issue_ids = [&](const PairTile& Tn, int chn) {
     const PairCell c = pair_cell(Tn, chn, cell);
     if (c.valid) {
@@ -557,12 +567,7 @@ __global__ void __launch_bounds__(PT2, 2) pairs_bwd_tc2_kernel(const __grid_cons
       rg32 = br.w_reg ? checked_id(m_hreg[cell], p.region_num, A.bad) : 0;
     }
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int idx = lane + 32 * q, cc = idx >> 3, part = idx & 7, col = s0 + 4 * part;
-      const int ci = __shfl_sync(0xffffffffu, it32, cc), cr = __shfl_sync(0xffffffffu, rg32, cc);
-      const float* src = col < br.w_poi ? br.hist_poi + (size_t)ci * br.w_poi + col : br.hist_reg + (size_t)cr * br.w_reg + (col - br.w_poi);
-      cp_async16(stg + (size_t)cc * STG_STRIDE + part * 16, src);
-    }
+    for (int q = 0; q < 8; ++q) cp_async16(RG.dst + (uint32_t)(q * 4 * STG_STRIDE), row_gather_src(RG, it32, rg32, q));
     if (chn == 0 && tid * 4 < Tn.nrows * D) {
       const int r = (tid * 4) / D, d = tid * 4 - r * D;
       const float* src = d < br.w_poi ? br.tgt_poi + (size_t)checked_id(m_psid[tid], p.item_num, A.bad) * br.w_poi + d
@@ -799,11 +804,7 @@ __global__ void __launch_bounds__(PT2, 2) pairs_bwd_tc2_kernel(const __grid_cons
     // second gather of this unit's history rows, in flight while the MMAs run (the staging aliases the DT image they read)
     float4 gv[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int idx = lane + 32 * q, cc = idx >> 3, part = idx & 7;
-      const int ci = __shfl_sync(0xffffffffu, it32, cc), cr = __shfl_sync(0xffffffffu, rg32, cc);
-      gv[q] = ldg_row4(br.hist_poi + (size_t)ci * br.w_poi, br.hist_reg + (size_t)cr * br.w_reg, br.w_poi, s0 + 4 * part);
-    }
+    for (int q = 0; q < 8; ++q) gv[q] = __ldg(reinterpret_cast<const float4*>(row_gather_src(RG, it32, rg32, q)));
     mbar_wait(bar, phase);
     phase ^= 1u;
     tc_fence_after();
@@ -811,10 +812,10 @@ __global__ void __launch_bounds__(PT2, 2) pairs_bwd_tc2_kernel(const __grid_cons
     // ---- epilogue 2: this half of the dq row to the workspace, dp contributions to the scratch (aliased on the X image) --------------
     {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int idx = lane + 32 * q, cc = idx >> 3, part = idx & 7;
-        *reinterpret_cast<float4*>(stg + (size_t)cc * STG_STRIDE + part * 16) = gv[q];
-      }
+      for (int q = 0; q < 8; ++q)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(RG.dst + (uint32_t)(q * 4 * STG_STRIDE)), "f"(gv[q].x), "f"(gv[q].y),
+                     "f"(gv[q].z), "f"(gv[q].w)
+                     : "memory");
       __syncwarp();
 #pragma unroll
       for (int c0 = 0; c0 < 32; c0 += 16) {
@@ -966,7 +967,9 @@ bool pairs_tc_bwd_supported(const NaisParams& p, const NaisPairs& b) {
 
 // grid <= 2 CTAs per SM (256 TMEM columns each); every CTA owns at least one tile (the caller passes min(n_items, grid))
 int launch_pairs_bwd_tc(const BwdArgs& A, int D, int grid, cudaStream_t stream) {
-  return D == 32 ? ptcb::launch<32>(A, grid, stream) : ptcb::launch2(A, grid, stream);  // D = 64: two threads per cell
+  if (D == 32) return ptcb::launch<32>(A, grid, stream);
+  // D = 64: two threads per cell when each 32-column half of a row lies in one table (every shipped model class)
+  return pair_gather_uniform(A.p.branch[A.bi]) ? ptcb::launch2(A, grid, stream) : ptcb::launch<64>(A, grid, stream);
 }
 
 }  // namespace nais

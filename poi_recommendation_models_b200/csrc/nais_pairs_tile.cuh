@@ -8,8 +8,16 @@ namespace nais {
 
 constexpr int PAIR_MAXROWS = 16;  // rows sharing one 128-cell tile when the history is short
 
+// floor(a / b) for 0 <= a <= 128, 1 <= b <= 128 without the ~25-instruction integer division sequence: (a + 0.5) / b is at least
+// 1 / 256 away from every integer, far more than the approximate divide's error (the pair kernels do this per cell and work unit)
+__device__ __forceinline__ int div_small(int a, int b) { return (int)__fdividef((float)a + 0.5f, (float)b); }
+
 __host__ __device__ inline int pair_rows_per_tile(int H) {
+#ifdef __CUDA_ARCH__
+  int r = H <= TC ? div_small(TC, H > 0 ? H : 1) : 1;
+#else
   int r = H <= TC ? TC / (H > 0 ? H : 1) : 1;
+#endif
   return r > PAIR_MAXROWS ? PAIR_MAXROWS : r;
 }
 
@@ -79,7 +87,39 @@ __device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem_addr, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem_addr), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// The warp-cooperative gather of the 32-float segment [s0, s0 + 32) of a warp's 32 history rows (ids it32 / rg32 held one per lane):
+// 8 lanes cover one row's 128 bytes, request q of a lane is row (lane / 8) + 4 q, and a lane's column — hence its offset in the
+// table row and its 16 bytes in the staged row — is the same in all 8 requests: set up once per kernel.  The whole segment must lie
+// in ONE table (w_poi a multiple of 32: every shipped model class; pair_gather_uniform() gates the kernels that use this), so one
+// shuffle per request fetches the id and the choice of the id register is warp-uniform.
+struct RowGather {
+  const float* tbl;  // table base + this lane's column
+  int stride;        // floats per table row
+  bool use_reg;      // the segment is in the region table (warp-uniform)
+  int row0;          // lane / 8
+  uint32_t dst;      // shared-memory address of this lane's 16 bytes of staged row `row0`
+};
+__host__ __device__ inline bool pair_gather_uniform(const NaisBranch& br) { return br.w_poi % 32 == 0; }
+__device__ __forceinline__ RowGather row_gather_init(const NaisBranch& br, int s0, int lane, const void* stg, int stg_stride) {
+  RowGather G;
+  const int part = lane & 7, col = s0 + 4 * part;
+  G.use_reg = s0 >= br.w_poi;
+  G.tbl = G.use_reg ? br.hist_reg + (col - br.w_poi) : br.hist_poi + col;
+  G.stride = G.use_reg ? br.w_reg : br.w_poi;
+  G.row0 = lane >> 3;
+  G.dst = (uint32_t)__cvta_generic_to_shared(stg) + (uint32_t)(G.row0 * stg_stride + part * 16);
+  return G;
+}
+// address of this lane's 16 bytes of request q (q = 0..7): the table row of cell row0 + 4 q of the warp
+__device__ __forceinline__ const float* row_gather_src(const RowGather& G, int it32, int rg32, int q) {
+  const int id = __shfl_sync(0xffffffffu, G.use_reg ? rg32 : it32, G.row0 + 4 * q);
+  return G.tbl + (size_t)id * G.stride;
+}
 
 // cell `cell` (0..127) of a work unit of those kernels (128 cells = chunk `ch` of a tile; a tile with H > 128 has several chunks,
 // else one): which row of the tile / history position it is, and where its inputs live
@@ -91,7 +131,7 @@ struct PairCell {
 __device__ __forceinline__ PairCell pair_cell(const PairTile& T, int ch, int cell) {
   PairCell c;
   if (T.H <= TC) {
-    c.r = cell / T.H;
+    c.r = div_small(cell, T.H);
     c.h = cell - c.r * T.H;
     c.valid = c.r < T.nrows;
   } else {
