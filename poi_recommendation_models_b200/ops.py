@@ -319,6 +319,17 @@ def _forward_launch(lib, p: NaisParams, b: NaisPairs, dev, want_mask: bool = Tru
     return score, row_sum, parts, mask
 
 
+# gradients param_reduce_kernel writes in full (csrc/nais_bwd.cu): no zero fill needed; every other tensor has rows / entries the
+# backward does not touch (untouched table rows, embed_distance of the one-branch variants)
+_FULLY_WRITTEN = {"attn_layer1.weight", "attn_layer1.bias", "attn_layer2.weight", "dist_layer.weight", "dist_layer.bias",
+                  "region_attn_layer1.weight", "region_attn_layer1.bias", "region_attn_layer2.weight"}
+
+
+def _grad_buffer(name: str, t: torch.Tensor, n_rows: int = 1) -> torch.Tensor:
+    mk = torch.empty_like if (name in _FULLY_WRITTEN and n_rows > 0) else torch.zeros_like  # (an empty batch launches nothing)
+    return mk(t, dtype=torch.float32, memory_format=torch.contiguous_format)
+
+
 def _fwd_bwd(pairs_precision):
     """`pairs_precision` is one name for both directions or a (forward, backward) pair."""
     return (pairs_precision, pairs_precision) if isinstance(pairs_precision, str) else tuple(pairs_precision)
@@ -377,8 +388,7 @@ def pairs_backward_raw(variant: str, beta: float, P: Dict[str, torch.Tensor], hi
     with torch.cuda.device(dev):
         p = build_params(variant, P, beta, keep, drop[0], drop[1], _fwd_bwd(drop[2])[1])
         b = _pairs_struct(hist, tgt, hreg, treg, aux, keep)
-        G = {n: torch.zeros_like(t, dtype=torch.float32, memory_format=torch.contiguous_format) for n, t in P.items()
-             if tables or n not in _TABLES}
+        G = {n: _grad_buffer(n, t, int(b.B)) for n, t in P.items() if tables or n not in _TABLES}
         g = NaisGrads()
         if tables:
             g.hist_poi[0], g.tgt_poi[0] = G["embed_history.weight"].data_ptr(), G["embed_target.weight"].data_ptr()
@@ -442,7 +452,7 @@ def pairs_backward_compact(variant: str, beta: float, P: Dict[str, torch.Tensor]
             raise RuntimeError("row-compacted gradients: one-branch variants only")
         b = _pairs_struct(hist, tgt, hreg, treg, aux, keep)
         ids = touched_rows(hist, tgt, hreg, treg)
-        G = {n: torch.zeros_like(t, dtype=torch.float32, memory_format=torch.contiguous_format) for n, t in P.items() if n not in _TABLES}
+        G = {n: _grad_buffer(n, t, int(b.B)) for n, t in P.items() if n not in _TABLES}
         g = NaisGrads()
         g.w1[0], g.b1[0], g.w2[0] = (G["attn_layer1.weight"].data_ptr(), G["attn_layer1.bias"].data_ptr(), G["attn_layer2.weight"].data_ptr())
         if "dist_layer.weight" in G:
@@ -500,7 +510,7 @@ def pairs_backward_adagrad(variant: str, beta: float, P: Dict[str, torch.Tensor]
         if p.n_branch != 1:
             raise RuntimeError("fused Adagrad: one-branch variants only")
         b = _pairs_struct(hist, tgt, hreg, treg, aux, keep)
-        G = {n: torch.zeros_like(t, dtype=torch.float32, memory_format=torch.contiguous_format) for n, t in P.items() if n not in _TABLES}
+        G = {n: _grad_buffer(n, t, int(b.B)) for n, t in P.items() if n not in _TABLES}
         g = NaisGrads()
         g.w1[0], g.b1[0], g.w2[0] = (G["attn_layer1.weight"].data_ptr(), G["attn_layer1.bias"].data_ptr(), G["attn_layer2.weight"].data_ptr())
         if "dist_layer.weight" in G:
