@@ -225,7 +225,7 @@ def test_ctypes_mirrors_match_the_header_layout(tmp_path):
     from poi_recommendation_models_b200 import _lib as L
     if shutil.which("gcc") is None:
         pytest.skip("gcc not available")
-    structs = ["NaisBranch", "NaisParams", "NaisPairs", "NaisGrads", "NaisAdagrad", "NaisCatalog", "NaisUsers"]
+    structs = ["NaisBranch", "NaisParams", "NaisPairs", "NaisGrads", "NaisAdagrad", "NaisDenseAdagrad", "NaisCatalog", "NaisUsers"]
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "nais_b200.h"', 'int main(void) {']
     for s in structs:
         cls = getattr(L, s)
@@ -244,6 +244,48 @@ def test_ctypes_mirrors_match_the_header_layout(tmp_path):
         assert int(got[s]) == C.sizeof(cls), s
         for f, _ in cls._fields_:
             assert int(got[f"{s}.{f}"]) == getattr(cls, f).offset, (s, f)
+
+
+def test_precision_flags_and_train_step_entry_validate():
+    """The `precision` flag bits of the header equal the Python names; nais_pairs_train_step checks its arguments before it
+    launches anything (no GPU here)."""
+    import ctypes as C
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "nais_b200.h")).read()
+    flags = dict((m.group(1), int(m.group(2), 16)) for m in re.finditer(r"#define (NAIS_PREC_FLAG_\w+) (0x[0-9a-fA-F]+)", hdr))
+    assert flags == {"NAIS_PREC_FLAG_GENERIC": _lib.PREC_FLAG_GENERIC, "NAIS_PREC_FLAG_ONE_CTA": _lib.PREC_FLAG_ONE_CTA}
+    assert _lib.PRECISIONS["tc_auto_onecta"] == _lib.PREC_TC_AUTO | _lib.PREC_FLAG_ONE_CTA
+    lib = _lib.load()
+    p, b = _lib.NaisParams(), _lib.NaisPairs()
+    assert lib.nais_pairs_train_step_workspace_bytes(C.byref(p), C.byref(b)) == 0                      # invalid params -> 0
+    assert lib.nais_pairs_train_step(C.byref(p), C.byref(b), None, None, None, None, None, None, None, 0, None) < 0
+    p.n_branch, p.hid, p.item_num = 1, 64, 10
+    p.branch[0].w_poi = 64
+    for f in ("hist_poi", "tgt_poi", "w1", "b1", "w2"):
+        setattr(p.branch[0], f, 16)  # (never dereferenced: the argument checks run first)
+    b.H = 4
+    assert lib.nais_pairs_train_step(C.byref(p), C.byref(b), None, None, None, None, None, None, None, 0, None) == -1  # NULL optimizer state
+
+
+def test_segment_structure_rides_in_one_upload():
+    """ops.segment_structure packs its index arrays (and the caller's extras) into one buffer: the views must equal the arrays."""
+    import torch
+    from poi_recommendation_models_b200 import ops
+    H = np.array([3, 0, 130, 17, 1], dtype=np.int64)
+    extra = np.arange(7, dtype=np.int64) * 11
+    st = ops.segment_structure(H, 5 * H, torch.device("cpu"), extra=[(extra, np.int64), (np.array([5, 6, 7], dtype=np.int32), np.int32)])
+    assert st["seg_offsets"].tolist() == [0, 3, 3, 133, 150, 151]
+    assert st["row_offsets"].tolist() == [0, 15, 15, 665, 750, 755]
+    assert st["seg_cell_offsets"].tolist() == np.concatenate([[0], np.cumsum(5 * H * H)]).tolist()
+    assert st["tile_seg"].dtype == torch.int32 and st["tile_row0"].dtype == torch.int64
+    assert st["n_tiles"] == len(st["tile_seg"]) == len(st["tile_row0"])
+    # tiles: min(16, 128 // H) rows of one segment each (1 row when H > 128); a segment without history has none
+    rows_per_tile = {0: 16, 2: 1, 3: 7, 4: 16}
+    for t in range(st["n_tiles"]):
+        s_ = int(st["tile_seg"][t])
+        assert s_ != 1 and (int(st["tile_row0"][t]) - int(st["row_offsets"][s_])) % rows_per_tile[s_] == 0
+    assert st["extra"][0].tolist() == extra.tolist() and st["extra"][1].tolist() == [5, 6, 7] and st["extra"][1].dtype == torch.int32
+    assert st["B"] == 755 and st["n_cells"] == int((5 * H * H).sum()) and st["max_hist"] == 130
 
 
 def test_bench_reference_arm_prints_the_contract_line():
