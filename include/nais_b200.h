@@ -289,6 +289,19 @@ NAIS_API int nais_pairs_train_step(const NaisParams* p, const NaisPairs* batch, 
                                    const NaisAdagrad* tables, const NaisDenseAdagrad* dense, float* loss, float* score,
                                    void* workspace, size_t workspace_bytes, nais_stream_t stream);
 
+/* The reference's training schedule — ONE optimizer step per user (run.py:227-255) — for a list of users in one call: per user,
+ * nais_sample_batch over his history (every positive + num_ng negatives each, labels [1, 0..0]: batches.py:67-108) and
+ * nais_pairs_train_step with the batch-mean BCE, enqueued back to back with no host work in between but the launches (~15 per
+ * user).  The user's history is the slice [host_indptr[u], host_indptr[u + 1]) of `indices` (the train matrix' CSR; no copy);
+ * entry_region / entry_coords are the region id / centred (lat, lon) of every CSR entry (region[indices], coords[indices]; NULL
+ * when the variant has no region table / distance lanes).  host_indptr and host_users are HOST arrays (read during the call).
+ * User i samples with seed + host_users[i].  losses: device float[n_users] (0 for a user without history).  One branch only. */
+NAIS_API size_t nais_train_users_workspace_bytes(const NaisParams* p, int32_t max_hist, int32_t num_ng);
+NAIS_API int nais_train_users(const NaisParams* p, const int64_t* host_indptr, const int64_t* indices, const int64_t* entry_region,
+                              const float* entry_coords, const int32_t* poi_region, const float* poi_coords, const int64_t* host_users,
+                              int32_t n_users, int32_t num_ng, uint64_t seed, const NaisAdagrad* tables, const NaisDenseAdagrad* dense,
+                              float* losses, void* workspace, size_t workspace_bytes, nais_stream_t stream);
+
 /* Workspace for nais_fullrank_topk / nais_fullrank_scores: n_users and nnz = offsets[n_users] are host-known. */
 NAIS_API size_t nais_fullrank_workspace_bytes(const NaisParams* p, int32_t n_users, int64_t nnz, int64_t poi_begin,
                                      int64_t poi_end, int32_t k, int32_t precision);

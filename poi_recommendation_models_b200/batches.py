@@ -106,6 +106,9 @@ class DeviceBatcher:
         self.coords32 = torch.from_numpy((c - np.array(self.center)).astype(np.float32)).to(dev)
         self.region32 = self.region.to(torch.int32)
         self._indptr_dev = torch.from_numpy(self.indptr).to(dev)
+        # region id and centred coordinates of every CSR entry: a user's history side data is then a slice (nais_train_users)
+        self.entry_region = self.region[self.indices].contiguous()
+        self.entry_coords = self.coords32[self.indices].contiguous()
 
     def multi_user_batch(self, uids, negative_num: int, seed: int = 0):
         """One training batch over MANY users as an `ops.SegmentedPairs`: for every user all positives, each

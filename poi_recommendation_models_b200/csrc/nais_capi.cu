@@ -351,6 +351,20 @@ size_t nais_pairs_train_step_workspace_bytes(const NaisParams* p, const NaisPair
   return train_step_layout(*p, *batch).total;
 }
 
+static int check_train_state(const NaisParams* p, const NaisAdagrad* tables, const NaisDenseAdagrad* dense) {
+  if (!tables || !dense) return NAIS_ERR_NULL;
+  if (p->n_branch != 1 || p->dist_mode == NAIS_DIST_KM) return NAIS_ERR_MODE;
+  if (!(tables->lr >= 0.f) || !(tables->eps >= 0.f) || !(dense->lr >= 0.f) || !(dense->eps >= 0.f)) return NAIS_ERR_MODE;
+  if (!dense->sum_w1 || !dense->sum_b1 || !dense->sum_w2) return NAIS_ERR_NULL;
+  if (p->dist_mode == NAIS_DIST_LATLON && (!dense->sum_dist_w || !dense->sum_dist_b)) return NAIS_ERR_NULL;
+  return 0;
+}
+
+// the launches of one optimizer step (arguments already checked)
+static int train_step_impl(const NaisParams* p, const NaisPairs* batch, const float* label, const float* row_weight,
+                           const NaisAdagrad* tables, const NaisDenseAdagrad* dense, float* loss, float* score_out, void* workspace,
+                           size_t workspace_bytes, cudaStream_t st);
+
 int nais_pairs_train_step(const NaisParams* p, const NaisPairs* batch, const float* label, const float* row_weight,
                           const NaisAdagrad* tables, const NaisDenseAdagrad* dense, float* loss, float* score_out, void* workspace,
                           size_t workspace_bytes, nais_stream_t stream) {
@@ -358,16 +372,22 @@ int nais_pairs_train_step(const NaisParams* p, const NaisPairs* batch, const flo
   if (rc) return rc;
   rc = check_pairs(p, batch);
   if (rc) return rc;
-  if (!tables || !dense || !loss) return NAIS_ERR_NULL;
-  if (p->n_branch != 1 || p->dist_mode == NAIS_DIST_KM) return NAIS_ERR_MODE;
-  if (!(tables->lr >= 0.f) || !(tables->eps >= 0.f) || !(dense->lr >= 0.f) || !(dense->eps >= 0.f)) return NAIS_ERR_MODE;
+  if (!loss) return NAIS_ERR_NULL;
+  rc = check_train_state(p, tables, dense);
+  if (rc) return rc;
   if (batch->B == 0) return 0;
-  if (!label || !workspace || !dense->sum_w1 || !dense->sum_b1 || !dense->sum_w2) return NAIS_ERR_NULL;
-  if (p->dist_mode == NAIS_DIST_LATLON && (!dense->sum_dist_w || !dense->sum_dist_b)) return NAIS_ERR_NULL;
+  if (!label || !workspace) return NAIS_ERR_NULL;
   if (!aligned16(workspace)) return NAIS_ERR_ALIGN;
+  return train_step_impl(p, batch, label, row_weight, tables, dense, loss, score_out, workspace, workspace_bytes,
+                         static_cast<cudaStream_t>(stream));
+}
+
+static int train_step_impl(const NaisParams* p, const NaisPairs* batch, const float* label, const float* row_weight,
+                           const NaisAdagrad* tables, const NaisDenseAdagrad* dense, float* loss, float* score_out, void* workspace,
+                           size_t workspace_bytes, cudaStream_t st) {
+  int rc;
   const TrainStepLayout L = train_step_layout(*p, *batch);
   if (workspace_bytes < L.total) return NAIS_ERR_WORKSPACE;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* base = reinterpret_cast<char*>(workspace);
   auto F = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
   // forward
@@ -404,6 +424,133 @@ int nais_pairs_train_step(const NaisParams* p, const NaisPairs* batch, const flo
   const float* const grads[5] = {g.w1[0], g.b1[0], g.w2[0], g.dist_w, g.dist_b};
   const int ns[5] = {p->hid * ldw, p->hid, p->hid, 4, 2};
   return launch_dense_adagrad(params, sums, grads, ns, dense->lr, dense->eps, st);
+}
+
+// ---- nais_train_users: the reference's one-user-per-step schedule, a list of users per call ---------------------------------------
+namespace {
+// the segment structure of a ONE-segment batch (H history items, R rows): offsets + the tile table, written on the device
+__global__ void single_segment_kernel(int H, int R, int rpt, int n_tiles, int64_t* seg_offsets, int64_t* row_offsets, int64_t* cell_offsets,
+                                      int32_t* tile_seg, int64_t* tile_row0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    seg_offsets[0] = 0, seg_offsets[1] = H;
+    row_offsets[0] = 0, row_offsets[1] = R;
+    cell_offsets[0] = 0, cell_offsets[1] = (int64_t)R * H;
+  }
+  if (i < n_tiles) {
+    tile_seg[i] = 0;
+    tile_row0[i] = (int64_t)i * rpt;
+  }
+}
+struct UsersLayout {
+  size_t seg, row, cell, tseg, trow, tgt, label, treg, tco, step, total;
+};
+inline int host_rows_per_tile(int H) {
+  int r = H <= 128 ? 128 / (H > 0 ? H : 1) : 1;
+  return r > 16 ? 16 : r;
+}
+NaisPairs max_user_batch(int max_hist, int num_ng) {
+  NaisPairs b;
+  memset(&b, 0, sizeof(b));
+  static const int64_t dummy[2] = {0, 0};
+  b.seg_offsets = dummy;  // (marks the segmented layout: only sizes are read from this struct)
+  b.n_seg = 1;
+  b.B = (int64_t)max_hist * (num_ng + 1);
+  b.n_cells = b.B * max_hist;
+  b.n_tiles = b.B;  // (an upper bound for every history length)
+  return b;
+}
+UsersLayout users_layout(const NaisParams& p, int max_hist, int num_ng) {
+  UsersLayout L;
+  const NaisPairs b = max_user_batch(max_hist, num_ng);
+  size_t o = 0;
+  L.seg = o, o += 256;
+  L.row = o, o += 256;
+  L.cell = o, o += 256;
+  L.tseg = o, o += ts_al((size_t)b.n_tiles * 4);
+  L.trow = o, o += ts_al((size_t)b.n_tiles * 8);
+  L.tgt = o, o += ts_al((size_t)b.B * 8);
+  L.label = o, o += ts_al((size_t)b.B * 4);
+  L.treg = o, o += ts_al((size_t)b.B * 8);
+  L.tco = o, o += ts_al((size_t)b.B * 8);
+  L.step = o, o += train_step_layout(p, b).total;
+  L.total = o;
+  return L;
+}
+}  // namespace
+
+size_t nais_train_users_workspace_bytes(const NaisParams* p, int32_t max_hist, int32_t num_ng) {
+  if (check_params(p) || p->n_branch != 1 || max_hist < 1 || num_ng < 0) return 0;
+  return users_layout(*p, max_hist, num_ng).total;
+}
+
+int nais_train_users(const NaisParams* p, const int64_t* host_indptr, const int64_t* indices, const int64_t* entry_region,
+                     const float* entry_coords, const int32_t* poi_region, const float* poi_coords, const int64_t* host_users,
+                     int32_t n_users, int32_t num_ng, uint64_t seed, const NaisAdagrad* tables, const NaisDenseAdagrad* dense, float* losses,
+                     void* workspace, size_t workspace_bytes, nais_stream_t stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  rc = check_train_state(p, tables, dense);
+  if (rc) return rc;
+  if (n_users < 0 || num_ng < 0) return NAIS_ERR_SHAPE;
+  if (n_users == 0) return 0;
+  if (!host_indptr || !indices || !host_users || !losses || !workspace) return NAIS_ERR_NULL;
+  const bool need_reg = p->branch[0].w_reg > 0, need_co = p->dist_mode == NAIS_DIST_LATLON;
+  if ((need_reg && (!entry_region || !poi_region)) || (need_co && (!entry_coords || !poi_coords))) return NAIS_ERR_NULL;
+  if (!aligned16(workspace)) return NAIS_ERR_ALIGN;
+  int max_hist = 0;
+  for (int i = 0; i < n_users; ++i) {
+    const int64_t u = host_users[i];
+    if (u < 0) return NAIS_ERR_SHAPE;
+    const int64_t H = host_indptr[u + 1] - host_indptr[u];
+    if (H < 0 || H > 0x7fffffff / (num_ng + 2)) return NAIS_ERR_SHAPE;
+    if ((int)H > max_hist) max_hist = (int)H;
+  }
+  if (max_hist == 0) return (int)cudaMemsetAsync(losses, 0, (size_t)n_users * 4, static_cast<cudaStream_t>(stream));
+  if ((int64_t)max_hist * (num_ng + 1) >= p->item_num) return NAIS_ERR_SHAPE;  // not enough unvisited POIs to draw from
+  const UsersLayout L = users_layout(*p, max_hist, num_ng);
+  if (workspace_bytes < L.total) return NAIS_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* base = reinterpret_cast<char*>(workspace);
+  auto I64 = [&](size_t off) { return reinterpret_cast<int64_t*>(base + off); };
+  for (int i = 0; i < n_users; ++i) {
+    const int64_t u = host_users[i], a = host_indptr[u];
+    const int H = (int)(host_indptr[u + 1] - a);
+    if (H == 0) {
+      cudaError_t e = cudaMemsetAsync(losses + i, 0, 4, st);
+      if (e != cudaSuccess) return (int)e;
+      continue;
+    }
+    const int R = H * (num_ng + 1), rpt = host_rows_per_tile(H), n_tiles = (R + rpt - 1) / rpt;
+    single_segment_kernel<<<(n_tiles + 255) / 256, 256, 0, st>>>(H, R, rpt, n_tiles, I64(L.seg), I64(L.row), I64(L.cell),
+                                                                 reinterpret_cast<int32_t*>(base + L.tseg), I64(L.trow));
+    NAIS_COUNT_LAUNCH(1);
+    rc = launch_sample_batch(I64(L.seg), indices + a, 1, I64(L.row), num_ng, p->item_num, need_reg ? poi_region : nullptr,
+                             need_co ? poi_coords : nullptr, seed + (uint64_t)u, H, I64(L.tgt), reinterpret_cast<float*>(base + L.label),
+                             need_reg ? I64(L.treg) : nullptr, need_co ? reinterpret_cast<float*>(base + L.tco) : nullptr, st);
+    if (rc) return rc;
+    NaisPairs b;
+    memset(&b, 0, sizeof(b));
+    b.hist = indices + a;
+    b.tgt = I64(L.tgt);
+    b.hreg = need_reg ? entry_region + a : nullptr;
+    b.treg = need_reg ? I64(L.treg) : nullptr;
+    b.B = R;
+    b.n_seg = 1;
+    b.seg_offsets = I64(L.seg);
+    b.row_offsets = I64(L.row);
+    b.seg_cell_offsets = I64(L.cell);
+    b.tile_seg = reinterpret_cast<int32_t*>(base + L.tseg);
+    b.tile_row0 = I64(L.trow);
+    b.n_tiles = n_tiles;
+    b.n_cells = (int64_t)R * H;
+    b.hist_coords = need_co ? entry_coords + 2 * a : nullptr;
+    b.tgt_coords = need_co ? reinterpret_cast<float*>(base + L.tco) : nullptr;
+    rc = train_step_impl(p, &b, reinterpret_cast<float*>(base + L.label), nullptr, tables, dense, losses + i, nullptr, base + L.step,
+                         workspace_bytes - L.step, st);
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 static int check_fullrank(const NaisParams* p, const NaisCatalog* cat, const NaisUsers* users, int64_t poi_begin,

@@ -151,6 +151,41 @@ class _NAISBase(nn.Module):
         self._plan_epoch = getattr(self, "_plan_epoch", 0) + 1  # the kernel stepped the tables behind torch's version counters
         return loss.detach()
 
+    def train_users(self, optimizer: torch.optim.Adagrad, batcher, uids, negative_num: int, seed: int = 0) -> torch.Tensor:
+        """The inner loop of `train_NAIS_region_distance` (run.py:227-255) — for every user: sample `negative_num` negatives per
+        positive, forward, BCELoss, backward, Adagrad step — for a whole list of users in ONE library call (`nais_train_users`):
+        the same optimizer steps in the same order as `for u in uids: fused_adagrad_step(optimizer, *batcher.multi_user_batch([u],
+        negative_num, seed + u))`, bit for bit, without the per-user Python work.  `batcher`: a batches.DeviceBatcher over the
+        train matrix.  Returns the per-user losses [len(uids)] on the device."""
+        if not isinstance(optimizer, torch.optim.Adagrad):
+            raise RuntimeError("train_users needs torch.optim.Adagrad (run.py:225)")
+        if self.variant == "disentangled" or type(self.loss_func) is not nn.BCELoss or self.loss_func.reduction != "mean":
+            raise RuntimeError("train_users: one-branch variants with the reference's mean BCELoss")
+        if self._dropout_on_l1 and self.training and self.drop.p > 0:
+            raise RuntimeError("train_users: dropout variants go through fused_adagrad_step (a fresh dropout seed per step)")
+        P = self._params()
+        group_of = {id(p): g for g in optimizer.param_groups for p in g["params"]}
+        groups = [group_of.get(id(t)) for t in P.values()]
+        if any(g is None for g in groups) or any(g["weight_decay"] != 0 or g["lr_decay"] != 0 or g.get("maximize", False) for g in groups):
+            raise RuntimeError("train_users: plain Adagrad (weight_decay = lr_decay = 0) on every parameter")
+        tg = {(group_of[id(t)]["lr"], group_of[id(t)]["eps"]) for n, t in P.items() if n in ops._TABLES}
+        dg = {(group_of[id(t)]["lr"], group_of[id(t)]["eps"]) for n, t in P.items() if n not in ops._TABLES}
+        if len(tg) != 1 or len(dg) != 1:
+            raise RuntimeError("train_users: the tables / the MLP tensors must each share lr and eps")
+        (lr_t, eps_t), (lr_d, eps_d) = next(iter(tg)), next(iter(dg))
+        sums = {n: optimizer.state[t]["sum"] for n, t in P.items()}
+        optimizer.zero_grad(set_to_none=True)
+        has_reg, has_ll = "embed_region.weight" in P, "dist_layer.weight" in P
+        losses = ops.train_users(self.variant, float(self.beta), P, sums, sums, lr_t, eps_t, lr_d, eps_d, batcher.indptr, batcher.indices,
+                                 batcher.entry_region if has_reg else None, batcher.entry_coords if has_ll else None,
+                                 batcher.region32 if has_reg else None, batcher.coords32 if has_ll else None, uids, negative_num, seed,
+                                 getattr(self, "pairs_precision", "auto") if isinstance(getattr(self, "pairs_precision", "auto"), str) else "auto")
+        n_steps = int(sum(1 for u in np.asarray(uids).reshape(-1) if batcher.indptr[int(u) + 1] > batcher.indptr[int(u)]))
+        for t in P.values():
+            optimizer.state[t]["step"] += n_steps
+        self._plan_epoch = getattr(self, "_plan_epoch", 0) + 1
+        return losses
+
     def get_mask(self, user_history, target_item):
         return user_history != target_item.reshape([len(target_item), 1])
 

