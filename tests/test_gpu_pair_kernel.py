@@ -67,3 +67,16 @@ def test_one_cta_flag_is_ignored_where_there_is_no_pair_kernel():
     a = m.predict_topk(users, 10, precision="tc_auto")
     b = m.predict_topk(users, 10, precision="tc_auto_onecta")
     assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
+
+
+def test_cta_pair_building_blocks_against_a_cpu_gemm():
+    """tests/umma_probe_pair.cu (built by __graft_entry__.build()): tcgen05 alloc / mma / commit with cta_group::2 on a cluster of
+    two CTAs — M = 256, N = 144 with each CTA staging half of B, the relay barrier, a generic-written A chunk, an e5m2 pass, the
+    multicast commit — every accumulator element equal to a CPU GEMM."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "umma_probe_pair.bin")
+    if not os.path.isfile(exe):
+        pytest.skip("probe binary not built (run __graft_entry__.build())")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "PAIR PROBE OK" in r.stdout, r.stdout + r.stderr
