@@ -928,8 +928,8 @@ size_t pairs_bwd_workspace_bytes(const NaisParams& p, const NaisPairs& b) { retu
 // streams forked from / joined to the caller's stream with events.  One pool per device, created on first use; the mutex is
 // held while a call ENQUEUES its work (cudaStreamWaitEvent binds to the record that precedes it at call time).
 struct SideStreams {
-  cudaStream_t s[2] = {nullptr, nullptr};
-  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+  cudaStream_t s[3] = {nullptr, nullptr, nullptr};  // [0], [1]: lists 1, 2; [2]: the long list's sort when it is forked ahead (phase 1)
+  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr}, sorted0 = nullptr;
   bool ok = false;
 };
 static std::mutex g_side_mu;
@@ -939,10 +939,10 @@ static SideStreams* side_streams() {  // (g_side_mu held)
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   SideStreams& S = pool[dev];
   if (!S.ok) {
-    bool good = cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming) == cudaSuccess;
-    for (int i = 0; i < 2 && good; ++i)
-      good = cudaStreamCreateWithFlags(&S.s[i], cudaStreamNonBlocking) == cudaSuccess &&
-             cudaEventCreateWithFlags(&S.join[i], cudaEventDisableTiming) == cudaSuccess;
+    bool good = cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventCreateWithFlags(&S.sorted0, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 3 && good; ++i) good = cudaStreamCreateWithFlags(&S.s[i], cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && good; ++i) good = cudaEventCreateWithFlags(&S.join[i], cudaEventDisableTiming) == cudaSuccess;
     if (!good) return nullptr;
     S.ok = true;
   }
@@ -962,10 +962,14 @@ static int launch_bwd_tile(const BwdArgs& A, int D, int grid, cudaStream_t strea
   return (int)cudaGetLastError();
 }
 
+// phase 0: the whole backward.  phase 1: only the id sorts, ALL of them on side streams (they do not depend on the gradients: the
+// one-call training step forks them before its forward so they run next to it); phase 2: the rest, on lists sorted by phase 1
+// (same p, b, g, opt, ws).  One branch in phases 1 / 2.
 int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score_parts, const float* row_sum,
                      const unsigned long long* act_mask, const float* dscore, const NaisGrads& g, const NaisAdagrad* opt, void* ws,
-                     size_t ws_bytes, cudaStream_t stream) {
+                     size_t ws_bytes, cudaStream_t stream, int phase) {
   if (pairs_n_cells(b) + b.B >= 0x7fffffffLL) return NAIS_ERR_SHAPE;
+  if (phase && p.n_branch != 1) return NAIS_ERR_MODE;
   if (opt && p.n_branch != 1) return NAIS_ERR_MODE;  // two branches share tables: two sparse steps != one dense step
   const BwdLayout L = bwd_layout(p, b);
   if (ws_bytes < L.total) return NAIS_ERR_WORKSPACE;
@@ -992,7 +996,7 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
                           br.w_poi > 0 && (g.tgt_poi[bi] || (opt && opt->sum_tgt_poi[bi])),
                           br.w_reg > 0 && (g.reg[bi] || (opt && opt->sum_reg[bi]))};
     // ---- 1. sort the ids (they do not depend on the gradients; stable radix sort: equal ids keep cell order) ----------------
-    if (want[0] || want[1] || want[2]) {
+    if (phase != 2 && (want[0] || want[1] || want[2])) {
       const int64_t n_thr = n_cells > b.B ? n_cells : b.B;
       make_keys_kernel<<<(unsigned)((n_thr + 255) / 256), 256, 0, stream>>>(
           b, p.item_num, p.region_num, want[0] ? I(L.kin[0]) : nullptr, U(L.vin[0]), want[1] ? I(L.kin[1]) : nullptr, U(L.vin[1]),
@@ -1001,14 +1005,20 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
       cudaEventRecord(side->fork, stream);
       for (int t = 2; t >= 0; --t) {  // (the caller's stream last: the side streams are busy while it sorts the long list)
         if (!want[t]) continue;
-        if (t) cudaStreamWaitEvent(side->s[t - 1], side->fork, 0);
+        cudaStream_t sort_stream = t ? side->s[t - 1] : (phase == 1 ? side->s[2] : stream);
+        if (sort_stream != stream) cudaStreamWaitEvent(sort_stream, side->fork, 0);
         const int n_rows = t == 2 ? p.region_num : p.item_num;
         int bits = 1;  // keys are 0 .. n_rows (n_rows = the "drop" key of an out-of-range id)
         while ((1ll << bits) <= n_rows && bits < 31) ++bits;
         size_t cb = L.cub_bytes;
         cub::DeviceRadixSort::SortPairs(base + L.cub[t], cb, I(L.kin[t]), I(L.kout[t]), U(L.vin[t]), U(L.vout[t]), (int)n_of[t], 0, bits,
-                                        stream_of(t));
+                                        sort_stream);
+        if (phase == 1 && t == 0) cudaEventRecord(side->sorted0, side->s[2]);
       }
+    }
+    if (phase == 1) {
+      cudaError_t e1 = cudaGetLastError();
+      return e1 == cudaSuccess ? 0 : (int)e1;
     }
     // ---- 2. the tile kernel ------------------------------------------------------------------------------------------------
     BwdArgs A;
@@ -1074,6 +1084,7 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
           bi == 0 ? g.dist_b : nullptr, p.dist_mode == NAIS_DIST_KM ? g.dist_embed : nullptr, D, bi > 0);
       NAIS_COUNT_LAUNCH(1);
     }
+    if (phase == 2 && want[0]) cudaStreamWaitEvent(stream, side->sorted0, 0);  // the long list was sorted on a side stream
     if (want[0]) seg(0, 0, br.w_poi, p.item_num, dest(g.hist_poi[bi], br.hist_poi, opt ? opt->sum_hist_poi[bi] : nullptr, g.remap_hist_poi[bi]));
     if (want[1]) seg(1, 0, br.w_poi, p.item_num, dest(g.tgt_poi[bi], br.tgt_poi, opt ? opt->sum_tgt_poi[bi] : nullptr, g.remap_tgt_poi[bi]));
     // (history-side and target-side region rows are one table in every variant: hist_reg == tgt_reg)

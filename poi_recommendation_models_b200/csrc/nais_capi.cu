@@ -23,7 +23,7 @@ int choose_splits(int n_users, int64_t range);
 size_t pairs_bwd_workspace_bytes(const NaisParams& p, const NaisPairs& b);
 int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score_parts, const float* row_sum,
                      const unsigned long long* act_mask, const float* dscore, const NaisGrads& g, const NaisAdagrad* opt, void* ws,
-                     size_t ws_bytes, cudaStream_t stream);
+                     size_t ws_bytes, cudaStream_t stream, int phase = 0);
 bool pairs_tc_bwd_supported(const NaisParams& p, const NaisPairs& b);
 size_t rows_adagrad_workspace_bytes(int64_t n, int w);
 int launch_rows_adagrad(const int32_t* keys, const float* rows, int64_t n, int w, int n_rows, float* grad_out, float* param, float* sum,
@@ -390,6 +390,19 @@ static int train_step_impl(const NaisParams* p, const NaisPairs* batch, const fl
   if (workspace_bytes < L.total) return NAIS_ERR_WORKSPACE;
   char* base = reinterpret_cast<char*>(workspace);
   auto F = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
+  // the gradient scratch of the MLP / distance layer (also tells the backward which lists it needs)
+  NaisGrads g;
+  memset(&g, 0, sizeof(g));
+  g.w1[0] = F(L.gw1);
+  g.b1[0] = F(L.gb1);
+  g.w2[0] = F(L.gw2);
+  if (p->dist_mode == NAIS_DIST_LATLON) {
+    g.dist_w = F(L.gdw);
+    g.dist_b = F(L.gdb);
+  }
+  // the id sorts of the backward depend on the batch only: forked onto side streams now, they run next to the forward
+  rc = launch_pairs_bwd(*p, *batch, nullptr, nullptr, nullptr, nullptr, g, tables, base + L.bwd, workspace_bytes - L.bwd, st, 1);
+  if (rc) return rc;
   // forward
   const bool tc_ok = pairs_tc_supported(*p, *batch) && device_is_sm100();
   if (p->pairs_precision == NAIS_PAIRS_TC && !tc_ok) return NAIS_ERR_SHAPE;
@@ -405,16 +418,7 @@ static int train_step_impl(const NaisParams* p, const NaisPairs* batch, const fl
   rc = launch_bce_dscore(F(L.score), label, row_weight, batch->B, F(L.dscore), loss, st);
   if (rc) return rc;
   // backward: MLP / distance-layer gradients to scratch, tables stepped in place
-  NaisGrads g;
-  memset(&g, 0, sizeof(g));
-  g.w1[0] = F(L.gw1);
-  g.b1[0] = F(L.gb1);
-  g.w2[0] = F(L.gw2);
-  if (p->dist_mode == NAIS_DIST_LATLON) {
-    g.dist_w = F(L.gdw);
-    g.dist_b = F(L.gdb);
-  }
-  rc = launch_pairs_bwd(*p, *batch, F(L.parts), F(L.row_sum), mask, F(L.dscore), g, tables, base + L.bwd, workspace_bytes - L.bwd, st);
+  rc = launch_pairs_bwd(*p, *batch, F(L.parts), F(L.row_sum), mask, F(L.dscore), g, tables, base + L.bwd, workspace_bytes - L.bwd, st, 2);
   if (rc) return rc;
   const NaisBranch& br = p->branch[0];
   const int lanes = p->dist_mode == NAIS_DIST_LATLON ? 2 : 0, ldw = br.w_poi + br.w_reg + lanes;
