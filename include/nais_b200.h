@@ -294,10 +294,11 @@ NAIS_API int nais_pairs_train_step(const NaisParams* p, const NaisPairs* batch, 
  * nais_pairs_train_step with the batch-mean BCE, enqueued back to back with no host work in between but the launches (~15 per
  * user).  The user's history is the slice [host_indptr[u], host_indptr[u + 1]) of `indices` (the train matrix' CSR; no copy);
  * entry_region / entry_coords are the region id / centred (lat, lon) of every CSR entry (region[indices], coords[indices]; NULL
- * when the variant has no region table / distance lanes).  host_indptr and host_users are HOST arrays (read during the call).
+ * when the variant has no region table / distance lanes).  host_indptr [n_rows + 1] and host_users are HOST arrays (read during
+ * the call; a user id outside [0, n_rows) is an argument error).
  * User i samples with seed + host_users[i].  losses: device float[n_users] (0 for a user without history).  One branch only. */
 NAIS_API size_t nais_train_users_workspace_bytes(const NaisParams* p, int32_t max_hist, int32_t num_ng);
-NAIS_API int nais_train_users(const NaisParams* p, const int64_t* host_indptr, const int64_t* indices, const int64_t* entry_region,
+NAIS_API int nais_train_users(const NaisParams* p, const int64_t* host_indptr, int64_t n_rows, const int64_t* indices, const int64_t* entry_region,
                               const float* entry_coords, const int32_t* poi_region, const float* poi_coords, const int64_t* host_users,
                               int32_t n_users, int32_t num_ng, uint64_t seed, const NaisAdagrad* tables, const NaisDenseAdagrad* dense,
                               float* losses, void* workspace, size_t workspace_bytes, nais_stream_t stream);

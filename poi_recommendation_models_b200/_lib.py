@@ -82,7 +82,7 @@ SYMBOLS = {
     "nais_pairs_train_step": (C.c_int, [C.POINTER(NaisParams), C.POINTER(NaisPairs), C.c_void_p, C.c_void_p, C.POINTER(NaisAdagrad),
                                         C.POINTER(NaisDenseAdagrad), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nais_train_users_workspace_bytes": (C.c_size_t, [C.POINTER(NaisParams), C.c_int32, C.c_int32]),
-    "nais_train_users": (C.c_int, [C.POINTER(NaisParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+    "nais_train_users": (C.c_int, [C.POINTER(NaisParams), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.POINTER(NaisAdagrad), C.POINTER(NaisDenseAdagrad),
                                    C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nais_rows_adagrad_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),

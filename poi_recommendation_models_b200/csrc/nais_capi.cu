@@ -488,7 +488,7 @@ size_t nais_train_users_workspace_bytes(const NaisParams* p, int32_t max_hist, i
   return users_layout(*p, max_hist, num_ng).total;
 }
 
-int nais_train_users(const NaisParams* p, const int64_t* host_indptr, const int64_t* indices, const int64_t* entry_region,
+int nais_train_users(const NaisParams* p, const int64_t* host_indptr, int64_t n_rows, const int64_t* indices, const int64_t* entry_region,
                      const float* entry_coords, const int32_t* poi_region, const float* poi_coords, const int64_t* host_users,
                      int32_t n_users, int32_t num_ng, uint64_t seed, const NaisAdagrad* tables, const NaisDenseAdagrad* dense, float* losses,
                      void* workspace, size_t workspace_bytes, nais_stream_t stream) {
@@ -505,7 +505,7 @@ int nais_train_users(const NaisParams* p, const int64_t* host_indptr, const int6
   int max_hist = 0;
   for (int i = 0; i < n_users; ++i) {
     const int64_t u = host_users[i];
-    if (u < 0) return NAIS_ERR_SHAPE;
+    if (u < 0 || u >= n_rows) return NAIS_ERR_SHAPE;
     const int64_t H = host_indptr[u + 1] - host_indptr[u];
     if (H < 0 || H > 0x7fffffff / (num_ng + 2)) return NAIS_ERR_SHAPE;
     if ((int)H > max_hist) max_hist = (int)H;

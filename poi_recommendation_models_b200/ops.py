@@ -614,7 +614,7 @@ def train_users(variant: str, beta: float, P: Dict[str, torch.Tensor], table_sum
         losses = torch.empty(max(hu.size, 1), device=dev, dtype=torch.float32)
         ws_bytes = lib.nais_train_users_workspace_bytes(C.byref(p), max(max_hist, 1), int(num_ng))
         ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
-        _lib.check(lib.nais_train_users(C.byref(p), hp.ctypes.data, indices.data_ptr(), _ptr(er), _ptr(ec), _ptr(pr), _ptr(pc),
+        _lib.check(lib.nais_train_users(C.byref(p), hp.ctypes.data, int(hp.size) - 1, indices.data_ptr(), _ptr(er), _ptr(ec), _ptr(pr), _ptr(pc),
                                         hu.ctypes.data, int(hu.size), int(num_ng), int(seed) & (2 ** 64 - 1), C.byref(o), C.byref(d),
                                         losses.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "nais_train_users")
         _poll_bad_index(dev)

@@ -265,6 +265,13 @@ def test_precision_flags_and_train_step_entry_validate():
         setattr(p.branch[0], f, 16)  # (never dereferenced: the argument checks run first)
     b.H = 4
     assert lib.nais_pairs_train_step(C.byref(p), C.byref(b), None, None, None, None, None, None, None, 0, None) == -1  # NULL optimizer state
+    ad, dn = _lib.NaisAdagrad(), _lib.NaisDenseAdagrad()
+    for f in ("sum_w1", "sum_b1", "sum_w2"):
+        setattr(dn, f, 16)
+    indptr, users = np.array([0, 3, 5], dtype=np.int64), np.array([2], dtype=np.int64)  # user 2 of a 2-row matrix
+    assert lib.nais_train_users(C.byref(p), indptr.ctypes.data, 2, 16, None, None, None, None, users.ctypes.data, 1, 4, 0, C.byref(ad),
+                                C.byref(dn), 16, 16, 1 << 20, None) == -2                                     # user id outside the matrix
+    assert lib.nais_train_users_workspace_bytes(C.byref(p), 100, 4) > 0
 
 
 def test_segment_structure_rides_in_one_upload():
