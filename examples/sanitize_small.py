@@ -46,14 +46,26 @@ def main():
         m.eval()
         m.set_catalog(region=data.region, coords=data.coords)
         users = m.make_users(data.indptr, data.indices)
-        precs = ("fp32",) if "disentangled" in name else ("fp32", "tc_split", "tc_mix", "tc_fast")
+        # (two branches: one tensor pass per branch + haversine in the epilogue; one branch: the CTA-pair and the one-CTA kernels)
+        precs = ("fp32", "tc_split", "tc_mix") if "disentangled" in name else ("fp32", "tc_split", "tc_mix", "tc_fast", "tc_auto_onecta")
         outs = []
         for prec in precs:
             outs.append(ops.fullrank_topk(m.variant, 0.5, m._params(), m._catalog, users, 10, precision=prec))
             ops.fullrank_scores(m.variant, 0.5, m._params(), m._catalog, users, 0, 300, precision=prec)
         ops.topk_merge(torch.stack([o[0] for o in outs], 1), torch.stack([o[1] for o in outs], 1))
+        if "disentangled" not in name:  # the one-call optimizer step and the in-library user loop (device sampler, BCE, Adagrad)
+            from poi_recommendation_models_b200 import batches as PB
+            m.train()
+            if hasattr(m, "drop"):
+                m.drop.p = 0.0
+            opt = torch.optim.Adagrad(m.parameters(), lr=0.01)
+            bt = PB.DeviceBatcher(data.train_csr(), data.region, data.coords, device=dev, seed=0)
+            b = bt.multi_user_batch(np.arange(4), 4, seed=1)
+            m.fused_adagrad_step(opt, b.label, b)
+            m.train_users(opt, bt, np.arange(6), 4, seed=2)
+        ops.check_indices(sync=True)
         torch.cuda.synchronize()
-        print(name, "ok", float(s.sum()))
+        print(name, "ok", float(s.detach().sum()))
 
 
 if __name__ == "__main__":
