@@ -226,6 +226,21 @@ NAIS_API int nais_pairs_backward(const NaisParams* p, const NaisPairs* batch, co
                         const uint64_t* act_mask, const float* dscore, const NaisGrads* grads, void* workspace,
                         size_t workspace_bytes, nais_stream_t stream);
 
+/* The pair above for a training step whose backward is known to follow (the torch.autograd.Function of the Python host layer):
+ * the backward's three id sorts depend on the batch only, so nais_pairs_forward_presort forks them onto the library's side streams
+ * BEFORE it enqueues the forward kernel (they run next to it: -50 us of a C3-sized step) and joins them to `stream` before it
+ * returns — everything enqueued on `stream` afterwards is ordered after the sorts, and `bwd_workspace` may be released like any
+ * other buffer of the call.  `grads`: only the NULL-ness of the table pointers (hist_poi / tgt_poi / reg, [0]) is read — it must
+ * match the NaisGrads of the backward.  nais_pairs_backward_presorted is nais_pairs_backward on the lists that call left in the
+ * workspace: same p, batch and workspace (nais_pairs_backward_workspace_bytes; contents untouched in between); one use per
+ * presort.  One branch only (NAIS_ERR_MODE otherwise: use the plain pair). */
+NAIS_API int nais_pairs_forward_presort(const NaisParams* p, const NaisPairs* batch, const NaisGrads* grads, float* score,
+                               float* row_sum, float* score_parts, uint64_t* act_mask, void* bwd_workspace,
+                               size_t bwd_workspace_bytes, nais_stream_t stream);
+NAIS_API int nais_pairs_backward_presorted(const NaisParams* p, const NaisPairs* batch, const float* score_parts, const float* row_sum,
+                                  const uint64_t* act_mask, const float* dscore, const NaisGrads* grads, void* workspace,
+                                  size_t workspace_bytes, nais_stream_t stream);
+
 /* One row-sparse Adagrad step from a key-ordered list of (table row id, gradient row) pairs — the union of the touched-row lists
  * the ranks of a data-parallel step exchange (SURVEY.md §8e 'Train partitioning').  keys [n] int32 ascending (equal ids
  * adjacent: their rows are summed first, in list order — deterministic, identical on every rank that holds the same list),

@@ -92,6 +92,10 @@ SYMBOLS = {
                                     C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nais_pairs_backward": (C.c_int, [C.POINTER(NaisParams), C.POINTER(NaisPairs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.POINTER(NaisGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nais_pairs_forward_presort": (C.c_int, [C.POINTER(NaisParams), C.POINTER(NaisPairs), C.POINTER(NaisGrads), C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nais_pairs_backward_presorted": (C.c_int, [C.POINTER(NaisParams), C.POINTER(NaisPairs), C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.POINTER(NaisGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
     "nais_pairs_backward_adagrad": (C.c_int, [C.POINTER(NaisParams), C.POINTER(NaisPairs), C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.POINTER(NaisGrads), C.POINTER(NaisAdagrad), C.c_void_p, C.c_size_t,
                                               C.c_void_p]),

@@ -964,7 +964,9 @@ static int launch_bwd_tile(const BwdArgs& A, int D, int grid, cudaStream_t strea
 
 // phase 0: the whole backward.  phase 1: only the id sorts, ALL of them on side streams (they do not depend on the gradients: the
 // one-call training step forks them before its forward so they run next to it); phase 2: the rest, on lists sorted by phase 1
-// (same p, b, g, opt, ws).  One branch in phases 1 / 2.
+// (same p, b, g, opt, ws).  phase 4: join the sort streams of a phase-1 call to `stream` (the forward of the autograd path ends with
+// it, so that nothing enqueued on `stream` later — or the caller's allocator — can overtake the sorts); phase 3: phase 2 after such
+// a join (no wait of its own for the long list).  One branch in phases 1 - 4.
 int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score_parts, const float* row_sum,
                      const unsigned long long* act_mask, const float* dscore, const NaisGrads& g, const NaisAdagrad* opt, void* ws,
                      size_t ws_bytes, cudaStream_t stream, int phase) {
@@ -996,7 +998,7 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
                           br.w_poi > 0 && (g.tgt_poi[bi] || (opt && opt->sum_tgt_poi[bi])),
                           br.w_reg > 0 && (g.reg[bi] || (opt && opt->sum_reg[bi]))};
     // ---- 1. sort the ids (they do not depend on the gradients; stable radix sort: equal ids keep cell order) ----------------
-    if (phase != 2 && (want[0] || want[1] || want[2])) {
+    if (phase < 2 && (want[0] || want[1] || want[2])) {
       const int64_t n_thr = n_cells > b.B ? n_cells : b.B;
       make_keys_kernel<<<(unsigned)((n_thr + 255) / 256), 256, 0, stream>>>(
           b, p.item_num, p.region_num, want[0] ? I(L.kin[0]) : nullptr, U(L.vin[0]), want[1] ? I(L.kin[1]) : nullptr, U(L.vin[1]),
@@ -1016,7 +1018,15 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
         if (phase == 1 && t == 0) cudaEventRecord(side->sorted0, side->s[2]);
       }
     }
-    if (phase == 1) {
+    if (phase == 4) {
+      for (int t = 0; t < 3; ++t) {
+        if (!want[t]) continue;
+        cudaEvent_t ev = t ? side->join[t - 1] : side->sorted0;
+        cudaEventRecord(ev, t ? side->s[t - 1] : side->s[2]);
+        cudaStreamWaitEvent(stream, ev, 0);
+      }
+    }
+    if (phase == 1 || phase == 4) {
       cudaError_t e1 = cudaGetLastError();
       return e1 == cudaSuccess ? 0 : (int)e1;
     }

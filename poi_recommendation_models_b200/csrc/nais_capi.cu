@@ -300,6 +300,53 @@ int nais_pairs_backward(const NaisParams* p, const NaisPairs* batch, const float
                           nullptr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+// Training forward of the autograd path: the coming backward's id sorts are forked onto the side streams, the forward kernel runs
+// next to them on the caller's stream, and the sorts are joined back before the call returns.
+int nais_pairs_forward_presort(const NaisParams* p, const NaisPairs* batch, const NaisGrads* grads, float* score, float* row_sum,
+                               float* score_parts, uint64_t* act_mask, void* bwd_workspace, size_t bwd_workspace_bytes,
+                               nais_stream_t stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  rc = check_pairs(p, batch);
+  if (rc) return rc;
+  if (!grads) return NAIS_ERR_NULL;
+  if (p->n_branch != 1) return NAIS_ERR_MODE;
+  if (batch->B && !score) return NAIS_ERR_NULL;
+  if (batch->B == 0) return 0;
+  if (!bwd_workspace) return NAIS_ERR_NULL;
+  if (!aligned16(bwd_workspace)) return NAIS_ERR_ALIGN;
+  if (bwd_workspace_bytes < pairs_bwd_workspace_bytes(*p, *batch)) return NAIS_ERR_WORKSPACE;
+  const bool tc_ok = pairs_tc_supported(*p, *batch) && device_is_sm100();
+  if (p->pairs_precision == NAIS_PAIRS_TC && !tc_ok) return NAIS_ERR_SHAPE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = launch_pairs_bwd(*p, *batch, nullptr, nullptr, nullptr, nullptr, *grads, nullptr, bwd_workspace, bwd_workspace_bytes, st, 1);
+  if (rc) return rc;
+  if (p->pairs_precision != NAIS_PAIRS_FP32 && tc_ok)
+    rc = launch_pairs_fwd_tc(*p, *batch, score, row_sum, score_parts, reinterpret_cast<unsigned long long*>(act_mask), st);
+  else
+    rc = launch_pairs_fwd(*p, *batch, score, row_sum, score_parts, st);
+  // (also after a failed forward launch: the caller may release the workspace as soon as this returns)
+  const int rj = launch_pairs_bwd(*p, *batch, nullptr, nullptr, nullptr, nullptr, *grads, nullptr, bwd_workspace, bwd_workspace_bytes, st, 4);
+  return rc ? rc : rj;
+}
+
+int nais_pairs_backward_presorted(const NaisParams* p, const NaisPairs* batch, const float* score_parts, const float* row_sum,
+                                  const uint64_t* act_mask, const float* dscore, const NaisGrads* grads, void* workspace,
+                                  size_t workspace_bytes, nais_stream_t stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  rc = check_pairs(p, batch);
+  if (rc) return rc;
+  if (!grads) return NAIS_ERR_NULL;
+  if (p->n_branch != 1) return NAIS_ERR_MODE;
+  if (batch->B == 0) return 0;
+  if (!score_parts || !row_sum || !dscore || !workspace) return NAIS_ERR_NULL;
+  if (!aligned16(workspace)) return NAIS_ERR_ALIGN;
+  if (workspace_bytes < pairs_bwd_workspace_bytes(*p, *batch)) return NAIS_ERR_WORKSPACE;
+  return launch_pairs_bwd(*p, *batch, score_parts, row_sum, reinterpret_cast<const unsigned long long*>(act_mask), dscore, *grads,
+                          nullptr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream), 3);
+}
+
 int nais_pairs_backward_adagrad(const NaisParams* p, const NaisPairs* batch, const float* score_parts, const float* row_sum,
                                 const uint64_t* act_mask, const float* dscore, const NaisGrads* grads, const NaisAdagrad* opt,
                                 void* workspace, size_t workspace_bytes, nais_stream_t stream) {

@@ -304,9 +304,27 @@ def pairs_dispatch(p: NaisParams, b: NaisPairs) -> Tuple[bool, bool]:
     return bool(f.value), bool(g.value)
 
 
-def _forward_launch(lib, p: NaisParams, b: NaisPairs, dev, want_mask: bool = True):
-    """nais_pairs_forward -> (score, row_sum, parts, act_mask): act_mask is the ReLU pattern the tcgen05 forward saves for the
-    tcgen05 backward (int64 [B*H]; None when the FP32 forward runs or hid > 64)."""
+# The autograd forward sorts the coming backward's id lists next to its own kernel (nais_pairs_forward_presort: the sorts depend on
+# the batch only; -50 us of a C3-sized step).  The backward workspace then lives from forward to backward instead of inside the
+# backward call; set to False to keep it transient (e.g. many forwards of large batches before the first backward).
+PRESORT_IN_FORWARD = True
+
+
+def _table_grads_skeleton(variant: str, ptr: int) -> NaisGrads:
+    """The NaisGrads of a dense-table backward with every wanted table pointer set to `ptr` — what nais_pairs_forward_presort
+    reads (NULL-ness only) to know which id lists the backward of `pairs_backward_raw(tables=True)` will reduce."""
+    g = NaisGrads()
+    g.hist_poi[0] = g.tgt_poi[0] = ptr
+    if variant in ("region", "region_distance"):
+        g.reg[0] = ptr
+    return g
+
+
+def _forward_launch(lib, p: NaisParams, b: NaisPairs, dev, want_mask: bool = True, presort_variant: Optional[str] = None):
+    """nais_pairs_forward -> (score, row_sum, parts, act_mask, presorted workspace): act_mask is the ReLU pattern the tcgen05
+    forward saves for the tcgen05 backward (int64 [B*H]; None when the FP32 forward runs or hid > 64).  With `presort_variant`
+    (one-branch variants) the call is nais_pairs_forward_presort and the last element is the backward workspace holding the
+    sorted id lists for nais_pairs_backward_presorted; else None."""
     B = b.B
     score = torch.empty(B, device=dev, dtype=torch.float32)
     row_sum = torch.empty(p.n_branch, B, device=dev, dtype=torch.float32)
@@ -314,9 +332,18 @@ def _forward_launch(lib, p: NaisParams, b: NaisPairs, dev, want_mask: bool = Tru
     mask = None
     if want_mask and B and p.n_branch == 1 and p.hid <= 64 and pairs_dispatch(p, b)[0]:
         mask = torch.empty(b.n_cells if b.seg_offsets else B * b.H, device=dev, dtype=torch.int64)
+    # (the backward tiles exist for D, hid <= 128: a wider forward-only shape keeps the plain call)
+    if presort_variant is not None and B and p.n_branch == 1 and p.hid <= 128 and p.branch[0].w_poi + p.branch[0].w_reg <= 128:
+        ws_bytes = lib.nais_pairs_backward_workspace_bytes(C.byref(p), C.byref(b))
+        ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
+        g = _table_grads_skeleton(presort_variant, ws.data_ptr())
+        _lib.check(lib.nais_pairs_forward_presort(C.byref(p), C.byref(b), C.byref(g), score.data_ptr(), row_sum.data_ptr(),
+                                                  parts.data_ptr(), _ptr(mask), ws.data_ptr(), ws_bytes, _stream()),
+                   "nais_pairs_forward_presort")
+        return score, row_sum, parts, mask, ws
     _lib.check(lib.nais_pairs_forward(C.byref(p), C.byref(b), score.data_ptr(), row_sum.data_ptr(), parts.data_ptr(), _ptr(mask),
                                       _stream()), "nais_pairs_forward")
-    return score, row_sum, parts, mask
+    return score, row_sum, parts, mask, None
 
 
 # gradients param_reduce_kernel writes in full (csrc/nais_bwd.cu): no zero fill needed; every other tensor has rows / entries the
@@ -348,9 +375,13 @@ class _PairsFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             p = build_params(variant, P, beta, keep, drop[0], drop[1], _fwd_bwd(drop[2])[0])
             b = _pairs_struct(hist, tgt, hreg, treg, aux, keep)
-            need_bwd = any(t.requires_grad for t in params)
-            score, row_sum, parts, mask = _forward_launch(lib, p, b, dev, want_mask=need_bwd)
+            need_bwd = any(t.requires_grad for t in params) and (len(drop) < 4 or bool(drop[3]))  # drop[3]: grad mode at the call
+            # (the forward and the backward must agree on the pair kernels' precision for the lists / workspace to match)
+            presort = need_bwd and PRESORT_IN_FORWARD and _fwd_bwd(drop[2])[0] == _fwd_bwd(drop[2])[1]
+            score, row_sum, parts, mask, ws = _forward_launch(lib, p, b, dev, want_mask=need_bwd,
+                                                              presort_variant=variant if presort else None)
             _poll_bad_index(dev)
+        ctx.presorted_ws = ws  # (not an input or an output: rides on ctx; used once)
         ctx.variant, ctx.beta, ctx.drop = variant, beta, drop
         ctx.seg = hist if isinstance(hist, SegmentedPairs) else None  # (not a tensor: rides on ctx)
         e = torch.empty(0)
@@ -371,17 +402,20 @@ class _PairsFunction(torch.autograd.Function):
         mask = mask if ctx.has[3] else None
         names = VARIANT_PARAMS[ctx.variant]
         P = dict(zip(names, params))
-        G = pairs_backward_raw(ctx.variant, ctx.beta, P, hist, tgt, hreg, treg, aux, row_sum, parts, dscore, ctx.drop, act_mask=mask)
+        ws, ctx.presorted_ws = ctx.presorted_ws, None  # (a second backward through a retained graph sorts again)
+        G = pairs_backward_raw(ctx.variant, ctx.beta, P, hist, tgt, hreg, treg, aux, row_sum, parts, dscore, ctx.drop, act_mask=mask,
+                               presorted_ws=ws)
         grads = tuple(G[n].to(P[n].dtype) if ctx.needs_input_grad[8 + i] else None for i, n in enumerate(names))
         return (None, None, None, None, None, None, None, None) + grads
 
 
 def pairs_backward_raw(variant: str, beta: float, P: Dict[str, torch.Tensor], hist, tgt, hreg, treg, aux, row_sum, parts, dscore,
-                       drop=(0.0, 0, "auto"), tables: bool = True, act_mask: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                       drop=(0.0, 0, "auto"), tables: bool = True, act_mask: Optional[torch.Tensor] = None,
+                       presorted_ws: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """nais_pairs_backward: every parameter gradient of `pairs_score` given dscore [B] and the forward's saved row sums / per-
     branch scores (/ ReLU pattern `act_mask`, when the tcgen05 forward produced one), as a dict of dense float32 tensors (zero
     rows for untouched table rows).  `tables=False` skips the embedding tables (no sort, no segment reduce): the attention-MLP /
-    dist-layer gradients only."""
+    dist-layer gradients only.  `presorted_ws`: the workspace nais_pairs_forward_presort left for this batch (`tables=True`)."""
     dev = _need_cuda(hist, tgt, dscore, *P.values())
     lib = _lib.load()
     keep: List[torch.Tensor] = []
@@ -406,10 +440,15 @@ def pairs_backward_raw(variant: str, beta: float, P: Dict[str, torch.Tensor], hi
                                          G["region_attn_layer2.weight"].data_ptr())
             g.dist_embed = G["embed_distance.weight"].data_ptr()
         ws_bytes = lib.nais_pairs_backward_workspace_bytes(C.byref(p), C.byref(b))
-        ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
         ds = _f32(dscore)
-        _lib.check(lib.nais_pairs_backward(C.byref(p), C.byref(b), parts.data_ptr(), row_sum.data_ptr(), _ptr(act_mask), ds.data_ptr(),
-                                           C.byref(g), ws.data_ptr(), ws_bytes, _stream()), "nais_pairs_backward")
+        if presorted_ws is not None and tables and p.n_branch == 1 and presorted_ws.numel() >= ws_bytes:
+            _lib.check(lib.nais_pairs_backward_presorted(C.byref(p), C.byref(b), parts.data_ptr(), row_sum.data_ptr(), _ptr(act_mask),
+                                                         ds.data_ptr(), C.byref(g), presorted_ws.data_ptr(), ws_bytes, _stream()),
+                       "nais_pairs_backward_presorted")
+        else:
+            ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
+            _lib.check(lib.nais_pairs_backward(C.byref(p), C.byref(b), parts.data_ptr(), row_sum.data_ptr(), _ptr(act_mask),
+                                               ds.data_ptr(), C.byref(g), ws.data_ptr(), ws_bytes, _stream()), "nais_pairs_backward")
         _poll_bad_index(dev)
     return G
 
@@ -420,7 +459,7 @@ def pairs_score(variant: str, beta: float, params: Sequence[torch.Tensor], hist,
     `dropout_p > 0` applies the train-mode dropout of NAIS_basic / NAIS_regionEmbedding (model.py:71,162) with the
     counter-based mask of NaisParams::dropout_seed; backward regenerates the same mask.  `pairs_precision`: "auto" = the
     tcgen05 forward / backward kernels where the shape has them (else the FP32 kernels), "fp32", "tc"."""
-    return _PairsFunction.apply(variant, beta, (float(dropout_p), int(dropout_seed), pairs_precision), hist, tgt, hreg, treg, aux,
+    return _PairsFunction.apply(variant, beta, (float(dropout_p), int(dropout_seed), pairs_precision, torch.is_grad_enabled()), hist, tgt, hreg, treg, aux,
                                 *params)
 
 
@@ -630,7 +669,7 @@ def pairs_forward_raw(variant: str, beta: float, P: Dict[str, torch.Tensor], his
     with torch.cuda.device(dev):
         p = build_params(variant, P, beta, keep, drop[0], drop[1], _fwd_bwd(drop[2])[0])
         b = _pairs_struct(hist, tgt, hreg, treg, aux, keep)
-        score, row_sum, parts, mask = _forward_launch(lib, p, b, dev)
+        score, row_sum, parts, mask, _ = _forward_launch(lib, p, b, dev)
         _poll_bad_index(dev)
     return score, row_sum, parts, mask
 

@@ -219,3 +219,43 @@ def test_device_batcher_layout_and_distribution():
     expected = 40 * 4 * len(data.history(0)) / len(nonvis)
     assert counts[data.history(0)].sum() == 0 and abs(counts[nonvis].mean() - expected) < 1e-9
     assert counts[nonvis].std() < 3 * np.sqrt(expected)  # roughly uniform over the non-visited POIs
+
+
+@pytest.mark.parametrize("variant", ["basic", "region", "distance", "region_distance"])
+def test_presorted_backward_is_bit_identical(variant):
+    """The autograd forward sorts the backward's id lists next to its kernel (nais_pairs_forward_presort /
+    nais_pairs_backward_presorted): same stable sort, same reduce order => the gradients of the plain pair, bit for bit.  Also:
+    two forwards before their backwards (the side streams and their events are shared), a retained graph's second backward
+    (sorts again), and a forward whose backward never runs."""
+    from poi_recommendation_models_b200 import ops
+    rng = np.random.default_rng(11)
+    N, D, hid, B, H = 500, 64, 64, 96, 37
+    coords, region, R = synthetic.make_catalog(N, seed=2)
+    sd = orc.init_state(variant, N, D, hid, R, 1, seed=4, style="trained")
+
+    def batch():
+        hist = np.stack([rng.choice(N, H, replace=False) for _ in range(B)]).astype(np.int64)
+        tgt = rng.integers(0, N, B).astype(np.int64)
+        tgt[::4] = hist[::4, 3]
+        return hist, tgt, orc.latlon_abs_diff(coords, tgt, hist), rng.normal(size=B)
+
+    b1, b2 = batch(), batch()
+
+    def run(presort, order):
+        ops.PRESORT_IN_FORWARD = presort
+        try:
+            m = util.make_model(variant, sd, 0.5)
+            s = [util.call(m, variant, _dev(h), _dev(t), _dev(region[h]), _dev(region[t]), _dev(a), pre_sigmoid=True) for h, t, a, _ in (b1, b2)]
+            _ = util.call(m, variant, _dev(b1[0]), _dev(b1[1]), _dev(region[b1[0]]), _dev(region[b1[1]]), _dev(b1[2]), pre_sigmoid=True)  # never differentiated
+            for i in order:
+                (s[i] * _dev((b1, b2)[i][3]).float()).sum().backward(retain_graph=True)
+            torch.cuda.synchronize()
+            return {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
+        finally:
+            ops.PRESORT_IN_FORWARD = True
+
+    for order in ((0, 1), (1, 0), (0, 0, 1)):
+        a, b = run(True, order), run(False, order)
+        assert a.keys() == b.keys()
+        for n in a:
+            assert torch.equal(a[n], b[n]), (variant, order, n, (a[n] - b[n]).abs().max().item())
