@@ -15,12 +15,13 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer into memory owned by the caller (PyTorch tensors); the library never
- *     allocates, frees or synchronises, and enqueues only on the given stream (one documented exception: nais_pairs_backward
- *     forks two library-owned side streams from it and joins them back before it returns);
+ *     allocates, frees or synchronises, and enqueues only on the given stream (documented exceptions: the pair backward /
+ *     training entry points fork library-owned side streams from it and join them back before they return);
  *   - return 0 = OK; negative = argument error found before any launch (see NAIS_ERR_*); positive = cudaError_t;
  *   - all entry points are stateless and re-entrant (no environment variables, no hidden switches: every option is an
  *     argument or a struct field declared here); one host thread per GPU is the intended use.  Library-owned state per device:
- *     a 4-byte "bad index" word (nais_poll_bad_index) and the two side streams + three events of nais_pairs_backward;
+ *     a 4-byte "bad index" word (nais_poll_bad_index), the side streams + events of nais_pairs_backward and the preparation
+ *     stream of nais_train_users;
  *   - no C++ types, no torch types: plain pointers and sizes.
  */
 #ifndef NAIS_B200_H_
@@ -311,7 +312,12 @@ NAIS_API int nais_pairs_train_step(const NaisParams* p, const NaisPairs* batch, 
  * entry_region / entry_coords are the region id / centred (lat, lon) of every CSR entry (region[indices], coords[indices]; NULL
  * when the variant has no region table / distance lanes).  host_indptr [n_rows + 1] and host_users are HOST arrays (read during
  * the call; a user id outside [0, n_rows) is an argument error).
- * User i samples with seed + host_users[i].  losses: device float[n_users] (0 for a user without history).  One branch only. */
+ * User i samples with seed + host_users[i].  losses: device float[n_users] (0 for a user without history).  One branch only.
+ * Streams: what depends on the batch only (segment structure, sampler, the id sorts of the backward) is enqueued ONE USER AHEAD on
+ * a library-owned preparation stream (one per device, created on first use) into the other half of the workspace, so the chain
+ * of dependent launches per optimizer step is forward -> BCE -> backward -> Adagrad; the preparation stream starts after the work
+ * already in `stream` and everything it does is consumed by work in `stream` before the call's last launch (events created and
+ * destroyed inside the call).  Same kernels on the same inputs per user: results are those of the sequential loop, bit for bit. */
 NAIS_API size_t nais_train_users_workspace_bytes(const NaisParams* p, int32_t max_hist, int32_t num_ng);
 NAIS_API int nais_train_users(const NaisParams* p, const int64_t* host_indptr, int64_t n_rows, const int64_t* indices, const int64_t* entry_region,
                               const float* entry_coords, const int32_t* poi_region, const float* poi_coords, const int64_t* host_users,

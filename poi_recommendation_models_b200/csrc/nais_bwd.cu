@@ -673,12 +673,25 @@ __global__ void segment_reduce_pass1_kernel(const int* __restrict__ keys, const 
 #pragma unroll
       for (int q = 0; q < NQ; ++q) r[u][q] = (j < cnt && col[q]) ? __ldcs(row + lane + 32 * q) : 0.f;
     }
+    // Fused Adagrad: a finished run's update reads its `sum` and `param` rows before it writes them, so a flush per run is a
+    // chain of dependent load -> store round trips (ncu launch list of one-user steps: 85 us for ONE 64-entry chunk of unique
+    // keys, the target list — the longest kernel of the step).  The runs that end inside this batch are collected (keys are
+    // warp-uniform) and updated together after it: all their loads first, then the same arithmetic, then the stores.
+    int fkey[SEG_ILP];
+    float facc[SEG_ILP][NQ];
 #pragma unroll
     for (int u = 0; u < SEG_ILP; ++u) {
       const int j = j0 + u;
+      fkey[u] = -1;
       if (j < cnt) {
         if (j > 0 && ((starts >> j) & 1ull)) {
-          flush(j);
+          if (out.param && key < n_rows && !(run_a == 0 && key == key_before)) {
+            fkey[u] = key;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) facc[u][q] = acc[q];
+          } else {
+            flush(j);
+          }
           run_a = j;
           key = j < 32 ? __shfl_sync(0xffffffffu, k0, j) : __shfl_sync(0xffffffffu, k1, j - 32);
 #pragma unroll
@@ -687,6 +700,33 @@ __global__ void segment_reduce_pass1_kernel(const int* __restrict__ keys, const 
 #pragma unroll
         for (int q = 0; q < NQ; ++q) acc[q] += r[u][q];
       }
+    }
+    if (out.param) {
+      float fs[SEG_ILP][NQ], fp[SEG_ILP][NQ];
+#pragma unroll
+      for (int u = 0; u < SEG_ILP; ++u)
+        if (fkey[u] >= 0) {
+#pragma unroll
+          for (int q = 0; q < NQ; ++q)
+            if (col[q]) {
+              const size_t idx = (size_t)fkey[u] * w + lane + 32 * q;
+              fs[u][q] = out.sum[idx];
+              fp[u][q] = out.param[idx];
+            }
+        }
+#pragma unroll
+      for (int u = 0; u < SEG_ILP; ++u)
+        if (fkey[u] >= 0) {
+#pragma unroll
+          for (int q = 0; q < NQ; ++q)
+            if (col[q]) {  // (seg_store's arithmetic)
+              const size_t idx = (size_t)fkey[u] * w + lane + 32 * q;
+              const float g = facc[u][q];
+              const float s2 = fmaf(g, g, fs[u][q]);
+              out.sum[idx] = s2;
+              out.param[idx] = fp[u][q] - out.lr * g / (sqrtf(s2) + out.eps);
+            }
+        }
     }
   }
   flush(cnt);

@@ -2,6 +2,7 @@
 #include <cstdio>
 
 #include <cstring>
+#include <mutex>
 
 #include "nais_common.cuh"
 #include "nais_pairs_tile.cuh"
@@ -215,10 +216,7 @@ const char* nais_strerror(int code) {
 }
 
 static bool device_is_sm100() {
-  int dev = 0, major = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-  return major == 10;
+  return device_info().major == 10;
 }
 
 size_t nais_rows_adagrad_workspace_bytes(int64_t n, int32_t w) {
@@ -410,7 +408,7 @@ static int check_train_state(const NaisParams* p, const NaisAdagrad* tables, con
 // the launches of one optimizer step (arguments already checked)
 static int train_step_impl(const NaisParams* p, const NaisPairs* batch, const float* label, const float* row_weight,
                            const NaisAdagrad* tables, const NaisDenseAdagrad* dense, float* loss, float* score_out, void* workspace,
-                           size_t workspace_bytes, cudaStream_t st);
+                           size_t workspace_bytes, cudaStream_t st, int part = 0);
 
 int nais_pairs_train_step(const NaisParams* p, const NaisPairs* batch, const float* label, const float* row_weight,
                           const NaisAdagrad* tables, const NaisDenseAdagrad* dense, float* loss, float* score_out, void* workspace,
@@ -429,9 +427,11 @@ int nais_pairs_train_step(const NaisParams* p, const NaisPairs* batch, const flo
                          static_cast<cudaStream_t>(stream));
 }
 
+// part 0: the whole step.  part 1: only the id sorts of its backward (on the side streams, joined to `st`: nais_train_users runs
+// them for the NEXT user on its preparation stream); part 2: the step on lists sorted by a part-1 call (same arguments).
 static int train_step_impl(const NaisParams* p, const NaisPairs* batch, const float* label, const float* row_weight,
                            const NaisAdagrad* tables, const NaisDenseAdagrad* dense, float* loss, float* score_out, void* workspace,
-                           size_t workspace_bytes, cudaStream_t st) {
+                           size_t workspace_bytes, cudaStream_t st, int part) {
   int rc;
   const TrainStepLayout L = train_step_layout(*p, *batch);
   if (workspace_bytes < L.total) return NAIS_ERR_WORKSPACE;
@@ -448,8 +448,11 @@ static int train_step_impl(const NaisParams* p, const NaisPairs* batch, const fl
     g.dist_b = F(L.gdb);
   }
   // the id sorts of the backward depend on the batch only: forked onto side streams now, they run next to the forward
-  rc = launch_pairs_bwd(*p, *batch, nullptr, nullptr, nullptr, nullptr, g, tables, base + L.bwd, workspace_bytes - L.bwd, st, 1);
-  if (rc) return rc;
+  if (part != 2) {
+    rc = launch_pairs_bwd(*p, *batch, nullptr, nullptr, nullptr, nullptr, g, tables, base + L.bwd, workspace_bytes - L.bwd, st, 1);
+    if (rc) return rc;
+  }
+  if (part == 1) return launch_pairs_bwd(*p, *batch, nullptr, nullptr, nullptr, nullptr, g, tables, base + L.bwd, workspace_bytes - L.bwd, st, 4);
   // forward
   const bool tc_ok = pairs_tc_supported(*p, *batch) && device_is_sm100();
   if (p->pairs_precision == NAIS_PAIRS_TC && !tc_ok) return NAIS_ERR_SHAPE;
@@ -465,7 +468,8 @@ static int train_step_impl(const NaisParams* p, const NaisPairs* batch, const fl
   rc = launch_bce_dscore(F(L.score), label, row_weight, batch->B, F(L.dscore), loss, st);
   if (rc) return rc;
   // backward: MLP / distance-layer gradients to scratch, tables stepped in place
-  rc = launch_pairs_bwd(*p, *batch, F(L.parts), F(L.row_sum), mask, F(L.dscore), g, tables, base + L.bwd, workspace_bytes - L.bwd, st, 2);
+  rc = launch_pairs_bwd(*p, *batch, F(L.parts), F(L.row_sum), mask, F(L.dscore), g, tables, base + L.bwd, workspace_bytes - L.bwd, st,
+                        part == 2 ? 3 : 2);
   if (rc) return rc;
   const NaisBranch& br = p->branch[0];
   const int lanes = p->dist_mode == NAIS_DIST_LATLON ? 2 : 0, ldw = br.w_poi + br.w_reg + lanes;
@@ -528,11 +532,22 @@ UsersLayout users_layout(const NaisParams& p, int max_hist, int num_ng) {
   L.total = o;
   return L;
 }
+
+// The preparation stream of nais_train_users: one per device, created on first use (like the side streams of the backward).
+std::mutex g_prep_mu;
+cudaStream_t prep_stream() {
+  static cudaStream_t pool[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(g_prep_mu);
+  if (!pool[dev] && cudaStreamCreateWithFlags(&pool[dev], cudaStreamNonBlocking) != cudaSuccess) pool[dev] = nullptr;
+  return pool[dev];
+}
 }  // namespace
 
 size_t nais_train_users_workspace_bytes(const NaisParams* p, int32_t max_hist, int32_t num_ng) {
   if (check_params(p) || p->n_branch != 1 || max_hist < 1 || num_ng < 0) return 0;
-  return users_layout(*p, max_hist, num_ng).total;
+  return 2 * users_layout(*p, max_hist, num_ng).total;  // two users in flight: one being prepared, one being stepped
 }
 
 int nais_train_users(const NaisParams* p, const int64_t* host_indptr, int64_t n_rows, const int64_t* indices, const int64_t* entry_region,
@@ -560,27 +575,47 @@ int nais_train_users(const NaisParams* p, const int64_t* host_indptr, int64_t n_
   if (max_hist == 0) return (int)cudaMemsetAsync(losses, 0, (size_t)n_users * 4, static_cast<cudaStream_t>(stream));
   if ((int64_t)max_hist * (num_ng + 1) >= p->item_num) return NAIS_ERR_SHAPE;  // not enough unvisited POIs to draw from
   const UsersLayout L = users_layout(*p, max_hist, num_ng);
-  if (workspace_bytes < L.total) return NAIS_ERR_WORKSPACE;
+  if (workspace_bytes < 2 * L.total) return NAIS_ERR_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  char* base = reinterpret_cast<char*>(workspace);
-  auto I64 = [&](size_t off) { return reinterpret_cast<int64_t*>(base + off); };
-  for (int i = 0; i < n_users; ++i) {
+  // One user per optimizer step is a chain of small dependent launches (GPU latency, not throughput).  What depends on the batch
+  // only — the segment structure, the sampler and the id sorts of the backward — is enqueued one user AHEAD on a library-owned
+  // preparation stream into the other half of the workspace; the step itself (forward, BCE, backward on the sorted lists, Adagrad)
+  // stays on the caller's stream.  Same kernels on the same inputs in the same order per user: results do not change.
+  cudaStream_t ps = prep_stream();
+  if (!ps) return (int)cudaErrorUnknown;
+  cudaEvent_t prepared[2] = {nullptr, nullptr}, stepped[2] = {nullptr, nullptr}, begin = nullptr;
+  bool ev_ok = cudaEventCreateWithFlags(&begin, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; i < 2 && ev_ok; ++i)
+    ev_ok = cudaEventCreateWithFlags(&prepared[i], cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&stepped[i], cudaEventDisableTiming) == cudaSuccess;
+  auto release = [&]() {  // (destroying an event that is still pending is legal: its resources go when it completes)
+    if (begin) cudaEventDestroy(begin);
+    for (int i = 0; i < 2; ++i) {
+      if (prepared[i]) cudaEventDestroy(prepared[i]);
+      if (stepped[i]) cudaEventDestroy(stepped[i]);
+    }
+  };
+  if (!ev_ok) {
+    release();
+    return (int)cudaErrorUnknown;
+  }
+  auto bail = [&](int code) {  // order the caller's stream after everything the preparation stream still holds, then report
+    if (cudaEventRecord(begin, ps) == cudaSuccess) cudaStreamWaitEvent(st, begin, 0);
+    release();
+    return code;
+  };
+  struct UserBatch {
+    NaisPairs b;
+    const float* label;
+    char* step;
+  };
+  auto buffers = [&](int i, int slot, UserBatch& ub) {  // the batch of host_users[i] in workspace half `slot` (H > 0)
+    char* base = reinterpret_cast<char*>(workspace) + (size_t)slot * L.total;
+    auto I64 = [&](size_t off) { return reinterpret_cast<int64_t*>(base + off); };
     const int64_t u = host_users[i], a = host_indptr[u];
     const int H = (int)(host_indptr[u + 1] - a);
-    if (H == 0) {
-      cudaError_t e = cudaMemsetAsync(losses + i, 0, 4, st);
-      if (e != cudaSuccess) return (int)e;
-      continue;
-    }
     const int R = H * (num_ng + 1), rpt = host_rows_per_tile(H), n_tiles = (R + rpt - 1) / rpt;
-    single_segment_kernel<<<(n_tiles + 255) / 256, 256, 0, st>>>(H, R, rpt, n_tiles, I64(L.seg), I64(L.row), I64(L.cell),
-                                                                 reinterpret_cast<int32_t*>(base + L.tseg), I64(L.trow));
-    NAIS_COUNT_LAUNCH(1);
-    rc = launch_sample_batch(I64(L.seg), indices + a, 1, I64(L.row), num_ng, p->item_num, need_reg ? poi_region : nullptr,
-                             need_co ? poi_coords : nullptr, seed + (uint64_t)u, H, I64(L.tgt), reinterpret_cast<float*>(base + L.label),
-                             need_reg ? I64(L.treg) : nullptr, need_co ? reinterpret_cast<float*>(base + L.tco) : nullptr, st);
-    if (rc) return rc;
-    NaisPairs b;
+    NaisPairs& b = ub.b;
     memset(&b, 0, sizeof(b));
     b.hist = indices + a;
     b.tgt = I64(L.tgt);
@@ -597,11 +632,68 @@ int nais_train_users(const NaisParams* p, const int64_t* host_indptr, int64_t n_
     b.n_cells = (int64_t)R * H;
     b.hist_coords = need_co ? entry_coords + 2 * a : nullptr;
     b.tgt_coords = need_co ? reinterpret_cast<float*>(base + L.tco) : nullptr;
-    rc = train_step_impl(p, &b, reinterpret_cast<float*>(base + L.label), nullptr, tables, dense, losses + i, nullptr, base + L.step,
-                         workspace_bytes - L.step, st);
-    if (rc) return rc;
+    ub.label = reinterpret_cast<float*>(base + L.label);
+    ub.step = base + L.step;
+  };
+  auto prepare = [&](int i, int slot) -> int {  // on the preparation stream
+    UserBatch ub;
+    buffers(i, slot, ub);
+    const int64_t u = host_users[i], a = host_indptr[u];
+    const int H = (int)(host_indptr[u + 1] - a);
+    char* base = reinterpret_cast<char*>(workspace) + (size_t)slot * L.total;
+    single_segment_kernel<<<((int)ub.b.n_tiles + 255) / 256, 256, 0, ps>>>(
+        H, (int)ub.b.B, host_rows_per_tile(H), (int)ub.b.n_tiles, const_cast<int64_t*>(ub.b.seg_offsets), const_cast<int64_t*>(ub.b.row_offsets),
+        const_cast<int64_t*>(ub.b.seg_cell_offsets), const_cast<int32_t*>(ub.b.tile_seg), const_cast<int64_t*>(ub.b.tile_row0));
+    NAIS_COUNT_LAUNCH(1);
+    int r = launch_sample_batch(ub.b.seg_offsets, indices + a, 1, ub.b.row_offsets, num_ng, p->item_num, need_reg ? poi_region : nullptr,
+                                need_co ? poi_coords : nullptr, seed + (uint64_t)u, H, const_cast<int64_t*>(ub.b.tgt),
+                                reinterpret_cast<float*>(base + L.label), need_reg ? const_cast<int64_t*>(ub.b.treg) : nullptr,
+                                need_co ? const_cast<float*>(ub.b.tgt_coords) : nullptr, ps);
+    if (r) return r;
+    return train_step_impl(p, &ub.b, ub.label, nullptr, tables, dense, nullptr, nullptr, ub.step, L.total - L.step, ps, 1);
+  };
+  // users with a history, in order; the others only get a zero loss
+  int next = 0;
+  auto advance = [&](int from) {
+    while (from < n_users && host_indptr[host_users[from] + 1] == host_indptr[host_users[from]]) ++from;
+    return from;
+  };
+  for (int i = 0; i < n_users; ++i)
+    if (host_indptr[host_users[i] + 1] == host_indptr[host_users[i]]) {
+      cudaError_t e = cudaMemsetAsync(losses + i, 0, 4, st);
+      if (e != cudaSuccess) return bail((int)e);
+    }
+  // the preparation stream starts after the work already in the caller's stream (the parameters, the CSR arrays)
+  if (cudaEventRecord(begin, st) != cudaSuccess || cudaStreamWaitEvent(ps, begin, 0) != cudaSuccess) return bail((int)cudaErrorUnknown);
+  next = advance(0);
+  int slot = 0;
+  if (next < n_users) {
+    rc = prepare(next, slot);
+    if (rc) return bail(rc);
+    cudaEventRecord(prepared[slot], ps);
   }
-  return 0;
+  int done = 0;  // steps enqueued so far
+  while (next < n_users) {
+    const int cur = next, cur_slot = slot;
+    next = advance(cur + 1);
+    slot ^= 1;
+    if (next < n_users) {  // prepare the next user into the other half: free once the step before `cur` has finished with it
+      if (done >= 1) cudaStreamWaitEvent(ps, stepped[slot], 0);
+      rc = prepare(next, slot);
+      if (rc) return bail(rc);
+      cudaEventRecord(prepared[slot], ps);
+    }
+    UserBatch ub;
+    buffers(cur, cur_slot, ub);
+    cudaStreamWaitEvent(st, prepared[cur_slot], 0);
+    rc = train_step_impl(p, &ub.b, ub.label, nullptr, tables, dense, losses + cur, nullptr, ub.step, L.total - L.step, st, 2);
+    if (rc) return bail(rc);
+    cudaEventRecord(stepped[cur_slot], st);
+    ++done;
+  }
+  cudaError_t e = cudaGetLastError();
+  release();
+  return e == cudaSuccess ? 0 : (int)e;
 }
 
 static int check_fullrank(const NaisParams* p, const NaisCatalog* cat, const NaisUsers* users, int64_t poi_begin,

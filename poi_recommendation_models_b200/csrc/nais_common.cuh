@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "nais_b200.h"
 
 namespace nais {
@@ -10,6 +12,45 @@ namespace nais {
 // launch counter (diagnostic): every kernel launch of the library goes through NAIS_COUNT_LAUNCH
 extern unsigned long long g_launches;
 #define NAIS_COUNT_LAUNCH(n) (__atomic_fetch_add(&::nais::g_launches, (unsigned long long)(n), __ATOMIC_RELAXED))
+
+// Host-side caches, per device, of what the launch paths would otherwise ask the driver on every call.  The one-user-per-step
+// training loop (nais_train_users) enqueues ~14 launches per ~100 us and is bound by the host's API calls
+// (examples/diag_train_users_timing.py), so each launcher sets its kernel's shared-memory attributes once per device (again only
+// if a call needs more than any before it) and reads compute capability / SM count from a table.
+struct DeviceInfo {
+  int dev, major, sms;
+};
+inline DeviceInfo device_info() {
+  static std::atomic<int> cache[64];  // 0 = unknown, else (major << 16 | sms) + 1
+  DeviceInfo d{0, 0, 148};
+  if (cudaGetDevice(&d.dev) != cudaSuccess) return d;
+  const bool slot = d.dev >= 0 && d.dev < 64;
+  const int c = slot ? cache[d.dev].load(std::memory_order_relaxed) : 0;
+  if (c) {
+    d.major = (c - 1) >> 16;
+    d.sms = (c - 1) & 0xffff;
+    return d;
+  }
+  cudaDeviceGetAttribute(&d.major, cudaDevAttrComputeCapabilityMajor, d.dev);
+  cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, d.dev);
+  if (slot && d.major > 0 && d.sms > 0) cache[d.dev].store(((d.major << 16) | d.sms) + 1, std::memory_order_relaxed);
+  return d;
+}
+// One of these (static) per launch site: `smem` bytes of dynamic shared memory (and the max-shared carveout) for `kernel`.
+struct SmemAttrOnce {
+  std::atomic<int> set[64] = {};
+  template <typename K>
+  cudaError_t operator()(K kernel, size_t smem, bool carveout = false) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool slot = dev >= 0 && dev < 64;
+    if (slot && (int)smem <= set[dev].load(std::memory_order_relaxed) - 1) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess && carveout) e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess && slot) set[dev].store((int)smem + 1, std::memory_order_relaxed);
+    return e;
+  }
+};
 
 // Device address (current device) of the library's 4-byte bad-index word (nais_capi.cu); every launcher passes it to its kernel.
 int* bad_index_flag();

@@ -652,9 +652,8 @@ static int launch2(const Args& A, int64_t n_items, int sms, cudaStream_t stream)
   const size_t smem = 2 * (size_t)(D / 8) * PT * 16 + 2 * (size_t)(D / 8) * HIDC * 16 +
                       4096 + (4 * (size_t)HIDC + 2 * PMAXROWS * D + 2 * PT + 2 * PMAXROWS + 8 + 6 * PT + PT) * 4 +
                       (3 * (size_t)PT2 + PMAXROWS) * 8 + ((size_t)PT + PMAXROWS) * 8 + 16;
-  cudaError_t e = cudaFuncSetAttribute(pairs_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(pairs_fwd_tc2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  static SmemAttrOnce attr;
+  cudaError_t e = attr(pairs_fwd_tc2_kernel, smem, true);
   if (e != cudaSuccess) return (int)e;
   int per_sm = 3;
   const int by_smem = (int)((227 * 1024) / (smem + 1024));
@@ -702,11 +701,9 @@ bool pairs_tc_supported(const NaisParams& p, const NaisPairs& b) {
 
 int launch_pairs_fwd_tc(const NaisParams& p, const NaisPairs& b, float* score, float* row_sum, float* parts,
                         unsigned long long* act_mask, cudaStream_t stream) {
-  int dev = 0, major = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-  if (major != 10) return NAIS_ERR_ARCH;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const DeviceInfo di = device_info();
+  if (di.major != 10) return NAIS_ERR_ARCH;
+  const int sms = di.sms;
   ptc::Args A;
   A.p = p;
   A.b = b;

@@ -927,9 +927,8 @@ static int launch2(const BwdArgs& A, int grid, cudaStream_t stream) {
                           (4 * HID + 3 * BWD_MAXROWS * D + 4 * BWD_MAXROWS + 4 * HID + 64 + 4 * PT) * 4 +
                           (3 * (size_t)PT + PT2 + BWD_MAXROWS) * 8 + ((size_t)PT + BWD_MAXROWS) * 8 + 4 * BWD_MAXROWS * 4 + 16;
   static_assert(2 * (smem + 1024) <= 228 * 1024, "two CTAs per SM");
-  cudaError_t e = cudaFuncSetAttribute(pairs_bwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(pairs_bwd_tc2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  static SmemAttrOnce attr;
+  cudaError_t e = attr(pairs_bwd_tc2_kernel, smem, true);
   if (e != cudaSuccess) return (int)e;
   pairs_bwd_tc2_kernel<<<grid, PT2, smem, stream>>>(A);
   NAIS_COUNT_LAUNCH(1);
@@ -959,10 +958,7 @@ bool pairs_tc_bwd_supported(const NaisParams& p, const NaisPairs& b) {
   if (p.dist_mode == NAIS_DIST_KM || p.dropout_p > 0.f) return false;
   if (!rows_vec4(br, 4)) return false;
   (void)b;
-  int dev = 0, major = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-  return major == 10;
+  return device_info().major == 10;
 }
 
 // grid <= 2 CTAs per SM (256 TMEM columns each); every CTA owns at least one tile (the caller passes min(n_items, grid))

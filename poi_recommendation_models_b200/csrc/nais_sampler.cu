@@ -145,7 +145,8 @@ int launch_sample_batch(const int64_t* seg_offsets, const int64_t* hist, int n_s
   A.cap = cap;
   const size_t smem = (size_t)smp::WARPS * cap * sizeof(uint32_t);
   if (smem > 200 * 1024) return NAIS_ERR_SHAPE;  // histories beyond ~1200 items x 5: sample those users on the host
-  cudaError_t e = cudaFuncSetAttribute(smp::sample_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemAttrOnce attr;
+  cudaError_t e = attr(smp::sample_batch_kernel, smem);
   if (e != cudaSuccess) return (int)e;
   smp::sample_batch_kernel<<<(n_seg + smp::WARPS - 1) / smp::WARPS, smp::WARPS * 32, smem, stream>>>(A);
   NAIS_COUNT_LAUNCH(1);
