@@ -619,6 +619,7 @@ template <int NQ>
 __global__ void segment_reduce_pass1_kernel(const int* __restrict__ keys, const uint32_t* __restrict__ src, int64_t n, SegRows R, int w,
                                             int n_rows, SegOut out, int* __restrict__ part_key, int* __restrict__ part_start,
                                             float* __restrict__ part_rows) {
+  constexpr int ILP = NQ == 1 ? 2 * SEG_ILP : SEG_ILP;  // rows in flight per warp (narrow rows: one register per row and lane)
   const int64_t chunk = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t start = chunk * SEG_CHUNK;
@@ -661,13 +662,13 @@ __global__ void segment_reduce_pass1_kernel(const int* __restrict__ keys, const 
         if (col[q]) part_rows[(size_t)slot * w + lane + 32 * q] = acc[q];
     }
   };
-  // rows are fetched SEG_ILP entries at a time whatever the run structure is (unique keys = runs of one entry must not turn
+  // rows are fetched ILP entries at a time whatever the run structure is (unique keys = runs of one entry must not turn
   // into a chain of dependent load -> store round trips); the run bookkeeping is a bit test per entry
-  for (int j0 = 0; j0 < cnt; j0 += SEG_ILP) {
-    float r[SEG_ILP][NQ];
+  for (int j0 = 0; j0 < cnt; j0 += ILP) {
+    float r[ILP][NQ];
 #pragma unroll
-    for (int u = 0; u < SEG_ILP; ++u) {
-      const int j = j0 + u;  // (j0 is a multiple of SEG_ILP = 8: a batch never straddles the two key registers)
+    for (int u = 0; u < ILP; ++u) {
+      const int j = j0 + u;  // (j0 is a multiple of ILP, which divides 32: a batch never straddles the two key registers)
       const unsigned long long pj = __shfl_sync(0xffffffffu, (unsigned long long)(j0 < 32 ? r0p : r1p), j & 31);
       const float* row = reinterpret_cast<const float*>(pj);
 #pragma unroll
@@ -677,10 +678,10 @@ __global__ void segment_reduce_pass1_kernel(const int* __restrict__ keys, const 
     // chain of dependent load -> store round trips (ncu launch list of one-user steps: 85 us for ONE 64-entry chunk of unique
     // keys, the target list — the longest kernel of the step).  The runs that end inside this batch are collected (keys are
     // warp-uniform) and updated together after it: all their loads first, then the same arithmetic, then the stores.
-    int fkey[SEG_ILP];
-    float facc[SEG_ILP][NQ];
+    int fkey[ILP];
+    float facc[ILP][NQ];
 #pragma unroll
-    for (int u = 0; u < SEG_ILP; ++u) {
+    for (int u = 0; u < ILP; ++u) {
       const int j = j0 + u;
       fkey[u] = -1;
       if (j < cnt) {
@@ -702,9 +703,9 @@ __global__ void segment_reduce_pass1_kernel(const int* __restrict__ keys, const 
       }
     }
     if (out.param) {
-      float fs[SEG_ILP][NQ], fp[SEG_ILP][NQ];
+      float fs[ILP][NQ], fp[ILP][NQ];
 #pragma unroll
-      for (int u = 0; u < SEG_ILP; ++u)
+      for (int u = 0; u < ILP; ++u)
         if (fkey[u] >= 0) {
 #pragma unroll
           for (int q = 0; q < NQ; ++q)
@@ -715,7 +716,7 @@ __global__ void segment_reduce_pass1_kernel(const int* __restrict__ keys, const 
             }
         }
 #pragma unroll
-      for (int u = 0; u < SEG_ILP; ++u)
+      for (int u = 0; u < ILP; ++u)
         if (fkey[u] >= 0) {
 #pragma unroll
           for (int q = 0; q < NQ; ++q)
@@ -1009,13 +1010,14 @@ static int launch_bwd_tile(const BwdArgs& A, int D, int grid, cudaStream_t strea
 // a join (no wait of its own for the long list).  One branch in phases 1 - 4.
 int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score_parts, const float* row_sum,
                      const unsigned long long* act_mask, const float* dscore, const NaisGrads& g, const NaisAdagrad* opt, void* ws,
-                     size_t ws_bytes, cudaStream_t stream, int phase) {
+                     size_t ws_bytes, cudaStream_t stream, int phase, const DenseAdagradLaunch* dense) {
   if (pairs_n_cells(b) + b.B >= 0x7fffffffLL) return NAIS_ERR_SHAPE;
   if (phase && p.n_branch != 1) return NAIS_ERR_MODE;
   if (opt && p.n_branch != 1) return NAIS_ERR_MODE;  // two branches share tables: two sparse steps != one dense step
   const BwdLayout L = bwd_layout(p, b);
   if (ws_bytes < L.total) return NAIS_ERR_WORKSPACE;
   char* base = reinterpret_cast<char*>(ws);
+  int dense_rc = 0;
   std::lock_guard<std::mutex> side_lock(g_side_mu);
   SideStreams* side = side_streams();
   if (!side) return (int)cudaErrorUnknown;
@@ -1133,6 +1135,12 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
           A.ws_part, grid, L.stride, p.hid, D, lanes, g.w1[bi], g.b1[bi], g.w2[bi], bi == 0 ? g.dist_w : nullptr,
           bi == 0 ? g.dist_b : nullptr, p.dist_mode == NAIS_DIST_KM ? g.dist_embed : nullptr, D, bi > 0);
       NAIS_COUNT_LAUNCH(1);
+      // the one-call training step's dense Adagrad of these tensors needs nothing else: right behind them, next to the table reduces
+      if (dense) {
+        const int rd = launch_dense_adagrad(dense->param, dense->sum, dense->grad, dense->n, dense->lr, dense->eps,
+                                            stream_of(want[1] ? 1 : (want[2] ? 2 : 0)));
+        if (rd) dense_rc = rd;
+      }
     }
     if (phase == 2 && want[0]) cudaStreamWaitEvent(stream, side->sorted0, 0);  // the long list was sorted on a side stream
     if (want[0]) seg(0, 0, br.w_poi, p.item_num, dest(g.hist_poi[bi], br.hist_poi, opt ? opt->sum_hist_poi[bi] : nullptr, g.remap_hist_poi[bi]));
@@ -1146,6 +1154,7 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
       }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
+    if (dense_rc) return dense_rc;
   }
   return 0;
 }

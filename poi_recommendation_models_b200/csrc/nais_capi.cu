@@ -24,7 +24,7 @@ int choose_splits(int n_users, int64_t range);
 size_t pairs_bwd_workspace_bytes(const NaisParams& p, const NaisPairs& b);
 int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score_parts, const float* row_sum,
                      const unsigned long long* act_mask, const float* dscore, const NaisGrads& g, const NaisAdagrad* opt, void* ws,
-                     size_t ws_bytes, cudaStream_t stream, int phase = 0);
+                     size_t ws_bytes, cudaStream_t stream, int phase = 0, const DenseAdagradLaunch* dense = nullptr);
 bool pairs_tc_bwd_supported(const NaisParams& p, const NaisPairs& b);
 size_t rows_adagrad_workspace_bytes(int64_t n, int w);
 int launch_rows_adagrad(const int32_t* keys, const float* rows, int64_t n, int w, int n_rows, float* grad_out, float* param, float* sum,
@@ -468,17 +468,18 @@ static int train_step_impl(const NaisParams* p, const NaisPairs* batch, const fl
   rc = launch_bce_dscore(F(L.score), label, row_weight, batch->B, F(L.dscore), loss, st);
   if (rc) return rc;
   // backward: MLP / distance-layer gradients to scratch, tables stepped in place
-  rc = launch_pairs_bwd(*p, *batch, F(L.parts), F(L.row_sum), mask, F(L.dscore), g, tables, base + L.bwd, workspace_bytes - L.bwd, st,
-                        part == 2 ? 3 : 2);
-  if (rc) return rc;
+  // (the dense Adagrad of the MLP / distance-layer tensors rides behind the kernel that finishes their gradients, next to the
+  // table reduces: one launch less on the step's chain of dependent launches)
   const NaisBranch& br = p->branch[0];
   const int lanes = p->dist_mode == NAIS_DIST_LATLON ? 2 : 0, ldw = br.w_poi + br.w_reg + lanes;
-  float* const params[5] = {const_cast<float*>(br.w1), const_cast<float*>(br.b1), const_cast<float*>(br.w2),
-                            lanes ? const_cast<float*>(p->dist_w) : nullptr, lanes ? const_cast<float*>(p->dist_b) : nullptr};
-  float* const sums[5] = {dense->sum_w1, dense->sum_b1, dense->sum_w2, dense->sum_dist_w, dense->sum_dist_b};
-  const float* const grads[5] = {g.w1[0], g.b1[0], g.w2[0], g.dist_w, g.dist_b};
-  const int ns[5] = {p->hid * ldw, p->hid, p->hid, 4, 2};
-  return launch_dense_adagrad(params, sums, grads, ns, dense->lr, dense->eps, st);
+  const DenseAdagradLaunch da = {{const_cast<float*>(br.w1), const_cast<float*>(br.b1), const_cast<float*>(br.w2),
+                                  lanes ? const_cast<float*>(p->dist_w) : nullptr, lanes ? const_cast<float*>(p->dist_b) : nullptr},
+                                 {dense->sum_w1, dense->sum_b1, dense->sum_w2, dense->sum_dist_w, dense->sum_dist_b},
+                                 {g.w1[0], g.b1[0], g.w2[0], g.dist_w, g.dist_b},
+                                 {p->hid * ldw, p->hid, p->hid, 4, 2},
+                                 dense->lr, dense->eps};
+  return launch_pairs_bwd(*p, *batch, F(L.parts), F(L.row_sum), mask, F(L.dscore), g, tables, base + L.bwd, workspace_bytes - L.bwd, st,
+                          part == 2 ? 3 : 2, &da);
 }
 
 // ---- nais_train_users: the reference's one-user-per-step schedule, a list of users per call ---------------------------------------

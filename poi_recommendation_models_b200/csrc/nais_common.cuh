@@ -52,6 +52,16 @@ struct SmemAttrOnce {
   }
 };
 
+// The dense Adagrad step of the MLP / distance-layer tensors (nais_pairs_train_step), as launch_pairs_bwd enqueues it right behind
+// the kernel that finishes their gradients: w1, b1, w2, dist_w, dist_b (NULL param = absent).
+struct DenseAdagradLaunch {
+  float* param[5];
+  float* sum[5];
+  const float* grad[5];
+  int n[5];
+  float lr, eps;
+};
+
 // Device address (current device) of the library's 4-byte bad-index word (nais_capi.cu); every launcher passes it to its kernel.
 int* bad_index_flag();
 // An id as the kernels use it: inside [0, n) or replaced by 0 with the bad-index word set (include/nais_b200.h,
