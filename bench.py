@@ -859,6 +859,7 @@ def main():
     ap.add_argument("--cpu-users", type=int, default=4, help="users in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-blocks", action="store_true", help="headline workload only: skip the value_exact / c4 / train_c3 blocks")
+    ap.add_argument("--no-presort", action="store_true", help="train: keep the backward's id sorts inside the backward call (A/B of ops.PRESORT_IN_FORWARD)")
     args = ap.parse_args()
     cfg = WORKLOADS[args.config]
 
@@ -881,6 +882,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     peaks = load_peaks()
+    if args.no_presort:
+        from poi_recommendation_models_b200 import ops as _ops
+        _ops.PRESORT_IN_FORWARD = False
     if args.mode == "train":
         run_train(args, dev, lib, peaks, rank, world)
         if world > 1:
