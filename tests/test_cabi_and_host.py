@@ -317,3 +317,34 @@ def test_bench_reference_arm_prints_the_contract_line():
     env1 = dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run(cmd, check=True, capture_output=True, text=True, env=env1, timeout=300)
     assert r.stdout.strip() == ""
+
+
+def test_presort_pair_validates_before_launching():
+    """nais_pairs_forward_presort / nais_pairs_backward_presorted: one branch only, a NaisGrads skeleton and a workspace of at least
+    nais_pairs_backward_workspace_bytes are required — all reported before anything is enqueued (no GPU here)."""
+    import ctypes as C
+    lib = _lib.load()
+    p, b, g = _lib.NaisParams(), _lib.NaisPairs(), _lib.NaisGrads()
+    assert lib.nais_pairs_forward_presort(C.byref(p), C.byref(b), C.byref(g), None, None, None, None, None, 0, None) == -2  # no branch
+    p.n_branch, p.hid, p.item_num = 1, 64, 10
+    p.branch[0].w_poi = 64
+    for f in ("hist_poi", "tgt_poi", "w1", "b1", "w2"):
+        setattr(p.branch[0], f, 16)  # (never dereferenced: the argument checks run first)
+    b.H = 4
+    assert lib.nais_pairs_forward_presort(C.byref(p), C.byref(b), None, None, None, None, None, None, 0, None) == -1        # no NaisGrads
+    assert lib.nais_pairs_forward_presort(C.byref(p), C.byref(b), C.byref(g), None, None, None, None, None, 0, None) == 0    # B = 0: nothing to do
+    b.B, b.hist, b.tgt = 8, 16, 16
+    assert lib.nais_pairs_forward_presort(C.byref(p), C.byref(b), C.byref(g), None, None, None, None, 16, 1 << 30, None) == -1  # no score
+    assert lib.nais_pairs_forward_presort(C.byref(p), C.byref(b), C.byref(g), 16, None, None, None, None, 0, None) == -1     # no workspace
+    need = lib.nais_pairs_backward_workspace_bytes(C.byref(p), C.byref(b))
+    assert need > 0
+    assert lib.nais_pairs_forward_presort(C.byref(p), C.byref(b), C.byref(g), 16, None, None, None, 16, need - 1, None) == -4  # too small
+    assert lib.nais_pairs_backward_presorted(C.byref(p), C.byref(b), 16, 16, None, 16, C.byref(g), 16, need - 1, None) == -4
+    assert lib.nais_pairs_backward_presorted(C.byref(p), C.byref(b), 16, 16, None, 16, C.byref(g), 24, need, None) == -3     # misaligned
+    p2 = _lib.NaisParams.from_buffer_copy(p)
+    p2.n_branch = 2
+    p2.branch[1] = p.branch[0]
+    assert lib.nais_pairs_forward_presort(C.byref(p2), C.byref(b), C.byref(g), 16, None, None, None, 16, 1 << 30, None) == -5  # two branches
+    assert lib.nais_pairs_backward_presorted(C.byref(p2), C.byref(b), 16, 16, None, 16, C.byref(g), 16, 1 << 30, None) == -5
+    # the one-user-ahead pipeline of nais_train_users holds two users: its workspace is twice one user's
+    assert lib.nais_train_users_workspace_bytes(C.byref(p), 100, 4) % 2 == 0
