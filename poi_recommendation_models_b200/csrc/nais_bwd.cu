@@ -975,8 +975,8 @@ size_t pairs_bwd_workspace_bytes(const NaisParams& p, const NaisPairs& b) { retu
 // streams forked from / joined to the caller's stream with events.  One pool per device, created on first use; the mutex is
 // held while a call ENQUEUES its work (cudaStreamWaitEvent binds to the record that precedes it at call time).
 struct SideStreams {
-  cudaStream_t s[3] = {nullptr, nullptr, nullptr};  // [0], [1]: lists 1, 2; [2]: the long list's sort when it is forked ahead (phase 1)
-  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr}, sorted0 = nullptr;
+  cudaStream_t s[3] = {nullptr, nullptr, nullptr};  // [0], [1]: lists 1, 2; [2]: the long list's sort when it is forked ahead (phase 1), then param_reduce
+  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr}, sorted0 = nullptr, pjoin = nullptr;  // pjoin: param_reduce (+ dense Adagrad) on s[2]
   bool ok = false;
 };
 static std::mutex g_side_mu;
@@ -987,7 +987,8 @@ static SideStreams* side_streams() {  // (g_side_mu held)
   SideStreams& S = pool[dev];
   if (!S.ok) {
     bool good = cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming) == cudaSuccess &&
-                cudaEventCreateWithFlags(&S.sorted0, cudaEventDisableTiming) == cudaSuccess;
+                cudaEventCreateWithFlags(&S.sorted0, cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventCreateWithFlags(&S.pjoin, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 3 && good; ++i) good = cudaStreamCreateWithFlags(&S.s[i], cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < 2 && good; ++i) good = cudaEventCreateWithFlags(&S.join[i], cudaEventDisableTiming) == cudaSuccess;
     if (!good) return nullptr;
@@ -1132,21 +1133,25 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
                             reinterpret_cast<float*>(base + L.prows[t]), stream_of(t));
     };
     // fork again: the side streams (still ordered after their own sorts) wait for the tile kernel, reduce their list, and join
-    if (want[1] || want[2]) cudaEventRecord(side->fork, stream);
+    cudaEventRecord(side->fork, stream);
     for (int t = 1; t < 3; ++t)
       if (want[t]) cudaStreamWaitEvent(side->s[t - 1], side->fork, 0);
-    {  // the per-CTA parameter partials -> w1 / b1 / w2 / distance-layer gradients, next to the short list
+    // the per-CTA parameter partials -> w1 / b1 / w2 / distance-layer gradients (and the dense Adagrad step behind them) on the
+    // third side stream, idle since the long list's sort: next to the three lists' reduces instead of in front of one of them
+    cudaStream_t pstream = side->s[2];
+    cudaStreamWaitEvent(pstream, side->fork, 0);
+    {
       const int n = p.hid * (D + lanes) + 2 * p.hid + 7;
-      param_reduce_kernel<<<(n + 255) / 256, 256, 0, stream_of(want[1] ? 1 : (want[2] ? 2 : 0))>>>(
+      param_reduce_kernel<<<(n + 255) / 256, 256, 0, pstream>>>(
           A.ws_part, grid, L.stride, p.hid, D, lanes, g.w1[bi], g.b1[bi], g.w2[bi], bi == 0 ? g.dist_w : nullptr,
           bi == 0 ? g.dist_b : nullptr, p.dist_mode == NAIS_DIST_KM ? g.dist_embed : nullptr, D, bi > 0);
       NAIS_COUNT_LAUNCH(1);
       // the one-call training step's dense Adagrad of these tensors needs nothing else: right behind them, next to the table reduces
       if (dense) {
-        const int rd = launch_dense_adagrad(dense->param, dense->sum, dense->grad, dense->n, dense->lr, dense->eps,
-                                            stream_of(want[1] ? 1 : (want[2] ? 2 : 0)));
+        const int rd = launch_dense_adagrad(dense->param, dense->sum, dense->grad, dense->n, dense->lr, dense->eps, pstream);
         if (rd) dense_rc = rd;
       }
+      cudaEventRecord(side->pjoin, pstream);
     }
     if (phase == 2 && want[0]) cudaStreamWaitEvent(stream, side->sorted0, 0);  // the long list was sorted on a side stream
     if (want[0]) seg(0, 0, br.w_poi, p.item_num, dest(g.hist_poi[bi], br.hist_poi, opt ? opt->sum_hist_poi[bi] : nullptr, g.remap_hist_poi[bi]));
@@ -1158,6 +1163,7 @@ int launch_pairs_bwd(const NaisParams& p, const NaisPairs& b, const float* score
         cudaEventRecord(side->join[t - 1], side->s[t - 1]);
         cudaStreamWaitEvent(stream, side->join[t - 1], 0);
       }
+    cudaStreamWaitEvent(stream, side->pjoin, 0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     if (dense_rc) return dense_rc;
