@@ -220,9 +220,10 @@ NAIS_API size_t nais_pairs_backward_workspace_bytes(const NaisParams* p, const N
 /* Given dscore[B] = dL/dscore, write every parameter gradient.  score_parts / row_sum / act_mask are the forward's outputs
  * (act_mask: NULL unless the tcgen05 forward wrote it).
  * Streams: everything is ordered after the work already in `stream`, and `stream` is ordered after everything this call
- * enqueues, as for any other entry point — but the sort + reduce of the target-id and region-id lists run on two streams the
- * library creates once per device (forked from / joined to `stream` with events inside the call; legal under stream capture).
- * The call holds a process-wide mutex while it enqueues, so concurrent callers on one device share those two streams safely. */
+ * enqueues, as for any other entry point — but the sort + reduce of the target-id and region-id lists and the reduce of the
+ * per-CTA MLP-gradient partials run on three streams the library creates once per device (forked from / joined to `stream`
+ * with events inside the call; legal under stream capture).
+ * The call holds a process-wide mutex while it enqueues, so concurrent callers on one device share those streams safely. */
 NAIS_API int nais_pairs_backward(const NaisParams* p, const NaisPairs* batch, const float* score_parts, const float* row_sum,
                         const uint64_t* act_mask, const float* dscore, const NaisGrads* grads, void* workspace,
                         size_t workspace_bytes, nais_stream_t stream);
